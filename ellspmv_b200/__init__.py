@@ -1,0 +1,333 @@
+"""ellspmv_b200 -- Python binding (ctypes) of the B200 SpMV C-ABI library.
+
+The product is the C ABI in ``include/ellspmv_cuda.h`` (built in-tree as
+``ellspmv_b200/lib/libellspmv_cuda.so``) and the C host programs under
+``ellspmv_b200/host``.  This module only exposes that ABI to Python for the
+tests and ``bench.py``; it holds no compute of its own and has no CPU
+fallback: importing it without the built library raises, and every compute
+call fails with ``ENODEV`` on a machine without a CUDA device.
+
+Names follow the reference (jamtrott/ellspmv): ``ellgemv`` / ``csrgemv`` take
+the same arguments, in the same order, as the reference's kernels
+(ellspmv.c:1129-1137, csrspmv.c:1565-1575) and return ``0`` or an errno.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import errno
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libellspmv_cuda.so")
+
+# ---- constants (include/ellspmv_cuda.h) -----------------------------------
+KERNEL_AUTO, KERNEL_THREAD, KERNEL_WARP = 0, 1, 2
+FMA = 1 << 4
+L2_PERSIST_X = 1 << 5
+NARROW_INDEX = 1 << 6
+ROWS_PER_THREAD_SHIFT = 8
+VARIANT_SHIFT = 12
+ACCUMULATE, OVERWRITE, ITERATE = 0, 1, 2
+GEN_LAPLACE2D, GEN_STENCIL27, GEN_RANDOM = 1, 2, 3
+
+
+def rows_per_thread(r: int) -> int:
+    return (r & 0x7) << ROWS_PER_THREAD_SHIFT
+
+
+def variant(v: int) -> int:
+    return (v & 0xF) << VARIANT_SHIFT
+
+
+class EllspmvCudaError(RuntimeError):
+    def __init__(self, err: int, where: str, detail: str):
+        self.errno = err
+        name = errno.errorcode.get(err, str(err))
+        super().__init__(f"{where}: {name} ({os.strerror(err)}): {detail}")
+
+
+class Info(C.Structure):
+    _fields_ = [
+        ("num_rows", C.c_int64), ("num_columns", C.c_int64), ("rowsize", C.c_int64),
+        ("row_begin", C.c_int64), ("global_rows", C.c_int64),
+        ("idx_width_bits", C.c_int), ("dev_idx_bits", C.c_int), ("slice_rows", C.c_int),
+        ("rows_per_thread", C.c_int), ("kernel", C.c_int), ("fma", C.c_int), ("device", C.c_int),
+        ("device_bytes", C.c_int64), ("min_col", C.c_int64), ("max_col", C.c_int64),
+        ("launches", C.c_int64),
+    ]
+
+
+# every symbol include/ellspmv_cuda.h declares: (restype, argtypes)
+_P = C.c_void_p
+_I64 = C.c_int64
+_PROTOTYPES = {
+    "ellspmv_cuda_upload": (C.c_int, [C.POINTER(_P), C.c_int, _I64, _I64, _I64, _P, _P, C.c_int, C.c_uint]),
+    "ellspmv_cuda_upload_shard": (C.c_int, [C.POINTER(_P), C.c_int, _I64, _I64, _I64, _I64, _I64, _P, _P, C.c_int, C.c_uint]),
+    "ellspmv_cuda_generate": (C.c_int, [C.POINTER(_P), C.c_int, C.POINTER(_I64), C.POINTER(C.c_double), C.c_uint64, C.c_int, _I64, _I64, C.c_int, C.c_uint]),
+    "ellspmv_cuda_spmv": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P]),
+    "ellspmv_cuda_spmv_device": (C.c_int, [_P, _P, _P, C.c_int, _P]),
+    "ellspmv_cuda_spmv_push": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.POINTER(_P), C.POINTER(_I64), C.POINTER(_I64), _P]),
+    "ellspmv_cuda_download": (C.c_int, [_P, _P, _P]),
+    "ellspmv_cuda_get_info": (C.c_int, [_P, C.POINTER(Info)]),
+    "ellspmv_cuda_free": (None, [_P]),
+    "csrspmv_cuda_upload": (C.c_int, [C.POINTER(_P), C.c_int, _I64, _I64, _P, _P, _P, C.c_int, C.c_uint]),
+    "csrspmv_cuda_generate": (C.c_int, [C.POINTER(_P), C.c_int, C.POINTER(_I64), C.POINTER(C.c_double), C.c_uint64, C.c_int, C.c_int, C.c_uint]),
+    "csrspmv_cuda_spmv": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P]),
+    "csrspmv_cuda_spmv_device": (C.c_int, [_P, _P, _P, C.c_int, _P]),
+    "csrspmv_cuda_device_bytes": (_I64, [_P]),
+    "csrspmv_cuda_free": (None, [_P]),
+    "ellspmv_cuda_malloc_host": (C.c_int, [C.POINTER(_P), _I64]),
+    "ellspmv_cuda_free_host": (None, [_P]),
+    "ellspmv_cuda_malloc_device": (C.c_int, [C.POINTER(_P), _I64]),
+    "ellspmv_cuda_free_device": (None, [_P]),
+    "ellspmv_cuda_ipc_export": (C.c_int, [_P, _P]),
+    "ellspmv_cuda_ipc_open": (C.c_int, [_P, C.POINTER(_P)]),
+    "ellspmv_cuda_ipc_close": (C.c_int, [_P]),
+    "ellspmv_cuda_device_count": (C.c_int, [C.POINTER(C.c_int)]),
+    "ellspmv_cuda_strerror": (C.c_char_p, [C.c_int]),
+    "ellspmv_cuda_last_error": (C.c_char_p, []),
+    "ellspmv_cuda_version": (C.c_int, []),
+}
+
+_lib: Optional[C.CDLL] = None
+
+
+def load_library() -> C.CDLL:
+    """Load the C-ABI library.  Fails loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `make -C ellspmv_b200/csrc` "
+            "(or python -c 'import __graft_entry__ as g; g.build()'). There is no fallback path.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in _PROTOTYPES.items():
+        fn = getattr(lib, name)   # AttributeError if the header and the library drift apart
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def _check(err: int, where: str) -> None:
+    if err != 0:
+        detail = load_library().ellspmv_cuda_last_error().decode("utf-8", "replace")
+        raise EllspmvCudaError(err, where, detail)
+
+
+def _ptr(obj) -> Optional[int]:
+    """Raw address of a numpy array, a torch tensor (host or device) or an int."""
+    if obj is None:
+        return None
+    if isinstance(obj, int):
+        return obj
+    if isinstance(obj, np.ndarray):
+        if not obj.flags["C_CONTIGUOUS"]:
+            raise ValueError("array must be C-contiguous")
+        return obj.ctypes.data
+    if hasattr(obj, "data_ptr"):
+        if not obj.is_contiguous():
+            raise ValueError("tensor must be contiguous")
+        return obj.data_ptr()
+    raise TypeError(f"cannot take the address of {type(obj)!r}")
+
+
+def _idx_bits(colidx) -> int:
+    if isinstance(colidx, np.ndarray):
+        if colidx.dtype == np.int32:
+            return 32
+        if colidx.dtype == np.int64:
+            return 64
+    elif hasattr(colidx, "dtype"):
+        s = str(colidx.dtype)
+        if s.endswith("int32"):
+            return 32
+        if s.endswith("int64"):
+            return 64
+    raise TypeError("column indices must be int32 or int64")
+
+
+def device_count() -> int:
+    n = C.c_int(0)
+    err = load_library().ellspmv_cuda_device_count(C.byref(n))
+    return n.value if err == 0 else 0
+
+
+class EllMatrix:
+    """A (shard of a) matrix resident on one GPU in sliced-ELL layout."""
+
+    def __init__(self, handle: int):
+        self._h = C.c_void_p(handle)
+
+    # -- construction -------------------------------------------------------
+    @classmethod
+    def upload(cls, num_rows: int, num_columns: int, rowsize: int, colidx, a, flags: int = 0,
+               *, global_rows: Optional[int] = None, row_begin: int = 0, device: int = -1) -> "EllMatrix":
+        lib = load_library()
+        h = C.c_void_p()
+        bits = _idx_bits(colidx) if colidx is not None else 32
+        if global_rows is None and row_begin == 0 and device < 0:
+            err = lib.ellspmv_cuda_upload(C.byref(h), bits, num_rows, num_columns, rowsize,
+                                          _ptr(colidx), _ptr(a), 1, flags)
+        else:
+            g = num_rows if global_rows is None else global_rows
+            err = lib.ellspmv_cuda_upload_shard(C.byref(h), bits, g, num_columns, rowsize, row_begin,
+                                                row_begin + num_rows, _ptr(colidx), _ptr(a), device, flags)
+        _check(err, "ellspmv_cuda_upload")
+        return cls(h.value)
+
+    @classmethod
+    def generate(cls, kind: int, dims: Sequence[int], vals: Sequence[float] = (0.0, 0.0), seed: int = 42,
+                 idx_bits: int = 32, row_begin: int = 0, row_end: int = -1, device: int = -1,
+                 flags: int = 0) -> "EllMatrix":
+        lib = load_library()
+        h = C.c_void_p()
+        d = (C.c_int64 * 3)(*(list(dims) + [0, 0, 0])[:3])
+        v = (C.c_double * 2)(*vals)
+        err = lib.ellspmv_cuda_generate(C.byref(h), kind, d, v, seed, idx_bits, row_begin, row_end, device, flags)
+        _check(err, "ellspmv_cuda_generate")
+        return cls(h.value)
+
+    # -- compute --------------------------------------------------------------
+    def spmv(self, y: np.ndarray, x: np.ndarray, repeat: int = 1, mode: int = ACCUMULATE) -> np.ndarray:
+        """HOST vectors in/out (y is updated in place); returns per-launch seconds."""
+        secs = np.zeros(max(repeat, 0), dtype=np.float64)
+        err = load_library().ellspmv_cuda_spmv(self._h, _ptr(y), _ptr(x), repeat, mode, _ptr(secs))
+        _check(err, "ellspmv_cuda_spmv")
+        return secs
+
+    def spmv_device(self, y_dev, x_dev, mode: int = ACCUMULATE, stream: int = 0) -> None:
+        err = load_library().ellspmv_cuda_spmv_device(self._h, _ptr(y_dev), _ptr(x_dev), mode, stream or None)
+        _check(err, "ellspmv_cuda_spmv_device")
+
+    def spmv_push(self, y_dev, x_dev, mode: int, peer_x: Sequence[int], row_lo: Sequence[int],
+                  row_hi: Sequence[int], stream: int = 0) -> None:
+        n = len(peer_x)
+        px = (C.c_void_p * max(n, 1))(*peer_x)
+        lo = (C.c_int64 * max(n, 1))(*row_lo)
+        hi = (C.c_int64 * max(n, 1))(*row_hi)
+        err = load_library().ellspmv_cuda_spmv_push(self._h, _ptr(y_dev), _ptr(x_dev), mode, n, px, lo, hi,
+                                                    stream or None)
+        _check(err, "ellspmv_cuda_spmv_push")
+
+    # -- inspection -------------------------------------------------------------
+    def info(self) -> Info:
+        out = Info()
+        _check(load_library().ellspmv_cuda_get_info(self._h, C.byref(out)), "ellspmv_cuda_get_info")
+        return out
+
+    def download(self):
+        """Row-major (colidx, a) host arrays, in the caller's index width."""
+        i = self.info()
+        dt = np.int32 if i.idx_width_bits == 32 else np.int64
+        colidx = np.empty(i.num_rows * i.rowsize, dtype=dt)
+        a = np.empty(i.num_rows * i.rowsize, dtype=np.float64)
+        _check(load_library().ellspmv_cuda_download(self._h, _ptr(colidx), _ptr(a)), "ellspmv_cuda_download")
+        return colidx, a
+
+    def free(self) -> None:
+        if self._h:
+            load_library().ellspmv_cuda_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.free()
+
+
+class CsrMatrix:
+    """A CSR matrix resident on one GPU (comparison path)."""
+
+    def __init__(self, handle: int):
+        self._h = C.c_void_p(handle)
+
+    @classmethod
+    def upload(cls, num_rows: int, num_columns: int, rowptr, colidx, a, flags: int = 0) -> "CsrMatrix":
+        h = C.c_void_p()
+        bits = _idx_bits(colidx) if colidx is not None else 32
+        err = load_library().csrspmv_cuda_upload(C.byref(h), bits, num_rows, num_columns, _ptr(rowptr),
+                                                 _ptr(colidx), _ptr(a), 1, flags)
+        _check(err, "csrspmv_cuda_upload")
+        return cls(h.value)
+
+    @classmethod
+    def generate(cls, kind: int, dims: Sequence[int], seed: int = 42, idx_bits: int = 32, device: int = -1,
+                 flags: int = 0) -> "CsrMatrix":
+        h = C.c_void_p()
+        d = (C.c_int64 * 3)(*(list(dims) + [0, 0, 0])[:3])
+        v = (C.c_double * 2)(0.0, 0.0)
+        err = load_library().csrspmv_cuda_generate(C.byref(h), kind, d, v, seed, idx_bits, device, flags)
+        _check(err, "csrspmv_cuda_generate")
+        return cls(h.value)
+
+    def spmv(self, y: np.ndarray, x: np.ndarray, repeat: int = 1, mode: int = ACCUMULATE) -> np.ndarray:
+        secs = np.zeros(max(repeat, 0), dtype=np.float64)
+        err = load_library().csrspmv_cuda_spmv(self._h, _ptr(y), _ptr(x), repeat, mode, _ptr(secs))
+        _check(err, "csrspmv_cuda_spmv")
+        return secs
+
+    def spmv_device(self, y_dev, x_dev, mode: int = ACCUMULATE, stream: int = 0) -> None:
+        err = load_library().csrspmv_cuda_spmv_device(self._h, _ptr(y_dev), _ptr(x_dev), mode, stream or None)
+        _check(err, "csrspmv_cuda_spmv_device")
+
+    def device_bytes(self) -> int:
+        return load_library().csrspmv_cuda_device_bytes(self._h)
+
+    def free(self) -> None:
+        if self._h:
+            load_library().csrspmv_cuda_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+# ---- reference-shaped operators -------------------------------------------------
+def ellgemv(num_rows, y, num_columns, x, ellsize, rowsize, colidx, a, flags: int = 0) -> int:
+    """Drop-in for the reference's ``ellgemv`` (ellspmv.c:1129-1153): y += A*x.
+
+    Same argument order and meaning; returns 0 or an errno value.  One-shot
+    convenience (upload, one launch, free) -- the host programs keep the
+    handle across the repeat loop instead.
+    """
+    if ellsize != num_rows * rowsize:
+        return errno.EINVAL
+    try:
+        A = EllMatrix.upload(num_rows, num_columns, rowsize, colidx, a, flags)
+        try:
+            A.spmv(y, x, 1, ACCUMULATE)
+        finally:
+            A.free()
+    except EllspmvCudaError as e:
+        return e.errno
+    return 0
+
+
+def csrgemv(num_rows, y, num_columns, x, csrsize, rowsizemin, rowsizemax, rowptr, colidx, a,
+            flags: int = 0) -> int:
+    """Drop-in for the reference's ``csrgemv`` (csrspmv.c:1565-1595): y += A*x."""
+    del csrsize, rowsizemin, rowsizemax
+    try:
+        A = CsrMatrix.upload(num_rows, num_columns, rowptr, colidx, a, flags)
+        try:
+            A.spmv(y, x, 1, ACCUMULATE)
+        finally:
+            A.free()
+    except EllspmvCudaError as e:
+        return e.errno
+    return 0

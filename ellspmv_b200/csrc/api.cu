@@ -1,0 +1,752 @@
+// api.cu -- the C ABI of include/ellspmv_cuda.h.
+//
+// Host-side glue only: device memory, streams, events and the copies around
+// the kernels in ell_kernels.cu / csr_kernels.cu / layout.cu.  The hot loop
+// it stands in for is the reference's repeat loop around ellgemv
+// (ellspmv.c:1821-1876) and csrgemv (csrspmv.c:2834-2901).
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "common.cuh"
+
+namespace ellspmv {
+
+static thread_local char g_last_error[512] = "";
+
+void set_last_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_to_errno(cudaError_t e)
+{
+    switch (e) {
+    case cudaSuccess: return 0;
+    case cudaErrorMemoryAllocation: return ENOMEM;
+    case cudaErrorInvalidValue:
+    case cudaErrorInvalidDevicePointer:
+    case cudaErrorInvalidDevice: return EINVAL;
+    case cudaErrorNoDevice:
+    case cudaErrorInsufficientDriver:
+    case cudaErrorInitializationError: return ENODEV;
+    case cudaErrorNotSupported: return ENOTSUP;
+    default: return EIO;
+    }
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; }
+        ok = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+}  // namespace ellspmv
+
+using namespace ellspmv;
+
+struct ellspmv_cuda_matrix {
+    int device = 0;
+    EllLayout lay = {};
+    int host_idx_bits = 32, dev_idx_bits = 32;
+    int64_t num_columns = 0, row_begin = 0, global_rows = 0;
+    unsigned flags = 0;
+    EllLaunchCfg cfg = {};
+    double *vals = nullptr;
+    void *cols = nullptr;
+    long long *d_minmax = nullptr;
+    int64_t min_col = 0, max_col = -1;
+    cudaStream_t stream = nullptr;
+    double *d_x = nullptr, *d_y = nullptr;   // vectors of the host-facing spmv
+    int64_t vec_len = 0;
+    std::vector<cudaEvent_t> events;
+    int64_t device_bytes = 0;
+    int64_t launches = 0;
+};
+
+struct csrspmv_cuda_matrix {
+    int device = 0;
+    int idx_bits = 32;
+    int64_t num_rows = 0, num_columns = 0, csrsize = 0;
+    unsigned flags = 0;
+    int kernel = ELLSPMV_CUDA_KERNEL_THREAD;
+    bool fma = false;
+    int64_t *rowptr = nullptr;
+    void *cols = nullptr;
+    double *vals = nullptr;
+    cudaStream_t stream = nullptr;
+    double *d_x = nullptr, *d_y = nullptr;
+    std::vector<cudaEvent_t> events;
+    int64_t device_bytes = 0;
+};
+
+namespace {
+
+int check_device(int *device)
+{
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0) {
+        cudaGetLastError();
+        ELL_FAIL(ENODEV, "no CUDA device available (%s); this library has no CPU fallback",
+                 e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+    if (*device < 0) ELL_CK(cudaGetDevice(device));
+    if (*device >= count) ELL_FAIL(EINVAL, "device %d out of range (have %d)", *device, count);
+    return 0;
+}
+
+// Decide layout + kernel from shape and flags.
+int configure(ellspmv_cuda_matrix *A, unsigned flags)
+{
+    A->flags = flags;
+    int R = (flags & ELLSPMV_CUDA_ROWS_PER_THREAD_MASK) >> ELLSPMV_CUDA_ROWS_PER_THREAD_SHIFT;
+    if (R == 0) R = 4;   // 256-bit value loads + 128-bit (idx32) / 256-bit (idx64) index loads
+    if (R != 1 && R != 2 && R != 4) ELL_FAIL(EINVAL, "rows per thread must be 1, 2 or 4 (got %d)", R);
+    int kernel = flags & ELLSPMV_CUDA_KERNEL_MASK;
+    if (kernel == ELLSPMV_CUDA_KERNEL_AUTO) kernel = ELLSPMV_CUDA_KERNEL_THREAD;
+    if (kernel != ELLSPMV_CUDA_KERNEL_THREAD && kernel != ELLSPMV_CUDA_KERNEL_WARP)
+        ELL_FAIL(EINVAL, "unknown kernel selector %d", kernel);
+    A->dev_idx_bits = A->host_idx_bits;
+    if (A->host_idx_bits == 64 && (flags & ELLSPMV_CUDA_NARROW_INDEX) && A->num_columns < (1LL << 31))
+        A->dev_idx_bits = 32;
+    A->lay.slice_rows = kBlockThreads * R;
+    A->lay.num_slices = (A->lay.num_rows + A->lay.slice_rows - 1) / A->lay.slice_rows;
+    cudaDeviceProp prop;
+    ELL_CK(cudaGetDeviceProperties(&prop, A->device));
+    A->cfg.idx_bits = A->dev_idx_bits;
+    A->cfg.rows_per_thread = R;
+    A->cfg.kernel = kernel;
+    A->cfg.variant = (flags & ELLSPMV_CUDA_VARIANT_MASK) >> ELLSPMV_CUDA_VARIANT_SHIFT;
+    A->cfg.fma = (flags & ELLSPMV_CUDA_FMA) != 0;
+    A->cfg.num_sms = prop.multiProcessorCount;
+    A->cfg.x_bytes = A->num_columns * 8;
+    A->cfg.persist_x = false;
+    if (flags & ELLSPMV_CUDA_L2_PERSIST_X) {
+        size_t want = (size_t)A->cfg.x_bytes;
+        size_t maxp = (size_t)prop.persistingL2CacheMaxSize;
+        size_t maxw = (size_t)prop.accessPolicyMaxWindowSize;
+        if (maxp > 0 && want <= maxw) {
+            ELL_CK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want < maxp ? want : maxp));
+            A->cfg.persist_x = true;
+        }
+    }
+    return 0;
+}
+
+int alloc_matrix(ellspmv_cuda_matrix *A)
+{
+    const int64_t n = A->lay.entries();
+    const size_t vb = (size_t)(n > 0 ? n : 1) * 8;
+    const size_t cb = (size_t)(n > 0 ? n : 1) * (A->dev_idx_bits / 8);
+    ELL_CK(cudaMalloc(&A->vals, vb));
+    ELL_CK(cudaMalloc(&A->cols, cb));
+    ELL_CK(cudaMalloc(&A->d_minmax, 2 * sizeof(long long)));
+    ELL_CK(cudaStreamCreateWithFlags(&A->stream, cudaStreamNonBlocking));
+    A->device_bytes = (int64_t)(vb + cb);
+    // the tail of the last slice must hold harmless entries (col 0, 0.0)
+    ELL_CK(cudaMemsetAsync(A->vals, 0, vb, A->stream));
+    ELL_CK(cudaMemsetAsync(A->cols, 0, cb, A->stream));
+    ELL_CK(init_minmax(A->d_minmax, A->stream));
+    return 0;
+}
+
+int finish_minmax(ellspmv_cuda_matrix *A)
+{
+    long long mm[2];
+    ELL_CK(cudaMemcpyAsync(mm, A->d_minmax, sizeof(mm), cudaMemcpyDeviceToHost, A->stream));
+    ELL_CK(cudaStreamSynchronize(A->stream));
+    A->min_col = mm[0];
+    A->max_col = mm[1];
+    if (A->max_col >= A->num_columns || (A->max_col >= 0 && A->min_col < 0))
+        ELL_FAIL(EINVAL, "column index out of range: [%lld, %lld] with %lld columns",
+                 mm[0], mm[1], (long long)A->num_columns);
+    return 0;
+}
+
+int ensure_vectors(ellspmv_cuda_matrix *A)
+{
+    int64_t need = A->lay.num_rows > A->num_columns ? A->lay.num_rows : A->num_columns;
+    if (need < 1) need = 1;
+    if (A->d_x && A->vec_len >= need) return 0;
+    if (A->d_x) cudaFree(A->d_x);
+    if (A->d_y) cudaFree(A->d_y);
+    A->d_x = A->d_y = nullptr;
+    ELL_CK(cudaMalloc(&A->d_x, (size_t)need * 8));
+    ELL_CK(cudaMalloc(&A->d_y, (size_t)need * 8));
+    A->vec_len = need;
+    A->device_bytes += 2 * need * 8;
+    return 0;
+}
+
+int ensure_events(std::vector<cudaEvent_t> &ev, size_t n)
+{
+    while (ev.size() < n) {
+        cudaEvent_t e;
+        ELL_CK(cudaEventCreate(&e));
+        ev.push_back(e);
+    }
+    return 0;
+}
+
+int launch(ellspmv_cuda_matrix *A, double *y_dev, const double *x_dev, int beta,
+           const PushTargets *push, cudaStream_t stream)
+{
+    EllSpmvArgs args = {};
+    args.vals = A->vals;
+    args.cols = A->cols;
+    args.x = x_dev;
+    args.y = y_dev;
+    args.num_rows = A->lay.num_rows;
+    args.row_begin = A->row_begin;
+    args.rowsize = A->lay.rowsize;
+    args.beta = beta;
+    if (push) args.push = *push; else args.push.num_peers = 0;
+    if (A->lay.rowsize == 0) {
+        // K = 0: y += 0 for beta=1, y = 0 for beta=0
+        if (!beta && A->lay.num_rows > 0)
+            ELL_CK(cudaMemsetAsync(y_dev, 0, (size_t)A->lay.num_rows * 8, stream));
+        return 0;
+    }
+    ELL_CK(launch_ell_spmv(A->cfg, args, A->lay.num_slices, stream));
+    A->launches++;
+    return 0;
+}
+
+int new_handle(ellspmv_cuda_matrix **out, int idx_width_bits, int64_t global_rows,
+               int64_t num_columns, int64_t rowsize, int64_t row_begin, int64_t row_end,
+               int device, unsigned flags)
+{
+    if (!out) ELL_FAIL(EINVAL, "out is NULL");
+    *out = nullptr;
+    if (idx_width_bits != 32 && idx_width_bits != 64)
+        ELL_FAIL(EINVAL, "idx_width_bits must be 32 or 64 (got %d)", idx_width_bits);
+    if (global_rows < 0 || num_columns < 0 || rowsize < 0 || rowsize > 0x7fffffff)
+        ELL_FAIL(EINVAL, "negative or oversized dimension");
+    if (row_begin < 0 || row_end < row_begin || row_end > global_rows)
+        ELL_FAIL(EINVAL, "row range [%lld, %lld) outside [0, %lld)", (long long)row_begin,
+                 (long long)row_end, (long long)global_rows);
+    if (idx_width_bits == 32 && (num_columns > 0x7fffffffLL || global_rows > 0x7fffffffLL))
+        ELL_FAIL(EINVAL, "dimension does not fit a 32-bit idx_t");
+    if (rowsize > 0 && num_columns == 0 && row_end > row_begin)
+        ELL_FAIL(EINVAL, "rowsize > 0 with zero columns");
+    int err = check_device(&device);
+    if (err) return err;
+    ellspmv_cuda_matrix *A = new (std::nothrow) ellspmv_cuda_matrix();
+    if (!A) ELL_FAIL(ENOMEM, "out of host memory");
+    A->device = device;
+    A->host_idx_bits = idx_width_bits;
+    A->num_columns = num_columns;
+    A->row_begin = row_begin;
+    A->global_rows = global_rows;
+    A->lay.num_rows = row_end - row_begin;
+    A->lay.rowsize = (int)rowsize;
+    *out = A;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ellspmv_cuda_version(void) { return ELLSPMV_CUDA_VERSION; }
+
+const char *ellspmv_cuda_last_error(void) { return g_last_error; }
+
+const char *ellspmv_cuda_strerror(int err)
+{
+    return err == 0 ? "success" : strerror(err);
+}
+
+int ellspmv_cuda_device_count(int *count)
+{
+    if (!count) ELL_FAIL(EINVAL, "count is NULL");
+    *count = 0;
+    cudaError_t e = cudaGetDeviceCount(count);
+    if (e != cudaSuccess) { cudaGetLastError(); *count = 0; ELL_FAIL(ENODEV, "%s", cudaGetErrorString(e)); }
+    return 0;
+}
+
+void ellspmv_cuda_free(ellspmv_cuda_matrix *A)
+{
+    if (!A) return;
+    DeviceGuard g(A->device);
+    if (A->stream) cudaStreamSynchronize(A->stream);
+    for (cudaEvent_t e : A->events) cudaEventDestroy(e);
+    if (A->vals) cudaFree(A->vals);
+    if (A->cols) cudaFree(A->cols);
+    if (A->d_minmax) cudaFree(A->d_minmax);
+    if (A->d_x) cudaFree(A->d_x);
+    if (A->d_y) cudaFree(A->d_y);
+    if (A->stream) cudaStreamDestroy(A->stream);
+    delete A;
+}
+
+int ellspmv_cuda_upload_shard(
+    ellspmv_cuda_matrix **out, int idx_width_bits,
+    int64_t global_rows, int64_t num_columns, int64_t rowsize,
+    int64_t row_begin, int64_t row_end,
+    const void *colidx, const double *a, int device, unsigned flags)
+{
+    int err = new_handle(out, idx_width_bits, global_rows, num_columns, rowsize, row_begin, row_end,
+                         device, flags);
+    if (err) return err;
+    ellspmv_cuda_matrix *A = *out;
+    DeviceGuard g(A->device);
+    auto fail = [&](int e) { ellspmv_cuda_free(A); *out = nullptr; return e; };
+    if ((err = configure(A, flags))) return fail(err);
+    if ((err = alloc_matrix(A))) return fail(err);
+    const int64_t rows = A->lay.num_rows, K = A->lay.rowsize;
+    if (rows > 0 && K > 0) {
+        if (!colidx || !a) { set_last_error("colidx or a is NULL"); return fail(EINVAL); }
+        // stream the row-major arrays through two staging buffers
+        const int ib = idx_width_bits / 8;
+        int64_t chunk_rows = (64LL << 20) / (K * (8 + ib));
+        if (chunk_rows < 1) chunk_rows = 1;
+        if (chunk_rows > rows) chunk_rows = rows;
+        double *sv[2] = {nullptr, nullptr};
+        void *sc[2] = {nullptr, nullptr};
+        cudaEvent_t done[2] = {nullptr, nullptr};
+        cudaError_t ce = cudaSuccess;
+        for (int b = 0; b < 2 && ce == cudaSuccess; b++) {
+            ce = cudaMalloc(&sv[b], (size_t)chunk_rows * K * 8);
+            if (ce == cudaSuccess) ce = cudaMalloc(&sc[b], (size_t)chunk_rows * K * ib);
+            if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&done[b], cudaEventDisableTiming);
+        }
+        int b = 0;
+        for (int64_t r0 = 0; r0 < rows && ce == cudaSuccess; r0 += chunk_rows, b ^= 1) {
+            const int64_t n = (rows - r0 < chunk_rows) ? rows - r0 : chunk_rows;
+            ce = cudaEventSynchronize(done[b]);   // staging buffer b free again
+            if (ce == cudaSuccess) ce = cudaMemcpyAsync(sv[b], a + r0 * K, (size_t)n * K * 8, cudaMemcpyDefault, A->stream);
+            if (ce == cudaSuccess) ce = cudaMemcpyAsync(sc[b], (const char *)colidx + r0 * K * ib, (size_t)n * K * ib, cudaMemcpyDefault, A->stream);
+            if (ce == cudaSuccess) ce = relayout_chunk(idx_width_bits, A->dev_idx_bits, sc[b], sv[b], A->cols, A->vals, A->lay, r0, n, A->d_minmax, A->stream);
+            if (ce == cudaSuccess) ce = cudaEventRecord(done[b], A->stream);
+        }
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(A->stream);
+        for (int i = 0; i < 2; i++) {
+            if (sv[i]) cudaFree(sv[i]);
+            if (sc[i]) cudaFree(sc[i]);
+            if (done[i]) cudaEventDestroy(done[i]);
+        }
+        if (ce != cudaSuccess) {
+            set_last_error("upload: %s", cudaGetErrorString(ce));
+            return fail(cuda_to_errno(ce));
+        }
+        if ((err = finish_minmax(A))) return fail(err);
+    } else {
+        cudaError_t ce = cudaStreamSynchronize(A->stream);
+        if (ce != cudaSuccess) { set_last_error("upload: %s", cudaGetErrorString(ce)); return fail(cuda_to_errno(ce)); }
+    }
+    return 0;
+}
+
+int ellspmv_cuda_upload(
+    ellspmv_cuda_matrix **out, int idx_width_bits,
+    int64_t num_rows, int64_t num_columns, int64_t rowsize,
+    const void *colidx, const double *a, int num_gpus, unsigned flags)
+{
+    if (num_gpus != 1)
+        ELL_FAIL(ENOTSUP, "num_gpus=%d: one handle drives one GPU; shard with "
+                          "ellspmv_cuda_upload_shard (one handle per GPU)", num_gpus);
+    return ellspmv_cuda_upload_shard(out, idx_width_bits, num_rows, num_columns, rowsize,
+                                     0, num_rows, colidx, a, -1, flags);
+}
+
+int ellspmv_cuda_generate(
+    ellspmv_cuda_matrix **out, int kind, const int64_t dims[3],
+    const double vals[2], uint64_t seed, int idx_width_bits,
+    int64_t row_begin, int64_t row_end, int device, unsigned flags)
+{
+    if (!dims) ELL_FAIL(EINVAL, "dims is NULL");
+    int64_t rows, cols, K;
+    double v[2] = {0.0, 0.0};
+    if (vals) { v[0] = vals[0]; v[1] = vals[1]; }
+    switch (kind) {
+    case ELLSPMV_CUDA_GEN_LAPLACE2D:
+        if (dims[0] < 1 || dims[1] < 1) ELL_FAIL(EINVAL, "laplace2d needs nx, ny >= 1");
+        rows = cols = dims[0] * dims[1]; K = 5; break;
+    case ELLSPMV_CUDA_GEN_STENCIL27:
+        if (dims[0] < 1 || dims[1] < 1 || dims[2] < 1) ELL_FAIL(EINVAL, "stencil27 needs nx, ny, nz >= 1");
+        rows = cols = dims[0] * dims[1] * dims[2]; K = 27; break;
+    case ELLSPMV_CUDA_GEN_RANDOM:
+        if (dims[0] < 0 || dims[1] < 1 || dims[2] < 0) ELL_FAIL(EINVAL, "random needs rows >= 0, cols >= 1, K >= 0");
+        rows = dims[0]; cols = dims[1]; K = dims[2]; break;
+    default:
+        ELL_FAIL(EINVAL, "unknown generator kind %d", kind);
+    }
+    if (row_end < 0) row_end = rows;
+    int err = new_handle(out, idx_width_bits, rows, cols, K, row_begin, row_end, device, flags);
+    if (err) return err;
+    ellspmv_cuda_matrix *A = *out;
+    DeviceGuard g(A->device);
+    auto fail = [&](int e) { ellspmv_cuda_free(A); *out = nullptr; return e; };
+    if ((err = configure(A, flags))) return fail(err);
+    if ((err = alloc_matrix(A))) return fail(err);
+    if (A->lay.num_rows > 0 && K > 0) {
+        cudaError_t ce = generate_sliced(kind, dims, v, seed, A->dev_idx_bits, A->cols, A->vals,
+                                         A->lay, row_begin, A->d_minmax, A->stream);
+        if (ce != cudaSuccess) { set_last_error("generate: %s", cudaGetErrorString(ce)); return fail(cuda_to_errno(ce)); }
+        if ((err = finish_minmax(A))) return fail(err);
+    } else {
+        cudaStreamSynchronize(A->stream);
+    }
+    return 0;
+}
+
+int ellspmv_cuda_download(const ellspmv_cuda_matrix *A, void *colidx, double *a)
+{
+    if (!A) ELL_FAIL(EINVAL, "matrix is NULL");
+    const int64_t rows = A->lay.num_rows, K = A->lay.rowsize;
+    if (rows == 0 || K == 0) return 0;
+    if (!colidx || !a) ELL_FAIL(EINVAL, "colidx or a is NULL");
+    DeviceGuard g(A->device);
+    const int ib = A->host_idx_bits / 8;
+    int64_t chunk_rows = (64LL << 20) / (K * (8 + ib));
+    if (chunk_rows < 1) chunk_rows = 1;
+    if (chunk_rows > rows) chunk_rows = rows;
+    double *sv = nullptr; void *sc = nullptr;
+    ELL_CK(cudaMalloc(&sv, (size_t)chunk_rows * K * 8));
+    cudaError_t ce = cudaMalloc(&sc, (size_t)chunk_rows * K * ib);
+    for (int64_t r0 = 0; r0 < rows && ce == cudaSuccess; r0 += chunk_rows) {
+        const int64_t n = (rows - r0 < chunk_rows) ? rows - r0 : chunk_rows;
+        ce = unlayout_chunk(A->dev_idx_bits, A->host_idx_bits, A->cols, A->vals, sc, sv, A->lay, r0, n, A->stream);
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(a + r0 * K, sv, (size_t)n * K * 8, cudaMemcpyDefault, A->stream);
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync((char *)colidx + r0 * K * ib, sc, (size_t)n * K * ib, cudaMemcpyDefault, A->stream);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(A->stream);
+    }
+    cudaFree(sv);
+    if (sc) cudaFree(sc);
+    if (ce != cudaSuccess) ELL_FAIL(cuda_to_errno(ce), "download: %s", cudaGetErrorString(ce));
+    return 0;
+}
+
+int ellspmv_cuda_get_info(const ellspmv_cuda_matrix *A, ellspmv_cuda_info *info)
+{
+    if (!A || !info) ELL_FAIL(EINVAL, "NULL argument");
+    memset(info, 0, sizeof(*info));
+    info->num_rows = A->lay.num_rows;
+    info->num_columns = A->num_columns;
+    info->rowsize = A->lay.rowsize;
+    info->row_begin = A->row_begin;
+    info->global_rows = A->global_rows;
+    info->idx_width_bits = A->host_idx_bits;
+    info->dev_idx_bits = A->dev_idx_bits;
+    info->slice_rows = A->lay.slice_rows;
+    info->rows_per_thread = A->cfg.rows_per_thread;
+    info->kernel = A->cfg.kernel;
+    info->fma = A->cfg.fma ? 1 : 0;
+    info->device = A->device;
+    info->device_bytes = A->device_bytes;
+    info->min_col = A->min_col;
+    info->max_col = A->max_col;
+    info->launches = A->launches;
+    return 0;
+}
+
+int ellspmv_cuda_spmv_device(
+    ellspmv_cuda_matrix *A, double *y_dev, const double *x_dev, int mode, void *stream)
+{
+    if (!A) ELL_FAIL(EINVAL, "matrix is NULL");
+    if (mode != ELLSPMV_CUDA_ACCUMULATE && mode != ELLSPMV_CUDA_OVERWRITE)
+        ELL_FAIL(EINVAL, "spmv_device: mode must be ACCUMULATE or OVERWRITE");
+    if (A->lay.num_rows > 0 && (!y_dev || (!x_dev && A->lay.rowsize > 0)))
+        ELL_FAIL(EINVAL, "NULL device vector");
+    DeviceGuard g(A->device);
+    return launch(A, y_dev, x_dev, mode == ELLSPMV_CUDA_ACCUMULATE ? 1 : 0, nullptr, (cudaStream_t)stream);
+}
+
+int ellspmv_cuda_spmv_push(
+    ellspmv_cuda_matrix *A, double *y_dev, const double *x_dev, int mode,
+    int num_peers, double *const *peer_x,
+    const int64_t *peer_row_lo, const int64_t *peer_row_hi, void *stream)
+{
+    if (!A) ELL_FAIL(EINVAL, "matrix is NULL");
+    if (mode != ELLSPMV_CUDA_ACCUMULATE && mode != ELLSPMV_CUDA_OVERWRITE)
+        ELL_FAIL(EINVAL, "spmv_push: mode must be ACCUMULATE or OVERWRITE");
+    if (num_peers < 0 || num_peers > kMaxPeers) ELL_FAIL(EINVAL, "num_peers must be 0..%d", kMaxPeers);
+    if (num_peers > 0 && (!peer_x || !peer_row_lo || !peer_row_hi)) ELL_FAIL(EINVAL, "NULL peer arrays");
+    if (A->lay.num_rows > 0 && (!y_dev || (!x_dev && A->lay.rowsize > 0)))
+        ELL_FAIL(EINVAL, "NULL device vector");
+    PushTargets pt = {};
+    pt.num_peers = num_peers;
+    for (int p = 0; p < num_peers; p++) {
+        if (!peer_x[p]) ELL_FAIL(EINVAL, "peer_x[%d] is NULL", p);
+        pt.x[p] = peer_x[p];
+        pt.row_lo[p] = peer_row_lo[p];
+        pt.row_hi[p] = peer_row_hi[p];
+    }
+    DeviceGuard g(A->device);
+    return launch(A, y_dev, x_dev, mode == ELLSPMV_CUDA_ACCUMULATE ? 1 : 0, &pt, (cudaStream_t)stream);
+}
+
+int ellspmv_cuda_spmv(
+    ellspmv_cuda_matrix *A, double *y, const double *x,
+    int repeat, int mode, double *seconds)
+{
+    if (!A) ELL_FAIL(EINVAL, "matrix is NULL");
+    if (repeat < 0) ELL_FAIL(EINVAL, "repeat < 0");
+    if (mode != ELLSPMV_CUDA_ACCUMULATE && mode != ELLSPMV_CUDA_OVERWRITE && mode != ELLSPMV_CUDA_ITERATE)
+        ELL_FAIL(EINVAL, "unknown mode %d", mode);
+    const int64_t rows = A->lay.num_rows, ncols = A->num_columns;
+    if ((rows > 0 && !y) || (ncols > 0 && !x)) ELL_FAIL(EINVAL, "NULL host vector");
+    if (mode == ELLSPMV_CUDA_ITERATE && !(A->row_begin == 0 && rows == A->global_rows && rows == ncols))
+        ELL_FAIL(EINVAL, "ITERATE needs a square, unsharded matrix");
+    if (repeat == 0) return 0;
+    DeviceGuard g(A->device);
+    int err = ensure_vectors(A);
+    if (err) return err;
+    if ((err = ensure_events(A->events, (size_t)repeat + 1))) return err;
+    cudaStream_t s = A->stream;
+    if (ncols > 0) ELL_CK(cudaMemcpyAsync(A->d_x, x, (size_t)ncols * 8, cudaMemcpyDefault, s));
+    if (mode == ELLSPMV_CUDA_ACCUMULATE && rows > 0)
+        ELL_CK(cudaMemcpyAsync(A->d_y, y, (size_t)rows * 8, cudaMemcpyDefault, s));
+    double *cur = A->d_x, *nxt = A->d_y;
+    ELL_CK(cudaEventRecord(A->events[0], s));
+    for (int r = 0; r < repeat; r++) {
+        if (mode == ELLSPMV_CUDA_ITERATE) {
+            if ((err = launch(A, nxt, cur, 0, nullptr, s))) return err;
+            double *t = cur; cur = nxt; nxt = t;
+        } else {
+            const int beta = mode == ELLSPMV_CUDA_ACCUMULATE ? 1 : 0;
+            if ((err = launch(A, A->d_y, A->d_x, beta, nullptr, s))) return err;
+        }
+        ELL_CK(cudaEventRecord(A->events[(size_t)r + 1], s));
+    }
+    const double *result = (mode == ELLSPMV_CUDA_ITERATE) ? cur : A->d_y;
+    if (rows > 0) ELL_CK(cudaMemcpyAsync(y, result, (size_t)rows * 8, cudaMemcpyDefault, s));
+    ELL_CK(cudaStreamSynchronize(s));
+    if (seconds) {
+        for (int r = 0; r < repeat; r++) {
+            float ms = 0.f;
+            ELL_CK(cudaEventElapsedTime(&ms, A->events[(size_t)r], A->events[(size_t)r + 1]));
+            seconds[r] = (double)ms * 1e-3;
+        }
+    }
+    return 0;
+}
+
+/* ---- CSR ---------------------------------------------------------------- */
+
+void csrspmv_cuda_free(csrspmv_cuda_matrix *A)
+{
+    if (!A) return;
+    DeviceGuard g(A->device);
+    if (A->stream) cudaStreamSynchronize(A->stream);
+    for (cudaEvent_t e : A->events) cudaEventDestroy(e);
+    if (A->rowptr) cudaFree(A->rowptr);
+    if (A->cols) cudaFree(A->cols);
+    if (A->vals) cudaFree(A->vals);
+    if (A->d_x) cudaFree(A->d_x);
+    if (A->d_y) cudaFree(A->d_y);
+    if (A->stream) cudaStreamDestroy(A->stream);
+    delete A;
+}
+
+static int csr_new(csrspmv_cuda_matrix **out, int idx_width_bits, int64_t num_rows,
+                   int64_t num_columns, int64_t csrsize, int device, unsigned flags)
+{
+    if (!out) ELL_FAIL(EINVAL, "out is NULL");
+    *out = nullptr;
+    if (idx_width_bits != 32 && idx_width_bits != 64) ELL_FAIL(EINVAL, "idx_width_bits must be 32 or 64");
+    if (num_rows < 0 || num_columns < 0 || csrsize < 0) ELL_FAIL(EINVAL, "negative dimension");
+    int err = check_device(&device);
+    if (err) return err;
+    csrspmv_cuda_matrix *A = new (std::nothrow) csrspmv_cuda_matrix();
+    if (!A) ELL_FAIL(ENOMEM, "out of host memory");
+    A->device = device;
+    A->idx_bits = idx_width_bits;
+    A->num_rows = num_rows;
+    A->num_columns = num_columns;
+    A->csrsize = csrsize;
+    A->flags = flags;
+    A->fma = (flags & ELLSPMV_CUDA_FMA) != 0;
+    int kernel = flags & ELLSPMV_CUDA_KERNEL_MASK;
+    A->kernel = kernel == ELLSPMV_CUDA_KERNEL_WARP ? ELLSPMV_CUDA_KERNEL_WARP : ELLSPMV_CUDA_KERNEL_THREAD;
+    *out = A;
+    DeviceGuard g(device);
+    auto fail = [&](cudaError_t ce) {
+        set_last_error("csr alloc: %s", cudaGetErrorString(ce));
+        csrspmv_cuda_free(A); *out = nullptr; return cuda_to_errno(ce);
+    };
+    cudaError_t ce;
+    const size_t nz = (size_t)(csrsize > 0 ? csrsize : 1);
+    if ((ce = cudaMalloc(&A->rowptr, (size_t)(num_rows + 1) * 8)) != cudaSuccess) return fail(ce);
+    if ((ce = cudaMalloc(&A->cols, nz * (idx_width_bits / 8))) != cudaSuccess) return fail(ce);
+    if ((ce = cudaMalloc(&A->vals, nz * 8)) != cudaSuccess) return fail(ce);
+    if ((ce = cudaMalloc(&A->d_x, (size_t)(num_columns > 0 ? num_columns : 1) * 8)) != cudaSuccess) return fail(ce);
+    if ((ce = cudaMalloc(&A->d_y, (size_t)(num_rows > 0 ? num_rows : 1) * 8)) != cudaSuccess) return fail(ce);
+    if ((ce = cudaStreamCreateWithFlags(&A->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(ce);
+    A->device_bytes = (num_rows + 1) * 8 + (int64_t)nz * (8 + idx_width_bits / 8) + (num_columns + num_rows) * 8;
+    return 0;
+}
+
+int csrspmv_cuda_upload(
+    csrspmv_cuda_matrix **out, int idx_width_bits,
+    int64_t num_rows, int64_t num_columns,
+    const int64_t *rowptr, const void *colidx, const double *a,
+    int num_gpus, unsigned flags)
+{
+    if (num_gpus != 1) ELL_FAIL(ENOTSUP, "csrspmv_cuda_upload: num_gpus must be 1");
+    if (!rowptr) ELL_FAIL(EINVAL, "rowptr is NULL");
+    int dev = -1;
+    int err = check_device(&dev);
+    if (err) return err;
+    // rowptr may live on the host or the device: fetch the last entry portably
+    int64_t csrsize = 0;
+    ELL_CK(cudaMemcpy(&csrsize, rowptr + num_rows, 8, cudaMemcpyDefault));
+    if (csrsize > 0 && (!colidx || !a)) ELL_FAIL(EINVAL, "colidx or a is NULL");
+    err = csr_new(out, idx_width_bits, num_rows, num_columns, csrsize, dev, flags);
+    if (err) return err;
+    csrspmv_cuda_matrix *A = *out;
+    DeviceGuard g(A->device);
+    cudaError_t ce = cudaMemcpyAsync(A->rowptr, rowptr, (size_t)(num_rows + 1) * 8, cudaMemcpyDefault, A->stream);
+    if (ce == cudaSuccess && csrsize > 0) ce = cudaMemcpyAsync(A->cols, colidx, (size_t)csrsize * (idx_width_bits / 8), cudaMemcpyDefault, A->stream);
+    if (ce == cudaSuccess && csrsize > 0) ce = cudaMemcpyAsync(A->vals, a, (size_t)csrsize * 8, cudaMemcpyDefault, A->stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(A->stream);
+    if (ce != cudaSuccess) {
+        set_last_error("csr upload: %s", cudaGetErrorString(ce));
+        csrspmv_cuda_free(A); *out = nullptr;
+        return cuda_to_errno(ce);
+    }
+    return 0;
+}
+
+int csrspmv_cuda_generate(
+    csrspmv_cuda_matrix **out, int kind, const int64_t dims[3],
+    const double vals[2], uint64_t seed, int idx_width_bits,
+    int device, unsigned flags)
+{
+    (void)vals;
+    if (!dims) ELL_FAIL(EINVAL, "dims is NULL");
+    if (kind != ELLSPMV_CUDA_GEN_RANDOM) ELL_FAIL(ENOTSUP, "csrspmv_cuda_generate: only the random kind");
+    if (dims[0] < 0 || dims[1] < 1 || dims[2] < 0) ELL_FAIL(EINVAL, "random needs rows >= 0, cols >= 1, K >= 0");
+    int err = csr_new(out, idx_width_bits, dims[0], dims[1], dims[0] * dims[2], device, flags);
+    if (err) return err;
+    csrspmv_cuda_matrix *A = *out;
+    DeviceGuard g(A->device);
+    cudaError_t ce = generate_csr_random(dims, seed, idx_width_bits, A->rowptr, A->cols, A->vals, A->stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(A->stream);
+    if (ce != cudaSuccess) {
+        set_last_error("csr generate: %s", cudaGetErrorString(ce));
+        csrspmv_cuda_free(A); *out = nullptr;
+        return cuda_to_errno(ce);
+    }
+    return 0;
+}
+
+int csrspmv_cuda_spmv_device(
+    csrspmv_cuda_matrix *A, double *y_dev, const double *x_dev, int mode, void *stream)
+{
+    if (!A) ELL_FAIL(EINVAL, "matrix is NULL");
+    if (mode != ELLSPMV_CUDA_ACCUMULATE && mode != ELLSPMV_CUDA_OVERWRITE)
+        ELL_FAIL(EINVAL, "mode must be ACCUMULATE or OVERWRITE");
+    if (A->num_rows > 0 && (!y_dev || !x_dev)) ELL_FAIL(EINVAL, "NULL device vector");
+    DeviceGuard g(A->device);
+    CsrSpmvArgs args = {A->rowptr, A->cols, A->vals, x_dev, y_dev, A->num_rows,
+                        mode == ELLSPMV_CUDA_ACCUMULATE ? 1 : 0};
+    ELL_CK(launch_csr_spmv(A->idx_bits, A->fma, A->kernel, args, (cudaStream_t)stream));
+    return 0;
+}
+
+int csrspmv_cuda_spmv(
+    csrspmv_cuda_matrix *A, double *y, const double *x,
+    int repeat, int mode, double *seconds)
+{
+    if (!A) ELL_FAIL(EINVAL, "matrix is NULL");
+    if (repeat < 0) ELL_FAIL(EINVAL, "repeat < 0");
+    if (mode != ELLSPMV_CUDA_ACCUMULATE && mode != ELLSPMV_CUDA_OVERWRITE)
+        ELL_FAIL(EINVAL, "mode must be ACCUMULATE or OVERWRITE");
+    if ((A->num_rows > 0 && !y) || (A->num_columns > 0 && !x)) ELL_FAIL(EINVAL, "NULL host vector");
+    if (repeat == 0) return 0;
+    DeviceGuard g(A->device);
+    int err = ensure_events(A->events, (size_t)repeat + 1);
+    if (err) return err;
+    cudaStream_t s = A->stream;
+    if (A->num_columns > 0) ELL_CK(cudaMemcpyAsync(A->d_x, x, (size_t)A->num_columns * 8, cudaMemcpyDefault, s));
+    if (mode == ELLSPMV_CUDA_ACCUMULATE && A->num_rows > 0)
+        ELL_CK(cudaMemcpyAsync(A->d_y, y, (size_t)A->num_rows * 8, cudaMemcpyDefault, s));
+    ELL_CK(cudaEventRecord(A->events[0], s));
+    for (int r = 0; r < repeat; r++) {
+        CsrSpmvArgs args = {A->rowptr, A->cols, A->vals, A->d_x, A->d_y, A->num_rows,
+                            mode == ELLSPMV_CUDA_ACCUMULATE ? 1 : 0};
+        ELL_CK(launch_csr_spmv(A->idx_bits, A->fma, A->kernel, args, s));
+        ELL_CK(cudaEventRecord(A->events[(size_t)r + 1], s));
+    }
+    if (A->num_rows > 0) ELL_CK(cudaMemcpyAsync(y, A->d_y, (size_t)A->num_rows * 8, cudaMemcpyDefault, s));
+    ELL_CK(cudaStreamSynchronize(s));
+    if (seconds) {
+        for (int r = 0; r < repeat; r++) {
+            float ms = 0.f;
+            ELL_CK(cudaEventElapsedTime(&ms, A->events[(size_t)r], A->events[(size_t)r + 1]));
+            seconds[r] = (double)ms * 1e-3;
+        }
+    }
+    return 0;
+}
+
+int64_t csrspmv_cuda_device_bytes(const csrspmv_cuda_matrix *A) { return A ? A->device_bytes : 0; }
+
+/* ---- utilities ------------------------------------------------------------ */
+
+int ellspmv_cuda_malloc_host(void **ptr, int64_t bytes)
+{
+    if (!ptr || bytes < 0) ELL_FAIL(EINVAL, "bad argument");
+    *ptr = nullptr;
+    int dev = -1;
+    int err = check_device(&dev);
+    if (err) return err;
+    ELL_CK(cudaMallocHost(ptr, (size_t)(bytes > 0 ? bytes : 1)));
+    return 0;
+}
+
+void ellspmv_cuda_free_host(void *ptr) { if (ptr) cudaFreeHost(ptr); }
+
+int ellspmv_cuda_malloc_device(void **ptr, int64_t bytes)
+{
+    if (!ptr || bytes < 0) ELL_FAIL(EINVAL, "bad argument");
+    *ptr = nullptr;
+    int dev = -1;
+    int err = check_device(&dev);
+    if (err) return err;
+    ELL_CK(cudaMalloc(ptr, (size_t)(bytes > 0 ? bytes : 1)));
+    return 0;
+}
+
+void ellspmv_cuda_free_device(void *ptr) { if (ptr) cudaFree(ptr); }
+
+int ellspmv_cuda_ipc_export(const void *dev_ptr, unsigned char handle[64])
+{
+    if (!dev_ptr || !handle) ELL_FAIL(EINVAL, "NULL argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    ELL_CK(cudaIpcGetMemHandle(&h, const_cast<void *>(dev_ptr)));
+    memcpy(handle, &h, 64);
+    return 0;
+}
+
+int ellspmv_cuda_ipc_open(const unsigned char handle[64], void **dev_ptr)
+{
+    if (!dev_ptr || !handle) ELL_FAIL(EINVAL, "NULL argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    ELL_CK(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+
+int ellspmv_cuda_ipc_close(void *dev_ptr)
+{
+    if (!dev_ptr) return 0;
+    ELL_CK(cudaIpcCloseMemHandle(dev_ptr));
+    return 0;
+}
+
+}  // extern "C"

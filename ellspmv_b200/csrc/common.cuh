@@ -1,0 +1,130 @@
+// common.cuh -- shared declarations of the sm_100a SpMV library.
+//
+// Internal header (C++/CUDA).  The public boundary is the C ABI in
+// include/ellspmv_cuda.h; nothing here is exported.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <errno.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/ellspmv_cuda.h"
+
+namespace ellspmv {
+
+// ---- error plumbing -----------------------------------------------------
+// The C ABI returns errno-style ints like the reference's kernels do
+// (ellspmv.c:1197 returns EINVAL); the text of the underlying CUDA error is
+// kept per host thread for ellspmv_cuda_last_error().
+void set_last_error(const char *fmt, ...);
+int  cuda_to_errno(cudaError_t e);
+
+#define ELL_CK(call)                                                        \
+    do {                                                                    \
+        cudaError_t e__ = (call);                                           \
+        if (e__ != cudaSuccess) {                                           \
+            ::ellspmv::set_last_error("%s:%d: %s -> %s", __FILE__, __LINE__, \
+                                      #call, cudaGetErrorString(e__));      \
+            return ::ellspmv::cuda_to_errno(e__);                           \
+        }                                                                   \
+    } while (0)
+
+#define ELL_FAIL(err, ...)                       \
+    do {                                         \
+        ::ellspmv::set_last_error(__VA_ARGS__);  \
+        return (err);                            \
+    } while (0)
+
+constexpr int kBlockThreads = 128;  // threads per CTA of the thread-per-row kernels
+constexpr int kMaxPeers = 8;
+
+// ---- sliced-ELL device layout -------------------------------------------
+// Rows are grouped into slices of S = kBlockThreads * R rows (R = rows per
+// thread).  Inside a slice the K slots are stored slot-major: element
+// (row r, slot l) of slice s lives at  s*S*K + l*S + (r mod S).  A CTA owns
+// one slice; for a fixed slot its threads read one contiguous run of S
+// values (S*8 bytes) and S indices, so every load is a fully coalesced
+// 128/256-bit vector load, and a slice is one contiguous S*K*(8+idx) byte
+// region of HBM.  Rows past num_rows in the last slice hold (col 0, 0.0).
+struct EllLayout {
+    int64_t num_rows;     // rows in this shard
+    int64_t num_slices;   // ceil(num_rows / slice_rows)
+    int     rowsize;      // K
+    int     slice_rows;   // S
+    __host__ __device__ int64_t padded_rows() const { return num_slices * (int64_t)slice_rows; }
+    __host__ __device__ int64_t entries() const { return padded_rows() * rowsize; }
+    __host__ __device__ int64_t offset(int64_t row, int slot) const {
+        int64_t s = row / slice_rows;
+        int64_t r = row - s * slice_rows;
+        return (s * rowsize + slot) * slice_rows + r;
+    }
+};
+
+// ---- fused exchange targets ---------------------------------------------
+struct PushTargets {
+    int      num_peers;
+    double  *x[kMaxPeers];       // peer vectors, indexed by GLOBAL row
+    int64_t  row_lo[kMaxPeers];  // global row range the peer needs
+    int64_t  row_hi[kMaxPeers];
+};
+
+struct EllSpmvArgs {
+    const double *vals;     // sliced layout
+    const void   *cols;     // sliced layout, int32 or int64
+    const double *x;        // num_columns
+    double       *y;        // shard rows (in/out)
+    int64_t       num_rows; // shard rows
+    int64_t       row_begin;// global index of shard row 0 (for push)
+    int           rowsize;
+    int           beta;     // 1: y += A x, 0: y = A x
+    PushTargets   push;
+};
+
+struct EllLaunchCfg {
+    int  idx_bits;         // 32 / 64 (device storage)
+    int  rows_per_thread;  // 1, 2, 4
+    int  kernel;           // ELLSPMV_CUDA_KERNEL_THREAD / _WARP
+    int  variant;          // 0 direct loads, 1 bulk-async staged
+    bool fma;
+    bool persist_x;        // attach an L2 access-policy window over x
+    int64_t x_bytes;
+    int  num_sms;
+};
+
+cudaError_t launch_ell_spmv(const EllLaunchCfg &cfg, const EllSpmvArgs &args,
+                            int64_t num_slices, cudaStream_t stream);
+
+// ---- CSR ---------------------------------------------------------------
+struct CsrSpmvArgs {
+    const int64_t *rowptr;
+    const void    *cols;
+    const double  *vals;
+    const double  *x;
+    double        *y;
+    int64_t        num_rows;
+    int            beta;
+};
+cudaError_t launch_csr_spmv(int idx_bits, bool fma, int kernel, const CsrSpmvArgs &args,
+                            cudaStream_t stream);
+
+// ---- layout / generators (layout.cu) -------------------------------------
+// row-major chunk (rows [row0, row0+rows) of the shard) -> sliced layout
+cudaError_t relayout_chunk(int src_idx_bits, int dst_idx_bits, const void *src_cols,
+                           const double *src_vals, void *dst_cols, double *dst_vals,
+                           const EllLayout &lay, int64_t row0, int64_t rows,
+                           long long *minmax /* device [2] */, cudaStream_t stream);
+// sliced layout -> row-major chunk
+cudaError_t unlayout_chunk(int dev_idx_bits, int host_idx_bits, const void *src_cols,
+                           const double *src_vals, void *dst_cols, double *dst_vals,
+                           const EllLayout &lay, int64_t row0, int64_t rows,
+                           cudaStream_t stream);
+cudaError_t generate_sliced(int kind, const int64_t dims[3], const double vals[2], uint64_t seed,
+                            int dst_idx_bits, void *dst_cols, double *dst_vals,
+                            const EllLayout &lay, int64_t row_begin,
+                            long long *minmax, cudaStream_t stream);
+cudaError_t generate_csr_random(const int64_t dims[3], uint64_t seed, int idx_bits,
+                                int64_t *rowptr, void *cols, double *vals, cudaStream_t stream);
+cudaError_t init_minmax(long long *minmax, cudaStream_t stream);
+
+}  // namespace ellspmv

@@ -1,0 +1,123 @@
+// csr_kernels.cu -- fp64 CSR y <- beta*y + A*x for sm_100a (comparison path).
+//
+// Replaces the reference's `csrgemv` loop (csrspmv.c:1588-1593):
+//     for i: yi = 0; for k in [rowptr[i], rowptr[i+1]): yi += a[k]*x[colidx[k]]; y[i] += yi
+//
+// csr_stream_kernel (bit-exact): a CTA owns a block of consecutive rows, i.e.
+// one contiguous run of entries.  The run is streamed through shared memory
+// in tiles: all threads load a[k], colidx[k] with coalesced loads, gather
+// x[colidx[k]] and park the rounded product a*x in shared memory; then each
+// thread adds up the products of ITS row in entry order.  Loads are coalesced
+// no matter how ragged the rows are, and the per-row rounding sequence
+// (mul, then left-to-right adds) is the reference's.
+//
+// csr_vector_kernel (tolerance mode): sub-warp per row with a shuffle tree.
+#include "common.cuh"
+
+namespace ellspmv {
+
+constexpr int kCsrRowsPerCta = 128;   // = kBlockThreads: one thread per row in the sum phase
+constexpr int kCsrTile = 2048;        // entries staged per pass (16 KB + skew)
+
+// one spare double per 32 breaks the power-of-two stride between rows of
+// equal length (K = 32 would otherwise hit one bank from every lane)
+__device__ __forceinline__ int skew(int i) { return i + (i >> 5); }
+
+template <typename IdxT, bool FMA>
+__global__ void __launch_bounds__(kBlockThreads)
+csr_stream_kernel(const CsrSpmvArgs a)
+{
+    __shared__ double prod[kCsrTile + kCsrTile / 32 + 1];
+    const IdxT *__restrict__ cols = reinterpret_cast<const IdxT *>(a.cols);
+    const double *__restrict__ vals = a.vals;
+    const double *__restrict__ x = a.x;
+
+    const int64_t r0 = (int64_t)blockIdx.x * kCsrRowsPerCta;
+    const int64_t r1 = (r0 + kCsrRowsPerCta < a.num_rows) ? r0 + kCsrRowsPerCta : a.num_rows;
+    const int64_t row = r0 + threadIdx.x;
+    const bool have_row = row < r1;
+    const int64_t kb = a.rowptr[r0], ke = a.rowptr[r1];
+    int64_t my_b = 0, my_e = 0;
+    if (have_row) { my_b = a.rowptr[row]; my_e = a.rowptr[row + 1]; }
+
+    double acc = 0.0;
+    for (int64_t t0 = kb; t0 < ke; t0 += kCsrTile) {
+        const int64_t t1 = (t0 + kCsrTile < ke) ? t0 + kCsrTile : ke;
+        const int n = (int)(t1 - t0);
+#pragma unroll 4
+        for (int i = threadIdx.x; i < n; i += kBlockThreads) {
+            const double v = __ldcs(vals + t0 + i);
+            const int64_t c = (int64_t)__ldcs(cols + t0 + i);
+            const double xv = __ldg(x + c);
+            prod[skew(i)] = FMA ? v * xv : __dmul_rn(v, xv);
+        }
+        __syncthreads();
+        if (have_row) {
+            const int64_t b = my_b > t0 ? my_b : t0;
+            const int64_t e = my_e < t1 ? my_e : t1;
+            for (int64_t k = b; k < e; k++) acc = __dadd_rn(acc, prod[skew((int)(k - t0))]);
+        }
+        __syncthreads();
+    }
+    if (have_row) {
+        const double yold = a.beta ? a.y[row] : 0.0;
+        a.y[row] = __dadd_rn(yold, acc);
+    }
+}
+
+// T lanes per row, entries strided by T, shuffle-xor reduction
+template <typename IdxT, int T, bool FMA>
+__global__ void __launch_bounds__(kBlockThreads)
+csr_vector_kernel(const CsrSpmvArgs a)
+{
+    const IdxT *__restrict__ cols = reinterpret_cast<const IdxT *>(a.cols);
+    const double *__restrict__ vals = a.vals;
+    const double *__restrict__ x = a.x;
+    const int64_t gid = (int64_t)blockIdx.x * kBlockThreads + threadIdx.x;
+    const int64_t row = gid / T;
+    const int j = (int)(gid % T);
+    double acc = 0.0;
+    if (row < a.num_rows) {
+        const int64_t b = a.rowptr[row], e = a.rowptr[row + 1];
+#pragma unroll 4
+        for (int64_t k = b + j; k < e; k += T) {
+            const double v = __ldcs(vals + k);
+            const int64_t c = (int64_t)__ldcs(cols + k);
+            const double xv = __ldg(x + c);
+            acc = FMA ? __fma_rn(v, xv, acc) : __dadd_rn(acc, __dmul_rn(v, xv));
+        }
+    }
+#pragma unroll
+    for (int off = 1; off < T; off <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (j == 0 && row < a.num_rows) a.y[row] = a.beta ? a.y[row] + acc : acc;
+}
+
+template <typename IdxT, bool FMA>
+static cudaError_t launch_csr_typed(int kernel, const CsrSpmvArgs &args, cudaStream_t stream)
+{
+    if (args.num_rows <= 0) return cudaSuccess;
+    if (kernel == ELLSPMV_CUDA_KERNEL_WARP) {
+        constexpr int T = 8;
+        const int64_t threads = args.num_rows * T;
+        const int64_t g = (threads + kBlockThreads - 1) / kBlockThreads;
+        if (g > 0x7fffffffLL) return cudaErrorInvalidValue;
+        csr_vector_kernel<IdxT, T, FMA><<<(unsigned)g, kBlockThreads, 0, stream>>>(args);
+    } else {
+        const int64_t g = (args.num_rows + kCsrRowsPerCta - 1) / kCsrRowsPerCta;
+        if (g > 0x7fffffffLL) return cudaErrorInvalidValue;
+        csr_stream_kernel<IdxT, FMA><<<(unsigned)g, kBlockThreads, 0, stream>>>(args);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_csr_spmv(int idx_bits, bool fma, int kernel, const CsrSpmvArgs &args,
+                            cudaStream_t stream)
+{
+    if (idx_bits == 64)
+        return fma ? launch_csr_typed<int64_t, true>(kernel, args, stream)
+                   : launch_csr_typed<int64_t, false>(kernel, args, stream);
+    return fma ? launch_csr_typed<int32_t, true>(kernel, args, stream)
+               : launch_csr_typed<int32_t, false>(kernel, args, stream);
+}
+
+}  // namespace ellspmv

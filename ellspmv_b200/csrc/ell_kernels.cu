@@ -1,0 +1,388 @@
+// ell_kernels.cu -- fp64 ELLPACK y <- beta*y + A*x for sm_100a.
+//
+// Replaces the reference's hot loop `ellgemv` (ellspmv.c:1146-1151):
+//     for i: yi = 0; for l < K: yi += a[i*K+l] * x[colidx[i*K+l]]; y[i] += yi
+//
+// Thread-per-row kernel (bit-exact path).  Each thread owns R consecutive
+// rows of one slice of the sliced-ELL layout (common.cuh) and walks the K
+// slots in the reference's order with separate __dmul_rn/__dadd_rn, so the
+// rounding sequence is exactly the reference's compiled loop (mul, then add,
+// left to right).  Per slot a thread issues ONE vector load
+// of R values (64/128/256-bit) and ONE vector load of R indices; consecutive
+// threads read consecutive addresses, so a warp's request is a contiguous
+// 32*R*8-byte run.  The matrix streams bypass L1 (L1::no_allocate) and are
+// marked evict-first in L2 where the ISA allows it (256-bit form), leaving
+// L1/L2 to the x gather, which goes through the read-only path (ld.global.nc).
+//
+// This kernel is HBM-bound: 2 flops per 12..16 streamed bytes.  Tensor cores
+// do not apply (gather + fp64 dot, no dense contraction).
+#include "common.cuh"
+
+namespace ellspmv {
+
+// ---- vector loads of the matrix streams ----------------------------------
+template <int R> struct Vals;
+template <> struct Vals<1> {
+    static __device__ __forceinline__ void ld(const double *p, double (&v)[1]) {
+        asm("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v[0]) : "l"(p));
+    }
+};
+template <> struct Vals<2> {
+    static __device__ __forceinline__ void ld(const double *p, double (&v)[2]) {
+        asm("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];"
+                     : "=d"(v[0]), "=d"(v[1]) : "l"(p));
+    }
+};
+template <> struct Vals<4> {
+    // 256-bit load: new with sm_100 (SASS LDG.E.NA.EFL2.256.CONSTANT)
+    static __device__ __forceinline__ void ld(const double *p, double (&v)[4]) {
+        unsigned long long b0, b1, b2, b3;
+        asm("ld.global.nc.L1::no_allocate.L2::evict_first.v4.b64 {%0,%1,%2,%3}, [%4];"
+                     : "=l"(b0), "=l"(b1), "=l"(b2), "=l"(b3) : "l"(p));
+        v[0] = __longlong_as_double(b0); v[1] = __longlong_as_double(b1);
+        v[2] = __longlong_as_double(b2); v[3] = __longlong_as_double(b3);
+    }
+};
+
+template <typename IdxT, int R> struct Cols;
+template <> struct Cols<int32_t, 1> {
+    static __device__ __forceinline__ void ld(const int32_t *p, int64_t (&c)[1]) {
+        int v; asm("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+        c[0] = v;
+    }
+};
+template <> struct Cols<int32_t, 2> {
+    static __device__ __forceinline__ void ld(const int32_t *p, int64_t (&c)[2]) {
+        int v0, v1;
+        asm("ld.global.nc.L1::no_allocate.v2.s32 {%0,%1}, [%2];" : "=r"(v0), "=r"(v1) : "l"(p));
+        c[0] = v0; c[1] = v1;
+    }
+};
+template <> struct Cols<int32_t, 4> {
+    static __device__ __forceinline__ void ld(const int32_t *p, int64_t (&c)[4]) {
+        int v0, v1, v2, v3;
+        asm("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3) : "l"(p));
+        c[0] = v0; c[1] = v1; c[2] = v2; c[3] = v3;
+    }
+};
+template <> struct Cols<int64_t, 1> {
+    static __device__ __forceinline__ void ld(const int64_t *p, int64_t (&c)[1]) {
+        long long v; asm("ld.global.nc.L1::no_allocate.s64 %0, [%1];" : "=l"(v) : "l"(p));
+        c[0] = v;
+    }
+};
+template <> struct Cols<int64_t, 2> {
+    static __device__ __forceinline__ void ld(const int64_t *p, int64_t (&c)[2]) {
+        long long v0, v1;
+        asm("ld.global.nc.L1::no_allocate.v2.s64 {%0,%1}, [%2];" : "=l"(v0), "=l"(v1) : "l"(p));
+        c[0] = v0; c[1] = v1;
+    }
+};
+template <> struct Cols<int64_t, 4> {
+    static __device__ __forceinline__ void ld(const int64_t *p, int64_t (&c)[4]) {
+        long long v0, v1, v2, v3;
+        asm("ld.global.nc.L1::no_allocate.L2::evict_first.v4.b64 {%0,%1,%2,%3}, [%4];"
+                     : "=l"(v0), "=l"(v1), "=l"(v2), "=l"(v3) : "l"(p));
+        c[0] = v0; c[1] = v1; c[2] = v2; c[3] = v3;
+    }
+};
+
+// ---- y vector access -------------------------------------------------------
+template <int R> struct YVec;
+template <> struct YVec<1> {
+    static __device__ __forceinline__ void ld(const double *p, double (&v)[1]) { v[0] = *p; }
+    static __device__ __forceinline__ void st(double *p, const double (&v)[1]) { *p = v[0]; }
+};
+template <> struct YVec<2> {
+    static __device__ __forceinline__ void ld(const double *p, double (&v)[2]) {
+        double2 t = *reinterpret_cast<const double2 *>(p); v[0] = t.x; v[1] = t.y;
+    }
+    static __device__ __forceinline__ void st(double *p, const double (&v)[2]) {
+        *reinterpret_cast<double2 *>(p) = make_double2(v[0], v[1]);
+    }
+};
+template <> struct YVec<4> {
+    static __device__ __forceinline__ void ld(const double *p, double (&v)[4]) {
+        double2 t0 = reinterpret_cast<const double2 *>(p)[0];
+        double2 t1 = reinterpret_cast<const double2 *>(p)[1];
+        v[0] = t0.x; v[1] = t0.y; v[2] = t1.x; v[3] = t1.y;
+    }
+    static __device__ __forceinline__ void st(double *p, const double (&v)[4]) {
+        reinterpret_cast<double2 *>(p)[0] = make_double2(v[0], v[1]);
+        reinterpret_cast<double2 *>(p)[1] = make_double2(v[2], v[3]);
+    }
+};
+
+template <bool FMA>
+__device__ __forceinline__ double madd(double acc, double a, double x) {
+    if (FMA) return __fma_rn(a, x, acc);
+    return __dadd_rn(acc, __dmul_rn(a, x));   // mul, then add: the reference's rounding
+}
+
+// slots handled per software-pipelined batch: all loads of a batch are
+// issued before any use, giving U*(1+1) streamed vector loads and U*R
+// gathers in flight per thread
+template <int R> struct Batch { static constexpr int U = (R == 4) ? 4 : (R == 2 ? 6 : 8); };
+
+// ---- thread-per-row kernel ------------------------------------------------
+// KU > 0: K known at compile time (fully unrolled); KU == 0: run-time K.
+// YVEC: y (and every push target) may be accessed with R-wide vectors.
+template <typename IdxT, int R, int KU, bool FMA, bool YVEC>
+__global__ void __launch_bounds__(kBlockThreads)
+ell_thread_kernel(const EllSpmvArgs a)
+{
+    constexpr int S = kBlockThreads * R;
+    constexpr int U = Batch<R>::U;
+    const int K = KU > 0 ? KU : a.rowsize;
+    const int64_t slice = blockIdx.x;
+    const int64_t row0 = slice * S + (int64_t)threadIdx.x * R;   // shard-local
+    if (row0 >= a.num_rows) return;
+
+    const int64_t base = slice * S * (int64_t)K + (int64_t)threadIdx.x * R;
+    const double *vp = a.vals + base;
+    const IdxT *cp = reinterpret_cast<const IdxT *>(a.cols) + base;
+    const double *__restrict__ x = a.x;
+
+    const bool full = row0 + R <= a.num_rows;
+    double yold[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) yold[r] = 0.0;
+    if (a.beta) {
+        if (YVEC && full) YVec<R>::ld(a.y + row0, yold);
+        else {
+#pragma unroll
+            for (int r = 0; r < R; r++) if (row0 + r < a.num_rows) yold[r] = a.y[row0 + r];
+        }
+    }
+
+    double acc[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) acc[r] = 0.0;
+
+    if (KU > 0) {
+#pragma unroll
+        for (int l0 = 0; l0 < KU; l0 += U) {
+            double v[U][R]; int64_t c[U][R]; double xv[U][R];
+#pragma unroll
+            for (int u = 0; u < U; u++) if (l0 + u < KU) {
+                Vals<R>::ld(vp + (int64_t)(l0 + u) * S, v[u]);
+                Cols<IdxT, R>::ld(cp + (int64_t)(l0 + u) * S, c[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) if (l0 + u < KU) {
+#pragma unroll
+                for (int r = 0; r < R; r++) xv[u][r] = __ldg(x + c[u][r]);
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) if (l0 + u < KU) {
+#pragma unroll
+                for (int r = 0; r < R; r++) acc[r] = madd<FMA>(acc[r], v[u][r], xv[u][r]);
+            }
+        }
+    } else {
+        int l0 = 0;
+#pragma unroll 1
+        for (; l0 + U <= K; l0 += U) {
+            double v[U][R]; int64_t c[U][R]; double xv[U][R];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                Vals<R>::ld(vp + (int64_t)(l0 + u) * S, v[u]);
+                Cols<IdxT, R>::ld(cp + (int64_t)(l0 + u) * S, c[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+#pragma unroll
+                for (int r = 0; r < R; r++) xv[u][r] = __ldg(x + c[u][r]);
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+#pragma unroll
+                for (int r = 0; r < R; r++) acc[r] = madd<FMA>(acc[r], v[u][r], xv[u][r]);
+            }
+        }
+#pragma unroll 1
+        for (; l0 < K; l0++) {
+            double v[R]; int64_t c[R];
+            Vals<R>::ld(vp + (int64_t)l0 * S, v);
+            Cols<IdxT, R>::ld(cp + (int64_t)l0 * S, c);
+#pragma unroll
+            for (int r = 0; r < R; r++) acc[r] = madd<FMA>(acc[r], v[r], __ldg(x + c[r]));
+        }
+    }
+
+    // y[i] += yi (beta=1) or y[i] = 0 + yi (beta=0; the add keeps -0 -> +0
+    // exactly like "y=0; y+=yi" on the CPU)
+    double out[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) out[r] = __dadd_rn(yold[r], acc[r]);
+
+    if (YVEC && full) {
+        YVec<R>::st(a.y + row0, out);
+    } else {
+#pragma unroll
+        for (int r = 0; r < R; r++) if (row0 + r < a.num_rows) a.y[row0 + r] = out[r];
+    }
+
+    // fused exchange: store the fresh y entries straight into the peers'
+    // next-x vectors (peer-mapped HBM over NVLink), restricted to the row
+    // range each peer references
+    const int np = a.push.num_peers;
+    if (np > 0) {
+        const int64_t g0 = a.row_begin + row0;
+        for (int p = 0; p < np; p++) {
+            double *px = a.push.x[p];
+            const int64_t lo = a.push.row_lo[p], hi = a.push.row_hi[p];
+            if (YVEC && full && g0 >= lo && g0 + R <= hi) {
+                YVec<R>::st(px + g0, out);
+            } else {
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    const int64_t g = g0 + r;
+                    if (row0 + r < a.num_rows && g >= lo && g < hi) px[g] = out[r];
+                }
+            }
+        }
+    }
+}
+
+// ---- sub-warp-per-row kernel (tolerance mode) -------------------------------
+// T lanes share one row: lane j of the group takes slots j, j+T, j+2T, ...
+// and the partial sums are combined with a shuffle-xor tree, so the
+// summation order differs from the reference (tolerance documented in
+// DESIGN.md).  Layout is the same sliced ELL with S = kBlockThreads rows.
+// Within a warp, lanes [j*(32/T), (j+1)*(32/T)) hold slot-class j for 32/T
+// consecutive rows, so each class reads a contiguous run.
+template <typename IdxT, int T, bool FMA>
+__global__ void __launch_bounds__(kBlockThreads)
+ell_subwarp_kernel(const EllSpmvArgs a, int slice_rows)
+{
+    constexpr int RW = 32 / T;                       // rows per warp
+    constexpr int WARPS = kBlockThreads / 32;
+    const int K = a.rowsize;
+    const int S = slice_rows;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int j = lane / RW, rl = lane % RW;
+    // a CTA covers WARPS*RW rows per pass and S rows in total
+    const int64_t slice = blockIdx.x;
+    const double *vbase = a.vals + slice * S * (int64_t)K;
+    const IdxT *cbase = reinterpret_cast<const IdxT *>(a.cols) + slice * S * (int64_t)K;
+    const double *__restrict__ x = a.x;
+    for (int r_in = warp * RW + rl; r_in < S; r_in += WARPS * RW) {
+        const int64_t row = slice * S + r_in;
+        double acc = 0.0;
+        if (row < a.num_rows) {
+#pragma unroll 4
+            for (int l = j; l < K; l += T) {
+                double v; int64_t c[1]; double vv[1];
+                Vals<1>::ld(vbase + (int64_t)l * S + r_in, vv); v = vv[0];
+                Cols<IdxT, 1>::ld(cbase + (int64_t)l * S + r_in, c);
+                acc = madd<FMA>(acc, v, __ldg(x + c[0]));
+            }
+        }
+#pragma unroll
+        for (int off = RW; off < 32; off <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+        if (j == 0 && row < a.num_rows) {
+            double out = a.beta ? a.y[row] + acc : acc;
+            a.y[row] = out;
+            const int64_t g = a.row_begin + row;
+            for (int p = 0; p < a.push.num_peers; p++)
+                if (g >= a.push.row_lo[p] && g < a.push.row_hi[p]) a.push.x[p][g] = out;
+        }
+    }
+}
+
+// ---- launcher ----------------------------------------------------------------
+template <typename IdxT, int R, int KU, bool FMA>
+static cudaError_t launch_thread_yvec(const EllSpmvArgs &args, int64_t num_slices, bool yvec,
+                                      cudaLaunchConfig_t &lc)
+{
+    (void)num_slices;
+    if (yvec) return cudaLaunchKernelEx(&lc, ell_thread_kernel<IdxT, R, KU, FMA, true>, args);
+    return cudaLaunchKernelEx(&lc, ell_thread_kernel<IdxT, R, KU, FMA, false>, args);
+}
+
+template <typename IdxT, int R, bool FMA>
+static cudaError_t launch_thread_k(const EllSpmvArgs &args, int64_t num_slices, bool yvec,
+                                   cudaLaunchConfig_t &lc)
+{
+    switch (args.rowsize) {
+    case 5:  return launch_thread_yvec<IdxT, R, 5, FMA>(args, num_slices, yvec, lc);
+    case 27: return launch_thread_yvec<IdxT, R, 27, FMA>(args, num_slices, yvec, lc);
+    case 32: return launch_thread_yvec<IdxT, R, 32, FMA>(args, num_slices, yvec, lc);
+    default: return launch_thread_yvec<IdxT, R, 0, FMA>(args, num_slices, yvec, lc);
+    }
+}
+
+template <typename IdxT, bool FMA>
+static cudaError_t launch_thread_r(int R, const EllSpmvArgs &args, int64_t num_slices, bool yvec,
+                                   cudaLaunchConfig_t &lc)
+{
+    switch (R) {
+    case 1: return launch_thread_k<IdxT, 1, FMA>(args, num_slices, yvec, lc);
+    case 2: return launch_thread_k<IdxT, 2, FMA>(args, num_slices, yvec, lc);
+    case 4: return launch_thread_k<IdxT, 4, FMA>(args, num_slices, yvec, lc);
+    default: return cudaErrorInvalidValue;
+    }
+}
+
+template <typename IdxT, bool FMA>
+static cudaError_t launch_subwarp(const EllSpmvArgs &args, int slice_rows, cudaLaunchConfig_t &lc)
+{
+    const int K = args.rowsize;
+    if (K >= 24) return cudaLaunchKernelEx(&lc, ell_subwarp_kernel<IdxT, 8, FMA>, args, slice_rows);
+    if (K >= 12) return cudaLaunchKernelEx(&lc, ell_subwarp_kernel<IdxT, 4, FMA>, args, slice_rows);
+    return cudaLaunchKernelEx(&lc, ell_subwarp_kernel<IdxT, 2, FMA>, args, slice_rows);
+}
+
+static bool aligned_to(const void *p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
+cudaError_t launch_ell_spmv(const EllLaunchCfg &cfg, const EllSpmvArgs &args,
+                            int64_t num_slices, cudaStream_t stream)
+{
+    if (num_slices <= 0) return cudaSuccess;
+    if (num_slices > 0x7fffffffLL) return cudaErrorInvalidValue;
+
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3((unsigned)num_slices);
+    lc.blockDim = dim3(kBlockThreads);
+    lc.dynamicSmemBytes = 0;
+    lc.stream = stream;
+    cudaLaunchAttribute attr[1];
+    lc.attrs = attr;
+    lc.numAttrs = 0;
+    if (cfg.persist_x && cfg.x_bytes > 0) {
+        // L2 persisting window over x: the gather target stays resident while
+        // the matrix streams pass through (B200 analogue of the reference's
+        // A64FX sector-cache isolation, ellspmv.c:1139-1141)
+        attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+        attr[0].val.accessPolicyWindow.base_ptr = const_cast<double *>(args.x);
+        attr[0].val.accessPolicyWindow.num_bytes = (size_t)cfg.x_bytes;
+        attr[0].val.accessPolicyWindow.hitRatio = 1.0f;
+        attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        lc.numAttrs = 1;
+    }
+
+    const bool i64 = cfg.idx_bits == 64;
+    if (cfg.kernel == ELLSPMV_CUDA_KERNEL_WARP) {
+        const int slice_rows = kBlockThreads * cfg.rows_per_thread;
+        if (i64) return cfg.fma ? launch_subwarp<int64_t, true>(args, slice_rows, lc)
+                                : launch_subwarp<int64_t, false>(args, slice_rows, lc);
+        return cfg.fma ? launch_subwarp<int32_t, true>(args, slice_rows, lc)
+                       : launch_subwarp<int32_t, false>(args, slice_rows, lc);
+    }
+
+    // vector y access needs R*8-byte alignment of y, of the row offset, and
+    // of every push target
+    const int R = cfg.rows_per_thread;
+    bool yvec = aligned_to(args.y, 8 * (size_t)R) && (args.row_begin % R == 0);
+    for (int p = 0; p < args.push.num_peers; p++) yvec = yvec && aligned_to(args.push.x[p], 8 * (size_t)R);
+
+    if (i64) return cfg.fma ? launch_thread_r<int64_t, true>(R, args, num_slices, yvec, lc)
+                            : launch_thread_r<int64_t, false>(R, args, num_slices, yvec, lc);
+    return cfg.fma ? launch_thread_r<int32_t, true>(R, args, num_slices, yvec, lc)
+                   : launch_thread_r<int32_t, false>(R, args, num_slices, yvec, lc);
+}
+
+}  // namespace ellspmv

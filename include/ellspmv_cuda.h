@@ -1,0 +1,236 @@
+/*
+ * ellspmv_cuda.h -- C ABI of the B200 (sm_100a) SpMV library.
+ *
+ * This is the drop-in boundary for the hot path of jamtrott/ellspmv: the
+ * fp64 ELLPACK kernel `ellgemv` (reference ellspmv.c:1129-1153) and, as the
+ * comparison path, the CSR kernel `csrgemv` (reference csrspmv.c:1565-1595).
+ * The reference has no FFI of its own; the entry points below are what a
+ * maintainer binds at the reference's three kernel call sites
+ * (ellspmv.c:1766-1767 warm-up, 1841-1842 timed; csrspmv.c:2766-2767,
+ * 2857-2858).  See INTEGRATION.md for the exact patch.
+ *
+ * Conventions (mirroring the reference):
+ *   - every function returns 0 on success or a positive errno value
+ *     (EINVAL, ENOMEM, ENODEV, EIO ...), like `ellgemv` does
+ *     (ellspmv.c:1197); ellspmv_cuda_last_error() has the detail;
+ *   - index width is a run-time argument here (32 or 64 bits) where the
+ *     reference fixes idx_t at compile time (ellspmv.c:112-130);
+ *   - host arrays stay owned by the caller; `upload` copies, the handle
+ *     owns all device memory, `free` releases it;
+ *   - calls on one handle must come from one host thread at a time (the
+ *     reference calls its kernel from every OpenMP thread; call this from
+ *     the master thread only).
+ *
+ * There is no CPU fallback: without a CUDA device every compute entry
+ * point fails with ENODEV.
+ */
+#ifndef ELLSPMV_CUDA_H
+#define ELLSPMV_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ELLSPMV_CUDA_VERSION 100 /* 1.00 */
+
+typedef struct ellspmv_cuda_matrix ellspmv_cuda_matrix; /* opaque, ELL  */
+typedef struct csrspmv_cuda_matrix csrspmv_cuda_matrix; /* opaque, CSR  */
+
+/* ---- flags for upload/generate (OR together) ------------------------- */
+enum {
+    /* kernel selection (low 4 bits) */
+    ELLSPMV_CUDA_KERNEL_AUTO   = 0, /* by nnz-per-row, see DESIGN.md            */
+    ELLSPMV_CUDA_KERNEL_THREAD = 1, /* thread-per-row, sequential slot order:   */
+                                    /*   bit-exact with the reference loop      */
+    ELLSPMV_CUDA_KERNEL_WARP   = 2, /* sub-warp-per-row + shuffle reduction:    */
+                                    /*   tolerance mode (summation order differs)*/
+    ELLSPMV_CUDA_KERNEL_MASK   = 0xf,
+    /* arithmetic: default is mul-then-add (__dmul_rn/__dadd_rn), the bits the
+     * reference's compiled loop produces; FMA allows contraction (tolerance) */
+    ELLSPMV_CUDA_FMA           = 1 << 4,
+    /* ask for an L2 persisting access-policy window over x when it fits */
+    ELLSPMV_CUDA_L2_PERSIST_X  = 1 << 5,
+    /* keep 64-bit column indices as 32-bit on the device when
+     * num_columns < 2^31 (a device-layout choice; host arrays and
+     * ellspmv_cuda_download() stay 64-bit and bit-exact) */
+    ELLSPMV_CUDA_NARROW_INDEX  = 1 << 6,
+    /* rows handled per thread in the thread-per-row kernel: 0 = auto */
+    ELLSPMV_CUDA_ROWS_PER_THREAD_SHIFT = 8,
+    ELLSPMV_CUDA_ROWS_PER_THREAD_MASK  = 0x7 << 8,
+    /* kernel variant for experiments (0 = default direct loads,
+     * 1 = bulk-async (TMA) staged through shared memory) */
+    ELLSPMV_CUDA_VARIANT_SHIFT = 12,
+    ELLSPMV_CUDA_VARIANT_MASK  = 0xf << 12
+};
+
+/* ---- modes for spmv -------------------------------------------------- */
+enum {
+    ELLSPMV_CUDA_ACCUMULATE = 0, /* y <- y + A*x, `repeat` times (reference semantics,   */
+                                 /*   x constant: ellspmv.c:1150, 1824-1843)             */
+    ELLSPMV_CUDA_OVERWRITE  = 1, /* y <- A*x                                             */
+    ELLSPMV_CUDA_ITERATE    = 2  /* x_{k+1} <- A*x_k, `repeat` times, result in y        */
+                                 /*   (BASELINE config 5; square A only)                 */
+};
+
+/* ---- synthetic matrix kinds for generate ------------ */
+enum {
+    ELLSPMV_CUDA_GEN_LAPLACE2D = 1, /* dims = {nx, ny, -}, K = 5,  vals = {centre, off} */
+    ELLSPMV_CUDA_GEN_STENCIL27 = 2, /* dims = {nx, ny, nz}, K = 27, vals = {centre, off} */
+    ELLSPMV_CUDA_GEN_RANDOM    = 3  /* dims = {rows, cols, K}, seeded, vals unused       */
+};
+
+typedef struct ellspmv_cuda_info {
+    int64_t num_rows;        /* rows held by this handle (the shard)        */
+    int64_t num_columns;
+    int64_t rowsize;         /* K                                           */
+    int64_t row_begin;       /* first global row of the shard               */
+    int64_t global_rows;     /* rows of the whole matrix                    */
+    int     idx_width_bits;  /* as given by the caller (host view)          */
+    int     dev_idx_bits;    /* as stored on the device                     */
+    int     slice_rows;      /* sliced-ELL slice height                     */
+    int     rows_per_thread;
+    int     kernel;          /* ELLSPMV_CUDA_KERNEL_THREAD / _WARP in use   */
+    int     fma;
+    int     device;          /* CUDA device ordinal                         */
+    int64_t device_bytes;    /* bytes of HBM held by the handle             */
+    int64_t min_col, max_col;/* column range referenced by this shard       */
+    int64_t launches;        /* SpMV kernel launches issued so far          */
+} ellspmv_cuda_info;
+
+/* ---- ELL ------------------------------------------------------------- */
+
+/*
+ * Copy a row-major ELL matrix (the arrays ell_from_coo produces,
+ * ellspmv.c:1081-1127: colidx[i*K+l], a[i*K+l], 0-based, padded) to the
+ * device and re-lay it as sliced ELL.  Replaces nothing in the reference;
+ * call it once after ell_from_coo (~ellspmv.c:1745).
+ *   idx_width_bits  32 or 64 (sizeof(idx_t)*8)
+ *   num_gpus        1 (sharding over several GPUs in one process is driven
+ *                   through ellspmv_cuda_upload_shard, one handle per GPU)
+ */
+int ellspmv_cuda_upload(
+    ellspmv_cuda_matrix **out, int idx_width_bits,
+    int64_t num_rows, int64_t num_columns, int64_t rowsize,
+    const void *colidx, const double *a, int num_gpus, unsigned flags);
+
+/*
+ * Same, for rows [row_begin, row_end) of a larger matrix on CUDA device
+ * `device`: colidx/a point at the shard's first row, column indices stay
+ * global.  Used for row-sharded repeated SpMV.
+ */
+int ellspmv_cuda_upload_shard(
+    ellspmv_cuda_matrix **out, int idx_width_bits,
+    int64_t global_rows, int64_t num_columns, int64_t rowsize,
+    int64_t row_begin, int64_t row_end,
+    const void *colidx, const double *a, int device, unsigned flags);
+
+/*
+ * Build rows [row_begin, row_end) of a synthetic matrix directly on the
+ * device, in device layout (for shapes too large to build on the host).
+ * Bit-identical to uploading the arrays the reference's ell_from_coo
+ * produces from the same entries (tested).  device < 0: current device.
+ */
+int ellspmv_cuda_generate(
+    ellspmv_cuda_matrix **out, int kind, const int64_t dims[3],
+    const double vals[2], uint64_t seed, int idx_width_bits,
+    int64_t row_begin, int64_t row_end, int device, unsigned flags);
+
+/*
+ * y <- y + A*x (mode ACCUMULATE; replaces the ellgemv call,
+ * ellspmv.c:1841-1842), with HOST vectors: x has num_columns entries, y has
+ * num_rows entries.  Copies x and y in, runs `repeat` kernel launches,
+ * copies y out.  seconds (may be NULL) receives `repeat` per-launch device
+ * times measured with CUDA events, the counterpart of the reference's
+ * per-iteration CLOCK_MONOTONIC pair (ellspmv.c:1825-1847).
+ */
+int ellspmv_cuda_spmv(
+    ellspmv_cuda_matrix *A, double *y, const double *x,
+    int repeat, int mode, double *seconds);
+
+/*
+ * One launch on DEVICE vectors, asynchronous on `stream` (a cudaStream_t;
+ * NULL = the legacy default stream).  x_dev: num_columns doubles; y_dev:
+ * the shard's num_rows doubles.  mode: ACCUMULATE or OVERWRITE.
+ */
+int ellspmv_cuda_spmv_device(
+    ellspmv_cuda_matrix *A, double *y_dev, const double *x_dev,
+    int mode, void *stream);
+
+/*
+ * As above, and additionally store each computed y[i] (global row
+ * row_begin+i) into up to 8 peer vectors: for peer p, rows in
+ * [peer_row_lo[p], peer_row_hi[p]) are written to peer_x[p][global row].
+ * peer_x are device pointers valid on this device (peer-mapped or IPC
+ * opened): the fused SpMV + exchange used for row-sharded repeated SpMV.
+ */
+int ellspmv_cuda_spmv_push(
+    ellspmv_cuda_matrix *A, double *y_dev, const double *x_dev, int mode,
+    int num_peers, double *const *peer_x,
+    const int64_t *peer_row_lo, const int64_t *peer_row_hi, void *stream);
+
+/* Copy the device matrix back as row-major host arrays of the caller's
+ * index width (inverse of upload; used to test bit-exactness). */
+int ellspmv_cuda_download(
+    const ellspmv_cuda_matrix *A, void *colidx, double *a);
+
+int  ellspmv_cuda_get_info(const ellspmv_cuda_matrix *A, ellspmv_cuda_info *info);
+void ellspmv_cuda_free(ellspmv_cuda_matrix *A);
+
+/* ---- CSR (comparison path) ------------------------------------------- */
+
+/* rowptr: num_rows+1 int64 (always 64-bit in the reference, csrspmv.c:1573);
+ * colidx: csrsize idx_t, 0-based; a: csrsize doubles. */
+int csrspmv_cuda_upload(
+    csrspmv_cuda_matrix **out, int idx_width_bits,
+    int64_t num_rows, int64_t num_columns,
+    const int64_t *rowptr, const void *colidx, const double *a,
+    int num_gpus, unsigned flags);
+
+/* CSR view of ELLSPMV_CUDA_GEN_RANDOM (every row has exactly K entries) */
+int csrspmv_cuda_generate(
+    csrspmv_cuda_matrix **out, int kind, const int64_t dims[3],
+    const double vals[2], uint64_t seed, int idx_width_bits,
+    int device, unsigned flags);
+
+/* replaces the csrgemv call, csrspmv.c:2857-2858 */
+int csrspmv_cuda_spmv(
+    csrspmv_cuda_matrix *A, double *y, const double *x,
+    int repeat, int mode, double *seconds);
+
+int csrspmv_cuda_spmv_device(
+    csrspmv_cuda_matrix *A, double *y_dev, const double *x_dev,
+    int mode, void *stream);
+
+int64_t csrspmv_cuda_device_bytes(const csrspmv_cuda_matrix *A);
+void csrspmv_cuda_free(csrspmv_cuda_matrix *A);
+
+/* ---- utilities -------------------------------------------------------- */
+
+/* pinned host memory for x / y so the copies inside spmv run at full PCIe
+ * rate (the host program allocates its vectors with these) */
+int  ellspmv_cuda_malloc_host(void **ptr, int64_t bytes);
+void ellspmv_cuda_free_host(void *ptr);
+
+/* plain device allocations (cudaMalloc) for the exchange vectors of the
+ * row-sharded path; unlike a sub-allocated framework tensor these can be
+ * exported over CUDA IPC as they are */
+int  ellspmv_cuda_malloc_device(void **ptr, int64_t bytes);
+void ellspmv_cuda_free_device(void *ptr);
+
+/* CUDA IPC plumbing for one-process-per-GPU sharding: export a device
+ * allocation as a 64-byte handle / open a peer's handle */
+int ellspmv_cuda_ipc_export(const void *dev_ptr, unsigned char handle[64]);
+int ellspmv_cuda_ipc_open(const unsigned char handle[64], void **dev_ptr);
+int ellspmv_cuda_ipc_close(void *dev_ptr);
+
+int ellspmv_cuda_device_count(int *count);
+const char *ellspmv_cuda_strerror(int err);
+const char *ellspmv_cuda_last_error(void);
+int ellspmv_cuda_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ELLSPMV_CUDA_H */

@@ -1,0 +1,142 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.json from the UNMODIFIED reference.
+
+Run in the build container only (needs /root/reference and oracle/_ref/,
+i.e. `make -C oracle`).  The reference has no golden vectors of its own
+(SURVEY.md 4), so these fixtures are outputs of the reference itself:
+  - function level, through oracle/_ref/libref_{ell,csr}{32,64}.so (the
+    reference's static ell_from_coo / ellgemv / csr_from_coo / csrgemv);
+  - program level, stdout of oracle/_ref/{ellspmv,csrspmv}[64] under LC_ALL=C.
+Floating-point vectors are stored as C99 hex floats (bit-exact).
+The tests that consume the fixtures never read /root/reference.
+"""
+import json
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+from oracle.pyoracle import REF_DIR, Reference  # noqa: E402
+
+
+def hexlist(v):
+    return [float(t).hex() for t in v]
+
+
+def write_mtx(path, nrows, ncols, ri, ci, a, field="real"):
+    with open(path, "w") as f:
+        f.write(f"%%MatrixMarket matrix coordinate {field} general\n")
+        f.write(f"{nrows} {ncols} {len(ri)}\n")
+        for r, c, v in zip(ri, ci, a):
+            if field == "pattern":
+                f.write(f"{r} {c}\n")
+            else:
+                f.write(f"{r} {c} {float(v):.17g}\n")
+
+
+def write_vec(path, v):
+    with open(path, "w") as f:
+        f.write("%%MatrixMarket vector array real general\n")
+        f.write(f"{len(v)}\n")
+        for t in v:
+            f.write(f"{float(t):.17g}\n")
+
+
+def run_binary(name, args):
+    env = dict(os.environ, LC_ALL="C", OMP_NUM_THREADS="4")
+    p = subprocess.run([os.path.join(REF_DIR, name)] + args, capture_output=True, text=True, env=env)
+    return {"returncode": p.returncode, "stdout": p.stdout}
+
+
+def case(name, nrows, ncols, ri, ci, a, x, y0, tmp):
+    out = {"name": name, "num_rows": nrows, "num_columns": ncols,
+           "rowidx": [int(t) for t in ri], "colidx": [int(t) for t in ci], "a": hexlist(a),
+           "x": hexlist(x), "y0": hexlist(y0)}
+    for bits in (32, 64):
+        dt = np.int32 if bits == 32 else np.int64
+        r, c = np.asarray(ri, dtype=dt), np.asarray(ci, dtype=dt)
+        av = np.asarray(a, dtype=np.float64)
+        ell = Reference("ell", bits)
+        K, ellsize, diagsize, ec, ea = ell.ell_from_coo(nrows, ncols, r, c, av)
+        y = np.array(y0, dtype=np.float64)
+        ell.ellgemv(nrows, y, ncols, np.asarray(x, dtype=np.float64), K, ec, ea, repeat=1)
+        y3 = np.array(y0, dtype=np.float64)
+        ell.ellgemv(nrows, y3, ncols, np.asarray(x, dtype=np.float64), K, ec, ea, repeat=3)
+        csr = Reference("csr", bits)
+        rowptr, cc, ca, lo, hi = csr.csr_from_coo(nrows, ncols, r, c, av)
+        yc = np.array(y0, dtype=np.float64)
+        csr.csrgemv(nrows, yc, ncols, np.asarray(x, dtype=np.float64), rowptr, cc, ca, 1, lo, hi)
+        out[f"idx{bits}"] = {
+            "rowsize": K, "ellsize": ellsize, "diagsize": diagsize,
+            "ellcolidx": [int(t) for t in ec], "ella": hexlist(ea),
+            "y_ell": hexlist(y), "y_ell_repeat3": hexlist(y3),
+            "rowptr": [int(t) for t in rowptr], "csrcolidx": [int(t) for t in cc], "csra": hexlist(ca),
+            "rowsizemin": lo, "rowsizemax": hi, "y_csr": hexlist(yc),
+        }
+    # whole-program goldens (x = ones, y0 = 0: the reference defaults) + x/y from files
+    A = os.path.join(tmp, name + ".mtx")
+    write_mtx(A, nrows, ncols, ri, ci, a)
+    out["program"] = {
+        "ellspmv": run_binary("ellspmv", [A]),
+        "ellspmv_repeat2_warmup1": run_binary("ellspmv", ["--repeat=2", "--warmup=1", A]),
+        "ellspmv64": run_binary("ellspmv64", [A]),
+        "csrspmv": run_binary("csrspmv", [A]),
+        "csrspmv64": run_binary("csrspmv64", [A]),
+    }
+    if nrows == ncols:   # x from file is only right for square A in the reference (Q3)
+        xf, yf = os.path.join(tmp, name + "_x.mtx"), os.path.join(tmp, name + "_y.mtx")
+        write_vec(xf, x)
+        write_vec(yf, y0)
+        out["program"]["ellspmv_xy"] = run_binary("ellspmv", [A, xf, yf])
+        out["program"]["csrspmv_xy"] = run_binary("csrspmv", [A, xf, yf])
+    return out
+
+
+def main():
+    cases = []
+    with tempfile.TemporaryDirectory() as tmp:
+        # 1. the reference's only fixture, test.mtx (entries parsed here, not copied)
+        ri, ci, a = [], [], []
+        with open("/root/reference/test.mtx") as f:
+            lines = [l for l in f if not l.startswith("%")]
+        nrows, ncols, nnz = map(int, lines[0].split())
+        for l in lines[1:1 + nnz]:
+            r, c, v = l.split()
+            ri.append(int(r)); ci.append(int(c)); a.append(float(v))
+        cases.append(case("test_mtx", nrows, ncols, ri, ci, a, [1.0] * ncols, [0.0] * nrows, tmp))
+
+        # 2. seeded random matrices: non-square both ways (padding rule Q16),
+        #    empty rows, duplicate entries (Q17), unsorted file order
+        rng = np.random.default_rng(20261018)
+        for name, nr, nc, nnz in [("rand_wide", 23, 37, 140), ("rand_tall", 41, 17, 160),
+                                  ("rand_square", 32, 32, 200), ("rand_sparse_rows", 50, 50, 60)]:
+            ri = rng.integers(1, nr + 1, nnz)
+            ci = rng.integers(1, nc + 1, nnz)
+            if name == "rand_sparse_rows":
+                ri = 1 + 3 * (ri // 3) % nr   # leaves many rows empty
+            ri[5], ci[5] = ri[4], ci[4]       # a duplicate (i, j)
+            a = rng.uniform(-2.0, 2.0, nnz)
+            x = rng.uniform(-1.0, 1.0, nc)
+            y0 = rng.uniform(-1.0, 1.0, nr)
+            cases.append(case(name, nr, nc, ri.tolist(), ci.tolist(), a.tolist(), x.tolist(), y0.tolist(), tmp))
+
+        # 3. a single full row and an all-empty matrix
+        cases.append(case("one_row", 1, 9, [1] * 9, list(range(9, 0, -1)), [float(i) for i in range(1, 10)],
+                          [0.5] * 9, [1.0], tmp))
+        cases.append(case("empty", 5, 4, [], [], [], [1.0] * 4, [2.0] * 5, tmp))
+
+    for c in cases:
+        # tmp paths differ run to run; nothing in stdout depends on them
+        with open(os.path.join(HERE, c["name"] + ".json"), "w") as f:
+            json.dump(c, f, indent=0, separators=(",", ":"))
+        print("wrote", c["name"], {b: c[f"idx{b}"]["rowsize"] for b in (32, 64)},
+              [v["returncode"] for v in c["program"].values()])
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,94 @@
+"""GPU parity of the CSR comparison path (csrspmv_cuda_*) against the
+oracle's csrgemv and the golden vectors of the unmodified reference."""
+import numpy as np
+import pytest
+
+import ellspmv_b200 as E
+from conftest import GOLDEN_CASES, bits_equal, load_golden, unhex
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+@pytest.mark.parametrize("bits", [32, 64])
+def test_golden_reference_vectors(lib, name, bits):
+    g = load_golden(name)
+    e = g[f"idx{bits}"]
+    dt = np.int32 if bits == 32 else np.int64
+    rowptr = np.array(e["rowptr"], dtype=np.int64)
+    cc, ca = np.array(e["csrcolidx"], dtype=dt), unhex(e["csra"])
+    A = E.CsrMatrix.upload(g["num_rows"], g["num_columns"], rowptr, cc, ca)
+    y = unhex(g["y0"])
+    A.spmv(y, unhex(g["x"]), 1, E.ACCUMULATE)
+    A.free()
+    assert bits_equal(y, unhex(e["y_csr"]))
+
+
+def ragged_csr(rng, nr, nc, maxlen, dt):
+    lens = rng.integers(0, maxlen + 1, nr)
+    lens[rng.integers(0, nr, max(nr // 10, 1))] = 0
+    if nr > 3:
+        lens[nr // 2] = 5 * maxlen + 3000          # one very long row (spans several tiles)
+    rowptr = np.zeros(nr + 1, dtype=np.int64)
+    np.cumsum(lens, out=rowptr[1:])
+    nnz = int(rowptr[-1])
+    return rowptr, rng.integers(0, nc, nnz).astype(dt), rng.standard_normal(nnz)
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 1), (100, 50, 4), (129, 1000, 40), (5000, 5000, 9), (1025, 300, 70)])
+@pytest.mark.parametrize("bits", [32, 64])
+def test_bit_exact_vs_oracle(lib, oracle, shape, bits):
+    nr, nc, maxlen = shape
+    dt = np.int32 if bits == 32 else np.int64
+    rng = np.random.default_rng(nr + nc + maxlen + bits)
+    rowptr, cc, ca = ragged_csr(rng, nr, nc, maxlen, dt)
+    x = rng.standard_normal(nc)
+    y0 = rng.standard_normal(nr)
+    want = y0.copy()
+    oracle.csrgemv(nr, want, x, rowptr, cc, ca)
+    A = E.CsrMatrix.upload(nr, nc, rowptr, cc, ca)
+    y = y0.copy()
+    A.spmv(y, x, 1, E.ACCUMULATE)
+    assert bits_equal(y, want)
+    want0 = np.zeros(nr)
+    oracle.csrgemv(nr, want0, x, rowptr, cc, ca)
+    A.spmv(y, x, 2, E.OVERWRITE)
+    assert bits_equal(y, want0)
+    A.free()
+    # tolerance modes
+    absprod = np.zeros(nr)
+    np.add.at(absprod, np.repeat(np.arange(nr), np.diff(rowptr)), np.abs(ca * x[cc]))
+    bound = (np.diff(rowptr) + 2) * 2.0 ** -53 * absprod
+    for flags in (E.FMA, E.KERNEL_WARP, E.KERNEL_WARP | E.FMA):
+        A = E.CsrMatrix.upload(nr, nc, rowptr, cc, ca, flags)
+        y = np.zeros(nr)
+        A.spmv(y, x, 1, E.ACCUMULATE)
+        A.free()
+        assert np.all(np.abs(y - want0) <= bound + 1e-300), flags
+
+
+def test_reference_shaped_operator(lib):
+    g = load_golden("test_mtx")
+    e = g["idx32"]
+    rowptr = np.array(e["rowptr"], dtype=np.int64)
+    cc, ca = np.array(e["csrcolidx"], dtype=np.int32), unhex(e["csra"])
+    y, x = np.zeros(4), np.ones(5)
+    assert E.csrgemv(4, y, 5, x, 9, 1, 5, rowptr, cc, ca) == 0
+    assert y.tolist() == [3, 1, 3, 6]
+
+
+def test_random_csr_is_the_ell_matrix(lib, oracle):
+    """BASELINE config 4: the CSR view of the random matrix has the same
+    entries as the ELL one, so both paths must give identical bits."""
+    dims = (30000, 30000, 32)
+    x = np.random.default_rng(2).standard_normal(dims[1])
+    Ae = E.EllMatrix.generate(E.GEN_RANDOM, dims, seed=42, idx_bits=32)
+    Ac = E.CsrMatrix.generate(E.GEN_RANDOM, dims, seed=42, idx_bits=32)
+    ye, yc = np.zeros(dims[0]), np.zeros(dims[0])
+    Ae.spmv(ye, x, 1, E.ACCUMULATE)
+    Ac.spmv(yc, x, 1, E.ACCUMULATE)
+    Ae.free(); Ac.free()
+    K, ncols, ec, ea, _ = oracle.gen_ell("random", dims, seed=42)
+    want = np.zeros(dims[0])
+    oracle.ellgemv(dims[0], want, x, K, ec, ea)
+    assert bits_equal(ye, want) and bits_equal(yc, want)

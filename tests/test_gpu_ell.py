@@ -1,0 +1,230 @@
+"""GPU parity of the ELL path through the C ABI (include/ellspmv_cuda.h),
+against the CPU oracle and the golden vectors of the unmodified reference.
+
+Bar: ELL arrays bit-exact; y bit-exact in the default mode (thread-per-row,
+mul-then-add); tolerance modes (FMA, sub-warp reduction) within the
+dot-product bound  |dy| <= (K+2) * 2^-53 * sum_l |a_il * x_l|  per row."""
+import numpy as np
+import pytest
+
+import ellspmv_b200 as E
+from conftest import GOLDEN_CASES, bits_equal, load_golden, unhex
+
+pytestmark = pytest.mark.gpu
+
+ALL_R = [1, 2, 4]
+
+
+def rand_ell(rng, nr, nc, K, dt, pad_frac=0.3):
+    """Row-major ELL arrays with the reference's padding rule on a random tail of each row."""
+    ec = rng.integers(0, nc, (nr, K)).astype(dt)
+    ea = rng.standard_normal((nr, K))
+    fill = rng.integers(0, K + 1, nr) if pad_frac > 0 else np.full(nr, K)
+    for i in range(nr):
+        ec[i, fill[i]:] = min(i, nc - 1)
+        ea[i, fill[i]:] = 0.0
+    return np.ascontiguousarray(ec.reshape(-1)), np.ascontiguousarray(ea.reshape(-1))
+
+
+def tol_bound(K, ec, ea, x, nr):
+    absprod = np.abs(ea.reshape(nr, K) * x[ec.reshape(nr, K)]).sum(axis=1) if K > 0 else np.zeros(nr)
+    return (K + 2) * 2.0 ** -53 * absprod
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+@pytest.mark.parametrize("bits", [32, 64])
+def test_golden_reference_vectors(lib, name, bits):
+    g = load_golden(name)
+    e = g[f"idx{bits}"]
+    dt = np.int32 if bits == 32 else np.int64
+    ec, ea = np.array(e["ellcolidx"], dtype=dt), unhex(e["ella"])
+    nr, nc, K = g["num_rows"], g["num_columns"], e["rowsize"]
+    for R in ALL_R:
+        A = E.EllMatrix.upload(nr, nc, K, ec, ea, E.rows_per_thread(R))
+        c2, a2 = A.download()
+        assert np.array_equal(c2, ec) and bits_equal(a2, ea)
+        y = unhex(g["y0"])
+        A.spmv(y, unhex(g["x"]), 1, E.ACCUMULATE)
+        assert bits_equal(y, unhex(e["y_ell"])), (name, bits, R)
+        y = unhex(g["y0"])
+        A.spmv(y, unhex(g["x"]), 3, E.ACCUMULATE)
+        assert bits_equal(y, unhex(e["y_ell_repeat3"]))
+        A.free()
+
+
+def test_reference_shaped_operator(lib):
+    g = load_golden("test_mtx")
+    e = g["idx32"]
+    ec, ea = np.array(e["ellcolidx"], dtype=np.int32), unhex(e["ella"])
+    y, x = np.zeros(4), np.ones(5)
+    assert E.ellgemv(4, y, 5, x, 20, 5, ec, ea) == 0
+    assert y.tolist() == [3, 1, 3, 6]
+    assert E.ellgemv(4, y, 5, x, 20, 5, ec, ea) == 0      # accumulates, like the reference
+    assert y.tolist() == [6, 2, 6, 12]
+    assert E.ellgemv(4, y, 5, x, 19, 5, ec, ea) != 0      # ellsize != N*K
+
+
+SHAPES = [(1, 1, 1), (3, 7, 2), (127, 127, 5), (128, 64, 5), (129, 300, 7), (511, 511, 27), (512, 512, 32),
+          (513, 100, 33), (1000, 1000, 1), (2049, 777, 16), (5000, 5000, 5), (4097, 4097, 27), (300, 5000, 64)]
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("bits", [32, 64])
+def test_bit_exact_vs_oracle(lib, oracle, shape, bits):
+    nr, nc, K = shape
+    dt = np.int32 if bits == 32 else np.int64
+    rng = np.random.default_rng(nr * 131 + nc * 7 + K + bits)
+    ec, ea = rand_ell(rng, nr, nc, K, dt)
+    x = rng.standard_normal(nc)
+    y0 = rng.standard_normal(nr)
+    want = y0.copy()
+    oracle.ellgemv(nr, want, x, K, ec, ea)
+    want0 = np.zeros(nr)
+    oracle.ellgemv(nr, want0, x, K, ec, ea)
+    for R in ALL_R:
+        for extra in (0, E.NARROW_INDEX, E.L2_PERSIST_X):
+            A = E.EllMatrix.upload(nr, nc, K, ec, ea, E.rows_per_thread(R) | extra)
+            info = A.info()
+            assert info.rows_per_thread == R and info.slice_rows == 128 * R
+            assert info.dev_idx_bits == (32 if (bits == 32 or extra == E.NARROW_INDEX) else 64)
+            assert info.min_col == ec.min() and info.max_col == ec.max()
+            c2, a2 = A.download()
+            assert c2.dtype == dt and np.array_equal(c2, ec) and bits_equal(a2, ea)
+            y = y0.copy()
+            A.spmv(y, x, 1, E.ACCUMULATE)
+            assert bits_equal(y, want), (shape, bits, R, extra)
+            y = rng.standard_normal(nr)                    # garbage that OVERWRITE must ignore
+            A.spmv(y, x, 1, E.OVERWRITE)
+            assert bits_equal(y, want0), (shape, bits, R, extra)
+            A.free()
+
+
+@pytest.mark.parametrize("flags", [E.FMA, E.KERNEL_WARP, E.KERNEL_WARP | E.FMA])
+@pytest.mark.parametrize("K", [3, 5, 16, 27, 32, 40])
+def test_tolerance_modes(lib, oracle, flags, K):
+    nr, nc = 3000, 2500
+    rng = np.random.default_rng(K + flags)
+    ec, ea = rand_ell(rng, nr, nc, K, np.int32)
+    x = rng.standard_normal(nc)
+    want = np.zeros(nr)
+    oracle.ellgemv(nr, want, x, K, ec, ea)
+    bound = tol_bound(K, ec, ea, x, nr)
+    for R in ALL_R:
+        A = E.EllMatrix.upload(nr, nc, K, ec, ea, flags | E.rows_per_thread(R))
+        y = np.zeros(nr)
+        A.spmv(y, x, 1, E.ACCUMULATE)
+        A.free()
+        assert np.all(np.abs(y - want) <= bound + 1e-300), (flags, K, R, np.max(np.abs(y - want)))
+
+
+def test_edge_cases(lib, oracle):
+    # no rows
+    A = E.EllMatrix.upload(0, 5, 3, np.zeros(0, dtype=np.int32), np.zeros(0))
+    A.spmv(np.zeros(0), np.ones(5), 2, E.ACCUMULATE)
+    A.free()
+    # K = 0: y unchanged under ACCUMULATE, zero under OVERWRITE
+    A = E.EllMatrix.upload(7, 5, 0, np.zeros(0, dtype=np.int64), np.zeros(0))
+    y = np.arange(7.0)
+    A.spmv(y, np.ones(5), 2, E.ACCUMULATE)
+    assert np.array_equal(y, np.arange(7.0))
+    A.spmv(y, np.ones(5), 1, E.OVERWRITE)
+    assert np.array_equal(y, np.zeros(7))
+    A.free()
+    # signed zeros: 0 + (-0) = +0 exactly like the CPU loop
+    ec = np.zeros(4, dtype=np.int32)
+    ea = np.array([-1.0, 0.0, 0.0, 0.0])
+    x = np.array([0.0])
+    want = np.array([-0.0])
+    oracle.ellgemv(1, want, x, 4, ec, ea)
+    A = E.EllMatrix.upload(1, 1, 4, ec, ea)
+    y = np.array([-0.0])
+    A.spmv(y, x, 1, E.ACCUMULATE)
+    assert bits_equal(y, want)
+    A.free()
+    # inf / nan propagate like on the CPU (0 * inf = nan in a padded slot)
+    ec = np.array([0, 1, 1, 1], dtype=np.int32)
+    ea = np.array([1.0, 0.0, 2.0, 0.0])
+    x = np.array([1.0, np.inf])
+    want = np.zeros(2)
+    oracle.ellgemv(2, want, x, 2, ec, ea)
+    A = E.EllMatrix.upload(2, 2, 2, ec, ea)
+    y = np.zeros(2)
+    A.spmv(y, x, 1, E.ACCUMULATE)
+    assert bits_equal(y, want) and np.isnan(y[0]) and np.isinf(y[1])
+    A.free()
+    # out-of-range column index is rejected at upload
+    with pytest.raises(E.EllspmvCudaError):
+        E.EllMatrix.upload(1, 3, 1, np.array([3], dtype=np.int32), np.ones(1))
+
+
+@pytest.mark.parametrize("bits", [32, 64])
+def test_iterate_mode(lib, oracle, bits):
+    dt = np.int32 if bits == 32 else np.int64
+    K, ncols, ec, ea, _ = oracle.gen_ell("stencil27", (12, 10, 11), (0.5, -1.0 / 52), bits=bits)
+    n = ncols
+    x0 = np.random.default_rng(5).uniform(-1, 1, n)
+    want = oracle.ell_iterate(n, x0, 7, K, ec, ea)
+    A = E.EllMatrix.upload(n, n, K, ec, ea)
+    y = np.zeros(n)
+    A.spmv(y, x0, 7, E.ITERATE)
+    assert bits_equal(y, want)
+    # even count too (result lives in the other buffer)
+    want = oracle.ell_iterate(n, x0, 4, K, ec, ea)
+    A.spmv(y, x0, 4, E.ITERATE)
+    assert bits_equal(y, want)
+    A.free()
+    B = E.EllMatrix.upload(3, 4, 1, np.zeros(3, dtype=dt), np.ones(3))
+    with pytest.raises(E.EllspmvCudaError):
+        B.spmv(np.zeros(3), np.ones(4), 1, E.ITERATE)    # not square
+    B.free()
+
+
+def test_device_vectors_and_shards(lib, oracle):
+    """Row shards with global column indices give the same bits as the whole
+    matrix (row sharding leaves each row's summation order untouched)."""
+    import torch
+    nr, nc, K = 5003, 5003, 9
+    rng = np.random.default_rng(11)
+    ec, ea = rand_ell(rng, nr, nc, K, np.int32)
+    x = rng.standard_normal(nc)
+    want = np.zeros(nr)
+    oracle.ellgemv(nr, want, x, K, ec, ea)
+    xd = torch.from_numpy(x).cuda()
+    yd = torch.full((nr,), 123.0, dtype=torch.float64, device="cuda")
+    cuts = [0, 1000, 1003, 3500, nr]
+    for lo, hi in zip(cuts[:-1], cuts[1:]):
+        S = E.EllMatrix.upload(hi - lo, nc, K, ec[lo * K:hi * K], ea[lo * K:hi * K], 0,
+                               global_rows=nr, row_begin=lo, device=0)
+        i = S.info()
+        assert (i.row_begin, i.num_rows, i.global_rows) == (lo, hi - lo, nr)
+        S.spmv_device(yd[lo:hi], xd, E.OVERWRITE, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        S.free()
+    assert bits_equal(yd.cpu().numpy(), want)
+
+
+def test_push_to_peer_vectors(lib, oracle):
+    """The fused exchange on one GPU: 'peers' are plain device vectors."""
+    import torch
+    nr = nc = 4099
+    K = 6
+    rng = np.random.default_rng(12)
+    ec, ea = rand_ell(rng, nr, nc, K, np.int64)
+    x = rng.standard_normal(nc)
+    want = np.zeros(nr)
+    oracle.ellgemv(nr, want, x, K, ec, ea)
+    xd = torch.from_numpy(x).cuda()
+    lo, hi = 1001, 3001      # deliberately not a multiple of 4
+    S = E.EllMatrix.upload(hi - lo, nc, K, ec[lo * K:hi * K], ea[lo * K:hi * K], 0,
+                           global_rows=nr, row_begin=lo, device=0)
+    own = torch.zeros(nr, dtype=torch.float64, device="cuda")
+    p0 = torch.zeros(nr, dtype=torch.float64, device="cuda")
+    p1 = torch.zeros(nr, dtype=torch.float64, device="cuda")
+    S.spmv_push(own[lo:hi], xd, E.OVERWRITE, [p0.data_ptr(), p1.data_ptr()], [0, 2000], [nr, 2500],
+                torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    S.free()
+    assert bits_equal(own[lo:hi].cpu().numpy(), want[lo:hi])
+    assert bits_equal(p0[lo:hi].cpu().numpy(), want[lo:hi]) and p0[:lo].abs().sum() == 0 and p0[hi:].abs().sum() == 0
+    assert bits_equal(p1[2000:2500].cpu().numpy(), want[2000:2500])
+    assert p1[:2000].abs().sum() == 0 and p1[2500:].abs().sum() == 0

@@ -1,0 +1,96 @@
+"""On-device generators of BASELINE.json's synthetic shapes are bit-identical
+to the oracle's (which tests/test_generators.py ties to ell_from_coo), and
+full-size properties of the headline workload hold."""
+import numpy as np
+import pytest
+
+import ellspmv_b200 as E
+from conftest import bits_equal
+
+pytestmark = pytest.mark.gpu
+
+KINDS = {"laplace2d": E.GEN_LAPLACE2D, "stencil27": E.GEN_STENCIL27, "random": E.GEN_RANDOM}
+CASES = [("laplace2d", (37, 29), (4.0, -1.0)), ("laplace2d", (1, 5), (4.0, -1.0)),
+         ("stencil27", (9, 7, 8), (26.0, -1.0)), ("stencil27", (2, 1, 3), (0.5, -1.0 / 52)),
+         ("random", (1234, 999, 32), (0.0, 0.0)), ("random", (100, 3_000_000_000, 5), (0.0, 0.0))]
+
+
+@pytest.mark.parametrize("kind,dims,vals", CASES)
+@pytest.mark.parametrize("bits", [32, 64])
+def test_device_generator_equals_oracle(lib, oracle, kind, dims, vals, bits):
+    if bits == 32 and max(dims) > 2 ** 31 - 1:
+        with pytest.raises(E.EllspmvCudaError):
+            E.EllMatrix.generate(KINDS[kind], dims, vals, 42, bits)
+        return
+    K, ncols, ec, ea, _ = oracle.gen_ell(kind, dims, vals, seed=42, bits=bits)
+    rows = len(ea) // K
+    for R in (1, 2, 4):
+        A = E.EllMatrix.generate(KINDS[kind], dims, vals, 42, bits, flags=E.rows_per_thread(R))
+        i = A.info()
+        assert (i.num_rows, i.num_columns, i.rowsize) == (rows, ncols, K)
+        assert (i.min_col, i.max_col) == (ec.min(), ec.max())
+        c2, a2 = A.download()
+        assert np.array_equal(c2, ec) and bits_equal(a2, ea)
+        A.free()
+    # a shard in the middle
+    lo, hi = rows // 3, (2 * rows) // 3 + 1
+    A = E.EllMatrix.generate(KINDS[kind], dims, vals, 42, bits, row_begin=lo, row_end=hi)
+    c2, a2 = A.download()
+    assert np.array_equal(c2, ec[lo * K:hi * K]) and bits_equal(a2, ea[lo * K:hi * K])
+    A.free()
+
+
+def test_generated_matrix_spmv_vs_oracle(lib, oracle):
+    for kind, dims, vals, bits in [("laplace2d", (300, 211), (4.0, -1.0), 32),
+                                   ("stencil27", (30, 31, 29), (26.0, -1.0), 64),
+                                   ("random", (20000, 20000, 32), (0, 0), 32)]:
+        K, ncols, ec, ea, _ = oracle.gen_ell(kind, dims, vals, bits=bits)
+        rows = len(ea) // K
+        x = np.random.default_rng(1).standard_normal(ncols)
+        want = np.zeros(rows)
+        oracle.ellgemv(rows, want, x, K, ec, ea)
+        A = E.EllMatrix.generate(KINDS[kind], dims, vals, 42, bits)
+        y = np.zeros(rows)
+        A.spmv(y, x, 1, E.ACCUMULATE)
+        A.free()
+        assert bits_equal(y, want), kind
+
+
+def test_full_size_laplacian_properties(lib):
+    """BASELINE config 2 at full size (8192^2 grid, 67M rows): size-independent
+    properties instead of an oracle run.  A*ones is the exact boundary
+    indicator (integer arithmetic in fp64), repeat accumulates linearly, and
+    A*(2x) == 2*(A*x) bit for bit (scaling by 2 is exact)."""
+    import torch
+    n = 8192
+    A = E.EllMatrix.generate(E.GEN_LAPLACE2D, (n, n), (4.0, -1.0), 42, 32)
+    rows = n * n
+    s = torch.cuda.current_stream().cuda_stream
+    x = torch.ones(rows, dtype=torch.float64, device="cuda")
+    y = torch.zeros(rows, dtype=torch.float64, device="cuda")
+    A.spmv_device(y, x, E.ACCUMULATE, s)
+    g = y.view(n, n)
+    want = torch.zeros(n, n, dtype=torch.float64, device="cuda")
+    want[0, :] += 1; want[-1, :] += 1; want[:, 0] += 1; want[:, -1] += 1
+    assert torch.equal(g, want)
+    A.spmv_device(y, x, E.ACCUMULATE, s)
+    A.spmv_device(y, x, E.ACCUMULATE, s)
+    assert torch.equal(g, 3 * want)
+    del want, g
+    gen = torch.Generator(device="cuda").manual_seed(7)
+    xr = torch.randn(rows, dtype=torch.float64, device="cuda", generator=gen)
+    y1 = torch.empty_like(xr)
+    A.spmv_device(y1, xr, E.OVERWRITE, s)
+    xr *= 2
+    A.spmv_device(y, xr, E.OVERWRITE, s)
+    assert torch.equal(y, 2 * y1)
+    # interior row, checked by hand against the 5-point formula in the oracle's order
+    xr /= 2
+    r = 4000 * n + 4000
+    xs = xr[[r - n, r - 1, r, r + 1, r + n]].cpu().numpy()
+    acc = 0.0
+    for v, xv in zip([-1.0, -1.0, 4.0, -1.0, -1.0], xs):
+        acc = acc + v * xv
+    assert y1[r].item() == 0.0 + acc
+    torch.cuda.synchronize()
+    A.free()
