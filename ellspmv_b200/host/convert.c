@@ -1,0 +1,123 @@
+/* convert.c -- see convert.h. */
+#include "convert.h"
+
+#include <errno.h>
+#include <stdlib.h>
+#include <string.h>
+
+void ell_free(struct ell_matrix *ell)
+{
+    free(ell->colidx);
+    free(ell->a);
+    memset(ell, 0, sizeof(*ell));
+}
+
+void csr_free(struct csr_matrix *csr)
+{
+    free(csr->rowptr);
+    free(csr->colidx);
+    free(csr->a);
+    memset(csr, 0, sizeof(*csr));
+}
+
+int ell_from_coo(struct ell_matrix *ell, idx_t num_rows, idx_t num_columns, int64_t num_nonzeros,
+                 const idx_t *rowidx, const idx_t *colidx, const double *a)
+{
+    memset(ell, 0, sizeof(*ell));
+    ell->num_rows = num_rows;
+    ell->num_columns = num_columns;
+    ell->diagsize = num_rows < num_columns ? num_rows : num_columns;
+
+    /* pass 1: entries per row; K is the widest row (ellspmv.c:944-955) */
+    int64_t *fill = calloc((size_t)num_rows + 1, sizeof(*fill));
+    if (!fill) return ENOMEM;
+    int64_t widest = 0;
+    for (int64_t k = 0; k < num_nonzeros; k++) {
+        int64_t n = ++fill[rowidx[k] - 1];
+        if (n > widest) widest = n;
+    }
+    if (widest > IDX_T_MAX || (widest > 0 && (int64_t)num_rows > INT64_MAX / widest)) { free(fill); return EOVERFLOW; }
+    const int64_t K = widest;
+    ell->rowsize = (idx_t)K;
+    ell->ellsize = (int64_t)num_rows * K;
+#if IDX_T_MAX == INT_MAX || (defined(IDXTYPEWIDTH) && IDXTYPEWIDTH == 32)
+    /* the reference computes ellsize and slot offsets in idx_t (Q9); a 32-bit
+     * build cannot address more than 2^31-1 slots, so say so instead of wrapping */
+    if (ell->ellsize > IDX_T_MAX) { free(fill); return EOVERFLOW; }
+#endif
+    size_t n = ell->ellsize > 0 ? (size_t)ell->ellsize : 1;
+    ell->colidx = malloc(n * sizeof(idx_t));
+    ell->a = malloc(n * sizeof(double));
+    if (!ell->colidx || !ell->a) { free(fill); ell_free(ell); return ENOMEM; }
+
+    /* pass 2: scatter in file order (ellspmv.c:1098-1107) */
+    memset(fill, 0, ((size_t)num_rows + 1) * sizeof(*fill));
+    for (int64_t k = 0; k < num_nonzeros; k++) {
+        const int64_t r = (int64_t)rowidx[k] - 1;
+        const int64_t slot = r * K + fill[r]++;
+        ell->colidx[slot] = colidx[k] - 1;
+        ell->a[slot] = a[k];
+    }
+    /* pass 3: padding (ellspmv.c:1111-1117) */
+#ifdef _OPENMP
+#pragma omp parallel for
+#endif
+    for (int64_t r = 0; r < (int64_t)num_rows; r++) {
+        const idx_t padcol = r < (int64_t)num_columns ? (idx_t)r : (idx_t)(num_columns - 1);
+        for (int64_t l = fill[r]; l < K; l++) {
+            ell->colidx[r * K + l] = padcol;
+            ell->a[r * K + l] = 0.0;
+        }
+    }
+    free(fill);
+    return 0;
+}
+
+int csr_from_coo(struct csr_matrix *csr, int symmetric, idx_t num_rows, idx_t num_columns,
+                 int64_t num_nonzeros, const idx_t *rowidx, const idx_t *colidx, const double *a)
+{
+    memset(csr, 0, sizeof(*csr));
+    csr->num_rows = num_rows;
+    csr->num_columns = num_columns;
+    /* symmetric expansion only for square matrices (csrspmv.c:1244) */
+    const int expand = symmetric && num_rows == num_columns;
+    int64_t *rowptr = calloc((size_t)num_rows + 2, sizeof(*rowptr));
+    if (!rowptr) return ENOMEM;
+    /* counts at rowptr[row] with 1-based rows -> after the prefix sum
+     * rowptr[i] is the start of 0-based row i */
+    for (int64_t k = 0; k < num_nonzeros; k++) {
+        rowptr[rowidx[k]]++;
+        if (expand && rowidx[k] != colidx[k]) rowptr[colidx[k]]++;
+    }
+    int64_t lo = num_rows > 0 ? rowptr[1] : 0, hi = 0;
+    for (int64_t i = 1; i <= (int64_t)num_rows; i++) {
+        if (rowptr[i] < lo) lo = rowptr[i];
+        if (rowptr[i] > hi) hi = rowptr[i];
+        rowptr[i] += rowptr[i - 1];
+    }
+    csr->rowsizemin = (idx_t)lo;
+    csr->rowsizemax = (idx_t)hi;
+    csr->csrsize = rowptr[num_rows];
+    size_t n = csr->csrsize > 0 ? (size_t)csr->csrsize : 1;
+    csr->colidx = malloc(n * sizeof(idx_t));
+    csr->a = malloc(n * sizeof(double));
+    if (!csr->colidx || !csr->a) { free(rowptr); csr_free(csr); return ENOMEM; }
+    /* stable placement: entry k goes to the next free slot of its row
+     * (and, when expanding, its mirror image right after it:
+     * csrspmv.c:1421-1425) */
+    for (int64_t k = 0; k < num_nonzeros; k++) {
+        const int64_t i = (int64_t)rowidx[k] - 1, j = (int64_t)colidx[k] - 1;
+        int64_t d = rowptr[i]++;
+        csr->colidx[d] = (idx_t)j;
+        csr->a[d] = a[k];
+        if (expand && i != j) {
+            d = rowptr[j]++;
+            csr->colidx[d] = (idx_t)i;
+            csr->a[d] = a[k];
+        }
+    }
+    for (int64_t i = num_rows; i > 0; i--) rowptr[i] = rowptr[i - 1];
+    rowptr[0] = 0;
+    csr->rowptr = rowptr;
+    return 0;
+}

@@ -1,0 +1,44 @@
+/*
+ * convert.h -- COO -> ELL / CSR conversion of the host programs.
+ *
+ * Produces, bit for bit, the arrays the reference's converters produce on
+ * their default paths (ell_from_coo_size / ell_from_coo, ellspmv.c:931-958,
+ * 1081-1127; csr_from_coo_size / csr_from_coo, csrspmv.c:1219-1267,
+ * 1390-1475): 0-based, row-major ELL with file-order slots and
+ * (min(i, ncols-1), 0.0) padding; CSR sorted by row, file order inside a
+ * row, with symmetric expansion for square symmetric input.
+ */
+#ifndef ELLSPMV_HOST_CONVERT_H
+#define ELLSPMV_HOST_CONVERT_H
+
+#include <stdint.h>
+
+#include "idx.h"
+
+struct ell_matrix {
+    idx_t num_rows, num_columns;
+    idx_t rowsize;      /* K */
+    idx_t diagsize;     /* min(rows, cols): only used by the printed model */
+    int64_t ellsize;    /* rows * K */
+    idx_t *colidx;      /* ellsize */
+    double *a;          /* ellsize */
+};
+
+struct csr_matrix {
+    idx_t num_rows, num_columns;
+    idx_t rowsizemin, rowsizemax;
+    int64_t csrsize;
+    int64_t *rowptr;    /* num_rows + 1 */
+    idx_t *colidx;      /* csrsize */
+    double *a;          /* csrsize */
+};
+
+/* rowidx/colidx are 1-based as read from the file.  Return 0 or errno. */
+int ell_from_coo(struct ell_matrix *ell, idx_t num_rows, idx_t num_columns, int64_t num_nonzeros,
+                 const idx_t *rowidx, const idx_t *colidx, const double *a);
+int csr_from_coo(struct csr_matrix *csr, int symmetric, idx_t num_rows, idx_t num_columns,
+                 int64_t num_nonzeros, const idx_t *rowidx, const idx_t *colidx, const double *a);
+void ell_free(struct ell_matrix *ell);
+void csr_free(struct csr_matrix *csr);
+
+#endif

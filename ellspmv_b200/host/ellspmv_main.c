@@ -1,0 +1,419 @@
+/*
+ * ellspmv_main.c -- host program `ellspmv`: y := A*x + y with A in ELLPACK
+ * format, the multiplication running on a B200 through the C ABI in
+ * include/ellspmv_cuda.h.
+ *
+ * Drop-in for the reference's `ellspmv` program (ellspmv.c:1226-1917): same
+ * positional arguments and options, same Matrix Market reader, same COO->ELL
+ * conversion (bit-exact arrays), same --repeat/--warmup/--verbose timing
+ * lines on stderr and the same result vector on stdout.  The only part that
+ * differs is the call site of the kernel (ellspmv.c:1766-1767, 1841-1842):
+ * instead of every OpenMP thread calling `ellgemv`, the master thread calls
+ *     ellspmv_cuda_upload()   once, after ell_from_coo
+ *     ellspmv_cuda_spmv()     for the warm-up + repeat launches
+ *     ellspmv_cuda_free()
+ *
+ * Known differences, on purpose:
+ *   - --separate-diagonal / --sort-rows are refused: in the reference they
+ *     are passed swapped into ell_from_coo and corrupt the result
+ *     (ellspmv.c:1094-1095 vs 1468-1471);
+ *   - x from a file is read with num_columns entries (the reference reads
+ *     num_rows, ellspmv.c:1574-1575, which is only right for square A);
+ *   - a matrix with more rows than columns works (the reference overruns its
+ *     `ellad` array, ellspmv.c:1447-1467, and aborts);
+ *   - new options for the GPU path (see --help).
+ */
+#include <errno.h>
+#include <float.h>
+#include <locale.h>
+#include <stdbool.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+#include <unistd.h>
+
+#include "../../include/ellspmv_cuda.h"
+#include "convert.h"
+#include "idx.h"
+#include "hostutil.h"
+#include "mtxfile.h"
+
+
+static const char *version = "1.10-b200";
+
+struct options {
+    const char *Apath, *xpath, *ypath;
+    int gzip;
+    bool separate_diagonal, sort_rows;
+    int repeat, warmup, verbose, quiet;
+    /* GPU options */
+    unsigned flags;
+    bool iterate;
+    const char *synthetic;
+    int device;
+};
+
+static void usage(FILE *f) { fprintf(f, "Usage: %s [OPTION..] A [x] [y]\n", prog); }
+
+static void help(FILE *f)
+{
+    usage(f);
+    fprintf(f, "\n");
+    fprintf(f, " Multiply a matrix by a vector on a CUDA device.\n");
+    fprintf(f, "\n");
+    fprintf(f, " The operation performed is ‘y := A*x + y’, where\n");
+    fprintf(f, " ‘A’ is a matrix, and ‘x’ and ‘y’ are vectors.\n");
+    fprintf(f, "\n");
+    fprintf(f, " Positional arguments are:\n");
+    fprintf(f, "  A    path to Matrix Market file for the matrix A\n");
+    fprintf(f, "  x    optional path to Matrix Market file for the vector x\n");
+    fprintf(f, "  y    optional path for to Matrix Market file for the vector y\n");
+    fprintf(f, "\n");
+    fprintf(f, " Other options are:\n");
+#ifdef HAVE_LIBZ
+    fprintf(f, "  -z, --gzip, --gunzip, --ungzip    filter files through gzip\n");
+#endif
+    fprintf(f, "  --separate-diagonal  (refused: broken in the reference, see source)\n");
+    fprintf(f, "  --sort-rows          (refused: broken in the reference, see source)\n");
+    fprintf(f, "  --repeat=N           repeat matrix-vector multiplication N times\n");
+    fprintf(f, "  --warmup=N                perform N additional warmup iterations\n");
+    fprintf(f, "  -q, --quiet          do not print Matrix Market output\n");
+    fprintf(f, "  -v, --verbose        be more verbose\n");
+    fprintf(f, "\n");
+    fprintf(f, " Options for the CUDA path are:\n");
+    fprintf(f, "  --kernel=thread|warp thread-per-row (bit-exact, default) or sub-warp-per-row\n");
+    fprintf(f, "  --fma                allow fused multiply-add (tolerance mode)\n");
+    fprintf(f, "  --rows-per-thread=N  1, 2 or 4 rows per thread [4]\n");
+    fprintf(f, "  --l2-persist-x       L2 persisting access window over x\n");
+    fprintf(f, "  --narrow-index       keep 64-bit column indices as 32-bit on the device\n");
+    fprintf(f, "  --iterate            compute x := A*x repeatedly (y := A^N x); square A only\n");
+    fprintf(f, "  --synthetic=SPEC     build A on the device instead of reading a file:\n");
+    fprintf(f, "                       laplace2d:NX,NY | stencil27:NX,NY,NZ | random:ROWS,COLS,K[,SEED]\n");
+    fprintf(f, "  --device=N           CUDA device ordinal [current]\n");
+    fprintf(f, "\n");
+    fprintf(f, "  -h, --help           display this help and exit\n");
+    fprintf(f, "  --version            display version information and exit\n");
+}
+
+static void print_version(FILE *f)
+{
+    fprintf(f, "%s %s\n", prog, version);
+    fprintf(f, "row/column offsets: %d-bit\n", IDX_BITS);
+#ifdef HAVE_LIBZ
+    fprintf(f, "zlib: yes\n");
+#else
+    fprintf(f, "zlib: no\n");
+#endif
+    int n = 0;
+    ellspmv_cuda_device_count(&n);
+    fprintf(f, "CUDA: libellspmv_cuda %d.%02d, %d device(s)\n", ellspmv_cuda_version() / 100,
+            ellspmv_cuda_version() % 100, n);
+}
+
+/* returns 0, or errno with *bad set to the offending argument index */
+static int parse_options(int argc, char **argv, struct options *o, int *bad)
+{
+    memset(o, 0, sizeof(*o));
+    o->repeat = 1;
+    o->device = -1;
+    int npos = 0;
+    bool only_positional = false;
+    for (int i = 1; i < argc; i++) {
+        *bad = i;
+        const char *a = argv[i], *v;
+        if (!only_positional) {
+            if (!strcmp(a, "--separate-diagonal")) { o->separate_diagonal = true; continue; }
+            if (!strcmp(a, "--sort-rows")) { o->sort_rows = true; continue; }
+            if (!strncmp(a, "--repeat", 8) && (a[8] == '=' || a[8] == '\0')) {
+                if (!(v = optval(argc, argv, &i, "--repeat"))) return EINVAL;
+                int err = to_int(v, &o->repeat);
+                if (err) return err;
+                continue;
+            }
+            if (!strncmp(a, "--warmup", 8) && (a[8] == '=' || a[8] == '\0')) {
+                if (!(v = optval(argc, argv, &i, "--warmup"))) return EINVAL;
+                if (to_int(v, &o->warmup)) return EINVAL;
+                continue;
+            }
+#ifdef HAVE_LIBZ
+            if (!strcmp(a, "-z") || !strcmp(a, "--gzip") || !strcmp(a, "--gunzip") || !strcmp(a, "--ungzip")) {
+                o->gzip = 1; continue;
+            }
+#endif
+            if (!strcmp(a, "-q") || !strcmp(a, "--quiet")) { o->quiet = 1; continue; }
+            if (!strcmp(a, "-v") || !strcmp(a, "--verbose")) { o->verbose++; continue; }
+            if (!strncmp(a, "--kernel", 8) && (a[8] == '=' || a[8] == '\0')) {
+                if (!(v = optval(argc, argv, &i, "--kernel"))) return EINVAL;
+                o->flags &= ~(unsigned)ELLSPMV_CUDA_KERNEL_MASK;
+                if (!strcmp(v, "thread")) o->flags |= ELLSPMV_CUDA_KERNEL_THREAD;
+                else if (!strcmp(v, "warp")) o->flags |= ELLSPMV_CUDA_KERNEL_WARP;
+                else if (strcmp(v, "auto")) return EINVAL;
+                continue;
+            }
+            if (!strcmp(a, "--fma")) { o->flags |= ELLSPMV_CUDA_FMA; continue; }
+            if (!strcmp(a, "--l2-persist-x")) { o->flags |= ELLSPMV_CUDA_L2_PERSIST_X; continue; }
+            if (!strcmp(a, "--narrow-index")) { o->flags |= ELLSPMV_CUDA_NARROW_INDEX; continue; }
+            if (!strncmp(a, "--rows-per-thread", 17) && (a[17] == '=' || a[17] == '\0')) {
+                int r;
+                if (!(v = optval(argc, argv, &i, "--rows-per-thread")) || to_int(v, &r)) return EINVAL;
+                if (r != 1 && r != 2 && r != 4) return EINVAL;
+                o->flags = (o->flags & ~(unsigned)ELLSPMV_CUDA_ROWS_PER_THREAD_MASK) |
+                           ((unsigned)r << ELLSPMV_CUDA_ROWS_PER_THREAD_SHIFT);
+                continue;
+            }
+            if (!strcmp(a, "--iterate")) { o->iterate = true; continue; }
+            if (!strncmp(a, "--synthetic", 11) && (a[11] == '=' || a[11] == '\0')) {
+                if (!(o->synthetic = optval(argc, argv, &i, "--synthetic"))) return EINVAL;
+                continue;
+            }
+            if (!strncmp(a, "--device", 8) && (a[8] == '=' || a[8] == '\0')) {
+                if (!(v = optval(argc, argv, &i, "--device")) || to_int(v, &o->device)) return EINVAL;
+                continue;
+            }
+            if (!strcmp(a, "-h") || !strcmp(a, "--help")) { help(stdout); exit(EXIT_SUCCESS); }
+            if (!strcmp(a, "--version")) { print_version(stdout); exit(EXIT_SUCCESS); }
+            if (!strcmp(a, "--")) { only_positional = true; continue; }
+        }
+        if (npos == 0) o->Apath = a;
+        else if (npos == 1) o->xpath = a;
+        else if (npos == 2) o->ypath = a;
+        else return EINVAL;
+        npos++;
+    }
+    if (o->synthetic && npos > 0) {
+        /* with --synthetic the positionals are [x] [y] */
+        o->ypath = o->xpath; o->xpath = o->Apath; o->Apath = NULL;
+        if (npos > 2) return EINVAL;
+    } else if (npos < 1 && !o->synthetic) {
+        usage(stdout);
+        exit(EXIT_FAILURE);
+    }
+    return 0;
+}
+
+static int parse_synthetic(const char *spec, int *kind, int64_t dims[3], double vals[2], uint64_t *seed)
+{
+    char name[32];
+    long long d[4] = {0, 0, 0, 42};
+    const char *colon = strchr(spec, ':');
+    if (!colon || (size_t)(colon - spec) >= sizeof(name)) return EINVAL;
+    memcpy(name, spec, (size_t)(colon - spec));
+    name[colon - spec] = '\0';
+    int n = sscanf(colon + 1, "%lld,%lld,%lld,%lld", &d[0], &d[1], &d[2], &d[3]);
+    *seed = 42;
+    if (!strcmp(name, "laplace2d") && n == 2) { *kind = ELLSPMV_CUDA_GEN_LAPLACE2D; vals[0] = 4.0; vals[1] = -1.0; }
+    else if (!strcmp(name, "stencil27") && n == 3) { *kind = ELLSPMV_CUDA_GEN_STENCIL27; vals[0] = 26.0; vals[1] = -1.0; }
+    else if (!strcmp(name, "stencil27s") && n == 3) { *kind = ELLSPMV_CUDA_GEN_STENCIL27; vals[0] = 0.5; vals[1] = -1.0 / 52.0; }
+    else if (!strcmp(name, "random") && n >= 3) { *kind = ELLSPMV_CUDA_GEN_RANDOM; if (n == 4) *seed = (uint64_t)d[3]; }
+    else return EINVAL;
+    dims[0] = d[0]; dims[1] = d[1]; dims[2] = d[2];
+    return 0;
+}
+
+int main(int argc, char *argv[])
+{
+    struct timespec t0, t1;
+    setlocale(LC_ALL, "");
+    const char *slash = strrchr(argv[0], '/');
+    prog = slash ? slash + 1 : argv[0];
+
+    struct options o;
+    int bad = 0;
+    int err = parse_options(argc, argv, &o, &bad);
+    if (err) {
+        fprintf(stderr, "%s: %s %s\n", prog, strerror(err), bad < argc ? argv[bad] : "");
+        return EXIT_FAILURE;
+    }
+    if (o.separate_diagonal || o.sort_rows) {
+        fprintf(stderr, "%s: --separate-diagonal/--sort-rows are not supported: the reference passes them "
+                        "swapped into ell_from_coo and computes a wrong result\n", prog);
+        return EXIT_FAILURE;
+    }
+
+    ellspmv_cuda_matrix *A = NULL;
+    idx_t num_rows = 0, num_columns = 0, rowsize = 0, diagsize = 0;
+    int64_t num_nonzeros = 0, ellsize = 0;
+
+    if (o.synthetic) {
+        /* build the matrix on the device (shapes too large for a text file) */
+        int kind = 0;
+        int64_t dims[3];
+        double vals[2] = {0, 0};
+        uint64_t seed;
+        if (parse_synthetic(o.synthetic, &kind, dims, vals, &seed)) {
+            fprintf(stderr, "%s: %s --synthetic=%s\n", prog, strerror(EINVAL), o.synthetic);
+            return EXIT_FAILURE;
+        }
+        if (o.verbose > 0) { fprintf(stderr, "cuda_generate: "); clock_gettime(CLOCK_MONOTONIC, &t0); }
+        err = ellspmv_cuda_generate(&A, kind, dims, vals, seed, IDX_BITS, 0, -1, o.device, o.flags);
+        if (err) {
+            if (o.verbose > 0) fprintf(stderr, "\n");
+            fprintf(stderr, "%s: %s (%s)\n", prog, strerror(err), ellspmv_cuda_last_error());
+            return EXIT_FAILURE;
+        }
+        ellspmv_cuda_info info;
+        ellspmv_cuda_get_info(A, &info);
+        num_rows = (idx_t)info.num_rows;
+        num_columns = (idx_t)info.num_columns;
+        rowsize = (idx_t)info.rowsize;
+        ellsize = info.num_rows * info.rowsize;
+        diagsize = num_rows < num_columns ? num_rows : num_columns;
+        num_nonzeros = ellsize;
+        if (o.verbose > 0) {
+            clock_gettime(CLOCK_MONOTONIC, &t1);
+            fprintf(stderr, "%'.6f seconds, %'" PRIdx " rows, %'" PRId64 " nonzeros, %'" PRIdx " nonzeros per row\n",
+                    seconds_between(t0, t1), num_rows, ellsize + num_rows, rowsize);
+        }
+    } else {
+        /* 2. read the matrix (ellspmv.c:1264-1377) */
+        if (o.verbose > 0) { fprintf(stderr, "mtxfile_read: "); clock_gettime(CLOCK_MONOTONIC, &t0); }
+        struct mtx_stream *s = mtx_open(o.Apath, o.gzip);
+        if (!s) { fprintf(stderr, "%s: %s: %s\n", prog, o.Apath, strerror(errno)); return EXIT_FAILURE; }
+        struct mtx_header h;
+        int64_t lines = 0, bytes = 0;
+        err = mtx_read_header(s, &h, &lines, &bytes);
+        if (!err && !(h.object == MTX_MATRIX && h.format == MTX_COORDINATE)) err = EINVAL;
+        if (err) {
+            if (o.verbose > 0) fprintf(stderr, "\n");
+            fprintf(stderr, "%s: %s:%" PRId64 ": %s\n", prog, o.Apath, lines + 1, strerror(err));
+            mtx_close(s);
+            return EXIT_FAILURE;
+        }
+        num_rows = h.num_rows; num_columns = h.num_columns; num_nonzeros = h.num_nonzeros;
+        size_t nz = num_nonzeros > 0 ? (size_t)num_nonzeros : 1;
+        idx_t *rowidx = malloc(nz * sizeof(idx_t));
+        idx_t *colidx = malloc(nz * sizeof(idx_t));
+        double *a = malloc(nz * sizeof(double));
+        if (!rowidx || !colidx || !a) {
+            if (o.verbose > 0) fprintf(stderr, "\n");
+            fprintf(stderr, "%s: %s\n", prog, strerror(ENOMEM));
+            return EXIT_FAILURE;
+        }
+        err = mtx_read_coordinate(s, &h, rowidx, colidx, a, &lines, &bytes);
+        if (err) {
+            if (o.verbose > 0) fprintf(stderr, "\n");
+            fprintf(stderr, "%s: %s:%" PRId64 ": %s\n", prog, o.Apath, lines + 1, strerror(err));
+            mtx_close(s);
+            return EXIT_FAILURE;
+        }
+        if (o.verbose > 0) {
+            clock_gettime(CLOCK_MONOTONIC, &t1);
+            fprintf(stderr, "%'.6f seconds (%'.1f MB/s)\n", seconds_between(t0, t1),
+                    1.0e-6 * (double)bytes / seconds_between(t0, t1));
+        }
+        mtx_close(s);
+
+        /* 3. convert to ELLPACK (ellspmv.c:1379-1486) */
+        if (o.verbose > 0) { fprintf(stderr, "ell_from_coo: "); clock_gettime(CLOCK_MONOTONIC, &t0); }
+        struct ell_matrix ell;
+        err = ell_from_coo(&ell, num_rows, num_columns, num_nonzeros, rowidx, colidx, a);
+        free(a); free(colidx); free(rowidx);
+        if (err) {
+            if (o.verbose > 0) fprintf(stderr, "\n");
+            fprintf(stderr, "%s: %s\n", prog, strerror(err));
+            return EXIT_FAILURE;
+        }
+        rowsize = ell.rowsize; ellsize = ell.ellsize; diagsize = ell.diagsize;
+        if (o.verbose > 0) {
+            clock_gettime(CLOCK_MONOTONIC, &t1);
+            fprintf(stderr, "%'.6f seconds, %'" PRIdx " rows, %'" PRId64 " nonzeros, %'" PRIdx " nonzeros per row\n",
+                    seconds_between(t0, t1), num_rows, ellsize + num_rows, rowsize);
+        }
+
+        /* device copy + re-layout: the one step the reference does not have */
+        if (o.verbose > 0) { fprintf(stderr, "cuda_upload: "); clock_gettime(CLOCK_MONOTONIC, &t0); }
+        if (o.device >= 0)
+            err = ellspmv_cuda_upload_shard(&A, IDX_BITS, num_rows, num_columns, rowsize, 0, num_rows,
+                                            ell.colidx, ell.a, o.device, o.flags);
+        else
+            err = ellspmv_cuda_upload(&A, IDX_BITS, num_rows, num_columns, rowsize, ell.colidx, ell.a, 1, o.flags);
+        ell_free(&ell);
+        if (err) {
+            if (o.verbose > 0) fprintf(stderr, "\n");
+            fprintf(stderr, "%s: %s (%s)\n", prog, strerror(err), ellspmv_cuda_last_error());
+            return EXIT_FAILURE;
+        }
+        if (o.verbose > 0) {
+            ellspmv_cuda_info info;
+            ellspmv_cuda_get_info(A, &info);
+            clock_gettime(CLOCK_MONOTONIC, &t1);
+            fprintf(stderr, "%'.6f seconds, device %d, %'" PRId64 " bytes, sliced ELL %d rows/slice, "
+                            "%d rows/thread, %d-bit indices\n",
+                    seconds_between(t0, t1), info.device, info.device_bytes, info.slice_rows,
+                    info.rows_per_thread, info.dev_idx_bits);
+        }
+    }
+
+    /* 4. vectors (ellspmv.c:1488-1702), in pinned memory so the copies run at PCIe rate */
+    double *x = NULL, *y = NULL;
+    if (ellspmv_cuda_malloc_host((void **)&x, (int64_t)(num_columns > 0 ? num_columns : 1) * 8) ||
+        ellspmv_cuda_malloc_host((void **)&y, (int64_t)(num_rows > 0 ? num_rows : 1) * 8)) {
+        fprintf(stderr, "%s: %s (%s)\n", prog, strerror(ENOMEM), ellspmv_cuda_last_error());
+        ellspmv_cuda_free(A);
+        return EXIT_FAILURE;
+    }
+    for (idx_t j = 0; j < num_columns; j++) x[j] = 1.0;
+    for (idx_t i = 0; i < num_rows; i++) y[i] = 0.0;
+    if (o.xpath && read_vector_file(o.xpath, o.gzip, num_columns, x, o.verbose)) goto fail;
+    if (o.ypath && read_vector_file(o.ypath, o.gzip, num_rows, y, o.verbose)) goto fail;
+
+    /* 5. warm-up and timed multiplications (ellspmv.c:1745-1876): y keeps
+     * accumulating across all of them, x stays fixed */
+    {
+        const int total = (o.warmup > 0 ? o.warmup : 0) + (o.repeat > 0 ? o.repeat : 0);
+        double *secs = calloc((size_t)(total > 0 ? total : 1), sizeof(double));
+        if (!secs) { fprintf(stderr, "%s: %s\n", prog, strerror(ENOMEM)); goto fail; }
+        err = ellspmv_cuda_spmv(A, y, x, total, o.iterate ? ELLSPMV_CUDA_ITERATE : ELLSPMV_CUDA_ACCUMULATE, secs);
+        if (err) {
+            fprintf(stderr, "%s: %s (%s)\n", prog, strerror(err), ellspmv_cuda_last_error());
+            free(secs);
+            goto fail;
+        }
+        if (o.verbose > 0) {
+            /* the reference's throughput model, padding and diagsize included (ellspmv.c:1857-1862) */
+            const int64_t num_flops = 2 * (ellsize + diagsize);
+            const int64_t min_bytes = (int64_t)num_rows * 8 + (int64_t)num_columns * 8 +
+                                      ellsize * (int64_t)sizeof(idx_t) + ellsize * 8 + (int64_t)diagsize * 8;
+            const int64_t max_bytes = (int64_t)num_rows * 8 + ellsize * 8 + ellsize * (int64_t)sizeof(idx_t) +
+                                      ellsize * 8 + (int64_t)diagsize * 8 + (int64_t)diagsize * 8;
+            double best = 0.0;
+            for (int r = 0; r < total; r++) {
+                const double t = secs[r];
+                fprintf(stderr, r < o.warmup ? "gemv (warmup): " : "gemv: ");
+                fprintf(stderr, "%'.6f seconds (%'.3f Gnz/s, %'.3f Gflop/s, %'.1f to %'.1f GB/s)\n", t,
+                        (double)num_nonzeros * 1e-9 / t, (double)num_flops * 1e-9 / t,
+                        (double)min_bytes * 1e-9 / t, (double)max_bytes * 1e-9 / t);
+                if (r >= o.warmup && (best == 0.0 || t < best)) best = t;
+            }
+            if (best > 0.0) {
+                /* effective-bytes roofline (values + indices + x + y read and written) */
+                const double eff = (double)ellsize * (8.0 + sizeof(idx_t)) + 8.0 * num_columns + 16.0 * num_rows;
+                fprintf(stderr, "cuda: best %'.6f seconds, %'.1f Gflop/s, %'.1f GB/s effective "
+                                "(values+indices+x+y), device-event time per launch\n",
+                        best, 2.0 * (double)ellsize * 1e-9 / best, eff * 1e-9 / best);
+            }
+        }
+        free(secs);
+    }
+
+    /* 6. result vector (ellspmv.c:1898-1912) */
+    if (!o.quiet) {
+        if (o.verbose > 0) { fprintf(stderr, "mtxfile_write:\n"); clock_gettime(CLOCK_MONOTONIC, &t0); }
+        mtx_write_vector(stdout, num_rows, y);
+        if (o.verbose > 0) {
+            clock_gettime(CLOCK_MONOTONIC, &t1);
+            fprintf(stderr, "mtxfile_write done in %'.6f seconds\n", seconds_between(t0, t1));
+        }
+    }
+    ellspmv_cuda_free_host(x);
+    ellspmv_cuda_free_host(y);
+    ellspmv_cuda_free(A);
+    return EXIT_SUCCESS;
+
+fail:
+    ellspmv_cuda_free_host(x);
+    ellspmv_cuda_free_host(y);
+    ellspmv_cuda_free(A);
+    return EXIT_FAILURE;
+}

@@ -142,7 +142,7 @@ def test_edge_cases(lib, oracle):
     assert bits_equal(y, want)
     A.free()
     # inf / nan propagate like on the CPU (0 * inf = nan in a padded slot)
-    ec = np.array([0, 1, 1, 1], dtype=np.int32)
+    ec = np.array([0, 1, 1, 0], dtype=np.int32)
     ea = np.array([1.0, 0.0, 2.0, 0.0])
     x = np.array([1.0, np.inf])
     want = np.zeros(2)

@@ -1,0 +1,136 @@
+"""Host side of the drop-in (no GPU needed): the Matrix Market reader and the
+COO->ELL / COO->CSR converters of the host programs reproduce the reference's
+arrays bit for bit (golden vectors), and the reader is as strict as the
+reference's (ellspmv.c:707-888)."""
+import errno
+import gzip
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import hostlib
+from conftest import GOLDEN_CASES, bits_equal, load_golden, unhex
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+@pytest.mark.parametrize("bits", [32, 64])
+def test_host_ell_arrays_match_reference(tmp_path, name, bits):
+    g = load_golden(name)
+    e = g[f"idx{bits}"]
+    p = str(tmp_path / "A.mtx")
+    hostlib.write_mtx(p, g["num_rows"], g["num_columns"], g["rowidx"], g["colidx"], unhex(g["a"]))
+    err, dims, ec, ea = hostlib.ell_from_file(bits, p)
+    assert err == 0
+    assert dims[:6] == [g["num_rows"], g["num_columns"], len(g["a"]), e["rowsize"], e["ellsize"], e["diagsize"]]
+    assert ec.tolist() == e["ellcolidx"] and bits_equal(ea, unhex(e["ella"]))
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+@pytest.mark.parametrize("bits", [32, 64])
+def test_host_csr_arrays_match_reference(tmp_path, name, bits):
+    g = load_golden(name)
+    e = g[f"idx{bits}"]
+    p = str(tmp_path / "A.mtx")
+    hostlib.write_mtx(p, g["num_rows"], g["num_columns"], g["rowidx"], g["colidx"], unhex(g["a"]))
+    err, dims, rowptr, cc, ca = hostlib.csr_from_file(bits, p)
+    assert err == 0
+    assert dims[3:6] == [len(e["csrcolidx"]), e["rowsizemin"], e["rowsizemax"]]
+    assert rowptr.tolist() == e["rowptr"] and cc.tolist() == e["csrcolidx"] and bits_equal(ca, unhex(e["csra"]))
+
+
+def test_symmetric_expansion_matches_reference_csr(tmp_path):
+    """csrspmv expands square symmetric input (csrspmv.c:1420-1427); checked
+    against the unmodified reference when oracle/_ref is there."""
+    from oracle.pyoracle import Reference
+    if not Reference.available("csr", 32):
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(9)
+    n, nnz = 30, 120
+    ri = rng.integers(1, n + 1, nnz)
+    ci = rng.integers(1, n + 1, nnz)
+    lo = ri >= ci
+    ri, ci = ri[lo], ci[lo]
+    a = rng.standard_normal(len(ri))
+    p = str(tmp_path / "S.mtx")
+    hostlib.write_mtx(p, n, n, ri.tolist(), ci.tolist(), a, symmetry="symmetric")
+    for bits in (32, 64):
+        dt = np.int32 if bits == 32 else np.int64
+        rowptr, cc, ca, lo_, hi_ = Reference("csr", bits).csr_from_coo(n, n, ri.astype(dt), ci.astype(dt), a, symmetric=True)
+        err, dims, rp2, cc2, ca2 = hostlib.csr_from_file(bits, p)
+        assert err == 0 and dims[4:6] == [lo_, hi_]
+        assert np.array_equal(rowptr, rp2) and np.array_equal(cc, cc2) and bits_equal(ca, ca2)
+        # the ELL program never expands symmetry (Q5): K counts the stored triangle only
+        err, d2, ec, ea = hostlib.ell_from_file(bits, p)
+        assert err == 0 and d2[4] == n * d2[3] and np.count_nonzero(ea) <= len(a)
+
+
+def test_fields_gzip_and_comments(tmp_path):
+    ri, ci, a = [1, 2, 2], [2, 1, 3], [3.0, -4.0, 5.0]
+    p = str(tmp_path / "I.mtx")
+    hostlib.write_mtx(p, 2, 3, ri, ci, a, field="integer", comments=("%c1", "% c2", "%"))
+    err, dims, ec, ea = hostlib.ell_from_file(32, p)
+    assert err == 0 and ea.tolist() == [3.0, 0.0, -4.0, 5.0] and ec.tolist() == [1, 0, 0, 2]
+    hostlib.write_mtx(p, 2, 3, ri, ci, a, field="pattern")
+    err, dims, ec, ea = hostlib.ell_from_file(64, p)
+    assert err == 0 and ea.tolist() == [1.0, 0.0, 1.0, 1.0]
+    with open(p, "rb") as f, gzip.open(p + ".gz", "wb") as z:
+        z.write(f.read())
+    err, dims, ec2, ea2 = hostlib.ell_from_file(64, p + ".gz", gzip=1)
+    assert err == 0 and np.array_equal(ec, ec2) and bits_equal(ea, ea2)
+
+
+BAD = {
+    "no banner": ("%MatrixMarket matrix coordinate real general\n1 1 1\n1 1 1.0\n", errno.EINVAL, 1),
+    "double space": ("%%MatrixMarket matrix  coordinate real general\n1 1 1\n1 1 1.0\n", errno.EINVAL, 1),
+    "array matrix": ("%%MatrixMarket matrix array real general\n1 1\n1.0\n", errno.EINVAL, 2),
+    "complex": ("%%MatrixMarket matrix coordinate complex general\n1 1 1\n1 1 1.0 0\n", errno.EINVAL, 1),
+    "size line": ("%%MatrixMarket matrix coordinate real general\n2 2\n1 1 1.0\n", errno.EINVAL, 2),
+    "tab separator": ("%%MatrixMarket matrix coordinate real general\n2 2 1\n1\t1 1.0\n", errno.EINVAL, 3),
+    "missing value": ("%%MatrixMarket matrix coordinate real general\n2 2 1\n1 1\n", errno.EINVAL, 3),
+    "row out of range": ("%%MatrixMarket matrix coordinate real general\n2 2 1\n3 1 1.0\n", errno.EINVAL, 3),
+    "col zero": ("%%MatrixMarket matrix coordinate real general\n2 2 1\n1 0 1.0\n", errno.EINVAL, 3),
+    "truncated": ("%%MatrixMarket matrix coordinate real general\n2 2 2\n1 1 1.0\n", -1, 4),
+    "long line": ("%%MatrixMarket matrix coordinate real general\n%" + "x" * 5000 + "\n1 1 1\n1 1 1.0\n", errno.EOVERFLOW, 2),
+}
+
+
+@pytest.mark.parametrize("case", sorted(BAD))
+def test_reader_rejects_what_the_reference_rejects(tmp_path, case):
+    text, want, line = BAD[case]
+    p = str(tmp_path / "bad.mtx")
+    with open(p, "w") as f:
+        f.write(text)
+    err, dims, _, _ = hostlib.ell_from_file(32, p)
+    assert err == want if want != -1 else err in (-1, 2 ** 32 - 1)
+    assert dims[6] + 1 == line          # "path:line:" the programs print
+
+
+def test_index_width_limits(tmp_path):
+    p = str(tmp_path / "big.mtx")
+    with open(p, "w") as f:
+        f.write("%%MatrixMarket matrix coordinate real general\n2 3000000000 1\n2 3000000000 2.5\n")
+    err, _, _, _ = hostlib.ell_from_file(32, p)
+    assert err == errno.ERANGE          # does not fit a 32-bit idx_t, like parse_int32_t (ellspmv.c:384-396)
+    err, dims, ec, ea = hostlib.ell_from_file(64, p)
+    assert err == 0 and dims[1] == 3000000000 and ec.tolist() == [0, 2999999999] and ea.tolist() == [0.0, 2.5]
+
+
+def test_programs_fail_loudly_without_a_gpu(tmp_path):
+    import ellspmv_b200 as E
+    if E.device_count() > 0:
+        pytest.skip("has a GPU")
+    hostlib.build_host()
+    g = load_golden("test_mtx")
+    p = str(tmp_path / "A.mtx")
+    hostlib.write_mtx(p, g["num_rows"], g["num_columns"], g["rowidx"], g["colidx"], unhex(g["a"]))
+    for prog in ("ellspmv", "ellspmv64", "csrspmv", "csrspmv64"):
+        r = subprocess.run([os.path.join(hostlib.BIN, prog), p], capture_output=True, text=True)
+        assert r.returncode == 1 and r.stdout == "" and "No such device" in r.stderr
+    r = subprocess.run([os.path.join(hostlib.BIN, "ellspmv"), "--help"], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.startswith("Usage: ellspmv [OPTION..] A [x] [y]")
+    r = subprocess.run([os.path.join(hostlib.BIN, "ellspmv")], capture_output=True, text=True)
+    assert r.returncode == 1 and r.stdout.startswith("Usage:")
+    r = subprocess.run([os.path.join(hostlib.BIN, "ellspmv"), "--repeat=x", p], capture_output=True, text=True)
+    assert r.returncode == 1 and "--repeat=x" in r.stderr
