@@ -110,7 +110,11 @@ int configure(ellspmv_cuda_matrix *A, unsigned flags)
 {
     A->flags = flags;
     int R = (flags & ELLSPMV_CUDA_ROWS_PER_THREAD_MASK) >> ELLSPMV_CUDA_ROWS_PER_THREAD_SHIFT;
-    if (R == 0) R = 4;   // 256-bit value loads + 128-bit (idx32) / 256-bit (idx64) index loads
+    // auto: 2 rows per thread = 128-bit value loads and 64-bit (idx32) / 128-bit
+    // (idx64) index loads.  Measured on B200 (profiles/r1_sweep.md): R=1/2/4 are
+    // within 3% of each other on every BASELINE shape, R=2 is best or second
+    // best on all of them; 256-bit loads (R=4) buy nothing on an HBM-bound stream.
+    if (R == 0) R = 2;
     if (R != 1 && R != 2 && R != 4) ELL_FAIL(EINVAL, "rows per thread must be 1, 2 or 4 (got %d)", R);
     int kernel = flags & ELLSPMV_CUDA_KERNEL_MASK;
     if (kernel == ELLSPMV_CUDA_KERNEL_AUTO) kernel = ELLSPMV_CUDA_KERNEL_THREAD;
