@@ -30,7 +30,7 @@ def oracle_stdout(oracle, g, bits, passes):
     for _ in range(passes):
         oracle.ellgemv(g["num_rows"], y, np.ones(g["num_columns"]), e["rowsize"],
                        np.array(e["ellcolidx"], dtype=dt), unhex(e["ella"]))
-    return "%%MatrixMarket vector array real general\n%d\n" % len(y) + "".join("%.15g\n" % v for v in y)
+    return "%%MatrixMarket vector array real general\n" + f"{len(y)}\n" + "".join("%.15g\n" % v for v in y)
 
 
 @pytest.mark.parametrize("name", GOLDEN_CASES)
