@@ -38,6 +38,19 @@ if ROOT not in sys.path:
 GRID = 8192                      # per-GPU grid is GRID x GRID
 K_LAPLACE = 5
 IDX_BYTES = 4
+
+# name -> (generator kind, K, index bits, (centre, off) for accumulate / iterate, dims(world), scaling)
+# iterate values have row sums of 1 (|A|_inf = 1), so x stays O(1) over any number of y -> x steps
+WORKLOADS = {
+    # BASELINE config 2, the headline: 8192x8192 grid per GPU, grid grows along x with N (weak)
+    "laplace2d": ("laplace2d", 5, 32, (4.0, -1.0), (0.5, 0.125), lambda w: (GRID * w, GRID), "weak"),
+    # BASELINE config 3: 384^3 per GPU, IDXTYPEWIDTH=64 (weak along x)
+    "stencil27_384": ("stencil27", 27, 64, (26.0, -1.0), (0.5, 1.0 / 52), lambda w: (384 * w, 384, 384), "weak"),
+    # BASELINE config 5: 768^3 fixed, row-sharded over N >= 2 GPUs (strong), y -> x
+    "stencil27_768": ("stencil27", 27, 64, (26.0, -1.0), (0.5, 1.0 / 52), lambda w: (768, 768, 768), "strong"),
+    # BASELINE config 4: random 50M x 32 (N = 1)
+    "random50m": ("random", 32, 32, (0.0, 0.0), (0.0, 0.0), lambda w: (50_000_000 * w, 50_000_000 * w, 32), "weak"),
+}
 FALLBACK_HBM_GBS = 6650.0        # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
 
 
@@ -237,12 +250,16 @@ def main_ours(args, rank: int, local_rank: int, world: int):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
-    rows = GRID * GRID                       # per GPU
-    nx_global = GRID * world
-    global_rows = rows * world
+    from ellspmv_b200.sharded import partition_rows
+    kind_name, K, idx_bits, vals_acc, vals_it, dims_of, scaling = WORKLOADS[args.workload]
+    kind = {"laplace2d": E.GEN_LAPLACE2D, "stencil27": E.GEN_STENCIL27, "random": E.GEN_RANDOM}[kind_name]
+    dims = dims_of(world)
+    global_rows = dims[0] if kind_name == "random" else int(np.prod(dims))
+    row_lo, row_hi = partition_rows(global_rows, world)[rank]
+    rows = row_hi - row_lo                   # this GPU's rows
     flags = args.flags
-    A = E.EllMatrix.generate(E.GEN_LAPLACE2D, (nx_global, GRID), (4.0, -1.0), 42, 32,
-                             row_begin=rank * rows, row_end=(rank + 1) * rows, device=local_rank, flags=flags)
+    A = E.EllMatrix.generate(kind, dims, vals_acc if world == 1 else vals_it, 42, idx_bits,
+                             row_begin=row_lo, row_end=row_hi, device=local_rank, flags=flags)
     info = A.info()
     stream = torch.cuda.current_stream()
     sptr = stream.cuda_stream
@@ -257,7 +274,7 @@ def main_ours(args, rank: int, local_rank: int, world: int):
 
     if world == 1:
         gen = torch.Generator(device=dev).manual_seed(1234)
-        x = torch.randn(global_rows, dtype=torch.float64, device=dev, generator=gen)
+        x = torch.randn(int(info.num_columns), dtype=torch.float64, device=dev, generator=gen)
         y = torch.zeros(rows, dtype=torch.float64, device=dev)
         mode_name = "accumulate (y += A*x, the reference's ellgemv semantics)"
 
@@ -267,7 +284,7 @@ def main_ours(args, rank: int, local_rank: int, world: int):
         y_rmw = True
     else:
         from ellspmv_b200.sharded import ShardedIterate
-        sharded = ShardedIterate(A, rank, world, exchange=args.exchange)
+        sharded = ShardedIterate(A, rank, world, exchange=args.exchange, barrier=args.barrier)
         sharded.set_x(lambda lo, hi: torch.ones(hi - lo, dtype=torch.float64, device=dev))
         mode_name = f"iterate (x <- A*x, exchange={sharded.exchange})"
 
@@ -295,13 +312,15 @@ def main_ours(args, rank: int, local_rank: int, world: int):
     launches = A.info().launches - launches_before - 0
     timed_launches = args.steps
 
-    flops_step = 2.0 * global_rows * K_LAPLACE
+    flops_step = 2.0 * global_rows * K
     value = flops_step / (ms_per_step * 1e-3) * 1e-9
-    bytes_launch = algorithmic_bytes(rows, rows if world == 1 else rows + 2 * GRID, K_LAPLACE, IDX_BYTES, y_rmw)
-    bytes_min = algorithmic_bytes(rows, rows, K_LAPLACE, IDX_BYTES, False)
+    # x entries this GPU's launch touches: the column range its rows reference
+    x_touched = int(info.max_col - info.min_col + 1) if kind_name != "random" else int(info.num_columns)
+    bytes_launch = algorithmic_bytes(rows, x_touched, K, idx_bits // 8, y_rmw)
+    bytes_min = algorithmic_bytes(rows, x_touched, K, idx_bits // 8, False)
     peak, peak_src = measured_peak()
     achieved = bytes_launch / (ms_per_step * 1e-3) * 1e-9
-    workload = f"laplace2d_{nx_global}x{GRID}_K5_idx32"
+    workload = f"{kind_name}_{'x'.join(str(d) for d in dims)}_K{K}_idx{idx_bits}"
 
     # second kernel-only figure at N=1: overwrite mode (y <- A*x), no y read
     extra = {}
@@ -322,7 +341,7 @@ def main_ours(args, rank: int, local_rank: int, world: int):
 
     # ---- e2e: the C-ABI call with HOST vectors ----------------------------------
     n_e2e = max(1, min(args.steps, args.e2e_steps))
-    xh = torch.empty(global_rows, dtype=torch.float64).pin_memory()
+    xh = torch.empty(int(info.num_columns), dtype=torch.float64).pin_memory()
     yh = torch.zeros(rows, dtype=torch.float64).pin_memory()
     xh.fill_(1.0)
     xn, yn = xh.numpy(), yh.numpy()
@@ -339,28 +358,28 @@ def main_ours(args, rank: int, local_rank: int, world: int):
         t_e2e = float(t.item())
     e2e_value = flops_step * n_e2e / t_e2e * 1e-9
     # sanity: A*ones accumulated n_e2e times is n_e2e * (boundary indicator); checked on the host result
-    if world == 1:
+    if world == 1 and args.workload == "laplace2d":
         g = yn.reshape(GRID, GRID)
         assert g[1:-1, 1:-1].max() == 0.0 and g[0, 1] == n_e2e and g[0, 0] == 2 * n_e2e, "e2e result is wrong"
 
     line = {
         "metric": "ell_spmv_fp64_gflops", "value": round(value, 2), "unit": "GFLOP/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": round(ms_per_step, 5), "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": round(ms_per_step, 5), "higher_is_better": True, "scaling": scaling,
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload, "rows_per_gpu": rows, "rowsize": K_LAPLACE, "idx_bits": 32,
+        "config": {"workload": workload, "rows_per_gpu": rows, "rowsize": K, "idx_bits": idx_bits,
                    "mode": mode_name, "rows_per_thread": info.rows_per_thread, "slice_rows": info.slice_rows,
                    "kernel": "thread-per-row, mul-then-add (bit-exact)" if not info.fma else "thread-per-row, fma",
-                   "l2": "inputs larger than L2 (4.0 GB matrix vs 126 MB L2), no flush needed",
+                   "l2": f"inputs larger than L2 ({rows * K * (8 + idx_bits // 8) / 1e9:.1f} GB matrix per GPU vs 126 MB L2), no flush needed",
                    "parallelism": f"rowshard{world}"},
         "gbs": round(achieved * world, 1),
         "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                      "frac": round(achieved / peak, 4), "traffic": recorded_traffic(workload if world == 1 else "sharded"),
                      "peak_source": peak_src, "bytes_per_launch": bytes_launch,
-                     "bytes_model": "K*(8+4)*rows + 8*ncols + 8*rows" + (" + 8*rows (y is read-modify-written)" if y_rmw else ""),
+                     "bytes_model": f"K*(8+{idx_bits // 8})*rows + 8*x_touched + 8*rows" + (" + 8*rows (y is read-modify-written)" if y_rmw else ""),
                      "achieved_y_once": round(bytes_min / (ms_per_step * 1e-3) * 1e-9, 1),
                      "frac_y_once": round(bytes_min / (ms_per_step * 1e-3) * 1e-9 / peak, 4)},
-        "e2e": {"value": round(e2e_value, 2), "unit": "GFLOP/s", "h2d_bytes_per_step": (global_rows + rows) * 8,
+        "e2e": {"value": round(e2e_value, 2), "unit": "GFLOP/s", "h2d_bytes_per_step": (int(info.num_columns) + rows) * 8,
                 "d2h_bytes_per_step": rows * 8, "steps": n_e2e, "ms_per_step": round(t_e2e / n_e2e * 1e3, 3),
                 "api": "ellspmv_cuda_spmv(A, y_host, x_host, 1, ACCUMULATE), pinned host vectors"},
         "gpu_launches": timed_launches,
@@ -370,7 +389,7 @@ def main_ours(args, rank: int, local_rank: int, world: int):
     if sharded is not None:
         line["exchange"] = sharded.describe()
 
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload == "laplace2d":
         try:
             r = cpu_reference_run(5, 1, budget_s=25.0)
             line["cpu_baseline"] = {"value": round(r["gflops"], 3), "unit": "GFLOP/s", "cores": r["cores"],
@@ -395,6 +414,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--exchange", choices=["auto", "push", "allgather"], default="auto")
+    ap.add_argument("--barrier", choices=["device", "nccl"], default="device")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="laplace2d")
     ap.add_argument("--flags", type=lambda s: int(s, 0), default=0, help="ELLSPMV_CUDA_* upload flags")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")

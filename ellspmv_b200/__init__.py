@@ -86,6 +86,7 @@ _PROTOTYPES = {
     "ellspmv_cuda_ipc_export": (C.c_int, [_P, _P]),
     "ellspmv_cuda_ipc_open": (C.c_int, [_P, C.POINTER(_P)]),
     "ellspmv_cuda_ipc_close": (C.c_int, [_P]),
+    "ellspmv_cuda_peer_barrier": (C.c_int, [C.c_int, C.c_int, _I64, _P, C.POINTER(_P), _P]),
     "ellspmv_cuda_device_count": (C.c_int, [C.POINTER(C.c_int)]),
     "ellspmv_cuda_strerror": (C.c_char_p, [C.c_int]),
     "ellspmv_cuda_last_error": (C.c_char_p, []),

@@ -66,6 +66,7 @@ struct ellspmv_cuda_matrix {
     long long *d_minmax = nullptr;
     int64_t min_col = 0, max_col = -1;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream_out = nullptr;       // D2H stream of the pipelined host call
     double *d_x = nullptr, *d_y = nullptr;   // vectors of the host-facing spmv
     int64_t vec_len = 0;
     std::vector<cudaEvent_t> events;
@@ -203,7 +204,7 @@ int ensure_events(std::vector<cudaEvent_t> &ev, size_t n)
 }
 
 int launch(ellspmv_cuda_matrix *A, double *y_dev, const double *x_dev, int beta,
-           const PushTargets *push, cudaStream_t stream)
+           const PushTargets *push, cudaStream_t stream, int64_t slice_begin = 0, int64_t num_slices = -1)
 {
     EllSpmvArgs args = {};
     args.vals = A->vals;
@@ -214,6 +215,8 @@ int launch(ellspmv_cuda_matrix *A, double *y_dev, const double *x_dev, int beta,
     args.row_begin = A->row_begin;
     args.rowsize = A->lay.rowsize;
     args.beta = beta;
+    args.slice_begin = slice_begin;
+    if (num_slices < 0) num_slices = A->lay.num_slices - slice_begin;
     if (push) args.push = *push; else args.push.num_peers = 0;
     if (A->lay.rowsize == 0) {
         // K = 0: y += 0 for beta=1, y = 0 for beta=0
@@ -221,8 +224,54 @@ int launch(ellspmv_cuda_matrix *A, double *y_dev, const double *x_dev, int beta,
             ELL_CK(cudaMemsetAsync(y_dev, 0, (size_t)A->lay.num_rows * 8, stream));
         return 0;
     }
-    ELL_CK(launch_ell_spmv(A->cfg, args, A->lay.num_slices, stream));
+    ELL_CK(launch_ell_spmv(A->cfg, args, num_slices, stream));
     A->launches++;
+    return 0;
+}
+
+// One y <- beta*y + A*x with host vectors, software-pipelined over row chunks:
+// x goes up first; then for each chunk the y rows go up (beta = 1), the chunk's
+// slices run, and the finished y rows come back on a second stream, so the
+// upload of chunk c+1 (host->device) overlaps the download of chunk c
+// (device->host) on the full-duplex PCIe link.  seconds = sum of the chunk
+// kernels' device-event times.
+int spmv_pipelined(ellspmv_cuda_matrix *A, double *y, const double *x, int beta, double *seconds)
+{
+    const int64_t rows = A->lay.num_rows, ncols = A->num_columns, S = A->lay.slice_rows;
+    const int64_t slices = A->lay.num_slices;
+    const int nchunks = (int)(slices < 8 ? slices : 8);
+    const int64_t chunk_slices = (slices + nchunks - 1) / nchunks;
+    int err = ensure_events(A->events, 2 * (size_t)nchunks);
+    if (err) return err;
+    if (!A->stream_out) ELL_CK(cudaStreamCreateWithFlags(&A->stream_out, cudaStreamNonBlocking));
+    cudaStream_t s = A->stream, so = A->stream_out;
+    ELL_CK(cudaMemcpyAsync(A->d_x, x, (size_t)ncols * 8, cudaMemcpyDefault, s));
+    int used = 0;
+    for (int c = 0; c < nchunks; c++) {
+        const int64_t s0 = c * chunk_slices;
+        if (s0 >= slices) break;
+        const int64_t ns = (slices - s0 < chunk_slices) ? slices - s0 : chunk_slices;
+        const int64_t r0 = s0 * S;
+        const int64_t r1 = (r0 + ns * S < rows) ? r0 + ns * S : rows;
+        if (beta) ELL_CK(cudaMemcpyAsync(A->d_y + r0, y + r0, (size_t)(r1 - r0) * 8, cudaMemcpyDefault, s));
+        ELL_CK(cudaEventRecord(A->events[2 * c], s));
+        if ((err = launch(A, A->d_y, A->d_x, beta, nullptr, s, s0, ns))) return err;
+        ELL_CK(cudaEventRecord(A->events[2 * c + 1], s));
+        ELL_CK(cudaStreamWaitEvent(so, A->events[2 * c + 1], 0));
+        ELL_CK(cudaMemcpyAsync(y + r0, A->d_y + r0, (size_t)(r1 - r0) * 8, cudaMemcpyDefault, so));
+        used = c + 1;
+    }
+    ELL_CK(cudaStreamSynchronize(s));
+    ELL_CK(cudaStreamSynchronize(so));
+    if (seconds) {
+        double total = 0.0;
+        for (int c = 0; c < used; c++) {
+            float ms = 0.f;
+            ELL_CK(cudaEventElapsedTime(&ms, A->events[2 * c], A->events[2 * c + 1]));
+            total += (double)ms * 1e-3;
+        }
+        seconds[0] = total;
+    }
     return 0;
 }
 
@@ -292,6 +341,7 @@ void ellspmv_cuda_free(ellspmv_cuda_matrix *A)
     if (A->d_x) cudaFree(A->d_x);
     if (A->d_y) cudaFree(A->d_y);
     if (A->stream) cudaStreamDestroy(A->stream);
+    if (A->stream_out) cudaStreamDestroy(A->stream_out);
     delete A;
 }
 
@@ -508,6 +558,8 @@ int ellspmv_cuda_spmv(
     DeviceGuard g(A->device);
     int err = ensure_vectors(A);
     if (err) return err;
+    if (repeat == 1 && mode != ELLSPMV_CUDA_ITERATE && rows >= (1 << 20) && A->lay.rowsize > 0 && ncols > 0)
+        return spmv_pipelined(A, y, x, mode == ELLSPMV_CUDA_ACCUMULATE ? 1 : 0, seconds);
     if ((err = ensure_events(A->events, (size_t)repeat + 1))) return err;
     cudaStream_t s = A->stream;
     if (ncols > 0) ELL_CK(cudaMemcpyAsync(A->d_x, x, (size_t)ncols * 8, cudaMemcpyDefault, s));
@@ -726,6 +778,22 @@ int ellspmv_cuda_malloc_device(void **ptr, int64_t bytes)
 }
 
 void ellspmv_cuda_free_device(void *ptr) { if (ptr) cudaFree(ptr); }
+
+int ellspmv_cuda_peer_barrier(int rank, int nranks, int64_t epoch, int64_t *local_flags,
+                              int64_t *const *peer_flags, void *stream)
+{
+    if (!local_flags || !peer_flags) ELL_FAIL(EINVAL, "NULL flag array");
+    if (nranks < 1 || nranks > kMaxRanks || rank < 0 || rank >= nranks)
+        ELL_FAIL(EINVAL, "rank %d / nranks %d out of range (max %d ranks)", rank, nranks, kMaxRanks);
+    long long *peers[kMaxRanks];
+    for (int p = 0; p < nranks; p++) {
+        if (!peer_flags[p]) ELL_FAIL(EINVAL, "peer_flags[%d] is NULL", p);
+        peers[p] = reinterpret_cast<long long *>(peer_flags[p]);
+    }
+    ELL_CK(launch_peer_barrier(rank, nranks, (long long)epoch, reinterpret_cast<long long *>(local_flags), peers,
+                               reinterpret_cast<int *>(local_flags + kMaxRanks), (cudaStream_t)stream));
+    return 0;
+}
 
 int ellspmv_cuda_ipc_export(const void *dev_ptr, unsigned char handle[64])
 {

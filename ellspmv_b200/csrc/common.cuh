@@ -76,6 +76,7 @@ struct EllSpmvArgs {
     double       *y;        // shard rows (in/out)
     int64_t       num_rows; // shard rows
     int64_t       row_begin;// global index of shard row 0 (for push)
+    int64_t       slice_begin; // first slice of this launch (chunked launches of the pipelined host call)
     int           rowsize;
     int           beta;     // 1: y += A x, 0: y = A x
     PushTargets   push;
@@ -126,5 +127,13 @@ cudaError_t generate_sliced(int kind, const int64_t dims[3], const double vals[2
 cudaError_t generate_csr_random(const int64_t dims[3], uint64_t seed, int idx_bits,
                                 int64_t *rowptr, void *cols, double *vals, cudaStream_t stream);
 cudaError_t init_minmax(long long *minmax, cudaStream_t stream);
+
+// ---- cross-GPU step barrier (barrier.cu) ----------------------------------
+// rank writes `epoch` into slot [rank] of every peer's flag array, then waits
+// until its own array shows `epoch` from every rank.  Flags are int64 in
+// peer-mapped device memory (one array of kMaxRanks slots per rank).
+constexpr int kMaxRanks = 16;
+cudaError_t launch_peer_barrier(int rank, int nranks, long long epoch, long long *local_flags,
+                                long long *const *peer_flags, int *error_flag, cudaStream_t stream);
 
 }  // namespace ellspmv

@@ -44,12 +44,32 @@ csr_stream_kernel(const CsrSpmvArgs a)
     for (int64_t t0 = kb; t0 < ke; t0 += kCsrTile) {
         const int64_t t1 = (t0 + kCsrTile < ke) ? t0 + kCsrTile : ke;
         const int n = (int)(t1 - t0);
-#pragma unroll 4
-        for (int i = threadIdx.x; i < n; i += kBlockThreads) {
-            const double v = __ldcs(vals + t0 + i);
-            const int64_t c = (int64_t)__ldcs(cols + t0 + i);
-            const double xv = __ldg(x + c);
-            prod[skew(i)] = FMA ? v * xv : __dmul_rn(v, xv);
+        // every thread stages kCsrTile/kBlockThreads = 16 entries: all index
+        // loads, then all value loads, then all gathers are issued before the
+        // first product is parked, so 16 gathers per thread are in flight
+        {
+            constexpr int PER = kCsrTile / kBlockThreads;
+            int64_t c[PER]; double v[PER], xv[PER];
+#pragma unroll
+            for (int u = 0; u < PER; u++) {
+                const int i = threadIdx.x + u * kBlockThreads;
+                c[u] = i < n ? (int64_t)__ldcs(cols + t0 + i) : 0;
+            }
+#pragma unroll
+            for (int u = 0; u < PER; u++) {
+                const int i = threadIdx.x + u * kBlockThreads;
+                v[u] = i < n ? __ldcs(vals + t0 + i) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < PER; u++) {
+                const int i = threadIdx.x + u * kBlockThreads;
+                xv[u] = i < n ? __ldg(x + c[u]) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < PER; u++) {
+                const int i = threadIdx.x + u * kBlockThreads;
+                if (i < n) prod[skew(i)] = FMA ? v[u] * xv[u] : __dmul_rn(v[u], xv[u]);
+            }
         }
         __syncthreads();
         if (have_row) {

@@ -135,7 +135,7 @@ ell_thread_kernel(const EllSpmvArgs a)
     constexpr int S = kBlockThreads * R;
     constexpr int U = Batch<R>::U;
     const int K = KU > 0 ? KU : a.rowsize;
-    const int64_t slice = blockIdx.x;
+    const int64_t slice = a.slice_begin + blockIdx.x;
     const int64_t row0 = slice * S + (int64_t)threadIdx.x * R;   // shard-local
     if (row0 >= a.num_rows) return;
 
@@ -264,7 +264,7 @@ ell_subwarp_kernel(const EllSpmvArgs a, int slice_rows)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int j = lane / RW, rl = lane % RW;
     // a CTA covers WARPS*RW rows per pass and S rows in total
-    const int64_t slice = blockIdx.x;
+    const int64_t slice = a.slice_begin + blockIdx.x;
     const double *vbase = a.vals + slice * S * (int64_t)K;
     const IdxT *cbase = reinterpret_cast<const IdxT *>(a.cols) + slice * S * (int64_t)K;
     const double *__restrict__ x = a.x;

@@ -114,8 +114,9 @@ class ShardedIterate:
     EllMatrix (or any object with .info(), .spmv_device(), .spmv_push())."""
 
     def __init__(self, A, rank: int, world: int, exchange: str = "auto", group=None,
-                 device: Optional[torch.device] = None):
+                 device: Optional[torch.device] = None, barrier: str = "device"):
         self.A, self.rank, self.world, self.group = A, rank, world, group
+        self.barrier = barrier            # "device": flag barrier kernel over peer memory; "nccl": 1-element all-reduce
         info = A.info()
         self.global_rows = int(info.global_rows)
         if int(info.num_columns) != self.global_rows:
@@ -167,6 +168,20 @@ class ShardedIterate:
             for buf in (0, 1):
                 self._peer_ptrs[buf] = [opened[p][buf] for p, _, _ in self.plan]
             self._flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+            # step barrier on the device: 32 int64 flags per rank, every rank maps all of them
+            self._flags = _DeviceBuffer(32, self.device)
+            self._flags.tensor.zero_()
+            torch.cuda.synchronize(self.device)
+            fh: List = [None] * world
+            dist.all_gather_object(fh, self._flags.ipc_handle(), group=group)
+            self._flag_ptrs = []
+            for p in range(world):
+                if p == rank:
+                    self._flag_ptrs.append(self._flags.ptr)
+                else:
+                    ptr = _ipc_open(fh[p])
+                    self._opened.append(ptr)
+                    self._flag_ptrs.append(ptr)
             dist.barrier(group=group)
 
     # -- data ---------------------------------------------------------------
@@ -195,13 +210,25 @@ class ShardedIterate:
             self.A.spmv_push(y, cur, OVERWRITE, self._peer_ptrs[1 - self.cur],
                              [lo for _, lo, _ in self.plan], [hi for _, _, hi in self.plan], stream)
             # orders step k's pushes before step k+1's gathers on every rank
-            dist.all_reduce(self._flag, group=self.group)
+            if self.barrier == "device":
+                self._peer_barrier(stream)
+            else:
+                dist.all_reduce(self._flag, group=self.group)
         else:
             self.A.spmv_device(y, cur, OVERWRITE, stream)
             if self.world > 1:
                 self._allgather(nxt)
         self.cur = 1 - self.cur
         self.steps_done += 1
+
+    def _peer_barrier(self, stream: int) -> None:
+        import ctypes as C
+        lib = load_library()
+        ptrs = (C.c_void_p * self.world)(*self._flag_ptrs)
+        err = lib.ellspmv_cuda_peer_barrier(self.rank, self.world, self.steps_done + 1, self._flags.ptr, ptrs,
+                                            stream or None)
+        if err:
+            raise EllspmvCudaError(err, "ellspmv_cuda_peer_barrier", lib.ellspmv_cuda_last_error().decode())
 
     def _allgather(self, full: torch.Tensor) -> None:
         if self.equal_parts:
@@ -221,7 +248,8 @@ class ShardedIterate:
 
     def describe(self) -> dict:
         sent = exchanged_bytes(self.rank, self.parts, self.needs, self.exchange)
-        return {"mode": self.exchange, "bytes_sent_per_step_rank0": sent,
+        return {"mode": self.exchange, "barrier": self.barrier if self.exchange == "push" else "nccl collective",
+                "bytes_sent_per_step_rank0": sent,
                 "rows_pushed_to_peers": [(p, hi - lo) for p, lo, hi in self.plan] if self.exchange == "push" else None,
                 "needs": self.needs[self.rank]}
 
@@ -234,3 +262,6 @@ class ShardedIterate:
         for b in self._bufs:
             b.free()
         self._bufs = []
+        if getattr(self, "_flags", None) is not None:
+            self._flags.free()
+            self._flags = None

@@ -225,6 +225,17 @@ int ellspmv_cuda_ipc_export(const void *dev_ptr, unsigned char handle[64]);
 int ellspmv_cuda_ipc_open(const unsigned char handle[64], void **dev_ptr);
 int ellspmv_cuda_ipc_close(void *dev_ptr);
 
+/*
+ * Device-side step barrier between the ranks of a row-sharded repeated SpMV,
+ * asynchronous on `stream`: writes `epoch` into slot [rank] of every rank's
+ * flag array and waits until the local array shows `epoch` from all ranks.
+ * Flag arrays are 32 zero-initialised int64 in ellspmv_cuda_malloc_device
+ * memory, peers' arrays opened over CUDA IPC; epochs must increase.  Slot
+ * [16] of the local array turns non-zero if a peer never arrived (~20 s).
+ */
+int ellspmv_cuda_peer_barrier(int rank, int nranks, int64_t epoch, int64_t *local_flags,
+                              int64_t *const *peer_flags, void *stream);
+
 int ellspmv_cuda_device_count(int *count);
 const char *ellspmv_cuda_strerror(int err);
 const char *ellspmv_cuda_last_error(void);

@@ -228,3 +228,26 @@ def test_push_to_peer_vectors(lib, oracle):
     assert bits_equal(p0[lo:hi].cpu().numpy(), want[lo:hi]) and p0[:lo].abs().sum() == 0 and p0[hi:].abs().sum() == 0
     assert bits_equal(p1[2000:2500].cpu().numpy(), want[2000:2500])
     assert p1[:2000].abs().sum() == 0 and p1[2500:].abs().sum() == 0
+
+
+@pytest.mark.parametrize("mode", [E.ACCUMULATE, E.OVERWRITE])
+def test_pipelined_host_call(lib, oracle, mode):
+    """>= 2^20 rows and repeat == 1 take the chunked, copy-overlapped path of
+    ellspmv_cuda_spmv; pinned and pageable host vectors, ragged last chunk."""
+    import torch
+    K, ncols, ec, ea, _ = oracle.gen_ell("laplace2d", (1500, 1001), (4.0, -1.0), bits=32)
+    rows = len(ea) // K
+    rng = np.random.default_rng(4)
+    x = rng.standard_normal(ncols)
+    y0 = rng.standard_normal(rows)
+    want = y0.copy() if mode == E.ACCUMULATE else np.zeros(rows)
+    oracle.ellgemv(rows, want, x, K, ec, ea)
+    A = E.EllMatrix.upload(rows, ncols, K, ec, ea)
+    y = y0.copy()
+    secs = A.spmv(y, x, 1, mode)
+    assert bits_equal(y, want) and secs[0] > 0
+    xp = torch.from_numpy(x).pin_memory()
+    yp = torch.from_numpy(y0.copy()).pin_memory()
+    A.spmv(yp.numpy(), xp.numpy(), 1, mode)
+    assert bits_equal(yp.numpy(), want)
+    A.free()

@@ -31,10 +31,11 @@ def _worker(rank, world, port, q):
         for kind, name, dims, vals, bits in CASES:
             rows = dims[0] if name == "random" else int(np.prod(dims))
             x0 = np.random.default_rng(0).uniform(-1, 1, rows)
-            for mode in ("allgather", "push"):
+            for mode in ("allgather", "push", "push-nccl"):
                 lo, hi = partition_rows(rows, world)[rank]
                 A = E.EllMatrix.generate(kind, dims, vals, 42, bits, row_begin=lo, row_end=hi, device=rank)
-                it = ShardedIterate(A, rank, world, exchange=mode)
+                it = ShardedIterate(A, rank, world, exchange=mode.split("-")[0],
+                                    barrier="nccl" if mode.endswith("nccl") else "device")
                 it.set_x(lambda a, b: torch.from_numpy(x0[a:b].copy()).to(dev))
                 for _ in range(6):
                     it.step(torch.cuda.current_stream().cuda_stream)
@@ -57,7 +58,7 @@ def test_sharded_equals_single_gpu(lib, oracle):
     procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    results = [q.get(timeout=600) for _ in range(world * len(CASES) * 2)]
+    results = [q.get(timeout=600) for _ in range(world * len(CASES) * 3)]
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
@@ -67,7 +68,7 @@ def test_sharded_equals_single_gpu(lib, oracle):
         rows = len(ea) // K
         x0 = np.random.default_rng(0).uniform(-1, 1, rows)
         want = oracle.ell_iterate(rows, x0, 6, K, ec, ea)
-        for mode in ("allgather", "push"):
+        for mode in ("allgather", "push", "push-nccl"):
             got = [r for r in results if r[0] == 0 and r[1] == name and r[2] == mode]
             assert len(got) == 1 and bits_equal(got[0][3], want), (name, mode)
             d = got[0][4]
