@@ -239,7 +239,7 @@ int spmv_pipelined(ellspmv_cuda_matrix *A, double *y, const double *x, int beta,
 {
     const int64_t rows = A->lay.num_rows, ncols = A->num_columns, S = A->lay.slice_rows;
     const int64_t slices = A->lay.num_slices;
-    const int nchunks = (int)(slices < 8 ? slices : 8);
+    const int nchunks = (int)(slices < 32 ? slices : 32);
     const int64_t chunk_slices = (slices + nchunks - 1) / nchunks;
     int err = ensure_events(A->events, 2 * (size_t)nchunks);
     if (err) return err;
