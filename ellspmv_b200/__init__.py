@@ -70,6 +70,8 @@ _PROTOTYPES = {
     "ellspmv_cuda_spmv": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P]),
     "ellspmv_cuda_spmv_device": (C.c_int, [_P, _P, _P, C.c_int, _P]),
     "ellspmv_cuda_spmv_push": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.POINTER(_P), C.POINTER(_I64), C.POINTER(_I64), _P]),
+    "ellspmv_cuda_set_diagonal": (C.c_int, [_P, _P, C.c_int]),
+    "csrspmv_cuda_set_diagonal": (C.c_int, [_P, _P]),
     "ellspmv_cuda_download": (C.c_int, [_P, _P, _P]),
     "ellspmv_cuda_get_info": (C.c_int, [_P, C.POINTER(Info)]),
     "ellspmv_cuda_free": (None, [_P]),
@@ -215,6 +217,10 @@ class EllMatrix:
                                                     stream or None)
         _check(err, "ellspmv_cuda_spmv_push")
 
+    def set_diagonal(self, ad, order: int = 0) -> None:
+        """y <- y + (ad.*x + A*x): the reference's ellgemvsd (order 0) / ellgemv16sd (order 1)."""
+        _check(load_library().ellspmv_cuda_set_diagonal(self._h, _ptr(ad), order), "ellspmv_cuda_set_diagonal")
+
     # -- inspection -------------------------------------------------------------
     def info(self) -> Info:
         out = Info()
@@ -282,6 +288,10 @@ class CsrMatrix:
     def spmv_device(self, y_dev, x_dev, mode: int = ACCUMULATE, stream: int = 0) -> None:
         err = load_library().csrspmv_cuda_spmv_device(self._h, _ptr(y_dev), _ptr(x_dev), mode, stream or None)
         _check(err, "csrspmv_cuda_spmv_device")
+
+    def set_diagonal(self, ad) -> None:
+        """y <- y + (ad.*x + A*x): the reference's csrgemvsd."""
+        _check(load_library().csrspmv_cuda_set_diagonal(self._h, _ptr(ad)), "csrspmv_cuda_set_diagonal")
 
     def device_bytes(self) -> int:
         return load_library().csrspmv_cuda_device_bytes(self._h)

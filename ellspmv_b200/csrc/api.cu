@@ -64,6 +64,8 @@ struct ellspmv_cuda_matrix {
     double *vals = nullptr;
     void *cols = nullptr;
     long long *d_minmax = nullptr;
+    double *d_ad = nullptr;                  // separately stored diagonal (shard rows), optional
+    int sd_order = 0;
     int64_t min_col = 0, max_col = -1;
     cudaStream_t stream = nullptr;
     cudaStream_t stream_out = nullptr;       // D2H stream of the pipelined host call
@@ -86,6 +88,7 @@ struct csrspmv_cuda_matrix {
     double *vals = nullptr;
     cudaStream_t stream = nullptr;
     double *d_x = nullptr, *d_y = nullptr;
+    double *d_ad = nullptr;                  // separately stored diagonal, optional
     std::vector<cudaEvent_t> events;
     int64_t device_bytes = 0;
 };
@@ -216,9 +219,11 @@ int launch(ellspmv_cuda_matrix *A, double *y_dev, const double *x_dev, int beta,
     args.rowsize = A->lay.rowsize;
     args.beta = beta;
     args.slice_begin = slice_begin;
+    args.ad = A->d_ad;
+    args.sd_order = A->sd_order;
     if (num_slices < 0) num_slices = A->lay.num_slices - slice_begin;
     if (push) args.push = *push; else args.push.num_peers = 0;
-    if (A->lay.rowsize == 0) {
+    if (A->lay.rowsize == 0 && !A->d_ad) {
         // K = 0: y += 0 for beta=1, y = 0 for beta=0
         if (!beta && A->lay.num_rows > 0)
             ELL_CK(cudaMemsetAsync(y_dev, 0, (size_t)A->lay.num_rows * 8, stream));
@@ -338,6 +343,7 @@ void ellspmv_cuda_free(ellspmv_cuda_matrix *A)
     if (A->vals) cudaFree(A->vals);
     if (A->cols) cudaFree(A->cols);
     if (A->d_minmax) cudaFree(A->d_minmax);
+    if (A->d_ad) cudaFree(A->d_ad);
     if (A->d_x) cudaFree(A->d_x);
     if (A->d_y) cudaFree(A->d_y);
     if (A->stream) cudaStreamDestroy(A->stream);
@@ -483,6 +489,32 @@ int ellspmv_cuda_download(const ellspmv_cuda_matrix *A, void *colidx, double *a)
     return 0;
 }
 
+int ellspmv_cuda_set_diagonal(ellspmv_cuda_matrix *A, const double *ad, int order)
+{
+    if (!A) ELL_FAIL(EINVAL, "matrix is NULL");
+    if (order != 0 && order != 1) ELL_FAIL(EINVAL, "order must be 0 (ellgemvsd) or 1 (ellgemv16sd)");
+    DeviceGuard g(A->device);
+    if (!ad) {
+        if (A->d_ad) { cudaFree(A->d_ad); A->d_ad = nullptr; }
+        return 0;
+    }
+    // x[i] is read at the row's own (global) index: every shard row needs a column
+    if (A->row_begin + A->lay.num_rows > A->num_columns)
+        ELL_FAIL(EINVAL, "separate diagonal needs rows <= columns (ellgemvsd reads x[i] for every row i)");
+    // the padded tail of the last slice is read with vector loads: allocate whole slices
+    const size_t n = (size_t)(A->lay.padded_rows() > 0 ? A->lay.padded_rows() : 1);
+    if (!A->d_ad) {
+        ELL_CK(cudaMalloc(&A->d_ad, n * 8));
+        A->device_bytes += (int64_t)n * 8;
+    }
+    ELL_CK(cudaMemsetAsync(A->d_ad, 0, n * 8, A->stream));
+    if (A->lay.num_rows > 0)
+        ELL_CK(cudaMemcpyAsync(A->d_ad, ad, (size_t)A->lay.num_rows * 8, cudaMemcpyDefault, A->stream));
+    ELL_CK(cudaStreamSynchronize(A->stream));
+    A->sd_order = order;
+    return 0;
+}
+
 int ellspmv_cuda_get_info(const ellspmv_cuda_matrix *A, ellspmv_cuda_info *info)
 {
     if (!A || !info) ELL_FAIL(EINVAL, "NULL argument");
@@ -599,6 +631,7 @@ void csrspmv_cuda_free(csrspmv_cuda_matrix *A)
     if (A->stream) cudaStreamSynchronize(A->stream);
     for (cudaEvent_t e : A->events) cudaEventDestroy(e);
     if (A->rowptr) cudaFree(A->rowptr);
+    if (A->d_ad) cudaFree(A->d_ad);
     if (A->cols) cudaFree(A->cols);
     if (A->vals) cudaFree(A->vals);
     if (A->d_x) cudaFree(A->d_x);
@@ -699,6 +732,27 @@ int csrspmv_cuda_generate(
     return 0;
 }
 
+int csrspmv_cuda_set_diagonal(csrspmv_cuda_matrix *A, const double *ad)
+{
+    if (!A) ELL_FAIL(EINVAL, "matrix is NULL");
+    DeviceGuard g(A->device);
+    if (!ad) {
+        if (A->d_ad) { cudaFree(A->d_ad); A->d_ad = nullptr; }
+        return 0;
+    }
+    if (A->num_rows > A->num_columns)
+        ELL_FAIL(EINVAL, "separate diagonal needs rows <= columns (csrgemvsd reads x[i] for every row i)");
+    const size_t n = (size_t)(A->num_rows > 0 ? A->num_rows : 1);
+    if (!A->d_ad) {
+        ELL_CK(cudaMalloc(&A->d_ad, n * 8));
+        A->device_bytes += (int64_t)n * 8;
+    }
+    if (A->num_rows > 0)
+        ELL_CK(cudaMemcpyAsync(A->d_ad, ad, (size_t)A->num_rows * 8, cudaMemcpyDefault, A->stream));
+    ELL_CK(cudaStreamSynchronize(A->stream));
+    return 0;
+}
+
 int csrspmv_cuda_spmv_device(
     csrspmv_cuda_matrix *A, double *y_dev, const double *x_dev, int mode, void *stream)
 {
@@ -708,7 +762,7 @@ int csrspmv_cuda_spmv_device(
     if (A->num_rows > 0 && (!y_dev || !x_dev)) ELL_FAIL(EINVAL, "NULL device vector");
     DeviceGuard g(A->device);
     CsrSpmvArgs args = {A->rowptr, A->cols, A->vals, x_dev, y_dev, A->num_rows,
-                        mode == ELLSPMV_CUDA_ACCUMULATE ? 1 : 0};
+                        mode == ELLSPMV_CUDA_ACCUMULATE ? 1 : 0, A->d_ad};
     ELL_CK(launch_csr_spmv(A->idx_bits, A->fma, A->kernel, args, (cudaStream_t)stream));
     return 0;
 }
@@ -733,7 +787,7 @@ int csrspmv_cuda_spmv(
     ELL_CK(cudaEventRecord(A->events[0], s));
     for (int r = 0; r < repeat; r++) {
         CsrSpmvArgs args = {A->rowptr, A->cols, A->vals, A->d_x, A->d_y, A->num_rows,
-                            mode == ELLSPMV_CUDA_ACCUMULATE ? 1 : 0};
+                            mode == ELLSPMV_CUDA_ACCUMULATE ? 1 : 0, A->d_ad};
         ELL_CK(launch_csr_spmv(A->idx_bits, A->fma, A->kernel, args, s));
         ELL_CK(cudaEventRecord(A->events[(size_t)r + 1], s));
     }

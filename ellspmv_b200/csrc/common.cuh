@@ -79,6 +79,8 @@ struct EllSpmvArgs {
     int64_t       slice_begin; // first slice of this launch (chunked launches of the pipelined host call)
     int           rowsize;
     int           beta;     // 1: y += A x, 0: y = A x
+    const double *ad;       // separately stored diagonal of the shard rows, or NULL
+    int           sd_order; // 0: y += ad*x + yi (ellgemvsd); 1: sum starts at ad*x (ellgemv16sd)
     PushTargets   push;
 };
 
@@ -105,6 +107,7 @@ struct CsrSpmvArgs {
     double        *y;
     int64_t        num_rows;
     int            beta;
+    const double  *ad;      // separately stored diagonal, or NULL (csrgemvsd)
 };
 cudaError_t launch_csr_spmv(int idx_bits, bool fma, int kernel, const CsrSpmvArgs &args,
                             cudaStream_t stream);

@@ -80,6 +80,8 @@ csr_stream_kernel(const CsrSpmvArgs a)
         __syncthreads();
     }
     if (have_row) {
+        // csrgemvsd (csrspmv.c:1622-1627): y += ad*x + yi
+        if (a.ad) acc = __dadd_rn(__dmul_rn(a.ad[row], __ldg(x + row)), acc);
         const double yold = a.beta ? a.y[row] : 0.0;
         a.y[row] = __dadd_rn(yold, acc);
     }
@@ -109,7 +111,10 @@ csr_vector_kernel(const CsrSpmvArgs a)
     }
 #pragma unroll
     for (int off = 1; off < T; off <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-    if (j == 0 && row < a.num_rows) a.y[row] = a.beta ? a.y[row] + acc : acc;
+    if (j == 0 && row < a.num_rows) {
+        if (a.ad) acc += a.ad[row] * __ldg(x + row);
+        a.y[row] = a.beta ? a.y[row] + acc : acc;
+    }
 }
 
 template <typename IdxT, bool FMA>

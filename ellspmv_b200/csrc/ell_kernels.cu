@@ -114,6 +114,21 @@ template <> struct YVec<4> {
     }
 };
 
+// ---- the x gather --------------------------------------------------------------
+// G = 0: ld.global.nc, L1-allocating (stencil-like matrices: neighbouring rows
+//        share x lines, L1/L2 serve most of the gather)
+// G = 1: ld.global.nc.L1::no_allocate (scattered matrices: an L1 fill pulls whole
+//        128-byte lines for 8 useful bytes; see profiles/r1_c4_gather.md)
+// G = 2: ld.global.cg (L2 only)
+template <int G> __device__ __forceinline__ double ldx(const double *p);
+template <> __device__ __forceinline__ double ldx<0>(const double *p) { return __ldg(p); }
+template <> __device__ __forceinline__ double ldx<1>(const double *p) {
+    double v; asm("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p)); return v;
+}
+template <> __device__ __forceinline__ double ldx<2>(const double *p) {
+    double v; asm("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p)); return v;
+}
+
 template <bool FMA>
 __device__ __forceinline__ double madd(double acc, double a, double x) {
     if (FMA) return __fma_rn(a, x, acc);
@@ -128,7 +143,7 @@ template <int R> struct Batch { static constexpr int U = (R == 4) ? 4 : (R == 2 
 // ---- thread-per-row kernel ------------------------------------------------
 // KU > 0: K known at compile time (fully unrolled); KU == 0: run-time K.
 // YVEC: y (and every push target) may be accessed with R-wide vectors.
-template <typename IdxT, int R, int KU, bool FMA, bool YVEC>
+template <typename IdxT, int R, int KU, bool FMA, bool YVEC, int G>
 __global__ void __launch_bounds__(kBlockThreads)
 ell_thread_kernel(const EllSpmvArgs a)
 {
@@ -156,9 +171,29 @@ ell_thread_kernel(const EllSpmvArgs a)
         }
     }
 
+    // separately stored diagonal (reference ellgemvsd / ellgemv16sd,
+    // ellspmv.c:1173-1178, 1201-1219): dx = ad[i]*x[i], x[i] at the row's GLOBAL index
+    const double *__restrict__ ad = a.ad;
+    double dx[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) dx[r] = 0.0;
+    if (ad) {
+        double d[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) d[r] = 0.0;
+        if (full) YVec<R>::ld(ad + row0, d);
+        else {
+#pragma unroll
+            for (int r = 0; r < R; r++) if (row0 + r < a.num_rows) d[r] = ad[row0 + r];
+        }
+#pragma unroll
+        for (int r = 0; r < R; r++)
+            if (row0 + r < a.num_rows) dx[r] = __dmul_rn(d[r], __ldg(x + a.row_begin + row0 + r));
+    }
+
     double acc[R];
 #pragma unroll
-    for (int r = 0; r < R; r++) acc[r] = 0.0;
+    for (int r = 0; r < R; r++) acc[r] = (ad && a.sd_order) ? dx[r] : 0.0;
 
     if (KU > 0) {
 #pragma unroll
@@ -172,7 +207,7 @@ ell_thread_kernel(const EllSpmvArgs a)
 #pragma unroll
             for (int u = 0; u < U; u++) if (l0 + u < KU) {
 #pragma unroll
-                for (int r = 0; r < R; r++) xv[u][r] = __ldg(x + c[u][r]);
+                for (int r = 0; r < R; r++) xv[u][r] = ldx<G>(x + c[u][r]);
             }
 #pragma unroll
             for (int u = 0; u < U; u++) if (l0 + u < KU) {
@@ -193,7 +228,7 @@ ell_thread_kernel(const EllSpmvArgs a)
 #pragma unroll
             for (int u = 0; u < U; u++) {
 #pragma unroll
-                for (int r = 0; r < R; r++) xv[u][r] = __ldg(x + c[u][r]);
+                for (int r = 0; r < R; r++) xv[u][r] = ldx<G>(x + c[u][r]);
             }
 #pragma unroll
             for (int u = 0; u < U; u++) {
@@ -207,13 +242,17 @@ ell_thread_kernel(const EllSpmvArgs a)
             Vals<R>::ld(vp + (int64_t)l0 * S, v);
             Cols<IdxT, R>::ld(cp + (int64_t)l0 * S, c);
 #pragma unroll
-            for (int r = 0; r < R; r++) acc[r] = madd<FMA>(acc[r], v[r], __ldg(x + c[r]));
+            for (int r = 0; r < R; r++) acc[r] = madd<FMA>(acc[r], v[r], ldx<G>(x + c[r]));
         }
     }
 
     // y[i] += yi (beta=1) or y[i] = 0 + yi (beta=0; the add keeps -0 -> +0
     // exactly like "y=0; y+=yi" on the CPU)
     double out[R];
+    if (ad && !a.sd_order) {
+#pragma unroll
+        for (int r = 0; r < R; r++) acc[r] = __dadd_rn(dx[r], acc[r]);   // ad*x + yi
+    }
 #pragma unroll
     for (int r = 0; r < R; r++) out[r] = __dadd_rn(yold[r], acc[r]);
 
@@ -283,6 +322,7 @@ ell_subwarp_kernel(const EllSpmvArgs a, int slice_rows)
 #pragma unroll
         for (int off = RW; off < 32; off <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
         if (j == 0 && row < a.num_rows) {
+            if (a.ad) acc += a.ad[row] * __ldg(x + a.row_begin + row);
             double out = a.beta ? a.y[row] + acc : acc;
             a.y[row] = out;
             const int64_t g = a.row_begin + row;
@@ -293,35 +333,45 @@ ell_subwarp_kernel(const EllSpmvArgs a, int slice_rows)
 }
 
 // ---- launcher ----------------------------------------------------------------
+template <typename IdxT, int R, int KU, bool FMA, int G>
+static cudaError_t launch_thread_g(const EllSpmvArgs &args, bool yvec, cudaLaunchConfig_t &lc)
+{
+    if (yvec) return cudaLaunchKernelEx(&lc, ell_thread_kernel<IdxT, R, KU, FMA, true, G>, args);
+    return cudaLaunchKernelEx(&lc, ell_thread_kernel<IdxT, R, KU, FMA, false, G>, args);
+}
+
 template <typename IdxT, int R, int KU, bool FMA>
 static cudaError_t launch_thread_yvec(const EllSpmvArgs &args, int64_t num_slices, bool yvec,
-                                      cudaLaunchConfig_t &lc)
+                                      cudaLaunchConfig_t &lc, int gather)
 {
-    (void)num_slices;
-    if (yvec) return cudaLaunchKernelEx(&lc, ell_thread_kernel<IdxT, R, KU, FMA, true>, args);
-    return cudaLaunchKernelEx(&lc, ell_thread_kernel<IdxT, R, KU, FMA, false>, args);
+    // only the L1-allocating read-only gather is instantiated: on B200 the other
+    // flavours are never faster (tools/experiments/l2_fetch_granularity.cu,
+    // profiles/r1_c4_gather.md): no_allocate loses the L1 reuse of stencil rows,
+    // and for scattered rows every flavour costs one 128-byte DRAM line per gather
+    (void)num_slices; (void)gather;
+    return launch_thread_g<IdxT, R, KU, FMA, 0>(args, yvec, lc);
 }
 
 template <typename IdxT, int R, bool FMA>
 static cudaError_t launch_thread_k(const EllSpmvArgs &args, int64_t num_slices, bool yvec,
-                                   cudaLaunchConfig_t &lc)
+                                   cudaLaunchConfig_t &lc, int gather)
 {
     switch (args.rowsize) {
-    case 5:  return launch_thread_yvec<IdxT, R, 5, FMA>(args, num_slices, yvec, lc);
-    case 27: return launch_thread_yvec<IdxT, R, 27, FMA>(args, num_slices, yvec, lc);
-    case 32: return launch_thread_yvec<IdxT, R, 32, FMA>(args, num_slices, yvec, lc);
-    default: return launch_thread_yvec<IdxT, R, 0, FMA>(args, num_slices, yvec, lc);
+    case 5:  return launch_thread_yvec<IdxT, R, 5, FMA>(args, num_slices, yvec, lc, gather);
+    case 27: return launch_thread_yvec<IdxT, R, 27, FMA>(args, num_slices, yvec, lc, gather);
+    case 32: return launch_thread_yvec<IdxT, R, 32, FMA>(args, num_slices, yvec, lc, gather);
+    default: return launch_thread_yvec<IdxT, R, 0, FMA>(args, num_slices, yvec, lc, gather);
     }
 }
 
 template <typename IdxT, bool FMA>
 static cudaError_t launch_thread_r(int R, const EllSpmvArgs &args, int64_t num_slices, bool yvec,
-                                   cudaLaunchConfig_t &lc)
+                                   cudaLaunchConfig_t &lc, int gather)
 {
     switch (R) {
-    case 1: return launch_thread_k<IdxT, 1, FMA>(args, num_slices, yvec, lc);
-    case 2: return launch_thread_k<IdxT, 2, FMA>(args, num_slices, yvec, lc);
-    case 4: return launch_thread_k<IdxT, 4, FMA>(args, num_slices, yvec, lc);
+    case 1: return launch_thread_k<IdxT, 1, FMA>(args, num_slices, yvec, lc, gather);
+    case 2: return launch_thread_k<IdxT, 2, FMA>(args, num_slices, yvec, lc, gather);
+    case 4: return launch_thread_k<IdxT, 4, FMA>(args, num_slices, yvec, lc, gather);
     default: return cudaErrorInvalidValue;
     }
 }
@@ -379,10 +429,11 @@ cudaError_t launch_ell_spmv(const EllLaunchCfg &cfg, const EllSpmvArgs &args,
     bool yvec = aligned_to(args.y, 8 * (size_t)R) && (args.row_begin % R == 0);
     for (int p = 0; p < args.push.num_peers; p++) yvec = yvec && aligned_to(args.push.x[p], 8 * (size_t)R);
 
-    if (i64) return cfg.fma ? launch_thread_r<int64_t, true>(R, args, num_slices, yvec, lc)
-                            : launch_thread_r<int64_t, false>(R, args, num_slices, yvec, lc);
-    return cfg.fma ? launch_thread_r<int32_t, true>(R, args, num_slices, yvec, lc)
-                   : launch_thread_r<int32_t, false>(R, args, num_slices, yvec, lc);
+    const int gather = 0;
+    if (i64) return cfg.fma ? launch_thread_r<int64_t, true>(R, args, num_slices, yvec, lc, gather)
+                            : launch_thread_r<int64_t, false>(R, args, num_slices, yvec, lc, gather);
+    return cfg.fma ? launch_thread_r<int32_t, true>(R, args, num_slices, yvec, lc, gather)
+                   : launch_thread_r<int32_t, false>(R, args, num_slices, yvec, lc, gather);
 }
 
 }  // namespace ellspmv

@@ -9,6 +9,7 @@ void ell_free(struct ell_matrix *ell)
 {
     free(ell->colidx);
     free(ell->a);
+    free(ell->ad);
     memset(ell, 0, sizeof(*ell));
 }
 
@@ -17,11 +18,12 @@ void csr_free(struct csr_matrix *csr)
     free(csr->rowptr);
     free(csr->colidx);
     free(csr->a);
+    free(csr->ad);
     memset(csr, 0, sizeof(*csr));
 }
 
 int ell_from_coo(struct ell_matrix *ell, idx_t num_rows, idx_t num_columns, int64_t num_nonzeros,
-                 const idx_t *rowidx, const idx_t *colidx, const double *a)
+                 const idx_t *rowidx, const idx_t *colidx, const double *a, int separate_diagonal)
 {
     memset(ell, 0, sizeof(*ell));
     ell->num_rows = num_rows;
@@ -33,6 +35,7 @@ int ell_from_coo(struct ell_matrix *ell, idx_t num_rows, idx_t num_columns, int6
     if (!fill) return ENOMEM;
     int64_t widest = 0;
     for (int64_t k = 0; k < num_nonzeros; k++) {
+        if (separate_diagonal && rowidx[k] == colidx[k]) continue;
         int64_t n = ++fill[rowidx[k] - 1];
         if (n > widest) widest = n;
     }
@@ -49,11 +52,16 @@ int ell_from_coo(struct ell_matrix *ell, idx_t num_rows, idx_t num_columns, int6
     ell->colidx = malloc(n * sizeof(idx_t));
     ell->a = malloc(n * sizeof(double));
     if (!ell->colidx || !ell->a) { free(fill); ell_free(ell); return ENOMEM; }
+    if (separate_diagonal) {
+        ell->ad = calloc(ell->diagsize > 0 ? (size_t)ell->diagsize : 1, sizeof(double));
+        if (!ell->ad) { free(fill); ell_free(ell); return ENOMEM; }
+    }
 
     /* pass 2: scatter in file order (ellspmv.c:1098-1107) */
     memset(fill, 0, ((size_t)num_rows + 1) * sizeof(*fill));
     for (int64_t k = 0; k < num_nonzeros; k++) {
         const int64_t r = (int64_t)rowidx[k] - 1;
+        if (separate_diagonal && rowidx[k] == colidx[k]) { ell->ad[r] += a[k]; continue; }
         const int64_t slot = r * K + fill[r]++;
         ell->colidx[slot] = colidx[k] - 1;
         ell->a[slot] = a[k];
@@ -74,18 +82,22 @@ int ell_from_coo(struct ell_matrix *ell, idx_t num_rows, idx_t num_columns, int6
 }
 
 int csr_from_coo(struct csr_matrix *csr, int symmetric, idx_t num_rows, idx_t num_columns,
-                 int64_t num_nonzeros, const idx_t *rowidx, const idx_t *colidx, const double *a)
+                 int64_t num_nonzeros, const idx_t *rowidx, const idx_t *colidx, const double *a,
+                 int separate_diagonal)
 {
     memset(csr, 0, sizeof(*csr));
     csr->num_rows = num_rows;
     csr->num_columns = num_columns;
     /* symmetric expansion only for square matrices (csrspmv.c:1244) */
     const int expand = symmetric && num_rows == num_columns;
+    /* like the reference, the diagonal is only split off for square matrices */
+    const int split = separate_diagonal && num_rows == num_columns;
     int64_t *rowptr = calloc((size_t)num_rows + 2, sizeof(*rowptr));
     if (!rowptr) return ENOMEM;
     /* counts at rowptr[row] with 1-based rows -> after the prefix sum
      * rowptr[i] is the start of 0-based row i */
     for (int64_t k = 0; k < num_nonzeros; k++) {
+        if (split && rowidx[k] == colidx[k]) continue;
         rowptr[rowidx[k]]++;
         if (expand && rowidx[k] != colidx[k]) rowptr[colidx[k]]++;
     }
@@ -95,18 +107,24 @@ int csr_from_coo(struct csr_matrix *csr, int symmetric, idx_t num_rows, idx_t nu
         if (rowptr[i] > hi) hi = rowptr[i];
         rowptr[i] += rowptr[i - 1];
     }
-    csr->rowsizemin = (idx_t)lo;
-    csr->rowsizemax = (idx_t)hi;
+    csr->rowsizemin = (idx_t)(lo + (split ? 1 : 0));      /* csrspmv.c:1261 */
+    csr->rowsizemax = (idx_t)(hi + (split ? 1 : 0));
     csr->csrsize = rowptr[num_rows];
+    csr->diagsize = split ? num_rows : 0;
     size_t n = csr->csrsize > 0 ? (size_t)csr->csrsize : 1;
     csr->colidx = malloc(n * sizeof(idx_t));
     csr->a = malloc(n * sizeof(double));
     if (!csr->colidx || !csr->a) { free(rowptr); csr_free(csr); return ENOMEM; }
+    if (split) {
+        csr->ad = calloc(num_rows > 0 ? (size_t)num_rows : 1, sizeof(double));
+        if (!csr->ad) { free(rowptr); csr_free(csr); return ENOMEM; }
+    }
     /* stable placement: entry k goes to the next free slot of its row
      * (and, when expanding, its mirror image right after it:
      * csrspmv.c:1421-1425) */
     for (int64_t k = 0; k < num_nonzeros; k++) {
         const int64_t i = (int64_t)rowidx[k] - 1, j = (int64_t)colidx[k] - 1;
+        if (split && i == j) { csr->ad[i] += a[k]; continue; }
         int64_t d = rowptr[i]++;
         csr->colidx[d] = (idx_t)j;
         csr->a[d] = a[k];

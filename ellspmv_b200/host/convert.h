@@ -22,6 +22,7 @@ struct ell_matrix {
     int64_t ellsize;    /* rows * K */
     idx_t *colidx;      /* ellsize */
     double *a;          /* ellsize */
+    double *ad;         /* diagsize entries when the diagonal is stored separately, else NULL */
 };
 
 struct csr_matrix {
@@ -31,13 +32,23 @@ struct csr_matrix {
     int64_t *rowptr;    /* num_rows + 1 */
     idx_t *colidx;      /* csrsize */
     double *a;          /* csrsize */
+    idx_t diagsize;     /* num_rows when the diagonal is stored separately, else 0 */
+    double *ad;         /* diagsize entries, or NULL */
 };
 
-/* rowidx/colidx are 1-based as read from the file.  Return 0 or errno. */
+/* rowidx/colidx are 1-based as read from the file.  Return 0 or errno.
+ *
+ * separate_diagonal: entries with row == column are summed (file order) into
+ * `ad` and left out of the ELL/CSR arrays.  For ELL this is what the
+ * reference's converters do when their two flags arrive in DECLARED order
+ * (ellspmv.c:946-949, 1098-1101); its own main() swaps them (Q1).  For CSR it
+ * is csrspmv.c:1249-1252 / 1409-1435 (square matrices; rowsizemin/max then
+ * count the diagonal). */
 int ell_from_coo(struct ell_matrix *ell, idx_t num_rows, idx_t num_columns, int64_t num_nonzeros,
-                 const idx_t *rowidx, const idx_t *colidx, const double *a);
+                 const idx_t *rowidx, const idx_t *colidx, const double *a, int separate_diagonal);
 int csr_from_coo(struct csr_matrix *csr, int symmetric, idx_t num_rows, idx_t num_columns,
-                 int64_t num_nonzeros, const idx_t *rowidx, const idx_t *colidx, const double *a);
+                 int64_t num_nonzeros, const idx_t *rowidx, const idx_t *colidx, const double *a,
+                 int separate_diagonal);
 void ell_free(struct ell_matrix *ell);
 void csr_free(struct csr_matrix *csr);
 

@@ -12,8 +12,10 @@
  * The reference's OpenMP thread-partitioning options (--partition-rows,
  * --partition-nonzeros, --precompute-partition, --rows-per-thread,
  * --columns-per-thread) describe how CPU threads split the rows; they are
- * accepted and ignored (a note is printed with -v).  --separate-diagonal and
- * --sort-rows are not implemented on the device path and are refused.
+ * accepted and ignored (a note is printed with -v).  --separate-diagonal is
+ * supported for square matrices (csrgemvsd, csrspmv.c:1598-1629; on a
+ * non-square matrix the reference skips the split but still reads the absent
+ * diagonal array, so that case is refused).  --sort-rows is refused.
  */
 #include <errno.h>
 #include <locale.h>
@@ -154,8 +156,8 @@ int main(int argc, char *argv[])
         fprintf(stderr, "%s: %s %s\n", prog, strerror(err), bad < argc ? argv[bad] : "");
         return EXIT_FAILURE;
     }
-    if (o.separate_diagonal || o.sort_rows) {
-        fprintf(stderr, "%s: --separate-diagonal/--sort-rows are not implemented on the CUDA path\n", prog);
+    if (o.sort_rows) {
+        fprintf(stderr, "%s: --sort-rows is not implemented on the CUDA path\n", prog);
         return EXIT_FAILURE;
     }
     if (o.ignored_partition && o.verbose > 0)
@@ -199,7 +201,13 @@ int main(int argc, char *argv[])
     /* 3. convert to CSR (csrspmv.c:1911-2287) */
     if (o.verbose > 0) { fprintf(stderr, "csr_from_coo: "); clock_gettime(CLOCK_MONOTONIC, &t0); }
     struct csr_matrix csr;
-    err = csr_from_coo(&csr, h.symmetry == MTX_SYMMETRIC, num_rows, num_columns, num_nonzeros, rowidx, colidx, a);
+    if (o.separate_diagonal && num_rows != num_columns) {
+        if (o.verbose > 0) fprintf(stderr, "\n");
+        fprintf(stderr, "%s: --separate-diagonal needs a square matrix\n", prog);
+        return EXIT_FAILURE;
+    }
+    err = csr_from_coo(&csr, h.symmetry == MTX_SYMMETRIC, num_rows, num_columns, num_nonzeros, rowidx, colidx, a,
+                       o.separate_diagonal);
     free(a); free(colidx); free(rowidx);
     if (err) {
         if (o.verbose > 0) fprintf(stderr, "\n");
@@ -207,16 +215,18 @@ int main(int argc, char *argv[])
         return EXIT_FAILURE;
     }
     const int64_t csrsize = csr.csrsize;
+    const int64_t diagsize = csr.diagsize;
     if (o.verbose > 0) {
         clock_gettime(CLOCK_MONOTONIC, &t1);
         fprintf(stderr, "%'.6f seconds, %'" PRIdx " rows, %'" PRIdx " columns, %'" PRId64 " nonzeros"
                         ", %'" PRIdx " to %'" PRIdx " nonzeros per row\n",
-                seconds_between(t0, t1), num_rows, num_columns, csrsize, csr.rowsizemin, csr.rowsizemax);
+                seconds_between(t0, t1), num_rows, num_columns, csrsize + diagsize, csr.rowsizemin, csr.rowsizemax);
     }
 
     if (o.verbose > 0) { fprintf(stderr, "cuda_upload: "); clock_gettime(CLOCK_MONOTONIC, &t0); }
     csrspmv_cuda_matrix *A = NULL;
     err = csrspmv_cuda_upload(&A, IDX_BITS, num_rows, num_columns, csr.rowptr, csr.colidx, csr.a, 1, o.flags);
+    if (!err && csr.ad) err = csrspmv_cuda_set_diagonal(A, csr.ad);
     csr_free(&csr);
     if (err) {
         if (o.verbose > 0) fprintf(stderr, "\n");
@@ -254,15 +264,17 @@ int main(int argc, char *argv[])
             goto fail;
         }
         if (o.verbose > 0) {
-            /* the reference's model with diagsize = 0 (csrspmv.c:2882-2887) */
-            const int64_t num_flops = 2 * csrsize;
+            /* the reference's model (csrspmv.c:2882-2887) */
+            const int64_t num_flops = 2 * (csrsize + diagsize);
             const int64_t min_bytes = (int64_t)num_rows * 8 + (int64_t)num_columns * 8 +
-                                      ((int64_t)num_rows + 1) * 8 + csrsize * (int64_t)sizeof(idx_t) + csrsize * 8;
+                                      ((int64_t)num_rows + 1) * 8 + csrsize * (int64_t)sizeof(idx_t) + csrsize * 8 +
+                                      diagsize * 8;
             const int64_t max_bytes = (int64_t)num_rows * 8 + csrsize * 8 + (int64_t)num_rows * 8 +
-                                      csrsize * (int64_t)sizeof(idx_t) + csrsize * 8;
+                                      csrsize * (int64_t)sizeof(idx_t) + csrsize * 8 + diagsize * 8 + diagsize * 8;
             for (int r = 0; r < total; r++) {
                 const double t = secs[r];
-                fprintf(stderr, r < o.warmup ? "gemv (warmup): " : "gemv: ");
+                const char *label = o.separate_diagonal ? "gemvsd" : "gemv";
+                fprintf(stderr, r < o.warmup ? "%s (warmup): " : "%s: ", label);
                 fprintf(stderr, "%'.6f seconds (%'.3f Gnz/s, %'.3f Gflop/s, %'.1f to %'.1f GB/s)\n", t,
                         (double)num_nonzeros * 1e-9 / t, (double)num_flops * 1e-9 / t,
                         (double)min_bytes * 1e-9 / t, (double)max_bytes * 1e-9 / t);

@@ -14,9 +14,12 @@
  *     ellspmv_cuda_free()
  *
  * Known differences, on purpose:
- *   - --separate-diagonal / --sort-rows are refused: in the reference they
- *     are passed swapped into ell_from_coo and corrupt the result
- *     (ellspmv.c:1094-1095 vs 1468-1471);
+ *   - --separate-diagonal does what the reference's functions do when their
+ *     flags arrive in DECLARED order (diagonal summed into `ad`, K counted
+ *     without it, kernel ellgemvsd / ellgemv16sd): the reference's main()
+ *     passes the two flags swapped into ell_from_coo and overruns its arrays
+ *     (ellspmv.c:1094-1095 vs 1468-1471).  --sort-rows is refused: the
+ *     reference's ELL rowsort sorts the wrong ranges (ellspmv.c:1121-1123);
  *   - x from a file is read with num_columns entries (the reference reads
  *     num_rows, ellspmv.c:1574-1575, which is only right for square A);
  *   - a matrix with more rows than columns works (the reference overruns its
@@ -74,7 +77,7 @@ static void help(FILE *f)
 #ifdef HAVE_LIBZ
     fprintf(f, "  -z, --gzip, --gunzip, --ungzip    filter files through gzip\n");
 #endif
-    fprintf(f, "  --separate-diagonal  (refused: broken in the reference, see source)\n");
+    fprintf(f, "  --separate-diagonal  store diagonal nonzeros separately\n");
     fprintf(f, "  --sort-rows          (refused: broken in the reference, see source)\n");
     fprintf(f, "  --repeat=N           repeat matrix-vector multiplication N times\n");
     fprintf(f, "  --warmup=N                perform N additional warmup iterations\n");
@@ -225,9 +228,13 @@ int main(int argc, char *argv[])
         fprintf(stderr, "%s: %s %s\n", prog, strerror(err), bad < argc ? argv[bad] : "");
         return EXIT_FAILURE;
     }
-    if (o.separate_diagonal || o.sort_rows) {
-        fprintf(stderr, "%s: --separate-diagonal/--sort-rows are not supported: the reference passes them "
-                        "swapped into ell_from_coo and computes a wrong result\n", prog);
+    if (o.sort_rows) {
+        fprintf(stderr, "%s: --sort-rows is not supported: the reference's ELL rowsort is handed per-row "
+                        "counts instead of offsets and scrambles the matrix\n", prog);
+        return EXIT_FAILURE;
+    }
+    if (o.separate_diagonal && o.synthetic) {
+        fprintf(stderr, "%s: --separate-diagonal is not supported with --synthetic\n", prog);
         return EXIT_FAILURE;
     }
 
@@ -307,7 +314,12 @@ int main(int argc, char *argv[])
         /* 3. convert to ELLPACK (ellspmv.c:1379-1486) */
         if (o.verbose > 0) { fprintf(stderr, "ell_from_coo: "); clock_gettime(CLOCK_MONOTONIC, &t0); }
         struct ell_matrix ell;
-        err = ell_from_coo(&ell, num_rows, num_columns, num_nonzeros, rowidx, colidx, a);
+        if (o.separate_diagonal && num_rows > num_columns) {
+            if (o.verbose > 0) fprintf(stderr, "\n");
+            fprintf(stderr, "%s: --separate-diagonal needs rows <= columns (the kernel reads x[i] for every row)\n", prog);
+            return EXIT_FAILURE;
+        }
+        err = ell_from_coo(&ell, num_rows, num_columns, num_nonzeros, rowidx, colidx, a, o.separate_diagonal);
         free(a); free(colidx); free(rowidx);
         if (err) {
             if (o.verbose > 0) fprintf(stderr, "\n");
@@ -328,6 +340,9 @@ int main(int argc, char *argv[])
                                             ell.colidx, ell.a, o.device, o.flags);
         else
             err = ellspmv_cuda_upload(&A, IDX_BITS, num_rows, num_columns, rowsize, ell.colidx, ell.a, 1, o.flags);
+        /* same dispatch as the reference: K == 16 takes the unrolled kernel's
+         * summation order (ellspmv.c:1759-1768) */
+        if (!err && o.separate_diagonal) err = ellspmv_cuda_set_diagonal(A, ell.ad, rowsize == 16 ? 1 : 0);
         ell_free(&ell);
         if (err) {
             if (o.verbose > 0) fprintf(stderr, "\n");
@@ -380,7 +395,8 @@ int main(int argc, char *argv[])
             double best = 0.0;
             for (int r = 0; r < total; r++) {
                 const double t = secs[r];
-                fprintf(stderr, r < o.warmup ? "gemv (warmup): " : "gemv: ");
+                const char *label = !o.separate_diagonal ? "gemv" : (rowsize == 16 ? "gemv16sd" : "gemvsd");
+                fprintf(stderr, r < o.warmup ? "%s (warmup): " : "%s: ", label);
                 fprintf(stderr, "%'.6f seconds (%'.3f Gnz/s, %'.3f Gflop/s, %'.1f to %'.1f GB/s)\n", t,
                         (double)num_nonzeros * 1e-9 / t, (double)num_flops * 1e-9 / t,
                         (double)min_bytes * 1e-9 / t, (double)max_bytes * 1e-9 / t);

@@ -33,37 +33,62 @@ static int read_coo(const char *path, int gzip, struct mtx_header *h, idx_t **ri
     return err;
 }
 
-/* dims = {rows, cols, nnz, rowsize, ellsize, diagsize, lines_read} */
+/* dims = {rows, cols, nnz, rowsize, ellsize, diagsize, lines_read}; ad may be NULL */
+int host_ell_from_file_sd(const char *path, int gzip, int separate_diagonal, int64_t dims[7],
+                          void **colidx, double **a, double **ad);
+
 int host_ell_from_file(const char *path, int gzip, int64_t dims[7], void **colidx, double **a)
+{
+    double *ad = NULL;
+    int err = host_ell_from_file_sd(path, gzip, 0, dims, colidx, a, &ad);
+    free(ad);
+    return err;
+}
+
+int host_ell_from_file_sd(const char *path, int gzip, int separate_diagonal, int64_t dims[7],
+                          void **colidx, double **a, double **ad)
 {
     struct mtx_header h;
     idx_t *ri, *ci; double *v;
     int err = read_coo(path, gzip, &h, &ri, &ci, &v, &dims[6]);
     if (err) return err;
     struct ell_matrix ell;
-    err = ell_from_coo(&ell, h.num_rows, h.num_columns, h.num_nonzeros, ri, ci, v);
+    err = ell_from_coo(&ell, h.num_rows, h.num_columns, h.num_nonzeros, ri, ci, v, separate_diagonal);
     free(ri); free(ci); free(v);
     if (err) return err;
     dims[0] = ell.num_rows; dims[1] = ell.num_columns; dims[2] = h.num_nonzeros;
     dims[3] = ell.rowsize; dims[4] = ell.ellsize; dims[5] = ell.diagsize;
-    *colidx = ell.colidx; *a = ell.a;
+    *colidx = ell.colidx; *a = ell.a; *ad = ell.ad;
     return 0;
 }
 
 /* dims = {rows, cols, nnz, csrsize, rowsizemin, rowsizemax, lines_read} */
+int host_csr_from_file_sd(const char *path, int gzip, int separate_diagonal, int64_t dims[7],
+                          int64_t **rowptr, void **colidx, double **a, double **ad);
+
 int host_csr_from_file(const char *path, int gzip, int64_t dims[7], int64_t **rowptr, void **colidx, double **a)
+{
+    double *ad = NULL;
+    int err = host_csr_from_file_sd(path, gzip, 0, dims, rowptr, colidx, a, &ad);
+    free(ad);
+    return err;
+}
+
+int host_csr_from_file_sd(const char *path, int gzip, int separate_diagonal, int64_t dims[7],
+                          int64_t **rowptr, void **colidx, double **a, double **ad)
 {
     struct mtx_header h;
     idx_t *ri, *ci; double *v;
     int err = read_coo(path, gzip, &h, &ri, &ci, &v, &dims[6]);
     if (err) return err;
     struct csr_matrix csr;
-    err = csr_from_coo(&csr, h.symmetry == MTX_SYMMETRIC, h.num_rows, h.num_columns, h.num_nonzeros, ri, ci, v);
+    err = csr_from_coo(&csr, h.symmetry == MTX_SYMMETRIC, h.num_rows, h.num_columns, h.num_nonzeros, ri, ci, v,
+                       separate_diagonal);
     free(ri); free(ci); free(v);
     if (err) return err;
     dims[0] = csr.num_rows; dims[1] = csr.num_columns; dims[2] = h.num_nonzeros;
     dims[3] = csr.csrsize; dims[4] = csr.rowsizemin; dims[5] = csr.rowsizemax;
-    *rowptr = csr.rowptr; *colidx = csr.colidx; *a = csr.a;
+    *rowptr = csr.rowptr; *colidx = csr.colidx; *a = csr.a; *ad = csr.ad;
     return 0;
 }
 

@@ -170,6 +170,16 @@ int ellspmv_cuda_spmv_push(
     int num_peers, double *const *peer_x,
     const int64_t *peer_row_lo, const int64_t *peer_row_hi, void *stream);
 
+/*
+ * Attach a separately stored diagonal: afterwards every spmv computes
+ * y <- y + (ad .* x + A*x), the reference's ellgemvsd (ellspmv.c:1155-1180;
+ * order 0: yi summed from 0, then ad*x + yi) or ellgemv16sd
+ * (ellspmv.c:1182-1221; order 1: the sum starts at ad*x).  ad has the shard's
+ * num_rows entries (host or device memory) and is copied; NULL detaches it.
+ * Needs rows <= columns, like the reference's kernels (they read x[i]).
+ */
+int ellspmv_cuda_set_diagonal(ellspmv_cuda_matrix *A, const double *ad, int order);
+
 /* Copy the device matrix back as row-major host arrays of the caller's
  * index width (inverse of upload; used to test bit-exactness). */
 int ellspmv_cuda_download(
@@ -193,6 +203,10 @@ int csrspmv_cuda_generate(
     csrspmv_cuda_matrix **out, int kind, const int64_t dims[3],
     const double vals[2], uint64_t seed, int idx_width_bits,
     int device, unsigned flags);
+
+/* attach the separately stored diagonal of csrgemvsd (csrspmv.c:1598-1629):
+ * y <- y + (ad .* x + A*x); ad has num_rows entries, NULL detaches it */
+int csrspmv_cuda_set_diagonal(csrspmv_cuda_matrix *A, const double *ad);
 
 /* replaces the csrgemv call, csrspmv.c:2857-2858 */
 int csrspmv_cuda_spmv(

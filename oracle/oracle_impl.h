@@ -188,6 +188,149 @@ int ONAME(oracle_csrgemv)(
 }
 
 /* ------------------------------------------------------------------ */
+/* Separate-diagonal variants.                 */
+/* ------------------------------------------------------------------ */
+
+/*
+ * ELL conversion with the diagonal split off, as ell_from_coo_size /
+ * ell_from_coo behave when their flags are passed in DECLARED order
+ * (separate_diagonal = true, sort_rows = false; ellspmv.c:946-949,
+ * 1098-1107).  The reference's own main() passes the two flags swapped
+ * (Q1), so this is the function-level contract, not the program's.
+ * K counts off-diagonal entries only; ellad[i] accumulates every (i,i)
+ * entry in file order; diagsize = min(rows, cols).
+ */
+int ONAME(oracle_ell_from_coo_sd_size)(
+    OIDX num_rows, OIDX num_columns, int64_t num_nonzeros,
+    const OIDX *rowidx, const OIDX *colidx, int64_t *rowcount,
+    int64_t *ellsize, OIDX *rowsize, OIDX *diagsize)
+{
+    for (int64_t i = 0; i <= (int64_t)num_rows; i++) rowcount[i] = 0;
+    for (int64_t k = 0; k < num_nonzeros; k++)
+        if (rowidx[k] != colidx[k]) rowcount[rowidx[k]]++;
+    int64_t widest = 0;
+    for (int64_t i = 1; i <= (int64_t)num_rows; i++) {
+        if (rowcount[i] > widest) widest = rowcount[i];
+        rowcount[i] += rowcount[i - 1];
+    }
+    *rowsize = (OIDX)widest;
+    *ellsize = (int64_t)num_rows * widest;
+    *diagsize = num_rows < num_columns ? num_rows : num_columns;
+    return 0;
+}
+
+int ONAME(oracle_ell_from_coo_sd)(
+    OIDX num_rows, OIDX num_columns, int64_t num_nonzeros,
+    const OIDX *rowidx, const OIDX *colidx, const double *a,
+    int64_t *fill, OIDX rowsize, OIDX *ellcolidx, double *ella, double *ellad)
+{
+    const int64_t K = rowsize;
+    const int64_t diagsize = num_rows < num_columns ? num_rows : num_columns;
+    for (int64_t i = 0; i <= (int64_t)num_rows; i++) fill[i] = 0;
+    for (int64_t i = 0; i < diagsize; i++) ellad[i] = 0.0;
+    for (int64_t k = 0; k < num_nonzeros; k++) {
+        int64_t r = (int64_t)rowidx[k] - 1;
+        if (rowidx[k] == colidx[k]) { ellad[r] += a[k]; continue; }
+        int64_t slot = r * K + fill[r];
+        ellcolidx[slot] = colidx[k] - 1;
+        ella[slot] = a[k];
+        fill[r]++;
+    }
+    for (int64_t r = 0; r < (int64_t)num_rows; r++) {
+        OIDX padcol = r < (int64_t)num_columns ? (OIDX)r : (OIDX)(num_columns - 1);
+        for (int64_t l = fill[r]; l < K; l++) { ellcolidx[r * K + l] = padcol; ella[r * K + l] = 0.0; }
+    }
+    return 0;
+}
+
+/*
+ * y <- y + (ad.*x + A*x).  order 0 follows ellgemvsd, ellspmv.c:1173-1178:
+ * yi = sum of the slots from 0, then y += ad*x + yi.  order 1 follows the
+ * hand-unrolled ellgemv16sd, ellspmv.c:1201-1219, generalised to any K:
+ * the sum starts from ad*x and the slots are added to it left to right.
+ */
+int ONAME(oracle_ellgemvsd)(
+    OIDX num_rows, double *y, const double *x,
+    OIDX rowsize, const OIDX *colidx, const double *a, const double *ad, int order)
+{
+    const int64_t K = rowsize;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static)
+#endif
+    for (int64_t r = 0; r < (int64_t)num_rows; r++) {
+        const OIDX *c = colidx + r * K;
+        const double *v = a + r * K;
+        double dx = ad[r] * x[r];
+        double acc = order ? dx : 0.0;
+        for (int64_t l = 0; l < K; l++) {
+            double prod = v[l] * x[c[l]];
+            acc = acc + prod;
+        }
+        if (!order) acc = dx + acc;
+        y[r] = y[r] + acc;
+    }
+    return 0;
+}
+
+/*
+ * CSR with the diagonal split off, square general matrices: follows
+ * csr_from_coo_size (csrspmv.c:1249-1252, 1261, 1265) and csr_from_coo
+ * (csrspmv.c:1428-1435).  rowsizemin/max count the diagonal (+1).
+ */
+int ONAME(oracle_csr_from_coo_sd)(
+    OIDX num_rows, int64_t num_nonzeros,
+    const OIDX *rowidx, const OIDX *colidx, const double *a,
+    int64_t *rowptr, int64_t *csrsize, OIDX *rowsizemin, OIDX *rowsizemax,
+    OIDX *csrcolidx, double *csra, double *csrad)
+{
+    for (int64_t i = 0; i <= (int64_t)num_rows; i++) rowptr[i] = 0;
+    for (int64_t k = 0; k < num_nonzeros; k++)
+        if (rowidx[k] != colidx[k]) rowptr[rowidx[k]]++;
+    int64_t lo = num_rows > 0 ? rowptr[1] : 0, hi = 0;
+    for (int64_t i = 1; i <= (int64_t)num_rows; i++) {
+        if (rowptr[i] < lo) lo = rowptr[i];
+        if (rowptr[i] > hi) hi = rowptr[i];
+        rowptr[i] += rowptr[i - 1];
+    }
+    *rowsizemin = (OIDX)(lo + 1);
+    *rowsizemax = (OIDX)(hi + 1);
+    *csrsize = rowptr[num_rows];
+    if (!csrcolidx) return 0;                       /* size pass only */
+    for (int64_t i = 0; i < (int64_t)num_rows; i++) csrad[i] = 0.0;
+    for (int64_t k = 0; k < num_nonzeros; k++) {
+        int64_t i = (int64_t)rowidx[k] - 1, j = (int64_t)colidx[k] - 1;
+        if (i == j) { csrad[i] += a[k]; continue; }
+        int64_t dst = rowptr[i]++;
+        csrcolidx[dst] = (OIDX)j;
+        csra[dst] = a[k];
+    }
+    for (int64_t i = num_rows; i > 0; i--) rowptr[i] = rowptr[i - 1];
+    rowptr[0] = 0;
+    return 0;
+}
+
+/* y <- y + (ad.*x + A*x) on CSR; follows csrgemvsd, csrspmv.c:1622-1627 */
+int ONAME(oracle_csrgemvsd)(
+    OIDX num_rows, double *y, const double *x,
+    const int64_t *rowptr, const OIDX *colidx, const double *a, const double *ad)
+{
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static)
+#endif
+    for (int64_t r = 0; r < (int64_t)num_rows; r++) {
+        double acc = 0.0;
+        for (int64_t k = rowptr[r]; k < rowptr[r + 1]; k++) {
+            double prod = a[k] * x[colidx[k]];
+            acc = acc + prod;
+        }
+        double dx = ad[r] * x[r];
+        acc = dx + acc;
+        y[r] = y[r] + acc;
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------ */
 /* Synthetic matrices of BASELINE.json's shapes.      */
 /* Each generator can emit the ELL arrays for a row range directly     */
 /* (row-major, reference padding rule) and the 1-based COO stream in   */

@@ -126,6 +126,59 @@ class Oracle:
         f.argtypes = [I, _P, _P, _P, _P, _P]
         assert f(num_rows, _p(y), _p(x), _p(rowptr), _p(colidx), _p(a)) == 0
 
+    # -- separate-diagonal variants ------------------------------------------------
+    def ell_from_coo_sd(self, num_rows, num_columns, rowidx, colidx, a):
+        """-> (rowsize, ellsize, diagsize, ellcolidx, ella, ellad): flags in declared order (Q1)."""
+        bits = rowidx.dtype.itemsize * 8
+        I = C.c_int32 if bits == 32 else C.c_int64
+        nnz = len(a)
+        rowcount = np.zeros(num_rows + 1, dtype=np.int64)
+        ellsize, rowsize, diagsize = _I64(), I(), I()
+        f = self._f("oracle_ell_from_coo_sd_size", bits)
+        f.argtypes = [I, I, _I64, _P, _P, _P, C.POINTER(_I64), C.POINTER(I), C.POINTER(I)]
+        assert f(num_rows, num_columns, nnz, _p(rowidx), _p(colidx), _p(rowcount), C.byref(ellsize),
+                 C.byref(rowsize), C.byref(diagsize)) == 0
+        ec = np.zeros(ellsize.value, dtype=_idt(bits))
+        ea = np.zeros(ellsize.value, dtype=np.float64)
+        ad = np.zeros(max(diagsize.value, 1), dtype=np.float64)[:diagsize.value]
+        g = self._f("oracle_ell_from_coo_sd", bits)
+        g.argtypes = [I, I, _I64, _P, _P, _P, _P, I, _P, _P, _P]
+        assert g(num_rows, num_columns, nnz, _p(rowidx), _p(colidx), _p(a), _p(rowcount), rowsize.value,
+                 _p(ec), _p(ea), _p(ad)) == 0
+        return rowsize.value, ellsize.value, diagsize.value, ec, ea, ad
+
+    def ellgemvsd(self, num_rows, y, x, rowsize, colidx, a, ad, order: int = 0) -> None:
+        bits = colidx.dtype.itemsize * 8
+        I = C.c_int32 if bits == 32 else C.c_int64
+        f = self._f("oracle_ellgemvsd", bits)
+        f.argtypes = [I, _P, _P, I, _P, _P, _P, C.c_int]
+        assert f(num_rows, _p(y), _p(x), rowsize, _p(colidx), _p(a), _p(ad), order) == 0
+
+    def csr_from_coo_sd(self, num_rows, rowidx, colidx, a):
+        """square general matrix -> (rowptr, csrcolidx, csra, csrad, rowsizemin, rowsizemax)"""
+        bits = rowidx.dtype.itemsize * 8
+        I = C.c_int32 if bits == 32 else C.c_int64
+        nnz = len(a)
+        rowptr = np.zeros(num_rows + 1, dtype=np.int64)
+        csrsize, lo, hi = _I64(), I(), I()
+        f = self._f("oracle_csr_from_coo_sd", bits)
+        f.argtypes = [I, _I64, _P, _P, _P, _P, C.POINTER(_I64), C.POINTER(I), C.POINTER(I), _P, _P, _P]
+        assert f(num_rows, nnz, _p(rowidx), _p(colidx), _p(a), _p(rowptr), C.byref(csrsize), C.byref(lo),
+                 C.byref(hi), None, None, None) == 0
+        cc = np.zeros(max(csrsize.value, 1), dtype=_idt(bits))[:csrsize.value]
+        ca = np.zeros(max(csrsize.value, 1), dtype=np.float64)[:csrsize.value]
+        ad = np.zeros(max(num_rows, 1), dtype=np.float64)[:num_rows]
+        assert f(num_rows, nnz, _p(rowidx), _p(colidx), _p(a), _p(rowptr), C.byref(csrsize), C.byref(lo),
+                 C.byref(hi), _p(cc), _p(ca), _p(ad)) == 0
+        return rowptr, cc, ca, ad, lo.value, hi.value
+
+    def csrgemvsd(self, num_rows, y, x, rowptr, colidx, a, ad) -> None:
+        bits = colidx.dtype.itemsize * 8
+        I = C.c_int32 if bits == 32 else C.c_int64
+        f = self._f("oracle_csrgemvsd", bits)
+        f.argtypes = [I, _P, _P, _P, _P, _P, _P]
+        assert f(num_rows, _p(y), _p(x), _p(rowptr), _p(colidx), _p(a), _p(ad)) == 0
+
     # -- synthetic matrices -----------------------------------------------------
     def gen_ell(self, kind: str, dims, vals=(0.0, 0.0), seed: int = 42, bits: int = 32,
                 row_begin: int = 0, row_end: Optional[int] = None):
@@ -265,3 +318,50 @@ class Reference:
         assert f(num_rows, _p(y), num_columns, _p(x), int(rowptr[num_rows]), rowsizemin, rowsizemax,
                  _p(rowptr), _p(colidx), _p(a), repeat, _p(secs)) == 0
         return secs
+
+    # -- separate-diagonal functions of the reference -------------------------------
+    def ell_from_coo_sd(self, num_rows, num_columns, rowidx, colidx, a):
+        nnz = len(a)
+        rowptr = np.zeros(num_rows + 1, dtype=np.int64)
+        ellsize, rowsize, diagsize = _I64(), _I64(), _I64()
+        f = self.lib.ref_ell_from_coo_sd_size
+        f.argtypes = [_I64, _I64, _I64, _P, _P, _P, _P, C.POINTER(_I64), C.POINTER(_I64), C.POINTER(_I64)]
+        assert f(num_rows, num_columns, nnz, _p(rowidx), _p(colidx), _p(a), _p(rowptr), C.byref(ellsize),
+                 C.byref(rowsize), C.byref(diagsize)) == 0
+        ec = np.empty(max(ellsize.value, 1), dtype=_idt(self.bits))[:ellsize.value]
+        ea = np.empty(max(ellsize.value, 1), dtype=np.float64)[:ellsize.value]
+        ad = np.empty(max(diagsize.value, 1), dtype=np.float64)[:diagsize.value]
+        g = self.lib.ref_ell_from_coo_sd
+        g.argtypes = [_I64, _I64, _I64, _P, _P, _P, _P, _I64, _I64, _P, _P, _P]
+        assert g(num_rows, num_columns, nnz, _p(rowidx), _p(colidx), _p(a), _p(rowptr), ellsize.value,
+                 rowsize.value, _p(ec), _p(ea), _p(ad)) == 0
+        return rowsize.value, ellsize.value, diagsize.value, ec, ea, ad
+
+    def ellgemvsd(self, which, num_rows, y, num_columns, x, rowsize, colidx, a, ad) -> int:
+        f = self.lib.ref_ellgemvsd
+        f.argtypes = [C.c_int, _I64, _P, _I64, _P, _I64, _I64, _P, _P, _P]
+        return f(which, num_rows, _p(y), num_columns, _p(x), num_rows * rowsize, rowsize, _p(colidx), _p(a), _p(ad))
+
+    def csr_from_coo_sd(self, num_rows, num_columns, rowidx, colidx, a, symmetric: bool = False):
+        nnz = len(a)
+        rowptr = np.zeros(num_rows + 1, dtype=np.int64)
+        csrsize, lo, hi, ds = _I64(), _I64(), _I64(), _I64()
+        f = self.lib.ref_csr_from_coo_sd_size
+        f.argtypes = [C.c_int, _I64, _I64, _I64, _P, _P, _P, _P, C.POINTER(_I64), C.POINTER(_I64),
+                      C.POINTER(_I64), C.POINTER(_I64)]
+        assert f(int(symmetric), num_rows, num_columns, nnz, _p(rowidx), _p(colidx), _p(a), _p(rowptr),
+                 C.byref(csrsize), C.byref(lo), C.byref(hi), C.byref(ds)) == 0
+        cc = np.empty(max(csrsize.value, 1), dtype=_idt(self.bits))[:csrsize.value]
+        ca = np.empty(max(csrsize.value, 1), dtype=np.float64)[:csrsize.value]
+        ad = np.empty(max(num_rows, 1), dtype=np.float64)[:num_rows]
+        g = self.lib.ref_csr_from_coo_sd
+        g.argtypes = [C.c_int, _I64, _I64, _I64, _P, _P, _P, _P, _I64, _I64, _I64, _P, _P, _P]
+        assert g(int(symmetric), num_rows, num_columns, nnz, _p(rowidx), _p(colidx), _p(a), _p(rowptr),
+                 csrsize.value, lo.value, hi.value, _p(cc), _p(ca), _p(ad)) == 0
+        return rowptr, cc, ca, ad, lo.value, hi.value, ds.value
+
+    def csrgemvsd(self, num_rows, y, num_columns, x, rowptr, colidx, a, ad, rowsizemin=0, rowsizemax=0) -> None:
+        f = self.lib.ref_csrgemvsd
+        f.argtypes = [_I64, _P, _I64, _P, _I64, _I64, _I64, _P, _P, _P, _P]
+        assert f(num_rows, _p(y), num_columns, _p(x), int(rowptr[num_rows]), rowsizemin, rowsizemax, _p(rowptr),
+                 _p(colidx), _p(a), _p(ad)) == 0

@@ -93,3 +93,59 @@ int ref_csrgemv(
     }
     return err;
 }
+
+/* ---- separate diagonal (square matrices; csrspmv.c:1249-1252, 1428-1435) ---- */
+int ref_csr_from_coo_sd_size(
+    int symmetric, int64_t num_rows, int64_t num_columns, int64_t num_nonzeros,
+    const void *rowidx, const void *colidx, const double *a,
+    int64_t *rowptr, int64_t *csrsize, int64_t *rowsizemin, int64_t *rowsizemax, int64_t *diagsize)
+{
+    idx_t lo = 0, hi = 0, ds = 0;
+    int err = csr_from_coo_size(
+        symmetric ? mtxsymmetric : mtxgeneral,
+        (idx_t)num_rows, (idx_t)num_columns, num_nonzeros,
+        (const idx_t *)rowidx, (const idx_t *)colidx, a,
+        rowptr, csrsize, &lo, &hi, &ds, true, partition_rows);
+    *rowsizemin = lo; *rowsizemax = hi; *diagsize = ds;
+    return err;
+}
+
+int ref_csr_from_coo_sd(
+    int symmetric, int64_t num_rows, int64_t num_columns, int64_t num_nonzeros,
+    const void *rowidx, const void *colidx, const double *a,
+    int64_t *rowptr, int64_t csrsize, int64_t rowsizemin, int64_t rowsizemax,
+    void *csrcolidx, double *csra, double *csrad)
+{
+    idx_t *cc = (idx_t *)csrcolidx;
+    for (int64_t k = 0; k < csrsize; k++) { cc[k] = 0; csra[k] = 0; }
+    for (int64_t k = 0; k < num_rows; k++) csrad[k] = 0;
+    return csr_from_coo(
+        symmetric ? mtxsymmetric : mtxgeneral,
+        (idx_t)num_rows, (idx_t)num_columns, num_nonzeros,
+        (const idx_t *)rowidx, (const idx_t *)colidx, a,
+        rowptr, csrsize, (idx_t)rowsizemin, (idx_t)rowsizemax,
+        cc, csra, csrad, true, false, partition_rows);
+}
+
+int ref_csrgemvsd(
+    int64_t num_rows, double *y, int64_t num_columns, const double *x,
+    int64_t csrsize, int64_t rowsizemin, int64_t rowsizemax,
+    const int64_t *rowptr, const void *colidx, const double *a, const double *ad)
+{
+    int err = 0;
+#ifdef _OPENMP
+    #pragma omp parallel
+#endif
+    {
+        int priverr = csrgemvsd(
+            (idx_t)num_rows, y, (idx_t)num_columns, x, csrsize,
+            (idx_t)rowsizemin, (idx_t)rowsizemax, rowptr, (const idx_t *)colidx, a, ad);
+        if (priverr) {
+#ifdef _OPENMP
+            #pragma omp critical
+#endif
+            err = priverr;
+        }
+    }
+    return err;
+}

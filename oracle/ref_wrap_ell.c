@@ -120,3 +120,57 @@ void ref_first_touch(int64_t num_rows, int64_t rowsize, void *colidx, double *a,
 #endif
     for (int64_t i = 0; i < num_rows; i++) y[i] = 0.0;
 }
+
+/* ---- separate-diagonal functions, flags in DECLARED order (Q1) ---------- */
+int ref_ell_from_coo_sd_size(
+    int64_t num_rows, int64_t num_columns, int64_t num_nonzeros,
+    const void *rowidx, const void *colidx, const double *a,
+    int64_t *rowptr, int64_t *ellsize, int64_t *rowsize, int64_t *diagsize)
+{
+    idx_t rs = 0, ds = 0;
+    int err = ell_from_coo_size(
+        (idx_t)num_rows, (idx_t)num_columns, num_nonzeros,
+        (const idx_t *)rowidx, (const idx_t *)colidx, a,
+        rowptr, ellsize, &rs, &ds, true);
+    *rowsize = rs; *diagsize = ds;
+    return err;
+}
+
+int ref_ell_from_coo_sd(
+    int64_t num_rows, int64_t num_columns, int64_t num_nonzeros,
+    const void *rowidx, const void *colidx, const double *a,
+    int64_t *rowptr, int64_t ellsize, int64_t rowsize,
+    void *ellcolidx, double *ella, double *ellad)
+{
+    idx_t *ec = (idx_t *)ellcolidx;
+    for (int64_t k = 0; k < ellsize; k++) { ec[k] = 0; ella[k] = 0; }
+    int64_t ds = num_rows < num_columns ? num_rows : num_columns;
+    for (int64_t k = 0; k < ds; k++) ellad[k] = 0;
+    return ell_from_coo(
+        (idx_t)num_rows, (idx_t)num_columns, num_nonzeros,
+        (const idx_t *)rowidx, (const idx_t *)colidx, a,
+        rowptr, ellsize, (idx_t)rowsize, ec, ella, ellad, true, false);
+}
+
+/* which = 0: ellgemvsd, 1: ellgemv16sd (returns EINVAL unless rowsize == 16) */
+int ref_ellgemvsd(
+    int which, int64_t num_rows, double *y, int64_t num_columns, const double *x,
+    int64_t ellsize, int64_t rowsize, const void *colidx, const double *a, const double *ad)
+{
+    int err = 0;
+#ifdef _OPENMP
+    #pragma omp parallel
+#endif
+    {
+        int priverr = which
+            ? ellgemv16sd((idx_t)num_rows, y, (idx_t)num_columns, x, ellsize, (idx_t)rowsize, (const idx_t *)colidx, a, ad)
+            : ellgemvsd((idx_t)num_rows, y, (idx_t)num_columns, x, ellsize, (idx_t)rowsize, (const idx_t *)colidx, a, ad);
+        if (priverr) {
+#ifdef _OPENMP
+            #pragma omp critical
+#endif
+            err = priverr;
+        }
+    }
+    return err;
+}

@@ -97,6 +97,46 @@ def case(name, nrows, ncols, ri, ci, a, x, y0, tmp):
     return out
 
 
+def case_sd(name, n, ri, ci, a, x, y0, tmp):
+    """Separate-diagonal goldens on a square matrix: the reference's functions
+    with their flags in DECLARED order (ELL; its main() swaps them, Q1) and the
+    CSR program, whose --separate-diagonal path is correct."""
+    out = {"name": name, "num_rows": n, "num_columns": n, "rowidx": [int(t) for t in ri],
+           "colidx": [int(t) for t in ci], "a": hexlist(a), "x": hexlist(x), "y0": hexlist(y0)}
+    xv = np.asarray(x, dtype=np.float64)
+    for bits in (32, 64):
+        dt = np.int32 if bits == 32 else np.int64
+        r, c = np.asarray(ri, dtype=dt), np.asarray(ci, dtype=dt)
+        av = np.asarray(a, dtype=np.float64)
+        ell = Reference("ell", bits)
+        K, ellsize, diagsize, ec, ea, ad = ell.ell_from_coo_sd(n, n, r, c, av)
+        y = np.array(y0, dtype=np.float64)
+        assert ell.ellgemvsd(0, n, y, n, xv, K, ec, ea, ad) == 0
+        y16 = None
+        if K == 16:
+            y16 = np.array(y0, dtype=np.float64)
+            assert ell.ellgemvsd(1, n, y16, n, xv, K, ec, ea, ad) == 0
+        csr = Reference("csr", bits)
+        rowptr, cc, ca, cad, lo, hi, ds = csr.csr_from_coo_sd(n, n, r, c, av)
+        yc = np.array(y0, dtype=np.float64)
+        csr.csrgemvsd(n, yc, n, xv, rowptr, cc, ca, cad, lo, hi)
+        out[f"idx{bits}"] = {
+            "rowsize": K, "ellsize": ellsize, "diagsize": diagsize, "ellcolidx": [int(t) for t in ec],
+            "ella": hexlist(ea), "ellad": hexlist(ad), "y_ellgemvsd": hexlist(y),
+            "y_ellgemv16sd": hexlist(y16) if y16 is not None else None,
+            "rowptr": [int(t) for t in rowptr], "csrcolidx": [int(t) for t in cc], "csra": hexlist(ca),
+            "csrad": hexlist(cad), "rowsizemin": lo, "rowsizemax": hi, "csr_diagsize": ds, "y_csrgemvsd": hexlist(yc),
+        }
+    A = os.path.join(tmp, name + ".mtx")
+    write_mtx(A, n, n, ri, ci, a)
+    xf, yf = os.path.join(tmp, name + "_x.mtx"), os.path.join(tmp, name + "_y.mtx")
+    write_vec(xf, x)
+    write_vec(yf, y0)
+    out["program"] = {"csrspmv_sd": run_binary("csrspmv", ["--separate-diagonal", A]),
+                      "csrspmv64_sd_xy": run_binary("csrspmv64", ["--separate-diagonal", "--repeat=2", A, xf, yf])}
+    return out
+
+
 def main():
     cases = []
     with tempfile.TemporaryDirectory() as tmp:
@@ -129,6 +169,22 @@ def main():
         cases.append(case("one_row", 1, 9, [1] * 9, list(range(9, 0, -1)), [float(i) for i in range(1, 10)],
                           [0.5] * 9, [1.0], tmp))
         cases.append(case("empty", 5, 4, [], [], [], [1.0] * 4, [2.0] * 5, tmp))
+
+        # 4. separate-diagonal cases (square): generic, duplicate diagonal entries, K == 16
+        rng = np.random.default_rng(77)
+        n, nnz = 40, 260
+        ri = rng.integers(1, n + 1, nnz); ci = rng.integers(1, n + 1, nnz)
+        ri[:30] = ci[:30]                       # plenty of diagonal entries, some repeated
+        cases.append(case_sd("sd_rand", n, ri.tolist(), ci.tolist(), rng.uniform(-2, 2, nnz).tolist(),
+                             rng.uniform(-1, 1, n).tolist(), rng.uniform(-1, 1, n).tolist(), tmp))
+        n = 48                                   # every row: diagonal + exactly 16 off-diagonals -> ellgemv16sd
+        ri, ci = [], []
+        for i in range(1, n + 1):
+            offs = [j for j in rng.permutation(n) + 1 if j != i][:16]
+            cols = offs[:7] + [i] + offs[7:]
+            ri += [i] * len(cols); ci += [int(j) for j in cols]
+        cases.append(case_sd("sd_k16", n, ri, ci, rng.uniform(-2, 2, len(ri)).tolist(),
+                             rng.uniform(-1, 1, n).tolist(), rng.uniform(-1, 1, n).tolist(), tmp))
 
     for c in cases:
         # tmp paths differ run to run; nothing in stdout depends on them

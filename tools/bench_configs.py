@@ -42,6 +42,8 @@ def main():
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--quick", action="store_true", help="small shapes (smoke the script itself)")
     ap.add_argument("--variants", default="all")
+    ap.add_argument("--extra-flags", type=lambda t: int(t, 0), default=0, help="OR-ed into every variant's flags")
+    ap.add_argument("--no-csr", action="store_true")
     args = ap.parse_args()
     peak, _ = measured_peak()
     q = args.quick
@@ -66,6 +68,9 @@ def main():
         if args.variants != "all":
             variants = [v for v in variants if any(t in v[0] for t in args.variants.split(","))]
         for vname, flags in variants:
+            flags |= args.extra_flags
+            if args.extra_flags:
+                vname += f" +0x{args.extra_flags:x}"
             A = E.EllMatrix.generate(kind, dims, vals, 42, bits, flags=flags)
             i = A.info()
             rows, ncols, K = i.num_rows, i.num_columns, i.rowsize
@@ -83,7 +88,7 @@ def main():
                                   "gbs_as_stored": round(stored / med * 1e-6, 1)}), flush=True)
             A.free()
             del x, y
-        if name == "c4":
+        if name == "c4" and not args.no_csr:
             for vname, flags in (("csr stream (bit-exact)", E.KERNEL_THREAD), ("csr vector T=8", E.KERNEL_WARP)):
                 Cm = E.CsrMatrix.generate(E.GEN_RANDOM, dims, 42, bits, flags=flags)
                 rows, ncols, K = dims
