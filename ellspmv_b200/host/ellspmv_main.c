@@ -297,7 +297,7 @@ int main(int argc, char *argv[])
             fprintf(stderr, "%s: %s\n", prog, strerror(ENOMEM));
             return EXIT_FAILURE;
         }
-        err = mtx_read_coordinate(s, &h, rowidx, colidx, a, &lines, &bytes);
+        err = (getenv("ELLSPMV_SERIAL_READER") ? mtx_read_coordinate : mtx_read_coordinate_parallel)(s, &h, rowidx, colidx, a, &lines, &bytes);
         if (err) {
             if (o.verbose > 0) fprintf(stderr, "\n");
             fprintf(stderr, "%s: %s:%" PRId64 ": %s\n", prog, o.Apath, lines + 1, strerror(err));

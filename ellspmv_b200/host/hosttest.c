@@ -27,7 +27,7 @@ static int read_coo(const char *path, int gzip, struct mtx_header *h, idx_t **ri
     size_t nz = h->num_nonzeros > 0 ? (size_t)h->num_nonzeros : 1;
     *ri = malloc(nz * sizeof(idx_t)); *ci = malloc(nz * sizeof(idx_t)); *a = malloc(nz * sizeof(double));
     if (!*ri || !*ci || !*a) { mtx_close(s); return ENOMEM; }
-    err = mtx_read_coordinate(s, h, *ri, *ci, *a, lines, &bytes);
+    err = (getenv("ELLSPMV_SERIAL_READER") ? mtx_read_coordinate : mtx_read_coordinate_parallel)(s, h, *ri, *ci, *a, lines, &bytes);
     mtx_close(s);
     if (err) { free(*ri); free(*ci); free(*a); }
     return err;

@@ -8,6 +8,13 @@
 #include <string.h>
 #include <unistd.h>
 
+#include <sys/mman.h>
+#include <sys/stat.h>
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
 #ifdef HAVE_LIBZ
 #include <zlib.h>
 #endif
@@ -204,6 +211,146 @@ int mtx_read_coordinate(struct mtx_stream *s, const struct mtx_header *h,
         }
         (*lines)++;
     }
+    return 0;
+}
+
+/* ---- parallel entry parser ---------------------------------------------------- */
+
+/* unsigned decimal field starting at p (must start with a digit); returns the
+ * end, or NULL when the field is not plain digits or does not fit int64 */
+static const char *scan_digits(const char *p, const char *end, int64_t *out)
+{
+    if (p >= end || *p < '0' || *p > '9') return NULL;
+    int64_t v = 0;
+    int nd = 0;
+    while (p < end && *p >= '0' && *p <= '9') {
+        if (++nd > 18) return NULL;
+        v = v * 10 + (*p - '0');
+        p++;
+    }
+    *out = v;
+    return p;
+}
+
+/* parse lines [first, first+count) that start at text; returns 0 or 1 (= use the serial reader) */
+static int parse_block(const char *text, const char *end, int64_t first, int64_t count,
+                       const struct mtx_header *h, int line_max,
+                       idx_t *rowidx, idx_t *colidx, double *a, int64_t *bytes_out)
+{
+    const int with_value = h->field != MTX_PATTERN;
+    const char *p = text;
+    int64_t bytes = 0;
+    char tmp[64];
+    for (int64_t k = first; k < first + count; k++) {
+        const char *nl = memchr(p, '\n', (size_t)(end - p));
+        const char *eol = nl ? nl : end;
+        if (eol - p + (nl ? 1 : 0) > line_max) return 1;
+        int64_t v;
+        const char *q = scan_digits(p, eol, &v);
+        if (!q || q >= eol || *q != ' ' || v < 1 || v > h->num_rows) return 1;
+        rowidx[k] = (idx_t)v;
+        bytes += q - p + 1;
+        const char *c0 = q + 1;
+        q = scan_digits(c0, eol, &v);
+        if (!q || v < 1 || v > h->num_columns) return 1;
+        colidx[k] = (idx_t)v;
+        bytes += q - c0;
+        if (with_value) {
+            if (q >= eol || *q != ' ') return 1;
+            const char *v0 = q + 1;
+            if (v0 >= eol || *v0 == ' ' || *v0 == '\t') return 1;   /* strtod would skip blanks: leave that to the serial reader */
+            char *stop;
+            double d;
+            errno = 0;
+            if (nl) {
+                d = strtod(v0, &stop);                              /* the newline ends the number */
+            } else {                                               /* last line without '\n': no terminator in the map */
+                size_t n = (size_t)(eol - v0);
+                if (n >= sizeof(tmp)) return 1;
+                memcpy(tmp, v0, n);
+                tmp[n] = '\0';
+                d = strtod(tmp, &stop);
+                stop = (char *)v0 + (stop - tmp);
+            }
+            if (stop == v0 || stop > eol || errno == ERANGE) return 1;
+            a[k] = d;
+            bytes += 1 + (stop - v0);
+        } else {
+            a[k] = 1.0;
+        }
+        p = nl ? nl + 1 : end;
+        if (!nl && k + 1 < first + count) return 1;
+    }
+    *bytes_out = bytes;
+    return 0;
+}
+
+int mtx_read_coordinate_parallel(struct mtx_stream *s, const struct mtx_header *h,
+                                 idx_t *rowidx, idx_t *colidx, double *a, int64_t *lines, int64_t *bytes)
+{
+    if (!s->f || h->num_nonzeros < (1 << 16))
+        return mtx_read_coordinate(s, h, rowidx, colidx, a, lines, bytes);
+    const long pos = ftell(s->f);
+    struct stat st;
+    if (pos < 0 || fstat(fileno(s->f), &st) != 0 || !S_ISREG(st.st_mode) || st.st_size <= pos)
+        return mtx_read_coordinate(s, h, rowidx, colidx, a, lines, bytes);
+    char *map = mmap(NULL, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fileno(s->f), 0);
+    if (map == MAP_FAILED) return mtx_read_coordinate(s, h, rowidx, colidx, a, lines, bytes);
+    const char *text = map + pos, *end = map + st.st_size;
+    int nthreads = 1;
+#ifdef _OPENMP
+    nthreads = omp_get_max_threads();
+#endif
+    if (nthreads > 256) nthreads = 256;
+    /* cut the text into nthreads pieces at line starts, count lines per piece */
+    const char *cut[257];
+    int64_t nlines[256], first[257], pbytes[256];
+    int bad = 0;
+    cut[0] = text;
+    for (int t = 1; t < nthreads; t++) {
+        const char *c = text + (int64_t)(end - text) / nthreads * t;
+        if (c < cut[t - 1]) c = cut[t - 1];
+        const char *nl = c < end ? memchr(c, '\n', (size_t)(end - c)) : NULL;
+        cut[t] = nl ? nl + 1 : end;
+    }
+    cut[nthreads] = end;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static, 1) num_threads(nthreads)
+#endif
+    for (int t = 0; t < nthreads; t++) {
+        int64_t n = 0;
+        const char *p = cut[t];
+        while (p < cut[t + 1]) {
+            const char *nl = memchr(p, '\n', (size_t)(cut[t + 1] - p));
+            n++;
+            if (!nl) break;
+            p = nl + 1;
+        }
+        nlines[t] = n;
+    }
+    first[0] = 0;
+    for (int t = 0; t < nthreads; t++) first[t + 1] = first[t] + nlines[t];
+    if (first[nthreads] < h->num_nonzeros) bad = 1;          /* premature end of file */
+    if (!bad) {
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static, 1) num_threads(nthreads) reduction(|:bad)
+#endif
+        for (int t = 0; t < nthreads; t++) {
+            pbytes[t] = 0;
+            int64_t f0 = first[t], cnt = nlines[t];
+            if (f0 >= h->num_nonzeros) continue;            /* lines past the declared count are ignored */
+            if (f0 + cnt > h->num_nonzeros) cnt = h->num_nonzeros - f0;
+            bad |= parse_block(cut[t], cut[t + 1], f0, cnt, h, s->line_max, rowidx, colidx, a, &pbytes[t]);
+        }
+    }
+    munmap(map, (size_t)st.st_size);
+    if (bad) {
+        /* let the serial reader produce the reference's exact answer (or error) */
+        if (fseek(s->f, pos, SEEK_SET) != 0) return EIO;
+        return mtx_read_coordinate(s, h, rowidx, colidx, a, lines, bytes);
+    }
+    for (int t = 0; t < nthreads; t++) *bytes += pbytes[t];
+    *lines += h->num_nonzeros;
     return 0;
 }
 

@@ -41,6 +41,19 @@ void mtx_close(struct mtx_stream *s);
 int mtx_read_header(struct mtx_stream *s, struct mtx_header *h, int64_t *lines, int64_t *bytes);
 int mtx_read_coordinate(struct mtx_stream *s, const struct mtx_header *h,
                         idx_t *rowidx, idx_t *colidx, double *a, int64_t *lines, int64_t *bytes);
+/*
+ * Same result as mtx_read_coordinate (arrays, *lines, *bytes, error code and
+ * error line), but the entry lines are parsed by all OpenMP threads from a
+ * memory map of the file: the reference's serial fgets/strtoll/strtod loop
+ * (ellspmv.c:808-888) runs at ~100 MB/s and dominates the wall clock for real
+ * matrices (README: 32 s of reading for a 0.01 s SpMV).  Lines that are not
+ * in the plain "digits SP digits [SP number] NL" form, gzip streams, and any
+ * error make it fall back to the serial reader, which then reports exactly
+ * what the reference would.
+ */
+int mtx_read_coordinate_parallel(struct mtx_stream *s, const struct mtx_header *h,
+                                 idx_t *rowidx, idx_t *colidx, double *a, int64_t *lines, int64_t *bytes);
+
 int mtx_read_vector(struct mtx_stream *s, enum mtx_field field, int64_t n, double *x,
                     int64_t *lines, int64_t *bytes);
 

@@ -12,7 +12,14 @@ HOST_DIR = os.path.join(ROOT, "ellspmv_b200", "host")
 BIN = os.path.join(HOST_DIR, "bin")
 
 
-def build_host():
+def build_host(force=False):
+    """Build the library and the host programs unless they are already there
+    (the GPU box receives them prebuilt; file times do not survive the copy,
+    so `make` would rebuild everything)."""
+    lib = os.path.join(ROOT, "ellspmv_b200", "lib", "libellspmv_cuda.so")
+    progs = [os.path.join(BIN, p) for p in ("ellspmv", "ellspmv64", "csrspmv", "csrspmv64", "libhost32.so", "libhost64.so")]
+    if not force and os.path.exists(lib) and all(os.path.exists(p) for p in progs):
+        return
     subprocess.run(["make", "-C", os.path.join(ROOT, "ellspmv_b200", "csrc"), "-j8"], check=True, stdout=subprocess.DEVNULL)
     subprocess.run(["make", "-C", HOST_DIR, "-j8"], check=True, stdout=subprocess.DEVNULL)
 

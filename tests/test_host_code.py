@@ -134,3 +134,71 @@ def test_programs_fail_loudly_without_a_gpu(tmp_path):
     assert r.returncode == 1 and r.stdout.startswith("Usage:")
     r = subprocess.run([os.path.join(hostlib.BIN, "ellspmv"), "--repeat=x", p], capture_output=True, text=True)
     assert r.returncode == 1 and "--repeat=x" in r.stderr
+
+
+def _big_mtx(path, nr, nc, nnz, seed=1, field="real", tail_newline=True, mutate=None):
+    rng = np.random.default_rng(seed)
+    ri = rng.integers(1, nr + 1, nnz)
+    ci = rng.integers(1, nc + 1, nnz)
+    a = rng.standard_normal(nnz)
+    lines = [f"{r} {c} {v:.17g}" if field == "real" else f"{r} {c}" for r, c, v in zip(ri, ci, a)]
+    if mutate:
+        mutate(lines)
+    with open(path, "w") as f:
+        f.write(f"%%MatrixMarket matrix coordinate {field} general\n% big\n{nr} {nc} {nnz}\n")
+        f.write("\n".join(lines))
+        if tail_newline:
+            f.write("\n")
+    return ri, ci, a
+
+
+@pytest.mark.parametrize("field,tail_newline", [("real", True), ("real", False), ("pattern", True)])
+def test_parallel_reader_equals_serial_reader(tmp_path, monkeypatch, field, tail_newline):
+    """>= 65536 entries take the mmap + OpenMP parser; it must give the serial
+    reader's arrays, and the serial reader's are pinned by the goldens above."""
+    p = str(tmp_path / "big.mtx")
+    ri, ci, a = _big_mtx(p, 5000, 7000, 150000, field=field, tail_newline=tail_newline)
+    monkeypatch.delenv("ELLSPMV_SERIAL_READER", raising=False)
+    err, dims, ec, ea = hostlib.ell_from_file(64, p)
+    monkeypatch.setenv("ELLSPMV_SERIAL_READER", "1")
+    err2, dims2, ec2, ea2 = hostlib.ell_from_file(64, p)
+    assert err == 0 and err2 == 0 and dims == dims2
+    assert np.array_equal(ec, ec2) and bits_equal(ea, ea2)
+    # and against an independent conversion of the values that were written
+    K = dims[3]
+    cnt = np.bincount(ri - 1, minlength=5000)
+    assert K == cnt.max() and dims[6] == 3 + 150000
+    row0 = np.flatnonzero(ri == ri[0])
+    want_vals = a[row0] if field == "real" else np.ones(len(row0))
+    r = ri[0] - 1
+    assert bits_equal(ea[r * K:r * K + len(row0)], want_vals)
+    assert np.array_equal(ec[r * K:r * K + len(row0)], ci[row0] - 1)
+
+
+@pytest.mark.parametrize("what", ["bad index", "tab", "short file", "leading blank", "plus sign", "huge value"])
+def test_parallel_reader_falls_back_to_the_serial_answer(tmp_path, monkeypatch, what):
+    p = str(tmp_path / "big.mtx")
+
+    def mutate(lines):
+        if what == "bad index":
+            lines[90000] = "999999 1 1.0"
+        elif what == "tab":
+            lines[90000] = "1\t1 1.0"
+        elif what == "short file":
+            del lines[100000:]
+        elif what == "leading blank":
+            lines[70000] = " 3 4 2.5"          # strtoll skips blanks: the reference accepts this line
+        elif what == "plus sign":
+            lines[70000] = "+3 4 +2.5"
+        elif what == "huge value":
+            lines[70000] = "3 4 1e999"
+    _big_mtx(p, 5000, 7000, 120000, mutate=mutate)
+    monkeypatch.delenv("ELLSPMV_SERIAL_READER", raising=False)
+    par = hostlib.ell_from_file(32, p)
+    monkeypatch.setenv("ELLSPMV_SERIAL_READER", "1")
+    ser = hostlib.ell_from_file(32, p)
+    assert par[0] == ser[0] and par[1] == ser[1]          # same error code, same "line" for the message
+    if ser[0] == 0:
+        assert np.array_equal(par[2], ser[2]) and bits_equal(par[3], ser[3])
+    else:
+        assert what in ("bad index", "tab", "short file", "huge value")
