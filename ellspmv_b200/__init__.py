@@ -66,6 +66,9 @@ _I64 = C.c_int64
 _PROTOTYPES = {
     "ellspmv_cuda_upload": (C.c_int, [C.POINTER(_P), C.c_int, _I64, _I64, _I64, _P, _P, C.c_int, C.c_uint]),
     "ellspmv_cuda_upload_shard": (C.c_int, [C.POINTER(_P), C.c_int, _I64, _I64, _I64, _I64, _I64, _P, _P, C.c_int, C.c_uint]),
+    "ellspmv_cuda_upload_coo": (C.c_int, [C.POINTER(_P), C.c_int, _I64, _I64, _I64, _P, _P, _P, C.c_int, C.c_uint]),
+    "csrspmv_cuda_upload_coo": (C.c_int, [C.POINTER(_P), C.c_int, _I64, _I64, _I64, _P, _P, _P, C.c_uint]),
+    "csrspmv_cuda_download": (C.c_int, [_P, _P, _P, _P]),
     "ellspmv_cuda_generate": (C.c_int, [C.POINTER(_P), C.c_int, C.POINTER(_I64), C.POINTER(C.c_double), C.c_uint64, C.c_int, _I64, _I64, C.c_int, C.c_uint]),
     "ellspmv_cuda_spmv": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P]),
     "ellspmv_cuda_spmv_device": (C.c_int, [_P, _P, _P, C.c_int, _P]),
@@ -184,6 +187,16 @@ class EllMatrix:
         return cls(h.value)
 
     @classmethod
+    def upload_coo(cls, num_rows: int, num_columns: int, rowidx, colidx, a, flags: int = 0,
+                   device: int = -1) -> "EllMatrix":
+        """COO (1-based, file order) -> ELL on the device; same matrix as ell_from_coo + upload."""
+        h = C.c_void_p()
+        err = load_library().ellspmv_cuda_upload_coo(C.byref(h), _idx_bits(rowidx), num_rows, num_columns, len(a),
+                                                     _ptr(rowidx), _ptr(colidx), _ptr(a), device, flags)
+        _check(err, "ellspmv_cuda_upload_coo")
+        return cls(h.value)
+
+    @classmethod
     def generate(cls, kind: int, dims: Sequence[int], vals: Sequence[float] = (0.0, 0.0), seed: int = 42,
                  idx_bits: int = 32, row_begin: int = 0, row_end: int = -1, device: int = -1,
                  flags: int = 0) -> "EllMatrix":
@@ -268,6 +281,24 @@ class CsrMatrix:
                                                  _ptr(colidx), _ptr(a), 1, flags)
         _check(err, "csrspmv_cuda_upload")
         return cls(h.value)
+
+    @classmethod
+    def upload_coo(cls, num_rows: int, num_columns: int, rowidx, colidx, a, flags: int = 0) -> "CsrMatrix":
+        """COO (1-based, file order) -> CSR on the device; same arrays as csr_from_coo (general matrices)."""
+        h = C.c_void_p()
+        err = load_library().csrspmv_cuda_upload_coo(C.byref(h), _idx_bits(rowidx), num_rows, num_columns, len(a),
+                                                     _ptr(rowidx), _ptr(colidx), _ptr(a), flags)
+        _check(err, "csrspmv_cuda_upload_coo")
+        m = cls(h.value)
+        m._shape = (num_rows, len(a), _idx_bits(rowidx))
+        return m
+
+    def download(self, num_rows: int, csrsize: int, idx_bits: int):
+        rowptr = np.empty(num_rows + 1, dtype=np.int64)
+        colidx = np.empty(max(csrsize, 1), dtype=np.int32 if idx_bits == 32 else np.int64)[:csrsize]
+        a = np.empty(max(csrsize, 1), dtype=np.float64)[:csrsize]
+        _check(load_library().csrspmv_cuda_download(self._h, _ptr(rowptr), _ptr(colidx), _ptr(a)), "csrspmv_cuda_download")
+        return rowptr, colidx, a
 
     @classmethod
     def generate(cls, kind: int, dims: Sequence[int], seed: int = 42, idx_bits: int = 32, device: int = -1,

@@ -421,6 +421,59 @@ int ellspmv_cuda_upload(
                                      0, num_rows, colidx, a, -1, flags);
 }
 
+int ellspmv_cuda_upload_coo(
+    ellspmv_cuda_matrix **out, int idx_width_bits,
+    int64_t num_rows, int64_t num_columns, int64_t num_nonzeros,
+    const void *rowidx, const void *colidx, const double *a, int device, unsigned flags)
+{
+    if (!out) ELL_FAIL(EINVAL, "out is NULL");
+    *out = nullptr;
+    if (idx_width_bits != 32 && idx_width_bits != 64) ELL_FAIL(EINVAL, "idx_width_bits must be 32 or 64");
+    if (num_rows < 0 || num_columns < 0 || num_nonzeros < 0) ELL_FAIL(EINVAL, "negative dimension");
+    if (num_nonzeros > 0 && (!rowidx || !colidx || !a)) ELL_FAIL(EINVAL, "NULL COO array");
+    int err = check_device(&device);
+    if (err) return err;
+    DeviceGuard g(device);
+    const size_t nz = (size_t)(num_nonzeros > 0 ? num_nonzeros : 1), ib = (size_t)idx_width_bits / 8;
+    void *d_ri = nullptr, *d_ci = nullptr;
+    double *d_a = nullptr;
+    cudaStream_t s = nullptr;
+    CooEllJob job;
+    int bad = 0;
+    ellspmv_cuda_matrix *A = nullptr;
+    cudaError_t ce = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+    if (ce == cudaSuccess) ce = cudaMalloc(&d_ri, nz * ib);
+    if (ce == cudaSuccess) ce = cudaMalloc(&d_ci, nz * ib);
+    if (ce == cudaSuccess) ce = cudaMalloc(&d_a, nz * 8);
+    if (ce == cudaSuccess && num_nonzeros > 0) ce = cudaMemcpyAsync(d_ri, rowidx, nz * ib, cudaMemcpyDefault, s);
+    if (ce == cudaSuccess && num_nonzeros > 0) ce = cudaMemcpyAsync(d_ci, colidx, nz * ib, cudaMemcpyDefault, s);
+    if (ce == cudaSuccess && num_nonzeros > 0) ce = cudaMemcpyAsync(d_a, a, nz * 8, cudaMemcpyDefault, s);
+    job.idx_bits = idx_width_bits;
+    job.nnz = num_nonzeros; job.num_rows = num_rows; job.num_columns = num_columns;
+    job.d_rowidx = d_ri; job.d_colidx = d_ci; job.d_a = d_a;
+    if (ce == cudaSuccess) ce = coo_to_ell_phase1(job, s, &bad);
+    err = 0;
+    if (ce != cudaSuccess) { set_last_error("upload_coo: %s", cudaGetErrorString(ce)); err = cuda_to_errno(ce); }
+    else if (bad) { set_last_error("upload_coo: row index outside [1, %lld]", (long long)num_rows); err = EINVAL; }
+    if (!err) err = new_handle(&A, idx_width_bits, num_rows, num_columns, job.rowsize, 0, num_rows, device, flags);
+    if (!err) err = configure(A, flags);
+    if (!err) err = alloc_matrix(A);
+    if (!err) {
+        ce = cudaStreamSynchronize(A->stream);     // memsets of alloc_matrix before the scatter on `s`
+        if (ce == cudaSuccess)
+            ce = coo_to_ell_phase2(job, A->dev_idx_bits, A->cols, A->vals, A->lay, A->d_minmax, s, &bad);
+        if (ce != cudaSuccess) { set_last_error("upload_coo: %s", cudaGetErrorString(ce)); err = cuda_to_errno(ce); }
+        else if (bad) { set_last_error("upload_coo: column index outside [1, %lld]", (long long)num_columns); err = EINVAL; }
+    }
+    if (!err && A->lay.num_rows > 0 && A->lay.rowsize > 0) err = finish_minmax(A);
+    coo_to_ell_release(job);
+    cudaFree(d_ri); cudaFree(d_ci); cudaFree(d_a);
+    if (s) cudaStreamDestroy(s);
+    if (err) { if (A) ellspmv_cuda_free(A); return err; }
+    *out = A;
+    return 0;
+}
+
 int ellspmv_cuda_generate(
     ellspmv_cuda_matrix **out, int kind, const int64_t dims[3],
     const double vals[2], uint64_t seed, int idx_width_bits,
@@ -709,6 +762,42 @@ int csrspmv_cuda_upload(
     return 0;
 }
 
+int csrspmv_cuda_upload_coo(
+    csrspmv_cuda_matrix **out, int idx_width_bits,
+    int64_t num_rows, int64_t num_columns, int64_t num_nonzeros,
+    const void *rowidx, const void *colidx, const double *a, unsigned flags)
+{
+    if (!out) ELL_FAIL(EINVAL, "out is NULL");
+    *out = nullptr;
+    if (num_nonzeros > 0 && (!rowidx || !colidx || !a)) ELL_FAIL(EINVAL, "NULL COO array");
+    int err = csr_new(out, idx_width_bits, num_rows, num_columns, num_nonzeros, -1, flags);
+    if (err) return err;
+    csrspmv_cuda_matrix *A = *out;
+    DeviceGuard g(A->device);
+    const size_t nz = (size_t)(num_nonzeros > 0 ? num_nonzeros : 1), ib = (size_t)idx_width_bits / 8;
+    void *d_ri = nullptr, *d_ci = nullptr;
+    double *d_a = nullptr;
+    int bad = 0;
+    cudaStream_t s = A->stream;
+    cudaError_t ce = cudaMalloc(&d_ri, nz * ib);
+    if (ce == cudaSuccess) ce = cudaMalloc(&d_ci, nz * ib);
+    if (ce == cudaSuccess) ce = cudaMalloc(&d_a, nz * 8);
+    if (ce == cudaSuccess && num_nonzeros > 0) ce = cudaMemcpyAsync(d_ri, rowidx, nz * ib, cudaMemcpyDefault, s);
+    if (ce == cudaSuccess && num_nonzeros > 0) ce = cudaMemcpyAsync(d_ci, colidx, nz * ib, cudaMemcpyDefault, s);
+    if (ce == cudaSuccess && num_nonzeros > 0) ce = cudaMemcpyAsync(d_a, a, nz * 8, cudaMemcpyDefault, s);
+    if (ce == cudaSuccess)
+        ce = coo_to_csr(idx_width_bits, d_ri, d_ci, d_a, num_nonzeros, num_rows, num_columns, A->rowptr, A->cols,
+                        A->vals, s, &bad);
+    cudaFree(d_ri); cudaFree(d_ci); cudaFree(d_a);
+    if (ce != cudaSuccess || bad) {
+        if (ce != cudaSuccess) set_last_error("csr upload_coo: %s", cudaGetErrorString(ce));
+        else set_last_error("csr upload_coo: row or column index out of range");
+        csrspmv_cuda_free(A); *out = nullptr;
+        return ce != cudaSuccess ? cuda_to_errno(ce) : EINVAL;
+    }
+    return 0;
+}
+
 int csrspmv_cuda_generate(
     csrspmv_cuda_matrix **out, int kind, const int64_t dims[3],
     const double vals[2], uint64_t seed, int idx_width_bits,
@@ -799,6 +888,20 @@ int csrspmv_cuda_spmv(
             ELL_CK(cudaEventElapsedTime(&ms, A->events[(size_t)r], A->events[(size_t)r + 1]));
             seconds[r] = (double)ms * 1e-3;
         }
+    }
+    return 0;
+}
+
+int csrspmv_cuda_download(const csrspmv_cuda_matrix *A, int64_t *rowptr, void *colidx, double *a)
+{
+    if (!A) ELL_FAIL(EINVAL, "matrix is NULL");
+    if (!rowptr) ELL_FAIL(EINVAL, "rowptr is NULL");
+    DeviceGuard g(A->device);
+    ELL_CK(cudaMemcpy(rowptr, A->rowptr, (size_t)(A->num_rows + 1) * 8, cudaMemcpyDefault));
+    if (A->csrsize > 0) {
+        if (!colidx || !a) ELL_FAIL(EINVAL, "colidx or a is NULL");
+        ELL_CK(cudaMemcpy(colidx, A->cols, (size_t)A->csrsize * (A->idx_bits / 8), cudaMemcpyDefault));
+        ELL_CK(cudaMemcpy(a, A->vals, (size_t)A->csrsize * 8, cudaMemcpyDefault));
     }
     return 0;
 }

@@ -131,6 +131,23 @@ cudaError_t generate_csr_random(const int64_t dims[3], uint64_t seed, int idx_bi
                                 int64_t *rowptr, void *cols, double *vals, cudaStream_t stream);
 cudaError_t init_minmax(long long *minmax, cudaStream_t stream);
 
+// ---- COO -> ELL / CSR on the device (convert.cu) ------------------------------
+struct CooEllJob {
+    int idx_bits = 32;
+    int64_t nnz = 0, num_rows = 0, num_columns = 0;
+    const void *d_rowidx = nullptr, *d_colidx = nullptr;   // 1-based, device copies of the file's arrays
+    const double *d_a = nullptr;
+    void *state = nullptr;                                 // sort workspace, owned by convert.cu
+    int64_t rowsize = 0;                                   // K, known after phase 1
+};
+cudaError_t coo_to_ell_phase1(CooEllJob &job, cudaStream_t stream, int *bad);
+cudaError_t coo_to_ell_phase2(CooEllJob &job, int dst_idx_bits, void *dst_cols, double *dst_vals,
+                              const EllLayout &lay, long long *minmax, cudaStream_t stream, int *bad);
+void coo_to_ell_release(CooEllJob &job);
+cudaError_t coo_to_csr(int idx_bits, const void *d_rowidx, const void *d_colidx, const double *d_a, int64_t nnz,
+                       int64_t num_rows, int64_t num_columns, int64_t *rowptr, void *csrcolidx, double *csra,
+                       cudaStream_t stream, int *bad);
+
 // ---- cross-GPU step barrier (barrier.cu) ----------------------------------
 // rank writes `epoch` into slot [rank] of every peer's flag array, then waits
 // until its own array shows `epoch` from every rank.  Flags are int64 in

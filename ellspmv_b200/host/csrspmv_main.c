@@ -36,7 +36,7 @@ static const char *version = "1.10-b200";
 struct options {
     const char *Apath, *xpath, *ypath;
     int gzip;
-    bool separate_diagonal, sort_rows, ignored_partition;
+    bool separate_diagonal, sort_rows, ignored_partition, device_convert;
     int repeat, warmup, verbose, quiet;
     unsigned flags;
 };
@@ -71,6 +71,7 @@ static void help(FILE *f)
     fprintf(f, " Options for the CUDA path are:\n");
     fprintf(f, "  --kernel=thread|warp      row-block streaming (bit-exact, default) or sub-warp-per-row\n");
     fprintf(f, "  --fma                     allow fused multiply-add (tolerance mode)\n");
+    fprintf(f, "  --device-convert          convert COO to CSR on the device (general matrices)\n");
     fprintf(f, "\n");
     fprintf(f, "  -h, --help                display this help and exit\n");
     fprintf(f, "  --version                 display version information and exit\n");
@@ -125,6 +126,7 @@ static int parse_options(int argc, char **argv, struct options *o, int *bad)
                 continue;
             }
             if (!strcmp(a, "--fma")) { o->flags |= ELLSPMV_CUDA_FMA; continue; }
+            if (!strcmp(a, "--device-convert")) { o->device_convert = true; continue; }
             if (!strcmp(a, "-h") || !strcmp(a, "--help")) { help(stdout); exit(EXIT_SUCCESS); }
             if (!strcmp(a, "--version")) {
                 printf("%s %s\nrow/column offsets: %d-bit\n", prog, version, IDX_BITS);
@@ -200,43 +202,67 @@ int main(int argc, char *argv[])
 
     /* 3. convert to CSR (csrspmv.c:1911-2287) */
     if (o.verbose > 0) { fprintf(stderr, "csr_from_coo: "); clock_gettime(CLOCK_MONOTONIC, &t0); }
-    struct csr_matrix csr;
     if (o.separate_diagonal && num_rows != num_columns) {
         if (o.verbose > 0) fprintf(stderr, "\n");
         fprintf(stderr, "%s: --separate-diagonal needs a square matrix\n", prog);
         return EXIT_FAILURE;
     }
-    err = csr_from_coo(&csr, h.symmetry == MTX_SYMMETRIC, num_rows, num_columns, num_nonzeros, rowidx, colidx, a,
-                       o.separate_diagonal);
-    free(a); free(colidx); free(rowidx);
-    if (err) {
-        if (o.verbose > 0) fprintf(stderr, "\n");
-        fprintf(stderr, "%s: %s\n", prog, strerror(err));
-        return EXIT_FAILURE;
-    }
-    const int64_t csrsize = csr.csrsize;
-    const int64_t diagsize = csr.diagsize;
-    if (o.verbose > 0) {
-        clock_gettime(CLOCK_MONOTONIC, &t1);
-        fprintf(stderr, "%'.6f seconds, %'" PRIdx " rows, %'" PRIdx " columns, %'" PRId64 " nonzeros"
-                        ", %'" PRIdx " to %'" PRIdx " nonzeros per row\n",
-                seconds_between(t0, t1), num_rows, num_columns, csrsize + diagsize, csr.rowsizemin, csr.rowsizemax);
-    }
-
-    if (o.verbose > 0) { fprintf(stderr, "cuda_upload: "); clock_gettime(CLOCK_MONOTONIC, &t0); }
     csrspmv_cuda_matrix *A = NULL;
-    err = csrspmv_cuda_upload(&A, IDX_BITS, num_rows, num_columns, csr.rowptr, csr.colidx, csr.a, 1, o.flags);
-    if (!err && csr.ad) err = csrspmv_cuda_set_diagonal(A, csr.ad);
-    csr_free(&csr);
-    if (err) {
-        if (o.verbose > 0) fprintf(stderr, "\n");
-        fprintf(stderr, "%s: %s (%s)\n", prog, strerror(err), ellspmv_cuda_last_error());
-        return EXIT_FAILURE;
-    }
-    if (o.verbose > 0) {
-        clock_gettime(CLOCK_MONOTONIC, &t1);
-        fprintf(stderr, "%'.6f seconds, %'" PRId64 " bytes on the device\n", seconds_between(t0, t1),
-                csrspmv_cuda_device_bytes(A));
+    int64_t csrsize, diagsize = 0;
+    if (o.device_convert && !o.separate_diagonal && h.symmetry == MTX_GENERAL) {
+        /* stable sort by row on the device; rowsizemin/max are only printed, count them here */
+        int64_t *cnt = calloc((size_t)num_rows + 1, sizeof(*cnt));
+        if (!cnt) { fprintf(stderr, "%s: %s\n", prog, strerror(ENOMEM)); return EXIT_FAILURE; }
+        for (int64_t k = 0; k < num_nonzeros; k++) cnt[rowidx[k] - 1]++;
+        int64_t lo = num_rows > 0 ? cnt[0] : 0, hi = 0;
+        for (idx_t i = 0; i < num_rows; i++) { if (cnt[i] < lo) lo = cnt[i]; if (cnt[i] > hi) hi = cnt[i]; }
+        free(cnt);
+        err = csrspmv_cuda_upload_coo(&A, IDX_BITS, num_rows, num_columns, num_nonzeros, rowidx, colidx, a, o.flags);
+        free(a); free(colidx); free(rowidx);
+        if (err) {
+            if (o.verbose > 0) fprintf(stderr, "\n");
+            fprintf(stderr, "%s: %s (%s)\n", prog, strerror(err), ellspmv_cuda_last_error());
+            return EXIT_FAILURE;
+        }
+        csrsize = num_nonzeros;
+        if (o.verbose > 0) {
+            clock_gettime(CLOCK_MONOTONIC, &t1);
+            fprintf(stderr, "%'.6f seconds, %'" PRIdx " rows, %'" PRIdx " columns, %'" PRId64 " nonzeros"
+                            ", %'" PRId64 " to %'" PRId64 " nonzeros per row\n",
+                    seconds_between(t0, t1), num_rows, num_columns, csrsize, lo, hi);
+        }
+    } else {
+        struct csr_matrix csr;
+        err = csr_from_coo(&csr, h.symmetry == MTX_SYMMETRIC, num_rows, num_columns, num_nonzeros, rowidx, colidx, a,
+                           o.separate_diagonal);
+        free(a); free(colidx); free(rowidx);
+        if (err) {
+            if (o.verbose > 0) fprintf(stderr, "\n");
+            fprintf(stderr, "%s: %s\n", prog, strerror(err));
+            return EXIT_FAILURE;
+        }
+        csrsize = csr.csrsize;
+        diagsize = csr.diagsize;
+        if (o.verbose > 0) {
+            clock_gettime(CLOCK_MONOTONIC, &t1);
+            fprintf(stderr, "%'.6f seconds, %'" PRIdx " rows, %'" PRIdx " columns, %'" PRId64 " nonzeros"
+                            ", %'" PRIdx " to %'" PRIdx " nonzeros per row\n",
+                    seconds_between(t0, t1), num_rows, num_columns, csrsize + diagsize, csr.rowsizemin, csr.rowsizemax);
+        }
+        if (o.verbose > 0) { fprintf(stderr, "cuda_upload: "); clock_gettime(CLOCK_MONOTONIC, &t0); }
+        err = csrspmv_cuda_upload(&A, IDX_BITS, num_rows, num_columns, csr.rowptr, csr.colidx, csr.a, 1, o.flags);
+        if (!err && csr.ad) err = csrspmv_cuda_set_diagonal(A, csr.ad);
+        csr_free(&csr);
+        if (err) {
+            if (o.verbose > 0) fprintf(stderr, "\n");
+            fprintf(stderr, "%s: %s (%s)\n", prog, strerror(err), ellspmv_cuda_last_error());
+            return EXIT_FAILURE;
+        }
+        if (o.verbose > 0) {
+            clock_gettime(CLOCK_MONOTONIC, &t1);
+            fprintf(stderr, "%'.6f seconds, %'" PRId64 " bytes on the device\n", seconds_between(t0, t1),
+                    csrspmv_cuda_device_bytes(A));
+        }
     }
 
     /* 4. vectors (csrspmv.c:2340-2631) */

@@ -52,7 +52,7 @@ struct options {
     int repeat, warmup, verbose, quiet;
     /* GPU options */
     unsigned flags;
-    bool iterate;
+    bool iterate, device_convert;
     const char *synthetic;
     int device;
 };
@@ -93,6 +93,7 @@ static void help(FILE *f)
     fprintf(f, "  --iterate            compute x := A*x repeatedly (y := A^N x); square A only\n");
     fprintf(f, "  --synthetic=SPEC     build A on the device instead of reading a file:\n");
     fprintf(f, "                       laplace2d:NX,NY | stencil27:NX,NY,NZ | random:ROWS,COLS,K[,SEED]\n");
+    fprintf(f, "  --device-convert     convert COO to ELL on the device (same arrays as the host conversion)\n");
     fprintf(f, "  --device=N           CUDA device ordinal [current]\n");
     fprintf(f, "\n");
     fprintf(f, "  -h, --help           display this help and exit\n");
@@ -166,6 +167,7 @@ static int parse_options(int argc, char **argv, struct options *o, int *bad)
                 continue;
             }
             if (!strcmp(a, "--iterate")) { o->iterate = true; continue; }
+            if (!strcmp(a, "--device-convert")) { o->device_convert = true; continue; }
             if (!strncmp(a, "--synthetic", 11) && (a[11] == '=' || a[11] == '\0')) {
                 if (!(o->synthetic = optval(argc, argv, &i, "--synthetic"))) return EINVAL;
                 continue;
@@ -313,6 +315,27 @@ int main(int argc, char *argv[])
 
         /* 3. convert to ELLPACK (ellspmv.c:1379-1486) */
         if (o.verbose > 0) { fprintf(stderr, "ell_from_coo: "); clock_gettime(CLOCK_MONOTONIC, &t0); }
+        if (o.device_convert && !o.separate_diagonal) {
+            /* stable sort by row on the device instead of the serial host scatter */
+            err = ellspmv_cuda_upload_coo(&A, IDX_BITS, num_rows, num_columns, num_nonzeros, rowidx, colidx, a,
+                                          o.device, o.flags);
+            free(a); free(colidx); free(rowidx);
+            if (err) {
+                if (o.verbose > 0) fprintf(stderr, "\n");
+                fprintf(stderr, "%s: %s (%s)\n", prog, strerror(err), ellspmv_cuda_last_error());
+                return EXIT_FAILURE;
+            }
+            ellspmv_cuda_info info;
+            ellspmv_cuda_get_info(A, &info);
+            rowsize = (idx_t)info.rowsize;
+            ellsize = info.num_rows * info.rowsize;
+            diagsize = num_rows < num_columns ? num_rows : num_columns;
+            if (o.verbose > 0) {
+                clock_gettime(CLOCK_MONOTONIC, &t1);
+                fprintf(stderr, "%'.6f seconds, %'" PRIdx " rows, %'" PRId64 " nonzeros, %'" PRIdx " nonzeros per row\n",
+                        seconds_between(t0, t1), num_rows, ellsize + num_rows, rowsize);
+            }
+        } else {
         struct ell_matrix ell;
         if (o.separate_diagonal && num_rows > num_columns) {
             if (o.verbose > 0) fprintf(stderr, "\n");
@@ -357,6 +380,7 @@ int main(int argc, char *argv[])
                             "%d rows/thread, %d-bit indices\n",
                     seconds_between(t0, t1), info.device, info.device_bytes, info.slice_rows,
                     info.rows_per_thread, info.dev_idx_bits);
+        }
         }
     }
 

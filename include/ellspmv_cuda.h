@@ -127,6 +127,19 @@ int ellspmv_cuda_upload_shard(
     const void *colidx, const double *a, int device, unsigned flags);
 
 /*
+ * COO -> ELL on the device: takes the arrays as read from the Matrix Market
+ * file (1-based rowidx/colidx, file order) and builds the same device matrix
+ * as ell_from_coo (ellspmv.c:931-958, 1081-1127) followed by
+ * ellspmv_cuda_upload would: K = widest row, entries in file order inside a
+ * row, (min(i, ncols-1), 0.0) padding.  Replaces the reference's serial host
+ * scatter; the result is bit-identical (ellspmv_cuda_download shows it).
+ */
+int ellspmv_cuda_upload_coo(
+    ellspmv_cuda_matrix **out, int idx_width_bits,
+    int64_t num_rows, int64_t num_columns, int64_t num_nonzeros,
+    const void *rowidx, const void *colidx, const double *a, int device, unsigned flags);
+
+/*
  * Build rows [row_begin, row_end) of a synthetic matrix directly on the
  * device, in device layout (for shapes too large to build on the host).
  * Bit-identical to uploading the arrays the reference's ell_from_coo
@@ -197,6 +210,16 @@ int csrspmv_cuda_upload(
     int64_t num_rows, int64_t num_columns,
     const int64_t *rowptr, const void *colidx, const double *a,
     int num_gpus, unsigned flags);
+
+/* COO -> CSR on the device (general matrices): the stable sort by row of
+ * csr_from_coo's default branch (csrspmv.c:1436-1465), bit-identical arrays */
+int csrspmv_cuda_upload_coo(
+    csrspmv_cuda_matrix **out, int idx_width_bits,
+    int64_t num_rows, int64_t num_columns, int64_t num_nonzeros,
+    const void *rowidx, const void *colidx, const double *a, unsigned flags);
+
+/* copy the CSR arrays back to the host (rowptr: num_rows+1 int64) */
+int csrspmv_cuda_download(const csrspmv_cuda_matrix *A, int64_t *rowptr, void *colidx, double *a);
 
 /* CSR view of ELLSPMV_CUDA_GEN_RANDOM (every row has exactly K entries) */
 int csrspmv_cuda_generate(
