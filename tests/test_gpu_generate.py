@@ -94,3 +94,80 @@ def test_full_size_laplacian_properties(lib):
     assert y1[r].item() == 0.0 + acc
     torch.cuda.synchronize()
     A.free()
+
+
+def test_full_size_stencil27_properties(lib):
+    """BASELINE config 3 at full size (27-point 384^3, IDXTYPEWIDTH=64, 56.6M rows,
+    24 GB matrix): A*ones = 26 - (#neighbours) exactly (small integers in fp64),
+    the index-narrowed device layout gives the same bits, and scaling x by 2
+    scales y by 2 bit for bit."""
+    import torch
+    n = 384
+    rows = n ** 3
+    s = torch.cuda.current_stream().cuda_stream
+    x = torch.ones(rows, dtype=torch.float64, device="cuda")
+    c = torch.full((n,), 3.0, dtype=torch.float64, device="cuda")
+    c[0] = c[-1] = 2.0
+    want = 27.0 - (c[:, None, None] * c[None, :, None] * c[None, None, :]).reshape(-1)   # 26 - (count - 1)
+    ys = []
+    for flags in (0, E.NARROW_INDEX):
+        A = E.EllMatrix.generate(E.GEN_STENCIL27, (n, n, n), (26.0, -1.0), 42, 64, flags=flags)
+        i = A.info()
+        assert (i.num_rows, i.rowsize, i.idx_width_bits, i.dev_idx_bits) == (rows, 27, 64, 32 if flags else 64)
+        y = torch.zeros(rows, dtype=torch.float64, device="cuda")
+        A.spmv_device(y, x, E.ACCUMULATE, s)
+        assert torch.equal(y, want)
+        gen = torch.Generator(device="cuda").manual_seed(3)
+        xr = torch.randn(rows, dtype=torch.float64, device="cuda", generator=gen)
+        A.spmv_device(y, xr, E.OVERWRITE, s)
+        y2 = torch.empty_like(y)
+        xr *= 2
+        A.spmv_device(y2, xr, E.OVERWRITE, s)
+        assert torch.equal(y2, 2 * y)
+        ys.append(y)
+        torch.cuda.synchronize()
+        A.free()
+        del y2, xr
+    assert torch.equal(ys[0], ys[1])
+
+
+def test_full_size_random_ell_equals_csr(lib):
+    """BASELINE config 4 at full size (50M x 32, 19 GB per format): the ELL
+    path and the CSR comparison path hold the same entries in the same order,
+    so y must agree bit for bit; spot rows are re-derived on the host from the
+    generator's definition."""
+    import torch
+    dims = (50_000_000, 50_000_000, 32)
+    s = torch.cuda.current_stream().cuda_stream
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn(dims[1], dtype=torch.float64, device="cuda", generator=gen)
+    Ae = E.EllMatrix.generate(E.GEN_RANDOM, dims, seed=42, idx_bits=32)
+    ye = torch.zeros(dims[0], dtype=torch.float64, device="cuda")
+    Ae.spmv_device(ye, x, E.ACCUMULATE, s)
+    torch.cuda.synchronize()
+    Ae.free()
+    Ac = E.CsrMatrix.generate(E.GEN_RANDOM, dims, seed=42, idx_bits=32)
+    yc = torch.zeros(dims[0], dtype=torch.float64, device="cuda")
+    Ac.spmv_device(yc, x, E.ACCUMULATE, s)
+    torch.cuda.synchronize()
+    Ac.free()
+    assert torch.equal(ye, yc)
+    # spot rows from the definition: u = splitmix64(seed ^ (r*K+l)), col = mulhi(u, ncols), val = 2*(sm(u)>>11)*2^-53 - 1
+    M = (1 << 64) - 1
+
+    def sm(v):
+        z = (v + 0x9E3779B97F4A7C15) & M
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & M
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & M
+        return z ^ (z >> 31)
+    for r in (0, 1, 31_415_926, dims[0] - 1):
+        cols, vals = [], []
+        for l in range(32):
+            u = sm(42 ^ (r * 32 + l))
+            cols.append((u * dims[1]) >> 64)
+            vals.append(2.0 * ((sm(u) >> 11) * 2.0 ** -53) - 1.0)
+        xs = x[torch.tensor(cols, device="cuda")].cpu().numpy()
+        acc = 0.0
+        for v, xv in zip(vals, xs):
+            acc = acc + v * xv
+        assert ye[r].item() == 0.0 + acc
