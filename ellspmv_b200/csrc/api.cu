@@ -114,11 +114,13 @@ int configure(ellspmv_cuda_matrix *A, unsigned flags)
 {
     A->flags = flags;
     int R = (flags & ELLSPMV_CUDA_ROWS_PER_THREAD_MASK) >> ELLSPMV_CUDA_ROWS_PER_THREAD_SHIFT;
-    // auto: 2 rows per thread = 128-bit value loads and 64-bit (idx32) / 128-bit
-    // (idx64) index loads.  Measured on B200 (profiles/r1_sweep.md): R=1/2/4 are
-    // within 3% of each other on every BASELINE shape, R=2 is best or second
-    // best on all of them; 256-bit loads (R=4) buy nothing on an HBM-bound stream.
-    if (R == 0) R = 2;
+    // auto: 1 row per thread (a warp reads 256 contiguous bytes of values and 128
+    // of indices per slot).  Measured on two B200 boxes (profiles/r1_sweep.md,
+    // profiles/r1_bulk_variant.md): R = 1 / 2 / 4 give 0.784 / 0.790-0.830 / 0.807 ms
+    // on BASELINE config 2 and 3.65 / 3.64-3.74 / 3.69 ms on config 3 -- wider
+    // (128/256-bit) loads buy nothing on this HBM-bound stream and the extra
+    // resident threads of R = 1 make it the most stable; R = 2 and 4 stay selectable.
+    if (R == 0) R = 1;
     if (R != 1 && R != 2 && R != 4) ELL_FAIL(EINVAL, "rows per thread must be 1, 2 or 4 (got %d)", R);
     int kernel = flags & ELLSPMV_CUDA_KERNEL_MASK;
     if (kernel == ELLSPMV_CUDA_KERNEL_AUTO) kernel = ELLSPMV_CUDA_KERNEL_THREAD;

@@ -97,6 +97,9 @@ struct EllLaunchCfg {
 
 cudaError_t launch_ell_spmv(const EllLaunchCfg &cfg, const EllSpmvArgs &args,
                             int64_t num_slices, cudaStream_t stream);
+// persistent bulk-async (TMA) staged variant, ell_bulk.cu; *handled = false: not applicable
+cudaError_t launch_ell_bulk(const EllLaunchCfg &cfg, const EllSpmvArgs &args, int64_t num_slices,
+                            cudaStream_t stream, bool *handled);
 
 // ---- CSR ---------------------------------------------------------------
 struct CsrSpmvArgs {

@@ -392,6 +392,11 @@ cudaError_t launch_ell_spmv(const EllLaunchCfg &cfg, const EllSpmvArgs &args,
 {
     if (num_slices <= 0) return cudaSuccess;
     if (num_slices > 0x7fffffffLL) return cudaErrorInvalidValue;
+    if ((cfg.variant & 1) && args.num_rows > 0) {
+        bool handled = false;
+        cudaError_t e = launch_ell_bulk(cfg, args, num_slices, stream, &handled);
+        if (e != cudaSuccess || handled) return e;
+    }
 
     cudaLaunchConfig_t lc = {};
     lc.gridDim = dim3((unsigned)num_slices);

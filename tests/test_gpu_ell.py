@@ -251,3 +251,30 @@ def test_pipelined_host_call(lib, oracle, mode):
     A.spmv(yp.numpy(), xp.numpy(), 1, mode)
     assert bits_equal(yp.numpy(), want)
     A.free()
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 1), (127, 300, 5), (1000, 1000, 7), (5003, 5003, 27), (40000, 40000, 5), (3000, 3000, 32)])
+@pytest.mark.parametrize("bits", [32, 64])
+def test_bulk_async_variant_is_bit_exact(lib, oracle, shape, bits):
+    """ELLSPMV_CUDA_VARIANT = 1: persistent CTAs fed by cp.async.bulk + mbarrier
+    (TMA) instead of per-thread vector loads; same bits as the oracle."""
+    nr, nc, K = shape
+    dt = np.int32 if bits == 32 else np.int64
+    rng = np.random.default_rng(nr + nc + K + bits)
+    ec, ea = rand_ell(rng, nr, nc, K, dt)
+    x = rng.standard_normal(nc)
+    y0 = rng.standard_normal(nr)
+    want = y0.copy()
+    oracle.ellgemv(nr, want, x, K, ec, ea)
+    want0 = np.zeros(nr)
+    oracle.ellgemv(nr, want0, x, K, ec, ea)
+    for R in ALL_R:
+        A = E.EllMatrix.upload(nr, nc, K, ec, ea, E.rows_per_thread(R) | E.variant(1))
+        y = y0.copy()
+        A.spmv(y, x, 2, E.ACCUMULATE)
+        want2 = want.copy()
+        oracle.ellgemv(nr, want2, x, K, ec, ea)
+        assert bits_equal(y, want2), (shape, bits, R)
+        A.spmv(y, x, 1, E.OVERWRITE)
+        assert bits_equal(y, want0), (shape, bits, R)
+        A.free()

@@ -58,6 +58,8 @@ def main():
         variants = []
         for R in (4, 2, 1):
             variants.append((f"thread R={R}", E.KERNEL_THREAD | E.rows_per_thread(R)))
+        for R in (1, 2, 4):
+            variants.append((f"bulk-async R={R}", E.KERNEL_THREAD | E.rows_per_thread(R) | E.variant(1)))
         variants.append(("thread R=4 fma", E.KERNEL_THREAD | E.rows_per_thread(4) | E.FMA))
         variants.append(("thread R=4 l2persist", E.KERNEL_THREAD | E.rows_per_thread(4) | E.L2_PERSIST_X))
         if bits == 64:
