@@ -139,3 +139,66 @@ int csr_from_coo(struct csr_matrix *csr, int symmetric, idx_t num_rows, idx_t nu
     csr->rowptr = rowptr;
     return 0;
 }
+
+/* stable insertion sort of entries [lo, hi) of one row by column */
+static void insertion_sort(idx_t *c, double *v, int64_t lo, int64_t hi)
+{
+    for (int64_t k = lo + 1; k < hi; k++) {
+        const idx_t ck = c[k];
+        const double vk = v[k];
+        int64_t l = k;
+        while (l > lo && c[l - 1] > ck) { c[l] = c[l - 1]; v[l] = v[l - 1]; l--; }
+        c[l] = ck;
+        v[l] = vk;
+    }
+}
+
+int csr_sort_rows(struct csr_matrix *csr)
+{
+    enum { RUN = 16 };
+    int err = 0;
+#ifdef _OPENMP
+#pragma omp parallel
+#endif
+    {
+        idx_t *tc = NULL;
+        double *tv = NULL;
+        int64_t cap = 0;
+#ifdef _OPENMP
+#pragma omp for schedule(dynamic, 256)
+#endif
+        for (int64_t i = 0; i < (int64_t)csr->num_rows; i++) {
+            idx_t *c = csr->colidx + csr->rowptr[i];
+            double *v = csr->a + csr->rowptr[i];
+            const int64_t n = csr->rowptr[i + 1] - csr->rowptr[i];
+            if (n <= RUN) { insertion_sort(c, v, 0, n); continue; }
+            /* long row: sorted runs of 16, then bottom-up merging; on equal
+             * columns the right-hand run wins, as in the reference */
+            for (int64_t q = 0; q < n - 1; q += RUN) insertion_sort(c, v, q, q + RUN < n ? q + RUN : n);
+            if (n > cap) {
+                free(tc); free(tv);
+                tc = malloc((size_t)n * sizeof(idx_t));
+                tv = malloc((size_t)n * sizeof(double));
+                cap = n;
+                if (!tc || !tv) { err = ENOMEM; cap = 0; continue; }
+            }
+            for (int64_t w = RUN; w < n; w *= 2) {
+                memcpy(tc, c, (size_t)n * sizeof(idx_t));
+                memcpy(tv, v, (size_t)n * sizeof(double));
+                for (int64_t q = 0; q < n - 1; q += 2 * w) {
+                    const int64_t mid = q + w < n ? q + w : n, end = q + 2 * w < n ? q + 2 * w : n;
+                    int64_t o = q, l = q, r = mid;
+                    while (l < mid && r < end) {
+                        if (tc[l] < tc[r]) { c[o] = tc[l]; v[o++] = tv[l++]; }
+                        else { c[o] = tc[r]; v[o++] = tv[r++]; }
+                    }
+                    while (l < mid) { c[o] = tc[l]; v[o++] = tv[l++]; }
+                    while (r < end) { c[o] = tc[r]; v[o++] = tv[r++]; }
+                }
+            }
+        }
+        free(tc);
+        free(tv);
+    }
+    return err;
+}

@@ -49,6 +49,9 @@ int ell_from_coo(struct ell_matrix *ell, idx_t num_rows, idx_t num_columns, int6
 int csr_from_coo(struct csr_matrix *csr, int symmetric, idx_t num_rows, idx_t num_columns,
                  int64_t num_nonzeros, const idx_t *rowidx, const idx_t *colidx, const double *a,
                  int separate_diagonal);
+/* --sort-rows for CSR: sort every row by column exactly like the reference's
+ * rowsort (csrspmv.c:1269-1388), including its tie order for duplicate columns */
+int csr_sort_rows(struct csr_matrix *csr);
 void ell_free(struct ell_matrix *ell);
 void csr_free(struct csr_matrix *csr);
 

@@ -15,7 +15,8 @@
  * accepted and ignored (a note is printed with -v).  --separate-diagonal is
  * supported for square matrices (csrgemvsd, csrspmv.c:1598-1629; on a
  * non-square matrix the reference skips the split but still reads the absent
- * diagonal array, so that case is refused).  --sort-rows is refused.
+ * diagonal array, so that case is refused).  --sort-rows sorts every row by
+ * column on the host with the reference's rowsort order (csrspmv.c:1269-1388).
  */
 #include <errno.h>
 #include <locale.h>
@@ -61,6 +62,8 @@ static void help(FILE *f)
 #ifdef HAVE_LIBZ
     fprintf(f, "  -z, --gzip, --gunzip, --ungzip    filter files through gzip\n");
 #endif
+    fprintf(f, "  --separate-diagonal       store diagonal nonzeros separately\n");
+    fprintf(f, "  --sort-rows               sort nonzeros by column within each row\n");
     fprintf(f, "  --partition-rows, --partition-nonzeros, --precompute-partition,\n");
     fprintf(f, "  --rows-per-thread=N.., --columns-per-thread=N..   accepted, ignored (CPU thread partitioning)\n");
     fprintf(f, "  --repeat=N                repeat matrix-vector multiplication N times\n");
@@ -158,10 +161,6 @@ int main(int argc, char *argv[])
         fprintf(stderr, "%s: %s %s\n", prog, strerror(err), bad < argc ? argv[bad] : "");
         return EXIT_FAILURE;
     }
-    if (o.sort_rows) {
-        fprintf(stderr, "%s: --sort-rows is not implemented on the CUDA path\n", prog);
-        return EXIT_FAILURE;
-    }
     if (o.ignored_partition && o.verbose > 0)
         fprintf(stderr, "%s: note: CPU thread-partitioning options are ignored on the CUDA path\n", prog);
 
@@ -209,7 +208,7 @@ int main(int argc, char *argv[])
     }
     csrspmv_cuda_matrix *A = NULL;
     int64_t csrsize, diagsize = 0;
-    if (o.device_convert && !o.separate_diagonal && h.symmetry == MTX_GENERAL) {
+    if (o.device_convert && !o.separate_diagonal && !o.sort_rows && h.symmetry == MTX_GENERAL) {
         /* stable sort by row on the device; rowsizemin/max are only printed, count them here */
         int64_t *cnt = calloc((size_t)num_rows + 1, sizeof(*cnt));
         if (!cnt) { fprintf(stderr, "%s: %s\n", prog, strerror(ENOMEM)); return EXIT_FAILURE; }
@@ -236,6 +235,7 @@ int main(int argc, char *argv[])
         err = csr_from_coo(&csr, h.symmetry == MTX_SYMMETRIC, num_rows, num_columns, num_nonzeros, rowidx, colidx, a,
                            o.separate_diagonal);
         free(a); free(colidx); free(rowidx);
+        if (!err && o.sort_rows) err = csr_sort_rows(&csr);
         if (err) {
             if (o.verbose > 0) fprintf(stderr, "\n");
             fprintf(stderr, "%s: %s\n", prog, strerror(err));

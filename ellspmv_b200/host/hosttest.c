@@ -82,8 +82,10 @@ int host_csr_from_file_sd(const char *path, int gzip, int separate_diagonal, int
     int err = read_coo(path, gzip, &h, &ri, &ci, &v, &dims[6]);
     if (err) return err;
     struct csr_matrix csr;
+    /* bit 1 of separate_diagonal asks for --sort-rows as well */
     err = csr_from_coo(&csr, h.symmetry == MTX_SYMMETRIC, h.num_rows, h.num_columns, h.num_nonzeros, ri, ci, v,
-                       separate_diagonal);
+                       separate_diagonal & 1);
+    if (!err && (separate_diagonal & 2)) err = csr_sort_rows(&csr);
     free(ri); free(ci); free(v);
     if (err) return err;
     dims[0] = csr.num_rows; dims[1] = csr.num_columns; dims[2] = h.num_nonzeros;

@@ -330,6 +330,59 @@ int ONAME(oracle_csrgemvsd)(
     return 0;
 }
 
+/*
+ * Sort the entries of every CSR row by column (--sort-rows).  Follows
+ * rowsort, csrspmv.c:1269-1388: rows of at most 16 entries get a stable
+ * insertion sort; longer rows are insertion-sorted in blocks of 16 and the
+ * blocks are merged bottom-up, doubling the width, where on EQUAL columns
+ * the entry of the right-hand run goes first (csrspmv.c:1356-1360) -- so
+ * duplicates of a column keep file order only inside a 16-block.
+ */
+int ONAME(oracle_rowsort)(
+    OIDX num_rows, const int64_t *rowptr, OIDX *colidx, double *a)
+{
+    const int64_t block = 16;
+    int64_t longest = 0;
+    for (int64_t i = 0; i < (int64_t)num_rows; i++)
+        if (rowptr[i + 1] - rowptr[i] > longest) longest = rowptr[i + 1] - rowptr[i];
+    OIDX *tc = (OIDX *)malloc((size_t)(longest > 0 ? longest : 1) * sizeof(OIDX));
+    double *ta = (double *)malloc((size_t)(longest > 0 ? longest : 1) * sizeof(double));
+    if (!tc || !ta) { free(tc); free(ta); return 12; }
+    for (int64_t i = 0; i < (int64_t)num_rows; i++) {
+        OIDX *c = colidx + rowptr[i];
+        double *v = a + rowptr[i];
+        const int64_t n = rowptr[i + 1] - rowptr[i];
+        const int64_t width = n <= block ? (n > 0 ? n : 1) : block;
+        for (int64_t q = 0; q < n - 1; q += width) {
+            const int64_t e = q + width < n ? q + width : n;
+            for (int64_t k = q + 1; k < e; k++) {
+                OIDX cj = c[k]; double vj = v[k];
+                int64_t l = k - 1;
+                while (l >= q && c[l] > cj) { c[l + 1] = c[l]; v[l + 1] = v[l]; l--; }
+                c[l + 1] = cj; v[l + 1] = vj;
+            }
+        }
+        if (n <= block) continue;
+        for (int64_t p = block; p < n; p *= 2) {
+            memcpy(tc, c, (size_t)n * sizeof(OIDX));
+            memcpy(ta, v, (size_t)n * sizeof(double));
+            for (int64_t q = 0; q < n - 1; q += 2 * p) {
+                const int64_t mid = q + p < n ? q + p : n, end = q + 2 * p < n ? q + 2 * p : n;
+                int64_t out = q, l = q, r = mid;
+                while (l < mid && r < end) {
+                    if (tc[l] < tc[r]) { c[out] = tc[l]; v[out] = ta[l]; l++; }
+                    else { c[out] = tc[r]; v[out] = ta[r]; r++; }
+                    out++;
+                }
+                while (l < mid) { c[out] = tc[l]; v[out] = ta[l]; l++; out++; }
+                while (r < end) { c[out] = tc[r]; v[out] = ta[r]; r++; out++; }
+            }
+        }
+    }
+    free(tc); free(ta);
+    return 0;
+}
+
 /* ------------------------------------------------------------------ */
 /* Synthetic matrices of BASELINE.json's shapes.      */
 /* Each generator can emit the ELL arrays for a row range directly     */

@@ -179,6 +179,14 @@ class Oracle:
         f.argtypes = [I, _P, _P, _P, _P, _P, _P]
         assert f(num_rows, _p(y), _p(x), _p(rowptr), _p(colidx), _p(a), _p(ad)) == 0
 
+    def rowsort(self, num_rows, rowptr, colidx, a) -> None:
+        """--sort-rows on a CSR matrix, in place (csrspmv.c:1269-1388)."""
+        bits = colidx.dtype.itemsize * 8
+        I = C.c_int32 if bits == 32 else C.c_int64
+        f = self._f("oracle_rowsort", bits)
+        f.argtypes = [I, _P, _P, _P]
+        assert f(num_rows, _p(rowptr), _p(colidx), _p(a)) == 0
+
     # -- synthetic matrices -----------------------------------------------------
     def gen_ell(self, kind: str, dims, vals=(0.0, 0.0), seed: int = 42, bits: int = 32,
                 row_begin: int = 0, row_end: Optional[int] = None):
@@ -365,3 +373,8 @@ class Reference:
         f.argtypes = [_I64, _P, _I64, _P, _I64, _I64, _I64, _P, _P, _P, _P]
         assert f(num_rows, _p(y), num_columns, _p(x), int(rowptr[num_rows]), rowsizemin, rowsizemax, _p(rowptr),
                  _p(colidx), _p(a), _p(ad)) == 0
+
+    def rowsort(self, num_rows, num_columns, rowptr, rowsizemax, colidx, a) -> None:
+        f = self.lib.ref_rowsort
+        f.argtypes = [_I64, _I64, _P, _I64, _P, _P]
+        assert f(num_rows, num_columns, _p(rowptr), rowsizemax, _p(colidx), _p(a)) == 0

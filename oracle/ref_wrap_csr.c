@@ -149,3 +149,10 @@ int ref_csrgemvsd(
     }
     return err;
 }
+
+/* ---- --sort-rows: the reference's rowsort on a CSR matrix (csrspmv.c:1269-1388) ---- */
+int ref_rowsort(int64_t num_rows, int64_t num_columns, int64_t *rowptr, int64_t rowsizemax,
+                void *colidx, double *a)
+{
+    return rowsort((idx_t)num_rows, (idx_t)num_columns, rowptr, (idx_t)rowsizemax, (idx_t *)colidx, a);
+}

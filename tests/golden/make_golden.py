@@ -71,7 +71,12 @@ def case(name, nrows, ncols, ri, ci, a, x, y0, tmp):
         rowptr, cc, ca, lo, hi = csr.csr_from_coo(nrows, ncols, r, c, av)
         yc = np.array(y0, dtype=np.float64)
         csr.csrgemv(nrows, yc, ncols, np.asarray(x, dtype=np.float64), rowptr, cc, ca, 1, lo, hi)
+        sc, sa = cc.copy(), ca.copy()
+        csr.rowsort(nrows, ncols, rowptr, hi, sc, sa)               # --sort-rows (csrspmv.c:1269-1388)
+        ys = np.array(y0, dtype=np.float64)
+        csr.csrgemv(nrows, ys, ncols, np.asarray(x, dtype=np.float64), rowptr, sc, sa, 1, lo, hi)
         out[f"idx{bits}"] = {
+            "csrcolidx_sorted": [int(t) for t in sc], "csra_sorted": hexlist(sa), "y_csr_sorted": hexlist(ys),
             "rowsize": K, "ellsize": ellsize, "diagsize": diagsize,
             "ellcolidx": [int(t) for t in ec], "ella": hexlist(ea),
             "y_ell": hexlist(y), "y_ell_repeat3": hexlist(y3),
@@ -87,6 +92,7 @@ def case(name, nrows, ncols, ri, ci, a, x, y0, tmp):
         "ellspmv64": run_binary("ellspmv64", [A]),
         "csrspmv": run_binary("csrspmv", [A]),
         "csrspmv64": run_binary("csrspmv64", [A]),
+        "csrspmv_sorted": run_binary("csrspmv", ["--sort-rows", A]),
     }
     if nrows == ncols:   # x from file is only right for square A in the reference (Q3)
         xf, yf = os.path.join(tmp, name + "_x.mtx"), os.path.join(tmp, name + "_y.mtx")
@@ -166,6 +172,12 @@ def main():
             cases.append(case(name, nr, nc, ri.tolist(), ci.tolist(), a.tolist(), x.tolist(), y0.tolist(), tmp))
 
         # 3. a single full row and an all-empty matrix
+        # a matrix with rows longer than 16 and many repeated columns: exercises the merge tie order
+        nr, nc, nnz = 12, 9, 700
+        ri = rng.integers(1, nr + 1, nnz); ri[:300] = 3
+        ci = rng.integers(1, nc + 1, nnz)
+        cases.append(case("long_rows", nr, nc, ri.tolist(), ci.tolist(), rng.uniform(-2, 2, nnz).tolist(),
+                          rng.uniform(-1, 1, nc).tolist(), rng.uniform(-1, 1, nr).tolist(), tmp))
         cases.append(case("one_row", 1, 9, [1] * 9, list(range(9, 0, -1)), [float(i) for i in range(1, 10)],
                           [0.5] * 9, [1.0], tmp))
         cases.append(case("empty", 5, 4, [], [], [], [1.0] * 4, [2.0] * 5, tmp))

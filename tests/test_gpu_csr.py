@@ -92,3 +92,27 @@ def test_random_csr_is_the_ell_matrix(lib, oracle):
     want = np.zeros(dims[0])
     oracle.ellgemv(dims[0], want, x, K, ec, ea)
     assert bits_equal(ye, want) and bits_equal(yc, want)
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_sort_rows_program_and_kernel(tmp_path, lib, name):
+    """csrspmv --sort-rows: stdout equals the reference program's, and the
+    kernel on the reference-sorted arrays gives the reference's y."""
+    import os
+    import subprocess
+
+    import hostlib
+    g = load_golden(name)
+    e = g["idx32"]
+    A = E.CsrMatrix.upload(g["num_rows"], g["num_columns"], np.array(e["rowptr"], dtype=np.int64),
+                           np.array(e["csrcolidx_sorted"], dtype=np.int32), unhex(e["csra_sorted"]))
+    y = unhex(g["y0"])
+    A.spmv(y, unhex(g["x"]), 1, E.ACCUMULATE)
+    A.free()
+    assert bits_equal(y, unhex(e["y_csr_sorted"]))
+    hostlib.build_host()
+    p = str(tmp_path / "A.mtx")
+    hostlib.write_mtx(p, g["num_rows"], g["num_columns"], g["rowidx"], g["colidx"], unhex(g["a"]), comments=())
+    r = subprocess.run([os.path.join(hostlib.BIN, "csrspmv"), "--sort-rows", p], capture_output=True, text=True,
+                       env=dict(os.environ, LC_ALL="C"))
+    assert r.returncode == 0 and r.stdout == g["program"]["csrspmv_sorted"]["stdout"]

@@ -202,3 +202,22 @@ def test_parallel_reader_falls_back_to_the_serial_answer(tmp_path, monkeypatch, 
         assert np.array_equal(par[2], ser[2]) and bits_equal(par[3], ser[3])
     else:
         assert what in ("bad index", "tab", "short file", "huge value")
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+@pytest.mark.parametrize("bits", [32, 64])
+def test_host_sort_rows_matches_reference(tmp_path, name, bits):
+    import ctypes as C
+    g = load_golden(name)
+    e = g[f"idx{bits}"]
+    p = str(tmp_path / "A.mtx")
+    hostlib.write_mtx(p, g["num_rows"], g["num_columns"], g["rowidx"], g["colidx"], unhex(g["a"]))
+    lib = hostlib.hostlib(bits)
+    it = C.c_int32 if bits == 32 else C.c_int64
+    dt = np.int32 if bits == 32 else np.int64
+    dims = (C.c_int64 * 7)()
+    rowptr, colidx, a, ad = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+    assert lib.host_csr_from_file_sd(p.encode(), 0, 2, dims, C.byref(rowptr), C.byref(colidx), C.byref(a), C.byref(ad)) == 0
+    assert hostlib._take(lib, rowptr, g["num_rows"] + 1, C.c_int64, np.int64).tolist() == e["rowptr"]
+    assert hostlib._take(lib, colidx, dims[3], it, dt).tolist() == e["csrcolidx_sorted"]
+    assert bits_equal(hostlib._take(lib, a, dims[3], C.c_double, np.float64), unhex(e["csra_sorted"]))

@@ -80,3 +80,19 @@ def test_iterate_is_repeated_overwrite(oracle):
         want = y
     got = oracle.ell_iterate(n, x, 3, K, ec, ea)
     assert bits_equal(got, want)
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+@pytest.mark.parametrize("bits", [32, 64])
+def test_rowsort_matches_reference(oracle, name, bits):
+    """--sort-rows for CSR (csrspmv.c:1269-1388), including the tie order of duplicate columns."""
+    g = load_golden(name)
+    e = g[f"idx{bits}"]
+    dt = np.int32 if bits == 32 else np.int64
+    rowptr = np.array(e["rowptr"], dtype=np.int64)
+    cc, ca = np.array(e["csrcolidx"], dtype=dt), unhex(e["csra"])
+    oracle.rowsort(g["num_rows"], rowptr, cc, ca)
+    assert cc.tolist() == e["csrcolidx_sorted"] and bits_equal(ca, unhex(e["csra_sorted"]))
+    y = unhex(g["y0"])
+    oracle.csrgemv(g["num_rows"], y, unhex(g["x"]), rowptr, cc, ca)
+    assert bits_equal(y, unhex(e["y_csr_sorted"]))
