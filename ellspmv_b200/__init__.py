@@ -56,7 +56,7 @@ class Info(C.Structure):
         ("idx_width_bits", C.c_int), ("dev_idx_bits", C.c_int), ("slice_rows", C.c_int),
         ("rows_per_thread", C.c_int), ("kernel", C.c_int), ("fma", C.c_int), ("device", C.c_int),
         ("device_bytes", C.c_int64), ("min_col", C.c_int64), ("max_col", C.c_int64),
-        ("launches", C.c_int64),
+        ("launches", C.c_int64), ("num_gpus", C.c_int),
     ]
 
 
@@ -70,6 +70,7 @@ _PROTOTYPES = {
     "csrspmv_cuda_upload_coo": (C.c_int, [C.POINTER(_P), C.c_int, _I64, _I64, _I64, _P, _P, _P, C.c_uint]),
     "csrspmv_cuda_download": (C.c_int, [_P, _P, _P, _P]),
     "ellspmv_cuda_generate": (C.c_int, [C.POINTER(_P), C.c_int, C.POINTER(_I64), C.POINTER(C.c_double), C.c_uint64, C.c_int, _I64, _I64, C.c_int, C.c_uint]),
+    "ellspmv_cuda_generate_sharded": (C.c_int, [C.POINTER(_P), C.c_int, C.POINTER(_I64), C.POINTER(C.c_double), C.c_uint64, C.c_int, C.c_int, C.c_uint]),
     "ellspmv_cuda_spmv": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P]),
     "ellspmv_cuda_spmv_device": (C.c_int, [_P, _P, _P, C.c_int, _P]),
     "ellspmv_cuda_spmv_push": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.POINTER(_P), C.POINTER(_I64), C.POINTER(_I64), _P]),
@@ -172,13 +173,14 @@ class EllMatrix:
     # -- construction -------------------------------------------------------
     @classmethod
     def upload(cls, num_rows: int, num_columns: int, rowsize: int, colidx, a, flags: int = 0,
-               *, global_rows: Optional[int] = None, row_begin: int = 0, device: int = -1) -> "EllMatrix":
+               *, global_rows: Optional[int] = None, row_begin: int = 0, device: int = -1,
+               num_gpus: int = 1) -> "EllMatrix":
         lib = load_library()
         h = C.c_void_p()
         bits = _idx_bits(colidx) if colidx is not None else 32
         if global_rows is None and row_begin == 0 and device < 0:
             err = lib.ellspmv_cuda_upload(C.byref(h), bits, num_rows, num_columns, rowsize,
-                                          _ptr(colidx), _ptr(a), 1, flags)
+                                          _ptr(colidx), _ptr(a), num_gpus, flags)
         else:
             g = num_rows if global_rows is None else global_rows
             err = lib.ellspmv_cuda_upload_shard(C.byref(h), bits, g, num_columns, rowsize, row_begin,
@@ -199,11 +201,15 @@ class EllMatrix:
     @classmethod
     def generate(cls, kind: int, dims: Sequence[int], vals: Sequence[float] = (0.0, 0.0), seed: int = 42,
                  idx_bits: int = 32, row_begin: int = 0, row_end: int = -1, device: int = -1,
-                 flags: int = 0) -> "EllMatrix":
+                 flags: int = 0, num_gpus: int = 1) -> "EllMatrix":
         lib = load_library()
         h = C.c_void_p()
         d = (C.c_int64 * 3)(*(list(dims) + [0, 0, 0])[:3])
         v = (C.c_double * 2)(*vals)
+        if num_gpus > 1:
+            err = lib.ellspmv_cuda_generate_sharded(C.byref(h), kind, d, v, seed, idx_bits, num_gpus, flags)
+            _check(err, "ellspmv_cuda_generate_sharded")
+            return cls(h.value)
         err = lib.ellspmv_cuda_generate(C.byref(h), kind, d, v, seed, idx_bits, row_begin, row_end, device, flags)
         _check(err, "ellspmv_cuda_generate")
         return cls(h.value)

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "handles.cuh"
 
 namespace ellspmv {
 
@@ -40,58 +41,9 @@ int cuda_to_errno(cudaError_t e)
     }
 }
 
-struct DeviceGuard {
-    int prev = -1;
-    bool ok = false;
-    explicit DeviceGuard(int dev) {
-        if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; }
-        ok = cudaSetDevice(dev) == cudaSuccess;
-    }
-    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
-};
-
 }  // namespace ellspmv
 
 using namespace ellspmv;
-
-struct ellspmv_cuda_matrix {
-    int device = 0;
-    EllLayout lay = {};
-    int host_idx_bits = 32, dev_idx_bits = 32;
-    int64_t num_columns = 0, row_begin = 0, global_rows = 0;
-    unsigned flags = 0;
-    EllLaunchCfg cfg = {};
-    double *vals = nullptr;
-    void *cols = nullptr;
-    long long *d_minmax = nullptr;
-    double *d_ad = nullptr;                  // separately stored diagonal (shard rows), optional
-    int sd_order = 0;
-    int64_t min_col = 0, max_col = -1;
-    cudaStream_t stream = nullptr;
-    cudaStream_t stream_out = nullptr;       // D2H stream of the pipelined host call
-    double *d_x = nullptr, *d_y = nullptr;   // vectors of the host-facing spmv
-    int64_t vec_len = 0;
-    std::vector<cudaEvent_t> events;
-    int64_t device_bytes = 0;
-    int64_t launches = 0;
-};
-
-struct csrspmv_cuda_matrix {
-    int device = 0;
-    int idx_bits = 32;
-    int64_t num_rows = 0, num_columns = 0, csrsize = 0;
-    unsigned flags = 0;
-    int kernel = ELLSPMV_CUDA_KERNEL_THREAD;
-    bool fma = false;
-    int64_t *rowptr = nullptr;
-    void *cols = nullptr;
-    double *vals = nullptr;
-    cudaStream_t stream = nullptr;
-    double *d_x = nullptr, *d_y = nullptr;
-    double *d_ad = nullptr;                  // separately stored diagonal, optional
-    std::vector<cudaEvent_t> events;
-    int64_t device_bytes = 0;
-};
 
 namespace {
 
@@ -334,6 +286,15 @@ int new_handle(ellspmv_cuda_matrix **out, int idx_width_bits, int64_t global_row
 
 }  // namespace
 
+namespace ellspmv {
+int launch_shard(ellspmv_cuda_matrix *A, double *y_dev, const double *x_dev, int beta,
+                 const PushTargets *push, cudaStream_t stream)
+{
+    return launch(A, y_dev, x_dev, beta, push, stream, 0, -1);
+}
+int ensure_event_count(std::vector<cudaEvent_t> &ev, size_t n) { return ensure_events(ev, n); }
+}  // namespace ellspmv
+
 extern "C" {
 
 int ellspmv_cuda_version(void) { return ELLSPMV_CUDA_VERSION; }
@@ -357,6 +318,7 @@ int ellspmv_cuda_device_count(int *count)
 void ellspmv_cuda_free(ellspmv_cuda_matrix *A)
 {
     if (!A) return;
+    if (!A->shards.empty()) { group_free(A); return; }
     DeviceGuard g(A->device);
     if (A->stream) cudaStreamSynchronize(A->stream);
     for (cudaEvent_t e : A->events) cudaEventDestroy(e);
@@ -434,9 +396,9 @@ int ellspmv_cuda_upload(
     int64_t num_rows, int64_t num_columns, int64_t rowsize,
     const void *colidx, const double *a, int num_gpus, unsigned flags)
 {
-    if (num_gpus != 1)
-        ELL_FAIL(ENOTSUP, "num_gpus=%d: one handle drives one GPU; shard with "
-                          "ellspmv_cuda_upload_shard (one handle per GPU)", num_gpus);
+    if (num_gpus < 1) ELL_FAIL(EINVAL, "num_gpus must be >= 1");
+    if (num_gpus > 1)
+        return group_upload(out, idx_width_bits, num_rows, num_columns, rowsize, colidx, a, num_gpus, flags);
     return ellspmv_cuda_upload_shard(out, idx_width_bits, num_rows, num_columns, rowsize,
                                      0, num_rows, colidx, a, -1, flags);
 }
@@ -535,9 +497,19 @@ int ellspmv_cuda_generate(
     return 0;
 }
 
+int ellspmv_cuda_generate_sharded(
+    ellspmv_cuda_matrix **out, int kind, const int64_t dims[3],
+    const double vals[2], uint64_t seed, int idx_width_bits, int num_gpus, unsigned flags)
+{
+    if (num_gpus < 1) ELL_FAIL(EINVAL, "num_gpus must be >= 1");
+    if (num_gpus == 1) return ellspmv_cuda_generate(out, kind, dims, vals, seed, idx_width_bits, 0, -1, -1, flags);
+    return group_generate(out, kind, dims, vals, seed, idx_width_bits, num_gpus, flags);
+}
+
 int ellspmv_cuda_download(const ellspmv_cuda_matrix *A, void *colidx, double *a)
 {
     if (!A) ELL_FAIL(EINVAL, "matrix is NULL");
+    if (!A->shards.empty()) return group_download(A, colidx, a);
     const int64_t rows = A->lay.num_rows, K = A->lay.rowsize;
     if (rows == 0 || K == 0) return 0;
     if (!colidx || !a) ELL_FAIL(EINVAL, "colidx or a is NULL");
@@ -565,6 +537,14 @@ int ellspmv_cuda_download(const ellspmv_cuda_matrix *A, void *colidx, double *a)
 int ellspmv_cuda_set_diagonal(ellspmv_cuda_matrix *A, const double *ad, int order)
 {
     if (!A) ELL_FAIL(EINVAL, "matrix is NULL");
+    if (!A->shards.empty()) {
+        // each shard takes its own rows of the diagonal
+        for (ellspmv_cuda_matrix *S : A->shards) {
+            int err = ellspmv_cuda_set_diagonal(S, ad ? ad + S->row_begin : nullptr, order);
+            if (err) return err;
+        }
+        return 0;
+    }
     if (order != 0 && order != 1) ELL_FAIL(EINVAL, "order must be 0 (ellgemvsd) or 1 (ellgemv16sd)");
     DeviceGuard g(A->device);
     if (!ad) {
@@ -591,6 +571,7 @@ int ellspmv_cuda_set_diagonal(ellspmv_cuda_matrix *A, const double *ad, int orde
 int ellspmv_cuda_get_info(const ellspmv_cuda_matrix *A, ellspmv_cuda_info *info)
 {
     if (!A || !info) ELL_FAIL(EINVAL, "NULL argument");
+    if (!A->shards.empty()) return group_info(A, info);
     memset(info, 0, sizeof(*info));
     info->num_rows = A->lay.num_rows;
     info->num_columns = A->num_columns;
@@ -608,6 +589,7 @@ int ellspmv_cuda_get_info(const ellspmv_cuda_matrix *A, ellspmv_cuda_info *info)
     info->min_col = A->min_col;
     info->max_col = A->max_col;
     info->launches = A->launches;
+    info->num_gpus = 1;
     return 0;
 }
 
@@ -615,6 +597,7 @@ int ellspmv_cuda_spmv_device(
     ellspmv_cuda_matrix *A, double *y_dev, const double *x_dev, int mode, void *stream)
 {
     if (!A) ELL_FAIL(EINVAL, "matrix is NULL");
+    if (!A->shards.empty()) ELL_FAIL(EINVAL, "spmv_device needs a single-GPU handle (this one spans %d GPUs)", (int)A->shards.size());
     if (mode != ELLSPMV_CUDA_ACCUMULATE && mode != ELLSPMV_CUDA_OVERWRITE)
         ELL_FAIL(EINVAL, "spmv_device: mode must be ACCUMULATE or OVERWRITE");
     if (A->lay.num_rows > 0 && (!y_dev || (!x_dev && A->lay.rowsize > 0)))
@@ -629,6 +612,7 @@ int ellspmv_cuda_spmv_push(
     const int64_t *peer_row_lo, const int64_t *peer_row_hi, void *stream)
 {
     if (!A) ELL_FAIL(EINVAL, "matrix is NULL");
+    if (!A->shards.empty()) ELL_FAIL(EINVAL, "spmv_push needs a single-GPU handle");
     if (mode != ELLSPMV_CUDA_ACCUMULATE && mode != ELLSPMV_CUDA_OVERWRITE)
         ELL_FAIL(EINVAL, "spmv_push: mode must be ACCUMULATE or OVERWRITE");
     if (num_peers < 0 || num_peers > kMaxPeers) ELL_FAIL(EINVAL, "num_peers must be 0..%d", kMaxPeers);
@@ -655,6 +639,7 @@ int ellspmv_cuda_spmv(
     if (repeat < 0) ELL_FAIL(EINVAL, "repeat < 0");
     if (mode != ELLSPMV_CUDA_ACCUMULATE && mode != ELLSPMV_CUDA_OVERWRITE && mode != ELLSPMV_CUDA_ITERATE)
         ELL_FAIL(EINVAL, "unknown mode %d", mode);
+    if (!A->shards.empty()) return group_spmv(A, y, x, repeat, mode, seconds);
     const int64_t rows = A->lay.num_rows, ncols = A->num_columns;
     if ((rows > 0 && !y) || (ncols > 0 && !x)) ELL_FAIL(EINVAL, "NULL host vector");
     if (mode == ELLSPMV_CUDA_ITERATE && !(A->row_begin == 0 && rows == A->global_rows && rows == ncols))

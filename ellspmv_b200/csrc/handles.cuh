@@ -1,0 +1,86 @@
+// handles.cuh -- the opaque handle types behind include/ellspmv_cuda.h, shared by
+// api.cu (one GPU) and group.cu (several GPUs driven by one host thread).
+#pragma once
+
+#include <vector>
+
+#include "common.cuh"
+
+namespace ellspmv {
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; }
+        ok = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+
+}  // namespace ellspmv
+
+struct ellspmv_cuda_matrix {
+    int device = 0;
+    ellspmv::EllLayout lay = {};
+    int host_idx_bits = 32, dev_idx_bits = 32;
+    int64_t num_columns = 0, row_begin = 0, global_rows = 0;
+    unsigned flags = 0;
+    ellspmv::EllLaunchCfg cfg = {};
+    double *vals = nullptr;
+    void *cols = nullptr;
+    long long *d_minmax = nullptr;
+    double *d_ad = nullptr;                  // separately stored diagonal (shard rows), optional
+    int sd_order = 0;
+    int64_t min_col = 0, max_col = -1;
+    cudaStream_t stream = nullptr;
+    cudaStream_t stream_out = nullptr;       // D2H stream of the pipelined host call
+    double *d_x = nullptr, *d_y = nullptr;   // vectors of the host-facing spmv
+    int64_t vec_len = 0;
+    std::vector<cudaEvent_t> events;
+    int64_t device_bytes = 0;
+    int64_t launches = 0;
+
+    // ---- group handle (num_gpus > 1): one shard handle per GPU ----------------
+    std::vector<ellspmv_cuda_matrix *> shards;
+    std::vector<double *> xb[2];            // per device: two full-length vectors (current / next x)
+    std::vector<long long *> bflags;        // per device: 32 int64 barrier flags
+    std::vector<std::vector<cudaEvent_t>> gevents;
+    long long epoch = 0;
+    int64_t vec_elems = 0;
+};
+
+struct csrspmv_cuda_matrix {
+    int device = 0;
+    int idx_bits = 32;
+    int64_t num_rows = 0, num_columns = 0, csrsize = 0;
+    unsigned flags = 0;
+    int kernel = ELLSPMV_CUDA_KERNEL_THREAD;
+    bool fma = false;
+    int64_t *rowptr = nullptr;
+    void *cols = nullptr;
+    double *vals = nullptr;
+    cudaStream_t stream = nullptr;
+    double *d_x = nullptr, *d_y = nullptr;
+    double *d_ad = nullptr;                  // separately stored diagonal, optional
+    std::vector<cudaEvent_t> events;
+    int64_t device_bytes = 0;
+};
+
+
+namespace ellspmv {
+// group.cu
+int group_upload(ellspmv_cuda_matrix **out, int idx_width_bits, int64_t num_rows, int64_t num_columns,
+                 int64_t rowsize, const void *colidx, const double *a, int num_gpus, unsigned flags);
+int group_generate(ellspmv_cuda_matrix **out, int kind, const int64_t dims[3], const double vals[2],
+                   uint64_t seed, int idx_width_bits, int num_gpus, unsigned flags);
+int group_spmv(ellspmv_cuda_matrix *G, double *y, const double *x, int repeat, int mode, double *seconds);
+int group_download(const ellspmv_cuda_matrix *G, void *colidx, double *a);
+int group_info(const ellspmv_cuda_matrix *G, ellspmv_cuda_info *info);
+void group_free(ellspmv_cuda_matrix *G);
+// api.cu internals the group needs
+int launch_shard(ellspmv_cuda_matrix *A, double *y_dev, const double *x_dev, int beta,
+                 const PushTargets *push, cudaStream_t stream);
+int ensure_event_count(std::vector<cudaEvent_t> &ev, size_t n);
+}  // namespace ellspmv

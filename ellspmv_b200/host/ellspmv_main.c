@@ -54,7 +54,7 @@ struct options {
     unsigned flags;
     bool iterate, device_convert;
     const char *synthetic;
-    int device;
+    int device, gpus;
 };
 
 static void usage(FILE *f) { fprintf(f, "Usage: %s [OPTION..] A [x] [y]\n", prog); }
@@ -94,6 +94,7 @@ static void help(FILE *f)
     fprintf(f, "  --synthetic=SPEC     build A on the device instead of reading a file:\n");
     fprintf(f, "                       laplace2d:NX,NY | stencil27:NX,NY,NZ | random:ROWS,COLS,K[,SEED]\n");
     fprintf(f, "  --device-convert     convert COO to ELL on the device (same arrays as the host conversion)\n");
+    fprintf(f, "  --gpus=N             shard the rows over CUDA devices 0..N-1 of this machine [1]\n");
     fprintf(f, "  --device=N           CUDA device ordinal [current]\n");
     fprintf(f, "\n");
     fprintf(f, "  -h, --help           display this help and exit\n");
@@ -121,6 +122,7 @@ static int parse_options(int argc, char **argv, struct options *o, int *bad)
     memset(o, 0, sizeof(*o));
     o->repeat = 1;
     o->device = -1;
+    o->gpus = 1;
     int npos = 0;
     bool only_positional = false;
     for (int i = 1; i < argc; i++) {
@@ -170,6 +172,10 @@ static int parse_options(int argc, char **argv, struct options *o, int *bad)
             if (!strcmp(a, "--device-convert")) { o->device_convert = true; continue; }
             if (!strncmp(a, "--synthetic", 11) && (a[11] == '=' || a[11] == '\0')) {
                 if (!(o->synthetic = optval(argc, argv, &i, "--synthetic"))) return EINVAL;
+                continue;
+            }
+            if (!strncmp(a, "--gpus", 6) && (a[6] == '=' || a[6] == '\0')) {
+                if (!(v = optval(argc, argv, &i, "--gpus")) || to_int(v, &o->gpus) || o->gpus < 1) return EINVAL;
                 continue;
             }
             if (!strncmp(a, "--device", 8) && (a[8] == '=' || a[8] == '\0')) {
@@ -255,7 +261,8 @@ int main(int argc, char *argv[])
             return EXIT_FAILURE;
         }
         if (o.verbose > 0) { fprintf(stderr, "cuda_generate: "); clock_gettime(CLOCK_MONOTONIC, &t0); }
-        err = ellspmv_cuda_generate(&A, kind, dims, vals, seed, IDX_BITS, 0, -1, o.device, o.flags);
+        if (o.gpus > 1) err = ellspmv_cuda_generate_sharded(&A, kind, dims, vals, seed, IDX_BITS, o.gpus, o.flags);
+        else err = ellspmv_cuda_generate(&A, kind, dims, vals, seed, IDX_BITS, 0, -1, o.device, o.flags);
         if (err) {
             if (o.verbose > 0) fprintf(stderr, "\n");
             fprintf(stderr, "%s: %s (%s)\n", prog, strerror(err), ellspmv_cuda_last_error());
@@ -315,7 +322,7 @@ int main(int argc, char *argv[])
 
         /* 3. convert to ELLPACK (ellspmv.c:1379-1486) */
         if (o.verbose > 0) { fprintf(stderr, "ell_from_coo: "); clock_gettime(CLOCK_MONOTONIC, &t0); }
-        if (o.device_convert && !o.separate_diagonal) {
+        if (o.device_convert && !o.separate_diagonal && o.gpus == 1) {
             /* stable sort by row on the device instead of the serial host scatter */
             err = ellspmv_cuda_upload_coo(&A, IDX_BITS, num_rows, num_columns, num_nonzeros, rowidx, colidx, a,
                                           o.device, o.flags);
@@ -358,11 +365,11 @@ int main(int argc, char *argv[])
 
         /* device copy + re-layout: the one step the reference does not have */
         if (o.verbose > 0) { fprintf(stderr, "cuda_upload: "); clock_gettime(CLOCK_MONOTONIC, &t0); }
-        if (o.device >= 0)
+        if (o.device >= 0 && o.gpus == 1)
             err = ellspmv_cuda_upload_shard(&A, IDX_BITS, num_rows, num_columns, rowsize, 0, num_rows,
                                             ell.colidx, ell.a, o.device, o.flags);
         else
-            err = ellspmv_cuda_upload(&A, IDX_BITS, num_rows, num_columns, rowsize, ell.colidx, ell.a, 1, o.flags);
+            err = ellspmv_cuda_upload(&A, IDX_BITS, num_rows, num_columns, rowsize, ell.colidx, ell.a, o.gpus, o.flags);
         /* same dispatch as the reference: K == 16 takes the unrolled kernel's
          * summation order (ellspmv.c:1759-1768) */
         if (!err && o.separate_diagonal) err = ellspmv_cuda_set_diagonal(A, ell.ad, rowsize == 16 ? 1 : 0);
@@ -376,9 +383,9 @@ int main(int argc, char *argv[])
             ellspmv_cuda_info info;
             ellspmv_cuda_get_info(A, &info);
             clock_gettime(CLOCK_MONOTONIC, &t1);
-            fprintf(stderr, "%'.6f seconds, device %d, %'" PRId64 " bytes, sliced ELL %d rows/slice, "
+            fprintf(stderr, "%'.6f seconds, %d GPU(s), %'" PRId64 " bytes, sliced ELL %d rows/slice, "
                             "%d rows/thread, %d-bit indices\n",
-                    seconds_between(t0, t1), info.device, info.device_bytes, info.slice_rows,
+                    seconds_between(t0, t1), info.num_gpus, info.device_bytes, info.slice_rows,
                     info.rows_per_thread, info.dev_idx_bits);
         }
         }

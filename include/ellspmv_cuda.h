@@ -97,6 +97,7 @@ typedef struct ellspmv_cuda_info {
     int64_t device_bytes;    /* bytes of HBM held by the handle             */
     int64_t min_col, max_col;/* column range referenced by this shard       */
     int64_t launches;        /* SpMV kernel launches issued so far          */
+    int     num_gpus;        /* GPUs behind this handle (row shards)        */
 } ellspmv_cuda_info;
 
 /* ---- ELL ------------------------------------------------------------- */
@@ -107,8 +108,13 @@ typedef struct ellspmv_cuda_info {
  * device and re-lay it as sliced ELL.  Replaces nothing in the reference;
  * call it once after ell_from_coo (~ellspmv.c:1745).
  *   idx_width_bits  32 or 64 (sizeof(idx_t)*8)
- *   num_gpus        1 (sharding over several GPUs in one process is driven
- *                   through ellspmv_cuda_upload_shard, one handle per GPU)
+ *   num_gpus        1, or N > 1: rows are split in N contiguous blocks
+ *                   (rows/N + (p < rows%N), the reference's static split,
+ *                   csrspmv.c:2238) over CUDA devices 0..N-1 of this process;
+ *                   ellspmv_cuda_spmv then drives all of them from the calling
+ *                   thread (peer access over NVLink; ITERATE uses the fused
+ *                   SpMV+push kernel and the device-side barrier, no NCCL).
+ *                   spmv_device/spmv_push need a single-GPU handle.
  */
 int ellspmv_cuda_upload(
     ellspmv_cuda_matrix **out, int idx_width_bits,
@@ -149,6 +155,11 @@ int ellspmv_cuda_generate(
     ellspmv_cuda_matrix **out, int kind, const int64_t dims[3],
     const double vals[2], uint64_t seed, int idx_width_bits,
     int64_t row_begin, int64_t row_end, int device, unsigned flags);
+
+/* the same over num_gpus row shards (see ellspmv_cuda_upload) */
+int ellspmv_cuda_generate_sharded(
+    ellspmv_cuda_matrix **out, int kind, const int64_t dims[3],
+    const double vals[2], uint64_t seed, int idx_width_bits, int num_gpus, unsigned flags);
 
 /*
  * y <- y + A*x (mode ACCUMULATE; replaces the ellgemv call,
