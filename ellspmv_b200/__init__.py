@@ -28,6 +28,7 @@ KERNEL_AUTO, KERNEL_THREAD, KERNEL_WARP = 0, 1, 2
 FMA = 1 << 4
 L2_PERSIST_X = 1 << 5
 NARROW_INDEX = 1 << 6
+COLUMN_BLOCKED = 1 << 7
 ROWS_PER_THREAD_SHIFT = 8
 VARIANT_SHIFT = 12
 ACCUMULATE, OVERWRITE, ITERATE = 0, 1, 2

@@ -150,6 +150,25 @@ int finish_minmax(ellspmv_cuda_matrix *A)
     return 0;
 }
 
+// ELLSPMV_CUDA_COLUMN_BLOCKED: bin the entries by column block so that each
+// block's slice of x stays in L2 (ell_blocked.cu); no-op when x already fits
+int build_column_blocks(ellspmv_cuda_matrix *A)
+{
+    if (!(A->flags & ELLSPMV_CUDA_COLUMN_BLOCKED) || A->lay.num_rows <= 0 || A->lay.rowsize <= 0) return 0;
+    // x bytes per column block: 48 MB stays resident in the 126 MB (2 x 63 MB) L2 next to the
+    // streaming matrix -- measured 11.6 / 9.2 / 9.8 / 13.5 ms at 32 / 48 / 64 / 80 MB on BASELINE
+    // config 4 (profiles/r1_c4_column_blocked.md); ELLSPMV_CUDA_BLOCK_BYTES overrides it
+    long long target = 48LL << 20;
+    if (const char *env = getenv("ELLSPMV_CUDA_BLOCK_BYTES")) {
+        long long v = atoll(env);
+        if (v >= 8) target = v;
+    }
+    cudaError_t ce = cb_build(&A->cb, A->dev_idx_bits, A->vals, A->cols, A->lay, A->num_columns, target, A->stream);
+    if (ce != cudaSuccess) { set_last_error("column blocking: %s", cudaGetErrorString(ce)); return cuda_to_errno(ce); }
+    A->device_bytes += cb_bytes(A->cb);
+    return 0;
+}
+
 int ensure_vectors(ellspmv_cuda_matrix *A)
 {
     int64_t need = A->lay.num_rows > A->num_columns ? A->lay.num_rows : A->num_columns;
@@ -195,6 +214,11 @@ int launch(ellspmv_cuda_matrix *A, double *y_dev, const double *x_dev, int beta,
     args.sd_order = A->sd_order;
     if (num_slices < 0) num_slices = A->lay.num_slices - slice_begin;
     if (push) args.push = *push; else args.push.num_peers = 0;
+    if (A->cb && !push && !A->d_ad && slice_begin == 0 && num_slices == A->lay.num_slices) {
+        ELL_CK(cb_spmv(A->cb, A->cfg.fma, x_dev, y_dev, A->lay.num_rows, A->num_columns, beta, stream));
+        A->launches += cb_blocks(A->cb);
+        return 0;
+    }
     if (A->lay.rowsize == 0 && !A->d_ad) {
         // K = 0: y += 0 for beta=1, y = 0 for beta=0
         if (!beta && A->lay.num_rows > 0)
@@ -326,6 +350,7 @@ void ellspmv_cuda_free(ellspmv_cuda_matrix *A)
     if (A->cols) cudaFree(A->cols);
     if (A->d_minmax) cudaFree(A->d_minmax);
     if (A->d_ad) cudaFree(A->d_ad);
+    if (A->cb) cb_free(A->cb);
     if (A->d_x) cudaFree(A->d_x);
     if (A->d_y) cudaFree(A->d_y);
     if (A->stream) cudaStreamDestroy(A->stream);
@@ -384,6 +409,7 @@ int ellspmv_cuda_upload_shard(
             return fail(cuda_to_errno(ce));
         }
         if ((err = finish_minmax(A))) return fail(err);
+        if ((err = build_column_blocks(A))) return fail(err);
     } else {
         cudaError_t ce = cudaStreamSynchronize(A->stream);
         if (ce != cudaSuccess) { set_last_error("upload: %s", cudaGetErrorString(ce)); return fail(cuda_to_errno(ce)); }
@@ -448,6 +474,7 @@ int ellspmv_cuda_upload_coo(
         else if (bad) { set_last_error("upload_coo: column index outside [1, %lld]", (long long)num_columns); err = EINVAL; }
     }
     if (!err && A->lay.num_rows > 0 && A->lay.rowsize > 0) err = finish_minmax(A);
+    if (!err) err = build_column_blocks(A);
     coo_to_ell_release(job);
     cudaFree(d_ri); cudaFree(d_ci); cudaFree(d_a);
     if (s) cudaStreamDestroy(s);
@@ -491,6 +518,7 @@ int ellspmv_cuda_generate(
                                          A->lay, row_begin, A->d_minmax, A->stream);
         if (ce != cudaSuccess) { set_last_error("generate: %s", cudaGetErrorString(ce)); return fail(cuda_to_errno(ce)); }
         if ((err = finish_minmax(A))) return fail(err);
+        if ((err = build_column_blocks(A))) return fail(err);
     } else {
         cudaStreamSynchronize(A->stream);
     }
@@ -648,7 +676,7 @@ int ellspmv_cuda_spmv(
     DeviceGuard g(A->device);
     int err = ensure_vectors(A);
     if (err) return err;
-    if (repeat == 1 && mode != ELLSPMV_CUDA_ITERATE && rows >= (1 << 20) && A->lay.rowsize > 0 && ncols > 0)
+    if (repeat == 1 && mode != ELLSPMV_CUDA_ITERATE && rows >= (1 << 20) && A->lay.rowsize > 0 && ncols > 0 && !A->cb)
         return spmv_pipelined(A, y, x, mode == ELLSPMV_CUDA_ACCUMULATE ? 1 : 0, seconds);
     if ((err = ensure_events(A->events, (size_t)repeat + 1))) return err;
     cudaStream_t s = A->stream;

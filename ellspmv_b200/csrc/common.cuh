@@ -134,6 +134,17 @@ cudaError_t generate_csr_random(const int64_t dims[3], uint64_t seed, int idx_bi
                                 int64_t *rowptr, void *cols, double *vals, cudaStream_t stream);
 cudaError_t init_minmax(long long *minmax, cudaStream_t stream);
 
+// ---- column-blocked ELL (ell_blocked.cu) ----------------------------------------
+struct CbMatrix;
+cudaError_t cb_build(CbMatrix **out, int idx_bits, const double *vals, const void *cols, const EllLayout &lay,
+                     int64_t num_columns, int64_t target_x_bytes, cudaStream_t stream);
+cudaError_t cb_spmv(const CbMatrix *cb, bool fma, const double *x, double *y, int64_t num_rows, int64_t num_columns,
+                    int beta, cudaStream_t stream);
+void cb_free(CbMatrix *cb);
+int64_t cb_bytes(const CbMatrix *cb);
+int cb_blocks(const CbMatrix *cb);
+int64_t cb_entries(const CbMatrix *cb);
+
 // ---- COO -> ELL / CSR on the device (convert.cu) ------------------------------
 struct CooEllJob {
     int idx_bits = 32;

@@ -56,6 +56,14 @@ enum {
      * num_columns < 2^31 (a device-layout choice; host arrays and
      * ellspmv_cuda_download() stay 64-bit and bit-exact) */
     ELLSPMV_CUDA_NARROW_INDEX  = 1 << 6,
+    /* bin the entries by column block so that each block's slice of x
+     * (<= 48 MB) stays in L2, and run y += A_b*x block after block: for
+     * matrices with scattered columns and an x larger than L2 (BASELINE
+     * config 4).  Tolerance mode: inside a block the reference's order is
+     * kept, but the per-block partial sums are added block by block; stored
+     * zeros are dropped.  Keeps the regular layout as well (download, push
+     * and separate-diagonal calls use it). */
+    ELLSPMV_CUDA_COLUMN_BLOCKED = 1 << 7,
     /* rows handled per thread in the thread-per-row kernel: 0 = auto */
     ELLSPMV_CUDA_ROWS_PER_THREAD_SHIFT = 8,
     ELLSPMV_CUDA_ROWS_PER_THREAD_MASK  = 0x7 << 8,

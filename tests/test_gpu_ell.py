@@ -278,3 +278,35 @@ def test_bulk_async_variant_is_bit_exact(lib, oracle, shape, bits):
         A.spmv(y, x, 1, E.OVERWRITE)
         assert bits_equal(y, want0), (shape, bits, R)
         A.free()
+
+
+@pytest.mark.parametrize("shape", [(1, 40, 3), (1000, 1000, 7), (5003, 9001, 27), (300, 70000, 32), (4097, 4097, 64)])
+@pytest.mark.parametrize("bits", [32, 64])
+def test_column_blocked_mode(lib, oracle, shape, bits, monkeypatch):
+    """ELLSPMV_CUDA_COLUMN_BLOCKED (tolerance mode): entries binned by column
+    block, y += A_b*x block after block.  Forced to many small blocks here."""
+    nr, nc, K = shape
+    dt = np.int32 if bits == 32 else np.int64
+    rng = np.random.default_rng(nr + nc + K + bits)
+    ec, ea = rand_ell(rng, nr, nc, K, dt)
+    x = rng.standard_normal(nc)
+    y0 = rng.standard_normal(nr)
+    want0 = np.zeros(nr)
+    oracle.ellgemv(nr, want0, x, K, ec, ea)
+    absprod = np.abs(ea.reshape(nr, K) * x[ec.reshape(nr, K)]).sum(axis=1)
+    bound = (K + 2 + 64) * 2.0 ** -53 * absprod            # up to 64 extra additions of block partial sums
+    for block_bytes in (256, 8 * 1024, 1 << 30):
+        monkeypatch.setenv("ELLSPMV_CUDA_BLOCK_BYTES", str(block_bytes))
+        for flags in (E.COLUMN_BLOCKED, E.COLUMN_BLOCKED | E.FMA):
+            A = E.EllMatrix.upload(nr, nc, K, ec, ea, flags)
+            c2, a2 = A.download()                       # the regular layout is still there, bit for bit
+            assert np.array_equal(c2, ec) and bits_equal(a2, ea)
+            y = y0.copy()
+            A.spmv(y, x, 1, E.ACCUMULATE)
+            assert np.all(np.abs(y - (y0 + want0)) <= bound + 4e-16 * np.abs(y0) + 1e-300), (shape, bits, block_bytes, flags)
+            y = rng.standard_normal(nr)
+            A.spmv(y, x, 1, E.OVERWRITE)
+            assert np.all(np.abs(y - want0) <= bound + 1e-300)
+            if block_bytes == 1 << 30 and flags == E.COLUMN_BLOCKED:
+                assert bits_equal(y, want0)             # one block: falls back to the bit-exact kernel
+            A.free()

@@ -26,7 +26,7 @@ CONFIGS = {
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
-    ap.add_argument("--path", default="ell", choices=["ell", "csr", "csrvec"])
+    ap.add_argument("--path", default="ell", choices=["ell", "csr", "csrvec"])  # --flags 0x80 = column-blocked ELL
     ap.add_argument("--launches", type=int, default=4)
     ap.add_argument("--flags", type=lambda s: int(s, 0), default=0)
     ap.add_argument("--mode", default="accumulate", choices=["accumulate", "overwrite"])
