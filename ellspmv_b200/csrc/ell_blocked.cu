@@ -134,6 +134,7 @@ struct CbMatrix {
     long long *offs = nullptr;        // num_blocks * num_micro + 1
     unsigned short *meta = nullptr;   // num_blocks * num_micro * 32: count | lane << 8, sorted by count
     int64_t bytes = 0;
+    int num_sms = 148;
     bool persist = false;             // an L2 persisting carve-out for the x block is configured
 };
 
@@ -210,6 +211,7 @@ cudaError_t cb_build(CbMatrix **out, int idx_bits, const double *vals, const voi
     int dev = 0;
     cudaDeviceProp prop;
     if (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&prop, dev) == cudaSuccess) {
+        cb->num_sms = prop.multiProcessorCount;
         const size_t want = (size_t)cb->lay.block_cols * 8;
         if (prop.persistingL2CacheMaxSize > 0 && want <= (size_t)prop.accessPolicyMaxWindowSize &&
             !getenv("ELLSPMV_CUDA_NO_PERSIST")) {
@@ -227,7 +229,11 @@ int cb_blocks(const CbMatrix *cb) { return cb ? cb->lay.num_blocks : 0; }
 int64_t cb_entries(const CbMatrix *cb) { return cb ? cb->lay.total_entries : 0; }
 
 // ---- kernel --------------------------------------------------------------------
-// one warp per micro-slice of one column block; lane p = the row with the p-th most entries
+// Persistent warps: warp w walks micro-slices w, w+W, w+2W, ... of one column
+// block; lane p = the row with the p-th most entries.  The (count, lane) record
+// and the start offset of the NEXT micro-slice are requested before the current
+// one is processed, which removes one of the three dependent memory hops
+// (record/offset -> entries -> gathers) from every task.
 template <typename IdxT, bool FMA>
 __global__ void __launch_bounds__(kBlockThreads)
 ell_blocked_kernel(const double *__restrict__ vals, const IdxT *__restrict__ cols, const long long *__restrict__ offs,
@@ -235,43 +241,52 @@ ell_blocked_kernel(const double *__restrict__ vals, const IdxT *__restrict__ col
                    int64_t num_rows, int64_t num_micro, int block, int mode /* 0: y = acc, 1: y += acc */)
 {
     const int lane = threadIdx.x & 31;
-    const int64_t m = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    int64_t m = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     if (m >= num_micro) return;
-    const int64_t i = (int64_t)block * num_micro + m;
-    const unsigned rec = meta[i * 32 + lane];
-    const int cnt = rec & 0xff;
-    const int64_t row = m * 32 + (rec >> 8);
-    long long base = offs[i];
-    const int maxc = __shfl_sync(0xffffffffu, cnt, 0);        // lane 0 holds the longest row
-    // y is only needed at the end: ask for it first so that its latency hides behind the loop
-    double yold = 0.0;
-    if (mode != 0 && cnt > 0) yold = y[row];
-    // U diagonals per batch, all loads of a batch before its gathers.  Kept at 4 and
-    // 32 registers on purpose: a deeper software pipeline (8 + prefetch, 96 registers)
-    // measured 14.3 ms on BASELINE config 4 against 9.6 ms for this one -- with only a
-    // few hundred entries per warp and block, resident warps hide the latency better
-    // than per-warp pipelining (profiles/r1_c4_column_blocked.md)
-    constexpr int U = 4;
-    double acc = 0.0;
-    for (int j = 0; j < maxc; j += U) {
-        double v[U], xv[U]; int64_t c[U];
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            const bool on = cnt > j + u;
-            const unsigned active = __ballot_sync(0xffffffffu, on);
-            v[u] = 0.0; c[u] = -1;
-            if (on) { v[u] = __ldcs(vals + base + lane); c[u] = (int64_t)__ldcs(cols + base + lane); }
-            base += __popc(active);
+    const int64_t i0 = (int64_t)block * num_micro;
+    unsigned rec_next = meta[(i0 + m) * 32 + lane];
+    long long base_next = offs[i0 + m];
+    for (; m < num_micro; m += warps) {
+        const unsigned rec = rec_next;
+        long long base = base_next;
+        const int64_t mn = m + warps;
+        if (mn < num_micro) {                       // prefetch the next task's record and offset
+            rec_next = meta[(i0 + mn) * 32 + lane];
+            base_next = offs[i0 + mn];
         }
+        const int cnt = rec & 0xff;
+        const int64_t row = m * 32 + (rec >> 8);
+        const int maxc = __shfl_sync(0xffffffffu, cnt, 0);        // lane 0 holds the longest row
+        // y is only needed at the end: ask for it first so that its latency hides behind the loop
+        double yold = 0.0;
+        if (mode != 0 && cnt > 0) yold = y[row];
+        // U diagonals per batch, all loads of a batch before its gathers.  Kept at 4 and few
+        // registers on purpose: a deeper per-warp pipeline (8 + prefetch, 96 registers) measured
+        // 14.3 ms on BASELINE config 4 against 9.6 ms -- with only a few hundred entries per
+        // task, resident warps hide latency better (profiles/r1_c4_column_blocked.md)
+        constexpr int U = 4;
+        double acc = 0.0;
+        for (int j = 0; j < maxc; j += U) {
+            double v[U], xv[U]; int64_t c[U];
 #pragma unroll
-        for (int u = 0; u < U; u++) xv[u] = c[u] >= 0 ? __ldg(x + c[u]) : 0.0;
+            for (int u = 0; u < U; u++) {
+                const bool on = cnt > j + u;
+                const unsigned active = __ballot_sync(0xffffffffu, on);
+                v[u] = 0.0; c[u] = -1;
+                if (on) { v[u] = __ldcs(vals + base + lane); c[u] = (int64_t)__ldcs(cols + base + lane); }
+                base += __popc(active);
+            }
 #pragma unroll
-        for (int u = 0; u < U; u++)
-            if (c[u] >= 0) acc = FMA ? __fma_rn(v[u], xv[u], acc) : __dadd_rn(acc, __dmul_rn(v[u], xv[u]));
-    }
-    if (row < num_rows) {
-        if (mode == 0) y[row] = __dadd_rn(0.0, acc);
-        else if (cnt > 0) y[row] = __dadd_rn(yold, acc);
+            for (int u = 0; u < U; u++) xv[u] = c[u] >= 0 ? __ldg(x + c[u]) : 0.0;
+#pragma unroll
+            for (int u = 0; u < U; u++)
+                if (c[u] >= 0) acc = FMA ? __fma_rn(v[u], xv[u], acc) : __dadd_rn(acc, __dmul_rn(v[u], xv[u]));
+        }
+        if (row < num_rows) {
+            if (mode == 0) y[row] = __dadd_rn(0.0, acc);
+            else if (cnt > 0) y[row] = __dadd_rn(yold, acc);
+        }
     }
 }
 
@@ -279,6 +294,15 @@ template <typename IdxT, bool FMA>
 static cudaError_t cb_launch_block(const CbMatrix *cb, const double *x, double *y, int64_t num_rows, int64_t num_columns,
                                    int b, int mode, unsigned grid, cudaStream_t stream)
 {
+    // persistent grid: exactly the CTAs that are resident at once (a multiple of the SM count)
+    static int per_sm = 0;
+    if (per_sm == 0) {
+        int n = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, ell_blocked_kernel<IdxT, FMA>, kBlockThreads, 0) != cudaSuccess || n < 1) n = 8;
+        per_sm = n;
+    }
+    const unsigned resident = (unsigned)(cb->num_sms * per_sm);
+    if (grid > resident) grid = resident;
     cudaLaunchConfig_t lc = {};
     lc.gridDim = dim3(grid);
     lc.blockDim = dim3(kBlockThreads);
@@ -308,9 +332,9 @@ cudaError_t cb_spmv(const CbMatrix *cb, bool fma, const double *x, double *y, in
                     int beta, cudaStream_t stream)
 {
     const CbLayout &L = cb->lay;
-    const int64_t grid = (L.num_micro * 32 + kBlockThreads - 1) / kBlockThreads;
+    int64_t grid = (L.num_micro * 32 + kBlockThreads - 1) / kBlockThreads;
     if (grid <= 0) return cudaSuccess;
-    if (grid > 0x7fffffffLL) return cudaErrorInvalidValue;
+    if (grid > 0x7fffffffLL) grid = 0x7fffffffLL;   // clipped to the resident CTA count at launch
     for (int b = 0; b < L.num_blocks; b++) {
         const int mode = (b == 0 && !beta) ? 0 : 1;
         cudaError_t e;
