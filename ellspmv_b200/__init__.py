@@ -25,6 +25,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libellspmv_cuda.so")
 
 # ---- constants (include/ellspmv_cuda.h) -----------------------------------
 KERNEL_AUTO, KERNEL_THREAD, KERNEL_WARP = 0, 1, 2
+KERNEL_CSR_SCALAR = 3   # CSR only: thread-per-row, bit-exact, for balanced rows (auto picks it)
 FMA = 1 << 4
 L2_PERSIST_X = 1 << 5
 NARROW_INDEX = 1 << 6

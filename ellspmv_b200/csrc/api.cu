@@ -745,7 +745,10 @@ static int csr_new(csrspmv_cuda_matrix **out, int idx_width_bits, int64_t num_ro
     A->flags = flags;
     A->fma = (flags & ELLSPMV_CUDA_FMA) != 0;
     int kernel = flags & ELLSPMV_CUDA_KERNEL_MASK;
-    A->kernel = kernel == ELLSPMV_CUDA_KERNEL_WARP ? ELLSPMV_CUDA_KERNEL_WARP : ELLSPMV_CUDA_KERNEL_THREAD;
+    // 0 = auto: bit-exact, scalar for balanced rows / stream for ragged ones (csr_pick_kernel);
+    // 1 = stream, 2 = vector (tolerance), 3 = scalar
+    A->auto_kernel = kernel == ELLSPMV_CUDA_KERNEL_AUTO;
+    A->kernel = kernel == ELLSPMV_CUDA_KERNEL_WARP ? ELLSPMV_CUDA_KERNEL_WARP : (kernel == 3 ? 3 : ELLSPMV_CUDA_KERNEL_THREAD);
     *out = A;
     DeviceGuard g(device);
     auto fail = [&](cudaError_t ce) {
@@ -761,6 +764,17 @@ static int csr_new(csrspmv_cuda_matrix **out, int idx_width_bits, int64_t num_ro
     if ((ce = cudaMalloc(&A->d_y, (size_t)(num_rows > 0 ? num_rows : 1) * 8)) != cudaSuccess) return fail(ce);
     if ((ce = cudaStreamCreateWithFlags(&A->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(ce);
     A->device_bytes = (num_rows + 1) * 8 + (int64_t)nz * (8 + idx_width_bits / 8) + (num_columns + num_rows) * 8;
+    return 0;
+}
+
+// bit-exact CSR kernels: thread-per-row (scalar) wins when the rows are balanced
+// (37 vs 48 ms on BASELINE config 4), the smem-staged stream kernel when they are ragged
+static int csr_pick_kernel(csrspmv_cuda_matrix *A)
+{
+    ELL_CK(csr_max_row_len(A->rowptr, A->num_rows, &A->max_row_len, A->stream));
+    if (!A->auto_kernel) return 0;
+    const int64_t avg = A->num_rows > 0 ? (A->csrsize + A->num_rows - 1) / A->num_rows : 0;
+    A->kernel = (A->max_row_len <= 4 * avg + 16) ? 3 : ELLSPMV_CUDA_KERNEL_THREAD;
     return 0;
 }
 
@@ -792,6 +806,7 @@ int csrspmv_cuda_upload(
         csrspmv_cuda_free(A); *out = nullptr;
         return cuda_to_errno(ce);
     }
+    if ((err = csr_pick_kernel(A))) { csrspmv_cuda_free(A); *out = nullptr; return err; }
     return 0;
 }
 
@@ -828,6 +843,7 @@ int csrspmv_cuda_upload_coo(
         csrspmv_cuda_free(A); *out = nullptr;
         return ce != cudaSuccess ? cuda_to_errno(ce) : EINVAL;
     }
+    if ((err = csr_pick_kernel(A))) { csrspmv_cuda_free(A); *out = nullptr; return err; }
     return 0;
 }
 
@@ -851,6 +867,7 @@ int csrspmv_cuda_generate(
         csrspmv_cuda_free(A); *out = nullptr;
         return cuda_to_errno(ce);
     }
+    if ((err = csr_pick_kernel(A))) { csrspmv_cuda_free(A); *out = nullptr; return err; }
     return 0;
 }
 

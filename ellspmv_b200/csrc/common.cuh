@@ -114,6 +114,7 @@ struct CsrSpmvArgs {
 };
 cudaError_t launch_csr_spmv(int idx_bits, bool fma, int kernel, const CsrSpmvArgs &args,
                             cudaStream_t stream);
+cudaError_t csr_max_row_len(const int64_t *rowptr, int64_t num_rows, int64_t *max_len, cudaStream_t stream);
 
 // ---- layout / generators (layout.cu) -------------------------------------
 // row-major chunk (rows [row0, row0+rows) of the shard) -> sliced layout

@@ -87,6 +87,43 @@ csr_stream_kernel(const CsrSpmvArgs a)
     }
 }
 
+// csr_scalar_kernel (bit-exact): one thread per row walking its entries in
+// order.  The loads are not coalesced (neighbouring threads are a row apart),
+// but every 32-byte sector a thread touches is used again by its next
+// iterations and L1/L2 keep it, so for rows of similar length the DRAM
+// traffic is the same as the stream kernel's without its two CTA barriers per
+// tile.  Used when the rows are balanced; ragged matrices take the stream kernel.
+template <typename IdxT, bool FMA>
+__global__ void __launch_bounds__(kBlockThreads)
+csr_scalar_kernel(const CsrSpmvArgs a)
+{
+    const IdxT *__restrict__ cols = reinterpret_cast<const IdxT *>(a.cols);
+    const double *__restrict__ vals = a.vals;
+    const double *__restrict__ x = a.x;
+    const int64_t row = (int64_t)blockIdx.x * kBlockThreads + threadIdx.x;
+    if (row >= a.num_rows) return;
+    const int64_t b = a.rowptr[row], e = a.rowptr[row + 1];
+    const double yold = a.beta ? a.y[row] : 0.0;
+    double acc = 0.0;
+    int64_t k = b;
+    for (; k + 8 <= e; k += 8) {
+        double v[8], xv[8]; int64_t c[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) { v[u] = __ldg(vals + k + u); c[u] = (int64_t)__ldg(cols + k + u); }
+#pragma unroll
+        for (int u = 0; u < 8; u++) xv[u] = __ldg(x + c[u]);
+#pragma unroll
+        for (int u = 0; u < 8; u++) acc = FMA ? __fma_rn(v[u], xv[u], acc) : __dadd_rn(acc, __dmul_rn(v[u], xv[u]));
+    }
+    for (; k < e; k++) {
+        const double v = __ldg(vals + k);
+        const double xv = __ldg(x + (int64_t)__ldg(cols + k));
+        acc = FMA ? __fma_rn(v, xv, acc) : __dadd_rn(acc, __dmul_rn(v, xv));
+    }
+    if (a.ad) acc = __dadd_rn(__dmul_rn(a.ad[row], __ldg(x + row)), acc);
+    a.y[row] = __dadd_rn(yold, acc);
+}
+
 // T lanes per row, entries strided by T, shuffle-xor reduction
 template <typename IdxT, int T, bool FMA>
 __global__ void __launch_bounds__(kBlockThreads)
@@ -117,6 +154,40 @@ csr_vector_kernel(const CsrSpmvArgs a)
     }
 }
 
+__global__ void csr_max_row_kernel(const int64_t *__restrict__ rowptr, int64_t num_rows, unsigned long long *out)
+{
+    unsigned long long best = 0;
+    for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < num_rows; r += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned long long n = (unsigned long long)(rowptr[r + 1] - rowptr[r]);
+        best = n > best ? n : best;
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        const unsigned long long o = __shfl_xor_sync(0xffffffffu, best, off);
+        best = o > best ? o : best;
+    }
+    if ((threadIdx.x & 31) == 0) atomicMax(out, best);
+}
+
+// longest row of a device CSR matrix (for choosing between the scalar and the stream kernel)
+cudaError_t csr_max_row_len(const int64_t *rowptr, int64_t num_rows, int64_t *max_len, cudaStream_t stream)
+{
+    *max_len = 0;
+    if (num_rows <= 0) return cudaSuccess;
+    unsigned long long *d = nullptr;
+    cudaError_t e = cudaMalloc(&d, 8);
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(d, 0, 8, stream);
+    int64_t g = (num_rows + 255) / 256;
+    if (g > 148 * 16) g = 148 * 16;
+    if (e == cudaSuccess) { csr_max_row_kernel<<<(unsigned)g, 256, 0, stream>>>(rowptr, num_rows, d); e = cudaGetLastError(); }
+    unsigned long long h = 0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&h, d, 8, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    cudaFree(d);
+    *max_len = (int64_t)h;
+    return e;
+}
+
 template <typename IdxT, bool FMA>
 static cudaError_t launch_csr_typed(int kernel, const CsrSpmvArgs &args, cudaStream_t stream)
 {
@@ -127,6 +198,10 @@ static cudaError_t launch_csr_typed(int kernel, const CsrSpmvArgs &args, cudaStr
         const int64_t g = (threads + kBlockThreads - 1) / kBlockThreads;
         if (g > 0x7fffffffLL) return cudaErrorInvalidValue;
         csr_vector_kernel<IdxT, T, FMA><<<(unsigned)g, kBlockThreads, 0, stream>>>(args);
+    } else if (kernel == 3) {
+        const int64_t g = (args.num_rows + kBlockThreads - 1) / kBlockThreads;
+        if (g > 0x7fffffffLL) return cudaErrorInvalidValue;
+        csr_scalar_kernel<IdxT, FMA><<<(unsigned)g, kBlockThreads, 0, stream>>>(args);
     } else {
         const int64_t g = (args.num_rows + kCsrRowsPerCta - 1) / kCsrRowsPerCta;
         if (g > 0x7fffffffLL) return cudaErrorInvalidValue;

@@ -57,7 +57,9 @@ struct csrspmv_cuda_matrix {
     int idx_bits = 32;
     int64_t num_rows = 0, num_columns = 0, csrsize = 0;
     unsigned flags = 0;
-    int kernel = ELLSPMV_CUDA_KERNEL_THREAD;
+    int kernel = ELLSPMV_CUDA_KERNEL_THREAD;   // 1 stream, 2 vector, 3 scalar (see csr_kernels.cu)
+    bool auto_kernel = true;                   // pick scalar vs stream from the row lengths
+    int64_t max_row_len = 0;
     bool fma = false;
     int64_t *rowptr = nullptr;
     void *cols = nullptr;

@@ -46,6 +46,9 @@ enum {
                                     /*   bit-exact with the reference loop      */
     ELLSPMV_CUDA_KERNEL_WARP   = 2, /* sub-warp-per-row + shuffle reduction:    */
                                     /*   tolerance mode (summation order differs)*/
+    CSRSPMV_CUDA_KERNEL_SCALAR = 3, /* CSR only: thread-per-row, bit-exact; AUTO picks it  */
+                                    /*   for balanced rows, the smem-staged stream kernel  */
+                                    /*   (KERNEL_THREAD) for ragged ones                   */
     ELLSPMV_CUDA_KERNEL_MASK   = 0xf,
     /* arithmetic: default is mul-then-add (__dmul_rn/__dadd_rn), the bits the
      * reference's compiled loop produces; FMA allows contraction (tolerance) */

@@ -46,15 +46,16 @@ def test_bit_exact_vs_oracle(lib, oracle, shape, bits):
     y0 = rng.standard_normal(nr)
     want = y0.copy()
     oracle.csrgemv(nr, want, x, rowptr, cc, ca)
-    A = E.CsrMatrix.upload(nr, nc, rowptr, cc, ca)
-    y = y0.copy()
-    A.spmv(y, x, 1, E.ACCUMULATE)
-    assert bits_equal(y, want)
     want0 = np.zeros(nr)
     oracle.csrgemv(nr, want0, x, rowptr, cc, ca)
-    A.spmv(y, x, 2, E.OVERWRITE)
-    assert bits_equal(y, want0)
-    A.free()
+    for kflag in (0, E.KERNEL_THREAD, 3):     # auto / smem-staged stream / thread-per-row scalar: all bit-exact
+        A = E.CsrMatrix.upload(nr, nc, rowptr, cc, ca, kflag)
+        y = y0.copy()
+        A.spmv(y, x, 1, E.ACCUMULATE)
+        assert bits_equal(y, want), kflag
+        A.spmv(y, x, 2, E.OVERWRITE)
+        assert bits_equal(y, want0), kflag
+        A.free()
     # tolerance modes
     absprod = np.zeros(nr)
     np.add.at(absprod, np.repeat(np.arange(nr), np.diff(rowptr)), np.abs(ca * x[cc]))

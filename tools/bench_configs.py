@@ -94,7 +94,7 @@ def main():
             A.free()
             del x, y
         if name == "c4" and not args.no_csr:
-            for vname, flags in (("csr stream (bit-exact)", E.KERNEL_THREAD), ("csr vector T=8", E.KERNEL_WARP)):
+            for vname, flags in (("csr stream (bit-exact)", E.KERNEL_THREAD), ("csr scalar (bit-exact)", 3), ("csr vector T=8", E.KERNEL_WARP)):
                 Cm = E.CsrMatrix.generate(E.GEN_RANDOM, dims, 42, bits, flags=flags)
                 rows, ncols, K = dims
                 gen = torch.Generator(device="cuda").manual_seed(1)
