@@ -380,6 +380,9 @@ template <typename IdxT, bool FMA>
 static cudaError_t launch_subwarp(const EllSpmvArgs &args, int slice_rows, cudaLaunchConfig_t &lc)
 {
     const int K = args.rowsize;
+    // lanes per row grow with the row length: about 6..12 slots per lane
+    if (K >= 192) return cudaLaunchKernelEx(&lc, ell_subwarp_kernel<IdxT, 32, FMA>, args, slice_rows);
+    if (K >= 96) return cudaLaunchKernelEx(&lc, ell_subwarp_kernel<IdxT, 16, FMA>, args, slice_rows);
     if (K >= 24) return cudaLaunchKernelEx(&lc, ell_subwarp_kernel<IdxT, 8, FMA>, args, slice_rows);
     if (K >= 12) return cudaLaunchKernelEx(&lc, ell_subwarp_kernel<IdxT, 4, FMA>, args, slice_rows);
     return cudaLaunchKernelEx(&lc, ell_subwarp_kernel<IdxT, 2, FMA>, args, slice_rows);
