@@ -282,11 +282,12 @@ class CsrMatrix:
         self._h = C.c_void_p(handle)
 
     @classmethod
-    def upload(cls, num_rows: int, num_columns: int, rowptr, colidx, a, flags: int = 0) -> "CsrMatrix":
+    def upload(cls, num_rows: int, num_columns: int, rowptr, colidx, a, flags: int = 0,
+               num_gpus: int = 1) -> "CsrMatrix":
         h = C.c_void_p()
         bits = _idx_bits(colidx) if colidx is not None else 32
         err = load_library().csrspmv_cuda_upload(C.byref(h), bits, num_rows, num_columns, _ptr(rowptr),
-                                                 _ptr(colidx), _ptr(a), 1, flags)
+                                                 _ptr(colidx), _ptr(a), num_gpus, flags)
         _check(err, "csrspmv_cuda_upload")
         return cls(h.value)
 

@@ -713,6 +713,7 @@ int ellspmv_cuda_spmv(
 void csrspmv_cuda_free(csrspmv_cuda_matrix *A)
 {
     if (!A) return;
+    if (!A->shards.empty()) { csr_group_free(A); return; }
     DeviceGuard g(A->device);
     if (A->stream) cudaStreamSynchronize(A->stream);
     for (cudaEvent_t e : A->events) cudaEventDestroy(e);
@@ -784,30 +785,10 @@ int csrspmv_cuda_upload(
     const int64_t *rowptr, const void *colidx, const double *a,
     int num_gpus, unsigned flags)
 {
-    if (num_gpus != 1) ELL_FAIL(ENOTSUP, "csrspmv_cuda_upload: num_gpus must be 1");
-    if (!rowptr) ELL_FAIL(EINVAL, "rowptr is NULL");
-    int dev = -1;
-    int err = check_device(&dev);
-    if (err) return err;
-    // rowptr may live on the host or the device: fetch the last entry portably
-    int64_t csrsize = 0;
-    ELL_CK(cudaMemcpy(&csrsize, rowptr + num_rows, 8, cudaMemcpyDefault));
-    if (csrsize > 0 && (!colidx || !a)) ELL_FAIL(EINVAL, "colidx or a is NULL");
-    err = csr_new(out, idx_width_bits, num_rows, num_columns, csrsize, dev, flags);
-    if (err) return err;
-    csrspmv_cuda_matrix *A = *out;
-    DeviceGuard g(A->device);
-    cudaError_t ce = cudaMemcpyAsync(A->rowptr, rowptr, (size_t)(num_rows + 1) * 8, cudaMemcpyDefault, A->stream);
-    if (ce == cudaSuccess && csrsize > 0) ce = cudaMemcpyAsync(A->cols, colidx, (size_t)csrsize * (idx_width_bits / 8), cudaMemcpyDefault, A->stream);
-    if (ce == cudaSuccess && csrsize > 0) ce = cudaMemcpyAsync(A->vals, a, (size_t)csrsize * 8, cudaMemcpyDefault, A->stream);
-    if (ce == cudaSuccess) ce = cudaStreamSynchronize(A->stream);
-    if (ce != cudaSuccess) {
-        set_last_error("csr upload: %s", cudaGetErrorString(ce));
-        csrspmv_cuda_free(A); *out = nullptr;
-        return cuda_to_errno(ce);
-    }
-    if ((err = csr_pick_kernel(A))) { csrspmv_cuda_free(A); *out = nullptr; return err; }
-    return 0;
+    if (num_gpus < 1) ELL_FAIL(EINVAL, "num_gpus must be >= 1");
+    if (num_gpus > 1)
+        return csr_group_upload(out, idx_width_bits, num_rows, num_columns, rowptr, colidx, a, num_gpus, flags);
+    return csr_upload_on(out, idx_width_bits, num_rows, num_columns, rowptr, colidx, a, -1, flags);
 }
 
 int csrspmv_cuda_upload_coo(
@@ -874,6 +855,13 @@ int csrspmv_cuda_generate(
 int csrspmv_cuda_set_diagonal(csrspmv_cuda_matrix *A, const double *ad)
 {
     if (!A) ELL_FAIL(EINVAL, "matrix is NULL");
+    if (!A->shards.empty()) {
+        for (size_t p = 0; p < A->shards.size(); p++) {
+            int err = csrspmv_cuda_set_diagonal(A->shards[p], ad ? ad + A->row_lo[p] : nullptr);
+            if (err) return err;
+        }
+        return 0;
+    }
     DeviceGuard g(A->device);
     if (!ad) {
         if (A->d_ad) { cudaFree(A->d_ad); A->d_ad = nullptr; }
@@ -896,6 +884,7 @@ int csrspmv_cuda_spmv_device(
     csrspmv_cuda_matrix *A, double *y_dev, const double *x_dev, int mode, void *stream)
 {
     if (!A) ELL_FAIL(EINVAL, "matrix is NULL");
+    if (!A->shards.empty()) ELL_FAIL(EINVAL, "spmv_device needs a single-GPU handle");
     if (mode != ELLSPMV_CUDA_ACCUMULATE && mode != ELLSPMV_CUDA_OVERWRITE)
         ELL_FAIL(EINVAL, "mode must be ACCUMULATE or OVERWRITE");
     if (A->num_rows > 0 && (!y_dev || !x_dev)) ELL_FAIL(EINVAL, "NULL device vector");
@@ -916,6 +905,7 @@ int csrspmv_cuda_spmv(
         ELL_FAIL(EINVAL, "mode must be ACCUMULATE or OVERWRITE");
     if ((A->num_rows > 0 && !y) || (A->num_columns > 0 && !x)) ELL_FAIL(EINVAL, "NULL host vector");
     if (repeat == 0) return 0;
+    if (!A->shards.empty()) return csr_group_spmv(A, y, x, repeat, mode, seconds);
     DeviceGuard g(A->device);
     int err = ensure_events(A->events, (size_t)repeat + 1);
     if (err) return err;
@@ -945,6 +935,7 @@ int csrspmv_cuda_spmv(
 int csrspmv_cuda_download(const csrspmv_cuda_matrix *A, int64_t *rowptr, void *colidx, double *a)
 {
     if (!A) ELL_FAIL(EINVAL, "matrix is NULL");
+    if (!A->shards.empty()) ELL_FAIL(ENOTSUP, "download needs a single-GPU handle");
     if (!rowptr) ELL_FAIL(EINVAL, "rowptr is NULL");
     DeviceGuard g(A->device);
     ELL_CK(cudaMemcpy(rowptr, A->rowptr, (size_t)(A->num_rows + 1) * 8, cudaMemcpyDefault));
@@ -1029,3 +1020,51 @@ int ellspmv_cuda_ipc_close(void *dev_ptr)
 }
 
 }  // extern "C"
+
+namespace ellspmv {
+
+// rowptr[0] may be non-zero (a row block of a larger matrix): it is rebased on the device
+static __global__ void rebase_rowptr_kernel(int64_t *rowptr, int64_t n, int64_t base)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        rowptr[i] -= base;
+}
+
+int csr_upload_on(csrspmv_cuda_matrix **out, int idx_width_bits, int64_t num_rows, int64_t num_columns,
+                  const int64_t *rowptr, const void *colidx, const double *a, int device, unsigned flags)
+{
+    if (!rowptr) ELL_FAIL(EINVAL, "rowptr is NULL");
+    int err = check_device(&device);
+    if (err) return err;
+    // rowptr may live on the host or the device: fetch both ends portably
+    int64_t first = 0, last = 0;
+    ELL_CK(cudaMemcpy(&first, rowptr, 8, cudaMemcpyDefault));
+    ELL_CK(cudaMemcpy(&last, rowptr + num_rows, 8, cudaMemcpyDefault));
+    const int64_t csrsize = last - first;
+    if (csrsize < 0) ELL_FAIL(EINVAL, "rowptr is not increasing");
+    if (csrsize > 0 && (!colidx || !a)) ELL_FAIL(EINVAL, "colidx or a is NULL");
+    err = csr_new(out, idx_width_bits, num_rows, num_columns, csrsize, device, flags);
+    if (err) return err;
+    csrspmv_cuda_matrix *A = *out;
+    DeviceGuard g(A->device);
+    const size_t ib = (size_t)idx_width_bits / 8;
+    cudaError_t ce = cudaMemcpyAsync(A->rowptr, rowptr, (size_t)(num_rows + 1) * 8, cudaMemcpyDefault, A->stream);
+    if (ce == cudaSuccess && first != 0) {
+        rebase_rowptr_kernel<<<64, 256, 0, A->stream>>>(A->rowptr, num_rows + 1, first);
+        ce = cudaGetLastError();
+    }
+    if (ce == cudaSuccess && csrsize > 0)
+        ce = cudaMemcpyAsync(A->cols, (const char *)colidx + (size_t)first * ib, (size_t)csrsize * ib, cudaMemcpyDefault, A->stream);
+    if (ce == cudaSuccess && csrsize > 0)
+        ce = cudaMemcpyAsync(A->vals, a + first, (size_t)csrsize * 8, cudaMemcpyDefault, A->stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(A->stream);
+    if (ce != cudaSuccess) {
+        set_last_error("csr upload: %s", cudaGetErrorString(ce));
+        csrspmv_cuda_free(A); *out = nullptr;
+        return cuda_to_errno(ce);
+    }
+    if ((err = csr_pick_kernel(A))) { csrspmv_cuda_free(A); *out = nullptr; return err; }
+    return 0;
+}
+
+}  // namespace ellspmv

@@ -339,4 +339,111 @@ int group_spmv(ellspmv_cuda_matrix *G, double *y, const double *x, int repeat, i
     return 0;
 }
 
+// ---- CSR over several GPUs (comparison path) ---------------------------------------
+// Contiguous row blocks balanced by entries, the reference's --partition-nonzeros
+// rule (csrspmv.c:1700-1708: start = p * ceil(nnz / T)), rounded to row boundaries.
+// x is constant in the reference's loop, so the shards are independent.
+
+void csr_group_free(csrspmv_cuda_matrix *G)
+{
+    if (!G) return;
+    std::vector<csrspmv_cuda_matrix *> shards;
+    shards.swap(G->shards);
+    for (csrspmv_cuda_matrix *S : shards) csrspmv_cuda_free(S);
+    delete G;
+}
+
+int csr_group_upload(csrspmv_cuda_matrix **out, int idx_width_bits, int64_t num_rows, int64_t num_columns,
+                     const int64_t *rowptr, const void *colidx, const double *a, int num_gpus, unsigned flags)
+{
+    if (!out) ELL_FAIL(EINVAL, "out is NULL");
+    *out = nullptr;
+    if (!rowptr) ELL_FAIL(EINVAL, "rowptr is NULL");
+    if (num_rows < 0 || num_columns < 0) ELL_FAIL(EINVAL, "negative dimension");
+    int count = 0;
+    ELL_CK(cudaGetDeviceCount(&count));
+    if (num_gpus > count) ELL_FAIL(ENODEV, "num_gpus=%d but only %d CUDA device(s) are visible", num_gpus, count);
+    // the partition needs rowptr on the host
+    std::vector<int64_t> rp((size_t)num_rows + 1);
+    ELL_CK(cudaMemcpy(rp.data(), rowptr, (size_t)(num_rows + 1) * 8, cudaMemcpyDefault));
+    const int64_t nnz = rp[num_rows] - rp[0];
+    const int64_t per = (nnz + num_gpus - 1) / num_gpus;
+    csrspmv_cuda_matrix *G = new (std::nothrow) csrspmv_cuda_matrix();
+    if (!G) ELL_FAIL(ENOMEM, "out of host memory");
+    G->idx_bits = idx_width_bits;
+    G->num_rows = num_rows;
+    G->num_columns = num_columns;
+    G->csrsize = nnz;
+    G->flags = flags;
+    G->row_lo.assign((size_t)num_gpus + 1, num_rows);
+    int64_t r = 0;
+    for (int p = 0; p < num_gpus; p++) {
+        const int64_t startnz = rp[0] + (int64_t)p * per;
+        while (r < num_rows && rp[r] < startnz) r++;          // first row that starts at or after the cut
+        G->row_lo[p] = p == 0 ? 0 : r;
+    }
+    int prev = -1;
+    cudaGetDevice(&prev);
+    int err = 0;
+    const int64_t ib = idx_width_bits / 8;
+    (void)ib;
+    for (int p = 0; p < num_gpus && !err; p++) {
+        const int64_t lo = G->row_lo[p], hi = G->row_lo[p + 1];
+        csrspmv_cuda_matrix *S = nullptr;
+        // the shard keeps the parent's entry offsets; csr_upload_on rebases rowptr and slices colidx / a
+        err = csr_upload_on(&S, idx_width_bits, hi - lo, num_columns, rowptr + lo, colidx, a, p, flags);
+        if (!err) { G->shards.push_back(S); G->device_bytes += S->device_bytes; }
+    }
+    if (prev >= 0) cudaSetDevice(prev);
+    if (err) { csr_group_free(G); return err; }
+    *out = G;
+    return 0;
+}
+
+int csr_group_spmv(csrspmv_cuda_matrix *G, double *y, const double *x, int repeat, int mode, double *seconds)
+{
+    const int n = (int)G->shards.size();
+    int prev = -1;
+    cudaGetDevice(&prev);
+    struct Restore { int d; ~Restore() { if (d >= 0) cudaSetDevice(d); } } restore{prev};
+    std::vector<std::vector<double>> secs((size_t)n, std::vector<double>((size_t)repeat, 0.0));
+    // every shard owns its x copy and y slice: issue everything asynchronously, then wait
+    for (int p = 0; p < n; p++) {
+        csrspmv_cuda_matrix *S = G->shards[p];
+        ELL_CK(cudaSetDevice(p));
+        int err = ensure_event_count(S->events, (size_t)repeat + 1);
+        if (err) return err;
+        cudaStream_t s = S->stream;
+        if (S->num_columns > 0) ELL_CK(cudaMemcpyAsync(S->d_x, x, (size_t)S->num_columns * 8, cudaMemcpyDefault, s));
+        if (mode == ELLSPMV_CUDA_ACCUMULATE && S->num_rows > 0)
+            ELL_CK(cudaMemcpyAsync(S->d_y, y + G->row_lo[p], (size_t)S->num_rows * 8, cudaMemcpyDefault, s));
+        ELL_CK(cudaEventRecord(S->events[0], s));
+        for (int r = 0; r < repeat; r++) {
+            CsrSpmvArgs args = {S->rowptr, S->cols, S->vals, S->d_x, S->d_y, S->num_rows,
+                                mode == ELLSPMV_CUDA_ACCUMULATE ? 1 : 0, S->d_ad};
+            ELL_CK(launch_csr_spmv(S->idx_bits, S->fma, S->kernel, args, s));
+            ELL_CK(cudaEventRecord(S->events[(size_t)r + 1], s));
+        }
+        if (S->num_rows > 0)
+            ELL_CK(cudaMemcpyAsync(y + G->row_lo[p], S->d_y, (size_t)S->num_rows * 8, cudaMemcpyDefault, s));
+    }
+    for (int p = 0; p < n; p++) {
+        csrspmv_cuda_matrix *S = G->shards[p];
+        ELL_CK(cudaSetDevice(p));
+        ELL_CK(cudaStreamSynchronize(S->stream));
+        for (int r = 0; r < repeat; r++) {
+            float ms = 0.f;
+            ELL_CK(cudaEventElapsedTime(&ms, S->events[(size_t)r], S->events[(size_t)r + 1]));
+            secs[(size_t)p][(size_t)r] = ms * 1e-3;
+        }
+    }
+    if (seconds)
+        for (int r = 0; r < repeat; r++) {
+            double worst = 0.0;
+            for (int p = 0; p < n; p++) if (secs[(size_t)p][(size_t)r] > worst) worst = secs[(size_t)p][(size_t)r];
+            seconds[r] = worst;
+        }
+    return 0;
+}
+
 }  // namespace ellspmv

@@ -69,6 +69,10 @@ struct csrspmv_cuda_matrix {
     double *d_ad = nullptr;                  // separately stored diagonal, optional
     std::vector<cudaEvent_t> events;
     int64_t device_bytes = 0;
+
+    // ---- group handle (num_gpus > 1): nnz-balanced contiguous row blocks, one per GPU ----
+    std::vector<csrspmv_cuda_matrix *> shards;
+    std::vector<int64_t> row_lo;             // first row of every shard (+ num_rows at the end)
 };
 
 
@@ -82,6 +86,12 @@ int group_spmv(ellspmv_cuda_matrix *G, double *y, const double *x, int repeat, i
 int group_download(const ellspmv_cuda_matrix *G, void *colidx, double *a);
 int group_info(const ellspmv_cuda_matrix *G, ellspmv_cuda_info *info);
 void group_free(ellspmv_cuda_matrix *G);
+int csr_group_upload(csrspmv_cuda_matrix **out, int idx_width_bits, int64_t num_rows, int64_t num_columns,
+                     const int64_t *rowptr, const void *colidx, const double *a, int num_gpus, unsigned flags);
+int csr_group_spmv(csrspmv_cuda_matrix *G, double *y, const double *x, int repeat, int mode, double *seconds);
+void csr_group_free(csrspmv_cuda_matrix *G);
+int csr_upload_on(csrspmv_cuda_matrix **out, int idx_width_bits, int64_t num_rows, int64_t num_columns,
+                  const int64_t *rowptr, const void *colidx, const double *a, int device, unsigned flags);
 // api.cu internals the group needs
 int launch_shard(ellspmv_cuda_matrix *A, double *y_dev, const double *x_dev, int beta,
                  const PushTargets *push, cudaStream_t stream);

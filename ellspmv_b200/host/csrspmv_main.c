@@ -38,7 +38,7 @@ struct options {
     const char *Apath, *xpath, *ypath;
     int gzip;
     bool separate_diagonal, sort_rows, ignored_partition, device_convert;
-    int repeat, warmup, verbose, quiet;
+    int repeat, warmup, verbose, quiet, gpus;
     unsigned flags;
 };
 
@@ -75,6 +75,7 @@ static void help(FILE *f)
     fprintf(f, "  --kernel=thread|warp      row-block streaming (bit-exact, default) or sub-warp-per-row\n");
     fprintf(f, "  --fma                     allow fused multiply-add (tolerance mode)\n");
     fprintf(f, "  --device-convert          convert COO to CSR on the device (general matrices)\n");
+    fprintf(f, "  --gpus=N                  split the rows in N nonzero-balanced blocks over devices 0..N-1 [1]\n");
     fprintf(f, "\n");
     fprintf(f, "  -h, --help                display this help and exit\n");
     fprintf(f, "  --version                 display version information and exit\n");
@@ -84,6 +85,7 @@ static int parse_options(int argc, char **argv, struct options *o, int *bad)
 {
     memset(o, 0, sizeof(*o));
     o->repeat = 1;
+    o->gpus = 1;
     int npos = 0;
     bool only_positional = false;
     for (int i = 1; i < argc; i++) {
@@ -130,6 +132,10 @@ static int parse_options(int argc, char **argv, struct options *o, int *bad)
             }
             if (!strcmp(a, "--fma")) { o->flags |= ELLSPMV_CUDA_FMA; continue; }
             if (!strcmp(a, "--device-convert")) { o->device_convert = true; continue; }
+            if (!strncmp(a, "--gpus", 6) && (a[6] == '=' || a[6] == '\0')) {
+                if (!(v = optval(argc, argv, &i, "--gpus")) || to_int(v, &o->gpus) || o->gpus < 1) return EINVAL;
+                continue;
+            }
             if (!strcmp(a, "-h") || !strcmp(a, "--help")) { help(stdout); exit(EXIT_SUCCESS); }
             if (!strcmp(a, "--version")) {
                 printf("%s %s\nrow/column offsets: %d-bit\n", prog, version, IDX_BITS);
@@ -208,7 +214,7 @@ int main(int argc, char *argv[])
     }
     csrspmv_cuda_matrix *A = NULL;
     int64_t csrsize, diagsize = 0;
-    if (o.device_convert && !o.separate_diagonal && !o.sort_rows && h.symmetry == MTX_GENERAL) {
+    if (o.device_convert && !o.separate_diagonal && !o.sort_rows && h.symmetry == MTX_GENERAL && o.gpus == 1) {
         /* stable sort by row on the device; rowsizemin/max are only printed, count them here */
         int64_t *cnt = calloc((size_t)num_rows + 1, sizeof(*cnt));
         if (!cnt) { fprintf(stderr, "%s: %s\n", prog, strerror(ENOMEM)); return EXIT_FAILURE; }
@@ -250,7 +256,7 @@ int main(int argc, char *argv[])
                     seconds_between(t0, t1), num_rows, num_columns, csrsize + diagsize, csr.rowsizemin, csr.rowsizemax);
         }
         if (o.verbose > 0) { fprintf(stderr, "cuda_upload: "); clock_gettime(CLOCK_MONOTONIC, &t0); }
-        err = csrspmv_cuda_upload(&A, IDX_BITS, num_rows, num_columns, csr.rowptr, csr.colidx, csr.a, 1, o.flags);
+        err = csrspmv_cuda_upload(&A, IDX_BITS, num_rows, num_columns, csr.rowptr, csr.colidx, csr.a, o.gpus, o.flags);
         if (!err && csr.ad) err = csrspmv_cuda_set_diagonal(A, csr.ad);
         csr_free(&csr);
         if (err) {

@@ -82,3 +82,36 @@ def test_host_program_gpus_option(tmp_path, oracle):
                         "--iterate", "--repeat=5"], capture_output=True, text=True, env=env)
     assert r.returncode == 0, r.stderr
     assert r.stdout.splitlines()[2:] == ["%.15g" % v for v in want]
+
+
+def test_csr_group(lib, oracle, tmp_path):
+    """CSR over several GPUs: nonzero-balanced contiguous row blocks (csrspmv.c:1700-1708)."""
+    n = ngpus()
+    rng = np.random.default_rng(8)
+    nr, nc = 20011, 15000
+    lens = rng.integers(0, 30, nr)
+    lens[:50] = 4000                                    # a heavy head: the balanced cut is far from nr/n
+    rowptr = np.zeros(nr + 1, dtype=np.int64)
+    np.cumsum(lens, out=rowptr[1:])
+    nnz = int(rowptr[-1])
+    for dt in (np.int32, np.int64):
+        cc = rng.integers(0, nc, nnz).astype(dt)
+        ca = rng.standard_normal(nnz)
+        x = rng.standard_normal(nc)
+        y0 = rng.standard_normal(nr)
+        want = y0.copy()
+        for _ in range(2):
+            oracle.csrgemv(nr, want, x, rowptr, cc, ca)
+        for flags in (0, E.KERNEL_THREAD, 3):
+            A = E.CsrMatrix.upload(nr, nc, rowptr, cc, ca, flags, num_gpus=n)
+            y = y0.copy()
+            secs = A.spmv(y, x, 2, E.ACCUMULATE)
+            assert bits_equal(y, want) and np.all(secs > 0)
+            A.free()
+    hostlib.build_host()
+    g = load_golden("rand_square")
+    p = str(tmp_path / "A.mtx")
+    hostlib.write_mtx(p, g["num_rows"], g["num_columns"], g["rowidx"], g["colidx"], unhex(g["a"]), comments=())
+    r = subprocess.run([os.path.join(hostlib.BIN, "csrspmv"), f"--gpus={n}", p], capture_output=True, text=True,
+                       env=dict(os.environ, LC_ALL="C"))
+    assert r.returncode == 0 and r.stdout == g["program"]["csrspmv"]["stdout"]
