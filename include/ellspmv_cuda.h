@@ -226,7 +226,10 @@ void ellspmv_cuda_free(ellspmv_cuda_matrix *A);
 /* ---- CSR (comparison path) ------------------------------------------- */
 
 /* rowptr: num_rows+1 int64 (always 64-bit in the reference, csrspmv.c:1573);
- * colidx: csrsize idx_t, 0-based; a: csrsize doubles. */
+ * colidx: csrsize idx_t, 0-based; a: csrsize doubles.
+ * num_gpus > 1: contiguous row blocks balanced by entries (the reference's
+ * --partition-nonzeros rule, csrspmv.c:1700-1708, rounded to row boundaries)
+ * over devices 0..N-1; csrspmv_cuda_spmv then drives all of them. */
 int csrspmv_cuda_upload(
     csrspmv_cuda_matrix **out, int idx_width_bits,
     int64_t num_rows, int64_t num_columns,
