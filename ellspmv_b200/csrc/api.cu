@@ -79,8 +79,8 @@ int configure(ellspmv_cuda_matrix *A, unsigned flags)
     if (kernel != ELLSPMV_CUDA_KERNEL_THREAD && kernel != ELLSPMV_CUDA_KERNEL_WARP)
         ELL_FAIL(EINVAL, "unknown kernel selector %d", kernel);
     A->dev_idx_bits = A->host_idx_bits;
-    if (A->host_idx_bits == 64 && (flags & ELLSPMV_CUDA_NARROW_INDEX) && A->num_columns < (1LL << 31))
-        A->dev_idx_bits = 32;
+    if (A->host_idx_bits == 64 && !(flags & ELLSPMV_CUDA_WIDE_INDEX) && A->num_columns < (1LL << 31))
+        A->dev_idx_bits = 32;     // index narrowing: a pure device-layout choice (bit-exact results)
     A->lay.slice_rows = kBlockThreads * R;
     A->lay.num_slices = (A->lay.num_rows + A->lay.slice_rows - 1) / A->lay.slice_rows;
     cudaDeviceProp prop;

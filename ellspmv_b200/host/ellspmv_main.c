@@ -89,7 +89,8 @@ static void help(FILE *f)
     fprintf(f, "  --fma                allow fused multiply-add (tolerance mode)\n");
     fprintf(f, "  --rows-per-thread=N  1, 2 or 4 rows per thread [4]\n");
     fprintf(f, "  --l2-persist-x       L2 persisting access window over x\n");
-    fprintf(f, "  --narrow-index       keep 64-bit column indices as 32-bit on the device\n");
+    fprintf(f, "  --wide-index         keep 64-bit column indices 64-bit on the device (default: stored as\n");
+    fprintf(f, "                       32-bit when the matrix has fewer than 2^31 columns)\n");
     fprintf(f, "  --column-blocked     bin entries by column block so x stays in L2 (tolerance mode;\n");
     fprintf(f, "                       for scattered matrices whose x is larger than the L2 cache)\n");
     fprintf(f, "  --iterate            compute x := A*x repeatedly (y := A^N x); square A only\n");
@@ -162,6 +163,7 @@ static int parse_options(int argc, char **argv, struct options *o, int *bad)
             if (!strcmp(a, "--fma")) { o->flags |= ELLSPMV_CUDA_FMA; continue; }
             if (!strcmp(a, "--l2-persist-x")) { o->flags |= ELLSPMV_CUDA_L2_PERSIST_X; continue; }
             if (!strcmp(a, "--narrow-index")) { o->flags |= ELLSPMV_CUDA_NARROW_INDEX; continue; }
+            if (!strcmp(a, "--wide-index")) { o->flags |= ELLSPMV_CUDA_WIDE_INDEX; continue; }
             if (!strcmp(a, "--column-blocked")) { o->flags |= ELLSPMV_CUDA_COLUMN_BLOCKED; continue; }
             if (!strncmp(a, "--rows-per-thread", 17) && (a[17] == '=' || a[17] == '\0')) {
                 int r;

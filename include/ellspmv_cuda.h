@@ -59,10 +59,13 @@ enum {
     ELLSPMV_CUDA_FMA           = 1 << 4,
     /* ask for an L2 persisting access-policy window over x when it fits */
     ELLSPMV_CUDA_L2_PERSIST_X  = 1 << 5,
-    /* keep 64-bit column indices as 32-bit on the device when
-     * num_columns < 2^31 (a device-layout choice; host arrays and
-     * ellspmv_cuda_download() stay 64-bit and bit-exact) */
+    /* 64-bit column indices are kept as 32-bit on the device whenever
+     * num_columns < 2^31: a device-layout choice, results and
+     * ellspmv_cuda_download() stay 64-bit and bit-exact, the index stream
+     * halves.  This is the default; NARROW_INDEX is accepted for
+     * compatibility, WIDE_INDEX keeps the caller's width on the device. */
     ELLSPMV_CUDA_NARROW_INDEX  = 1 << 6,
+    ELLSPMV_CUDA_WIDE_INDEX    = 1 << 16,
     /* bin the entries by column block so that each block's slice of x
      * (<= 48 MB) stays in L2, and run y += A_b*x block after block: for
      * matrices with scattered columns and an x larger than L2 (BASELINE

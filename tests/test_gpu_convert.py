@@ -55,7 +55,7 @@ def test_random_vs_oracle(lib, oracle, shape, bits):
     a = rng.standard_normal(nnz)
     assert np.bincount(ri, minlength=nr + 1).max() * nr < 80_000_000     # guard: the ELL arrays must stay small
     K, ellsize, _, ec, ea = oracle.ell_from_coo(nr, nc, ri, ci, a)
-    for flags in (0, E.rows_per_thread(4), E.NARROW_INDEX):
+    for flags in (0, E.rows_per_thread(4), E.WIDE_INDEX):
         A = E.EllMatrix.upload_coo(nr, nc, ri, ci, a, flags)
         assert A.info().rowsize == K
         ec2, ea2 = A.download()

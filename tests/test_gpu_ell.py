@@ -82,11 +82,11 @@ def test_bit_exact_vs_oracle(lib, oracle, shape, bits):
     want0 = np.zeros(nr)
     oracle.ellgemv(nr, want0, x, K, ec, ea)
     for R in ALL_R:
-        for extra in (0, E.NARROW_INDEX, E.L2_PERSIST_X):
+        for extra in (0, E.WIDE_INDEX, E.L2_PERSIST_X):
             A = E.EllMatrix.upload(nr, nc, K, ec, ea, E.rows_per_thread(R) | extra)
             info = A.info()
             assert info.rows_per_thread == R and info.slice_rows == 128 * R
-            assert info.dev_idx_bits == (32 if (bits == 32 or extra == E.NARROW_INDEX) else 64)
+            assert info.dev_idx_bits == (64 if (bits == 64 and extra == E.WIDE_INDEX) else 32)
             assert info.min_col == ec.min() and info.max_col == ec.max()
             c2, a2 = A.download()
             assert c2.dtype == dt and np.array_equal(c2, ec) and bits_equal(a2, ea)

@@ -99,7 +99,7 @@ def test_full_size_laplacian_properties(lib):
 def test_full_size_stencil27_properties(lib):
     """BASELINE config 3 at full size (27-point 384^3, IDXTYPEWIDTH=64, 56.6M rows,
     24 GB matrix): A*ones = 26 - (#neighbours) exactly (small integers in fp64),
-    the index-narrowed device layout gives the same bits, and scaling x by 2
+    the default index-narrowed device layout and the wide one give the same bits, and scaling x by 2
     scales y by 2 bit for bit."""
     import torch
     n = 384
@@ -110,10 +110,10 @@ def test_full_size_stencil27_properties(lib):
     c[0] = c[-1] = 2.0
     want = 27.0 - (c[:, None, None] * c[None, :, None] * c[None, None, :]).reshape(-1)   # 26 - (count - 1)
     ys = []
-    for flags in (0, E.NARROW_INDEX):
+    for flags in (E.WIDE_INDEX, 0):
         A = E.EllMatrix.generate(E.GEN_STENCIL27, (n, n, n), (26.0, -1.0), 42, 64, flags=flags)
         i = A.info()
-        assert (i.num_rows, i.rowsize, i.idx_width_bits, i.dev_idx_bits) == (rows, 27, 64, 32 if flags else 64)
+        assert (i.num_rows, i.rowsize, i.idx_width_bits, i.dev_idx_bits) == (rows, 27, 64, 64 if flags else 32)
         y = torch.zeros(rows, dtype=torch.float64, device="cuda")
         A.spmv_device(y, x, E.ACCUMULATE, s)
         assert torch.equal(y, want)

@@ -66,8 +66,8 @@ def main():
         variants.append(("thread R=4 fma", E.KERNEL_THREAD | E.rows_per_thread(4) | E.FMA))
         variants.append(("thread R=4 l2persist", E.KERNEL_THREAD | E.rows_per_thread(4) | E.L2_PERSIST_X))
         if bits == 64:
-            variants.append(("thread R=4 narrow", E.KERNEL_THREAD | E.rows_per_thread(4) | E.NARROW_INDEX))
-            variants.append(("thread R=2 narrow", E.KERNEL_THREAD | E.rows_per_thread(2) | E.NARROW_INDEX))
+            variants.append(("thread R=1 wide-index", E.KERNEL_THREAD | E.rows_per_thread(1) | E.WIDE_INDEX))
+            variants.append(("thread R=2 wide-index", E.KERNEL_THREAD | E.rows_per_thread(2) | E.WIDE_INDEX))
         for R in (1, 4):
             variants.append((f"warp S={128 * R}", E.KERNEL_WARP | E.rows_per_thread(R)))
         if args.variants != "all":
