@@ -69,3 +69,36 @@ def test_argument_validation_is_reported_as_einval(lib):
     assert lib.ellspmv_cuda_upload(C.byref(h), 32, -1, 1, 1, None, None, 1, 0) == errno.EINVAL
     assert lib.ellspmv_cuda_spmv(None, None, None, 1, 0, None) == errno.EINVAL
     lib.ellspmv_cuda_free(None)   # no-op, like free(NULL)
+
+
+def test_header_is_plain_c_and_links(tmp_path, lib):
+    """The boundary is a C ABI: the header must compile as C99 and a C caller
+    must link against the library with nothing but -lellspmv_cuda."""
+    import subprocess
+    src = tmp_path / "caller.c"
+    src.write_text(r'''
+#include <errno.h>
+#include <stdio.h>
+#include "ellspmv_cuda.h"
+int main(void) {
+    int colidx[4] = {0, 1, 0, 1};
+    double a[4] = {1, 2, 3, 4}, x[2] = {1, 1}, y[2] = {0, 0};
+    ellspmv_cuda_matrix *A = NULL;
+    int n = -1;
+    ellspmv_cuda_device_count(&n);
+    int err = ellspmv_cuda_upload(&A, 32, 2, 2, 2, colidx, a, 1, 0);
+    if (n <= 0) { printf("nodev %d %s\n", err == ENODEV, ellspmv_cuda_strerror(err)); return err == ENODEV ? 0 : 1; }
+    if (err) return 2;
+    err = ellspmv_cuda_spmv(A, y, x, 1, ELLSPMV_CUDA_ACCUMULATE, NULL);
+    ellspmv_cuda_free(A);
+    printf("y %g %g\n", y[0], y[1]);
+    return (err == 0 && y[0] == 3 && y[1] == 7) ? 0 : 3;
+}
+''')
+    exe = tmp_path / "caller"
+    libdir = os.path.dirname(E.LIB_PATH)
+    cmd = ["/usr/bin/gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src),
+           "-L", libdir, "-lellspmv_cuda", f"-Wl,-rpath,{libdir}", "-o", str(exe)]
+    subprocess.run(cmd, check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, (r.stdout, r.stderr)
