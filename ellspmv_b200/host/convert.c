@@ -10,6 +10,7 @@ void ell_free(struct ell_matrix *ell)
     free(ell->colidx);
     free(ell->a);
     free(ell->ad);
+    free(ell->rowcount);
     memset(ell, 0, sizeof(*ell));
 }
 
@@ -77,7 +78,7 @@ int ell_from_coo(struct ell_matrix *ell, idx_t num_rows, idx_t num_columns, int6
             ell->a[r * K + l] = 0.0;
         }
     }
-    free(fill);
+    ell->rowcount = fill;      /* entries per row, for ell_sort_rows */
     return 0;
 }
 
@@ -153,9 +154,34 @@ static void insertion_sort(idx_t *c, double *v, int64_t lo, int64_t hi)
     }
 }
 
-int csr_sort_rows(struct csr_matrix *csr)
+/* sort n entries (c, v) by column: runs of 16 by stable insertion sort, then
+ * bottom-up merging where, on equal columns, the right-hand run wins -- the
+ * order the reference's rowsort produces (csrspmv.c:1279-1376).  tc/tv: scratch of n. */
+static void sort_one_row(idx_t *c, double *v, int64_t n, idx_t *tc, double *tv)
 {
     enum { RUN = 16 };
+    if (n <= RUN) { insertion_sort(c, v, 0, n); return; }
+    for (int64_t q = 0; q < n - 1; q += RUN) insertion_sort(c, v, q, q + RUN < n ? q + RUN : n);
+    for (int64_t w = RUN; w < n; w *= 2) {
+        memcpy(tc, c, (size_t)n * sizeof(idx_t));
+        memcpy(tv, v, (size_t)n * sizeof(double));
+        for (int64_t q = 0; q < n - 1; q += 2 * w) {
+            const int64_t mid = q + w < n ? q + w : n, end = q + 2 * w < n ? q + 2 * w : n;
+            int64_t o = q, l = q, r = mid;
+            while (l < mid && r < end) {
+                if (tc[l] < tc[r]) { c[o] = tc[l]; v[o++] = tv[l++]; }
+                else { c[o] = tc[r]; v[o++] = tv[r++]; }
+            }
+            while (l < mid) { c[o] = tc[l]; v[o++] = tv[l++]; }
+            while (r < end) { c[o] = tc[r]; v[o++] = tv[r++]; }
+        }
+    }
+}
+
+/* rows [0, num_rows): row i holds n_i = len(i) entries starting at start(i) */
+static int sort_rows(idx_t *colidx, double *a, int64_t num_rows, const int64_t *rowptr /* or NULL */,
+                     int64_t stride, const int64_t *rowcount /* with stride */)
+{
     int err = 0;
 #ifdef _OPENMP
 #pragma omp parallel
@@ -167,38 +193,31 @@ int csr_sort_rows(struct csr_matrix *csr)
 #ifdef _OPENMP
 #pragma omp for schedule(dynamic, 256)
 #endif
-        for (int64_t i = 0; i < (int64_t)csr->num_rows; i++) {
-            idx_t *c = csr->colidx + csr->rowptr[i];
-            double *v = csr->a + csr->rowptr[i];
-            const int64_t n = csr->rowptr[i + 1] - csr->rowptr[i];
-            if (n <= RUN) { insertion_sort(c, v, 0, n); continue; }
-            /* long row: sorted runs of 16, then bottom-up merging; on equal
-             * columns the right-hand run wins, as in the reference */
-            for (int64_t q = 0; q < n - 1; q += RUN) insertion_sort(c, v, q, q + RUN < n ? q + RUN : n);
-            if (n > cap) {
+        for (int64_t i = 0; i < num_rows; i++) {
+            const int64_t start = rowptr ? rowptr[i] : i * stride;
+            const int64_t n = rowptr ? rowptr[i + 1] - rowptr[i] : rowcount[i];
+            if (n > 16 && n > cap) {
                 free(tc); free(tv);
                 tc = malloc((size_t)n * sizeof(idx_t));
                 tv = malloc((size_t)n * sizeof(double));
                 cap = n;
                 if (!tc || !tv) { err = ENOMEM; cap = 0; continue; }
             }
-            for (int64_t w = RUN; w < n; w *= 2) {
-                memcpy(tc, c, (size_t)n * sizeof(idx_t));
-                memcpy(tv, v, (size_t)n * sizeof(double));
-                for (int64_t q = 0; q < n - 1; q += 2 * w) {
-                    const int64_t mid = q + w < n ? q + w : n, end = q + 2 * w < n ? q + 2 * w : n;
-                    int64_t o = q, l = q, r = mid;
-                    while (l < mid && r < end) {
-                        if (tc[l] < tc[r]) { c[o] = tc[l]; v[o++] = tv[l++]; }
-                        else { c[o] = tc[r]; v[o++] = tv[r++]; }
-                    }
-                    while (l < mid) { c[o] = tc[l]; v[o++] = tv[l++]; }
-                    while (r < end) { c[o] = tc[r]; v[o++] = tv[r++]; }
-                }
-            }
+            sort_one_row(colidx + start, a + start, n, tc, tv);
         }
         free(tc);
         free(tv);
     }
     return err;
+}
+
+int csr_sort_rows(struct csr_matrix *csr)
+{
+    return sort_rows(csr->colidx, csr->a, csr->num_rows, csr->rowptr, 0, NULL);
+}
+
+int ell_sort_rows(struct ell_matrix *ell)
+{
+    if (!ell->rowcount) return EINVAL;
+    return sort_rows(ell->colidx, ell->a, ell->num_rows, NULL, ell->rowsize, ell->rowcount);
 }

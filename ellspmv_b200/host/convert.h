@@ -23,6 +23,7 @@ struct ell_matrix {
     idx_t *colidx;      /* ellsize */
     double *a;          /* ellsize */
     double *ad;         /* diagsize entries when the diagonal is stored separately, else NULL */
+    int64_t *rowcount;  /* entries per row before the padding (kept for --sort-rows) */
 };
 
 struct csr_matrix {
@@ -52,6 +53,13 @@ int csr_from_coo(struct csr_matrix *csr, int symmetric, idx_t num_rows, idx_t nu
 /* --sort-rows for CSR: sort every row by column exactly like the reference's
  * rowsort (csrspmv.c:1269-1388), including its tie order for duplicate columns */
 int csr_sort_rows(struct csr_matrix *csr);
+/* --sort-rows for ELL: the entries of every row (not the padding) sorted by
+ * column with the same order the reference's rowsort gives the CSR rows, so
+ * ELL row i == sorted CSR row i followed by padding.  The reference's own ELL
+ * --sort-rows hands rowsort per-row counts where it expects offsets and
+ * scrambles the matrix (ellspmv.c:1121-1123); this is the intended
+ * behaviour. */
+int ell_sort_rows(struct ell_matrix *ell);
 void ell_free(struct ell_matrix *ell);
 void csr_free(struct csr_matrix *csr);
 

@@ -18,7 +18,8 @@
  *     flags arrive in DECLARED order (diagonal summed into `ad`, K counted
  *     without it, kernel ellgemvsd / ellgemv16sd): the reference's main()
  *     passes the two flags swapped into ell_from_coo and overruns its arrays
- *     (ellspmv.c:1094-1095 vs 1468-1471).  --sort-rows is refused: the
+ *     (ellspmv.c:1094-1095 vs 1468-1471).  --sort-rows sorts every row's
+ *     entries by column like the reference's CSR program does; the
  *     reference's ELL rowsort sorts the wrong ranges (ellspmv.c:1121-1123);
  *   - x from a file is read with num_columns entries (the reference reads
  *     num_rows, ellspmv.c:1574-1575, which is only right for square A);
@@ -78,7 +79,7 @@ static void help(FILE *f)
     fprintf(f, "  -z, --gzip, --gunzip, --ungzip    filter files through gzip\n");
 #endif
     fprintf(f, "  --separate-diagonal  store diagonal nonzeros separately\n");
-    fprintf(f, "  --sort-rows          (refused: broken in the reference, see source)\n");
+    fprintf(f, "  --sort-rows          sort nonzeros by column within each row\n");
     fprintf(f, "  --repeat=N           repeat matrix-vector multiplication N times\n");
     fprintf(f, "  --warmup=N                perform N additional warmup iterations\n");
     fprintf(f, "  -q, --quiet          do not print Matrix Market output\n");
@@ -241,9 +242,8 @@ int main(int argc, char *argv[])
         fprintf(stderr, "%s: %s %s\n", prog, strerror(err), bad < argc ? argv[bad] : "");
         return EXIT_FAILURE;
     }
-    if (o.sort_rows) {
-        fprintf(stderr, "%s: --sort-rows is not supported: the reference's ELL rowsort is handed per-row "
-                        "counts instead of offsets and scrambles the matrix\n", prog);
+    if (o.sort_rows && o.synthetic) {
+        fprintf(stderr, "%s: --sort-rows is not supported with --synthetic\n", prog);
         return EXIT_FAILURE;
     }
     if (o.separate_diagonal && o.synthetic) {
@@ -327,7 +327,7 @@ int main(int argc, char *argv[])
 
         /* 3. convert to ELLPACK (ellspmv.c:1379-1486) */
         if (o.verbose > 0) { fprintf(stderr, "ell_from_coo: "); clock_gettime(CLOCK_MONOTONIC, &t0); }
-        if (o.device_convert && !o.separate_diagonal && o.gpus == 1) {
+        if (o.device_convert && !o.separate_diagonal && !o.sort_rows && o.gpus == 1) {
             /* stable sort by row on the device instead of the serial host scatter */
             err = ellspmv_cuda_upload_coo(&A, IDX_BITS, num_rows, num_columns, num_nonzeros, rowidx, colidx, a,
                                           o.device, o.flags);
@@ -356,6 +356,9 @@ int main(int argc, char *argv[])
         }
         err = ell_from_coo(&ell, num_rows, num_columns, num_nonzeros, rowidx, colidx, a, o.separate_diagonal);
         free(a); free(colidx); free(rowidx);
+        /* intended --sort-rows: every row's entries by column, padding last (the
+         * reference's ELL version is broken, see convert.h) */
+        if (!err && o.sort_rows) err = ell_sort_rows(&ell);
         if (err) {
             if (o.verbose > 0) fprintf(stderr, "\n");
             fprintf(stderr, "%s: %s\n", prog, strerror(err));

@@ -53,12 +53,15 @@ int host_ell_from_file_sd(const char *path, int gzip, int separate_diagonal, int
     int err = read_coo(path, gzip, &h, &ri, &ci, &v, &dims[6]);
     if (err) return err;
     struct ell_matrix ell;
-    err = ell_from_coo(&ell, h.num_rows, h.num_columns, h.num_nonzeros, ri, ci, v, separate_diagonal);
+    /* bit 1 of separate_diagonal asks for --sort-rows as well */
+    err = ell_from_coo(&ell, h.num_rows, h.num_columns, h.num_nonzeros, ri, ci, v, separate_diagonal & 1);
+    if (!err && (separate_diagonal & 2)) err = ell_sort_rows(&ell);
     free(ri); free(ci); free(v);
     if (err) return err;
     dims[0] = ell.num_rows; dims[1] = ell.num_columns; dims[2] = h.num_nonzeros;
     dims[3] = ell.rowsize; dims[4] = ell.ellsize; dims[5] = ell.diagsize;
     *colidx = ell.colidx; *a = ell.a; *ad = ell.ad;
+    free(ell.rowcount);
     return 0;
 }
 

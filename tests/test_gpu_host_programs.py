@@ -94,3 +94,15 @@ def test_synthetic_and_iterate_options(oracle):
     assert r.stdout.splitlines()[2:] == ["%.15g" % v for v in want]
     r = run("ellspmv", ["--separate-diagonal", "--synthetic=laplace2d:4,4"])
     assert r.returncode == 1 and "not supported" in r.stderr
+
+
+@pytest.mark.parametrize("name", ["rand_square", "long_rows", "rand_wide"])
+def test_ell_sort_rows_prints_what_the_reference_csr_program_prints(tmp_path, name):
+    """ellspmv --sort-rows (intended semantics) adds the same products in the same
+    order as csrspmv --sort-rows, plus trailing zero padding."""
+    g = load_golden(name)
+    A = str(tmp_path / "A.mtx")
+    hostlib.write_mtx(A, g["num_rows"], g["num_columns"], g["rowidx"], g["colidx"], unhex(g["a"]), comments=())
+    r = run("ellspmv", ["--sort-rows", A])
+    assert r.returncode == 0, r.stderr
+    assert r.stdout.replace("\n-0\n", "\n0\n") == g["program"]["csrspmv_sorted"]["stdout"].replace("\n-0\n", "\n0\n")

@@ -221,3 +221,29 @@ def test_host_sort_rows_matches_reference(tmp_path, name, bits):
     assert hostlib._take(lib, rowptr, g["num_rows"] + 1, C.c_int64, np.int64).tolist() == e["rowptr"]
     assert hostlib._take(lib, colidx, dims[3], it, dt).tolist() == e["csrcolidx_sorted"]
     assert bits_equal(hostlib._take(lib, a, dims[3], C.c_double, np.float64), unhex(e["csra_sorted"]))
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+@pytest.mark.parametrize("bits", [32, 64])
+def test_host_ell_sort_rows_equals_sorted_csr_rows(tmp_path, name, bits):
+    """Intended ELL --sort-rows: row i == the reference-sorted CSR row i, then padding."""
+    import ctypes as C
+    g = load_golden(name)
+    e = g[f"idx{bits}"]
+    p = str(tmp_path / "A.mtx")
+    hostlib.write_mtx(p, g["num_rows"], g["num_columns"], g["rowidx"], g["colidx"], unhex(g["a"]))
+    lib = hostlib.hostlib(bits)
+    it = C.c_int32 if bits == 32 else C.c_int64
+    dt = np.int32 if bits == 32 else np.int64
+    dims = (C.c_int64 * 7)()
+    colidx, a, ad = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    assert lib.host_ell_from_file_sd(p.encode(), 0, 2, dims, C.byref(colidx), C.byref(a), C.byref(ad)) == 0
+    K, nr = dims[3], g["num_rows"]
+    ec = hostlib._take(lib, colidx, dims[4], it, dt).reshape(nr, K) if K else np.zeros((nr, 0), dtype=dt)
+    ea = hostlib._take(lib, a, dims[4], C.c_double, np.float64).reshape(nr, K) if K else np.zeros((nr, 0))
+    rowptr = e["rowptr"]
+    sc, sa = np.array(e["csrcolidx_sorted"], dtype=dt), unhex(e["csra_sorted"])
+    for i in range(nr):
+        n = rowptr[i + 1] - rowptr[i]
+        assert np.array_equal(ec[i, :n], sc[rowptr[i]:rowptr[i + 1]]) and bits_equal(ea[i, :n], sa[rowptr[i]:rowptr[i + 1]])
+        assert np.all(ec[i, n:] == min(i, g["num_columns"] - 1)) and np.all(ea[i, n:] == 0.0)
