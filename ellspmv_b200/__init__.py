@@ -30,6 +30,7 @@ FMA = 1 << 4
 L2_PERSIST_X = 1 << 5
 NARROW_INDEX = 1 << 6
 COLUMN_BLOCKED = 1 << 7
+STAGED_GATHER = 1 << 17
 WIDE_INDEX = 1 << 16
 ROWS_PER_THREAD_SHIFT = 8
 VARIANT_SHIFT = 12

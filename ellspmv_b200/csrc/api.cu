@@ -154,7 +154,9 @@ int finish_minmax(ellspmv_cuda_matrix *A)
 // block's slice of x stays in L2 (ell_blocked.cu); no-op when x already fits
 int build_column_blocks(ellspmv_cuda_matrix *A)
 {
-    if (!(A->flags & ELLSPMV_CUDA_COLUMN_BLOCKED) || A->lay.num_rows <= 0 || A->lay.rowsize <= 0) return 0;
+    if (!(A->flags & (ELLSPMV_CUDA_COLUMN_BLOCKED | ELLSPMV_CUDA_STAGED_GATHER)) || A->lay.num_rows <= 0 ||
+        A->lay.rowsize <= 0)
+        return 0;
     // x bytes per column block: 48 MB stays resident in the 126 MB (2 x 63 MB) L2 next to the
     // streaming matrix -- measured 11.6 / 9.2 / 9.8 / 13.5 ms at 32 / 48 / 64 / 80 MB on BASELINE
     // config 4 (profiles/r1_c4_column_blocked.md); ELLSPMV_CUDA_BLOCK_BYTES overrides it
@@ -162,6 +164,13 @@ int build_column_blocks(ellspmv_cuda_matrix *A)
     if (const char *env = getenv("ELLSPMV_CUDA_BLOCK_BYTES")) {
         long long v = atoll(env);
         if (v >= 8) target = v;
+    }
+    if (A->flags & ELLSPMV_CUDA_STAGED_GATHER) {
+        // the bit-exact flavour (ell_staged.cu); wins over COLUMN_BLOCKED when both are set
+        cudaError_t ce = sg_build(&A->sg, A->dev_idx_bits, A->cols, A->lay, A->num_columns, target, A->stream);
+        if (ce != cudaSuccess) { set_last_error("staged gather: %s", cudaGetErrorString(ce)); return cuda_to_errno(ce); }
+        A->device_bytes += sg_bytes(A->sg);
+        return 0;
     }
     cudaError_t ce = cb_build(&A->cb, A->dev_idx_bits, A->vals, A->cols, A->lay, A->num_columns, target, A->stream);
     if (ce != cudaSuccess) { set_last_error("column blocking: %s", cudaGetErrorString(ce)); return cuda_to_errno(ce); }
@@ -214,6 +223,12 @@ int launch(ellspmv_cuda_matrix *A, double *y_dev, const double *x_dev, int beta,
     args.sd_order = A->sd_order;
     if (num_slices < 0) num_slices = A->lay.num_slices - slice_begin;
     if (push) args.push = *push; else args.push.num_peers = 0;
+    if (A->sg && !push && slice_begin == 0 && num_slices == A->lay.num_slices) {
+        ELL_CK(sg_spmv(A->sg, A->cfg.fma, A->vals, x_dev, y_dev, A->d_ad, A->sd_order, A->lay.num_rows,
+                       A->num_columns, A->row_begin, beta, stream));
+        A->launches += sg_launches(A->sg);
+        return 0;
+    }
     if (A->cb && !push && !A->d_ad && slice_begin == 0 && num_slices == A->lay.num_slices) {
         ELL_CK(cb_spmv(A->cb, A->cfg.fma, x_dev, y_dev, A->lay.num_rows, A->num_columns, beta, stream));
         A->launches += cb_blocks(A->cb);
@@ -351,6 +366,7 @@ void ellspmv_cuda_free(ellspmv_cuda_matrix *A)
     if (A->d_minmax) cudaFree(A->d_minmax);
     if (A->d_ad) cudaFree(A->d_ad);
     if (A->cb) cb_free(A->cb);
+    if (A->sg) sg_free(A->sg);
     if (A->d_x) cudaFree(A->d_x);
     if (A->d_y) cudaFree(A->d_y);
     if (A->stream) cudaStreamDestroy(A->stream);
@@ -676,7 +692,7 @@ int ellspmv_cuda_spmv(
     DeviceGuard g(A->device);
     int err = ensure_vectors(A);
     if (err) return err;
-    if (repeat == 1 && mode != ELLSPMV_CUDA_ITERATE && rows >= (1 << 20) && A->lay.rowsize > 0 && ncols > 0 && !A->cb)
+    if (repeat == 1 && mode != ELLSPMV_CUDA_ITERATE && rows >= (1 << 20) && A->lay.rowsize > 0 && ncols > 0 && !A->cb && !A->sg)
         return spmv_pipelined(A, y, x, mode == ELLSPMV_CUDA_ACCUMULATE ? 1 : 0, seconds);
     if ((err = ensure_events(A->events, (size_t)repeat + 1))) return err;
     cudaStream_t s = A->stream;

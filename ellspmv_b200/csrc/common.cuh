@@ -146,6 +146,17 @@ int64_t cb_bytes(const CbMatrix *cb);
 int cb_blocks(const CbMatrix *cb);
 int64_t cb_entries(const CbMatrix *cb);
 
+// ---- column-blocked, staged gather: bit-exact (ell_staged.cu) ---------------------
+struct SgMatrix;
+cudaError_t sg_build(SgMatrix **out, int idx_bits, const void *cols, const EllLayout &lay, int64_t num_columns,
+                     int64_t target_x_bytes, cudaStream_t stream);
+cudaError_t sg_spmv(const SgMatrix *sg, bool fma, const double *vals, const double *x, double *y, const double *ad,
+                    int sd_order, int64_t num_rows, int64_t num_columns, int64_t row_begin, int beta,
+                    cudaStream_t stream);
+void sg_free(SgMatrix *sg);
+int64_t sg_bytes(const SgMatrix *sg);
+int sg_launches(const SgMatrix *sg);
+
 // ---- COO -> ELL / CSR on the device (convert.cu) ------------------------------
 struct CooEllJob {
     int idx_bits = 32;

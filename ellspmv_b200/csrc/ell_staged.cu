@@ -1,0 +1,383 @@
+// ell_staged.cu -- column-blocked ELL with the x gather STAGED through HBM
+// (ELLSPMV_CUDA_STAGED_GATHER): the bit-exact answer to matrices whose x does not
+// fit in L2.
+//
+// Why: on B200 a random 8-byte gather that misses L2 costs a ~100-byte line fill
+// (profiles/r1_c4_gather.md), so the plain kernel runs BASELINE config 4 (random
+// 50M x 32, x = 400 MB) at 9x its algorithmic bytes.  ell_blocked.cu fixes the
+// locality by summing block after block, which changes the association of the
+// row sums (tolerance mode).  Here the two halves of `a*x[col]` are separated
+// instead, so that the arithmetic keeps the reference's exact order
+// (ellspmv.c:1146-1151):
+//
+//   phase 1 (gather): the column indices are stored a second time, sorted by
+//     (column block, slice).  One launch per column block walks its run of
+//     indices -- a flat, perfectly coalesced stream -- gathers x[col] while that
+//     block's slice of x (<= 48 MB) is pinned in L2 by an access-policy window,
+//     and writes the gathered values as a flat stream xg.
+//   phase 2 (sum): one CTA per slice.  For a slice the gathered values are nb
+//     contiguous runs of xg (one per column block); one thread fetches them into
+//     shared memory with bulk-async copies (cp.async.bulk + mbarrier, SASS
+//     UBLKCP) while the CTA already loads its first values.  A 16-bit `pos`
+//     stream in the sliced-ELL layout says where entry (row, slot) landed, and
+//     every thread then runs the reference's loop over ITS row, slot 0..K-1,
+//     mul then add: the same roundings as ell_thread_kernel, bit for bit.
+//
+// Bytes per stored entry: phase 1 reads idx (4/8) and writes 8; phase 2 reads
+// 8 (value) + 2 (pos) + 8 (xg) -> 30 B for 32-bit indices, against ~112 B of
+// DRAM traffic per entry for the direct gather.  Device memory: +(idx + 2 + 8)
+// bytes per entry.
+#include <cub/cub.cuh>
+
+#include "common.cuh"
+
+namespace ellspmv {
+
+constexpr int kSgMaxBlocks = 64;
+constexpr int kSgHeader = 16;                 // the mbarrier in front of the staging buffer
+constexpr int kSgMaxSmem = 200 * 1024;
+
+struct SgMatrix {
+    int idx_bits = 32;
+    int num_blocks = 0;
+    int64_t block_cols = 0;
+    int64_t num_slices = 0;
+    int slice_rows = 0, rowsize = 0;
+    int64_t total = 0;                        // entries of gcols / xg (segments padded to even length)
+    void *gcols = nullptr;                    // column indices sorted by (block, slice)
+    long long *seg = nullptr;                 // num_blocks * num_slices + 1 segment starts
+    unsigned short *pos = nullptr;            // sliced-ELL layout: index into the slice's staging buffer
+    double *xg = nullptr;                     // gathered x, same order as gcols
+    long long block_start[kSgMaxBlocks + 1];  // host copy of seg[b * num_slices]
+    int64_t bytes = 0;
+    size_t smem = 0;
+    bool persist = false;
+};
+
+void sg_free(SgMatrix *sg)
+{
+    if (!sg) return;
+    cudaFree(sg->gcols); cudaFree(sg->seg); cudaFree(sg->pos); cudaFree(sg->xg);
+    delete sg;
+}
+int64_t sg_bytes(const SgMatrix *sg) { return sg ? sg->bytes : 0; }
+int sg_launches(const SgMatrix *sg) { return sg ? sg->num_blocks + 1 : 0; }
+
+// ---- build ---------------------------------------------------------------------
+template <typename IdxT>
+__global__ void __launch_bounds__(kBlockThreads)
+sg_count_kernel(const IdxT *__restrict__ cols, int S, int K, int nb, int64_t block_cols, int64_t ns,
+                long long *__restrict__ sizes)
+{
+    __shared__ int cnt[kSgMaxBlocks];
+    const int64_t s = blockIdx.x;
+    for (int b = threadIdx.x; b < nb; b += blockDim.x) cnt[b] = 0;
+    __syncthreads();
+    const IdxT *c = cols + s * S * (int64_t)K;
+    for (int i = threadIdx.x; i < S * K; i += blockDim.x) atomicAdd(&cnt[(int)((int64_t)c[i] / block_cols)], 1);
+    __syncthreads();
+    for (int b = threadIdx.x; b < nb; b += blockDim.x) sizes[(int64_t)b * ns + s] = (cnt[b] + 1) & ~1;
+}
+
+template <typename IdxT>
+__global__ void __launch_bounds__(kBlockThreads)
+sg_fill_kernel(const IdxT *__restrict__ cols, int S, int K, int nb, int64_t block_cols, int64_t ns,
+               const long long *__restrict__ seg, IdxT *__restrict__ gcols, unsigned short *__restrict__ pos)
+{
+    __shared__ int cursor[kSgMaxBlocks];
+    __shared__ int prefix[kSgMaxBlocks];
+    __shared__ long long start[kSgMaxBlocks];
+    const int64_t s = blockIdx.x;
+    for (int b = threadIdx.x; b < nb; b += blockDim.x) {
+        cursor[b] = 0;
+        start[b] = seg[(int64_t)b * ns + s];
+        prefix[b] = (int)(seg[(int64_t)b * ns + s + 1] - start[b]);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int b = 0; b < nb; b++) { const int len = prefix[b]; prefix[b] = run; run += len; }
+    }
+    __syncthreads();
+    const int64_t base = s * S * (int64_t)K;
+    for (int i = threadIdx.x; i < S * K; i += blockDim.x) {
+        const IdxT c = cols[base + i];
+        const int b = (int)((int64_t)c / block_cols);
+        const int r = atomicAdd(&cursor[b], 1);
+        gcols[start[b] + r] = c;
+        pos[base + i] = (unsigned short)(prefix[b] + r);
+    }
+}
+
+template <typename IdxT>
+static cudaError_t sg_build_typed(SgMatrix *sg, const IdxT *cols, cudaStream_t stream)
+{
+    const int64_t ns = sg->num_slices, n = (int64_t)sg->num_blocks * ns;
+    const int S = sg->slice_rows, K = sg->rowsize, nb = sg->num_blocks;
+    cudaError_t e;
+    long long *sizes = nullptr;
+    void *temp = nullptr;
+    if ((e = cudaMalloc(&sizes, (size_t)(n + 1) * 8)) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&sg->seg, (size_t)(n + 1) * 8)) != cudaSuccess) { cudaFree(sizes); return e; }
+    e = cudaMemsetAsync(sizes, 0, (size_t)(n + 1) * 8, stream);
+    if (e == cudaSuccess) {
+        sg_count_kernel<IdxT><<<(unsigned)ns, kBlockThreads, 0, stream>>>(cols, S, K, nb, sg->block_cols, ns, sizes);
+        e = cudaGetLastError();
+    }
+    size_t temp_bytes = 0;
+    if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(nullptr, temp_bytes, sizes, sg->seg, n + 1, stream);
+    if (e == cudaSuccess) e = cudaMalloc(&temp, temp_bytes + 16);
+    if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(temp, temp_bytes, sizes, sg->seg, n + 1, stream);
+    for (int b = 0; b <= nb && e == cudaSuccess; b++)
+        e = cudaMemcpyAsync(&sg->block_start[b], sg->seg + (int64_t)b * ns, 8, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    cudaFree(sizes);
+    cudaFree(temp);
+    if (e != cudaSuccess) return e;
+    sg->total = sg->block_start[nb];
+    const size_t ne = (size_t)sg->total + 8;                 // slack: phase 1 works in aligned groups of 4
+    const size_t nk = (size_t)ns * S * K;
+    if ((e = cudaMalloc(&sg->gcols, ne * sizeof(IdxT))) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&sg->pos, nk * 2)) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&sg->xg, ne * 8)) != cudaSuccess) return e;
+    sg->bytes = (int64_t)(ne * (sizeof(IdxT) + 8) + nk * 2 + (size_t)(n + 1) * 8);
+    // the padding entry of an odd segment gathers x[0]
+    if ((e = cudaMemsetAsync(sg->gcols, 0, ne * sizeof(IdxT), stream)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(sg->xg, 0, ne * 8, stream)) != cudaSuccess) return e;
+    sg_fill_kernel<IdxT><<<(unsigned)ns, kBlockThreads, 0, stream>>>(cols, S, K, nb, sg->block_cols, ns, sg->seg,
+                                                                      (IdxT *)sg->gcols, sg->pos);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    return cudaStreamSynchronize(stream);
+}
+
+static cudaError_t sg_prepare_kernels();   // per device: allow the large dynamic shared memory
+
+// *out = nullptr (and success) when staging does not apply: x already fits the
+// target, or a slice's gathered values do not fit shared memory / 16-bit positions
+cudaError_t sg_build(SgMatrix **out, int idx_bits, const void *cols, const EllLayout &lay, int64_t num_columns,
+                     int64_t target_x_bytes, cudaStream_t stream)
+{
+    *out = nullptr;
+    if (lay.num_rows <= 0 || lay.rowsize <= 0 || num_columns <= 0) return cudaSuccess;
+    int64_t nb = (num_columns * 8 + target_x_bytes - 1) / target_x_bytes;
+    if (nb <= 1) return cudaSuccess;
+    if (nb > kSgMaxBlocks) nb = kSgMaxBlocks;
+    const int64_t stage = (int64_t)lay.slice_rows * lay.rowsize + nb;       // entries staged per slice
+    if (stage > 65536 || kSgHeader + stage * 8 > kSgMaxSmem || lay.num_slices > 0x7fffffffLL) return cudaSuccess;
+    SgMatrix *sg = new (std::nothrow) SgMatrix();
+    if (!sg) return cudaErrorMemoryAllocation;
+    sg->idx_bits = idx_bits;
+    sg->num_blocks = (int)nb;
+    sg->block_cols = (num_columns + nb - 1) / nb;
+    sg->num_slices = lay.num_slices;
+    sg->slice_rows = lay.slice_rows;
+    sg->rowsize = lay.rowsize;
+    sg->smem = (size_t)(kSgHeader + stage * 8);
+    cudaError_t e = idx_bits == 64 ? sg_build_typed<int64_t>(sg, (const int64_t *)cols, stream)
+                                   : sg_build_typed<int32_t>(sg, (const int32_t *)cols, stream);
+    if (e == cudaSuccess) e = sg_prepare_kernels();
+    if (e != cudaSuccess) { sg_free(sg); return e; }
+    int dev = 0;
+    cudaDeviceProp prop;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&prop, dev) == cudaSuccess) {
+        const size_t want = (size_t)sg->block_cols * 8;
+        if (prop.persistingL2CacheMaxSize > 0 && want <= (size_t)prop.accessPolicyMaxWindowSize &&
+            !getenv("ELLSPMV_CUDA_NO_PERSIST")) {
+            const size_t lim = want < (size_t)prop.persistingL2CacheMaxSize ? want : (size_t)prop.persistingL2CacheMaxSize;
+            if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, lim) == cudaSuccess) sg->persist = true;
+            cudaGetLastError();
+        }
+    }
+    *out = sg;
+    return cudaSuccess;
+}
+
+// ---- phase 1: xg[e] = x[gcols[e]] over one column block's run ----------------------
+__device__ __forceinline__ void ld4(const int32_t *p, int64_t (&c)[4])
+{
+    const int4 t = __ldcs(reinterpret_cast<const int4 *>(p));
+    c[0] = t.x; c[1] = t.y; c[2] = t.z; c[3] = t.w;
+}
+__device__ __forceinline__ void ld4(const int64_t *p, int64_t (&c)[4])
+{
+    const longlong2 t0 = __ldcs(reinterpret_cast<const longlong2 *>(p));
+    const longlong2 t1 = __ldcs(reinterpret_cast<const longlong2 *>(p) + 1);
+    c[0] = t0.x; c[1] = t0.y; c[2] = t1.x; c[3] = t1.y;
+}
+
+template <typename IdxT>
+__global__ void __launch_bounds__(256)
+sg_gather_kernel(const IdxT *__restrict__ gcols, const double *__restrict__ x, double *__restrict__ xg,
+                 int64_t first_group, int64_t num_groups)
+{
+    const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (g >= num_groups) return;
+    const int64_t e = (first_group + g) * 4;
+    int64_t c[4];
+    ld4(gcols + e, c);
+    double v[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) v[i] = __ldg(x + c[i]);
+    __stcs(reinterpret_cast<double2 *>(xg + e), make_double2(v[0], v[1]));
+    __stcs(reinterpret_cast<double2 *>(xg + e) + 1, make_double2(v[2], v[3]));
+}
+
+// ---- phase 2: the reference's row loop over staged x values ------------------------
+__device__ __forceinline__ uint32_t sg_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <bool FMA>
+__global__ void
+sg_sum_kernel(const double *__restrict__ vals, const unsigned short *__restrict__ pos, const long long *__restrict__ seg,
+              const double *__restrict__ xg, const double *__restrict__ x, double *__restrict__ y,
+              const double *__restrict__ ad, int sd_order, int64_t num_rows, int64_t row_begin, int64_t ns, int nb,
+              int K, int beta)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem);
+    double *stage = reinterpret_cast<double *>(smem + kSgHeader);
+    const int S = blockDim.x, tid = threadIdx.x;
+    const int64_t s = blockIdx.x;
+
+    // segment starts and lengths of this slice, one per column block
+    __shared__ long long s_o0[kSgMaxBlocks];
+    __shared__ int s_len[kSgMaxBlocks];
+    if (tid < nb) {
+        const long long o = seg[(int64_t)tid * ns + s];
+        s_o0[tid] = o;
+        s_len[tid] = (int)(seg[(int64_t)tid * ns + s + 1] - o);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sg_smem_u32(bar)), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        // segments are padded to even length (16-byte copies) and sum to at most S*K + nb entries
+        int total = 0;
+        for (int b = 0; b < nb; b++) total += s_len[b];
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                     ::"r"(sg_smem_u32(bar)), "r"((uint32_t)total * 8u) : "memory");
+        int run = 0;
+        for (int b = 0; b < nb; b++) {
+            const int len = s_len[b];
+            if (len > 0)
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(sg_smem_u32(stage + run)), "l"(xg + s_o0[b]), "r"((uint32_t)len * 8u),
+                               "r"(sg_smem_u32(bar)) : "memory");
+            run += len;
+        }
+    }
+
+    const int64_t row = s * S + tid;
+    const bool live = row < num_rows;
+    const int64_t base = s * S * (int64_t)K + tid;
+    const double *vp = vals + base;
+    const unsigned short *pp = pos + base;
+    double yold = 0.0, dx = 0.0;
+    if (live && beta) yold = y[row];
+    if (live && ad) dx = __dmul_rn(ad[row], __ldg(x + row_begin + row));
+
+    constexpr int U = 8;
+    double v[U]; unsigned p[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        v[u] = 0.0; p[u] = 0;
+        if (u < K) { v[u] = __ldcs(vp + (int64_t)u * S); p[u] = __ldcs(pp + (int64_t)u * S); }
+    }
+    __syncthreads();                       // the barrier is initialised before anyone polls it
+    {
+        uint32_t ok = 0;
+        for (int spins = 0; !ok && spins < (1 << 24); spins++)
+            asm volatile("{\n\t.reg .pred p;\n\t"
+                         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                         "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(sg_smem_u32(bar)), "r"(0) : "memory");
+    }
+
+    double acc = (ad && sd_order) ? dx : 0.0;
+    int l0 = 0;
+#pragma unroll 1
+    for (; l0 + U <= K; l0 += U) {
+        double vn[U]; unsigned pn[U];
+        const bool more = l0 + 2 * U <= K;
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            vn[u] = 0.0; pn[u] = 0;
+            if (more) { vn[u] = __ldcs(vp + (int64_t)(l0 + U + u) * S); pn[u] = __ldcs(pp + (int64_t)(l0 + U + u) * S); }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const double xv = stage[p[u]];
+            acc = FMA ? __fma_rn(v[u], xv, acc) : __dadd_rn(acc, __dmul_rn(v[u], xv));
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) { v[u] = vn[u]; p[u] = pn[u]; }
+    }
+    if (l0 < K) {
+        // K % U leftover slots; for K < U they sit in the preloaded registers
+        if (l0 == 0) {
+#pragma unroll
+            for (int u = 0; u < U; u++)
+                if (u < K) {
+                    const double xv = stage[p[u]];
+                    acc = FMA ? __fma_rn(v[u], xv, acc) : __dadd_rn(acc, __dmul_rn(v[u], xv));
+                }
+        } else {
+#pragma unroll 1
+            for (; l0 < K; l0++) {
+                const double xv = stage[__ldcs(pp + (int64_t)l0 * S)];
+                const double vv = __ldcs(vp + (int64_t)l0 * S);
+                acc = FMA ? __fma_rn(vv, xv, acc) : __dadd_rn(acc, __dmul_rn(vv, xv));
+            }
+        }
+    }
+    if (!live) return;
+    if (ad && !sd_order) acc = __dadd_rn(dx, acc);
+    y[row] = __dadd_rn(yold, acc);
+}
+
+static cudaError_t sg_prepare_kernels()
+{
+    cudaError_t e = cudaFuncSetAttribute(sg_sum_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSgMaxSmem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(sg_sum_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSgMaxSmem);
+    return e;
+}
+
+cudaError_t sg_spmv(const SgMatrix *sg, bool fma, const double *vals, const double *x, double *y, const double *ad,
+                    int sd_order, int64_t num_rows, int64_t num_columns, int64_t row_begin, int beta,
+                    cudaStream_t stream)
+{
+    // phase 1, block after block in stream order
+    for (int b = 0; b < sg->num_blocks; b++) {
+        const int64_t g0 = sg->block_start[b] / 4, g1 = (sg->block_start[b + 1] + 3) / 4;
+        if (g1 <= g0) continue;
+        cudaLaunchConfig_t lc = {};
+        lc.gridDim = dim3((unsigned)((g1 - g0 + 255) / 256));
+        lc.blockDim = dim3(256);
+        lc.stream = stream;
+        cudaLaunchAttribute attr[1];
+        lc.attrs = attr;
+        lc.numAttrs = 0;
+        if (sg->persist) {
+            const int64_t c0 = (int64_t)b * sg->block_cols;
+            int64_t c1 = c0 + sg->block_cols;
+            if (c1 > num_columns) c1 = num_columns;
+            attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+            attr[0].val.accessPolicyWindow.base_ptr = const_cast<double *>(x + c0);
+            attr[0].val.accessPolicyWindow.num_bytes = (size_t)(c1 - c0) * 8;
+            attr[0].val.accessPolicyWindow.hitRatio = 1.0f;
+            attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            lc.numAttrs = 1;
+        }
+        cudaError_t e = sg->idx_bits == 64
+            ? cudaLaunchKernelEx(&lc, sg_gather_kernel<int64_t>, (const int64_t *)sg->gcols, x, sg->xg, g0, g1 - g0)
+            : cudaLaunchKernelEx(&lc, sg_gather_kernel<int32_t>, (const int32_t *)sg->gcols, x, sg->xg, g0, g1 - g0);
+        if (e != cudaSuccess) return e;
+    }
+    // phase 2
+    auto kernel = fma ? sg_sum_kernel<true> : sg_sum_kernel<false>;
+    kernel<<<(unsigned)sg->num_slices, sg->slice_rows, sg->smem, stream>>>(
+        vals, sg->pos, sg->seg, sg->xg, x, y, ad, sd_order, num_rows, row_begin, sg->num_slices, sg->num_blocks,
+        sg->rowsize, beta);
+    return cudaGetLastError();
+}
+
+}  // namespace ellspmv

@@ -94,6 +94,8 @@ static void help(FILE *f)
     fprintf(f, "                       32-bit when the matrix has fewer than 2^31 columns)\n");
     fprintf(f, "  --column-blocked     bin entries by column block so x stays in L2 (tolerance mode;\n");
     fprintf(f, "                       for scattered matrices whose x is larger than the L2 cache)\n");
+    fprintf(f, "  --staged-gather      column blocks with the gather staged through device memory: the\n");
+    fprintf(f, "                       same bits as the default kernel, for the same kind of matrix\n");
     fprintf(f, "  --iterate            compute x := A*x repeatedly (y := A^N x); square A only\n");
     fprintf(f, "  --synthetic=SPEC     build A on the device instead of reading a file:\n");
     fprintf(f, "                       laplace2d:NX,NY | stencil27:NX,NY,NZ | random:ROWS,COLS,K[,SEED]\n");
@@ -166,6 +168,7 @@ static int parse_options(int argc, char **argv, struct options *o, int *bad)
             if (!strcmp(a, "--narrow-index")) { o->flags |= ELLSPMV_CUDA_NARROW_INDEX; continue; }
             if (!strcmp(a, "--wide-index")) { o->flags |= ELLSPMV_CUDA_WIDE_INDEX; continue; }
             if (!strcmp(a, "--column-blocked")) { o->flags |= ELLSPMV_CUDA_COLUMN_BLOCKED; continue; }
+            if (!strcmp(a, "--staged-gather")) { o->flags |= ELLSPMV_CUDA_STAGED_GATHER; continue; }
             if (!strncmp(a, "--rows-per-thread", 17) && (a[17] == '=' || a[17] == '\0')) {
                 int r;
                 if (!(v = optval(argc, argv, &i, "--rows-per-thread")) || to_int(v, &r)) return EINVAL;

@@ -74,6 +74,16 @@ enum {
      * zeros are dropped.  Keeps the regular layout as well (download, push
      * and separate-diagonal calls use it). */
     ELLSPMV_CUDA_COLUMN_BLOCKED = 1 << 7,
+    /* the bit-exact way to block by columns: store the column indices a
+     * second time sorted by (column block, slice); per SpMV, gather x block
+     * after block (each block's slice of x pinned in L2) into a flat stream
+     * in HBM, then run the reference's row loop -- slot 0..K-1, mul then
+     * add -- over the staged values (bulk-async copies into shared memory).
+     * Same bits as the default kernel, ~30 B instead of ~110 B of DRAM
+     * traffic per stored entry when x is much larger than L2; costs
+     * idx + 10 bytes of device memory per entry.  No-op when x fits one
+     * block or a slice's K*128 staged values do not fit shared memory. */
+    ELLSPMV_CUDA_STAGED_GATHER  = 1 << 17,
     /* rows handled per thread in the thread-per-row kernel: 0 = auto */
     ELLSPMV_CUDA_ROWS_PER_THREAD_SHIFT = 8,
     ELLSPMV_CUDA_ROWS_PER_THREAD_MASK  = 0x7 << 8,

@@ -310,3 +310,69 @@ def test_column_blocked_mode(lib, oracle, shape, bits, monkeypatch):
             if block_bytes == 1 << 30 and flags == E.COLUMN_BLOCKED:
                 assert bits_equal(y, want0)             # one block: falls back to the bit-exact kernel
             A.free()
+
+
+@pytest.mark.parametrize("shape", [(1, 40, 3), (1000, 1000, 7), (5003, 9001, 27), (300, 70000, 32), (4097, 4097, 64),
+                                   (777, 5000, 150)])
+@pytest.mark.parametrize("bits", [32, 64])
+def test_staged_gather_is_bit_exact(lib, oracle, shape, bits, monkeypatch):
+    """ELLSPMV_CUDA_STAGED_GATHER: column blocks with the gather staged through
+    device memory keep the reference's summation order, so the result is the
+    oracle's bit for bit -- with many small blocks, with one block (falls back to
+    the plain kernel), with R = 2/4 slices, wide indices and a separate diagonal."""
+    nr, nc, K = shape
+    dt = np.int32 if bits == 32 else np.int64
+    rng = np.random.default_rng(nr + nc + K + bits + 1)
+    ec, ea = rand_ell(rng, nr, nc, K, dt)
+    x = rng.standard_normal(nc)
+    y0 = rng.standard_normal(nr)
+    want0 = np.zeros(nr)
+    oracle.ellgemv(nr, want0, x, K, ec, ea)
+    want1 = y0.copy()
+    oracle.ellgemv(nr, want1, x, K, ec, ea)
+    want2 = want1.copy()
+    oracle.ellgemv(nr, want2, x, K, ec, ea)
+    for block_bytes in (256, 8 * 1024, 1 << 30):
+        monkeypatch.setenv("ELLSPMV_CUDA_BLOCK_BYTES", str(block_bytes))
+        for flags in (E.STAGED_GATHER, E.STAGED_GATHER | E.rows_per_thread(2), E.STAGED_GATHER | E.rows_per_thread(4),
+                      E.STAGED_GATHER | E.WIDE_INDEX, E.STAGED_GATHER | E.COLUMN_BLOCKED):
+            A = E.EllMatrix.upload(nr, nc, K, ec, ea, flags)
+            c2, a2 = A.download()
+            assert np.array_equal(c2, ec) and bits_equal(a2, ea)
+            y = y0.copy()
+            A.spmv(y, x, 2, E.ACCUMULATE)
+            assert bits_equal(y, want2), (shape, bits, block_bytes, flags)
+            y = rng.standard_normal(nr)
+            A.spmv(y, x, 1, E.OVERWRITE)
+            assert bits_equal(y, want0), (shape, bits, block_bytes, flags)
+            A.free()
+
+
+def test_staged_gather_tolerance_and_special_values(lib, oracle, monkeypatch):
+    """FMA on the staged path stays inside the dot-product bound; inf/NaN in x
+    propagate exactly like in the reference loop (no stored zero is dropped)."""
+    nr, nc, K = 3000, 4000, 9
+    rng = np.random.default_rng(99)
+    ec, ea = rand_ell(rng, nr, nc, K, np.int32)
+    ea[rng.random(ea.shape) < 0.2] = 0.0                # explicit zeros / padding-like entries
+    x = rng.standard_normal(nc)
+    monkeypatch.setenv("ELLSPMV_CUDA_BLOCK_BYTES", "4096")
+    want = np.zeros(nr)
+    oracle.ellgemv(nr, want, x, K, ec, ea)
+    A = E.EllMatrix.upload(nr, nc, K, ec, ea, E.STAGED_GATHER | E.FMA)
+    y = np.zeros(nr)
+    A.spmv(y, x, 1, E.OVERWRITE)
+    absprod = np.abs(ea.reshape(nr, K) * x[ec.reshape(nr, K)]).sum(axis=1)
+    assert np.all(np.abs(y - want) <= (K + 2) * 2.0 ** -53 * absprod + 1e-300)
+    A.free()
+    x[::7] = np.inf
+    x[3::11] = np.nan
+    x[5::13] = -0.0
+    want = np.zeros(nr)
+    with np.errstate(all="ignore"):
+        oracle.ellgemv(nr, want, x, K, ec, ea)
+    A = E.EllMatrix.upload(nr, nc, K, ec, ea, E.STAGED_GATHER)
+    y = np.zeros(nr)
+    A.spmv(y, x, 1, E.OVERWRITE)
+    assert bits_equal(y, want)
+    A.free()

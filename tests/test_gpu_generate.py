@@ -146,6 +146,17 @@ def test_full_size_random_ell_equals_csr(lib):
     Ae.spmv_device(ye, x, E.ACCUMULATE, s)
     torch.cuda.synchronize()
     Ae.free()
+    # the staged-gather path (column blocks, gather staged through HBM) must give the same bits
+    As = E.EllMatrix.generate(E.GEN_RANDOM, dims, seed=42, idx_bits=32, flags=E.STAGED_GATHER)
+    ysg = torch.zeros(dims[0], dtype=torch.float64, device="cuda")
+    As.spmv_device(ysg, x, E.ACCUMULATE, s)
+    torch.cuda.synchronize()
+    assert torch.equal(ye, ysg)
+    As.spmv_device(ysg, x, E.OVERWRITE, s)
+    torch.cuda.synchronize()
+    assert torch.equal(ye, ysg)
+    As.free()
+    del ysg
     Ac = E.CsrMatrix.generate(E.GEN_RANDOM, dims, seed=42, idx_bits=32)
     yc = torch.zeros(dims[0], dtype=torch.float64, device="cuda")
     Ac.spmv_device(yc, x, E.ACCUMULATE, s)

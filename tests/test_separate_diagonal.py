@@ -113,8 +113,9 @@ def test_gpu_golden(lib, name, bits):
 @pytest.mark.gpu
 @pytest.mark.parametrize("bits", [32, 64])
 @pytest.mark.parametrize("shape", [(3000, 3000, 200000), (700, 900, 9000), (1, 1, 1)])
-def test_gpu_vs_oracle(lib, oracle, bits, shape):
+def test_gpu_vs_oracle(lib, oracle, bits, shape, monkeypatch):
     import ellspmv_b200 as E
+    monkeypatch.setenv("ELLSPMV_CUDA_BLOCK_BYTES", "2048")   # several column blocks for the staged-gather pass
     nr, nc, nnz = shape
     dt = np.int32 if bits == 32 else np.int64
     rng = np.random.default_rng(nr + nnz + bits)
@@ -130,14 +131,15 @@ def test_gpu_vs_oracle(lib, oracle, bits, shape):
         oracle.ellgemvsd(nr, want, x, K, ec, ea, ad, order)
         want0 = np.zeros(nr)
         oracle.ellgemvsd(nr, want0, x, K, ec, ea, ad, order)
-        A = E.EllMatrix.upload(nr, nc, K, ec, ea)
-        A.set_diagonal(ad, order)
-        y = y0.copy()
-        A.spmv(y, x, 1, E.ACCUMULATE)
-        assert bits_equal(y, want)
-        A.spmv(y, x, 1, E.OVERWRITE)
-        assert bits_equal(y, want0)
-        A.free()
+        for flags in (0, E.STAGED_GATHER):
+            A = E.EllMatrix.upload(nr, nc, K, ec, ea, flags)
+            A.set_diagonal(ad, order)
+            y = y0.copy()
+            A.spmv(y, x, 1, E.ACCUMULATE)
+            assert bits_equal(y, want), (order, flags)
+            A.spmv(y, x, 1, E.OVERWRITE)
+            assert bits_equal(y, want0), (order, flags)
+            A.free()
     # tolerance modes
     absprod = np.abs(ea.reshape(nr, K) * x[ec.reshape(nr, K)]).sum(axis=1) + np.abs(ad[:nr] * x[:nr])
     for flags in (E.FMA, E.KERNEL_WARP):

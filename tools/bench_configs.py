@@ -61,6 +61,7 @@ def main():
         for R in (1, 2, 4):
             variants.append((f"bulk-async R={R}", E.KERNEL_THREAD | E.rows_per_thread(R) | E.variant(1)))
         if name == "c4":
+            variants.append(("staged-gather", E.KERNEL_THREAD | E.STAGED_GATHER))
             variants.append(("column-blocked", E.KERNEL_THREAD | E.COLUMN_BLOCKED))
             variants.append(("column-blocked fma", E.KERNEL_THREAD | E.COLUMN_BLOCKED | E.FMA))
         variants.append(("thread R=4 fma", E.KERNEL_THREAD | E.rows_per_thread(4) | E.FMA))
