@@ -225,7 +225,7 @@ int launch(ellspmv_cuda_matrix *A, double *y_dev, const double *x_dev, int beta,
     if (push) args.push = *push; else args.push.num_peers = 0;
     if (A->sg && !push && slice_begin == 0 && num_slices == A->lay.num_slices) {
         ELL_CK(sg_spmv(A->sg, A->cfg.fma, A->vals, x_dev, y_dev, A->d_ad, A->sd_order, A->lay.num_rows,
-                       A->num_columns, A->row_begin, beta, stream));
+                       A->row_begin, beta, stream));
         A->launches += sg_launches(A->sg);
         return 0;
     }

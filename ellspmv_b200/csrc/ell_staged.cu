@@ -12,9 +12,9 @@
 //
 //   phase 1 (gather): the column indices are stored a second time, sorted by
 //     (column block, slice).  One launch per column block walks its run of
-//     indices -- a flat, perfectly coalesced stream -- gathers x[col] while that
-//     block's slice of x (<= 48 MB) is pinned in L2 by an access-policy window,
-//     and writes the gathered values as a flat stream xg.
+//     indices -- a flat, perfectly coalesced stream -- gathers x[col] -- the live
+//     part of x is then that block's slice (<= 48 MB), which stays in L2 -- and
+//     writes the gathered values as a flat stream xg.
 //   phase 2 (sum): one CTA per slice.  For a slice the gathered values are nb
 //     contiguous runs of xg (one per column block); one thread fetches them into
 //     shared memory with bulk-async copies (cp.async.bulk + mbarrier, SASS
@@ -22,6 +22,16 @@
 //     stream in the sliced-ELL layout says where entry (row, slot) landed, and
 //     every thread then runs the reference's loop over ITS row, slot 0..K-1,
 //     mul then add: the same roundings as ell_thread_kernel, bit for bit.
+//
+// Measured on BASELINE config 4 (profiles/r1_staged_gather.md): 13.6 ms against
+// 28.2 ms for the direct gather, same bits.  Phase 2 runs at 103 % of the measured
+// HBM copy peak (4.4 ms, ncu DRAM traffic = its algorithmic 29.7 GB).  Phase 1
+// (9.2 ms) is bound by the SM -> L2 request port: every gathered value is its own
+// 128-byte-line request (l1tex2xbar request cycles 91 % busy, ~175 G gathers/s),
+// HBM only 28 % busy.  Running phase 2 of one row panel next to phase 1 of the
+// next (two streams, priorities) was tried and LOSES (14.7-17.7 ms): not kept.
+// An L2 persisting window over the x block changes nothing here (13.62 ms with
+// and without): not used.
 //
 // Bytes per stored entry: phase 1 reads idx (4/8) and writes 8; phase 2 reads
 // 8 (value) + 2 (pos) + 8 (xg) -> 30 B for 32-bit indices, against ~112 B of
@@ -48,11 +58,14 @@ struct SgMatrix {
     long long *seg = nullptr;                 // num_blocks * num_slices + 1 segment starts
     unsigned short *pos = nullptr;            // sliced-ELL layout: index into the slice's staging buffer
     double *xg = nullptr;                     // gathered x, same order as gcols
-    long long block_start[kSgMaxBlocks + 1];  // host copy of seg[b * num_slices]
+    long long run_start[kSgMaxBlocks + 1];    // host copy: where column block b's run starts (seg[b * num_slices])
     int64_t bytes = 0;
-    size_t smem = 0;
-    bool persist = false;
+    size_t smem = 0;                          // dynamic shared memory of phase 2
 };
+
+// Segment (slice s, block b) starts at seg[b * num_slices + s]: blocks outermost, so
+// that a block's run and a segment's end (the next index) are both contiguous.
+__host__ __device__ __forceinline__ int64_t sg_seg_index(int64_t s, int b, int64_t ns) { return (int64_t)b * ns + s; }
 
 void sg_free(SgMatrix *sg)
 {
@@ -76,7 +89,7 @@ sg_count_kernel(const IdxT *__restrict__ cols, int S, int K, int nb, int64_t blo
     const IdxT *c = cols + s * S * (int64_t)K;
     for (int i = threadIdx.x; i < S * K; i += blockDim.x) atomicAdd(&cnt[(int)((int64_t)c[i] / block_cols)], 1);
     __syncthreads();
-    for (int b = threadIdx.x; b < nb; b += blockDim.x) sizes[(int64_t)b * ns + s] = (cnt[b] + 1) & ~1;
+    for (int b = threadIdx.x; b < nb; b += blockDim.x) sizes[sg_seg_index(s, b, ns)] = (cnt[b] + 1) & ~1;
 }
 
 template <typename IdxT>
@@ -90,8 +103,9 @@ sg_fill_kernel(const IdxT *__restrict__ cols, int S, int K, int nb, int64_t bloc
     const int64_t s = blockIdx.x;
     for (int b = threadIdx.x; b < nb; b += blockDim.x) {
         cursor[b] = 0;
-        start[b] = seg[(int64_t)b * ns + s];
-        prefix[b] = (int)(seg[(int64_t)b * ns + s + 1] - start[b]);
+        const int64_t i = sg_seg_index(s, b, ns);
+        start[b] = seg[i];
+        prefix[b] = (int)(seg[i + 1] - start[b]);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -129,13 +143,13 @@ static cudaError_t sg_build_typed(SgMatrix *sg, const IdxT *cols, cudaStream_t s
     if (e == cudaSuccess) e = cudaMalloc(&temp, temp_bytes + 16);
     if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(temp, temp_bytes, sizes, sg->seg, n + 1, stream);
     for (int b = 0; b <= nb && e == cudaSuccess; b++)
-        e = cudaMemcpyAsync(&sg->block_start[b], sg->seg + (int64_t)b * ns, 8, cudaMemcpyDeviceToHost, stream);
+        e = cudaMemcpyAsync(&sg->run_start[b], sg->seg + (int64_t)b * ns, 8, cudaMemcpyDeviceToHost, stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
     cudaFree(sizes);
     cudaFree(temp);
     if (e != cudaSuccess) return e;
-    sg->total = sg->block_start[nb];
-    const size_t ne = (size_t)sg->total + 8;                 // slack: phase 1 works in aligned groups of 4
+    sg->total = sg->run_start[nb];
+    const size_t ne = (size_t)sg->total + 8;                 // slack: phase 1 loads indices in aligned groups of 4
     const size_t nk = (size_t)ns * S * K;
     if ((e = cudaMalloc(&sg->gcols, ne * sizeof(IdxT))) != cudaSuccess) return e;
     if ((e = cudaMalloc(&sg->pos, nk * 2)) != cudaSuccess) return e;
@@ -177,17 +191,6 @@ cudaError_t sg_build(SgMatrix **out, int idx_bits, const void *cols, const EllLa
                                    : sg_build_typed<int32_t>(sg, (const int32_t *)cols, stream);
     if (e == cudaSuccess) e = sg_prepare_kernels();
     if (e != cudaSuccess) { sg_free(sg); return e; }
-    int dev = 0;
-    cudaDeviceProp prop;
-    if (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&prop, dev) == cudaSuccess) {
-        const size_t want = (size_t)sg->block_cols * 8;
-        if (prop.persistingL2CacheMaxSize > 0 && want <= (size_t)prop.accessPolicyMaxWindowSize &&
-            !getenv("ELLSPMV_CUDA_NO_PERSIST")) {
-            const size_t lim = want < (size_t)prop.persistingL2CacheMaxSize ? want : (size_t)prop.persistingL2CacheMaxSize;
-            if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, lim) == cudaSuccess) sg->persist = true;
-            cudaGetLastError();
-        }
-    }
     *out = sg;
     return cudaSuccess;
 }
@@ -208,18 +211,18 @@ __device__ __forceinline__ void ld4(const int64_t *p, int64_t (&c)[4])
 template <typename IdxT>
 __global__ void __launch_bounds__(256)
 sg_gather_kernel(const IdxT *__restrict__ gcols, const double *__restrict__ x, double *__restrict__ xg,
-                 int64_t first_group, int64_t num_groups)
+                 int64_t lo, int64_t hi /* run [lo, hi), both even */)
 {
-    const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (g >= num_groups) return;
-    const int64_t e = (first_group + g) * 4;
+    const int64_t e = ((lo >> 2) + blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * 4;
+    if (e >= hi) return;
     int64_t c[4];
-    ld4(gcols + e, c);
-    double v[4];
-#pragma unroll
-    for (int i = 0; i < 4; i++) v[i] = __ldg(x + c[i]);
-    __stcs(reinterpret_cast<double2 *>(xg + e), make_double2(v[0], v[1]));
-    __stcs(reinterpret_cast<double2 *>(xg + e) + 1, make_double2(v[2], v[3]));
+    ld4(gcols + e, c);                                   // aligned group of 4 (the arrays carry slack)
+    const bool on0 = e >= lo, on1 = e + 2 < hi;          // which of the two pairs belong to this run
+    double v[4] = {0.0, 0.0, 0.0, 0.0};
+    if (on0) { v[0] = __ldg(x + c[0]); v[1] = __ldg(x + c[1]); }
+    if (on1) { v[2] = __ldg(x + c[2]); v[3] = __ldg(x + c[3]); }
+    if (on0) __stcs(reinterpret_cast<double2 *>(xg + e), make_double2(v[0], v[1]));
+    if (on1) __stcs(reinterpret_cast<double2 *>(xg + e) + 1, make_double2(v[2], v[3]));
 }
 
 // ---- phase 2: the reference's row loop over staged x values ------------------------
@@ -229,8 +232,8 @@ template <bool FMA>
 __global__ void
 sg_sum_kernel(const double *__restrict__ vals, const unsigned short *__restrict__ pos, const long long *__restrict__ seg,
               const double *__restrict__ xg, const double *__restrict__ x, double *__restrict__ y,
-              const double *__restrict__ ad, int sd_order, int64_t num_rows, int64_t row_begin, int64_t ns, int nb,
-              int K, int beta)
+              const double *__restrict__ ad, int sd_order, int64_t num_rows, int64_t row_begin, int64_t ns,
+              int nb, int K, int beta)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem);
@@ -242,9 +245,10 @@ sg_sum_kernel(const double *__restrict__ vals, const unsigned short *__restrict_
     __shared__ long long s_o0[kSgMaxBlocks];
     __shared__ int s_len[kSgMaxBlocks];
     if (tid < nb) {
-        const long long o = seg[(int64_t)tid * ns + s];
+        const int64_t i = sg_seg_index(s, tid, ns);
+        const long long o = seg[i];
         s_o0[tid] = o;
-        s_len[tid] = (int)(seg[(int64_t)tid * ns + s + 1] - o);
+        s_len[tid] = (int)(seg[i + 1] - o);
     }
     __syncthreads();
     if (tid == 0) {
@@ -341,35 +345,20 @@ static cudaError_t sg_prepare_kernels()
 }
 
 cudaError_t sg_spmv(const SgMatrix *sg, bool fma, const double *vals, const double *x, double *y, const double *ad,
-                    int sd_order, int64_t num_rows, int64_t num_columns, int64_t row_begin, int beta,
-                    cudaStream_t stream)
+                    int sd_order, int64_t num_rows, int64_t row_begin, int beta, cudaStream_t stream)
 {
-    // phase 1, block after block in stream order
+    // phase 1, one launch per column block in stream order: while block b's run is
+    // gathered, the live part of x is that block's slice, which stays in L2 by itself
     for (int b = 0; b < sg->num_blocks; b++) {
-        const int64_t g0 = sg->block_start[b] / 4, g1 = (sg->block_start[b + 1] + 3) / 4;
-        if (g1 <= g0) continue;
-        cudaLaunchConfig_t lc = {};
-        lc.gridDim = dim3((unsigned)((g1 - g0 + 255) / 256));
-        lc.blockDim = dim3(256);
-        lc.stream = stream;
-        cudaLaunchAttribute attr[1];
-        lc.attrs = attr;
-        lc.numAttrs = 0;
-        if (sg->persist) {
-            const int64_t c0 = (int64_t)b * sg->block_cols;
-            int64_t c1 = c0 + sg->block_cols;
-            if (c1 > num_columns) c1 = num_columns;
-            attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
-            attr[0].val.accessPolicyWindow.base_ptr = const_cast<double *>(x + c0);
-            attr[0].val.accessPolicyWindow.num_bytes = (size_t)(c1 - c0) * 8;
-            attr[0].val.accessPolicyWindow.hitRatio = 1.0f;
-            attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-            attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-            lc.numAttrs = 1;
-        }
-        cudaError_t e = sg->idx_bits == 64
-            ? cudaLaunchKernelEx(&lc, sg_gather_kernel<int64_t>, (const int64_t *)sg->gcols, x, sg->xg, g0, g1 - g0)
-            : cudaLaunchKernelEx(&lc, sg_gather_kernel<int32_t>, (const int32_t *)sg->gcols, x, sg->xg, g0, g1 - g0);
+        const int64_t lo = sg->run_start[b], hi = sg->run_start[b + 1];
+        if (hi <= lo) continue;
+        const int64_t groups = (hi + 3) / 4 - lo / 4;
+        const unsigned grid = (unsigned)((groups + 255) / 256);
+        if (sg->idx_bits == 64)
+            sg_gather_kernel<int64_t><<<grid, 256, 0, stream>>>((const int64_t *)sg->gcols, x, sg->xg, lo, hi);
+        else
+            sg_gather_kernel<int32_t><<<grid, 256, 0, stream>>>((const int32_t *)sg->gcols, x, sg->xg, lo, hi);
+        cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }
     // phase 2
