@@ -60,6 +60,18 @@ def algorithmic_bytes(rows: int, ncols: int, K: int, idx_bytes: int, y_rmw: bool
     return rows * K * (8 + idx_bytes) + 8 * ncols + 8 * rows * (2 if y_rmw else 1)
 
 
+def kernel_description(flags: int, fma: bool) -> str:
+    """Which of the library's ELL kernels the upload flags select (include/ellspmv_cuda.h)."""
+    arith = "fma (tolerance)" if fma else "mul-then-add"
+    if flags & (1 << 17):
+        return f"staged gather: column blocks, gather staged through HBM, then thread-per-row, {arith}" + ("" if fma else " (bit-exact)")
+    if flags & (1 << 7):
+        return f"column-blocked, per-block partial sums, {arith} (tolerance)"
+    if (flags & 0xf) == 2:
+        return f"sub-warp-per-row + shuffle reduction, {arith} (tolerance)"
+    return f"thread-per-row, {arith}" + ("" if fma else " (bit-exact)")
+
+
 def measured_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -374,7 +386,7 @@ def main_ours(args, rank: int, local_rank: int, world: int):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload, "rows_per_gpu": rows, "rowsize": K, "idx_bits": idx_bits,
                    "mode": mode_name, "rows_per_thread": info.rows_per_thread, "slice_rows": info.slice_rows,
-                   "kernel": "thread-per-row, mul-then-add (bit-exact)" if not info.fma else "thread-per-row, fma",
+                   "kernel": kernel_description(flags, bool(info.fma)),
                    "l2": f"inputs larger than L2 ({rows * K * (8 + idx_bits // 8) / 1e9:.1f} GB matrix per GPU vs 126 MB L2), no flush needed",
                    "parallelism": f"rowshard{world}"},
         "gbs": round(achieved * world, 1),

@@ -223,9 +223,9 @@ int launch(ellspmv_cuda_matrix *A, double *y_dev, const double *x_dev, int beta,
     args.sd_order = A->sd_order;
     if (num_slices < 0) num_slices = A->lay.num_slices - slice_begin;
     if (push) args.push = *push; else args.push.num_peers = 0;
-    if (A->sg && !push && slice_begin == 0 && num_slices == A->lay.num_slices) {
+    if (A->sg && slice_begin == 0 && num_slices == A->lay.num_slices) {
         ELL_CK(sg_spmv(A->sg, A->cfg.fma, A->vals, x_dev, y_dev, A->d_ad, A->sd_order, A->lay.num_rows,
-                       A->row_begin, beta, stream));
+                       A->row_begin, beta, push, stream));
         A->launches += sg_launches(A->sg);
         return 0;
     }

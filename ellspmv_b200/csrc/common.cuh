@@ -151,7 +151,8 @@ struct SgMatrix;
 cudaError_t sg_build(SgMatrix **out, int idx_bits, const void *cols, const EllLayout &lay, int64_t num_columns,
                      int64_t target_x_bytes, cudaStream_t stream);
 cudaError_t sg_spmv(const SgMatrix *sg, bool fma, const double *vals, const double *x, double *y, const double *ad,
-                    int sd_order, int64_t num_rows, int64_t row_begin, int beta, cudaStream_t stream);
+                    int sd_order, int64_t num_rows, int64_t row_begin, int beta, const PushTargets *push,
+                    cudaStream_t stream);
 void sg_free(SgMatrix *sg);
 int64_t sg_bytes(const SgMatrix *sg);
 int sg_launches(const SgMatrix *sg);

@@ -233,7 +233,7 @@ __global__ void
 sg_sum_kernel(const double *__restrict__ vals, const unsigned short *__restrict__ pos, const long long *__restrict__ seg,
               const double *__restrict__ xg, const double *__restrict__ x, double *__restrict__ y,
               const double *__restrict__ ad, int sd_order, int64_t num_rows, int64_t row_begin, int64_t ns,
-              int nb, int K, int beta)
+              int nb, int K, int beta, const PushTargets push)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem);
@@ -334,7 +334,13 @@ sg_sum_kernel(const double *__restrict__ vals, const unsigned short *__restrict_
     }
     if (!live) return;
     if (ad && !sd_order) acc = __dadd_rn(dx, acc);
-    y[row] = __dadd_rn(yold, acc);
+    const double out = __dadd_rn(yold, acc);
+    y[row] = out;
+    // fused exchange, as in ell_thread_kernel: the fresh entry goes straight into the
+    // next-x vector of every peer that references this row
+    const int64_t g = row_begin + row;
+    for (int p = 0; p < push.num_peers; p++)
+        if (g >= push.row_lo[p] && g < push.row_hi[p]) push.x[p][g] = out;
 }
 
 static cudaError_t sg_prepare_kernels()
@@ -345,8 +351,11 @@ static cudaError_t sg_prepare_kernels()
 }
 
 cudaError_t sg_spmv(const SgMatrix *sg, bool fma, const double *vals, const double *x, double *y, const double *ad,
-                    int sd_order, int64_t num_rows, int64_t row_begin, int beta, cudaStream_t stream)
+                    int sd_order, int64_t num_rows, int64_t row_begin, int beta, const PushTargets *push,
+                    cudaStream_t stream)
 {
+    PushTargets pt;
+    if (push) pt = *push; else pt.num_peers = 0;
     // phase 1, one launch per column block in stream order: while block b's run is
     // gathered, the live part of x is that block's slice, which stays in L2 by itself
     for (int b = 0; b < sg->num_blocks; b++) {
@@ -365,7 +374,7 @@ cudaError_t sg_spmv(const SgMatrix *sg, bool fma, const double *vals, const doub
     auto kernel = fma ? sg_sum_kernel<true> : sg_sum_kernel<false>;
     kernel<<<(unsigned)sg->num_slices, sg->slice_rows, sg->smem, stream>>>(
         vals, sg->pos, sg->seg, sg->xg, x, y, ad, sd_order, num_rows, row_begin, sg->num_slices, sg->num_blocks,
-        sg->rowsize, beta);
+        sg->rowsize, beta, pt);
     return cudaGetLastError();
 }
 

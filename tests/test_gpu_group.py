@@ -24,7 +24,11 @@ def ngpus():
     (E.GEN_LAPLACE2D, "laplace2d", (61, 100), (0.5, 0.125), 32),
     (E.GEN_STENCIL27, "stencil27", (23, 9, 11), (0.5, 1.0 / 52), 64),
     (E.GEN_RANDOM, "random", (5003, 5003, 9), (0.0, 0.0), 32)])
-def test_group_equals_oracle(lib, oracle, kind, name, dims, vals, bits):
+@pytest.mark.parametrize("flags", [0, E.STAGED_GATHER])
+def test_group_equals_oracle(lib, oracle, kind, name, dims, vals, bits, flags, monkeypatch):
+    # STAGED_GATHER: every shard gathers x column block by column block (several blocks at this
+    # size with 4 KB per block) and the fused push runs out of the staged sum kernel
+    monkeypatch.setenv("ELLSPMV_CUDA_BLOCK_BYTES", "4096")
     n = ngpus()
     K, ncols, ec, ea, _ = oracle.gen_ell(name, dims, vals, seed=42, bits=bits)
     rows = len(ea) // K
@@ -34,8 +38,8 @@ def test_group_equals_oracle(lib, oracle, kind, name, dims, vals, bits):
     want = y0.copy()
     for _ in range(3):
         oracle.ellgemv(rows, want, x, K, ec, ea)
-    for A in (E.EllMatrix.upload(rows, ncols, K, ec, ea, num_gpus=n),
-              E.EllMatrix.generate(kind, dims, vals, 42, bits, num_gpus=n)):
+    for A in (E.EllMatrix.upload(rows, ncols, K, ec, ea, flags, num_gpus=n),
+              E.EllMatrix.generate(kind, dims, vals, 42, bits, flags=flags, num_gpus=n)):
         i = A.info()
         assert (i.num_gpus, i.num_rows, i.rowsize) == (n, rows, K)
         assert (i.min_col, i.max_col) == (ec.min(), ec.max())
