@@ -31,6 +31,7 @@ L2_PERSIST_X = 1 << 5
 NARROW_INDEX = 1 << 6
 COLUMN_BLOCKED = 1 << 7
 STAGED_GATHER = 1 << 17
+NO_PATTERN = 1 << 18
 WIDE_INDEX = 1 << 16
 ROWS_PER_THREAD_SHIFT = 8
 VARIANT_SHIFT = 12
@@ -60,7 +61,7 @@ class Info(C.Structure):
         ("idx_width_bits", C.c_int), ("dev_idx_bits", C.c_int), ("slice_rows", C.c_int),
         ("rows_per_thread", C.c_int), ("kernel", C.c_int), ("fma", C.c_int), ("device", C.c_int),
         ("device_bytes", C.c_int64), ("min_col", C.c_int64), ("max_col", C.c_int64),
-        ("launches", C.c_int64), ("num_gpus", C.c_int),
+        ("launches", C.c_int64), ("num_gpus", C.c_int), ("pattern_rows", C.c_int64),
     ]
 
 

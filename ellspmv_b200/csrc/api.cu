@@ -132,6 +132,8 @@ void warm_kernels(ellspmv_cuda_matrix *A)
     args.num_rows = 0;
     args.rowsize = A->lay.rowsize;
     args.beta = 1;
+    args.patid = A->pat.patid;
+    args.pat = A->pat.pat;
     if (launch_ell_spmv(A->cfg, args, 1, A->stream) == cudaSuccess) cudaStreamSynchronize(A->stream);
     cudaGetLastError();
 }
@@ -147,6 +149,21 @@ int finish_minmax(ellspmv_cuda_matrix *A)
     if (A->max_col >= A->num_columns || (A->max_col >= 0 && A->min_col < 0))
         ELL_FAIL(EINVAL, "column index out of range: [%lld, %lld] with %lld columns",
                  mm[0], mm[1], (long long)A->num_columns);
+    return 0;
+}
+
+// Offset patterns (pattern.cu): groups of 32 rows whose column indices are row + d[l] stop
+// reading the index stream.  On by default for the thread-per-row kernel with one row per
+// thread; ELLSPMV_CUDA_NO_PATTERN turns it off.
+int build_patterns(ellspmv_cuda_matrix *A)
+{
+    if ((A->flags & ELLSPMV_CUDA_NO_PATTERN) || A->cfg.kernel != ELLSPMV_CUDA_KERNEL_THREAD ||
+        A->cfg.rows_per_thread != 1 || A->lay.num_rows <= 0 || A->lay.rowsize <= 0)
+        return 0;
+    cudaError_t ce = pattern_build(&A->pat, A->dev_idx_bits, A->cols, A->lay, A->row_begin, A->stream);
+    if (ce != cudaSuccess) { set_last_error("offset patterns: %s", cudaGetErrorString(ce)); return cuda_to_errno(ce); }
+    A->device_bytes += A->pat.bytes;
+    if (A->pat.patid) warm_kernels(A);
     return 0;
 }
 
@@ -221,6 +238,8 @@ int launch(ellspmv_cuda_matrix *A, double *y_dev, const double *x_dev, int beta,
     args.slice_begin = slice_begin;
     args.ad = A->d_ad;
     args.sd_order = A->sd_order;
+    args.patid = A->pat.patid;
+    args.pat = A->pat.pat;
     if (num_slices < 0) num_slices = A->lay.num_slices - slice_begin;
     if (push) args.push = *push; else args.push.num_peers = 0;
     if (A->sg && slice_begin == 0 && num_slices == A->lay.num_slices) {
@@ -365,6 +384,7 @@ void ellspmv_cuda_free(ellspmv_cuda_matrix *A)
     if (A->cols) cudaFree(A->cols);
     if (A->d_minmax) cudaFree(A->d_minmax);
     if (A->d_ad) cudaFree(A->d_ad);
+    pattern_free(&A->pat);
     if (A->cb) cb_free(A->cb);
     if (A->sg) sg_free(A->sg);
     if (A->d_x) cudaFree(A->d_x);
@@ -425,6 +445,7 @@ int ellspmv_cuda_upload_shard(
             return fail(cuda_to_errno(ce));
         }
         if ((err = finish_minmax(A))) return fail(err);
+        if ((err = build_patterns(A))) return fail(err);
         if ((err = build_column_blocks(A))) return fail(err);
     } else {
         cudaError_t ce = cudaStreamSynchronize(A->stream);
@@ -490,6 +511,7 @@ int ellspmv_cuda_upload_coo(
         else if (bad) { set_last_error("upload_coo: column index outside [1, %lld]", (long long)num_columns); err = EINVAL; }
     }
     if (!err && A->lay.num_rows > 0 && A->lay.rowsize > 0) err = finish_minmax(A);
+    if (!err) err = build_patterns(A);
     if (!err) err = build_column_blocks(A);
     coo_to_ell_release(job);
     cudaFree(d_ri); cudaFree(d_ci); cudaFree(d_a);
@@ -534,6 +556,7 @@ int ellspmv_cuda_generate(
                                          A->lay, row_begin, A->d_minmax, A->stream);
         if (ce != cudaSuccess) { set_last_error("generate: %s", cudaGetErrorString(ce)); return fail(cuda_to_errno(ce)); }
         if ((err = finish_minmax(A))) return fail(err);
+        if ((err = build_patterns(A))) return fail(err);
         if ((err = build_column_blocks(A))) return fail(err);
     } else {
         cudaStreamSynchronize(A->stream);
@@ -634,6 +657,7 @@ int ellspmv_cuda_get_info(const ellspmv_cuda_matrix *A, ellspmv_cuda_info *info)
     info->max_col = A->max_col;
     info->launches = A->launches;
     info->num_gpus = 1;
+    info->pattern_rows = A->pat.covered * 32;
     return 0;
 }
 

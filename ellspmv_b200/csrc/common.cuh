@@ -38,6 +38,7 @@ int  cuda_to_errno(cudaError_t e);
 
 constexpr int kBlockThreads = 128;  // threads per CTA of the thread-per-row kernels
 constexpr int kMaxPeers = 8;
+constexpr int kMaxPatterns = 16;    // offset-pattern dictionary size (pattern.cu)
 
 // ---- sliced-ELL device layout -------------------------------------------
 // Rows are grouped into slices of S = kBlockThreads * R rows (R = rows per
@@ -82,6 +83,8 @@ struct EllSpmvArgs {
     const double *ad;       // separately stored diagonal of the shard rows, or NULL
     int           sd_order; // 0: y += ad*x + yi (ellgemvsd); 1: sum starts at ad*x (ellgemv16sd)
     PushTargets   push;
+    const unsigned char *patid; // offset patterns (pattern.cu): one id per 32 rows, 0xff = explicit indices; or NULL
+    const long long     *pat;   // dictionary [kMaxPatterns][K] of column offsets relative to the GLOBAL row
 };
 
 struct EllLaunchCfg {
@@ -134,6 +137,18 @@ cudaError_t generate_sliced(int kind, const int64_t dims[3], const double vals[2
 cudaError_t generate_csr_random(const int64_t dims[3], uint64_t seed, int idx_bits,
                                 int64_t *rowptr, void *cols, double *vals, cudaStream_t stream);
 cudaError_t init_minmax(long long *minmax, cudaStream_t stream);
+
+// ---- offset patterns: groups of 32 rows whose column indices are row + d[l] (pattern.cu) ----
+struct PatternSet {
+    unsigned char *patid = nullptr;   // device: padded_rows / 32 ids
+    long long *pat = nullptr;         // device: kMaxPatterns * K offsets
+    int num_patterns = 0;
+    int64_t groups = 0, covered = 0;  // groups of 32 rows: all / patterned
+    int64_t bytes = 0;
+};
+cudaError_t pattern_build(PatternSet *ps, int idx_bits, const void *cols, const EllLayout &lay, int64_t row_begin,
+                          cudaStream_t stream);
+void pattern_free(PatternSet *ps);
 
 // ---- column-blocked ELL (ell_blocked.cu) ----------------------------------------
 struct CbMatrix;

@@ -143,7 +143,10 @@ template <int R> struct Batch { static constexpr int U = (R == 4) ? 4 : (R == 2 
 // ---- thread-per-row kernel ------------------------------------------------
 // KU > 0: K known at compile time (fully unrolled); KU == 0: run-time K.
 // YVEC: y (and every push target) may be accessed with R-wide vectors.
-template <typename IdxT, int R, int KU, bool FMA, bool YVEC, int G>
+// PAT (R = 1 only): the handle has offset patterns (pattern.cu).  A warp whose 32 rows
+// share one offset vector d[] computes col = row + d[l] from the dictionary (a uniform
+// load that lives in L1) and never touches its 128/256-byte lines of the index stream.
+template <typename IdxT, int R, int KU, bool FMA, bool YVEC, int G, bool PAT>
 __global__ void __launch_bounds__(kBlockThreads)
 ell_thread_kernel(const EllSpmvArgs a)
 {
@@ -158,6 +161,18 @@ ell_thread_kernel(const EllSpmvArgs a)
     const double *vp = a.vals + base;
     const IdxT *cp = reinterpret_cast<const IdxT *>(a.cols) + base;
     const double *__restrict__ x = a.x;
+
+    // warp-uniform: this warp's pattern (or none); rowg = the row's global index
+    const long long *__restrict__ prow = nullptr;
+    const int64_t rowg = a.row_begin + row0;
+    if (PAT) {
+        const unsigned pid = __ldg(a.patid + (row0 >> 5));
+        if (pid != 0xffu) prow = a.pat + (int64_t)pid * K;
+    }
+    auto load_cols = [&](int l, int64_t (&c)[R]) {
+        if (PAT && prow) c[0] = rowg + __ldg(prow + l);
+        else Cols<IdxT, R>::ld(cp + (int64_t)l * S, c);
+    };
 
     const bool full = row0 + R <= a.num_rows;
     double yold[R];
@@ -202,7 +217,7 @@ ell_thread_kernel(const EllSpmvArgs a)
 #pragma unroll
             for (int u = 0; u < U; u++) if (l0 + u < KU) {
                 Vals<R>::ld(vp + (int64_t)(l0 + u) * S, v[u]);
-                Cols<IdxT, R>::ld(cp + (int64_t)(l0 + u) * S, c[u]);
+                load_cols(l0 + u, c[u]);
             }
 #pragma unroll
             for (int u = 0; u < U; u++) if (l0 + u < KU) {
@@ -223,7 +238,7 @@ ell_thread_kernel(const EllSpmvArgs a)
 #pragma unroll
             for (int u = 0; u < U; u++) {
                 Vals<R>::ld(vp + (int64_t)(l0 + u) * S, v[u]);
-                Cols<IdxT, R>::ld(cp + (int64_t)(l0 + u) * S, c[u]);
+                load_cols(l0 + u, c[u]);
             }
 #pragma unroll
             for (int u = 0; u < U; u++) {
@@ -240,7 +255,7 @@ ell_thread_kernel(const EllSpmvArgs a)
         for (; l0 < K; l0++) {
             double v[R]; int64_t c[R];
             Vals<R>::ld(vp + (int64_t)l0 * S, v);
-            Cols<IdxT, R>::ld(cp + (int64_t)l0 * S, c);
+            load_cols(l0, c);
 #pragma unroll
             for (int r = 0; r < R; r++) acc[r] = madd<FMA>(acc[r], v[r], ldx<G>(x + c[r]));
         }
@@ -336,8 +351,14 @@ ell_subwarp_kernel(const EllSpmvArgs a, int slice_rows)
 template <typename IdxT, int R, int KU, bool FMA, int G>
 static cudaError_t launch_thread_g(const EllSpmvArgs &args, bool yvec, cudaLaunchConfig_t &lc)
 {
-    if (yvec) return cudaLaunchKernelEx(&lc, ell_thread_kernel<IdxT, R, KU, FMA, true, G>, args);
-    return cudaLaunchKernelEx(&lc, ell_thread_kernel<IdxT, R, KU, FMA, false, G>, args);
+    if (R == 1 && args.patid) {
+        // offset patterns exist only for one row per thread (a warp = one group of 32 rows)
+        constexpr bool P = R == 1;
+        if (yvec) return cudaLaunchKernelEx(&lc, ell_thread_kernel<IdxT, R, KU, FMA, true, G, P>, args);
+        return cudaLaunchKernelEx(&lc, ell_thread_kernel<IdxT, R, KU, FMA, false, G, P>, args);
+    }
+    if (yvec) return cudaLaunchKernelEx(&lc, ell_thread_kernel<IdxT, R, KU, FMA, true, G, false>, args);
+    return cudaLaunchKernelEx(&lc, ell_thread_kernel<IdxT, R, KU, FMA, false, G, false>, args);
 }
 
 template <typename IdxT, int R, int KU, bool FMA>

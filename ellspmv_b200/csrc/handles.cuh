@@ -33,6 +33,7 @@ struct ellspmv_cuda_matrix {
     long long *d_minmax = nullptr;
     double *d_ad = nullptr;                  // separately stored diagonal (shard rows), optional
     int sd_order = 0;
+    ellspmv::PatternSet pat;                 // offset patterns of the index stream (pattern.cu), optional
     ellspmv::SgMatrix *sg = nullptr;         // staged-gather copy (ELLSPMV_CUDA_STAGED_GATHER), optional
     ellspmv::CbMatrix *cb = nullptr;         // column-blocked copy (ELLSPMV_CUDA_COLUMN_BLOCKED), optional
     int64_t min_col = 0, max_col = -1;

@@ -1,0 +1,196 @@
+// pattern.cu -- offset patterns: column indices that need not be streamed.
+//
+// The SpMV is HBM-bound and 4 of every 12 streamed bytes (8 of 16 with wide
+// indices) are column indices.  In a matrix that comes from a structured grid,
+// almost every row has the SAME column offsets relative to its own index:
+// colidx[i][l] = i + d[l] (2D 5-point Laplacian: d = -n, -1, 0, +1, +n).  At
+// upload the library looks for that: a group of 32 consecutive rows (one warp of
+// the thread-per-row kernel) is "patterned" when all of its rows share one offset
+// vector d[0..K-1]; the up to 16 most common vectors form a dictionary, every
+// group gets a one-byte pattern id (0xff = none), and for a patterned group the
+// kernel computes col = row + d[l] from the dictionary (a warp-uniform, L1-resident
+// load) instead of loading the 128/256-byte line of indices from HBM.
+//
+// This is a device-layout choice like the 64->32-bit index narrowing: the column
+// used for every entry is the stored one (every group is verified against the
+// dictionary entry by entry, not by hash), so results stay bit-exact; the explicit
+// index array is kept (download, the other kernels and the un-patterned groups use
+// it).  Only the index stream is touched: values are always read, so matrices with
+// variable coefficients on a regular grid profit just the same.
+#include <algorithm>
+#include <unordered_map>
+#include <vector>
+
+#include "common.cuh"
+
+namespace ellspmv {
+
+namespace {
+
+struct PatHashes { unsigned long long h[kMaxPatterns]; };
+
+__device__ __forceinline__ unsigned long long pat_mix(unsigned long long h, long long d)
+{
+    h = (h ^ (unsigned long long)d) * 0x9E3779B97F4A7C15ull;
+    return h ^ (h >> 29);
+}
+
+// one warp per group of 32 rows: signature = hash of the shared offset vector, 0 = rows differ
+template <typename IdxT>
+__global__ void __launch_bounds__(256)
+pat_signature_kernel(const IdxT *__restrict__ cols, EllLayout lay, int64_t row_begin, int64_t num_groups,
+                     unsigned long long *__restrict__ sig)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t g = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (g >= num_groups) return;
+    const int64_t row = g * 32 + lane;
+    bool uniform = __all_sync(0xffffffffu, row < lay.num_rows);      // the ragged last group stays explicit
+    unsigned long long h = 0x243F6A8885A308D3ull;
+    for (int l = 0; l < lay.rowsize && uniform; l++) {
+        const long long d = (long long)cols[lay.offset(row, l)] - (row_begin + row);
+        const long long d0 = __shfl_sync(0xffffffffu, d, 0);
+        uniform = __all_sync(0xffffffffu, d == d0);
+        h = pat_mix(h, d0);
+    }
+    if (lane == 0) sig[g] = uniform ? (h | 1ull) : 0ull;
+}
+
+__global__ void pat_sample_kernel(const unsigned long long *__restrict__ sig, int64_t stride, int64_t n,
+                                  unsigned long long *__restrict__ out)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = sig[i * stride];
+}
+
+// dictionary entry p = the offsets of the first row of its representative group
+template <typename IdxT>
+__global__ void pat_extract_kernel(const IdxT *__restrict__ cols, EllLayout lay, int64_t row_begin,
+                                   const long long *__restrict__ reps, int npat, long long *__restrict__ pat)
+{
+    const int p = blockIdx.x;
+    if (p >= npat) return;
+    const int64_t row = reps[p] * 32;
+    for (int l = threadIdx.x; l < lay.rowsize; l += blockDim.x)
+        pat[(int64_t)p * lay.rowsize + l] = (long long)cols[lay.offset(row, l)] - (row_begin + row);
+}
+
+// final word: a group takes pattern p only if EVERY entry of EVERY row equals row + pat[p][l]
+template <typename IdxT>
+__global__ void __launch_bounds__(256)
+pat_classify_kernel(const IdxT *__restrict__ cols, EllLayout lay, int64_t row_begin, int64_t num_groups,
+                    const unsigned long long *__restrict__ sig, PatHashes hashes, int npat,
+                    const long long *__restrict__ pat, unsigned char *__restrict__ patid,
+                    unsigned long long *__restrict__ covered)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t g = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (g >= num_groups) return;
+    const unsigned long long s = sig[g];
+    int p = -1;
+    if (s != 0)
+        for (int q = 0; q < npat; q++)
+            if (hashes.h[q] == s) { p = q; break; }
+    bool ok = p >= 0;
+    if (ok) {
+        const int64_t row = g * 32 + lane;
+        const long long *d = pat + (int64_t)p * lay.rowsize;
+        for (int l = 0; l < lay.rowsize && ok; l++)
+            ok = __all_sync(0xffffffffu, (long long)cols[lay.offset(row, l)] - (row_begin + row) == d[l]);
+    }
+    if (lane == 0) {
+        patid[g] = ok ? (unsigned char)p : (unsigned char)0xff;
+        if (ok) atomicAdd(covered, 1ull);
+    }
+}
+
+template <typename IdxT>
+cudaError_t pattern_build_typed(PatternSet *ps, const IdxT *cols, const EllLayout &lay, int64_t row_begin,
+                                cudaStream_t stream)
+{
+    const int64_t groups = lay.padded_rows() / 32;
+    const int K = lay.rowsize;
+    cudaError_t e;
+    unsigned long long *sig = nullptr, *sample = nullptr, *covered = nullptr;
+    long long *reps = nullptr;
+    auto cleanup = [&]() { cudaFree(sig); cudaFree(sample); cudaFree(covered); cudaFree(reps); };
+    if ((e = cudaMalloc(&sig, (size_t)groups * 8)) != cudaSuccess) return e;
+    const unsigned grid = (unsigned)((groups * 32 + 255) / 256);
+    pat_signature_kernel<IdxT><<<grid, 256, 0, stream>>>(cols, lay, row_begin, groups, sig);
+    if ((e = cudaGetLastError()) != cudaSuccess) { cleanup(); return e; }
+
+    // dictionary candidates: the most common signatures of a strided sample (the
+    // classification below verifies every group, so sampling cannot cost correctness)
+    const int64_t want = 1 << 20;
+    const int64_t stride = (groups + want - 1) / want;
+    const int64_t n = (groups + stride - 1) / stride;
+    if ((e = cudaMalloc(&sample, (size_t)n * 8)) != cudaSuccess) { cleanup(); return e; }
+    pat_sample_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(sig, stride, n, sample);
+    std::vector<unsigned long long> hs((size_t)n);
+    if ((e = cudaMemcpyAsync(hs.data(), sample, (size_t)n * 8, cudaMemcpyDeviceToHost, stream)) != cudaSuccess ||
+        (e = cudaStreamSynchronize(stream)) != cudaSuccess) { cleanup(); return e; }
+    struct Cand { unsigned long long h; int64_t count, first; };
+    std::unordered_map<unsigned long long, Cand> seen;
+    for (int64_t i = 0; i < n; i++) {
+        if (hs[(size_t)i] == 0) continue;
+        auto it = seen.find(hs[(size_t)i]);
+        if (it == seen.end()) seen.emplace(hs[(size_t)i], Cand{hs[(size_t)i], 1, i * stride});
+        else it->second.count++;
+    }
+    std::vector<Cand> cands;
+    cands.reserve(seen.size());
+    for (auto &kv : seen) cands.push_back(kv.second);
+    std::sort(cands.begin(), cands.end(), [](const Cand &a, const Cand &b) {
+        return a.count != b.count ? a.count > b.count : a.first < b.first;
+    });
+    const int npat = (int)std::min<size_t>(cands.size(), (size_t)kMaxPatterns);
+    if (npat == 0) { cleanup(); return cudaSuccess; }
+
+    PatHashes hashes = {};
+    long long hreps[kMaxPatterns] = {};
+    for (int p = 0; p < npat; p++) { hashes.h[p] = cands[(size_t)p].h; hreps[p] = cands[(size_t)p].first; }
+    if ((e = cudaMalloc(&reps, sizeof(hreps))) != cudaSuccess) { cleanup(); return e; }
+    if ((e = cudaMalloc(&covered, 8)) != cudaSuccess) { cleanup(); return e; }
+    if ((e = cudaMalloc(&ps->pat, (size_t)kMaxPatterns * K * 8)) != cudaSuccess) { cleanup(); return e; }
+    if ((e = cudaMalloc(&ps->patid, (size_t)groups)) != cudaSuccess) { cleanup(); return e; }
+    cudaMemcpyAsync(reps, hreps, sizeof(hreps), cudaMemcpyHostToDevice, stream);
+    cudaMemsetAsync(covered, 0, 8, stream);
+    cudaMemsetAsync(ps->pat, 0, (size_t)kMaxPatterns * K * 8, stream);
+    pat_extract_kernel<IdxT><<<npat, 128, 0, stream>>>(cols, lay, row_begin, reps, npat, ps->pat);
+    pat_classify_kernel<IdxT><<<grid, 256, 0, stream>>>(cols, lay, row_begin, groups, sig, hashes, npat, ps->pat,
+                                                        ps->patid, covered);
+    unsigned long long hc = 0;
+    if ((e = cudaGetLastError()) != cudaSuccess ||
+        (e = cudaMemcpyAsync(&hc, covered, 8, cudaMemcpyDeviceToHost, stream)) != cudaSuccess ||
+        (e = cudaStreamSynchronize(stream)) != cudaSuccess) { cleanup(); return e; }
+    cleanup();
+    ps->num_patterns = npat;
+    ps->groups = groups;
+    ps->covered = (int64_t)hc;
+    ps->bytes = groups + (int64_t)kMaxPatterns * K * 8;
+    return cudaSuccess;
+}
+
+}  // namespace
+
+void pattern_free(PatternSet *ps)
+{
+    cudaFree(ps->patid);
+    cudaFree(ps->pat);
+    *ps = PatternSet{};
+}
+
+// Leaves *ps empty (and returns success) when fewer than 1 group in 10 is patterned:
+// the table would cost a byte per group and buy nothing.
+cudaError_t pattern_build(PatternSet *ps, int idx_bits, const void *cols, const EllLayout &lay, int64_t row_begin,
+                          cudaStream_t stream)
+{
+    *ps = PatternSet{};
+    if (lay.num_rows < 32 || lay.rowsize <= 0 || lay.rowsize > 4096 || lay.slice_rows % 32 != 0) return cudaSuccess;
+    cudaError_t e = idx_bits == 64 ? pattern_build_typed<int64_t>(ps, (const int64_t *)cols, lay, row_begin, stream)
+                                   : pattern_build_typed<int32_t>(ps, (const int32_t *)cols, lay, row_begin, stream);
+    if (e != cudaSuccess || ps->covered * 10 < ps->groups) pattern_free(ps);
+    return e;
+}
+
+}  // namespace ellspmv

@@ -84,6 +84,16 @@ enum {
      * idx + 10 bytes of device memory per entry.  No-op when x fits one
      * block or a slice's K*128 staged values do not fit shared memory. */
     ELLSPMV_CUDA_STAGED_GATHER  = 1 << 17,
+    /* offset patterns (on by default, thread-per-row kernel with one row
+     * per thread): at upload, groups of 32 consecutive rows whose column
+     * indices are all row + d[l] for one offset vector d (structured grids:
+     * nearly every row) are found and verified entry by entry; the kernel
+     * then computes those columns from a 16-entry dictionary of offset
+     * vectors instead of streaming them from HBM.  A device-layout choice
+     * like the index narrowing: same columns, same bits, download()
+     * unchanged; only the index bytes of patterned rows are no longer read.
+     * NO_PATTERN keeps every group on the explicit index stream. */
+    ELLSPMV_CUDA_NO_PATTERN     = 1 << 18,
     /* rows handled per thread in the thread-per-row kernel: 0 = auto */
     ELLSPMV_CUDA_ROWS_PER_THREAD_SHIFT = 8,
     ELLSPMV_CUDA_ROWS_PER_THREAD_MASK  = 0x7 << 8,
@@ -126,6 +136,8 @@ typedef struct ellspmv_cuda_info {
     int64_t min_col, max_col;/* column range referenced by this shard       */
     int64_t launches;        /* SpMV kernel launches issued so far          */
     int     num_gpus;        /* GPUs behind this handle (row shards)        */
+    int64_t pattern_rows;    /* rows whose column indices come from an      */
+                             /*   offset pattern instead of the index stream */
 } ellspmv_cuda_info;
 
 /* ---- ELL ------------------------------------------------------------- */

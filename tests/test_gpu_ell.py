@@ -381,3 +381,97 @@ def test_staged_gather_tolerance_and_special_values(lib, oracle, monkeypatch):
         A.spmv(y, x, 1, E.OVERWRITE)
         assert bits_equal(y, want), flags
         A.free()
+
+
+def banded_ell(nr, nc, offsets, dt, rng):
+    """ELL arrays of a matrix whose row i holds columns i + d for d in offsets (clipped rows get
+    the reference's padding: column min(i, nc-1), value 0)."""
+    K = len(offsets)
+    ec = np.empty((nr, K), dtype=dt)
+    ea = np.zeros((nr, K))
+    for i in range(nr):
+        cols = [i + d for d in offsets if 0 <= i + d < nc]
+        ec[i, :len(cols)] = cols
+        ea[i, :len(cols)] = rng.standard_normal(len(cols))
+        ec[i, len(cols):] = min(i, nc - 1)
+    return ec.reshape(-1), ea.reshape(-1)
+
+
+@pytest.mark.parametrize("bits", [32, 64])
+def test_offset_patterns_are_found_and_change_nothing(lib, oracle, bits):
+    """Groups of 32 rows whose column indices are row + d[l] take them from the pattern
+    dictionary instead of the index stream (pattern.cu).  Same bits with and without, for
+    narrowed and wide indices; download() still returns the explicit arrays."""
+    dt = np.int32 if bits == 32 else np.int64
+    rng = np.random.default_rng(7 + bits)
+    nr = nc = 5000
+    ec, ea = banded_ell(nr, nc, (-70, -1, 0, 1, 70), dt, rng)
+    x = rng.standard_normal(nc)
+    y0 = rng.standard_normal(nr)
+    want = y0.copy()
+    oracle.ellgemv(nr, want, x, 5, ec, ea)
+    for flags, expect_patterns in ((0, True), (E.WIDE_INDEX, True), (E.FMA | E.NO_PATTERN, False), (E.NO_PATTERN, False),
+                                   (E.rows_per_thread(2), False), (E.KERNEL_WARP, False)):
+        A = E.EllMatrix.upload(nr, nc, 5, ec, ea, flags)
+        rows = A.info().pattern_rows
+        # interior groups: rows 70..4929 minus the groups straddling the two boundaries
+        assert (rows >= 4700) if expect_patterns else (rows == 0), (flags, rows)
+        c2, a2 = A.download()
+        assert np.array_equal(c2, ec) and bits_equal(a2, ea)
+        y = y0.copy()
+        A.spmv(y, x, 1, E.ACCUMULATE)
+        if flags & (E.FMA | E.KERNEL_WARP):
+            assert np.allclose(y, want, rtol=1e-13, atol=1e-13)
+        else:
+            assert bits_equal(y, want), flags
+        A.free()
+
+
+def test_offset_patterns_adversarial(lib, oracle):
+    """One deviating entry keeps its group on the explicit stream; more distinct patterns than the
+    dictionary holds leaves the rest explicit; a random matrix finds nothing.  Always the oracle's bits."""
+    rng = np.random.default_rng(11)
+    nr = nc = 4096
+    # (a) a single entry of a single row differs from its group's pattern
+    ec, ea = banded_ell(nr, nc, (-3, 0, 5), np.int32, rng)
+    ec = ec.reshape(nr, 3)
+    ec[1000, 2] = 17
+    ec[2049, 0] = 2049            # same column as slot 1: a duplicate column inside the row
+    ec = ec.reshape(-1)
+    # (b) 40 stripes of rows, each with its own offsets: more than 16 patterns
+    ec2 = np.empty((nr, 2), dtype=np.int32)
+    for i in range(nr):
+        stripe = i // 96
+        ec2[i] = ((i + stripe) % nc, (i + 2 * stripe + 1) % nc)
+    ea2 = rng.standard_normal(nr * 2)
+    # (c) random
+    ec3 = rng.integers(0, nc, nr * 4).astype(np.int32)
+    ea3 = rng.standard_normal(nr * 4)
+    x = rng.standard_normal(nc)
+    for K, cols, vals, lo, hi in ((3, ec, ea, 3900, 4096 - 64), (2, ec2.reshape(-1), ea2, 32, 4096 - 1024), (4, ec3, ea3, 0, 0)):
+        want = np.zeros(nr)
+        oracle.ellgemv(nr, want, x, K, cols, vals)
+        A = E.EllMatrix.upload(nr, nc, K, cols, vals)
+        rows = A.info().pattern_rows
+        assert lo <= rows <= hi, (K, rows)
+        y = np.zeros(nr)
+        A.spmv(y, x, 1, E.OVERWRITE)
+        assert bits_equal(y, want), K
+        A.free()
+
+
+def test_offset_patterns_in_a_row_shard(lib, oracle):
+    """A shard's rows are local, its columns global: the pattern offsets are relative to the GLOBAL row."""
+    rng = np.random.default_rng(5)
+    nr = nc = 3000
+    ec, ea = banded_ell(nr, nc, (-40, 0, 1, 40), np.int32, rng)
+    x = rng.standard_normal(nc)
+    want = np.zeros(nr)
+    oracle.ellgemv(nr, want, x, 4, ec, ea)
+    lo, hi = 1111, 2777
+    A = E.EllMatrix.upload(hi - lo, nc, 4, ec[lo * 4:hi * 4], ea[lo * 4:hi * 4], global_rows=nr, row_begin=lo)
+    assert A.info().pattern_rows >= (hi - lo) - 96
+    y = np.zeros(hi - lo)
+    A.spmv(y, x, 1, E.OVERWRITE)
+    assert bits_equal(y, want[lo:hi])
+    A.free()
