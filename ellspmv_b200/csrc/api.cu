@@ -153,14 +153,15 @@ int finish_minmax(ellspmv_cuda_matrix *A)
 }
 
 // Offset patterns (pattern.cu): groups of 32 rows whose column indices are row + d[l] stop
-// reading the index stream.  On by default for the thread-per-row kernel with one row per
-// thread; ELLSPMV_CUDA_NO_PATTERN turns it off.
+// reading the index stream.  On by default for the thread-per-row kernel;
+// ELLSPMV_CUDA_NO_PATTERN turns it off.
 int build_patterns(ellspmv_cuda_matrix *A)
 {
     if ((A->flags & ELLSPMV_CUDA_NO_PATTERN) || A->cfg.kernel != ELLSPMV_CUDA_KERNEL_THREAD ||
-        A->cfg.rows_per_thread != 1 || A->lay.num_rows <= 0 || A->lay.rowsize <= 0)
+        A->lay.num_rows <= 0 || A->lay.rowsize <= 0)
         return 0;
-    cudaError_t ce = pattern_build(&A->pat, A->dev_idx_bits, A->cols, A->lay, A->row_begin, A->stream);
+    cudaError_t ce = pattern_build(&A->pat, A->dev_idx_bits, A->cols, A->lay, A->cfg.rows_per_thread, A->row_begin,
+                                   A->stream);
     if (ce != cudaSuccess) { set_last_error("offset patterns: %s", cudaGetErrorString(ce)); return cuda_to_errno(ce); }
     A->device_bytes += A->pat.bytes;
     if (A->pat.patid) warm_kernels(A);
@@ -657,7 +658,7 @@ int ellspmv_cuda_get_info(const ellspmv_cuda_matrix *A, ellspmv_cuda_info *info)
     info->max_col = A->max_col;
     info->launches = A->launches;
     info->num_gpus = 1;
-    info->pattern_rows = A->pat.covered * 32;
+    info->pattern_rows = A->pat.covered * A->pat.group_rows;
     return 0;
 }
 

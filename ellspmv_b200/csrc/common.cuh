@@ -83,7 +83,7 @@ struct EllSpmvArgs {
     const double *ad;       // separately stored diagonal of the shard rows, or NULL
     int           sd_order; // 0: y += ad*x + yi (ellgemvsd); 1: sum starts at ad*x (ellgemv16sd)
     PushTargets   push;
-    const unsigned char *patid; // offset patterns (pattern.cu): one id per 32 rows, 0xff = explicit indices; or NULL
+    const unsigned char *patid; // offset patterns (pattern.cu): one id per warp (32*R rows), 0xff = explicit indices; or NULL
     const long long     *pat;   // dictionary [kMaxPatterns][K] of column offsets relative to the GLOBAL row
 };
 
@@ -143,11 +143,12 @@ struct PatternSet {
     unsigned char *patid = nullptr;   // device: padded_rows / 32 ids
     long long *pat = nullptr;         // device: kMaxPatterns * K offsets
     int num_patterns = 0;
-    int64_t groups = 0, covered = 0;  // groups of 32 rows: all / patterned
+    int group_rows = 32;              // 32 * rows per thread
+    int64_t groups = 0, covered = 0;  // groups: all / patterned
     int64_t bytes = 0;
 };
-cudaError_t pattern_build(PatternSet *ps, int idx_bits, const void *cols, const EllLayout &lay, int64_t row_begin,
-                          cudaStream_t stream);
+cudaError_t pattern_build(PatternSet *ps, int idx_bits, const void *cols, const EllLayout &lay, int rows_per_thread,
+                          int64_t row_begin, cudaStream_t stream);
 void pattern_free(PatternSet *ps);
 
 // ---- column-blocked ELL (ell_blocked.cu) ----------------------------------------

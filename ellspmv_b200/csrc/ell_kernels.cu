@@ -143,9 +143,9 @@ template <int R> struct Batch { static constexpr int U = (R == 4) ? 4 : (R == 2 
 // ---- thread-per-row kernel ------------------------------------------------
 // KU > 0: K known at compile time (fully unrolled); KU == 0: run-time K.
 // YVEC: y (and every push target) may be accessed with R-wide vectors.
-// PAT (R = 1 only): the handle has offset patterns (pattern.cu).  A warp whose 32 rows
-// share one offset vector d[] computes col = row + d[l] from the dictionary (a uniform
-// load that lives in L1) and never touches its 128/256-byte lines of the index stream.
+// PAT: the handle has offset patterns (pattern.cu).  A warp whose 32*R rows share one
+// offset vector d[] computes col = row + d[l] from the dictionary (a uniform load that
+// lives in L1) and never touches its lines of the index stream.
 template <typename IdxT, int R, int KU, bool FMA, bool YVEC, int G, bool PAT>
 __global__ void __launch_bounds__(kBlockThreads)
 ell_thread_kernel(const EllSpmvArgs a)
@@ -166,12 +166,17 @@ ell_thread_kernel(const EllSpmvArgs a)
     const long long *__restrict__ prow = nullptr;
     const int64_t rowg = a.row_begin + row0;
     if (PAT) {
-        const unsigned pid = __ldg(a.patid + (row0 >> 5));
+        const unsigned pid = __ldg(a.patid + ((slice * kBlockThreads + threadIdx.x) >> 5));
         if (pid != 0xffu) prow = a.pat + (int64_t)pid * K;
     }
     auto load_cols = [&](int l, int64_t (&c)[R]) {
-        if (PAT && prow) c[0] = rowg + __ldg(prow + l);
-        else Cols<IdxT, R>::ld(cp + (int64_t)l * S, c);
+        if (PAT && prow) {
+            const int64_t c0 = rowg + __ldg(prow + l);
+#pragma unroll
+            for (int r = 0; r < R; r++) c[r] = c0 + r;
+        } else {
+            Cols<IdxT, R>::ld(cp + (int64_t)l * S, c);
+        }
     };
 
     const bool full = row0 + R <= a.num_rows;
@@ -351,11 +356,9 @@ ell_subwarp_kernel(const EllSpmvArgs a, int slice_rows)
 template <typename IdxT, int R, int KU, bool FMA, int G>
 static cudaError_t launch_thread_g(const EllSpmvArgs &args, bool yvec, cudaLaunchConfig_t &lc)
 {
-    if (R == 1 && args.patid) {
-        // offset patterns exist only for one row per thread (a warp = one group of 32 rows)
-        constexpr bool P = R == 1;
-        if (yvec) return cudaLaunchKernelEx(&lc, ell_thread_kernel<IdxT, R, KU, FMA, true, G, P>, args);
-        return cudaLaunchKernelEx(&lc, ell_thread_kernel<IdxT, R, KU, FMA, false, G, P>, args);
+    if (args.patid) {
+        if (yvec) return cudaLaunchKernelEx(&lc, ell_thread_kernel<IdxT, R, KU, FMA, true, G, true>, args);
+        return cudaLaunchKernelEx(&lc, ell_thread_kernel<IdxT, R, KU, FMA, false, G, true>, args);
     }
     if (yvec) return cudaLaunchKernelEx(&lc, ell_thread_kernel<IdxT, R, KU, FMA, true, G, false>, args);
     return cudaLaunchKernelEx(&lc, ell_thread_kernel<IdxT, R, KU, FMA, false, G, false>, args);

@@ -4,8 +4,8 @@
 // indices) are column indices.  In a matrix that comes from a structured grid,
 // almost every row has the SAME column offsets relative to its own index:
 // colidx[i][l] = i + d[l] (2D 5-point Laplacian: d = -n, -1, 0, +1, +n).  At
-// upload the library looks for that: a group of 32 consecutive rows (one warp of
-// the thread-per-row kernel) is "patterned" when all of its rows share one offset
+// upload the library looks for that: a group of 32*R consecutive rows (one warp of
+// the thread-per-row kernel, R rows per thread) is "patterned" when all of its rows share one offset
 // vector d[0..K-1]; the up to 16 most common vectors form a dictionary, every
 // group gets a one-byte pattern id (0xff = none), and for a patterned group the
 // kernel computes col = row + d[l] from the dictionary (a warp-uniform, L1-resident
@@ -36,21 +36,25 @@ __device__ __forceinline__ unsigned long long pat_mix(unsigned long long h, long
 }
 
 // one warp per group of 32 rows: signature = hash of the shared offset vector, 0 = rows differ
+// (a group = the 32*R consecutive rows one warp of the thread-per-row kernel owns; lane j
+// holds rows j*R .. j*R+R-1 of it)
 template <typename IdxT>
 __global__ void __launch_bounds__(256)
-pat_signature_kernel(const IdxT *__restrict__ cols, EllLayout lay, int64_t row_begin, int64_t num_groups,
+pat_signature_kernel(const IdxT *__restrict__ cols, EllLayout lay, int R, int64_t row_begin, int64_t num_groups,
                      unsigned long long *__restrict__ sig)
 {
     const int lane = threadIdx.x & 31;
     const int64_t g = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     if (g >= num_groups) return;
-    const int64_t row = g * 32 + lane;
-    bool uniform = __all_sync(0xffffffffu, row < lay.num_rows);      // the ragged last group stays explicit
+    const int64_t row = (g * 32 + lane) * R;
+    bool uniform = __all_sync(0xffffffffu, row + R <= lay.num_rows);  // the ragged last group stays explicit
     unsigned long long h = 0x243F6A8885A308D3ull;
     for (int l = 0; l < lay.rowsize && uniform; l++) {
         const long long d = (long long)cols[lay.offset(row, l)] - (row_begin + row);
         const long long d0 = __shfl_sync(0xffffffffu, d, 0);
-        uniform = __all_sync(0xffffffffu, d == d0);
+        bool same = d == d0;
+        for (int r = 1; r < R; r++) same = same && (long long)cols[lay.offset(row + r, l)] - (row_begin + row + r) == d0;
+        uniform = __all_sync(0xffffffffu, same);
         h = pat_mix(h, d0);
     }
     if (lane == 0) sig[g] = uniform ? (h | 1ull) : 0ull;
@@ -65,12 +69,12 @@ __global__ void pat_sample_kernel(const unsigned long long *__restrict__ sig, in
 
 // dictionary entry p = the offsets of the first row of its representative group
 template <typename IdxT>
-__global__ void pat_extract_kernel(const IdxT *__restrict__ cols, EllLayout lay, int64_t row_begin,
+__global__ void pat_extract_kernel(const IdxT *__restrict__ cols, EllLayout lay, int R, int64_t row_begin,
                                    const long long *__restrict__ reps, int npat, long long *__restrict__ pat)
 {
     const int p = blockIdx.x;
     if (p >= npat) return;
-    const int64_t row = reps[p] * 32;
+    const int64_t row = reps[p] * 32 * R;
     for (int l = threadIdx.x; l < lay.rowsize; l += blockDim.x)
         pat[(int64_t)p * lay.rowsize + l] = (long long)cols[lay.offset(row, l)] - (row_begin + row);
 }
@@ -78,7 +82,7 @@ __global__ void pat_extract_kernel(const IdxT *__restrict__ cols, EllLayout lay,
 // final word: a group takes pattern p only if EVERY entry of EVERY row equals row + pat[p][l]
 template <typename IdxT>
 __global__ void __launch_bounds__(256)
-pat_classify_kernel(const IdxT *__restrict__ cols, EllLayout lay, int64_t row_begin, int64_t num_groups,
+pat_classify_kernel(const IdxT *__restrict__ cols, EllLayout lay, int R, int64_t row_begin, int64_t num_groups,
                     const unsigned long long *__restrict__ sig, PatHashes hashes, int npat,
                     const long long *__restrict__ pat, unsigned char *__restrict__ patid,
                     unsigned long long *__restrict__ covered)
@@ -93,10 +97,13 @@ pat_classify_kernel(const IdxT *__restrict__ cols, EllLayout lay, int64_t row_be
             if (hashes.h[q] == s) { p = q; break; }
     bool ok = p >= 0;
     if (ok) {
-        const int64_t row = g * 32 + lane;
+        const int64_t row = (g * 32 + lane) * R;
         const long long *d = pat + (int64_t)p * lay.rowsize;
-        for (int l = 0; l < lay.rowsize && ok; l++)
-            ok = __all_sync(0xffffffffu, (long long)cols[lay.offset(row, l)] - (row_begin + row) == d[l]);
+        for (int l = 0; l < lay.rowsize && ok; l++) {
+            bool same = true;
+            for (int r = 0; r < R; r++) same = same && (long long)cols[lay.offset(row + r, l)] - (row_begin + row + r) == d[l];
+            ok = __all_sync(0xffffffffu, same);
+        }
     }
     if (lane == 0) {
         patid[g] = ok ? (unsigned char)p : (unsigned char)0xff;
@@ -105,10 +112,10 @@ pat_classify_kernel(const IdxT *__restrict__ cols, EllLayout lay, int64_t row_be
 }
 
 template <typename IdxT>
-cudaError_t pattern_build_typed(PatternSet *ps, const IdxT *cols, const EllLayout &lay, int64_t row_begin,
+cudaError_t pattern_build_typed(PatternSet *ps, const IdxT *cols, const EllLayout &lay, int R, int64_t row_begin,
                                 cudaStream_t stream)
 {
-    const int64_t groups = lay.padded_rows() / 32;
+    const int64_t groups = lay.padded_rows() / (32 * R);
     const int K = lay.rowsize;
     cudaError_t e;
     unsigned long long *sig = nullptr, *sample = nullptr, *covered = nullptr;
@@ -116,7 +123,7 @@ cudaError_t pattern_build_typed(PatternSet *ps, const IdxT *cols, const EllLayou
     auto cleanup = [&]() { cudaFree(sig); cudaFree(sample); cudaFree(covered); cudaFree(reps); };
     if ((e = cudaMalloc(&sig, (size_t)groups * 8)) != cudaSuccess) return e;
     const unsigned grid = (unsigned)((groups * 32 + 255) / 256);
-    pat_signature_kernel<IdxT><<<grid, 256, 0, stream>>>(cols, lay, row_begin, groups, sig);
+    pat_signature_kernel<IdxT><<<grid, 256, 0, stream>>>(cols, lay, R, row_begin, groups, sig);
     if ((e = cudaGetLastError()) != cudaSuccess) { cleanup(); return e; }
 
     // dictionary candidates: the most common signatures of a strided sample (the
@@ -156,8 +163,8 @@ cudaError_t pattern_build_typed(PatternSet *ps, const IdxT *cols, const EllLayou
     cudaMemcpyAsync(reps, hreps, sizeof(hreps), cudaMemcpyHostToDevice, stream);
     cudaMemsetAsync(covered, 0, 8, stream);
     cudaMemsetAsync(ps->pat, 0, (size_t)kMaxPatterns * K * 8, stream);
-    pat_extract_kernel<IdxT><<<npat, 128, 0, stream>>>(cols, lay, row_begin, reps, npat, ps->pat);
-    pat_classify_kernel<IdxT><<<grid, 256, 0, stream>>>(cols, lay, row_begin, groups, sig, hashes, npat, ps->pat,
+    pat_extract_kernel<IdxT><<<npat, 128, 0, stream>>>(cols, lay, R, row_begin, reps, npat, ps->pat);
+    pat_classify_kernel<IdxT><<<grid, 256, 0, stream>>>(cols, lay, R, row_begin, groups, sig, hashes, npat, ps->pat,
                                                         ps->patid, covered);
     unsigned long long hc = 0;
     if ((e = cudaGetLastError()) != cudaSuccess ||
@@ -166,6 +173,7 @@ cudaError_t pattern_build_typed(PatternSet *ps, const IdxT *cols, const EllLayou
     cleanup();
     ps->num_patterns = npat;
     ps->groups = groups;
+    ps->group_rows = 32 * R;
     ps->covered = (int64_t)hc;
     ps->bytes = groups + (int64_t)kMaxPatterns * K * 8;
     return cudaSuccess;
@@ -182,13 +190,15 @@ void pattern_free(PatternSet *ps)
 
 // Leaves *ps empty (and returns success) when fewer than 1 group in 10 is patterned:
 // the table would cost a byte per group and buy nothing.
-cudaError_t pattern_build(PatternSet *ps, int idx_bits, const void *cols, const EllLayout &lay, int64_t row_begin,
-                          cudaStream_t stream)
+cudaError_t pattern_build(PatternSet *ps, int idx_bits, const void *cols, const EllLayout &lay, int rows_per_thread,
+                          int64_t row_begin, cudaStream_t stream)
 {
     *ps = PatternSet{};
-    if (lay.num_rows < 32 || lay.rowsize <= 0 || lay.rowsize > 4096 || lay.slice_rows % 32 != 0) return cudaSuccess;
-    cudaError_t e = idx_bits == 64 ? pattern_build_typed<int64_t>(ps, (const int64_t *)cols, lay, row_begin, stream)
-                                   : pattern_build_typed<int32_t>(ps, (const int32_t *)cols, lay, row_begin, stream);
+    const int R = rows_per_thread;
+    if (lay.num_rows < 32 * R || lay.rowsize <= 0 || lay.rowsize > 4096 || lay.slice_rows != kBlockThreads * R)
+        return cudaSuccess;
+    cudaError_t e = idx_bits == 64 ? pattern_build_typed<int64_t>(ps, (const int64_t *)cols, lay, R, row_begin, stream)
+                                   : pattern_build_typed<int32_t>(ps, (const int32_t *)cols, lay, R, row_begin, stream);
     if (e != cudaSuccess || ps->covered * 10 < ps->groups) pattern_free(ps);
     return e;
 }

@@ -399,8 +399,8 @@ def banded_ell(nr, nc, offsets, dt, rng):
 
 @pytest.mark.parametrize("bits", [32, 64])
 def test_offset_patterns_are_found_and_change_nothing(lib, oracle, bits):
-    """Groups of 32 rows whose column indices are row + d[l] take them from the pattern
-    dictionary instead of the index stream (pattern.cu).  Same bits with and without, for
+    """Groups of 32*R rows (one warp) whose column indices are row + d[l] take them from the
+    pattern dictionary instead of the index stream (pattern.cu).  Same bits with and without, for
     narrowed and wide indices; download() still returns the explicit arrays."""
     dt = np.int32 if bits == 32 else np.int64
     rng = np.random.default_rng(7 + bits)
@@ -411,7 +411,7 @@ def test_offset_patterns_are_found_and_change_nothing(lib, oracle, bits):
     want = y0.copy()
     oracle.ellgemv(nr, want, x, 5, ec, ea)
     for flags, expect_patterns in ((0, True), (E.WIDE_INDEX, True), (E.FMA | E.NO_PATTERN, False), (E.NO_PATTERN, False),
-                                   (E.rows_per_thread(2), False), (E.KERNEL_WARP, False)):
+                                   (E.rows_per_thread(2), True), (E.rows_per_thread(4), True), (E.KERNEL_WARP, False)):
         A = E.EllMatrix.upload(nr, nc, 5, ec, ea, flags)
         rows = A.info().pattern_rows
         # interior groups: rows 70..4929 minus the groups straddling the two boundaries
