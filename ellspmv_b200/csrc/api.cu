@@ -66,13 +66,13 @@ int configure(ellspmv_cuda_matrix *A, unsigned flags)
 {
     A->flags = flags;
     int R = (flags & ELLSPMV_CUDA_ROWS_PER_THREAD_MASK) >> ELLSPMV_CUDA_ROWS_PER_THREAD_SHIFT;
-    // auto: 1 row per thread (a warp reads 256 contiguous bytes of values and 128
-    // of indices per slot).  Measured on two B200 boxes (profiles/r1_sweep.md,
-    // profiles/r1_bulk_variant.md): R = 1 / 2 / 4 give 0.784 / 0.790-0.830 / 0.807 ms
-    // on BASELINE config 2 and 3.65 / 3.64-3.74 / 3.69 ms on config 3 -- wider
-    // (128/256-bit) loads buy nothing on this HBM-bound stream and the extra
-    // resident threads of R = 1 make it the most stable; R = 2 and 4 stay selectable.
-    if (R == 0) R = 1;
+    // auto: enough loads in flight per thread to cover the HBM latency.  With long rows one
+    // row per thread does it (K = 27: R = 1 / 2 / 4 give 2.61 / 2.69 / 2.71 ms on BASELINE
+    // config 3); with K = 5 a thread that owns one row has 48 bytes in flight and the kernel is
+    // latency-bound as soon as the offset patterns (pattern.cu) take the index stream away:
+    // 0.747 / 0.675 / 0.668 ms on config 2 (profiles/r1_offset_patterns.md).  In between is
+    // interpolated: about 20 matrix entries per thread.
+    if (R == 0) R = A->lay.rowsize <= 6 ? 4 : (A->lay.rowsize <= 12 ? 2 : 1);
     if (R != 1 && R != 2 && R != 4) ELL_FAIL(EINVAL, "rows per thread must be 1, 2 or 4 (got %d)", R);
     int kernel = flags & ELLSPMV_CUDA_KERNEL_MASK;
     if (kernel == ELLSPMV_CUDA_KERNEL_AUTO) kernel = ELLSPMV_CUDA_KERNEL_THREAD;
@@ -132,7 +132,8 @@ void warm_kernels(ellspmv_cuda_matrix *A)
     args.num_rows = 0;
     args.rowsize = A->lay.rowsize;
     args.beta = 1;
-    args.patid = A->pat.patid;
+    args.gmap = A->pat.gmap;
+    args.xcols = A->pat.xcols;
     args.pat = A->pat.pat;
     if (launch_ell_spmv(A->cfg, args, 1, A->stream) == cudaSuccess) cudaStreamSynchronize(A->stream);
     cudaGetLastError();
@@ -164,7 +165,7 @@ int build_patterns(ellspmv_cuda_matrix *A)
                                    A->stream);
     if (ce != cudaSuccess) { set_last_error("offset patterns: %s", cudaGetErrorString(ce)); return cuda_to_errno(ce); }
     A->device_bytes += A->pat.bytes;
-    if (A->pat.patid) warm_kernels(A);
+    if (A->pat.gmap) warm_kernels(A);
     return 0;
 }
 
@@ -239,7 +240,8 @@ int launch(ellspmv_cuda_matrix *A, double *y_dev, const double *x_dev, int beta,
     args.slice_begin = slice_begin;
     args.ad = A->d_ad;
     args.sd_order = A->sd_order;
-    args.patid = A->pat.patid;
+    args.gmap = A->pat.gmap;
+    args.xcols = A->pat.xcols;
     args.pat = A->pat.pat;
     if (num_slices < 0) num_slices = A->lay.num_slices - slice_begin;
     if (push) args.push = *push; else args.push.num_peers = 0;

@@ -88,7 +88,7 @@ static void help(FILE *f)
     fprintf(f, " Options for the CUDA path are:\n");
     fprintf(f, "  --kernel=thread|warp thread-per-row (bit-exact, default) or sub-warp-per-row\n");
     fprintf(f, "  --fma                allow fused multiply-add (tolerance mode)\n");
-    fprintf(f, "  --rows-per-thread=N  1, 2 or 4 rows per thread [4]\n");
+    fprintf(f, "  --rows-per-thread=N  1, 2 or 4 rows per thread [by row length]\n");
     fprintf(f, "  --l2-persist-x       L2 persisting access window over x\n");
     fprintf(f, "  --wide-index         keep 64-bit column indices 64-bit on the device (default: stored as\n");
     fprintf(f, "                       32-bit when the matrix has fewer than 2^31 columns)\n");
@@ -96,6 +96,8 @@ static void help(FILE *f)
     fprintf(f, "                       for scattered matrices whose x is larger than the L2 cache)\n");
     fprintf(f, "  --staged-gather      column blocks with the gather staged through device memory: the\n");
     fprintf(f, "                       same bits as the default kernel, for the same kind of matrix\n");
+    fprintf(f, "  --no-pattern         always stream the column indices (default: groups of rows whose\n");
+    fprintf(f, "                       indices are row + fixed offsets take them from a small table)\n");
     fprintf(f, "  --iterate            compute x := A*x repeatedly (y := A^N x); square A only\n");
     fprintf(f, "  --synthetic=SPEC     build A on the device instead of reading a file:\n");
     fprintf(f, "                       laplace2d:NX,NY | stencil27:NX,NY,NZ | random:ROWS,COLS,K[,SEED]\n");
@@ -169,6 +171,7 @@ static int parse_options(int argc, char **argv, struct options *o, int *bad)
             if (!strcmp(a, "--wide-index")) { o->flags |= ELLSPMV_CUDA_WIDE_INDEX; continue; }
             if (!strcmp(a, "--column-blocked")) { o->flags |= ELLSPMV_CUDA_COLUMN_BLOCKED; continue; }
             if (!strcmp(a, "--staged-gather")) { o->flags |= ELLSPMV_CUDA_STAGED_GATHER; continue; }
+            if (!strcmp(a, "--no-pattern")) { o->flags |= ELLSPMV_CUDA_NO_PATTERN; continue; }
             if (!strncmp(a, "--rows-per-thread", 17) && (a[17] == '=' || a[17] == '\0')) {
                 int r;
                 if (!(v = optval(argc, argv, &i, "--rows-per-thread")) || to_int(v, &r)) return EINVAL;
