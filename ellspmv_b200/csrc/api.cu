@@ -132,8 +132,7 @@ void warm_kernels(ellspmv_cuda_matrix *A)
     args.num_rows = 0;
     args.rowsize = A->lay.rowsize;
     args.beta = 1;
-    args.gmap = A->pat.gmap;
-    args.xcols = A->pat.xcols;
+    args.patid = A->pat.patid;
     args.pat = A->pat.pat;
     if (launch_ell_spmv(A->cfg, args, 1, A->stream) == cudaSuccess) cudaStreamSynchronize(A->stream);
     cudaGetLastError();
@@ -165,7 +164,7 @@ int build_patterns(ellspmv_cuda_matrix *A)
                                    A->stream);
     if (ce != cudaSuccess) { set_last_error("offset patterns: %s", cudaGetErrorString(ce)); return cuda_to_errno(ce); }
     A->device_bytes += A->pat.bytes;
-    if (A->pat.gmap) warm_kernels(A);
+    if (A->pat.patid) warm_kernels(A);
     return 0;
 }
 
@@ -240,8 +239,7 @@ int launch(ellspmv_cuda_matrix *A, double *y_dev, const double *x_dev, int beta,
     args.slice_begin = slice_begin;
     args.ad = A->d_ad;
     args.sd_order = A->sd_order;
-    args.gmap = A->pat.gmap;
-    args.xcols = A->pat.xcols;
+    args.patid = A->pat.patid;
     args.pat = A->pat.pat;
     if (num_slices < 0) num_slices = A->lay.num_slices - slice_begin;
     if (push) args.push = *push; else args.push.num_peers = 0;

@@ -83,9 +83,7 @@ struct EllSpmvArgs {
     const double *ad;       // separately stored diagonal of the shard rows, or NULL
     int           sd_order; // 0: y += ad*x + yi (ellgemvsd); 1: sum starts at ad*x (ellgemv16sd)
     PushTargets   push;
-    const int           *gmap;  // offset patterns (pattern.cu), one entry per warp (32*R rows) or NULL:
-                                //   < 0: pattern -1-gmap; >= 0: ordinal of the group in xcols
-    const void          *xcols; // compacted indices of the explicit groups, [ordinal][slot][32*R]
+    const unsigned char *patid; // offset patterns (pattern.cu): one id per warp (32*R rows), 0xff = explicit indices; or NULL
     const long long     *pat;   // dictionary [kMaxPatterns][K] of column offsets relative to the GLOBAL row
 };
 
@@ -142,8 +140,7 @@ cudaError_t init_minmax(long long *minmax, cudaStream_t stream);
 
 // ---- offset patterns: groups of 32 rows whose column indices are row + d[l] (pattern.cu) ----
 struct PatternSet {
-    int *gmap = nullptr;              // device: one entry per group (see EllSpmvArgs)
-    void *xcols = nullptr;            // device: the explicit groups' indices, compacted
+    unsigned char *patid = nullptr;   // device: padded_rows / 32 ids
     long long *pat = nullptr;         // device: kMaxPatterns * K offsets
     int num_patterns = 0;
     int group_rows = 32;              // 32 * rows per thread

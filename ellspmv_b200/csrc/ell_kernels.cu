@@ -160,21 +160,14 @@ ell_thread_kernel(const EllSpmvArgs a)
     const int64_t base = slice * S * (int64_t)K + (int64_t)threadIdx.x * R;
     const double *vp = a.vals + base;
     const IdxT *cp = reinterpret_cast<const IdxT *>(a.cols) + base;
-    int cstride = S;                         // distance between two slots of the index stream
     const double *__restrict__ x = a.x;
 
     // warp-uniform: this warp's pattern (or none); rowg = the row's global index
     const long long *__restrict__ prow = nullptr;
     const int64_t rowg = a.row_begin + row0;
     if (PAT) {
-        const int gm = __ldg(a.gmap + ((slice * kBlockThreads + threadIdx.x) >> 5));
-        if (gm < 0) {
-            prow = a.pat + (int64_t)(-1 - gm) * K;
-        } else {
-            // explicit group: its indices sit compacted, [slot][32*R rows], at ordinal gm
-            cp = reinterpret_cast<const IdxT *>(a.xcols) + (int64_t)gm * K * (32 * R) + (threadIdx.x & 31) * R;
-            cstride = 32 * R;
-        }
+        const unsigned pid = __ldg(a.patid + ((slice * kBlockThreads + threadIdx.x) >> 5));
+        if (pid != 0xffu) prow = a.pat + (int64_t)pid * K;
     }
     auto load_cols = [&](int l, int64_t (&c)[R]) {
         if (PAT && prow) {
@@ -182,7 +175,7 @@ ell_thread_kernel(const EllSpmvArgs a)
 #pragma unroll
             for (int r = 0; r < R; r++) c[r] = c0 + r;
         } else {
-            Cols<IdxT, R>::ld(cp + (int64_t)l * cstride, c);
+            Cols<IdxT, R>::ld(cp + (int64_t)l * S, c);
         }
     };
 
@@ -363,7 +356,7 @@ ell_subwarp_kernel(const EllSpmvArgs a, int slice_rows)
 template <typename IdxT, int R, int KU, bool FMA, int G>
 static cudaError_t launch_thread_g(const EllSpmvArgs &args, bool yvec, cudaLaunchConfig_t &lc)
 {
-    if (args.gmap) {
+    if (args.patid) {
         if (yvec) return cudaLaunchKernelEx(&lc, ell_thread_kernel<IdxT, R, KU, FMA, true, G, true>, args);
         return cudaLaunchKernelEx(&lc, ell_thread_kernel<IdxT, R, KU, FMA, false, G, true>, args);
     }

@@ -7,13 +7,9 @@
 // upload the library looks for that: a group of 32*R consecutive rows (one warp of
 // the thread-per-row kernel, R rows per thread) is "patterned" when all of its rows share one offset
 // vector d[0..K-1]; the up to 16 most common vectors form a dictionary, every
-// group gets a 32-bit map entry, and for a patterned group the kernel computes
-// col = row + d[l] from the dictionary (a warp-uniform, L1-resident load) instead
-// of loading its lines of indices from HBM.  The indices of the remaining
-// ("explicit") groups are stored a second time, compacted group after group
-// ([group][slot][32*R rows]): read from the regular sliced array they would be
-// isolated 128-byte lines between skipped ones, which HBM serves poorly (27-point
-// 384^3: 2.61 ms, against 2.46 ms for the same kernel on 256-byte lines).
+// group gets a one-byte pattern id (0xff = none), and for a patterned group the
+// kernel computes col = row + d[l] from the dictionary (a warp-uniform, L1-resident
+// load) instead of loading the 128/256-byte line of indices from HBM.
 //
 // This is a device-layout choice like the 64->32-bit index narrowing: the column
 // used for every entry is the stored one (every group is verified against the
@@ -21,8 +17,6 @@
 // index array is kept (download, the other kernels and the un-patterned groups use
 // it).  Only the index stream is touched: values are always read, so matrices with
 // variable coefficients on a regular grid profit just the same.
-#include <cub/cub.cuh>
-
 #include <algorithm>
 #include <unordered_map>
 #include <vector>
@@ -90,7 +84,8 @@ template <typename IdxT>
 __global__ void __launch_bounds__(256)
 pat_classify_kernel(const IdxT *__restrict__ cols, EllLayout lay, int R, int64_t row_begin, int64_t num_groups,
                     const unsigned long long *__restrict__ sig, PatHashes hashes, int npat,
-                    const long long *__restrict__ pat, int *__restrict__ gmap, int *__restrict__ is_explicit)
+                    const long long *__restrict__ pat, unsigned char *__restrict__ patid,
+                    unsigned long long *__restrict__ covered)
 {
     const int lane = threadIdx.x & 31;
     const int64_t g = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
@@ -111,28 +106,9 @@ pat_classify_kernel(const IdxT *__restrict__ cols, EllLayout lay, int R, int64_t
         }
     }
     if (lane == 0) {
-        gmap[g] = ok ? -1 - p : 0;
-        is_explicit[g] = ok ? 0 : 1;
+        patid[g] = ok ? (unsigned char)p : (unsigned char)0xff;
+        if (ok) atomicAdd(covered, 1ull);
     }
-}
-
-// explicit groups: gmap = ordinal among the explicit groups, indices copied to the compact array
-template <typename IdxT>
-__global__ void __launch_bounds__(256)
-pat_compact_kernel(const IdxT *__restrict__ cols, EllLayout lay, int R, int64_t num_groups,
-                   const int *__restrict__ ordinal, int *__restrict__ gmap, IdxT *__restrict__ xcols)
-{
-    const int lane = threadIdx.x & 31;
-    const int64_t g = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    if (g >= num_groups || gmap[g] < 0) return;
-    const int64_t ord = ordinal[g];
-    const int64_t row = (g * 32 + lane) * R;
-    const int GR = 32 * R;
-    for (int l = 0; l < lay.rowsize; l++)
-        for (int r = 0; r < R; r++)
-            xcols[(ord * lay.rowsize + l) * GR + lane * R + r] = cols[lay.offset(row + r, l)];
-    __syncwarp();
-    if (lane == 0) gmap[g] = (int)ord;
 }
 
 template <typename IdxT>
@@ -142,12 +118,9 @@ cudaError_t pattern_build_typed(PatternSet *ps, const IdxT *cols, const EllLayou
     const int64_t groups = lay.padded_rows() / (32 * R);
     const int K = lay.rowsize;
     cudaError_t e;
-    unsigned long long *sig = nullptr, *sample = nullptr;
+    unsigned long long *sig = nullptr, *sample = nullptr, *covered = nullptr;
     long long *reps = nullptr;
-    int *flag = nullptr, *ordinal = nullptr;
-    void *temp = nullptr;
-    auto cleanup = [&]() { cudaFree(sig); cudaFree(sample); cudaFree(reps); cudaFree(flag); cudaFree(ordinal); cudaFree(temp); };
-    if (groups >= 0x7fffffffLL) return cudaSuccess;
+    auto cleanup = [&]() { cudaFree(sig); cudaFree(sample); cudaFree(covered); cudaFree(reps); };
     if ((e = cudaMalloc(&sig, (size_t)groups * 8)) != cudaSuccess) return e;
     const unsigned grid = (unsigned)((groups * 32 + 255) / 256);
     pat_signature_kernel<IdxT><<<grid, 256, 0, stream>>>(cols, lay, R, row_begin, groups, sig);
@@ -184,37 +157,25 @@ cudaError_t pattern_build_typed(PatternSet *ps, const IdxT *cols, const EllLayou
     long long hreps[kMaxPatterns] = {};
     for (int p = 0; p < npat; p++) { hashes.h[p] = cands[(size_t)p].h; hreps[p] = cands[(size_t)p].first; }
     if ((e = cudaMalloc(&reps, sizeof(hreps))) != cudaSuccess) { cleanup(); return e; }
-    if ((e = cudaMalloc(&flag, (size_t)(groups + 1) * 4)) != cudaSuccess) { cleanup(); return e; }
-    if ((e = cudaMalloc(&ordinal, (size_t)(groups + 1) * 4)) != cudaSuccess) { cleanup(); return e; }
+    if ((e = cudaMalloc(&covered, 8)) != cudaSuccess) { cleanup(); return e; }
     if ((e = cudaMalloc(&ps->pat, (size_t)kMaxPatterns * K * 8)) != cudaSuccess) { cleanup(); return e; }
-    if ((e = cudaMalloc(&ps->gmap, (size_t)groups * 4)) != cudaSuccess) { cleanup(); return e; }
+    if ((e = cudaMalloc(&ps->patid, (size_t)groups)) != cudaSuccess) { cleanup(); return e; }
     cudaMemcpyAsync(reps, hreps, sizeof(hreps), cudaMemcpyHostToDevice, stream);
-    cudaMemsetAsync(flag, 0, (size_t)(groups + 1) * 4, stream);
+    cudaMemsetAsync(covered, 0, 8, stream);
     cudaMemsetAsync(ps->pat, 0, (size_t)kMaxPatterns * K * 8, stream);
     pat_extract_kernel<IdxT><<<npat, 128, 0, stream>>>(cols, lay, R, row_begin, reps, npat, ps->pat);
     pat_classify_kernel<IdxT><<<grid, 256, 0, stream>>>(cols, lay, R, row_begin, groups, sig, hashes, npat, ps->pat,
-                                                        ps->gmap, flag);
-    if ((e = cudaGetLastError()) != cudaSuccess) { cleanup(); return e; }
-    size_t temp_bytes = 0;
-    if ((e = cub::DeviceScan::ExclusiveSum(nullptr, temp_bytes, flag, ordinal, groups + 1, stream)) != cudaSuccess ||
-        (e = cudaMalloc(&temp, temp_bytes + 16)) != cudaSuccess ||
-        (e = cub::DeviceScan::ExclusiveSum(temp, temp_bytes, flag, ordinal, groups + 1, stream)) != cudaSuccess) {
-        cleanup(); return e;
-    }
-    int num_explicit = 0;
-    if ((e = cudaMemcpyAsync(&num_explicit, ordinal + groups, 4, cudaMemcpyDeviceToHost, stream)) != cudaSuccess ||
+                                                        ps->patid, covered);
+    unsigned long long hc = 0;
+    if ((e = cudaGetLastError()) != cudaSuccess ||
+        (e = cudaMemcpyAsync(&hc, covered, 8, cudaMemcpyDeviceToHost, stream)) != cudaSuccess ||
         (e = cudaStreamSynchronize(stream)) != cudaSuccess) { cleanup(); return e; }
+    cleanup();
     ps->num_patterns = npat;
     ps->groups = groups;
     ps->group_rows = 32 * R;
-    ps->covered = groups - num_explicit;
-    if (ps->covered * 10 < groups) { cleanup(); return cudaSuccess; }      // not worth it: the caller drops the set
-    const size_t xn = (size_t)(num_explicit > 0 ? num_explicit : 1) * K * 32 * R;
-    if ((e = cudaMalloc(&ps->xcols, xn * sizeof(IdxT))) != cudaSuccess) { cleanup(); return e; }
-    pat_compact_kernel<IdxT><<<grid, 256, 0, stream>>>(cols, lay, R, groups, ordinal, ps->gmap, (IdxT *)ps->xcols);
-    if ((e = cudaGetLastError()) != cudaSuccess || (e = cudaStreamSynchronize(stream)) != cudaSuccess) { cleanup(); return e; }
-    cleanup();
-    ps->bytes = groups * 4 + (int64_t)kMaxPatterns * K * 8 + (int64_t)(xn * sizeof(IdxT));
+    ps->covered = (int64_t)hc;
+    ps->bytes = groups + (int64_t)kMaxPatterns * K * 8;
     return cudaSuccess;
 }
 
@@ -222,14 +183,13 @@ cudaError_t pattern_build_typed(PatternSet *ps, const IdxT *cols, const EllLayou
 
 void pattern_free(PatternSet *ps)
 {
-    cudaFree(ps->gmap);
-    cudaFree(ps->xcols);
+    cudaFree(ps->patid);
     cudaFree(ps->pat);
     *ps = PatternSet{};
 }
 
 // Leaves *ps empty (and returns success) when fewer than 1 group in 10 is patterned:
-// the map and the compacted copy would cost memory and buy nothing.
+// the table would cost a byte per group and buy nothing.
 cudaError_t pattern_build(PatternSet *ps, int idx_bits, const void *cols, const EllLayout &lay, int rows_per_thread,
                           int64_t row_begin, cudaStream_t stream)
 {
@@ -239,7 +199,7 @@ cudaError_t pattern_build(PatternSet *ps, int idx_bits, const void *cols, const 
         return cudaSuccess;
     cudaError_t e = idx_bits == 64 ? pattern_build_typed<int64_t>(ps, (const int64_t *)cols, lay, R, row_begin, stream)
                                    : pattern_build_typed<int32_t>(ps, (const int32_t *)cols, lay, R, row_begin, stream);
-    if (e != cudaSuccess || !ps->xcols) pattern_free(ps);
+    if (e != cudaSuccess || ps->covered * 10 < ps->groups) pattern_free(ps);
     return e;
 }
 

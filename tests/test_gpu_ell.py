@@ -451,7 +451,7 @@ def test_offset_patterns_adversarial(lib, oracle):
     for K, cols, vals, lo, hi in ((3, ec, ea, 3900, 4096 - 64), (2, ec2.reshape(-1), ea2, 32, 4096 - 1024), (4, ec3, ea3, 0, 0)):
         want = np.zeros(nr)
         oracle.ellgemv(nr, want, x, K, cols, vals)
-        A = E.EllMatrix.upload(nr, nc, K, cols, vals)
+        A = E.EllMatrix.upload(nr, nc, K, cols, vals, E.rows_per_thread(1))    # groups of 32 rows
         rows = A.info().pattern_rows
         assert lo <= rows <= hi, (K, rows)
         y = np.zeros(nr)
@@ -470,7 +470,7 @@ def test_offset_patterns_in_a_row_shard(lib, oracle):
     oracle.ellgemv(nr, want, x, 4, ec, ea)
     lo, hi = 1111, 2777
     A = E.EllMatrix.upload(hi - lo, nc, 4, ec[lo * 4:hi * 4], ea[lo * 4:hi * 4], global_rows=nr, row_begin=lo)
-    assert A.info().pattern_rows >= (hi - lo) - 96
+    assert A.info().pattern_rows >= (hi - lo) - 256        # K = 4: four rows per thread, groups of 128
     y = np.zeros(hi - lo)
     A.spmv(y, x, 1, E.OVERWRITE)
     assert bits_equal(y, want[lo:hi])
