@@ -389,7 +389,9 @@ def main_ours(args, rank: int, local_rank: int, world: int):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload, "rows_per_gpu": rows, "rowsize": K, "idx_bits": idx_bits,
                    "mode": mode_name, "rows_per_thread": info.rows_per_thread, "slice_rows": info.slice_rows,
-                   "kernel": kernel_description(flags, bool(info.fma)),
+                   "kernel": kernel_description(flags, bool(info.fma))
+                   + (f"; {pattern_rows / max(rows, 1):.1%} of the rows take their column indices from an offset pattern"
+                      if pattern_rows else ""),
                    "l2": f"inputs larger than L2 ({rows * K * (8 + idx_bits // 8) / 1e9:.1f} GB matrix per GPU vs 126 MB L2), no flush needed",
                    "parallelism": f"rowshard{world}"},
         "gbs": round(achieved * world, 1),
