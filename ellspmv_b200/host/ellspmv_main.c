@@ -398,9 +398,9 @@ int main(int argc, char *argv[])
             ellspmv_cuda_get_info(A, &info);
             clock_gettime(CLOCK_MONOTONIC, &t1);
             fprintf(stderr, "%'.6f seconds, %d GPU(s), %'" PRId64 " bytes, sliced ELL %d rows/slice, "
-                            "%d rows/thread, %d-bit indices\n",
+                            "%d rows/thread, %d-bit indices, %'" PRId64 " rows on offset patterns\n",
                     seconds_between(t0, t1), info.num_gpus, info.device_bytes, info.slice_rows,
-                    info.rows_per_thread, info.dev_idx_bits);
+                    info.rows_per_thread, info.dev_idx_bits, info.pattern_rows);
         }
         }
     }
