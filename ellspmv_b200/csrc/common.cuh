@@ -83,6 +83,7 @@ struct EllSpmvArgs {
     const double *ad;       // separately stored diagonal of the shard rows, or NULL
     int           sd_order; // 0: y += ad*x + yi (ellgemvsd); 1: sum starts at ad*x (ellgemv16sd)
     PushTargets   push;
+    int           prefetch;     // slices ahead whose value stream is requested into L2 (0 = none)
     const unsigned char *patid; // offset patterns (pattern.cu): one id per warp (32*R rows), 0xff = explicit indices; or NULL
     const long long     *pat;   // dictionary [kMaxPatterns][K] of column offsets relative to the GLOBAL row
 };

@@ -155,6 +155,21 @@ ell_thread_kernel(const EllSpmvArgs a)
     const int K = KU > 0 ? KU : a.rowsize;
     const int64_t slice = a.slice_begin + blockIdx.x;
     const int64_t row0 = slice * S + (int64_t)threadIdx.x * R;   // shard-local
+
+    // L2 prefetch (only launched with it when the matrix has offset patterns): one thread asks
+    // the bulk-copy engine to pull the value stream of the slice `prefetch` CTAs ahead into L2
+    // (cp.async.bulk.prefetch.L2, SASS UBLKPF.L2: no registers, no shared memory).  Without the
+    // index stream the kernel is latency-bound -- the register file caps the bytes its loads keep
+    // in flight -- and these requests are in flight on top of them: config 3 2.55 -> 2.09 ms,
+    // config 2 0.668 -> 0.609 ms, flat from 64 to 300 slices ahead, worse beyond ~2000 (L2
+    // thrash) and useless for kernels that are already HBM- or gather-bound
+    // (profiles/r1_offset_patterns.md).
+    if (PAT && a.prefetch > 0 && threadIdx.x == 0) {
+        const int64_t ps = slice + a.prefetch;
+        if ((ps + 1) * S <= a.num_rows)
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;"
+                         :: "l"(a.vals + ps * S * (int64_t)K), "r"((unsigned)(S * K * 8)) : "memory");
+    }
     if (row0 >= a.num_rows) return;
 
     const int64_t base = slice * S * (int64_t)K + (int64_t)threadIdx.x * R;
@@ -414,10 +429,14 @@ static cudaError_t launch_subwarp(const EllSpmvArgs &args, int slice_rows, cudaL
 
 static bool aligned_to(const void *p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
-cudaError_t launch_ell_spmv(const EllLaunchCfg &cfg, const EllSpmvArgs &args,
+cudaError_t launch_ell_spmv(const EllLaunchCfg &cfg, const EllSpmvArgs &args_in,
                             int64_t num_slices, cudaStream_t stream)
 {
     if (num_slices <= 0) return cudaSuccess;
+    EllSpmvArgs args = args_in;
+    // experiments: ELLSPMV_CUDA_PREFETCH_SLICES overrides the prefetch distance (0 = off)
+    static const int prefetch_env = getenv("ELLSPMV_CUDA_PREFETCH_SLICES") ? atoi(getenv("ELLSPMV_CUDA_PREFETCH_SLICES")) : -1;
+    if (prefetch_env >= 0) args.prefetch = prefetch_env;
     if (num_slices > 0x7fffffffLL) return cudaErrorInvalidValue;
     if ((cfg.variant & 1) && args.num_rows > 0) {
         bool handled = false;
