@@ -242,7 +242,9 @@ int launch(ellspmv_cuda_matrix *A, double *y_dev, const double *x_dev, int beta,
     args.patid = A->pat.patid;
     args.pat = A->pat.pat;
     // value-stream L2 prefetch 128 slices ahead when most rows are patterned (ell_kernels.cu)
-    args.prefetch = (A->pat.patid && A->pat.covered * 2 >= A->pat.groups) ? 128 : 0;
+    // (long rows have the loads in flight anyway; keep one request at or below 256 KB)
+    args.prefetch = (A->pat.patid && A->pat.covered * 2 >= A->pat.groups &&
+                     (int64_t)A->lay.slice_rows * A->lay.rowsize * 8 <= (1 << 18)) ? 128 : 0;
     if (num_slices < 0) num_slices = A->lay.num_slices - slice_begin;
     if (push) args.push = *push; else args.push.num_peers = 0;
     if (A->sg && slice_begin == 0 && num_slices == A->lay.num_slices) {
