@@ -86,12 +86,16 @@ def main():
             for mode_name, mode in (("accumulate", E.ACCUMULATE), ("overwrite", E.OVERWRITE)):
                 med, best, avg = time_launches(lambda: A.spmv_device(y, x, mode, sptr), args.reps)
                 b = rows * K * (8 + bits // 8) + 8 * ncols + 8 * rows * (2 if mode == E.ACCUMULATE else 1)
-                stored = rows * K * (8 + i.dev_idx_bits // 8) + 8 * ncols + 8 * rows * (2 if mode == E.ACCUMULATE else 1)
+                # bytes the kernel really streams: narrowed indices, and none at all for patterned rows
+                stored = (rows * K * 8 + (rows - i.pattern_rows) * K * (i.dev_idx_bits // 8) + 8 * ncols
+                          + 8 * rows * (2 if mode == E.ACCUMULATE else 1))
                 print(json.dumps({"config": name, "kind": kind_name, "dims": dims, "idx_bits": bits, "variant": vname,
                                   "mode": mode_name, "ms_median": round(med, 4), "ms_best": round(best, 4),
                                   "ms_avg": round(avg, 4), "gflops": round(2.0 * rows * K / med * 1e-6, 1),
                                   "gbs_effective": round(b / med * 1e-6, 1), "frac_of_measured_peak": round(b / med * 1e-6 / peak, 4),
-                                  "gbs_as_stored": round(stored / med * 1e-6, 1)}), flush=True)
+                                  "gbs_as_stored": round(stored / med * 1e-6, 1),
+                                  "rows_per_thread": i.rows_per_thread,
+                                  "pattern_rows_frac": round(i.pattern_rows / max(rows, 1), 4)}), flush=True)
             A.free()
             del x, y
         if name == "c4" and not args.no_csr:
