@@ -475,3 +475,76 @@ def test_offset_patterns_in_a_row_shard(lib, oracle):
     A.spmv(y, x, 1, E.OVERWRITE)
     assert bits_equal(y, want[lo:hi])
     A.free()
+
+
+def expected_pattern_rows(ec, K, nr, R, row_begin=0, max_patterns=16):
+    """numpy restatement of the upload-time pattern search (pattern.cu) for matrices small
+    enough that every group is sampled: groups of 32*R rows sharing one offset vector, kept
+    if that vector is among the 16 most common (ties: first seen), dropped below 10 % coverage."""
+    S = 128 * R
+    G = 32 * R
+    padded = -(-nr // S) * S
+    groups = padded // G
+    off = ec.reshape(nr, K).astype(np.int64) - (row_begin + np.arange(nr, dtype=np.int64))[:, None]
+    sig = {}
+    uniform = []
+    for g in range(groups):
+        lo, hi = g * G, (g + 1) * G
+        if hi > nr:
+            uniform.append(None)
+            continue
+        blk = off[lo:hi]
+        if (blk == blk[0]).all():
+            key = tuple(blk[0])
+            uniform.append(key)
+            cnt, first = sig.get(key, (0, g))
+            sig[key] = (cnt + 1, first)
+        else:
+            uniform.append(None)
+    best = sorted(sig.items(), key=lambda kv: (-kv[1][0], kv[1][1]))[:max_patterns]
+    keep = {k for k, _ in best}
+    covered = sum(1 for u in uniform if u is not None and u in keep)
+    return covered * G if covered * 10 >= groups else 0
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_offset_patterns_randomized(lib, oracle, seed):
+    """Random banded matrices with random damage, every rows-per-thread choice, both index
+    widths, whole matrices and row shards: the patterned rows are exactly the ones the numpy
+    restatement finds, and y is the oracle's bit for bit."""
+    rng = np.random.default_rng(1000 + seed)
+    K = int(rng.integers(1, 13))
+    nr = int(rng.integers(40, 4000))
+    nc = nr + int(rng.integers(0, 50))
+    dt = np.int32 if seed % 2 == 0 else np.int64
+    offsets = sorted(int(v) for v in rng.integers(-60, 60, K))
+    ec, ea = banded_ell(nr, nc, offsets, dt, rng)
+    ec = ec.reshape(nr, K)
+    for _ in range(int(rng.integers(0, 6))):                       # damage a few entries
+        ec[int(rng.integers(0, nr)), int(rng.integers(0, K))] = int(rng.integers(0, nc))
+    if seed % 3 == 0:                                               # a second family of rows
+        lo = (nr // 2 // 128) * 128
+        ec[lo:, 0] = np.minimum(np.arange(lo, nr) + 3, nc - 1)
+    ec = ec.reshape(-1)
+    x = rng.standard_normal(nc)
+    want = np.zeros(nr)
+    oracle.ellgemv(nr, want, x, K, ec, ea)
+    auto_R = 4 if K <= 6 else (2 if K <= 12 else 1)
+    for R in (0, 1, 2, 4):
+        A = E.EllMatrix.upload(nr, nc, K, ec, ea, E.rows_per_thread(R) if R else 0)
+        info = A.info()
+        assert info.rows_per_thread == (R or auto_R)
+        assert info.pattern_rows == expected_pattern_rows(ec, K, nr, R or auto_R), (seed, K, nr, R)
+        y = rng.standard_normal(nr)
+        A.spmv(y, x, 1, E.OVERWRITE)
+        assert bits_equal(y, want), (seed, K, nr, R)
+        A.free()
+    # a row shard: local rows, global columns
+    lo, hi = nr // 5, nr - nr // 7
+    A = E.EllMatrix.upload(hi - lo, nc, K, ec[lo * K:hi * K], ea[lo * K:hi * K], E.rows_per_thread(1),
+                           global_rows=nr, row_begin=lo)
+    assert A.info().pattern_rows == expected_pattern_rows(ec[lo * K:hi * K], K, hi - lo, 1, row_begin=lo)
+    y = np.zeros(hi - lo)
+    A.spmv(y, x, 1, E.OVERWRITE)
+    assert bits_equal(y, want[lo:hi])
+    A.free()
