@@ -67,12 +67,12 @@ int configure(ellspmv_cuda_matrix *A, unsigned flags)
     A->flags = flags;
     int R = (flags & ELLSPMV_CUDA_ROWS_PER_THREAD_MASK) >> ELLSPMV_CUDA_ROWS_PER_THREAD_SHIFT;
     // auto: enough loads in flight per thread to cover the HBM latency.  With long rows one
-    // row per thread does it (K = 27: R = 1 / 2 / 4 give 2.61 / 2.69 / 2.71 ms on BASELINE
-    // config 3); with K = 5 a thread that owns one row has 48 bytes in flight and the kernel is
-    // latency-bound as soon as the offset patterns (pattern.cu) take the index stream away:
-    // 0.747 / 0.675 / 0.668 ms on config 2 (profiles/r1_offset_patterns.md).  In between is
-    // interpolated: about 20 matrix entries per thread.
-    if (R == 0) R = A->lay.rowsize <= 6 ? 4 : (A->lay.rowsize <= 12 ? 2 : 1);
+    // row per thread does it and keeps the pattern groups small (K = 27: R = 1 / 2 / 4 give
+    // 2.09 / 2.57 / 2.71 ms on BASELINE config 3, coverage 83 / 67 / 33 %); with K = 5 a thread
+    // that owns one row has 48 bytes in flight and the kernel is latency-bound once the offset
+    // patterns (pattern.cu) take the index stream away: 0.649 / 0.603 / 0.608 ms on config 2
+    // (profiles/r1_offset_patterns.md).  The boundary at K = 12 is interpolated.
+    if (R == 0) R = A->lay.rowsize <= 12 ? 2 : 1;
     if (R != 1 && R != 2 && R != 4) ELL_FAIL(EINVAL, "rows per thread must be 1, 2 or 4 (got %d)", R);
     int kernel = flags & ELLSPMV_CUDA_KERNEL_MASK;
     if (kernel == ELLSPMV_CUDA_KERNEL_AUTO) kernel = ELLSPMV_CUDA_KERNEL_THREAD;

@@ -470,7 +470,7 @@ def test_offset_patterns_in_a_row_shard(lib, oracle):
     oracle.ellgemv(nr, want, x, 4, ec, ea)
     lo, hi = 1111, 2777
     A = E.EllMatrix.upload(hi - lo, nc, 4, ec[lo * 4:hi * 4], ea[lo * 4:hi * 4], global_rows=nr, row_begin=lo)
-    assert A.info().pattern_rows >= (hi - lo) - 256        # K = 4: four rows per thread, groups of 128
+    assert A.info().pattern_rows >= (hi - lo) - 128        # K = 4: two rows per thread, groups of 64
     y = np.zeros(hi - lo)
     A.spmv(y, x, 1, E.OVERWRITE)
     assert bits_equal(y, want[lo:hi])
@@ -529,7 +529,7 @@ def test_offset_patterns_randomized(lib, oracle, seed):
     x = rng.standard_normal(nc)
     want = np.zeros(nr)
     oracle.ellgemv(nr, want, x, K, ec, ea)
-    auto_R = 4 if K <= 6 else (2 if K <= 12 else 1)
+    auto_R = 2 if K <= 12 else 1
     for R in (0, 1, 2, 4):
         A = E.EllMatrix.upload(nr, nc, K, ec, ea, E.rows_per_thread(R) if R else 0)
         info = A.info()
