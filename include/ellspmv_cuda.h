@@ -94,7 +94,8 @@ enum {
      * unchanged; only the index bytes of patterned rows are no longer read.
      * NO_PATTERN keeps every group on the explicit index stream. */
     ELLSPMV_CUDA_NO_PATTERN     = 1 << 18,
-    /* rows handled per thread in the thread-per-row kernel: 0 = auto */
+    /* rows handled per thread in the thread-per-row kernel (1, 2 or 4):
+     * 0 = auto = 2 for rows of at most 12 entries, else 1 */
     ELLSPMV_CUDA_ROWS_PER_THREAD_SHIFT = 8,
     ELLSPMV_CUDA_ROWS_PER_THREAD_MASK  = 0x7 << 8,
     /* kernel variant for experiments (0 = default direct loads,
