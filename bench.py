@@ -396,7 +396,7 @@ def main_ours(args, rank: int, local_rank: int, world: int):
                    "parallelism": f"rowshard{world}"},
         "gbs": round(achieved * world, 1),
         "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                     "frac": round(achieved / peak, 4), "traffic": recorded_traffic(workload if world == 1 else "sharded"),
+                     "frac": round(achieved / peak, 4), "traffic": recorded_traffic((workload + ("_staged" if flags & (1 << 17) else "")) if world == 1 else "sharded"),
                      "peak_source": peak_src, "bytes_per_launch": bytes_launch,
                      "bytes_model": f"K*(8+{idx_bits // 8})*rows + 8*x_touched + 8*rows" + (" + 8*rows (y is read-modify-written)" if y_rmw else ""),
                      "achieved_as_stored": round(bytes_stored / (ms_per_step * 1e-3) * 1e-9, 1),
