@@ -12,7 +12,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
-GOLDEN_CASES = ["test_mtx", "rand_wide", "rand_tall", "rand_square", "rand_sparse_rows", "long_rows", "one_row", "empty"]
+GOLDEN_CASES = ["test_mtx", "rand_wide", "rand_tall", "rand_square", "rand_sparse_rows", "long_rows", "one_row", "empty", "grid5"]
 
 
 def pytest_configure(config):

@@ -198,6 +198,22 @@ def main():
         cases.append(case_sd("sd_k16", n, ri, ci, rng.uniform(-2, 2, len(ri)).tolist(),
                              rng.uniform(-1, 1, n).tolist(), rng.uniform(-1, 1, n).tolist(), tmp))
 
+        # 5. a structured grid (2D 5-point stencil) with variable coefficients, entries in the order of
+        #    whole groups of 32 / 64 rows share one vector of column offsets, so the
+        #    device's offset-pattern path (pattern.cu) is pinned to the reference's own output
+        rng = np.random.default_rng(99)
+        nx, ny = 3, 200      # grid lines of 200 rows: most groups of 32 / 64 rows lie inside one line
+        ri, ci = [], []
+        for i in range(nx):
+            for j in range(ny):
+                r = i * ny + j
+                for di, dj in ((-1, 0), (0, -1), (0, 0), (0, 1), (1, 0)):
+                    if 0 <= i + di < nx and 0 <= j + dj < ny:
+                        ri.append(r + 1); ci.append((i + di) * ny + (j + dj) + 1)
+        n = nx * ny
+        cases.append(case("grid5", n, n, ri, ci, rng.uniform(-2, 2, len(ri)).tolist(),
+                          rng.uniform(-1, 1, n).tolist(), rng.uniform(-1, 1, n).tolist(), tmp))
+
     for c in cases:
         # tmp paths differ run to run; nothing in stdout depends on them
         with open(os.path.join(HERE, c["name"] + ".json"), "w") as f:
