@@ -27,9 +27,10 @@
 // 28.2 ms for the direct gather, same bits.  Phase 2 runs at 103 % of the measured
 // HBM copy peak (4.4 ms, ncu DRAM traffic = its algorithmic 29.7 GB).  Phase 1
 // (9.2 ms) keeps the SM -> L2 request port 91 % busy (every gathered value is its
-// own line request) at 174 G gathers/s, HBM only 28 % busy; a pure-gather
-// micro-benchmark reaches ~300 G/s on the same path (profiles/r1_gather_paths.md),
-// so a persistent phase 1 with longer-lived threads is the next step.  Running
+// own line request) at 174 G gathers/s, HBM only 28 % busy.  A pure-gather
+// micro-benchmark reaches ~300 G/s on the same path, but a persistent phase 1
+// with 2-4x the loads in flight measures the same 176 G/s: the index stream in
+// and the value stream out share that port (profiles/r1_gather_paths.md).  Running
 // phase 2 of one row panel next to phase 1 of the next (two streams, priorities)
 // was tried and LOSES (14.7-17.7 ms): not kept.
 // An L2 persisting window over the x block changes nothing here (13.62 ms with

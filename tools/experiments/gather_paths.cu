@@ -128,6 +128,56 @@ __global__ void __launch_bounds__(128) bulk_kernel(const double *__restrict__ ta
     if (acc == 1.2345e300) out[tid] = acc;
 }
 
+// ---- phase1: the staged gather's phase 1 in isolation -- indices streamed from HBM, gathered
+// values streamed back -- with short-lived threads (one group of 4 per thread, as shipped in
+// round 1) and with persistent threads (grid-stride over G groups, all index loads of a batch
+// first, then all gathers, then the stores)
+__global__ void fill_index_kernel(int *__restrict__ idx, int64_t n, uint32_t mask)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        idx[i] = (int)(mix32((uint32_t)i * 2654435761U + (uint32_t)(i >> 32)) & mask);
+}
+
+__global__ void __launch_bounds__(256) phase1_short_kernel(const int *__restrict__ idx, const double *__restrict__ table,
+                                                           double *__restrict__ xg, int64_t groups)
+{
+    const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (g >= groups) return;
+    const int4 c = __ldcs(reinterpret_cast<const int4 *>(idx) + g);
+    const double v0 = __ldg(table + c.x), v1 = __ldg(table + c.y), v2 = __ldg(table + c.z), v3 = __ldg(table + c.w);
+    __stcs(reinterpret_cast<double2 *>(xg) + 2 * g, make_double2(v0, v1));
+    __stcs(reinterpret_cast<double2 *>(xg) + 2 * g + 1, make_double2(v2, v3));
+}
+
+template <int G>
+__global__ void __launch_bounds__(256) phase1_persistent_kernel(const int *__restrict__ idx, const double *__restrict__ table,
+                                                                double *__restrict__ xg, int64_t groups)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t g0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g0 < groups; g0 += stride * G) {
+        int4 c[G];
+        double v[G][4];
+#pragma unroll
+        for (int j = 0; j < G; j++) {
+            const int64_t g = g0 + j * stride;
+            c[j] = g < groups ? __ldcs(reinterpret_cast<const int4 *>(idx) + g) : make_int4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int j = 0; j < G; j++) {
+            v[j][0] = __ldg(table + c[j].x); v[j][1] = __ldg(table + c[j].y);
+            v[j][2] = __ldg(table + c[j].z); v[j][3] = __ldg(table + c[j].w);
+        }
+#pragma unroll
+        for (int j = 0; j < G; j++) {
+            const int64_t g = g0 + j * stride;
+            if (g < groups) {
+                __stcs(reinterpret_cast<double2 *>(xg) + 2 * g, make_double2(v[j][0], v[j][1]));
+                __stcs(reinterpret_cast<double2 *>(xg) + 2 * g + 1, make_double2(v[j][2], v[j][3]));
+            }
+        }
+    }
+}
+
 static float time_ms(cudaEvent_t a, cudaEvent_t b) { float ms = 0; CK(cudaEventElapsedTime(&ms, a, b)); return ms; }
 
 int main()
@@ -188,6 +238,41 @@ int main()
         CK(cudaDeviceSynchronize());
         printf("{\"path\": \"dsmem\", \"cluster\": 8, \"table_MB\": %.2f, \"sms_used\": %d, \"gathers\": %.3g, \"ms\": %.3f, \"Ggathers_per_s\": %.1f, \"scaled_to_all_sms\": %.1f}\n",
                8 * words * 8 / 1e6, grid, n, time_ms(e0, e1), n / time_ms(e0, e1) * 1e-6, n / time_ms(e0, e1) * 1e-6 * sms / grid);
+    }
+
+    // ---- phase 1 in isolation: 200 M entries (one column block of BASELINE config 4), 48 MB table
+    {
+        const int64_t n = 200LL * 1000 * 1000, groups = n / 4;
+        const uint32_t words = 6u << 20;                     // 48 MB of doubles; mask below keeps 32 MB of it hot
+        int *idx; double *table, *xg;
+        CK(cudaMalloc(&idx, (size_t)n * 4)); CK(cudaMalloc(&table, (size_t)words * 8)); CK(cudaMalloc(&xg, (size_t)n * 8));
+        CK(cudaMemset(table, 0, (size_t)words * 8));
+        fill_index_kernel<<<sms * 8, 256>>>(idx, n, (4u << 20) - 1);
+        auto report = [&](const char *name, int per_thread) {
+            CK(cudaDeviceSynchronize());
+            printf("{\"path\": \"phase1\", \"variant\": \"%s\", \"groups_per_thread_batch\": %d, \"entries\": %.3g, \"ms\": %.3f, \"Ggathers_per_s\": %.1f}\n",
+                   name, per_thread, (double)n, time_ms(e0, e1), (double)n / time_ms(e0, e1) * 1e-6);
+        };
+        const unsigned short_grid = (unsigned)((groups + 255) / 256);
+        phase1_short_kernel<<<short_grid, 256>>>(idx, table, xg, groups);
+        CK(cudaEventRecord(e0));
+        phase1_short_kernel<<<short_grid, 256>>>(idx, table, xg, groups);
+        CK(cudaEventRecord(e1));
+        report("short-lived threads (round 1)", 1);
+        for (int ctas_per_sm : {4, 8}) {
+            const unsigned grid = (unsigned)(sms * ctas_per_sm);
+            phase1_persistent_kernel<2><<<grid, 256>>>(idx, table, xg, groups);
+            CK(cudaEventRecord(e0));
+            phase1_persistent_kernel<2><<<grid, 256>>>(idx, table, xg, groups);
+            CK(cudaEventRecord(e1));
+            report(ctas_per_sm == 4 ? "persistent, 4 CTAs/SM" : "persistent, 8 CTAs/SM", 2);
+            phase1_persistent_kernel<4><<<grid, 256>>>(idx, table, xg, groups);
+            CK(cudaEventRecord(e0));
+            phase1_persistent_kernel<4><<<grid, 256>>>(idx, table, xg, groups);
+            CK(cudaEventRecord(e1));
+            report(ctas_per_sm == 4 ? "persistent, 4 CTAs/SM" : "persistent, 8 CTAs/SM", 4);
+        }
+        CK(cudaFree(idx)); CK(cudaFree(table)); CK(cudaFree(xg));
     }
 
     // ---- bulk: 16-byte copies from a 32 MB table
