@@ -79,6 +79,8 @@ _PROTOTYPES = {
     "ellspmv_cuda_spmv": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P]),
     "ellspmv_cuda_spmv_device": (C.c_int, [_P, _P, _P, C.c_int, _P]),
     "ellspmv_cuda_spmv_push": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.POINTER(_P), C.POINTER(_I64), C.POINTER(_I64), _P]),
+    "ellspmv_cuda_spmv_exchange": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.POINTER(_P), C.POINTER(_I64), C.POINTER(_I64),
+                                             C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(_P), _P, _I64, _P]),
     "ellspmv_cuda_set_diagonal": (C.c_int, [_P, _P, C.c_int]),
     "csrspmv_cuda_set_diagonal": (C.c_int, [_P, _P]),
     "ellspmv_cuda_download": (C.c_int, [_P, _P, _P]),
@@ -240,6 +242,21 @@ class EllMatrix:
         err = load_library().ellspmv_cuda_spmv_push(self._h, _ptr(y_dev), _ptr(x_dev), mode, n, px, lo, hi,
                                                     stream or None)
         _check(err, "ellspmv_cuda_spmv_push")
+
+    def spmv_exchange(self, y_dev, x_dev, mode: int, peer_x: Sequence[int], row_lo: Sequence[int],
+                      row_hi: Sequence[int], rank: int, sync_ranks: Sequence[int], sync_flags: Sequence[int],
+                      local_flags: int, epoch: int, stream: int = 0) -> None:
+        """Fused SpMV + push + step signalling (ellspmv_cuda_spmv_exchange)."""
+        n = len(peer_x)
+        px = (C.c_void_p * max(n, 1))(*peer_x)
+        lo = (C.c_int64 * max(n, 1))(*row_lo)
+        hi = (C.c_int64 * max(n, 1))(*row_hi)
+        m = len(sync_ranks)
+        sr = (C.c_int * max(m, 1))(*sync_ranks)
+        sf = (C.c_void_p * max(m, 1))(*sync_flags)
+        err = load_library().ellspmv_cuda_spmv_exchange(self._h, _ptr(y_dev), _ptr(x_dev), mode, n, px, lo, hi,
+                                                        rank, m, sr, sf, local_flags, epoch, stream or None)
+        _check(err, "ellspmv_cuda_spmv_exchange")
 
     def set_diagonal(self, ad, order: int = 0) -> None:
         """y <- y + (ad.*x + A*x): the reference's ellgemvsd (order 0) / ellgemv16sd (order 1)."""

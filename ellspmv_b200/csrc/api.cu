@@ -146,9 +146,13 @@ int finish_minmax(ellspmv_cuda_matrix *A)
     A->min_col = mm[0];
     A->max_col = mm[1];
     warm_kernels(A);
-    if (A->max_col >= A->num_columns || (A->max_col >= 0 && A->min_col < 0))
+    // the max accumulator starts at -1 and negative indices never raise it, so the lower
+    // bound is checked on its own (min still at its start value = no entries at all)
+    const bool any = mm[0] != 0x7fffffffffffffffLL;
+    if (any && (mm[0] < 0 || mm[1] >= A->num_columns))
         ELL_FAIL(EINVAL, "column index out of range: [%lld, %lld] with %lld columns",
-                 mm[0], mm[1], (long long)A->num_columns);
+                 mm[0], mm[1] < mm[0] ? mm[0] : mm[1], (long long)A->num_columns);
+    if (!any) { A->min_col = 0; A->max_col = -1; }
     return 0;
 }
 
@@ -211,6 +215,24 @@ int ensure_vectors(ellspmv_cuda_matrix *A)
     return 0;
 }
 
+// The part of x a handle's kernels read: the column range its stored entries reference
+// ([min_col, max_col], from the upload-time reduction) plus, with a separately stored
+// diagonal, its own global rows.  The host-vector calls upload only this range: a row shard
+// of a stencil needs its own slice and two halo planes, not all of x (the reference passes
+// the whole x to every thread, ellspmv.c:1841-1842; over PCIe that would be N copies of it).
+void x_range(const ellspmv_cuda_matrix *A, int64_t *lo, int64_t *hi)
+{
+    int64_t a = A->min_col, b = A->max_col + 1;
+    if (b <= a) { a = 0; b = 0; }
+    if (A->d_ad && A->lay.num_rows > 0) {
+        const int64_t r0 = A->row_begin, r1 = A->row_begin + A->lay.num_rows;
+        if (b <= a) { a = r0; b = r1; }
+        else { a = r0 < a ? r0 : a; b = r1 > b ? r1 : b; }
+    }
+    if (b > A->num_columns) b = A->num_columns;
+    *lo = a; *hi = b;
+}
+
 int ensure_events(std::vector<cudaEvent_t> &ev, size_t n)
 {
     while (ev.size() < n) {
@@ -222,10 +244,19 @@ int ensure_events(std::vector<cudaEvent_t> &ev, size_t n)
 }
 
 int launch(ellspmv_cuda_matrix *A, double *y_dev, const double *x_dev, int beta,
-           const PushTargets *push, cudaStream_t stream, int64_t slice_begin = 0, int64_t num_slices = -1);
+           const PushTargets *push, cudaStream_t stream, int64_t slice_begin = 0, int64_t num_slices = -1,
+           const StepSync *sync = nullptr);
+
+// can this handle's SpMV launch carry the fused step synchronisation (ell_thread_kernel only)?
+bool fused_sync_capable(const ellspmv_cuda_matrix *A)
+{
+    return A->cfg.kernel == ELLSPMV_CUDA_KERNEL_THREAD && !(A->cfg.variant & 1) && !A->sg && !A->cb &&
+           A->lay.rowsize > 0 && A->lay.num_rows > 0;
+}
 
 int launch(ellspmv_cuda_matrix *A, double *y_dev, const double *x_dev, int beta,
-           const PushTargets *push, cudaStream_t stream, int64_t slice_begin, int64_t num_slices)
+           const PushTargets *push, cudaStream_t stream, int64_t slice_begin, int64_t num_slices,
+           const StepSync *sync)
 {
     EllSpmvArgs args = {};
     args.vals = A->vals;
@@ -247,6 +278,7 @@ int launch(ellspmv_cuda_matrix *A, double *y_dev, const double *x_dev, int beta,
                      (int64_t)A->lay.slice_rows * A->lay.rowsize * 8 <= (1 << 18)) ? 128 : 0;
     if (num_slices < 0) num_slices = A->lay.num_slices - slice_begin;
     if (push) args.push = *push; else args.push.num_peers = 0;
+    if (sync) args.sync = *sync;          // only passed for a full launch of a fused_sync_capable handle
     if (A->sg && slice_begin == 0 && num_slices == A->lay.num_slices) {
         ELL_CK(sg_spmv(A->sg, A->cfg.fma, A->vals, x_dev, y_dev, A->d_ad, A->sd_order, A->lay.num_rows,
                        A->row_begin, beta, push, stream));
@@ -285,7 +317,10 @@ int spmv_pipelined(ellspmv_cuda_matrix *A, double *y, const double *x, int beta,
     if (err) return err;
     if (!A->stream_out) ELL_CK(cudaStreamCreateWithFlags(&A->stream_out, cudaStreamNonBlocking));
     cudaStream_t s = A->stream, so = A->stream_out;
-    ELL_CK(cudaMemcpyAsync(A->d_x, x, (size_t)ncols * 8, cudaMemcpyDefault, s));
+    int64_t xlo, xhi;
+    x_range(A, &xlo, &xhi);
+    (void)ncols;
+    if (xhi > xlo) ELL_CK(cudaMemcpyAsync(A->d_x + xlo, x + xlo, (size_t)(xhi - xlo) * 8, cudaMemcpyDefault, s));
     int used = 0;
     for (int c = 0; c < nchunks; c++) {
         const int64_t s0 = c * chunk_slices;
@@ -356,6 +391,46 @@ int launch_shard(ellspmv_cuda_matrix *A, double *y_dev, const double *x_dev, int
     return launch(A, y_dev, x_dev, beta, push, stream, 0, -1);
 }
 int ensure_event_count(std::vector<cudaEvent_t> &ev, size_t n) { return ensure_events(ev, n); }
+
+int launch_shard_exchange(ellspmv_cuda_matrix *A, double *y_dev, const double *x_dev, int beta,
+                          const PushTargets *push, StepSync sync, cudaStream_t stream)
+{
+    if (!fused_sync_capable(A)) {
+        // kernels without the fused form: push, then signal + wait in a one-warp kernel
+        int err = launch(A, y_dev, x_dev, beta, push, stream, 0, -1);
+        if (err) return err;
+        ELL_CK(launch_peer_sync(sync, stream));
+        return 0;
+    }
+    if (!A->d_remote) {
+        // one-off: which slices read columns outside this shard's own (16-aligned) row range
+        const int64_t lo = (A->row_begin + 15) & ~(int64_t)15;
+        const int64_t hi = (A->row_begin + A->lay.num_rows) & ~(int64_t)15;
+        ELL_CK(cudaMalloc(&A->d_remote, (size_t)A->lay.num_slices));
+        ELL_CK(cudaMalloc(&A->d_done, sizeof(unsigned)));
+        ELL_CK(cudaMemsetAsync(A->d_done, 0, sizeof(unsigned), A->stream));
+        ELL_CK(mark_remote_slices(A->dev_idx_bits, A->cols, A->lay, lo, hi, A->d_remote, A->stream));
+        ELL_CK(cudaStreamSynchronize(A->stream));
+        A->device_bytes += A->lay.num_slices + 4;
+    }
+    sync.done = A->d_done;
+    sync.remote = A->d_remote;
+    return launch(A, y_dev, x_dev, beta, push, stream, 0, -1, &sync);
+}
+void shard_x_range(const ellspmv_cuda_matrix *A, int64_t *lo, int64_t *hi) { x_range(A, lo, hi); }
+// same for a CSR handle: the stored column range, plus its own global rows with csrgemvsd's diagonal
+void csr_x_range(const csrspmv_cuda_matrix *A, int64_t *lo, int64_t *hi)
+{
+    int64_t a = A->min_col, b = A->max_col + 1;
+    if (b <= a) { a = 0; b = 0; }
+    if (A->d_ad && A->num_rows > 0) {
+        const int64_t r0 = A->row_begin, r1 = A->row_begin + A->num_rows;
+        if (b <= a) { a = r0; b = r1; }
+        else { a = r0 < a ? r0 : a; b = r1 > b ? r1 : b; }
+    }
+    if (b > A->num_columns) b = A->num_columns;
+    *lo = a; *hi = b;
+}
 }  // namespace ellspmv
 
 extern "C" {
@@ -389,6 +464,8 @@ void ellspmv_cuda_free(ellspmv_cuda_matrix *A)
     if (A->cols) cudaFree(A->cols);
     if (A->d_minmax) cudaFree(A->d_minmax);
     if (A->d_ad) cudaFree(A->d_ad);
+    if (A->d_remote) cudaFree(A->d_remote);
+    if (A->d_done) cudaFree(A->d_done);
     pattern_free(&A->pat);
     if (A->cb) cb_free(A->cb);
     if (A->sg) sg_free(A->sg);
@@ -704,6 +781,50 @@ int ellspmv_cuda_spmv_push(
     return launch(A, y_dev, x_dev, mode == ELLSPMV_CUDA_ACCUMULATE ? 1 : 0, &pt, (cudaStream_t)stream);
 }
 
+int ellspmv_cuda_spmv_exchange(
+    ellspmv_cuda_matrix *A, double *y_dev, const double *x_dev, int mode,
+    int num_peers, double *const *peer_x, const int64_t *peer_row_lo, const int64_t *peer_row_hi,
+    int rank, int num_sync, const int *sync_ranks, int64_t *const *sync_flags,
+    int64_t *local_flags, int64_t epoch, void *stream)
+{
+    if (!A) ELL_FAIL(EINVAL, "matrix is NULL");
+    if (!A->shards.empty()) ELL_FAIL(EINVAL, "spmv_exchange needs a single-GPU handle");
+    if (mode != ELLSPMV_CUDA_ACCUMULATE && mode != ELLSPMV_CUDA_OVERWRITE)
+        ELL_FAIL(EINVAL, "spmv_exchange: mode must be ACCUMULATE or OVERWRITE");
+    if (num_peers < 0 || num_peers > kMaxPeers) ELL_FAIL(EINVAL, "num_peers must be 0..%d", kMaxPeers);
+    if (num_peers > 0 && (!peer_x || !peer_row_lo || !peer_row_hi)) ELL_FAIL(EINVAL, "NULL peer arrays");
+    if (num_sync < 0 || num_sync > kMaxPeers) ELL_FAIL(EINVAL, "num_sync must be 0..%d", kMaxPeers);
+    if (num_sync > 0 && (!sync_ranks || !sync_flags)) ELL_FAIL(EINVAL, "NULL sync arrays");
+    if (!local_flags) ELL_FAIL(EINVAL, "local_flags is NULL");
+    if (rank < 0 || rank >= kMaxRanks) ELL_FAIL(EINVAL, "rank %d out of range (max %d ranks)", rank, kMaxRanks);
+    if (epoch < 1) ELL_FAIL(EINVAL, "epoch must be >= 1");
+    if (A->lay.num_rows > 0 && (!y_dev || (!x_dev && A->lay.rowsize > 0)))
+        ELL_FAIL(EINVAL, "NULL device vector");
+    PushTargets pt = {};
+    pt.num_peers = num_peers;
+    for (int p = 0; p < num_peers; p++) {
+        if (!peer_x[p]) ELL_FAIL(EINVAL, "peer_x[%d] is NULL", p);
+        pt.x[p] = peer_x[p];
+        pt.row_lo[p] = peer_row_lo[p];
+        pt.row_hi[p] = peer_row_hi[p];
+    }
+    StepSync sy = {};
+    sy.local_flags = reinterpret_cast<long long *>(local_flags);
+    sy.num_peers = num_sync;
+    sy.rank = rank;
+    sy.epoch = (long long)epoch;
+    sy.error = reinterpret_cast<int *>(local_flags + kMaxRanks);
+    for (int p = 0; p < num_sync; p++) {
+        if (!sync_flags[p]) ELL_FAIL(EINVAL, "sync_flags[%d] is NULL", p);
+        if (sync_ranks[p] < 0 || sync_ranks[p] >= kMaxRanks) ELL_FAIL(EINVAL, "sync_ranks[%d] out of range", p);
+        sy.peer_flags[p] = reinterpret_cast<long long *>(sync_flags[p]);
+        sy.peer_rank[p] = sync_ranks[p];
+    }
+    DeviceGuard g(A->device);
+    return launch_shard_exchange(A, y_dev, x_dev, mode == ELLSPMV_CUDA_ACCUMULATE ? 1 : 0, &pt, sy,
+                                 (cudaStream_t)stream);
+}
+
 int ellspmv_cuda_spmv(
     ellspmv_cuda_matrix *A, double *y, const double *x,
     int repeat, int mode, double *seconds)
@@ -725,7 +846,9 @@ int ellspmv_cuda_spmv(
         return spmv_pipelined(A, y, x, mode == ELLSPMV_CUDA_ACCUMULATE ? 1 : 0, seconds);
     if ((err = ensure_events(A->events, (size_t)repeat + 1))) return err;
     cudaStream_t s = A->stream;
-    if (ncols > 0) ELL_CK(cudaMemcpyAsync(A->d_x, x, (size_t)ncols * 8, cudaMemcpyDefault, s));
+    int64_t xlo = 0, xhi = ncols;
+    if (mode != ELLSPMV_CUDA_ITERATE) x_range(A, &xlo, &xhi);      // ITERATE: every entry becomes an output
+    if (xhi > xlo) ELL_CK(cudaMemcpyAsync(A->d_x + xlo, x + xlo, (size_t)(xhi - xlo) * 8, cudaMemcpyDefault, s));
     if (mode == ELLSPMV_CUDA_ACCUMULATE && rows > 0)
         ELL_CK(cudaMemcpyAsync(A->d_y, y, (size_t)rows * 8, cudaMemcpyDefault, s));
     double *cur = A->d_x, *nxt = A->d_y;
@@ -764,6 +887,7 @@ void csrspmv_cuda_free(csrspmv_cuda_matrix *A)
     for (cudaEvent_t e : A->events) cudaEventDestroy(e);
     if (A->rowptr) cudaFree(A->rowptr);
     if (A->d_ad) cudaFree(A->d_ad);
+    if (A->d_scratch) cudaFree(A->d_scratch);
     if (A->cols) cudaFree(A->cols);
     if (A->vals) cudaFree(A->vals);
     if (A->d_x) cudaFree(A->d_x);
@@ -808,6 +932,7 @@ static int csr_new(csrspmv_cuda_matrix **out, int idx_width_bits, int64_t num_ro
     if ((ce = cudaMalloc(&A->vals, nz * 8)) != cudaSuccess) return fail(ce);
     if ((ce = cudaMalloc(&A->d_x, (size_t)(num_columns > 0 ? num_columns : 1) * 8)) != cudaSuccess) return fail(ce);
     if ((ce = cudaMalloc(&A->d_y, (size_t)(num_rows > 0 ? num_rows : 1) * 8)) != cudaSuccess) return fail(ce);
+    if ((ce = cudaMalloc(&A->d_scratch, 32)) != cudaSuccess) return fail(ce);
     if ((ce = cudaStreamCreateWithFlags(&A->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(ce);
     A->device_bytes = (num_rows + 1) * 8 + (int64_t)nz * (8 + idx_width_bits / 8) + (num_columns + num_rows) * 8;
     return 0;
@@ -817,7 +942,18 @@ static int csr_new(csrspmv_cuda_matrix **out, int idx_width_bits, int64_t num_ro
 // (37 vs 48 ms on BASELINE config 4), the smem-staged stream kernel when they are ragged
 static int csr_pick_kernel(csrspmv_cuda_matrix *A)
 {
-    ELL_CK(csr_max_row_len(A->rowptr, A->num_rows, &A->max_row_len, A->stream));
+    // the same checks an ELL upload makes: a bad rowptr or column index is EINVAL here,
+    // never an out-of-bounds gather in the kernels
+    CsrInspection in;
+    ELL_CK(csr_inspect(A->idx_bits, A->rowptr, A->cols, A->num_rows, A->csrsize, A->d_scratch, &in, A->stream));
+    if (in.bad_rows > 0)
+        ELL_FAIL(EINVAL, "rowptr is not non-decreasing (%lld row(s) end before they start)", (long long)in.bad_rows);
+    if (A->csrsize > 0 && (in.min_col < 0 || in.max_col >= A->num_columns))
+        ELL_FAIL(EINVAL, "column index out of range: [%lld, %lld] with %lld columns", (long long)in.min_col,
+                 (long long)in.max_col, (long long)A->num_columns);
+    A->max_row_len = in.max_row_len;
+    A->min_col = in.min_col;
+    A->max_col = in.max_col;
     if (!A->auto_kernel) return 0;
     const int64_t avg = A->num_rows > 0 ? (A->csrsize + A->num_rows - 1) / A->num_rows : 0;
     A->kernel = (A->max_row_len <= 4 * avg + 16) ? 3 : ELLSPMV_CUDA_KERNEL_THREAD;
@@ -912,7 +1048,8 @@ int csrspmv_cuda_set_diagonal(csrspmv_cuda_matrix *A, const double *ad)
         if (A->d_ad) { cudaFree(A->d_ad); A->d_ad = nullptr; }
         return 0;
     }
-    if (A->num_rows > A->num_columns)
+    // x[i] is read at the row's own GLOBAL index (a shard's rows start at row_begin)
+    if (A->row_begin + A->num_rows > A->num_columns)
         ELL_FAIL(EINVAL, "separate diagonal needs rows <= columns (csrgemvsd reads x[i] for every row i)");
     const size_t n = (size_t)(A->num_rows > 0 ? A->num_rows : 1);
     if (!A->d_ad) {
@@ -935,7 +1072,7 @@ int csrspmv_cuda_spmv_device(
     if (A->num_rows > 0 && (!y_dev || !x_dev)) ELL_FAIL(EINVAL, "NULL device vector");
     DeviceGuard g(A->device);
     CsrSpmvArgs args = {A->rowptr, A->cols, A->vals, x_dev, y_dev, A->num_rows,
-                        mode == ELLSPMV_CUDA_ACCUMULATE ? 1 : 0, A->d_ad};
+                        mode == ELLSPMV_CUDA_ACCUMULATE ? 1 : 0, A->d_ad, A->row_begin};
     ELL_CK(launch_csr_spmv(A->idx_bits, A->fma, A->kernel, args, (cudaStream_t)stream));
     return 0;
 }
@@ -955,13 +1092,15 @@ int csrspmv_cuda_spmv(
     int err = ensure_events(A->events, (size_t)repeat + 1);
     if (err) return err;
     cudaStream_t s = A->stream;
-    if (A->num_columns > 0) ELL_CK(cudaMemcpyAsync(A->d_x, x, (size_t)A->num_columns * 8, cudaMemcpyDefault, s));
+    int64_t xlo, xhi;
+    csr_x_range(A, &xlo, &xhi);
+    if (xhi > xlo) ELL_CK(cudaMemcpyAsync(A->d_x + xlo, x + xlo, (size_t)(xhi - xlo) * 8, cudaMemcpyDefault, s));
     if (mode == ELLSPMV_CUDA_ACCUMULATE && A->num_rows > 0)
         ELL_CK(cudaMemcpyAsync(A->d_y, y, (size_t)A->num_rows * 8, cudaMemcpyDefault, s));
     ELL_CK(cudaEventRecord(A->events[0], s));
     for (int r = 0; r < repeat; r++) {
         CsrSpmvArgs args = {A->rowptr, A->cols, A->vals, A->d_x, A->d_y, A->num_rows,
-                            mode == ELLSPMV_CUDA_ACCUMULATE ? 1 : 0, A->d_ad};
+                            mode == ELLSPMV_CUDA_ACCUMULATE ? 1 : 0, A->d_ad, A->row_begin};
         ELL_CK(launch_csr_spmv(A->idx_bits, A->fma, A->kernel, args, s));
         ELL_CK(cudaEventRecord(A->events[(size_t)r + 1], s));
     }
@@ -1076,7 +1215,8 @@ static __global__ void rebase_rowptr_kernel(int64_t *rowptr, int64_t n, int64_t 
 }
 
 int csr_upload_on(csrspmv_cuda_matrix **out, int idx_width_bits, int64_t num_rows, int64_t num_columns,
-                  const int64_t *rowptr, const void *colidx, const double *a, int device, unsigned flags)
+                  const int64_t *rowptr, const void *colidx, const double *a, int device, unsigned flags,
+                  int64_t row_begin)
 {
     if (!rowptr) ELL_FAIL(EINVAL, "rowptr is NULL");
     int err = check_device(&device);
@@ -1091,6 +1231,7 @@ int csr_upload_on(csrspmv_cuda_matrix **out, int idx_width_bits, int64_t num_row
     err = csr_new(out, idx_width_bits, num_rows, num_columns, csrsize, device, flags);
     if (err) return err;
     csrspmv_cuda_matrix *A = *out;
+    A->row_begin = row_begin;
     DeviceGuard g(A->device);
     const size_t ib = (size_t)idx_width_bits / 8;
     cudaError_t ce = cudaMemcpyAsync(A->rowptr, rowptr, (size_t)(num_rows + 1) * 8, cudaMemcpyDefault, A->stream);

@@ -58,4 +58,31 @@ cudaError_t launch_peer_barrier(int rank, int nranks, long long epoch, long long
     return cudaGetLastError();
 }
 
+__global__ void peer_sync_kernel(const StepSync a)
+{
+    const int p = threadIdx.x;
+    if (p >= a.num_peers) return;
+    __threadfence_system();
+    asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(a.peer_flags[p] + a.rank), "l"(a.epoch) : "memory");
+    const long long *src = a.local_flags + a.peer_rank[p];
+    const long long t0 = clock64();
+    long long seen;
+    for (;;) {
+        asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(seen) : "l"(src) : "memory");
+        if (seen >= a.epoch) break;
+        if (clock64() - t0 > 40000000000LL) {
+            if (a.error) *a.error = 1 + a.peer_rank[p];
+            break;
+        }
+        __nanosleep(64);
+    }
+}
+
+cudaError_t launch_peer_sync(const StepSync &sync, cudaStream_t stream)
+{
+    if (sync.num_peers <= 0) return cudaSuccess;
+    peer_sync_kernel<<<1, 32, 0, stream>>>(sync);
+    return cudaGetLastError();
+}
+
 }  // namespace ellspmv

@@ -70,6 +70,24 @@ struct PushTargets {
     int64_t  row_hi[kMaxPeers];
 };
 
+// ---- fused step synchronisation of the row-sharded y -> x loop (ell_kernels.cu) ----------
+// Instead of a barrier kernel between two steps, the SpMV kernel itself signals and waits:
+// its last CTA to finish stores the step number into slot [rank] of every listed rank's flag
+// array (peer-mapped HBM, system-scope release), and only the CTAs that read halo columns or
+// push to a peer wait -- at their start -- until the listed ranks have signalled the previous
+// step.  Interior CTAs never wait, so the flag round trip over NVLink hides behind them.
+struct StepSync {
+    long long *local_flags;            // this rank's flag array, slot [q] = last step rank q finished; NULL = off
+    long long *peer_flags[kMaxPeers];  // flag arrays of the ranks below (peer-mapped)
+    int        peer_rank[kMaxPeers];   // the ranks this one exchanges with (pushes to or is pushed by)
+    int        num_peers;
+    int        rank;
+    long long  epoch;                  // this step's number (>= 1): wait for epoch-1, signal epoch
+    unsigned  *done;                   // CTAs finished so far (device memory, zero between launches)
+    const unsigned char *remote;       // per slice: reads columns outside the 16-aligned local row range
+    int       *error;                  // set when a peer never showed up
+};
+
 struct EllSpmvArgs {
     const double *vals;     // sliced layout
     const void   *cols;     // sliced layout, int32 or int64
@@ -86,6 +104,7 @@ struct EllSpmvArgs {
     int           prefetch;     // slices ahead whose value stream is requested into L2 (0 = none)
     const unsigned char *patid; // offset patterns (pattern.cu): one id per warp (32*R rows), 0xff = explicit indices; or NULL
     const long long     *pat;   // dictionary [kMaxPatterns][K] of column offsets relative to the GLOBAL row
+    StepSync      sync;
 };
 
 struct EllLaunchCfg {
@@ -114,11 +133,14 @@ struct CsrSpmvArgs {
     double        *y;
     int64_t        num_rows;
     int            beta;
-    const double  *ad;      // separately stored diagonal, or NULL (csrgemvsd)
+    const double  *ad;      // separately stored diagonal of these rows, or NULL (csrgemvsd)
+    int64_t        row_begin; // global index of row 0 (a row block of a larger matrix): csrgemvsd reads x[global row]
 };
 cudaError_t launch_csr_spmv(int idx_bits, bool fma, int kernel, const CsrSpmvArgs &args,
                             cudaStream_t stream);
-cudaError_t csr_max_row_len(const int64_t *rowptr, int64_t num_rows, int64_t *max_len, cudaStream_t stream);
+struct CsrInspection { int64_t max_row_len, bad_rows, min_col, max_col; };
+cudaError_t csr_inspect(int idx_bits, const int64_t *rowptr, const void *cols, int64_t num_rows, int64_t csrsize,
+                        unsigned long long *scratch /* device, 32 bytes */, CsrInspection *res, cudaStream_t stream);
 
 // ---- layout / generators (layout.cu) -------------------------------------
 // row-major chunk (rows [row0, row0+rows) of the shard) -> sliced layout
@@ -138,6 +160,8 @@ cudaError_t generate_sliced(int kind, const int64_t dims[3], const double vals[2
 cudaError_t generate_csr_random(const int64_t dims[3], uint64_t seed, int idx_bits,
                                 int64_t *rowptr, void *cols, double *vals, cudaStream_t stream);
 cudaError_t init_minmax(long long *minmax, cudaStream_t stream);
+cudaError_t mark_remote_slices(int idx_bits, const void *cols, const EllLayout &lay, int64_t lo, int64_t hi,
+                               unsigned char *remote, cudaStream_t stream);
 
 // ---- offset patterns: groups of 32 rows whose column indices are row + d[l] (pattern.cu) ----
 struct PatternSet {
@@ -198,5 +222,8 @@ cudaError_t coo_to_csr(int idx_bits, const void *d_rowidx, const void *d_colidx,
 constexpr int kMaxRanks = 16;
 cudaError_t launch_peer_barrier(int rank, int nranks, long long epoch, long long *local_flags,
                                 long long *const *peer_flags, int *error_flag, cudaStream_t stream);
+// the same between a rank and the ranks it exchanges with only (the protocol of StepSync, for the
+// kernels that do not carry the fused form): signal `epoch` to them, wait for `epoch` from them
+cudaError_t launch_peer_sync(const StepSync &sync, cudaStream_t stream);
 
 }  // namespace ellspmv

@@ -81,7 +81,7 @@ csr_stream_kernel(const CsrSpmvArgs a)
     }
     if (have_row) {
         // csrgemvsd (csrspmv.c:1622-1627): y += ad*x + yi
-        if (a.ad) acc = __dadd_rn(__dmul_rn(a.ad[row], __ldg(x + row)), acc);
+        if (a.ad) acc = __dadd_rn(__dmul_rn(a.ad[row], __ldg(x + a.row_begin + row)), acc);
         const double yold = a.beta ? a.y[row] : 0.0;
         a.y[row] = __dadd_rn(yold, acc);
     }
@@ -120,7 +120,7 @@ csr_scalar_kernel(const CsrSpmvArgs a)
         const double xv = __ldg(x + (int64_t)__ldg(cols + k));
         acc = FMA ? __fma_rn(v, xv, acc) : __dadd_rn(acc, __dmul_rn(v, xv));
     }
-    if (a.ad) acc = __dadd_rn(__dmul_rn(a.ad[row], __ldg(x + row)), acc);
+    if (a.ad) acc = __dadd_rn(__dmul_rn(a.ad[row], __ldg(x + a.row_begin + row)), acc);
     a.y[row] = __dadd_rn(yold, acc);
 }
 
@@ -149,43 +149,74 @@ csr_vector_kernel(const CsrSpmvArgs a)
 #pragma unroll
     for (int off = 1; off < T; off <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
     if (j == 0 && row < a.num_rows) {
-        if (a.ad) acc += a.ad[row] * __ldg(x + row);
+        if (a.ad) acc += a.ad[row] * __ldg(x + a.row_begin + row);
         a.y[row] = a.beta ? a.y[row] + acc : acc;
     }
 }
 
-__global__ void csr_max_row_kernel(const int64_t *__restrict__ rowptr, int64_t num_rows, unsigned long long *out)
+// ---- upload-time inspection ----------------------------------------------------
+// One pass over rowptr and colidx: the longest row (kernel choice), whether rowptr is
+// non-decreasing, and the range of the stored column indices -- the same checks every ELL
+// upload makes (finish_minmax in api.cu), so that a bad index is EINVAL at upload and never an
+// out-of-bounds gather.  out[0] = max row length, out[1] = rows with rowptr[r+1] < rowptr[r],
+// out[2] = min column, out[3] = max column (as signed values).
+template <typename IdxT>
+__global__ void csr_inspect_kernel(const int64_t *__restrict__ rowptr, const IdxT *__restrict__ cols,
+                                   int64_t num_rows, int64_t csrsize, unsigned long long *out)
 {
-    unsigned long long best = 0;
-    for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < num_rows; r += (int64_t)gridDim.x * blockDim.x) {
-        const unsigned long long n = (unsigned long long)(rowptr[r + 1] - rowptr[r]);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t t0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    long long best = 0, bad = 0, lo = 0x7fffffffffffffffLL, hi = -0x7fffffffffffffffLL - 1;
+    for (int64_t r = t0; r < num_rows; r += stride) {
+        const long long n = rowptr[r + 1] - rowptr[r];
+        if (n < 0) bad++;
         best = n > best ? n : best;
     }
-    for (int off = 16; off > 0; off >>= 1) {
-        const unsigned long long o = __shfl_xor_sync(0xffffffffu, best, off);
-        best = o > best ? o : best;
+    for (int64_t k = t0; k < csrsize; k += stride) {
+        const long long c = (long long)cols[k];
+        lo = c < lo ? c : lo;
+        hi = c > hi ? c : hi;
     }
-    if ((threadIdx.x & 31) == 0) atomicMax(out, best);
+    for (int off = 16; off > 0; off >>= 1) {
+        const long long ob = __shfl_xor_sync(0xffffffffu, best, off); best = ob > best ? ob : best;
+        bad += __shfl_xor_sync(0xffffffffu, bad, off);
+        const long long ol = __shfl_xor_sync(0xffffffffu, lo, off); lo = ol < lo ? ol : lo;
+        const long long oh = __shfl_xor_sync(0xffffffffu, hi, off); hi = oh > hi ? oh : hi;
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMax(reinterpret_cast<long long *>(out), best);
+        if (bad) atomicAdd(out + 1, (unsigned long long)bad);
+        atomicMin(reinterpret_cast<long long *>(out) + 2, lo);
+        atomicMax(reinterpret_cast<long long *>(out) + 3, hi);
+    }
 }
 
-// longest row of a device CSR matrix (for choosing between the scalar and the stream kernel)
-cudaError_t csr_max_row_len(const int64_t *rowptr, int64_t num_rows, int64_t *max_len, cudaStream_t stream)
+// scratch: 4 x 8 bytes of device memory owned by the handle
+cudaError_t csr_inspect(int idx_bits, const int64_t *rowptr, const void *cols, int64_t num_rows, int64_t csrsize,
+                        unsigned long long *scratch, CsrInspection *res, cudaStream_t stream)
 {
-    *max_len = 0;
+    res->max_row_len = 0; res->bad_rows = 0; res->min_col = 0; res->max_col = -1;
     if (num_rows <= 0) return cudaSuccess;
-    unsigned long long *d = nullptr;
-    cudaError_t e = cudaMalloc(&d, 8);
-    if (e != cudaSuccess) return e;
-    e = cudaMemsetAsync(d, 0, 8, stream);
-    int64_t g = (num_rows + 255) / 256;
+    const long long init[4] = {0, 0, 0x7fffffffffffffffLL, -0x7fffffffffffffffLL - 1};
+    cudaError_t e = cudaMemcpyAsync(scratch, init, sizeof(init), cudaMemcpyHostToDevice, stream);
+    const int64_t work = num_rows > csrsize ? num_rows : csrsize;
+    int64_t g = (work + 255) / 256;
     if (g > 148 * 16) g = 148 * 16;
-    if (e == cudaSuccess) { csr_max_row_kernel<<<(unsigned)g, 256, 0, stream>>>(rowptr, num_rows, d); e = cudaGetLastError(); }
-    unsigned long long h = 0;
-    if (e == cudaSuccess) e = cudaMemcpyAsync(&h, d, 8, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) {
+        if (idx_bits == 64)
+            csr_inspect_kernel<int64_t><<<(unsigned)g, 256, 0, stream>>>(rowptr, (const int64_t *)cols, num_rows, csrsize, scratch);
+        else
+            csr_inspect_kernel<int32_t><<<(unsigned)g, 256, 0, stream>>>(rowptr, (const int32_t *)cols, num_rows, csrsize, scratch);
+        e = cudaGetLastError();
+    }
+    long long h[4] = {0, 0, 0, -1};
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h, scratch, sizeof(h), cudaMemcpyDeviceToHost, stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
-    cudaFree(d);
-    *max_len = (int64_t)h;
-    return e;
+    if (e != cudaSuccess) return e;
+    res->max_row_len = h[0];
+    res->bad_rows = h[1];
+    if (csrsize > 0) { res->min_col = h[2]; res->max_col = h[3]; }
+    return cudaSuccess;
 }
 
 template <typename IdxT, bool FMA>

@@ -170,7 +170,39 @@ ell_thread_kernel(const EllSpmvArgs a)
             asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;"
                          :: "l"(a.vals + ps * S * (int64_t)K), "r"((unsigned)(S * K * 8)) : "memory");
     }
-    if (row0 >= a.num_rows) return;
+    // fused step synchronisation (row-sharded y -> x loop): a CTA that reads halo columns or
+    // pushes into a peer's vector first waits until those peers have finished the previous step
+    // (their pushes have landed here, and they no longer read the vector this step overwrites)
+    const bool synced = a.sync.local_flags != nullptr;
+    bool cta_pushes = false;
+    if (synced) {
+        const int64_t g_lo = a.row_begin + slice * S;
+        const int64_t g_hi = g_lo + S;
+        for (int p = 0; p < a.push.num_peers; p++)
+            cta_pushes = cta_pushes || (g_lo < a.push.row_hi[p] && g_hi > a.push.row_lo[p]);
+        if (cta_pushes || a.sync.remote[slice]) {
+            if (threadIdx.x < a.sync.num_peers) {
+                const long long *src = a.sync.local_flags + a.sync.peer_rank[threadIdx.x];
+                const long long want = a.sync.epoch - 1;
+                const long long t0 = clock64();
+                long long seen;
+                for (;;) {
+                    asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(seen) : "l"(src) : "memory");
+                    if (seen >= want) break;
+                    if (clock64() - t0 > 40000000000LL) {   // ~20 s: a peer died; do not hang the GPU
+                        if (a.sync.error) *a.sync.error = 1 + a.sync.peer_rank[threadIdx.x];
+                        break;
+                    }
+                    __nanosleep(32);
+                }
+            }
+            __syncthreads();
+        }
+    }
+    if (row0 >= a.num_rows) {
+        if (synced) __syncthreads();      // pairs with the barrier before the completion count below
+        return;
+    }
 
     const int64_t base = slice * S * (int64_t)K + (int64_t)threadIdx.x * R;
     const double *vp = a.vals + base;
@@ -315,6 +347,22 @@ ell_thread_kernel(const EllSpmvArgs a)
                     const int64_t g = g0 + r;
                     if (row0 + r < a.num_rows && g >= lo && g < hi) px[g] = out[r];
                 }
+            }
+        }
+    }
+
+    // completion count: the last CTA of the launch tells the peers that this rank's step is done
+    if (synced) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            if (cta_pushes) __threadfence_system(); else __threadfence();
+            const unsigned prev = atomicAdd(a.sync.done, 1u);
+            if (prev == gridDim.x - 1) {
+                *a.sync.done = 0;                       // every CTA has counted: ready for the next launch
+                __threadfence_system();
+                for (int p = 0; p < a.sync.num_peers; p++)
+                    asm volatile("st.release.sys.global.s64 [%0], %1;"
+                                 ::"l"(a.sync.peer_flags[p] + a.sync.rank), "l"(a.sync.epoch) : "memory");
             }
         }
     }

@@ -37,6 +37,16 @@ void split_rows(int64_t rows, int n, std::vector<int64_t> &lo, std::vector<int64
     }
 }
 
+// the global rows of `owner` that `reader`'s stored entries reference, if any
+bool overlap(const ellspmv_cuda_matrix *reader, const ellspmv_cuda_matrix *owner, int64_t *lo, int64_t *hi)
+{
+    if (reader->max_col < reader->min_col) return false;
+    *lo = reader->min_col > owner->row_begin ? reader->min_col : owner->row_begin;
+    const int64_t end = owner->row_begin + owner->lay.num_rows;
+    *hi = reader->max_col + 1 < end ? reader->max_col + 1 : end;
+    return *lo < *hi;
+}
+
 int enable_peers(int n)
 {
     int count = 0;
@@ -238,20 +248,18 @@ int group_spmv(ellspmv_cuda_matrix *G, double *y, const double *x, int repeat, i
     // events: one per device per iteration boundary
     for (int p = 0; p < n; p++) {
         ELL_CK(cudaSetDevice(p));
-        int err = ensure_event_count(G->gevents[p], (size_t)repeat + 2);
+        int err = ensure_event_count(G->gevents[p], (size_t)repeat + 1);
         if (err) return err;
     }
-    // x: host -> device 0, then device 0 -> the others over NVLink
-    ELL_CK(cudaSetDevice(0));
-    cudaStream_t s0 = G->shards[0]->stream;
-    if (ncols > 0) ELL_CK(cudaMemcpyAsync(G->xb[0][0], x, (size_t)ncols * 8, cudaMemcpyDefault, s0));
-    cudaEvent_t x_ready = G->gevents[0][(size_t)repeat + 1];
-    ELL_CK(cudaEventRecord(x_ready, s0));
-    for (int p = 1; p < n; p++) {
+    // x: every device takes the range its shard references (its own slice plus the halo for a
+    // stencil, everything for a scattered matrix) straight from the host vector, all copies in
+    // flight at once -- not N copies of the whole vector (api.cu: shard_x_range)
+    for (int p = 0; p < n; p++) {
+        ellspmv_cuda_matrix *S = G->shards[p];
+        int64_t lo, hi;
+        shard_x_range(S, &lo, &hi);
         ELL_CK(cudaSetDevice(p));
-        cudaStream_t sp = G->shards[p]->stream;
-        ELL_CK(cudaStreamWaitEvent(sp, x_ready, 0));
-        if (ncols > 0) ELL_CK(cudaMemcpyPeerAsync(G->xb[0][p], p, G->xb[0][0], 0, (size_t)ncols * 8, sp));
+        if (hi > lo) ELL_CK(cudaMemcpyAsync(G->xb[0][p] + lo, x + lo, (size_t)(hi - lo) * 8, cudaMemcpyDefault, S->stream));
     }
     const bool iterate = mode == ELLSPMV_CUDA_ITERATE;
     const int beta = mode == ELLSPMV_CUDA_ACCUMULATE ? 1 : 0;
@@ -280,27 +288,32 @@ int group_spmv(ellspmv_cuda_matrix *G, double *y, const double *x, int repeat, i
             int err;
             if (iterate) {
                 const int nxt = 1 - cur;
+                // one kernel per device and step: SpMV, push of the rows the peers reference, and the
+                // step hand-shake with exactly those peers (fused where the kernel carries it)
                 PushTargets pt = {};
+                StepSync sy = {};
+                sy.local_flags = G->bflags[p];
+                sy.rank = p;
+                sy.epoch = G->epoch + 1;
+                sy.error = reinterpret_cast<int *>(G->bflags[p] + kMaxRanks);
                 for (int q = 0; q < n; q++) {
                     if (q == p) continue;
-                    const ellspmv_cuda_matrix *T = G->shards[q];
-                    if (T->max_col < T->min_col) continue;
-                    int64_t lo = T->min_col > S->row_begin ? T->min_col : S->row_begin;
-                    int64_t hi = T->max_col + 1 < S->row_begin + S->lay.num_rows ? T->max_col + 1 : S->row_begin + S->lay.num_rows;
-                    if (lo >= hi) continue;
-                    pt.x[pt.num_peers] = G->xb[nxt][q];
-                    pt.row_lo[pt.num_peers] = lo;
-                    pt.row_hi[pt.num_peers] = hi;
-                    pt.num_peers++;
+                    int64_t lo, hi;
+                    const bool to_q = overlap(G->shards[q], S, &lo, &hi);      // rows of p that q reads
+                    if (to_q) {
+                        pt.x[pt.num_peers] = G->xb[nxt][q];
+                        pt.row_lo[pt.num_peers] = lo;
+                        pt.row_hi[pt.num_peers] = hi;
+                        pt.num_peers++;
+                    }
+                    int64_t lo2, hi2;
+                    if (to_q || overlap(S, G->shards[q], &lo2, &hi2)) {        // ... or rows of q that p reads
+                        sy.peer_flags[sy.num_peers] = G->bflags[q];
+                        sy.peer_rank[sy.num_peers] = q;
+                        sy.num_peers++;
+                    }
                 }
-                err = launch_shard(S, G->xb[nxt][p] + S->row_begin, G->xb[cur][p], 0, &pt, S->stream);
-                if (!err) {
-                    long long *peers[kMaxRanks];
-                    for (int q = 0; q < n; q++) peers[q] = G->bflags[q];
-                    cudaError_t ce = launch_peer_barrier(p, n, G->epoch + 1, G->bflags[p], peers,
-                                                         reinterpret_cast<int *>(G->bflags[p] + kMaxRanks), S->stream);
-                    if (ce != cudaSuccess) { set_last_error("peer barrier: %s", cudaGetErrorString(ce)); err = cuda_to_errno(ce); }
-                }
+                err = launch_shard_exchange(S, G->xb[nxt][p] + S->row_begin, G->xb[cur][p], 0, &pt, sy, S->stream);
             } else {
                 err = launch_shard(S, G->xb[1][p] + S->row_begin, G->xb[0][p], beta, nullptr, S->stream);
             }
@@ -334,7 +347,12 @@ int group_spmv(ellspmv_cuda_matrix *G, double *y, const double *x, int repeat, i
         long long mark = 0;
         ELL_CK(cudaSetDevice(p));
         ELL_CK(cudaMemcpy(&mark, G->bflags[p] + kMaxRanks, sizeof(mark), cudaMemcpyDeviceToHost));
-        if (mark) ELL_FAIL(EIO, "device %d gave up waiting for a peer in the step barrier", p);
+        if (mark) {
+            // report once: clear the mark so that the handle stays usable after the error
+            cudaMemset(G->bflags[p] + kMaxRanks, 0, sizeof(mark));
+            ELL_FAIL(EIO, "device %d gave up waiting for device %lld in the step synchronisation", p,
+                     (long long)(mark & 0xffffffffLL) - 1);
+        }
     }
     return 0;
 }
@@ -391,7 +409,7 @@ int csr_group_upload(csrspmv_cuda_matrix **out, int idx_width_bits, int64_t num_
         const int64_t lo = G->row_lo[p], hi = G->row_lo[p + 1];
         csrspmv_cuda_matrix *S = nullptr;
         // the shard keeps the parent's entry offsets; csr_upload_on rebases rowptr and slices colidx / a
-        err = csr_upload_on(&S, idx_width_bits, hi - lo, num_columns, rowptr + lo, colidx, a, p, flags);
+        err = csr_upload_on(&S, idx_width_bits, hi - lo, num_columns, rowptr + lo, colidx, a, p, flags, lo);
         if (!err) { G->shards.push_back(S); G->device_bytes += S->device_bytes; }
     }
     if (prev >= 0) cudaSetDevice(prev);
@@ -414,13 +432,15 @@ int csr_group_spmv(csrspmv_cuda_matrix *G, double *y, const double *x, int repea
         int err = ensure_event_count(S->events, (size_t)repeat + 1);
         if (err) return err;
         cudaStream_t s = S->stream;
-        if (S->num_columns > 0) ELL_CK(cudaMemcpyAsync(S->d_x, x, (size_t)S->num_columns * 8, cudaMemcpyDefault, s));
+        int64_t xlo, xhi;
+        csr_x_range(S, &xlo, &xhi);
+        if (xhi > xlo) ELL_CK(cudaMemcpyAsync(S->d_x + xlo, x + xlo, (size_t)(xhi - xlo) * 8, cudaMemcpyDefault, s));
         if (mode == ELLSPMV_CUDA_ACCUMULATE && S->num_rows > 0)
             ELL_CK(cudaMemcpyAsync(S->d_y, y + G->row_lo[p], (size_t)S->num_rows * 8, cudaMemcpyDefault, s));
         ELL_CK(cudaEventRecord(S->events[0], s));
         for (int r = 0; r < repeat; r++) {
             CsrSpmvArgs args = {S->rowptr, S->cols, S->vals, S->d_x, S->d_y, S->num_rows,
-                                mode == ELLSPMV_CUDA_ACCUMULATE ? 1 : 0, S->d_ad};
+                                mode == ELLSPMV_CUDA_ACCUMULATE ? 1 : 0, S->d_ad, S->row_begin};
             ELL_CK(launch_csr_spmv(S->idx_bits, S->fma, S->kernel, args, s));
             ELL_CK(cudaEventRecord(S->events[(size_t)r + 1], s));
         }

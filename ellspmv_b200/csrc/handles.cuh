@@ -37,6 +37,8 @@ struct ellspmv_cuda_matrix {
     ellspmv::SgMatrix *sg = nullptr;         // staged-gather copy (ELLSPMV_CUDA_STAGED_GATHER), optional
     ellspmv::CbMatrix *cb = nullptr;         // column-blocked copy (ELLSPMV_CUDA_COLUMN_BLOCKED), optional
     int64_t min_col = 0, max_col = -1;
+    unsigned char *d_remote = nullptr;       // per slice: reads columns outside the shard's rows (fused step sync)
+    unsigned *d_done = nullptr;              // CTA completion counter of the fused step sync
     cudaStream_t stream = nullptr;
     cudaStream_t stream_out = nullptr;       // D2H stream of the pipelined host call
     double *d_x = nullptr, *d_y = nullptr;   // vectors of the host-facing spmv
@@ -58,6 +60,7 @@ struct csrspmv_cuda_matrix {
     int device = 0;
     int idx_bits = 32;
     int64_t num_rows = 0, num_columns = 0, csrsize = 0;
+    int64_t row_begin = 0;                     // global index of row 0 (shard of a group handle)
     unsigned flags = 0;
     int kernel = ELLSPMV_CUDA_KERNEL_THREAD;   // 1 stream, 2 vector, 3 scalar (see csr_kernels.cu)
     bool auto_kernel = true;                   // pick scalar vs stream from the row lengths
@@ -69,6 +72,8 @@ struct csrspmv_cuda_matrix {
     cudaStream_t stream = nullptr;
     double *d_x = nullptr, *d_y = nullptr;
     double *d_ad = nullptr;                  // separately stored diagonal, optional
+    unsigned long long *d_scratch = nullptr; // 32 bytes for the upload-time inspection (csr_inspect)
+    int64_t min_col = 0, max_col = -1;       // range of the stored column indices
     std::vector<cudaEvent_t> events;
     int64_t device_bytes = 0;
 
@@ -93,9 +98,16 @@ int csr_group_upload(csrspmv_cuda_matrix **out, int idx_width_bits, int64_t num_
 int csr_group_spmv(csrspmv_cuda_matrix *G, double *y, const double *x, int repeat, int mode, double *seconds);
 void csr_group_free(csrspmv_cuda_matrix *G);
 int csr_upload_on(csrspmv_cuda_matrix **out, int idx_width_bits, int64_t num_rows, int64_t num_columns,
-                  const int64_t *rowptr, const void *colidx, const double *a, int device, unsigned flags);
+                  const int64_t *rowptr, const void *colidx, const double *a, int device, unsigned flags,
+                  int64_t row_begin = 0);
 // api.cu internals the group needs
 int launch_shard(ellspmv_cuda_matrix *A, double *y_dev, const double *x_dev, int beta,
                  const PushTargets *push, cudaStream_t stream);
+// fused SpMV + push + step signalling (falls back to push + peer_sync kernel where the kernel in
+// use does not carry the fused form); sync.done / sync.remote are filled in from the handle
+int launch_shard_exchange(ellspmv_cuda_matrix *A, double *y_dev, const double *x_dev, int beta,
+                          const PushTargets *push, StepSync sync, cudaStream_t stream);
 int ensure_event_count(std::vector<cudaEvent_t> &ev, size_t n);
+void shard_x_range(const ellspmv_cuda_matrix *A, int64_t *lo, int64_t *hi);   // the part of x a shard's kernels read
+void csr_x_range(const csrspmv_cuda_matrix *A, int64_t *lo, int64_t *hi);
 }  // namespace ellspmv

@@ -286,4 +286,38 @@ cudaError_t generate_csr_random(const int64_t dims[3], uint64_t seed, int idx_bi
     return cudaGetLastError();
 }
 
+// ---- which slices read columns outside the shard's own rows (fused step sync, ell_kernels.cu) ----
+// remote[s] = 1 when slice s references a column outside [lo, hi): such a CTA must wait for the
+// peers' pushes of the previous step before it gathers.  lo/hi are the shard's row range shrunk
+// to multiples of 16 entries (one 128-byte line of x), so a CTA that does not wait never pulls a
+// line into L1 that also holds entries a peer is still writing.
+template <typename IdxT>
+__global__ void __launch_bounds__(kBlockThreads)
+slice_remote_kernel(const IdxT *__restrict__ cols, EllLayout lay, long long lo, long long hi,
+                    unsigned char *__restrict__ remote)
+{
+    const int64_t s = blockIdx.x;
+    const int n = lay.slice_rows * lay.rowsize;
+    const IdxT *c = cols + s * (int64_t)n;
+    int any = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const long long v = (long long)c[i];
+        any |= (v < lo || v >= hi);
+    }
+    any = __syncthreads_or(any);
+    if (threadIdx.x == 0) remote[s] = any ? 1 : 0;
+}
+
+cudaError_t mark_remote_slices(int idx_bits, const void *cols, const EllLayout &lay, int64_t lo, int64_t hi,
+                               unsigned char *remote, cudaStream_t stream)
+{
+    if (lay.num_slices <= 0) return cudaSuccess;
+    if (lay.num_slices > 0x7fffffffLL) return cudaErrorInvalidValue;
+    if (idx_bits == 64)
+        slice_remote_kernel<int64_t><<<(unsigned)lay.num_slices, kBlockThreads, 0, stream>>>((const int64_t *)cols, lay, lo, hi, remote);
+    else
+        slice_remote_kernel<int32_t><<<(unsigned)lay.num_slices, kBlockThreads, 0, stream>>>((const int32_t *)cols, lay, lo, hi, remote);
+    return cudaGetLastError();
+}
+
 }  // namespace ellspmv

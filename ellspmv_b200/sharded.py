@@ -59,6 +59,17 @@ def push_plan(rank: int, parts: Sequence[Range], needs: Sequence[Range]) -> List
     return plan
 
 
+def sync_ranks(rank: int, parts: Sequence[Range], needs: Sequence[Range]) -> List[int]:
+    """The ranks this one exchanges rows with: those it pushes to and those that push to it.
+    These are the ranks whose previous step must be over before this rank's halo CTAs start
+    (their pushes have landed; they no longer read the vector this step overwrites)."""
+    out = {p for p, _, _ in push_plan(rank, parts, needs)}
+    for p in range(len(parts)):
+        if p != rank and any(q == rank for q, _, _ in push_plan(p, parts, needs)):
+            out.add(p)
+    return sorted(out)
+
+
 def exchanged_bytes(rank: int, parts: Sequence[Range], needs: Sequence[Range], mode: str) -> int:
     """Bytes this rank sends per step."""
     if mode == "allgather":
@@ -114,9 +125,13 @@ class ShardedIterate:
     EllMatrix (or any object with .info(), .spmv_device(), .spmv_push())."""
 
     def __init__(self, A, rank: int, world: int, exchange: str = "auto", group=None,
-                 device: Optional[torch.device] = None, barrier: str = "device"):
+                 device: Optional[torch.device] = None, barrier: str = "fused"):
         self.A, self.rank, self.world, self.group = A, rank, world, group
-        self.barrier = barrier            # "device": flag barrier kernel over peer memory; "nccl": 1-element all-reduce
+        # "fused": the SpMV kernel signals and waits itself (ellspmv_cuda_spmv_exchange), neighbours only;
+        # "device": flag barrier kernel over peer memory after the kernel; "nccl": 1-element all-reduce
+        if barrier not in ("fused", "device", "nccl"):
+            raise ValueError(f"unknown barrier {barrier!r}")
+        self.barrier = barrier
         info = A.info()
         self.global_rows = int(info.global_rows)
         if int(info.num_columns) != self.global_rows:
@@ -182,6 +197,7 @@ class ShardedIterate:
                     ptr = _ipc_open(fh[p])
                     self._opened.append(ptr)
                     self._flag_ptrs.append(ptr)
+            self._sync_ranks = sync_ranks(rank, self.parts, self.needs)
             dist.barrier(group=group)
 
     # -- data ---------------------------------------------------------------
@@ -206,7 +222,13 @@ class ShardedIterate:
     def step(self, stream: int = 0) -> None:
         cur, nxt = self.x[self.cur], self.x[1 - self.cur]
         y = nxt[self.lo:self.hi]
-        if self.exchange == "push" and self.world > 1:
+        if self.exchange == "push" and self.world > 1 and self.barrier == "fused":
+            # one kernel: SpMV, push, and the step hand-shake with the neighbouring ranks
+            self.A.spmv_exchange(y, cur, OVERWRITE, self._peer_ptrs[1 - self.cur],
+                                 [lo for _, lo, _ in self.plan], [hi for _, _, hi in self.plan],
+                                 self.rank, self._sync_ranks, [self._flag_ptrs[p] for p in self._sync_ranks],
+                                 self._flags.ptr, self.steps_done + 1, stream)
+        elif self.exchange == "push" and self.world > 1:
             self.A.spmv_push(y, cur, OVERWRITE, self._peer_ptrs[1 - self.cur],
                              [lo for _, lo, _ in self.plan], [hi for _, _, hi in self.plan], stream)
             # orders step k's pushes before step k+1's gathers on every rank
@@ -239,8 +261,21 @@ class ShardedIterate:
                     src = p if self.group is None else dist.get_global_rank(self.group, p)
                     dist.broadcast(full[a:b], src=src, group=self.group)
 
+    def check(self) -> None:
+        """Raise if a step synchronisation on the device gave up waiting for a peer
+        (slot 16 of the flag array, written after ~20 s): the vectors are then stale."""
+        if getattr(self, "_flags", None) is None:
+            return
+        if self.is_cuda:
+            torch.cuda.synchronize(self.device)
+        mark = int(self._flags.tensor.view(torch.int64)[16].item()) & 0xFFFFFFFF
+        if mark:
+            raise EllspmvCudaError(5, "ShardedIterate",   # EIO
+                                   f"rank {self.rank} gave up waiting for rank {mark - 1} in the step synchronisation")
+
     def gather_result(self) -> torch.Tensor:
         """Full current vector assembled on every rank (for checking)."""
+        self.check()
         out = self.x[self.cur].clone()
         if self.world > 1:
             self._allgather(out)
@@ -255,6 +290,12 @@ class ShardedIterate:
 
     def close(self) -> None:
         lib = load_library()
+        try:
+            self.check()
+        finally:
+            self._release(lib)
+
+    def _release(self, lib) -> None:
         for p in self._opened:
             lib.ellspmv_cuda_ipc_close(p)
         self._opened = []

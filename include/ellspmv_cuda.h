@@ -236,6 +236,28 @@ int ellspmv_cuda_spmv_push(
     const int64_t *peer_row_lo, const int64_t *peer_row_hi, void *stream);
 
 /*
+ * The fused step of the row-sharded y -> x loop (BASELINE config 5): spmv_push plus the
+ * synchronisation between this rank and the ranks it exchanges rows with, inside the SpMV
+ * kernel.  CTAs that read halo columns or push wait -- at their start -- until every rank in
+ * sync_ranks has finished step epoch-1; interior CTAs never wait; the last CTA to finish
+ * stores `epoch` into slot [rank] of each of those ranks' flag arrays (system-scope release
+ * over NVLink).  No barrier kernel, no NCCL call between two steps.
+ *   sync_ranks/sync_flags  the ranks this one pushes to or is pushed by, and their flag arrays
+ *                          (peer-mapped; see ellspmv_cuda_peer_barrier for the array's shape)
+ *   local_flags            this rank's own flag array; slot [16] turns non-zero if a peer never
+ *                          arrived (~20 s), slot [rank] is unused
+ *   epoch                  1, 2, 3, ... one per step, the same on every rank
+ * Handles whose kernel has no fused form (sub-warp kernel, staged gather) run spmv_push
+ * followed by a one-warp signal-and-wait kernel with the same protocol.
+ */
+int ellspmv_cuda_spmv_exchange(
+    ellspmv_cuda_matrix *A, double *y_dev, const double *x_dev, int mode,
+    int num_peers, double *const *peer_x,
+    const int64_t *peer_row_lo, const int64_t *peer_row_hi,
+    int rank, int num_sync, const int *sync_ranks, int64_t *const *sync_flags,
+    int64_t *local_flags, int64_t epoch, void *stream);
+
+/*
  * Attach a separately stored diagonal: afterwards every spmv computes
  * y <- y + (ad .* x + A*x), the reference's ellgemvsd (ellspmv.c:1155-1180;
  * order 0: yi summed from 0, then ad*x + yi) or ellgemv16sd

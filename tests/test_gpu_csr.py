@@ -117,3 +117,37 @@ def test_sort_rows_program_and_kernel(tmp_path, lib, name):
     r = subprocess.run([os.path.join(hostlib.BIN, "csrspmv"), "--sort-rows", p], capture_output=True, text=True,
                        env=dict(os.environ, LC_ALL="C"))
     assert r.returncode == 0 and r.stdout == g["program"]["csrspmv_sorted"]["stdout"]
+
+
+def test_upload_validates_rowptr_and_columns(lib):
+    """csrspmv_cuda_upload checks what every ELL upload checks: a decreasing rowptr or a column
+    outside [0, num_columns) is EINVAL, not an out-of-bounds gather."""
+    rowptr = np.array([0, 2, 4, 6], dtype=np.int64)
+    a = np.ones(6)
+    for dt in (np.int32, np.int64):
+        ok = np.array([0, 1, 2, 3, 4, 5], dtype=dt)
+        E.CsrMatrix.upload(3, 6, rowptr, ok, a).free()
+        for bad in ([0, 1, 2, 6, 4, 5], [0, 1, -1, 3, 4, 5], [-2] * 6):
+            with pytest.raises(E.EllspmvCudaError) as ei:
+                E.CsrMatrix.upload(3, 6, rowptr, np.array(bad, dtype=dt), a)
+            assert ei.value.errno == 22
+        with pytest.raises(E.EllspmvCudaError) as ei:
+            E.CsrMatrix.upload(3, 6, np.array([0, 4, 2, 6], dtype=np.int64), ok, a)
+        assert ei.value.errno == 22
+
+
+def test_host_call_reads_only_the_referenced_x_range(lib, oracle):
+    rng = np.random.default_rng(8)
+    nr, nc = 300, 5000
+    rowptr, ec, ea = ragged_csr(rng, nr, 400, 9, np.int32)
+    ec = (ec + 1000).astype(np.int32)                  # columns 1000..1399 only
+    x = rng.standard_normal(nc)
+    want = np.zeros(nr)
+    oracle.csrgemv(nr, want, x, rowptr, ec, ea)
+    xp = np.full(nc, np.nan)
+    xp[ec.min():ec.max() + 1] = x[ec.min():ec.max() + 1]
+    A = E.CsrMatrix.upload(nr, nc, rowptr, ec, ea)
+    y = np.zeros(nr)
+    A.spmv(y, xp, 1, E.ACCUMULATE)
+    A.free()
+    assert bits_equal(y, want)

@@ -234,6 +234,85 @@ def test_push_to_peer_vectors(lib, oracle):
     assert p1[:2000].abs().sum() == 0 and p1[2500:].abs().sum() == 0
 
 
+def test_exchange_on_one_gpu(lib, oracle):
+    """ellspmv_cuda_spmv_exchange with two shards of one matrix on ONE device, each playing a
+    rank: SpMV + push + the fused step hand-shake, several steps of x <- A*x, bits of the
+    oracle's iteration.  (Both 'ranks' run on the same GPU on two streams, so a CTA that waits
+    is really waiting for the other shard's kernel.)"""
+    import torch
+    for name, dims, vals, bits in [("laplace2d", (700, 97), (0.25, -0.125), 32),
+                                   ("stencil27", (30, 9, 11), (0.5, -1.0 / 52), 64)]:
+        K, ncols, ec, ea, _ = oracle.gen_ell(name, dims, vals, bits=bits)
+        rows = len(ea) // K
+        x0 = np.random.default_rng(5).uniform(-1, 1, rows)
+        steps = 7
+        want = oracle.ell_iterate(rows, x0, steps, K, ec, ea)
+        cut = rows // 2 + 3                                   # not a multiple of 16
+        parts = [(0, cut), (cut, rows)]
+        S = [E.EllMatrix.upload(b - a, ncols, K, ec[a * K:b * K], ea[a * K:b * K], 0, global_rows=rows,
+                                row_begin=a, device=0) for a, b in parts]
+        needs = [(S[r].info().min_col, S[r].info().max_col + 1) for r in range(2)]
+        # each rank owns two full-length vectors and a flag array
+        xb = [[torch.zeros(rows, dtype=torch.float64, device="cuda") for _ in range(2)] for _ in range(2)]
+        flags = [torch.zeros(32, dtype=torch.int64, device="cuda") for _ in range(2)]
+        for r in range(2):
+            xb[r][0].copy_(torch.from_numpy(x0))
+        torch.cuda.synchronize()
+        streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+        cur = 0
+        for k in range(steps):
+            for r in range(2):
+                o = 1 - r
+                a, b = parts[r]
+                lo, hi = max(a, needs[o][0]), min(b, needs[o][1])
+                S[r].spmv_exchange(xb[r][1 - cur][a:b], xb[r][cur], E.OVERWRITE, [xb[o][1 - cur].data_ptr()], [lo], [hi],
+                                   r, [o], [flags[o].data_ptr()], flags[r].data_ptr(), k + 1, streams[r].cuda_stream)
+            cur = 1 - cur
+        torch.cuda.synchronize()
+        got = torch.cat([xb[0][cur][:cut], xb[1][cur][cut:]]).cpu().numpy()
+        assert bits_equal(got, want), name
+        assert int(flags[0][1]) == steps and int(flags[1][0]) == steps and int(flags[0][16]) == 0
+        for m in S:
+            m.free()
+
+
+def test_host_call_uploads_only_the_referenced_x_range(lib, oracle):
+    """A row shard's host-vector call reads x only on the column range the shard references
+    (its rows and the halo): poison everything else."""
+    K, ncols, ec, ea, _ = oracle.gen_ell("laplace2d", (1500, 1001), (4.0, -1.0), bits=32)
+    rows = len(ea) // K
+    rng = np.random.default_rng(6)
+    x = rng.standard_normal(ncols)
+    a, b = rows // 3, 2 * rows // 3 + 5
+    want = np.zeros(b - a)
+    oracle.ellgemv(b - a, want, x, K, ec[a * K:b * K], ea[a * K:b * K])
+    S = E.EllMatrix.upload(b - a, ncols, K, ec[a * K:b * K], ea[a * K:b * K], 0, global_rows=rows, row_begin=a, device=0)
+    i = S.info()
+    xp = np.full(ncols, np.nan)
+    xp[i.min_col:i.max_col + 1] = x[i.min_col:i.max_col + 1]
+    assert i.max_col - i.min_col + 1 < ncols // 2
+    for repeat in (1, 2):          # the pipelined path (>= 2^20 rows would take it) and the plain one
+        y = np.zeros(b - a)
+        S.spmv(y, xp, repeat, E.OVERWRITE)
+        assert bits_equal(y, want)
+    S.free()
+
+
+def test_negative_column_indices_are_rejected(lib):
+    """All-negative indices used to slip through the range check (the max accumulator starts at -1)."""
+    for dt in (np.int32, np.int64):
+        ec = np.full(6, -3, dtype=dt)
+        with pytest.raises(E.EllspmvCudaError) as ei:
+            E.EllMatrix.upload(3, 10, 2, ec, np.ones(6))
+        assert ei.value.errno == 22
+        ec = np.array([0, 1, -1, 2, 3, 4], dtype=dt)
+        with pytest.raises(E.EllspmvCudaError):
+            E.EllMatrix.upload(3, 10, 2, ec, np.ones(6))
+        ec = np.array([0, 1, 10, 2, 3, 4], dtype=dt)
+        with pytest.raises(E.EllspmvCudaError):
+            E.EllMatrix.upload(3, 10, 2, ec, np.ones(6))
+
+
 @pytest.mark.parametrize("mode", [E.ACCUMULATE, E.OVERWRITE])
 def test_pipelined_host_call(lib, oracle, mode):
     """>= 2^20 rows and repeat == 1 take the chunked, copy-overlapped path of
@@ -255,6 +334,16 @@ def test_pipelined_host_call(lib, oracle, mode):
     A.spmv(yp.numpy(), xp.numpy(), 1, mode)
     assert bits_equal(yp.numpy(), want)
     A.free()
+    # a row shard (>= 2^20 rows) through the same path: only its x range is uploaded
+    a, b = 100_003, rows - 77
+    S = E.EllMatrix.upload(b - a, ncols, K, ec[a * K:b * K], ea[a * K:b * K], 0, global_rows=rows, row_begin=a, device=0)
+    i = S.info()
+    xq = np.full(ncols, np.nan)
+    xq[i.min_col:i.max_col + 1] = x[i.min_col:i.max_col + 1]
+    y = y0[a:b].copy()
+    S.spmv(y, xq, 1, mode)
+    assert bits_equal(y, want[a:b])
+    S.free()
 
 
 @pytest.mark.parametrize("shape", [(1, 1, 1), (127, 300, 5), (1000, 1000, 7), (5003, 5003, 27), (40000, 40000, 5), (3000, 3000, 32)])

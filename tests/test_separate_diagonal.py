@@ -162,6 +162,49 @@ def test_gpu_vs_oracle(lib, oracle, bits, shape, monkeypatch):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("bits", [32, 64])
+def test_gpu_separate_diagonal_on_several_gpus(lib, oracle, bits):
+    """csrgemvsd / ellgemvsd over row shards: every shard multiplies its diagonal entry with x at
+    the row's GLOBAL index (the CSR shards used the shard-local row: wrong for every shard but
+    the first)."""
+    import torch
+
+    import ellspmv_b200 as E
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    n = min(torch.cuda.device_count(), 4)
+    nr = nc = 3001
+    nnz = 90000
+    dt = np.int32 if bits == 32 else np.int64
+    rng = np.random.default_rng(77 + bits)
+    ri = rng.integers(1, nr + 1, nnz).astype(dt)
+    ci = rng.integers(1, nc + 1, nnz).astype(dt)
+    ci[: nnz // 5] = ri[: nnz // 5]
+    a = rng.standard_normal(nnz)
+    x = rng.standard_normal(nc)
+    y0 = rng.standard_normal(nr)
+    rowptr, cc, ca, cad, _, _ = oracle.csr_from_coo_sd(nr, ri, ci, a)
+    want = y0.copy()
+    oracle.csrgemvsd(nr, want, x, rowptr, cc, ca, cad)
+    Cm = E.CsrMatrix.upload(nr, nc, rowptr, cc, ca, num_gpus=n)
+    Cm.set_diagonal(cad)
+    y = y0.copy()
+    Cm.spmv(y, x, 1, E.ACCUMULATE)
+    Cm.free()
+    assert bits_equal(y, want)
+    K, _, _, ec, ea, ad = oracle.ell_from_coo_sd(nr, nc, ri, ci, a)
+    for order in (0, 1):
+        want = y0.copy()
+        oracle.ellgemvsd(nr, want, x, K, ec, ea, ad, order)
+        A = E.EllMatrix.upload(nr, nc, K, ec, ea, num_gpus=n)
+        A.set_diagonal(ad, order)
+        y = y0.copy()
+        A.spmv(y, x, 1, E.ACCUMULATE)
+        A.free()
+        assert bits_equal(y, want), order
+
+
+@pytest.mark.gpu
 def test_gpu_rejects_more_rows_than_columns(lib):
     import ellspmv_b200 as E
     A = E.EllMatrix.upload(5, 3, 1, np.zeros(5, dtype=np.int32), np.ones(5))

@@ -44,6 +44,22 @@ def test_push_plan_restricts_to_what_peers_reference():
     assert push_plan(0, [(0, 0), (0, 5)], [(0, 0), (0, 5)]) == []
 
 
+def test_sync_ranks_are_the_ranks_rows_are_exchanged_with():
+    from ellspmv_b200.sharded import sync_ranks
+    parts = partition_rows(400, 4)
+    needs = [(max(0, a - 10), min(400, b + 10)) for a, b in parts]      # stencil: neighbours only
+    assert [sync_ranks(r, parts, needs) for r in range(4)] == [[1], [0, 2], [1, 3], [2]]
+    needs = [(0, 400)] * 4                                               # scattered: everybody
+    assert sync_ranks(2, parts, needs) == [0, 1, 3]
+    # one-directional: rank 1 reads rank 0's rows, rank 0 reads only its own -> both list each other
+    # (rank 0 must not overwrite what rank 1 still reads; rank 1 must see rank 0's pushes)
+    needs = [(0, 100), (50, 200)]
+    parts2 = [(0, 100), (100, 200)]
+    assert sync_ranks(0, parts2, needs) == [1] and sync_ranks(1, parts2, needs) == [0]
+    # block diagonal: nobody to wait for
+    assert sync_ranks(0, parts2, [(0, 100), (100, 200)]) == []
+
+
 class _Info:
     pass
 
