@@ -3,24 +3,38 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-A step is one pass of the hot path (the reference's `ellgemv`, y <- y + A*x,
+A step is one pass of the hot path (the reference's `ellgemv` loop,
 ellspmv.c:1146-1151) over the synthetic 2D 5-point Laplacian on an 8192x8192
-grid per GPU (BASELINE config 2: 67,108,864 rows, K = 5, 32-bit indices).
+grid per GPU (BASELINE config 2: 67,108,864 rows, K = 5, 32-bit indices), in
+the y -> x form of BASELINE config 5: x_{k+1} <- A*x_k.  The SAME step is timed
+at every N (at N = 1 there is simply nobody to exchange with), so the driver's
+scaling efficiency compares like with like.
 
-  value     whole-job GFLOP/s (2*N*K flops per step, padding counted like the
-            reference does, ellspmv.c:1857), matrix and vectors resident in HBM
-  roofline  algorithmic bytes per launch / CUDA-event time of the kernel
-            against the measured HBM copy bandwidth (MEASURED_PEAKS.json)
-  e2e       the same metric through the C-ABI call with HOST vectors
-            (ellspmv_cuda_spmv: H2D x and y, launch, D2H y inside the timing)
-  cpu_baseline  the unmodified reference's ellgemv (oracle/_ref) on the box's
-            host cores, same matrix -- a reported baseline, not the target
+  value      whole-job GFLOP/s (2*N*K flops per step, padding counted like the
+             reference does, ellspmv.c:1857), matrix and vectors resident in HBM
+  roofline   the bytes the kernel has to move as the matrix is stored on the
+             device (values + the index bytes that are really read + x + y) per
+             CUDA-event time, against the measured HBM copy bandwidth
+             (MEASURED_PEAKS.json); `algorithmic` is SURVEY.md 8(d)'s figure
+             (every index counted at the caller's width), `compression_gain`
+             their ratio
+  accumulate the reference's own semantics (y <- y + A*x, x constant) on the
+             same matrix, kernel only
+  e2e        the same metric through the C-ABI call with HOST vectors
+             (ellspmv_cuda_spmv, ACCUMULATE: H2D of the x range the shard
+             references and of y, launch, D2H of y inside the timing)
+  cpu_baseline   the unmodified reference's ellgemv (oracle/_ref) on the box's
+             host cores, same matrix -- a reported baseline, not the target
+  other_configs  (N = 1) BASELINE configs 3 and 4 (ELL and CSR), kernel only,
+             each with its CPU baseline on a bounded sample
+  config5    (N > 1) BASELINE config 5 itself: 27-point 768^3, strong-scaled,
+             100 iterations, fused push exchange and NCCL all-gather
+  parity_check   (N > 1) after k steps every rank recomputes its rows from the
+             gathered x_k with the plain single-GPU launch and compares them bit
+             for bit with its slice of the sharded x_{k+1}
 
-N > 1 (launched by torchrun, one rank per GPU): the grid grows to
-(N*8192)x8192 (weak scaling), rows are sharded in contiguous blocks, and a
-step is x_{k+1} <- A*x_k with the exchange of y into every rank's next x
-(BASELINE config 5's y->x loop).  --impl reference times the reference's own
-CPU implementation (rank 0 only).
+N > 1 is launched by torchrun, one rank per GPU.  --impl reference times the
+reference's own CPU implementation (rank 0 only).
 """
 from __future__ import annotations
 
@@ -36,11 +50,9 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 GRID = 8192                      # per-GPU grid is GRID x GRID
-K_LAPLACE = 5
-IDX_BYTES = 4
 
-# name -> (generator kind, K, index bits, (centre, off) for accumulate / iterate, dims(world), scaling)
-# iterate values have row sums of 1 (|A|_inf = 1), so x stays O(1) over any number of y -> x steps
+# name -> (generator kind, K, index bits, (centre, off) reference values / iterate values, dims(world), scaling)
+# iterate values have row sums of at most 1 (|A|_inf <= 1), so x stays O(1) over any number of y -> x steps
 WORKLOADS = {
     # BASELINE config 2, the headline: 8192x8192 grid per GPU, grid grows along x with N (weak)
     "laplace2d": ("laplace2d", 5, 32, (4.0, -1.0), (0.5, 0.125), lambda w: (GRID * w, GRID), "weak"),
@@ -54,22 +66,30 @@ WORKLOADS = {
 FALLBACK_HBM_GBS = 6650.0        # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
 
 
+def workload_name(name: str, world: int) -> str:
+    kind, K, bits, _, _, dims_of, _ = WORKLOADS[name]
+    return f"{kind}_{'x'.join(str(d) for d in dims_of(world))}_K{K}_idx{bits}"
+
+
 def algorithmic_bytes(rows: int, ncols: int, K: int, idx_bytes: int, y_rmw: bool) -> int:
     """values + indices + x once + y once (+ y read when y is
     truly read-modify-written, i.e. the reference's accumulate semantics)."""
     return rows * K * (8 + idx_bytes) + 8 * ncols + 8 * rows * (2 if y_rmw else 1)
 
 
-def kernel_description(flags: int, fma: bool) -> str:
-    """Which of the library's ELL kernels the upload flags select (include/ellspmv_cuda.h)."""
-    arith = "fma (tolerance)" if fma else "mul-then-add"
-    if flags & (1 << 17):
-        return f"staged gather: column blocks, gather staged through HBM, then thread-per-row, {arith}" + ("" if fma else " (bit-exact)")
+def kernel_description(info, flags: int) -> str:
+    """Which of the library's ELL kernels the handle runs (include/ellspmv_cuda.h)."""
+    arith = "fma (tolerance)" if info.fma else "mul-then-add"
+    exact = "" if info.fma else " (bit-exact)"
+    if getattr(info, "staged", 0):
+        return f"staged gather: column blocks, gather staged through HBM, then thread-per-row, {arith}{exact}"
     if flags & (1 << 7):
         return f"column-blocked, per-block partial sums, {arith} (tolerance)"
-    if (flags & 0xf) == 2:
+    if info.kernel == 2:
         return f"sub-warp-per-row + shuffle reduction, {arith} (tolerance)"
-    return f"thread-per-row, {arith}" + ("" if fma else " (bit-exact)")
+    if info.kernel == 4:
+        return f"long rows: CTA per row group, products parked in shared memory, sequential adds, {arith}{exact}"
+    return f"thread-per-row, {arith}{exact}"
 
 
 def measured_peak():
@@ -81,13 +101,27 @@ def measured_peak():
         return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
 
 
-def recorded_traffic(workload: str):
+def recorded_traffic(key: str):
     """dram__bytes_read+write per launch from the committed ncu --set full capture."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            return json.load(f).get(workload)
+            return json.load(f).get(key)
     except Exception:
         return None
+
+
+def host_cores() -> dict:
+    logical = os.cpu_count() or 1
+    try:
+        import psutil
+        physical = psutil.cpu_count(logical=False) or logical
+    except Exception:
+        physical = logical
+    try:
+        usable = len(os.sched_getaffinity(0))
+    except Exception:
+        usable = logical
+    return {"physical": physical, "logical": logical, "usable": usable}
 
 
 class ClockSampler:
@@ -131,6 +165,7 @@ class ClockSampler:
 
     def start(self):
         if self.nv is not None:
+            self._stop.clear()
             self._thread = threading.Thread(target=self._run, daemon=True)
             self._thread.start()
 
@@ -138,6 +173,7 @@ class ClockSampler:
         self._stop.set()
         if self._thread is not None:
             self._thread.join(timeout=1.0)
+            self._thread = None
 
     def summary(self):
         if not self.samples:
@@ -146,38 +182,69 @@ class ClockSampler:
         return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
                 "samples": len(s)}
 
+    def nvlink_tx_bytes(self):
+        """NVLink payload bytes this GPU has sent so far (NVML throughput counter, KiB), or None."""
+        try:
+            nv = self.nv
+            fid = getattr(nv, "NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX", 138)
+            vals = nv.nvmlDeviceGetFieldValues(self.h, [(fid, 0xFFFFFFFF)])
+            v = vals[0]
+            if v.nvmlReturn != 0:
+                return None
+            return int(v.value.ullVal) * 1024
+        except Exception:
+            return None
+
 
 # ---------------------------------------------------------------------------
 # CPU reference arm / cpu_baseline
 # ---------------------------------------------------------------------------
-def cpu_reference_run(steps: int, warmup: int, budget_s: float):
-    """Time the reference's own ellgemv on the host cores, on BASELINE config 2.
+def use_all_host_threads() -> int:
+    """torchrun injects OMP_NUM_THREADS=1 into every rank; that is not the user's choice of a
+    thread count for the CPU baseline.  Give the reference the cores this process may use."""
+    n = host_cores()["usable"]
+    if os.environ.get("WORLD_SIZE", "1") != "1" and os.environ.get("OMP_NUM_THREADS", "") in ("", "1"):
+        os.environ["OMP_NUM_THREADS"] = str(n)
+        try:
+            import ctypes
+            ctypes.CDLL("libgomp.so.1").omp_set_num_threads(n)   # in case libgomp is already initialised
+        except Exception:
+            pass
+    return n
 
-    Uses oracle/_ref/libref_ell32.so (the UNMODIFIED reference compiled by
-    oracle/Makefile) when present -> kind "reference"; otherwise the oracle's
-    C restatement -> kind "port".  The matrix is the same 8192x8192-grid
-    Laplacian built by the oracle's generator, first-touched in parallel like
-    the reference's main() does (Q11).  If steps*t would exceed the budget,
-    a step becomes a bounded sample: the first `sample_rows` rows."""
+
+def cpu_reference_run(workload: str, world: int, steps: int, warmup: int, budget_s: float, fmt: str = "ell"):
+    """Time the reference's own kernel on the host cores, on `workload` as the GPU arm runs it.
+
+    Uses oracle/_ref/libref_{ell,csr}{32,64}.so (the UNMODIFIED reference compiled by
+    oracle/Makefile) when present -> kind "reference"; otherwise the oracle's C restatement ->
+    kind "port".  The arrays come from the oracle's generator, first-touched in parallel like
+    the reference's main() does (Q11); x has the full length of the workload.  A step is a
+    bounded sample -- the first `rows` rows -- sized so that (steps + warmup) passes fit the
+    budget; GFLOP/s of this bandwidth-bound loop does not depend on the sample length."""
     import numpy as np
 
     from oracle.pyoracle import Oracle, Reference
 
+    kind_name, K, idx_bits, vals_acc, _, dims_of, _ = WORKLOADS[workload]
+    dims = dims_of(world)
+    rows_full = dims[0] if kind_name == "random" else int(np.prod(dims))
+    ncols = dims[1] if kind_name == "random" else rows_full
     orc = Oracle()
-    ref = Reference("ell", 32) if Reference.available("ell", 32) else None
+    ref = Reference(fmt, idx_bits) if Reference.available(fmt, idx_bits) else None
     kind = "reference" if ref is not None else "port"
-    cores = ref.num_threads() if ref is not None else orc.num_threads()
-    rows_full = GRID * GRID
-    K = K_LAPLACE
+    threads = ref.num_threads() if ref is not None else orc.num_threads()
+    idt = np.int32 if idx_bits == 32 else np.int64
+    bytes_per_row = K * (8 + idx_bits // 8) + 16
 
     def build(rows):
-        ec = np.empty(rows * K, dtype=np.int32)
+        ec = np.empty(rows * K, dtype=idt)
         ea = np.empty(rows * K, dtype=np.float64)
-        x = np.empty(rows_full, dtype=np.float64)
+        x = np.empty(ncols, dtype=np.float64)
         y = np.empty(rows, dtype=np.float64)
-        if ref is not None:
-            ref.first_touch(rows, K, ec, ea, rows_full, x, y)
-        _, _, c, a, _ = orc.gen_ell("laplace2d", (GRID, GRID), (4.0, -1.0), bits=32, row_begin=0, row_end=rows)
+        if ref is not None and fmt == "ell":
+            ref.first_touch(rows, K, ec, ea, ncols, x, y)
+        _, _, c, a, _ = orc.gen_ell(kind_name, dims, vals_acc, seed=42, bits=idx_bits, row_begin=0, row_end=rows)
         ec[:] = c
         ea[:] = a
         del c, a
@@ -186,8 +253,19 @@ def cpu_reference_run(steps: int, warmup: int, budget_s: float):
         return ec, ea, x, y
 
     def run(ec, ea, x, y, rows, n):
+        if fmt == "csr":
+            # every generated row has exactly K stored entries: the CSR arrays are the row-major ELL arrays
+            rowptr = np.arange(rows + 1, dtype=np.int64) * K
+            if ref is not None:
+                return ref.csrgemv(rows, y, ncols, x, rowptr, ec, ea, repeat=n, rowsizemin=K, rowsizemax=K)
+            out = []
+            for _ in range(n):
+                t0 = time.perf_counter()
+                orc.csrgemv(rows, y, x, rowptr, ec, ea)
+                out.append(time.perf_counter() - t0)
+            return np.array(out)
         if ref is not None:
-            return ref.ellgemv(rows, y, rows_full, x, K, ec, ea, repeat=n)
+            return ref.ellgemv(rows, y, ncols, x, K, ec, ea, repeat=n)
         out = []
         for _ in range(n):
             t0 = time.perf_counter()
@@ -195,50 +273,75 @@ def cpu_reference_run(steps: int, warmup: int, budget_s: float):
             out.append(time.perf_counter() - t0)
         return np.array(out)
 
-    rows = rows_full
-    try:
-        ec, ea, x, y = build(rows)
-    except MemoryError:
-        rows = rows_full // 4
-        ec, ea, x, y = build(rows)
+    # first guess: 1 GB of matrix, then scale to the budget from a probe
+    rows = min(rows_full, max(1 << 16, (1 << 30) // bytes_per_row))
+    ec, ea, x, y = build(rows)
     t_probe = float(np.min(run(ec, ea, x, y, rows, 2)))
-    if t_probe * (steps + warmup) > budget_s and rows > 1 << 20:
-        frac = budget_s / (t_probe * (steps + warmup))
-        rows = max(1 << 20, int(rows * frac) // GRID * GRID)
+    want = budget_s / max(steps + warmup + 2, 1)
+    if t_probe < want / 2 and rows < rows_full:
+        grow = min(rows_full, int(rows * min(want / t_probe, 6.0)))
+        if grow > rows * 1.5 and grow * bytes_per_row < (12 << 30):
+            rows = grow
+            del ec, ea, y
+            ec, ea, x, y = build(rows)
+    elif t_probe * (steps + warmup) > budget_s and rows > 1 << 18:
+        rows = max(1 << 18, int(rows * budget_s / (t_probe * (steps + warmup))))
         ec, ea, y = ec[: rows * K], ea[: rows * K], y[:rows]
     run(ec, ea, x, y, rows, max(warmup, 1))
     secs = run(ec, ea, x, y, rows, steps)
     total = float(np.sum(secs))
     flops = 2.0 * rows * K
-    sample = (f"{steps} timed passes of the reference ellgemv over "
-              f"{'all' if rows == rows_full else 'the first'} {rows} rows of the {GRID}x{GRID}-grid "
-              f"5-point Laplacian (K=5, idx32), {cores} OpenMP threads, after {max(warmup, 1)} warm-up")
+    cores = host_cores()
+    sample = (f"{steps} timed passes of the reference {'csrgemv' if fmt == 'csr' else 'ellgemv'} over "
+              f"{'all' if rows == rows_full else 'the first'} {rows} of {rows_full} rows of {workload_name(workload, world)} "
+              f"(x of full length {ncols}), {threads} OpenMP threads on {cores['physical']} physical / "
+              f"{cores['logical']} logical cores, after {max(warmup, 1)} warm-up")
     return {
-        "kind": kind, "cores": cores, "sample": sample, "rows": rows,
+        "kind": kind, "cores": threads, "physical_cores": cores["physical"], "logical_cores": cores["logical"],
+        "omp_num_threads": threads, "sample": sample, "rows": rows,
         "gflops": flops * steps / total * 1e-9,
         "best_gflops": flops / float(np.min(secs)) * 1e-9,
         "ms_per_step": total / steps * 1e3,
-        "gbs": algorithmic_bytes(rows, rows_full if rows == rows_full else rows, K, IDX_BYTES, True) * steps / total * 1e-9,
+        "gbs": (rows * K * (8 + idx_bits // 8) + 16 * rows + (8 * ncols if rows == rows_full else 0)) * steps / total * 1e-9,
     }
 
 
-def main_reference(args, rank: int):
+def baseline_record(r: dict) -> dict:
+    return {"value": round(r["gflops"], 3), "unit": "GFLOP/s", "cores": r["cores"], "kind": r["kind"],
+            "physical_cores": r["physical_cores"], "logical_cores": r["logical_cores"],
+            "omp_num_threads": r["omp_num_threads"], "sample": r["sample"],
+            "best": round(r["best_gflops"], 3), "gbs_effective": round(r["gbs"], 2)}
+
+
+def workload_config(workload: str, world: int) -> dict:
+    """What is computed, not how: identical in the GPU arm and the reference arm."""
+    import numpy as np
+    kind_name, K, idx_bits, _, _, dims_of, scaling = WORKLOADS[workload]
+    dims = dims_of(world)
+    rows = dims[0] if kind_name == "random" else int(np.prod(dims))
+    return {"workload": workload_name(workload, world), "rows": rows, "rowsize": K, "idx_bits": idx_bits,
+            "rows_per_gpu": rows // world, "parallelism": f"rowshard{world}"}
+
+
+def main_reference(args, rank: int, world: int):
     if rank != 0:
         return 0
-    r = cpu_reference_run(args.steps, args.warmup, budget_s=150.0)
+    threads = use_all_host_threads()
+    r = cpu_reference_run(args.workload, world, args.steps, args.warmup, budget_s=120.0)
     line = {
         "impl": "reference",
         "metric": "ell_spmv_fp64_gflops", "value": round(r["gflops"], 3), "unit": "GFLOP/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": round(r["ms_per_step"], 4), "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": round(r["ms_per_step"], 4), "higher_is_better": True,
+        "scaling": WORKLOADS[args.workload][6],
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"laplace2d_{GRID}x{GRID}_K5_idx32", "mode": "accumulate (y += A*x)",
-                   "rows": r["rows"], "host": "CPU, OpenMP"},
-        "cpu_baseline": {"value": round(r["gflops"], 3), "unit": "GFLOP/s", "cores": r["cores"],
-                         "kind": r["kind"], "sample": r["sample"], "gbs_effective": round(r["gbs"], 2)},
+        "config": workload_config(args.workload, world),
+        "step": "accumulate (y <- y + A*x, x constant): the only form the reference's ellgemv has; timed on a "
+                "bounded sample of the rows (see cpu_baseline.sample), host cores only",
+        "cpu_baseline": baseline_record(r),
         "e2e": {"value": round(r["gflops"], 3), "unit": "GFLOP/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "gpu_launches": 0, "host_threads_available": threads,
     }
     print(json.dumps(line), flush=True)
     return 0
@@ -247,6 +350,170 @@ def main_reference(args, rank: int):
 # ---------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------
+def time_steps(torch, stream, step, steps: int, barrier):
+    """CUDA-event time of exactly `steps` calls of step(), barrier + synchronize on both sides."""
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        step()
+    e1.record(stream)
+    barrier()
+    return e0.elapsed_time(e1)
+
+
+def kernel_record(E, info, rows: int, K: int, idx_bits: int, ms: float, y_rmw: bool, x_touched: int, peak: float,
+                  entries=None) -> dict:
+    """Throughput and the two byte models for one launch that took `ms`.
+    as stored: 64-bit indices are kept as 32-bit on the device when they fit, and rows whose
+    indices follow an offset pattern never read them."""
+    n_entries = rows * K if entries is None else entries
+    dev_ib = int(info.dev_idx_bits) // 8 if info is not None else idx_bits // 8
+    pattern_rows = int(info.pattern_rows) if info is not None else 0
+    alg = n_entries * (8 + idx_bits // 8) + 8 * x_touched + 8 * rows * (2 if y_rmw else 1)
+    stored = n_entries * (8 + dev_ib) - pattern_rows * K * dev_ib + 8 * x_touched + 8 * rows * (2 if y_rmw else 1)
+    return {"ms_per_step": round(ms, 5), "gflops": round(2.0 * n_entries / ms * 1e-6, 2),
+            "as_stored_gbs": round(stored / ms * 1e-6, 1), "frac_as_stored": round(stored / ms * 1e-6 / peak, 4),
+            "algorithmic_gbs": round(alg / ms * 1e-6, 1), "frac_algorithmic": round(alg / ms * 1e-6 / peak, 4),
+            "bytes_as_stored": stored, "bytes_algorithmic": alg,
+            "pattern_rows_frac": round(pattern_rows / max(rows, 1), 4)}
+
+
+def other_configs(E, torch, dev, sptr, stream, reps: int, peak: float, with_cpu: bool):
+    """BASELINE configs 3 and 4 (ELL and the CSR comparison path), kernel only, N = 1."""
+    import numpy as np
+    out = []
+
+    def sync():
+        torch.cuda.synchronize()
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        return time_steps(torch, stream, fn, reps, sync) / reps
+
+    for name, fmt in (("stencil27_384", "ell"), ("random50m", "ell"), ("random50m", "csr")):
+        kind_name, K, idx_bits, vals_acc, _, dims_of, _ = WORKLOADS[name]
+        kind = {"laplace2d": E.GEN_LAPLACE2D, "stencil27": E.GEN_STENCIL27, "random": E.GEN_RANDOM}[kind_name]
+        dims = dims_of(1)
+        rows = dims[0] if kind_name == "random" else int(np.prod(dims))
+        ncols = dims[1] if kind_name == "random" else rows
+        rec = {"config": workload_name(name, 1), "format": fmt, "flags": 0}
+        try:
+            gen = torch.Generator(device=dev).manual_seed(4321)
+            x = torch.randn(ncols, dtype=torch.float64, device=dev, generator=gen)
+            y = torch.zeros(rows, dtype=torch.float64, device=dev)
+            if fmt == "ell":
+                A = E.EllMatrix.generate(kind, dims, vals_acc, 42, idx_bits, flags=0)
+                info = A.info()
+                ms = timed(lambda: A.spmv_device(y, x, E.ACCUMULATE, sptr))
+                rec.update(kernel_record(E, info, rows, K, idx_bits, ms, True, ncols, peak))
+                rec["kernel"] = kernel_description(info, 0)
+                rec["launches_per_step"] = int(getattr(info, "launches_per_spmv", 1)) or 1
+                rec["device_bytes"] = int(info.device_bytes)
+            else:
+                A = E.CsrMatrix.generate(kind, dims, seed=42, idx_bits=idx_bits)
+                ms = timed(lambda: A.spmv_device(y, x, E.ACCUMULATE, sptr))
+                rec.update(kernel_record(E, None, rows, K, idx_bits, ms, True, ncols, peak))
+                # csrspmv.c:2882-2887: the CSR byte model adds the row pointers
+                extra = 8 * (rows + 1)
+                for k in ("bytes_as_stored", "bytes_algorithmic"):
+                    rec[k] += extra
+                rec["as_stored_gbs"] = round(rec["bytes_as_stored"] / ms * 1e-6, 1)
+                rec["algorithmic_gbs"] = round(rec["bytes_algorithmic"] / ms * 1e-6, 1)
+                rec["frac_as_stored"] = round(rec["as_stored_gbs"] / peak, 4)
+                rec["frac_algorithmic"] = round(rec["algorithmic_gbs"] / peak, 4)
+                rec["kernel"] = A.describe() if hasattr(A, "describe") else "csr"
+                rec["device_bytes"] = int(A.device_bytes())
+            rec["mode"] = "accumulate (y <- y + A*x)"
+            rec["traffic"] = recorded_traffic(f"{rec['config']}_{fmt}")
+            A.free()
+            del x, y
+            torch.cuda.empty_cache()
+        except Exception as exc:              # keep the headline line even if a side config fails
+            rec["error"] = repr(exc)
+        if with_cpu and "error" not in rec:
+            try:
+                r = cpu_reference_run(name, 1, 3, 1, budget_s=8.0, fmt=fmt)
+                rec["cpu_baseline"] = baseline_record(r)
+            except Exception as exc:
+                rec["cpu_baseline"] = {"value": None, "sample": f"failed: {exc!r}"}
+        out.append(rec)
+    return out
+
+
+def parity_check(E, torch, dist, it, A, sptr, dev) -> dict:
+    """x_k gathered on every rank -> plain single-GPU launch over this rank's rows -> compare with
+    the slice the sharded step produces from its own (pushed / gathered) copy of x_k."""
+    xk = it.gather_result()                                   # full x_k on every rank
+    rows = it.hi - it.lo
+    want = torch.empty(rows, dtype=torch.float64, device=dev)
+    A.spmv_device(want, xk, E.OVERWRITE, sptr)
+    it.step(sptr)
+    torch.cuda.synchronize()
+    it.check()
+    got = it.local()
+    same = bool(torch.equal(got.view(torch.int64), want.view(torch.int64)))
+    finite = bool(torch.isfinite(got).all())
+    t = torch.tensor([1 if (same and finite) else 0], dtype=torch.int32, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return {"bit_equal": bool(t.item() == 1), "after_steps": it.steps_done - 1,
+            "how": "every rank: plain spmv_device over its rows from the all-gathered x_k == its slice of the "
+                   "sharded x_{k+1}, fp64 bit patterns, MIN over ranks"}
+
+
+def run_config5(E, torch, dist, rank, world, local_rank, dev, sptr, stream, peak, sampler, iters: int = 100) -> dict:
+    """BASELINE config 5: 27-point stencil 768^3 (IDXTYPEWIDTH=64), rows sharded over the ranks,
+    `iters` iterations of x <- A*x, with the fused push exchange and with the NCCL all-gather."""
+    import numpy as np
+
+    from ellspmv_b200.sharded import ShardedIterate, partition_rows
+    kind_name, K, idx_bits, _, vals_it, dims_of, _ = WORKLOADS["stencil27_768"]
+    dims = dims_of(world)
+    global_rows = int(np.prod(dims))
+    lo, hi = partition_rows(global_rows, world)[rank]
+    rows = hi - lo
+    rec = {"config": workload_name("stencil27_768", world), "iterations": iters, "scaling": "strong",
+           "rows_per_gpu": rows}
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    A = E.EllMatrix.generate(E.GEN_STENCIL27, dims, vals_it, 42, idx_bits, row_begin=lo, row_end=hi, device=local_rank)
+    info = A.info()
+    x_touched = int(info.max_col - info.min_col + 1)
+    rec["kernel"] = kernel_description(info, 0)
+    for exchange in ("push", "allgather"):
+        it = ShardedIterate(A, rank, world, exchange=exchange)
+        it.set_x(lambda a, b: torch.ones(b - a, dtype=torch.float64, device=dev))
+        for _ in range(3):
+            it.step(sptr)
+        barrier()
+        tx0 = sampler.nvlink_tx_bytes()
+        ms = time_steps(torch, stream, lambda: it.step(sptr), iters, barrier)
+        tx1 = sampler.nvlink_tx_bytes()
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item()) / iters
+        r = kernel_record(E, info, rows, K, idx_bits, ms, False, x_touched, peak)
+        d = it.describe()
+        out = {"ms_per_step": r["ms_per_step"], "gflops": round(2.0 * global_rows * K / ms * 1e-6, 1),
+               "per_gpu_as_stored_gbs": r["as_stored_gbs"], "per_gpu_frac_as_stored": r["frac_as_stored"],
+               "per_gpu_algorithmic_gbs": r["algorithmic_gbs"],
+               "bytes_sent_per_step_rank0_planned": d["bytes_sent_per_step_rank0"],
+               "bytes_sent_per_step_rank0_nvml": (round((tx1 - tx0) / iters) if tx0 is not None and tx1 is not None else None),
+               "barrier": d["barrier"]}
+        if exchange == "push":
+            out["parity_check"] = parity_check(E, torch, dist, it, A, sptr, dev)
+        rec[exchange] = out
+        it.close()
+    rec["pattern_rows_frac"] = round(int(info.pattern_rows) / max(rows, 1), 4)
+    A.free()
+    torch.cuda.empty_cache()
+    return rec
+
+
 def main_ours(args, rank: int, local_rank: int, world: int):
     import numpy as np
     import torch
@@ -262,7 +529,7 @@ def main_ours(args, rank: int, local_rank: int, world: int):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
-    from ellspmv_b200.sharded import partition_rows
+    from ellspmv_b200.sharded import ShardedIterate, partition_rows
     kind_name, K, idx_bits, vals_acc, vals_it, dims_of, scaling = WORKLOADS[args.workload]
     kind = {"laplace2d": E.GEN_LAPLACE2D, "stencil27": E.GEN_STENCIL27, "random": E.GEN_RANDOM}[kind_name]
     dims = dims_of(world)
@@ -270,11 +537,14 @@ def main_ours(args, rank: int, local_rank: int, world: int):
     row_lo, row_hi = partition_rows(global_rows, world)[rank]
     rows = row_hi - row_lo                   # this GPU's rows
     flags = args.flags
-    A = E.EllMatrix.generate(kind, dims, vals_acc if world == 1 else vals_it, 42, idx_bits,
+    # one matrix for every mode: the iterate values (row sums <= 1) keep x bounded over any number of steps
+    A = E.EllMatrix.generate(kind, dims, vals_it if kind_name != "random" else vals_acc, 42, idx_bits,
                              row_begin=row_lo, row_end=row_hi, device=local_rank, flags=flags)
     info = A.info()
     stream = torch.cuda.current_stream()
     sptr = stream.cuda_stream
+    peak, peak_src = measured_peak()
+    warmup = max(args.warmup, 3)
 
     def barrier():
         if dist is not None:
@@ -282,85 +552,107 @@ def main_ours(args, rank: int, local_rank: int, world: int):
         torch.cuda.synchronize()
 
     sampler = ClockSampler(local_rank)
+    x_touched = int(info.max_col - info.min_col + 1) if kind_name != "random" else int(info.num_columns)
+    square = int(info.num_columns) == global_rows
 
+    # ---- headline: x_{k+1} <- A*x_k, the same step at every N ----------------------------------
+    sharded = None
     if world == 1:
         gen = torch.Generator(device=dev).manual_seed(1234)
-        x = torch.randn(int(info.num_columns), dtype=torch.float64, device=dev, generator=gen)
-        y = torch.zeros(rows, dtype=torch.float64, device=dev)
-        mode_name = "accumulate (y += A*x, the reference's ellgemv semantics)"
+        xs = [torch.randn(int(info.num_columns), dtype=torch.float64, device=dev, generator=gen),
+              torch.zeros(max(int(info.num_columns), rows), dtype=torch.float64, device=dev)]
+        state = {"cur": 0}
 
         def step():
-            A.spmv_device(y, x, E.ACCUMULATE, sptr)
-        sharded = None
-        y_rmw = True
+            c = state["cur"]
+            A.spmv_device(xs[1 - c], xs[c], E.OVERWRITE, sptr)
+            if square:
+                state["cur"] = 1 - c
+        step_name = "iterate (x_{k+1} <- A*x_k on two resident vectors; one GPU: no exchange)"
     else:
-        from ellspmv_b200.sharded import ShardedIterate
         sharded = ShardedIterate(A, rank, world, exchange=args.exchange, barrier=args.barrier)
         sharded.set_x(lambda lo, hi: torch.ones(hi - lo, dtype=torch.float64, device=dev))
-        mode_name = f"iterate (x <- A*x, exchange={sharded.exchange})"
+        step_name = (f"iterate (x_{{k+1}} <- A*x_k, rows sharded over {world} GPUs, exchange={sharded.exchange}, "
+                     f"step hand-shake={sharded.barrier if sharded.exchange == 'push' else 'nccl collective'})")
 
         def step():
             sharded.step(sptr)
-        y_rmw = False
 
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(warmup):
         step()
     barrier()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     launches_before = A.info().launches
     sampler.start()
-    ev[0].record(stream)
-    for i in range(args.steps):
-        step()
-        ev[i + 1].record(stream)
-    barrier()
+    total_ms = time_steps(torch, stream, step, args.steps, barrier)
     sampler.stop()
-    total_ms = ev[0].elapsed_time(ev[-1])
     if dist is not None:
         t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = float(t.item())
     ms_per_step = total_ms / args.steps
-    # our kernels launched inside the timed region: the SpMV launches counted by the library,
-    # plus one device-barrier kernel per step in the fused push mode
+    # our kernels launched inside the timed region: the SpMV launches counted by the library
+    # (the fused exchange needs no other kernel), plus one barrier kernel per step in the
+    # "device" hand-shake mode
     timed_launches = int(A.info().launches - launches_before)
     if sharded is not None and sharded.exchange == "push" and sharded.barrier == "device":
         timed_launches += args.steps
 
     flops_step = 2.0 * global_rows * K
     value = flops_step / (ms_per_step * 1e-3) * 1e-9
-    # x entries this GPU's launch touches: the column range its rows reference
-    x_touched = int(info.max_col - info.min_col + 1) if kind_name != "random" else int(info.num_columns)
-    bytes_launch = algorithmic_bytes(rows, x_touched, K, idx_bits // 8, y_rmw)
-    bytes_min = algorithmic_bytes(rows, x_touched, K, idx_bits // 8, False)
-    # what the kernel really streams: 64-bit indices are stored as 32-bit on the device by default
-    # ... and rows whose indices follow an offset pattern do not read their indices at all
-    pattern_rows = int(info.pattern_rows)
-    bytes_stored = (algorithmic_bytes(rows, x_touched, K, int(info.dev_idx_bits) // 8, y_rmw)
-                    - pattern_rows * K * (int(info.dev_idx_bits) // 8))
-    peak, peak_src = measured_peak()
-    achieved = bytes_launch / (ms_per_step * 1e-3) * 1e-9
-    workload = f"{kind_name}_{'x'.join(str(d) for d in dims)}_K{K}_idx{idx_bits}"
+    head = kernel_record(E, info, rows, K, idx_bits, ms_per_step, False, x_touched, peak)
+    if sharded is not None:
+        sharded.check()
 
-    # second kernel-only figure at N=1: overwrite mode (y <- A*x), no y read
-    extra = {}
+    line = {
+        "metric": "ell_spmv_fp64_gflops", "value": round(value, 2), "unit": "GFLOP/s",
+        "n_gpus": world, "steps": args.steps, "warmup": warmup,
+        "ms_per_step": round(ms_per_step, 5), "higher_is_better": True, "scaling": scaling,
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.workload, world),
+        "step": step_name,
+        "kernel": {"name": kernel_description(info, flags), "rows_per_thread": info.rows_per_thread,
+                   "slice_rows": info.slice_rows, "dev_idx_bits": int(info.dev_idx_bits),
+                   "pattern_rows_frac": head["pattern_rows_frac"],
+                   "l2": f"inputs larger than L2 ({rows * K * (8 + idx_bits // 8) / 1e9:.1f} GB matrix per GPU vs 126 MB L2), no flush needed"},
+        "gbs": round(head["as_stored_gbs"] * world, 1),
+        "roofline": {"bound": "hbm", "achieved": head["as_stored_gbs"], "peak": peak, "unit": "GB/s",
+                     "frac": head["frac_as_stored"],
+                     "traffic": recorded_traffic(workload_name(args.workload, 1) + "_iterate") if world == 1 else None,
+                     "peak_source": peak_src, "bytes_per_launch": head["bytes_as_stored"],
+                     "bytes_model": "as stored on the device: 8*K*rows (values) + index bytes actually read "
+                                    "(device index width; rows on an offset pattern read none) + 8*x_touched + 8*rows (y written once)",
+                     "algorithmic": {"achieved": head["algorithmic_gbs"], "frac": head["frac_algorithmic"],
+                                     "bytes_per_launch": head["bytes_algorithmic"],
+                                     "bytes_model": f"SURVEY 8(d): K*(8+{idx_bits // 8})*rows + 8*x_touched + 8*rows"},
+                     "compression_gain": round(head["bytes_algorithmic"] / head["bytes_as_stored"], 4)},
+        "gpu_launches": timed_launches,
+    }
+
+    # ---- the reference's own semantics on the same matrix: y <- y + A*x, x constant ---------------
     if world == 1:
+        y = torch.zeros(rows, dtype=torch.float64, device=dev)
+        xa = xs[0]
         for _ in range(3):
-            A.spmv_device(y, x, E.OVERWRITE, sptr)
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            A.spmv_device(y, xa, E.ACCUMULATE, sptr)
         n2 = min(args.steps, 50)
-        e0.record(stream)
-        for _ in range(n2):
-            A.spmv_device(y, x, E.OVERWRITE, sptr)
-        e1.record(stream)
-        torch.cuda.synchronize()
-        ms2 = e0.elapsed_time(e1) / n2
-        extra["overwrite"] = {"ms_per_step": round(ms2, 5), "gflops": round(flops_step / ms2 * 1e-6, 2),
-                              "gbs": round(bytes_min / ms2 * 1e-6, 1), "frac": round(bytes_min / ms2 * 1e-6 / peak, 4)}
+        ms2 = time_steps(torch, stream, lambda: A.spmv_device(y, xa, E.ACCUMULATE, sptr), n2, barrier) / n2
+        acc = kernel_record(E, info, rows, K, idx_bits, ms2, True, x_touched, peak)
+        acc["traffic"] = recorded_traffic(workload_name(args.workload, 1) + "_accumulate")
+        line["accumulate"] = acc
+        del y
+    else:
+        line["parity_check"] = parity_check(E, torch, dist, sharded, A, sptr, dev)
+        line["exchange"] = sharded.describe()
+    line["clocks"] = sampler.summary()
 
-    # ---- e2e: the C-ABI call with HOST vectors ----------------------------------
+    # ---- e2e: the C-ABI call with HOST vectors ------------------------------------------------
     n_e2e = max(1, min(args.steps, args.e2e_steps))
+    if sharded is not None:
+        sharded.close()
+        sharded = None
+    if world == 1:
+        del xs
+    torch.cuda.empty_cache()
     xh = torch.empty(int(info.num_columns), dtype=torch.float64).pin_memory()
     yh = torch.zeros(rows, dtype=torch.float64).pin_memory()
     xh.fill_(1.0)
@@ -377,54 +669,42 @@ def main_ours(args, rank: int, local_rank: int, world: int):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_e2e = float(t.item())
     e2e_value = flops_step * n_e2e / t_e2e * 1e-9
-    # sanity: A*ones accumulated n_e2e times is n_e2e * (boundary indicator); checked on the host result
-    if world == 1 and args.workload == "laplace2d":
-        g = yn.reshape(GRID, GRID)
-        assert g[1:-1, 1:-1].max() == 0.0 and g[0, 1] == n_e2e and g[0, 0] == 2 * n_e2e, "e2e result is wrong"
+    # sanity on the host result: A*ones accumulated n times.  With the iterate values (centre 0.5,
+    # neighbours 0.125) a row sums to 0.5 + 0.125 * (number of neighbours inside the grid).
+    if args.workload == "laplace2d":
+        g = yn.reshape(-1, GRID)
+        first = rank == 0
+        inner = g[1:-1, 1:-1] if world == 1 else g[1 if first else 0:-1 if rank == world - 1 else None, 1:-1]
+        assert inner.min() == inner.max() == n_e2e * 1.0, "e2e result is wrong (interior rows)"
+        if first:
+            assert g[0, 0] == n_e2e * 0.75 and g[0, 1] == n_e2e * 0.875, "e2e result is wrong (corner/edge rows)"
+    line["e2e"] = {"value": round(e2e_value, 2), "unit": "GFLOP/s",
+                   "h2d_bytes_per_step": (x_touched + rows) * 8, "d2h_bytes_per_step": rows * 8,
+                   "steps": n_e2e, "ms_per_step": round(t_e2e / n_e2e * 1e3, 3),
+                   "api": "ellspmv_cuda_spmv(A, y_host, x_host, 1, ACCUMULATE) on every rank's shard, pinned host "
+                          "vectors; x is uploaded on the column range the shard references only"}
+    del xh, yh, xn, yn
+    A.free()
+    torch.cuda.empty_cache()
 
-    line = {
-        "metric": "ell_spmv_fp64_gflops", "value": round(value, 2), "unit": "GFLOP/s",
-        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": round(ms_per_step, 5), "higher_is_better": True, "scaling": scaling,
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload, "rows_per_gpu": rows, "rowsize": K, "idx_bits": idx_bits,
-                   "mode": mode_name, "rows_per_thread": info.rows_per_thread, "slice_rows": info.slice_rows,
-                   "kernel": kernel_description(flags, bool(info.fma))
-                   + (f"; {pattern_rows / max(rows, 1):.1%} of the rows take their column indices from an offset pattern"
-                      if pattern_rows else ""),
-                   "l2": f"inputs larger than L2 ({rows * K * (8 + idx_bits // 8) / 1e9:.1f} GB matrix per GPU vs 126 MB L2), no flush needed",
-                   "parallelism": f"rowshard{world}"},
-        "gbs": round(achieved * world, 1),
-        "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                     "frac": round(achieved / peak, 4), "traffic": recorded_traffic((workload + ("_staged" if flags & (1 << 17) else "")) if world == 1 else "sharded"),
-                     "peak_source": peak_src, "bytes_per_launch": bytes_launch,
-                     "bytes_model": f"K*(8+{idx_bits // 8})*rows + 8*x_touched + 8*rows" + (" + 8*rows (y is read-modify-written)" if y_rmw else ""),
-                     "achieved_as_stored": round(bytes_stored / (ms_per_step * 1e-3) * 1e-9, 1),
-                     "frac_as_stored": round(bytes_stored / (ms_per_step * 1e-3) * 1e-9 / peak, 4),
-                     "dev_idx_bits": int(info.dev_idx_bits),
-                     "pattern_rows_frac": round(pattern_rows / max(rows, 1), 4),
-                     "achieved_y_once": round(bytes_min / (ms_per_step * 1e-3) * 1e-9, 1),
-                     "frac_y_once": round(bytes_min / (ms_per_step * 1e-3) * 1e-9 / peak, 4)},
-        "e2e": {"value": round(e2e_value, 2), "unit": "GFLOP/s", "h2d_bytes_per_step": (int(info.num_columns) + rows) * 8,
-                "d2h_bytes_per_step": rows * 8, "steps": n_e2e, "ms_per_step": round(t_e2e / n_e2e * 1e3, 3),
-                "api": "ellspmv_cuda_spmv(A, y_host, x_host, 1, ACCUMULATE), pinned host vectors"},
-        "gpu_launches": timed_launches,
-        "clocks": sampler.summary(),
-    }
-    line.update(extra)
-    if sharded is not None:
-        line["exchange"] = sharded.describe()
-
-    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload == "laplace2d":
+    # ---- the other BASELINE configs ---------------------------------------------------------------
+    if world == 1 and args.workload == "laplace2d" and not args.no_other_configs:
+        line["other_configs"] = other_configs(E, torch, dev, sptr, stream, min(args.steps, 20), peak,
+                                              with_cpu=not args.no_cpu_baseline)
+    if world > 1 and args.workload == "laplace2d" and not args.no_config5:
         try:
-            r = cpu_reference_run(5, 1, budget_s=25.0)
-            line["cpu_baseline"] = {"value": round(r["gflops"], 3), "unit": "GFLOP/s", "cores": r["cores"],
-                                    "kind": r["kind"], "sample": r["sample"],
-                                    "best": round(r["best_gflops"], 3), "gbs_effective": round(r["gbs"], 2)}
+            line["config5"] = run_config5(E, torch, dist, rank, world, local_rank, dev, sptr, stream, peak, sampler,
+                                          iters=args.config5_iters)
+        except Exception as exc:
+            line["config5"] = {"error": repr(exc)}
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            r = cpu_reference_run(args.workload, 1, 5, 1, budget_s=20.0)
+            line["cpu_baseline"] = baseline_record(r)
         except Exception as exc:   # the baseline is informative; never lose the GPU line over it
             line["cpu_baseline"] = {"value": None, "unit": "GFLOP/s", "cores": os.cpu_count(), "kind": "port",
                                     "sample": f"failed: {exc!r}"}
-    A.free()
     if rank == 0:
         print(json.dumps(line), flush=True)
     if dist is not None:
@@ -440,17 +720,20 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--exchange", choices=["auto", "push", "allgather"], default="auto")
-    ap.add_argument("--barrier", choices=["device", "nccl"], default="device")
+    ap.add_argument("--barrier", choices=["fused", "device", "nccl"], default="fused")
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="laplace2d")
     ap.add_argument("--flags", type=lambda s: int(s, 0), default=0, help="ELLSPMV_CUDA_* upload flags")
     ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--config5-iters", type=int, default=100)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true")
+    ap.add_argument("--no-config5", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
-        return main_reference(args, rank)
+        return main_reference(args, rank, world)
     if world != args.gpus:
         if world == 1 and args.gpus > 1:
             raise SystemExit(f"--gpus {args.gpus} needs torchrun with {args.gpus} ranks (WORLD_SIZE is 1)")

@@ -32,6 +32,7 @@ NARROW_INDEX = 1 << 6
 COLUMN_BLOCKED = 1 << 7
 STAGED_GATHER = 1 << 17
 NO_PATTERN = 1 << 18
+NO_STAGED_GATHER = 1 << 19
 WIDE_INDEX = 1 << 16
 ROWS_PER_THREAD_SHIFT = 8
 VARIANT_SHIFT = 12
@@ -62,6 +63,17 @@ class Info(C.Structure):
         ("rows_per_thread", C.c_int), ("kernel", C.c_int), ("fma", C.c_int), ("device", C.c_int),
         ("device_bytes", C.c_int64), ("min_col", C.c_int64), ("max_col", C.c_int64),
         ("launches", C.c_int64), ("num_gpus", C.c_int), ("pattern_rows", C.c_int64),
+        ("staged", C.c_int), ("launches_per_spmv", C.c_int), ("tune_ms", C.c_double * 2),
+        ("exception_entries", C.c_int64), ("long_rows", C.c_int64),
+    ]
+
+
+class CsrInfo(C.Structure):
+    _fields_ = [
+        ("num_rows", C.c_int64), ("num_columns", C.c_int64), ("csrsize", C.c_int64),
+        ("min_row_len", C.c_int64), ("max_row_len", C.c_int64), ("min_col", C.c_int64), ("max_col", C.c_int64),
+        ("device_bytes", C.c_int64), ("kernel", C.c_int), ("ell_view", C.c_int), ("ell_staged", C.c_int),
+        ("launches_per_spmv", C.c_int), ("ell_pattern_rows", C.c_int64), ("num_gpus", C.c_int), ("fma", C.c_int),
     ]
 
 
@@ -91,6 +103,7 @@ _PROTOTYPES = {
     "csrspmv_cuda_spmv": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P]),
     "csrspmv_cuda_spmv_device": (C.c_int, [_P, _P, _P, C.c_int, _P]),
     "csrspmv_cuda_device_bytes": (_I64, [_P]),
+    "csrspmv_cuda_get_info": (C.c_int, [_P, C.POINTER(CsrInfo)]),
     "csrspmv_cuda_free": (None, [_P]),
     "ellspmv_cuda_malloc_host": (C.c_int, [C.POINTER(_P), _I64]),
     "ellspmv_cuda_free_host": (None, [_P]),
@@ -355,6 +368,23 @@ class CsrMatrix:
 
     def device_bytes(self) -> int:
         return load_library().csrspmv_cuda_device_bytes(self._h)
+
+    def info(self) -> CsrInfo:
+        out = CsrInfo()
+        _check(load_library().csrspmv_cuda_get_info(self._h, C.byref(out)), "csrspmv_cuda_get_info")
+        return out
+
+    def describe(self) -> str:
+        """Which kernels a launch of this handle runs."""
+        i = self.info()
+        arith = "fma (tolerance)" if i.fma else "mul-then-add (bit-exact)"
+        if i.ell_view:
+            how = "rows of one length" if i.ell_view == 2 else "per-row lengths"
+            path = ("staged gather (column blocks), then thread-per-row" if i.ell_staged else "thread-per-row")
+            return f"sliced-ELL view of the CSR rows ({how}, width {i.max_row_len}): {path}, {arith}"
+        name = {1: "smem-staged stream kernel", 2: "sub-warp per row + shuffle tree (tolerance)",
+                3: "scalar thread-per-row", 5: "adaptive row blocks (short rows streamed, long rows cooperatively)"}
+        return f"native CSR: {name.get(i.kernel, str(i.kernel))}, {arith}"
 
     def free(self) -> None:
         if self._h:

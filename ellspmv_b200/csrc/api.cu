@@ -75,6 +75,7 @@ int configure(ellspmv_cuda_matrix *A, unsigned flags)
     if (R == 0) R = A->lay.rowsize <= 12 ? 2 : 1;
     if (R != 1 && R != 2 && R != 4) ELL_FAIL(EINVAL, "rows per thread must be 1, 2 or 4 (got %d)", R);
     int kernel = flags & ELLSPMV_CUDA_KERNEL_MASK;
+    A->kernel_auto = kernel == ELLSPMV_CUDA_KERNEL_AUTO;
     if (kernel == ELLSPMV_CUDA_KERNEL_AUTO) kernel = ELLSPMV_CUDA_KERNEL_THREAD;
     if (kernel != ELLSPMV_CUDA_KERNEL_THREAD && kernel != ELLSPMV_CUDA_KERNEL_WARP)
         ELL_FAIL(EINVAL, "unknown kernel selector %d", kernel);
@@ -174,11 +175,86 @@ int build_patterns(ellspmv_cuda_matrix *A)
 
 // ELLSPMV_CUDA_COLUMN_BLOCKED: bin the entries by column block so that each
 // block's slice of x stays in L2 (ell_blocked.cu); no-op when x already fits
+int launch(ellspmv_cuda_matrix *A, double *y_dev, const double *x_dev, int beta,
+           const PushTargets *push, cudaStream_t stream, int64_t slice_begin, int64_t num_slices,
+           const StepSync *sync);
+
+// KERNEL_AUTO for matrices with scattered columns (BASELINE config 4): when x does not fit in
+// L2, no offset pattern was found and a warp's gather touches many different lines, build the
+// staged gather, time it against the direct gather on scratch vectors and keep the faster one.
+// Both give the same bits (ell_staged.cu), so the choice is invisible in the results.
+int auto_staged_gather(ellspmv_cuda_matrix *A, long long block_bytes)
+{
+    const int64_t x_bytes = A->num_columns * 8;
+    if (!A->kernel_auto || (A->flags & (ELLSPMV_CUDA_NO_STAGED_GATHER | ELLSPMV_CUDA_COLUMN_BLOCKED)) ||
+        A->cfg.kernel != ELLSPMV_CUDA_KERNEL_THREAD || (A->cfg.variant & 1))
+        return 0;
+    long long min_x = 96LL << 20;                    // L2 is 126 MB: below this x mostly stays resident by itself
+    if (const char *env = getenv("ELLSPMV_CUDA_AUTO_STAGED_MIN_X_BYTES")) min_x = atoll(env);
+    if (x_bytes <= min_x || A->pat.patid) return 0;
+    double lines = 0.0;
+    ELL_CK(sg_scatter_estimate(A->dev_idx_bits, A->cols, A->lay, &lines, A->stream));
+    if (lines < 16.0) return 0;                      // gathers mostly share lines: L1/L2 serve them
+    size_t free_b = 0, total_b = 0;
+    ELL_CK(cudaMemGetInfo(&free_b, &total_b));
+    const int64_t scratch = (A->num_columns + A->lay.num_rows) * 8;
+    if ((int64_t)free_b < sg_bytes_estimate(A->dev_idx_bits, A->lay) + scratch + (1LL << 30)) return 0;
+    cudaError_t ce = sg_build(&A->sg, A->dev_idx_bits, A->cols, A->lay, A->num_columns, block_bytes, A->stream);
+    if (ce == cudaErrorMemoryAllocation) { cudaGetLastError(); A->sg = nullptr; return 0; }
+    if (ce != cudaSuccess) { set_last_error("staged gather: %s", cudaGetErrorString(ce)); return cuda_to_errno(ce); }
+    if (!A->sg) return 0;
+    // the trial: one warm-up and two timed launches of each path on zeroed scratch vectors
+    double *sx = nullptr, *sy = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    SgMatrix *sg = A->sg;
+    auto cleanup = [&]() { cudaFree(sx); cudaFree(sy); if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); };
+    ce = cudaMalloc(&sx, (size_t)A->num_columns * 8);
+    if (ce == cudaSuccess) ce = cudaMalloc(&sy, (size_t)(A->lay.num_rows > 0 ? A->lay.num_rows : 1) * 8);
+    if (ce == cudaSuccess) ce = cudaMemsetAsync(sx, 0, (size_t)A->num_columns * 8, A->stream);
+    if (ce == cudaSuccess) ce = cudaEventCreate(&e0);
+    if (ce == cudaSuccess) ce = cudaEventCreate(&e1);
+    if (ce != cudaSuccess) {
+        // no room for the trial: keep the staged path only on request
+        cudaGetLastError(); cleanup(); sg_free(A->sg); A->sg = nullptr;
+        return 0;
+    }
+    const int64_t launches_before = A->launches;
+    int err = 0;
+    for (int path = 0; path < 2 && !err; path++) {
+        A->sg = path ? sg : nullptr;
+        err = launch(A, sy, sx, 0, nullptr, A->stream, 0, -1, nullptr);
+        if (!err && cudaEventRecord(e0, A->stream) != cudaSuccess) err = EIO;
+        for (int i = 0; i < 2 && !err; i++) err = launch(A, sy, sx, 0, nullptr, A->stream, 0, -1, nullptr);
+        if (!err && (cudaEventRecord(e1, A->stream) != cudaSuccess || cudaEventSynchronize(e1) != cudaSuccess)) err = EIO;
+        float ms = 0.f;
+        if (!err && cudaEventElapsedTime(&ms, e0, e1) != cudaSuccess) err = EIO;
+        A->tune_ms[path] = ms / 2.0;
+    }
+    A->launches = launches_before;
+    A->sg = sg;
+    cleanup();
+    if (err) { set_last_error("staged gather trial failed"); return err; }
+    if (A->tune_ms[1] < A->tune_ms[0]) {
+        A->staged_mode = 2;
+        A->device_bytes += sg_bytes(A->sg);
+    } else {
+        sg_free(A->sg);
+        A->sg = nullptr;
+    }
+    return 0;
+}
+
 int build_column_blocks(ellspmv_cuda_matrix *A)
 {
-    if (!(A->flags & (ELLSPMV_CUDA_COLUMN_BLOCKED | ELLSPMV_CUDA_STAGED_GATHER)) || A->lay.num_rows <= 0 ||
-        A->lay.rowsize <= 0)
-        return 0;
+    if (A->lay.num_rows <= 0 || A->lay.rowsize <= 0) return 0;
+    if (!(A->flags & (ELLSPMV_CUDA_COLUMN_BLOCKED | ELLSPMV_CUDA_STAGED_GATHER))) {
+        long long target = 48LL << 20;
+        if (const char *env = getenv("ELLSPMV_CUDA_BLOCK_BYTES")) {
+            long long v = atoll(env);
+            if (v >= 8) target = v;
+        }
+        return auto_staged_gather(A, target);
+    }
     // x bytes per column block: 48 MB stays resident in the 126 MB (2 x 63 MB) L2 next to the
     // streaming matrix -- measured 11.6 / 9.2 / 9.8 / 13.5 ms at 32 / 48 / 64 / 80 MB on BASELINE
     // config 4 (profiles/r1_c4_column_blocked.md); ELLSPMV_CUDA_BLOCK_BYTES overrides it
@@ -192,6 +268,7 @@ int build_column_blocks(ellspmv_cuda_matrix *A)
         cudaError_t ce = sg_build(&A->sg, A->dev_idx_bits, A->cols, A->lay, A->num_columns, target, A->stream);
         if (ce != cudaSuccess) { set_last_error("staged gather: %s", cudaGetErrorString(ce)); return cuda_to_errno(ce); }
         A->device_bytes += sg_bytes(A->sg);
+        if (A->sg) A->staged_mode = 1;
         return 0;
     }
     cudaError_t ce = cb_build(&A->cb, A->dev_idx_bits, A->vals, A->cols, A->lay, A->num_columns, target, A->stream);
@@ -272,6 +349,7 @@ int launch(ellspmv_cuda_matrix *A, double *y_dev, const double *x_dev, int beta,
     args.sd_order = A->sd_order;
     args.patid = A->pat.patid;
     args.pat = A->pat.pat;
+    args.rowlen = A->d_rowlen;
     // value-stream L2 prefetch 128 slices ahead when most rows are patterned (ell_kernels.cu)
     // (long rows have the loads in flight anyway; keep one request at or below 256 KB)
     args.prefetch = (A->pat.patid && A->pat.covered * 2 >= A->pat.groups &&
@@ -281,7 +359,7 @@ int launch(ellspmv_cuda_matrix *A, double *y_dev, const double *x_dev, int beta,
     if (sync) args.sync = *sync;          // only passed for a full launch of a fused_sync_capable handle
     if (A->sg && slice_begin == 0 && num_slices == A->lay.num_slices) {
         ELL_CK(sg_spmv(A->sg, A->cfg.fma, A->vals, x_dev, y_dev, A->d_ad, A->sd_order, A->lay.num_rows,
-                       A->row_begin, beta, push, stream));
+                       A->row_begin, beta, push, stream, A->d_rowlen));
         A->launches += sg_launches(A->sg);
         return 0;
     }
@@ -385,6 +463,14 @@ int new_handle(ellspmv_cuda_matrix **out, int idx_width_bits, int64_t global_row
 }  // namespace
 
 namespace ellspmv {
+// one y <- beta*y + A*x on a single-GPU CSR handle: through the ELL view when there is one
+int csr_launch(csrspmv_cuda_matrix *A, double *y_dev, const double *x_dev, int beta, cudaStream_t stream)
+{
+    if (A->ell) return launch(A->ell, y_dev, x_dev, beta, nullptr, stream, 0, -1, nullptr);
+    CsrSpmvArgs args = {A->rowptr, A->cols, A->vals, x_dev, y_dev, A->num_rows, beta, A->d_ad, A->row_begin};
+    ELL_CK(launch_csr_spmv(A->idx_bits, A->fma, A->kernel, args, stream));
+    return 0;
+}
 int launch_shard(ellspmv_cuda_matrix *A, double *y_dev, const double *x_dev, int beta,
                  const PushTargets *push, cudaStream_t stream)
 {
@@ -464,6 +550,7 @@ void ellspmv_cuda_free(ellspmv_cuda_matrix *A)
     if (A->cols) cudaFree(A->cols);
     if (A->d_minmax) cudaFree(A->d_minmax);
     if (A->d_ad) cudaFree(A->d_ad);
+    if (A->d_rowlen) cudaFree(A->d_rowlen);
     if (A->d_remote) cudaFree(A->d_remote);
     if (A->d_done) cudaFree(A->d_done);
     pattern_free(&A->pat);
@@ -740,6 +827,10 @@ int ellspmv_cuda_get_info(const ellspmv_cuda_matrix *A, ellspmv_cuda_info *info)
     info->launches = A->launches;
     info->num_gpus = 1;
     info->pattern_rows = A->pat.covered * A->pat.group_rows;
+    info->staged = A->sg ? A->staged_mode : 0;
+    info->launches_per_spmv = A->sg ? sg_launches(A->sg) : (A->cb ? cb_blocks(A->cb) : 1);
+    info->tune_ms[0] = A->tune_ms[0];
+    info->tune_ms[1] = A->tune_ms[1];
     return 0;
 }
 
@@ -888,6 +979,7 @@ void csrspmv_cuda_free(csrspmv_cuda_matrix *A)
     if (A->rowptr) cudaFree(A->rowptr);
     if (A->d_ad) cudaFree(A->d_ad);
     if (A->d_scratch) cudaFree(A->d_scratch);
+    if (A->ell) ellspmv_cuda_free(A->ell);
     if (A->cols) cudaFree(A->cols);
     if (A->vals) cudaFree(A->vals);
     if (A->d_x) cudaFree(A->d_x);
@@ -932,9 +1024,61 @@ static int csr_new(csrspmv_cuda_matrix **out, int idx_width_bits, int64_t num_ro
     if ((ce = cudaMalloc(&A->vals, nz * 8)) != cudaSuccess) return fail(ce);
     if ((ce = cudaMalloc(&A->d_x, (size_t)(num_columns > 0 ? num_columns : 1) * 8)) != cudaSuccess) return fail(ce);
     if ((ce = cudaMalloc(&A->d_y, (size_t)(num_rows > 0 ? num_rows : 1) * 8)) != cudaSuccess) return fail(ce);
-    if ((ce = cudaMalloc(&A->d_scratch, 32)) != cudaSuccess) return fail(ce);
+    if ((ce = cudaMalloc(&A->d_scratch, 40)) != cudaSuccess) return fail(ce);
     if ((ce = cudaStreamCreateWithFlags(&A->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(ce);
     A->device_bytes = (num_rows + 1) * 8 + (int64_t)nz * (8 + idx_width_bits / 8) + (num_columns + num_rows) * 8;
+    return 0;
+}
+
+// KERNEL_AUTO on a CSR matrix with balanced rows: keep a sliced-ELL view of the same entries
+// (width = the longest row) and run the launches through the ELL kernels -- coalesced streams,
+// offset patterns, L2 prefetch and the staged gather for scattered columns all apply, where the
+// native CSR kernels below gather with one thread per row.  The view carries the rows' lengths:
+// a slot past a row's end is never touched arithmetically, so the result is csrgemv's
+// (csrspmv.c:1588-1593) bit for bit, non-finite x included.  Rows of one length need no
+// length array at all (the random matrix of BASELINE config 4, every row K entries).
+// Skipped when the padding would exceed 25 % of the entries, a row is longer than 1024, or
+// memory is short; the CSR arrays stay on the device either way (download, fallback).
+static int csr_build_ell_view(csrspmv_cuda_matrix *A)
+{
+    if (A->num_rows <= 0 || A->csrsize <= 0 || A->max_row_len <= 0 || A->max_row_len > 1024) return 0;
+    if (getenv("CSRSPMV_CUDA_NO_ELL_VIEW")) return 0;
+    const int64_t K = A->max_row_len;
+    const int64_t padded = A->num_rows * K;
+    if (padded > A->csrsize + A->csrsize / 4 + 4096) return 0;
+    const bool uniform = A->min_row_len == A->max_row_len;
+    size_t free_b = 0, total_b = 0;
+    ELL_CK(cudaMemGetInfo(&free_b, &total_b));
+    if ((int64_t)free_b < padded * (8 + A->idx_bits / 8) + A->num_rows * 4 + (1LL << 30)) return 0;
+    unsigned flags = A->flags & (ELLSPMV_CUDA_FMA | ELLSPMV_CUDA_WIDE_INDEX | ELLSPMV_CUDA_NO_PATTERN |
+                                 ELLSPMV_CUDA_NO_STAGED_GATHER | ELLSPMV_CUDA_STAGED_GATHER | ELLSPMV_CUDA_L2_PERSIST_X);
+    if (!uniform) flags |= (1u << ELLSPMV_CUDA_ROWS_PER_THREAD_SHIFT) | ELLSPMV_CUDA_NO_PATTERN;   // the length-aware kernel: R = 1, explicit indices
+    ellspmv_cuda_matrix *V = nullptr;
+    int err = new_handle(&V, A->idx_bits, A->row_begin + A->num_rows, A->num_columns, K, A->row_begin,
+                         A->row_begin + A->num_rows, A->device, flags);
+    if (err) return err;
+    auto fail = [&](int e) { ellspmv_cuda_free(V); return e; };
+    if ((err = configure(V, flags))) return fail(err);
+    if ((err = alloc_matrix(V))) {
+        if (err == ENOMEM) { ellspmv_cuda_free(V); cudaGetLastError(); return 0; }
+        return fail(err);
+    }
+    cudaError_t ce = cudaSuccess;
+    if (!uniform) ce = cudaMalloc(&V->d_rowlen, (size_t)V->lay.padded_rows() * sizeof(int));
+    if (ce == cudaSuccess && !uniform) ce = cudaMemsetAsync(V->d_rowlen, 0, (size_t)V->lay.padded_rows() * sizeof(int), V->stream);
+    if (ce == cudaSuccess)
+        ce = csr_to_sliced(A->idx_bits, V->dev_idx_bits, A->rowptr, A->cols, A->vals, V->cols, V->vals, V->d_rowlen,
+                           V->lay, V->stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(V->stream);
+    if (ce != cudaSuccess) { set_last_error("csr -> ell view: %s", cudaGetErrorString(ce)); return fail(cuda_to_errno(ce)); }
+    if (!uniform) V->device_bytes += V->lay.padded_rows() * (int64_t)sizeof(int);
+    V->min_col = A->min_col;                       // checked by csr_inspect already
+    V->max_col = A->max_col;
+    warm_kernels(V);
+    if ((err = build_patterns(V))) return fail(err);
+    if ((err = build_column_blocks(V))) return fail(err);
+    A->ell = V;
+    A->device_bytes += V->device_bytes;
     return 0;
 }
 
@@ -952,12 +1096,17 @@ static int csr_pick_kernel(csrspmv_cuda_matrix *A)
         ELL_FAIL(EINVAL, "column index out of range: [%lld, %lld] with %lld columns", (long long)in.min_col,
                  (long long)in.max_col, (long long)A->num_columns);
     A->max_row_len = in.max_row_len;
+    A->min_row_len = in.min_row_len;
     A->min_col = in.min_col;
     A->max_col = in.max_col;
     if (!A->auto_kernel) return 0;
     const int64_t avg = A->num_rows > 0 ? (A->csrsize + A->num_rows - 1) / A->num_rows : 0;
     A->kernel = (A->max_row_len <= 4 * avg + 16) ? 3 : ELLSPMV_CUDA_KERNEL_THREAD;
-    return 0;
+    // ELLSPMV_CUDA_FMA: the stream kernel parks ROUNDED products and cannot contract; so that the
+    // bits under FMA do not depend on the row-length distribution (or differ between the shards of
+    // a group), AUTO then always takes a sequential-fma kernel: the ELL view or the scalar kernel
+    if (A->fma) A->kernel = 3;
+    return csr_build_ell_view(A);
 }
 
 int csrspmv_cuda_upload(
@@ -1046,6 +1195,7 @@ int csrspmv_cuda_set_diagonal(csrspmv_cuda_matrix *A, const double *ad)
     DeviceGuard g(A->device);
     if (!ad) {
         if (A->d_ad) { cudaFree(A->d_ad); A->d_ad = nullptr; }
+        if (A->ell) return ellspmv_cuda_set_diagonal(A->ell, nullptr, 0);
         return 0;
     }
     // x[i] is read at the row's own GLOBAL index (a shard's rows start at row_begin)
@@ -1059,6 +1209,8 @@ int csrspmv_cuda_set_diagonal(csrspmv_cuda_matrix *A, const double *ad)
     if (A->num_rows > 0)
         ELL_CK(cudaMemcpyAsync(A->d_ad, ad, (size_t)A->num_rows * 8, cudaMemcpyDefault, A->stream));
     ELL_CK(cudaStreamSynchronize(A->stream));
+    // csrgemvsd (csrspmv.c:1622-1627) is ellgemvsd's order: the slots summed from 0, then ad*x + yi
+    if (A->ell) return ellspmv_cuda_set_diagonal(A->ell, A->d_ad, 0);
     return 0;
 }
 
@@ -1071,10 +1223,7 @@ int csrspmv_cuda_spmv_device(
         ELL_FAIL(EINVAL, "mode must be ACCUMULATE or OVERWRITE");
     if (A->num_rows > 0 && (!y_dev || !x_dev)) ELL_FAIL(EINVAL, "NULL device vector");
     DeviceGuard g(A->device);
-    CsrSpmvArgs args = {A->rowptr, A->cols, A->vals, x_dev, y_dev, A->num_rows,
-                        mode == ELLSPMV_CUDA_ACCUMULATE ? 1 : 0, A->d_ad, A->row_begin};
-    ELL_CK(launch_csr_spmv(A->idx_bits, A->fma, A->kernel, args, (cudaStream_t)stream));
-    return 0;
+    return csr_launch(A, y_dev, x_dev, mode == ELLSPMV_CUDA_ACCUMULATE ? 1 : 0, (cudaStream_t)stream);
 }
 
 int csrspmv_cuda_spmv(
@@ -1099,9 +1248,7 @@ int csrspmv_cuda_spmv(
         ELL_CK(cudaMemcpyAsync(A->d_y, y, (size_t)A->num_rows * 8, cudaMemcpyDefault, s));
     ELL_CK(cudaEventRecord(A->events[0], s));
     for (int r = 0; r < repeat; r++) {
-        CsrSpmvArgs args = {A->rowptr, A->cols, A->vals, A->d_x, A->d_y, A->num_rows,
-                            mode == ELLSPMV_CUDA_ACCUMULATE ? 1 : 0, A->d_ad, A->row_begin};
-        ELL_CK(launch_csr_spmv(A->idx_bits, A->fma, A->kernel, args, s));
+        if ((err = csr_launch(A, A->d_y, A->d_x, mode == ELLSPMV_CUDA_ACCUMULATE ? 1 : 0, s))) return err;
         ELL_CK(cudaEventRecord(A->events[(size_t)r + 1], s));
     }
     if (A->num_rows > 0) ELL_CK(cudaMemcpyAsync(y, A->d_y, (size_t)A->num_rows * 8, cudaMemcpyDefault, s));
@@ -1132,6 +1279,41 @@ int csrspmv_cuda_download(const csrspmv_cuda_matrix *A, int64_t *rowptr, void *c
 }
 
 int64_t csrspmv_cuda_device_bytes(const csrspmv_cuda_matrix *A) { return A ? A->device_bytes : 0; }
+
+int csrspmv_cuda_get_info(const csrspmv_cuda_matrix *A, csrspmv_cuda_info *info)
+{
+    if (!A || !info) ELL_FAIL(EINVAL, "NULL argument");
+    memset(info, 0, sizeof(*info));
+    info->num_rows = A->num_rows;
+    info->num_columns = A->num_columns;
+    info->csrsize = A->csrsize;
+    info->device_bytes = A->device_bytes;
+    info->fma = A->fma ? 1 : 0;
+    info->num_gpus = A->shards.empty() ? 1 : (int)A->shards.size();
+    const csrspmv_cuda_matrix *S = A->shards.empty() ? A : A->shards[0];   // a group reports its first shard's kernels
+    info->min_row_len = S->min_row_len;
+    info->max_row_len = S->max_row_len;
+    info->min_col = S->min_col;
+    info->max_col = S->max_col;
+    info->kernel = S->kernel;
+    info->launches_per_spmv = 1;
+    if (S->ell) {
+        info->ell_view = S->ell->d_rowlen ? 1 : 2;
+        info->ell_staged = S->ell->sg ? S->ell->staged_mode : 0;
+        info->launches_per_spmv = S->ell->sg ? sg_launches(S->ell->sg) : 1;
+        info->ell_pattern_rows = S->ell->pat.covered * S->ell->pat.group_rows;
+    }
+    if (!A->shards.empty()) {
+        info->max_row_len = 0;
+        info->min_row_len = 0x7fffffffffffffffLL;
+        for (const csrspmv_cuda_matrix *T : A->shards) {
+            if (T->max_row_len > info->max_row_len) info->max_row_len = T->max_row_len;
+            if (T->num_rows > 0 && T->min_row_len < info->min_row_len) info->min_row_len = T->min_row_len;
+        }
+        if (info->min_row_len == 0x7fffffffffffffffLL) info->min_row_len = 0;
+    }
+    return 0;
+}
 
 /* ---- utilities ------------------------------------------------------------ */
 

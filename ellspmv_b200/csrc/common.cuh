@@ -105,6 +105,8 @@ struct EllSpmvArgs {
     const unsigned char *patid; // offset patterns (pattern.cu): one id per warp (32*R rows), 0xff = explicit indices; or NULL
     const long long     *pat;   // dictionary [kMaxPatterns][K] of column offsets relative to the GLOBAL row
     StepSync      sync;
+    const int    *rowlen;   // per row: how many leading slots count (CSR view: the rest is never touched
+                            //   arithmetically, so no 0*inf from a padded slot); NULL = all K
 };
 
 struct EllLaunchCfg {
@@ -138,9 +140,9 @@ struct CsrSpmvArgs {
 };
 cudaError_t launch_csr_spmv(int idx_bits, bool fma, int kernel, const CsrSpmvArgs &args,
                             cudaStream_t stream);
-struct CsrInspection { int64_t max_row_len, bad_rows, min_col, max_col; };
+struct CsrInspection { int64_t max_row_len, min_row_len, bad_rows, min_col, max_col; };
 cudaError_t csr_inspect(int idx_bits, const int64_t *rowptr, const void *cols, int64_t num_rows, int64_t csrsize,
-                        unsigned long long *scratch /* device, 32 bytes */, CsrInspection *res, cudaStream_t stream);
+                        unsigned long long *scratch /* device, 40 bytes */, CsrInspection *res, cudaStream_t stream);
 
 // ---- layout / generators (layout.cu) -------------------------------------
 // row-major chunk (rows [row0, row0+rows) of the shard) -> sliced layout
@@ -160,6 +162,11 @@ cudaError_t generate_sliced(int kind, const int64_t dims[3], const double vals[2
 cudaError_t generate_csr_random(const int64_t dims[3], uint64_t seed, int idx_bits,
                                 int64_t *rowptr, void *cols, double *vals, cudaStream_t stream);
 cudaError_t init_minmax(long long *minmax, cudaStream_t stream);
+// CSR rows -> sliced-ELL layout of width lay.rowsize (>= the longest row): entries keep their order,
+// the unused slots of a row get (its last column or 0, 0.0), rowlen[r] = the row's length
+cudaError_t csr_to_sliced(int src_idx_bits, int dst_idx_bits, const int64_t *rowptr, const void *src_cols,
+                          const double *src_vals, void *dst_cols, double *dst_vals, int *rowlen,
+                          const EllLayout &lay, cudaStream_t stream);
 cudaError_t mark_remote_slices(int idx_bits, const void *cols, const EllLayout &lay, int64_t lo, int64_t hi,
                                unsigned char *remote, cudaStream_t stream);
 
@@ -193,7 +200,10 @@ cudaError_t sg_build(SgMatrix **out, int idx_bits, const void *cols, const EllLa
                      int64_t target_x_bytes, cudaStream_t stream);
 cudaError_t sg_spmv(const SgMatrix *sg, bool fma, const double *vals, const double *x, double *y, const double *ad,
                     int sd_order, int64_t num_rows, int64_t row_begin, int beta, const PushTargets *push,
-                    cudaStream_t stream);
+                    cudaStream_t stream, const int *rowlen = nullptr);
+cudaError_t sg_scatter_estimate(int idx_bits, const void *cols, const EllLayout &lay, double *lines_per_gather,
+                                cudaStream_t stream);
+int64_t sg_bytes_estimate(int idx_bits, const EllLayout &lay);
 void sg_free(SgMatrix *sg);
 int64_t sg_bytes(const SgMatrix *sg);
 int sg_launches(const SgMatrix *sg);

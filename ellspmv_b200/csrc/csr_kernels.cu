@@ -159,18 +159,19 @@ csr_vector_kernel(const CsrSpmvArgs a)
 // non-decreasing, and the range of the stored column indices -- the same checks every ELL
 // upload makes (finish_minmax in api.cu), so that a bad index is EINVAL at upload and never an
 // out-of-bounds gather.  out[0] = max row length, out[1] = rows with rowptr[r+1] < rowptr[r],
-// out[2] = min column, out[3] = max column (as signed values).
+// out[2] = min column, out[3] = max column (as signed values), out[4] = min row length.
 template <typename IdxT>
 __global__ void csr_inspect_kernel(const int64_t *__restrict__ rowptr, const IdxT *__restrict__ cols,
                                    int64_t num_rows, int64_t csrsize, unsigned long long *out)
 {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t t0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    long long best = 0, bad = 0, lo = 0x7fffffffffffffffLL, hi = -0x7fffffffffffffffLL - 1;
+    long long best = 0, least = 0x7fffffffffffffffLL, bad = 0, lo = 0x7fffffffffffffffLL, hi = -0x7fffffffffffffffLL - 1;
     for (int64_t r = t0; r < num_rows; r += stride) {
         const long long n = rowptr[r + 1] - rowptr[r];
         if (n < 0) bad++;
         best = n > best ? n : best;
+        least = n < least ? n : least;
     }
     for (int64_t k = t0; k < csrsize; k += stride) {
         const long long c = (long long)cols[k];
@@ -179,6 +180,7 @@ __global__ void csr_inspect_kernel(const int64_t *__restrict__ rowptr, const Idx
     }
     for (int off = 16; off > 0; off >>= 1) {
         const long long ob = __shfl_xor_sync(0xffffffffu, best, off); best = ob > best ? ob : best;
+        const long long om = __shfl_xor_sync(0xffffffffu, least, off); least = om < least ? om : least;
         bad += __shfl_xor_sync(0xffffffffu, bad, off);
         const long long ol = __shfl_xor_sync(0xffffffffu, lo, off); lo = ol < lo ? ol : lo;
         const long long oh = __shfl_xor_sync(0xffffffffu, hi, off); hi = oh > hi ? oh : hi;
@@ -188,16 +190,17 @@ __global__ void csr_inspect_kernel(const int64_t *__restrict__ rowptr, const Idx
         if (bad) atomicAdd(out + 1, (unsigned long long)bad);
         atomicMin(reinterpret_cast<long long *>(out) + 2, lo);
         atomicMax(reinterpret_cast<long long *>(out) + 3, hi);
+        atomicMin(reinterpret_cast<long long *>(out) + 4, least);
     }
 }
 
-// scratch: 4 x 8 bytes of device memory owned by the handle
+// scratch: 5 x 8 bytes of device memory owned by the handle
 cudaError_t csr_inspect(int idx_bits, const int64_t *rowptr, const void *cols, int64_t num_rows, int64_t csrsize,
                         unsigned long long *scratch, CsrInspection *res, cudaStream_t stream)
 {
-    res->max_row_len = 0; res->bad_rows = 0; res->min_col = 0; res->max_col = -1;
+    res->max_row_len = 0; res->min_row_len = 0; res->bad_rows = 0; res->min_col = 0; res->max_col = -1;
     if (num_rows <= 0) return cudaSuccess;
-    const long long init[4] = {0, 0, 0x7fffffffffffffffLL, -0x7fffffffffffffffLL - 1};
+    const long long init[5] = {0, 0, 0x7fffffffffffffffLL, -0x7fffffffffffffffLL - 1, 0x7fffffffffffffffLL};
     cudaError_t e = cudaMemcpyAsync(scratch, init, sizeof(init), cudaMemcpyHostToDevice, stream);
     const int64_t work = num_rows > csrsize ? num_rows : csrsize;
     int64_t g = (work + 255) / 256;
@@ -209,11 +212,12 @@ cudaError_t csr_inspect(int idx_bits, const int64_t *rowptr, const void *cols, i
             csr_inspect_kernel<int32_t><<<(unsigned)g, 256, 0, stream>>>(rowptr, (const int32_t *)cols, num_rows, csrsize, scratch);
         e = cudaGetLastError();
     }
-    long long h[4] = {0, 0, 0, -1};
+    long long h[5] = {0, 0, 0, -1, 0};
     if (e == cudaSuccess) e = cudaMemcpyAsync(h, scratch, sizeof(h), cudaMemcpyDeviceToHost, stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
     if (e != cudaSuccess) return e;
     res->max_row_len = h[0];
+    res->min_row_len = h[4];
     res->bad_rows = h[1];
     if (csrsize > 0) { res->min_col = h[2]; res->max_col = h[3]; }
     return cudaSuccess;

@@ -146,7 +146,10 @@ template <int R> struct Batch { static constexpr int U = (R == 4) ? 4 : (R == 2 
 // PAT: the handle has offset patterns (pattern.cu).  A warp whose 32*R rows share one
 // offset vector d[] computes col = row + d[l] from the dictionary (a uniform load that
 // lives in L1) and never touches its lines of the index stream.
-template <typename IdxT, int R, int KU, bool FMA, bool YVEC, int G, bool PAT>
+// LEN: rows carry their own length (a.rowlen): slots past it are loaded but never enter the
+// arithmetic.  This is the CSR view (csrgemv has no padded slots, csrspmv.c:1588-1593); only
+// instantiated for R = 1, run-time K, no patterns.
+template <typename IdxT, int R, int KU, bool FMA, bool YVEC, int G, bool PAT, bool LEN = false>
 __global__ void __launch_bounds__(kBlockThreads)
 ell_thread_kernel(const EllSpmvArgs a)
 {
@@ -262,6 +265,12 @@ ell_thread_kernel(const EllSpmvArgs a)
 #pragma unroll
     for (int r = 0; r < R; r++) acc[r] = (ad && a.sd_order) ? dx[r] : 0.0;
 
+    int len = K, kmax = K;
+    if (LEN) {
+        len = a.rowlen[row0];
+        kmax = __reduce_max_sync(__activemask(), len);      // slots past the warp's longest row are not even loaded
+    }
+
     if (KU > 0) {
 #pragma unroll
         for (int l0 = 0; l0 < KU; l0 += U) {
@@ -284,8 +293,9 @@ ell_thread_kernel(const EllSpmvArgs a)
         }
     } else {
         int l0 = 0;
+        const int Kl = LEN ? kmax : K;
 #pragma unroll 1
-        for (; l0 + U <= K; l0 += U) {
+        for (; l0 + U <= Kl; l0 += U) {
             double v[U][R]; int64_t c[U][R]; double xv[U][R];
 #pragma unroll
             for (int u = 0; u < U; u++) {
@@ -300,16 +310,18 @@ ell_thread_kernel(const EllSpmvArgs a)
 #pragma unroll
             for (int u = 0; u < U; u++) {
 #pragma unroll
-                for (int r = 0; r < R; r++) acc[r] = madd<FMA>(acc[r], v[u][r], xv[u][r]);
+                for (int r = 0; r < R; r++)
+                    if (!LEN || l0 + u < len) acc[r] = madd<FMA>(acc[r], v[u][r], xv[u][r]);
             }
         }
 #pragma unroll 1
-        for (; l0 < K; l0++) {
+        for (; l0 < Kl; l0++) {
             double v[R]; int64_t c[R];
             Vals<R>::ld(vp + (int64_t)l0 * S, v);
             load_cols(l0, c);
 #pragma unroll
-            for (int r = 0; r < R; r++) acc[r] = madd<FMA>(acc[r], v[r], ldx<G>(x + c[r]));
+            for (int r = 0; r < R; r++)
+                if (!LEN || l0 < len) acc[r] = madd<FMA>(acc[r], v[r], ldx<G>(x + c[r]));
         }
     }
 
@@ -419,6 +431,12 @@ ell_subwarp_kernel(const EllSpmvArgs a, int slice_rows)
 template <typename IdxT, int R, int KU, bool FMA, int G>
 static cudaError_t launch_thread_g(const EllSpmvArgs &args, bool yvec, cudaLaunchConfig_t &lc)
 {
+    if (args.rowlen) {
+        // per-row lengths (CSR view): one row per thread, run-time K, explicit indices
+        if (R != 1 || KU != 0 || args.patid) return cudaErrorInvalidValue;
+        if (yvec) return cudaLaunchKernelEx(&lc, ell_thread_kernel<IdxT, 1, 0, FMA, true, G, false, true>, args);
+        return cudaLaunchKernelEx(&lc, ell_thread_kernel<IdxT, 1, 0, FMA, false, G, false, true>, args);
+    }
     if (args.patid) {
         if (yvec) return cudaLaunchKernelEx(&lc, ell_thread_kernel<IdxT, R, KU, FMA, true, G, true>, args);
         return cudaLaunchKernelEx(&lc, ell_thread_kernel<IdxT, R, KU, FMA, false, G, true>, args);
@@ -443,6 +461,7 @@ template <typename IdxT, int R, bool FMA>
 static cudaError_t launch_thread_k(const EllSpmvArgs &args, int64_t num_slices, bool yvec,
                                    cudaLaunchConfig_t &lc, int gather)
 {
+    if (args.rowlen) return launch_thread_yvec<IdxT, R, 0, FMA>(args, num_slices, yvec, lc, gather);
     switch (args.rowsize) {
     case 5:  return launch_thread_yvec<IdxT, R, 5, FMA>(args, num_slices, yvec, lc, gather);
     case 27: return launch_thread_yvec<IdxT, R, 27, FMA>(args, num_slices, yvec, lc, gather);

@@ -167,6 +167,61 @@ static cudaError_t sg_build_typed(SgMatrix *sg, const IdxT *cols, cudaStream_t s
     return cudaStreamSynchronize(stream);
 }
 
+// ---- how scattered are the gathers? (pre-filter of KERNEL_AUTO's staged-gather trial) -------
+// For sampled slices, the number of different 128-byte lines of x that the 32 lanes of a warp
+// touch with one gather instruction (32 consecutive rows, same slot), averaged: ~2-3 for a
+// stencil, 32 for a uniformly random matrix.
+template <typename IdxT>
+__global__ void __launch_bounds__(kBlockThreads)
+sg_scatter_kernel(const IdxT *__restrict__ cols, EllLayout lay, int64_t stride, unsigned long long *out)
+{
+    const int64_t s = blockIdx.x * stride;
+    if (s >= lay.num_slices) return;
+    const int S = lay.slice_rows, K = lay.rowsize;
+    const IdxT *c = cols + s * S * (int64_t)K;
+    unsigned long long lines = 0, instr = 0;
+    for (int i = threadIdx.x; i < S * K; i += blockDim.x) {     // S is a multiple of 32: a warp stays inside one slot
+        const long long line = (long long)c[i] >> 4;
+        const unsigned peers = __match_any_sync(0xffffffffu, line);
+        if ((threadIdx.x & 31) == __ffs(peers) - 1) lines++;    // one lane per distinct line
+        if ((threadIdx.x & 31) == 0) instr++;
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        lines += __shfl_xor_sync(0xffffffffu, lines, off);
+        instr += __shfl_xor_sync(0xffffffffu, instr, off);
+    }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(out, lines); atomicAdd(out + 1, instr); }
+}
+
+cudaError_t sg_scatter_estimate(int idx_bits, const void *cols, const EllLayout &lay, double *lines_per_gather,
+                                cudaStream_t stream)
+{
+    *lines_per_gather = 0.0;
+    if (lay.num_slices <= 0 || lay.rowsize <= 0) return cudaSuccess;
+    const int64_t samples = lay.num_slices < 512 ? lay.num_slices : 512;
+    const int64_t stride = lay.num_slices / samples;
+    unsigned long long *d = nullptr, h[2] = {0, 0};
+    cudaError_t e = cudaMalloc(&d, 16);
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(d, 0, 16, stream);
+    if (e == cudaSuccess) {
+        if (idx_bits == 64) sg_scatter_kernel<int64_t><<<(unsigned)samples, kBlockThreads, 0, stream>>>((const int64_t *)cols, lay, stride, d);
+        else sg_scatter_kernel<int32_t><<<(unsigned)samples, kBlockThreads, 0, stream>>>((const int32_t *)cols, lay, stride, d);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h, d, 16, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    cudaFree(d);
+    if (e == cudaSuccess && h[1] > 0) *lines_per_gather = (double)h[0] / (double)h[1];
+    return e;
+}
+
+// device memory the staged copy of a matrix will take (to check against what is free)
+int64_t sg_bytes_estimate(int idx_bits, const EllLayout &lay)
+{
+    return lay.entries() * (int64_t)(idx_bits / 8 + 10) + (64LL << 20);
+}
+
 static cudaError_t sg_prepare_kernels();   // per device: allow the large dynamic shared memory
 
 // *out = nullptr (and success) when staging does not apply: x already fits the
@@ -236,7 +291,7 @@ __global__ void
 sg_sum_kernel(const double *__restrict__ vals, const unsigned short *__restrict__ pos, const long long *__restrict__ seg,
               const double *__restrict__ xg, const double *__restrict__ x, double *__restrict__ y,
               const double *__restrict__ ad, int sd_order, int64_t num_rows, int64_t row_begin, int64_t ns,
-              int nb, int K, int beta, const PushTargets push)
+              int nb, int K, int beta, const PushTargets push, const int *__restrict__ rowlen)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem);
@@ -279,6 +334,8 @@ sg_sum_kernel(const double *__restrict__ vals, const unsigned short *__restrict_
     const double *vp = vals + base;
     const unsigned short *pp = pos + base;
     double yold = 0.0, dx = 0.0;
+    // CSR view: only the first rowlen[row] slots enter the arithmetic (see ell_thread_kernel's LEN)
+    const int len = (rowlen && live) ? rowlen[row] : K;
     if (live && beta) yold = y[row];
     if (live && ad) dx = __dmul_rn(ad[row], __ldg(x + row_begin + row));
 
@@ -312,7 +369,7 @@ sg_sum_kernel(const double *__restrict__ vals, const unsigned short *__restrict_
 #pragma unroll
         for (int u = 0; u < U; u++) {
             const double xv = stage[p[u]];
-            acc = FMA ? __fma_rn(v[u], xv, acc) : __dadd_rn(acc, __dmul_rn(v[u], xv));
+            if (l0 + u < len) acc = FMA ? __fma_rn(v[u], xv, acc) : __dadd_rn(acc, __dmul_rn(v[u], xv));
         }
 #pragma unroll
         for (int u = 0; u < U; u++) { v[u] = vn[u]; p[u] = pn[u]; }
@@ -322,7 +379,7 @@ sg_sum_kernel(const double *__restrict__ vals, const unsigned short *__restrict_
         if (l0 == 0) {
 #pragma unroll
             for (int u = 0; u < U; u++)
-                if (u < K) {
+                if (u < K && u < len) {
                     const double xv = stage[p[u]];
                     acc = FMA ? __fma_rn(v[u], xv, acc) : __dadd_rn(acc, __dmul_rn(v[u], xv));
                 }
@@ -331,7 +388,7 @@ sg_sum_kernel(const double *__restrict__ vals, const unsigned short *__restrict_
             for (; l0 < K; l0++) {
                 const double xv = stage[__ldcs(pp + (int64_t)l0 * S)];
                 const double vv = __ldcs(vp + (int64_t)l0 * S);
-                acc = FMA ? __fma_rn(vv, xv, acc) : __dadd_rn(acc, __dmul_rn(vv, xv));
+                if (l0 < len) acc = FMA ? __fma_rn(vv, xv, acc) : __dadd_rn(acc, __dmul_rn(vv, xv));
             }
         }
     }
@@ -355,7 +412,7 @@ static cudaError_t sg_prepare_kernels()
 
 cudaError_t sg_spmv(const SgMatrix *sg, bool fma, const double *vals, const double *x, double *y, const double *ad,
                     int sd_order, int64_t num_rows, int64_t row_begin, int beta, const PushTargets *push,
-                    cudaStream_t stream)
+                    cudaStream_t stream, const int *rowlen)
 {
     PushTargets pt;
     if (push) pt = *push; else pt.num_peers = 0;
@@ -377,7 +434,7 @@ cudaError_t sg_spmv(const SgMatrix *sg, bool fma, const double *vals, const doub
     auto kernel = fma ? sg_sum_kernel<true> : sg_sum_kernel<false>;
     kernel<<<(unsigned)sg->num_slices, sg->slice_rows, sg->smem, stream>>>(
         vals, sg->pos, sg->seg, sg->xg, x, y, ad, sd_order, num_rows, row_begin, sg->num_slices, sg->num_blocks,
-        sg->rowsize, beta, pt);
+        sg->rowsize, beta, pt, rowlen);
     return cudaGetLastError();
 }
 

@@ -439,9 +439,7 @@ int csr_group_spmv(csrspmv_cuda_matrix *G, double *y, const double *x, int repea
             ELL_CK(cudaMemcpyAsync(S->d_y, y + G->row_lo[p], (size_t)S->num_rows * 8, cudaMemcpyDefault, s));
         ELL_CK(cudaEventRecord(S->events[0], s));
         for (int r = 0; r < repeat; r++) {
-            CsrSpmvArgs args = {S->rowptr, S->cols, S->vals, S->d_x, S->d_y, S->num_rows,
-                                mode == ELLSPMV_CUDA_ACCUMULATE ? 1 : 0, S->d_ad, S->row_begin};
-            ELL_CK(launch_csr_spmv(S->idx_bits, S->fma, S->kernel, args, s));
+            if ((err = csr_launch(S, S->d_y, S->d_x, mode == ELLSPMV_CUDA_ACCUMULATE ? 1 : 0, s))) return err;
             ELL_CK(cudaEventRecord(S->events[(size_t)r + 1], s));
         }
         if (S->num_rows > 0)

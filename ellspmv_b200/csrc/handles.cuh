@@ -34,7 +34,11 @@ struct ellspmv_cuda_matrix {
     double *d_ad = nullptr;                  // separately stored diagonal (shard rows), optional
     int sd_order = 0;
     ellspmv::PatternSet pat;                 // offset patterns of the index stream (pattern.cu), optional
-    ellspmv::SgMatrix *sg = nullptr;         // staged-gather copy (ELLSPMV_CUDA_STAGED_GATHER), optional
+    ellspmv::SgMatrix *sg = nullptr;         // staged-gather copy (ELLSPMV_CUDA_STAGED_GATHER or KERNEL_AUTO's choice), optional
+    int *d_rowlen = nullptr;                 // per-row lengths (CSR view built by csrspmv_cuda_*), optional
+    int staged_mode = 0;                     // 0 direct gather, 1 staged on request, 2 staged chosen by the timed trial
+    double tune_ms[2] = {0.0, 0.0};          // KERNEL_AUTO's trial at upload: direct, staged
+    bool kernel_auto = false;                // the caller left the kernel choice to the library
     ellspmv::CbMatrix *cb = nullptr;         // column-blocked copy (ELLSPMV_CUDA_COLUMN_BLOCKED), optional
     int64_t min_col = 0, max_col = -1;
     unsigned char *d_remote = nullptr;       // per slice: reads columns outside the shard's rows (fused step sync)
@@ -73,6 +77,9 @@ struct csrspmv_cuda_matrix {
     double *d_x = nullptr, *d_y = nullptr;
     double *d_ad = nullptr;                  // separately stored diagonal, optional
     unsigned long long *d_scratch = nullptr; // 32 bytes for the upload-time inspection (csr_inspect)
+    ellspmv_cuda_matrix *ell = nullptr;      // sliced-ELL view of the same entries (KERNEL_AUTO, balanced rows): the
+                                             //   launches go through the ELL kernels with per-row lengths
+    int64_t min_row_len = 0;
     int64_t min_col = 0, max_col = -1;       // range of the stored column indices
     std::vector<cudaEvent_t> events;
     int64_t device_bytes = 0;
@@ -109,5 +116,6 @@ int launch_shard_exchange(ellspmv_cuda_matrix *A, double *y_dev, const double *x
                           const PushTargets *push, StepSync sync, cudaStream_t stream);
 int ensure_event_count(std::vector<cudaEvent_t> &ev, size_t n);
 void shard_x_range(const ellspmv_cuda_matrix *A, int64_t *lo, int64_t *hi);   // the part of x a shard's kernels read
+int csr_launch(csrspmv_cuda_matrix *A, double *y_dev, const double *x_dev, int beta, cudaStream_t stream);
 void csr_x_range(const csrspmv_cuda_matrix *A, int64_t *lo, int64_t *hi);
 }  // namespace ellspmv

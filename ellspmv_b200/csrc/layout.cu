@@ -320,4 +320,64 @@ cudaError_t mark_remote_slices(int idx_bits, const void *cols, const EllLayout &
     return cudaGetLastError();
 }
 
+// ---- CSR rows -> sliced ELL (the ELL view of a balanced CSR matrix, api.cu) --------------------
+// One CTA per slice: its rows' entries are one contiguous run of the CSR arrays, read coalesced;
+// each entry finds its row by bisection in the slice's row pointers (shared memory).
+template <typename SrcI, typename DstI>
+__global__ void __launch_bounds__(kBlockThreads)
+csr_to_sliced_kernel(const int64_t *__restrict__ rowptr, const SrcI *__restrict__ src_cols,
+                     const double *__restrict__ src_vals, DstI *__restrict__ dst_cols,
+                     double *__restrict__ dst_vals, int *__restrict__ rowlen, EllLayout lay)
+{
+    extern __shared__ long long s_rp[];              // slice_rows + 1 row pointers
+    const int S = lay.slice_rows, K = lay.rowsize;
+    const int64_t s = blockIdx.x;
+    const int64_t r0 = s * S;
+    const int nr = (int)((r0 + S <= lay.num_rows) ? S : lay.num_rows - r0);
+    for (int i = threadIdx.x; i <= nr; i += blockDim.x) s_rp[i] = rowptr[r0 + i];
+    __syncthreads();
+    const int64_t kb = s_rp[0], ke = s_rp[nr];
+    const int64_t base = s * S * (int64_t)K;
+    for (int64_t k = kb + threadIdx.x; k < ke; k += blockDim.x) {
+        int lo = 0, hi = nr;                          // last row with s_rp[row] <= k
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (s_rp[mid] <= k) lo = mid; else hi = mid;
+        }
+        const int l = (int)(k - s_rp[lo]);
+        const int64_t d = base + (int64_t)l * S + lo;
+        dst_cols[d] = (DstI)src_cols[k];
+        dst_vals[d] = src_vals[k];
+    }
+    for (int r = threadIdx.x; r < nr; r += blockDim.x) {
+        const int len = (int)(s_rp[r + 1] - s_rp[r]);
+        if (rowlen) rowlen[r0 + r] = len;
+        const DstI pad = len > 0 ? (DstI)src_cols[s_rp[r + 1] - 1] : (DstI)0;
+        for (int l = len; l < K; l++) {
+            const int64_t d = base + (int64_t)l * S + r;
+            dst_cols[d] = pad;
+            dst_vals[d] = 0.0;
+        }
+    }
+}
+
+cudaError_t csr_to_sliced(int src_idx_bits, int dst_idx_bits, const int64_t *rowptr, const void *src_cols,
+                          const double *src_vals, void *dst_cols, double *dst_vals, int *rowlen,
+                          const EllLayout &lay, cudaStream_t stream)
+{
+    if (lay.num_slices <= 0) return cudaSuccess;
+    if (lay.num_slices > 0x7fffffffLL) return cudaErrorInvalidValue;
+    const unsigned g = (unsigned)lay.num_slices;
+    const size_t smem = (size_t)(lay.slice_rows + 1) * 8;
+    if (src_idx_bits == 32 && dst_idx_bits == 32)
+        csr_to_sliced_kernel<int32_t, int32_t><<<g, kBlockThreads, smem, stream>>>(rowptr, (const int32_t *)src_cols, src_vals, (int32_t *)dst_cols, dst_vals, rowlen, lay);
+    else if (src_idx_bits == 64 && dst_idx_bits == 64)
+        csr_to_sliced_kernel<int64_t, int64_t><<<g, kBlockThreads, smem, stream>>>(rowptr, (const int64_t *)src_cols, src_vals, (int64_t *)dst_cols, dst_vals, rowlen, lay);
+    else if (src_idx_bits == 64 && dst_idx_bits == 32)
+        csr_to_sliced_kernel<int64_t, int32_t><<<g, kBlockThreads, smem, stream>>>(rowptr, (const int64_t *)src_cols, src_vals, (int32_t *)dst_cols, dst_vals, rowlen, lay);
+    else
+        return cudaErrorInvalidValue;
+    return cudaGetLastError();
+}
+
 }  // namespace ellspmv

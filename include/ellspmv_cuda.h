@@ -50,9 +50,15 @@ enum {
                                     /*   bit-exact with the reference loop      */
     ELLSPMV_CUDA_KERNEL_WARP   = 2, /* sub-warp-per-row + shuffle reduction:    */
                                     /*   tolerance mode (summation order differs)*/
-    CSRSPMV_CUDA_KERNEL_SCALAR = 3, /* CSR only: thread-per-row, bit-exact; AUTO picks it  */
-                                    /*   for balanced rows, the smem-staged stream kernel  */
-                                    /*   (KERNEL_THREAD) for ragged ones                   */
+    CSRSPMV_CUDA_KERNEL_SCALAR = 3, /* CSR only: thread-per-row, bit-exact.  CSR AUTO:     */
+                                    /*   balanced rows (padding <= 25 %) run through a     */
+                                    /*   sliced-ELL view with per-row lengths (the ELL     */
+                                    /*   kernels, same bits as csrgemv); otherwise scalar  */
+                                    /*   or the smem-staged stream kernel (KERNEL_THREAD)  */
+                                    /*   by row raggedness.  With ELLSPMV_CUDA_FMA the     */
+                                    /*   stream kernel cannot contract (it parks rounded   */
+                                    /*   products): AUTO then never picks it, so the bits  */
+                                    /*   do not depend on the row lengths                  */
     ELLSPMV_CUDA_KERNEL_MASK   = 0xf,
     /* arithmetic: default is mul-then-add (__dmul_rn/__dadd_rn), the bits the
      * reference's compiled loop produces; FMA allows contraction (tolerance) */
@@ -94,6 +100,13 @@ enum {
      * unchanged; only the index bytes of patterned rows are no longer read.
      * NO_PATTERN keeps every group on the explicit index stream. */
     ELLSPMV_CUDA_NO_PATTERN     = 1 << 18,
+    /* KERNEL_AUTO builds the staged gather by itself for matrices whose x is
+     * larger than L2, whose rows follow no offset pattern and whose gathers are
+     * scattered (a warp's 32 columns fall into more than 16 different 128-byte
+     * lines on average), times both paths once at upload and keeps the faster
+     * one -- the results are the same bits either way.  NO_STAGED_GATHER keeps
+     * the direct gather without a trial. */
+    ELLSPMV_CUDA_NO_STAGED_GATHER = 1 << 19,
     /* rows handled per thread in the thread-per-row kernel (1, 2 or 4):
      * 0 = auto = 2 for rows of at most 12 entries, else 1 */
     ELLSPMV_CUDA_ROWS_PER_THREAD_SHIFT = 8,
@@ -139,6 +152,14 @@ typedef struct ellspmv_cuda_info {
     int     num_gpus;        /* GPUs behind this handle (row shards)        */
     int64_t pattern_rows;    /* rows whose column indices come from an      */
                              /*   offset pattern instead of the index stream */
+    int     staged;          /* 1: the staged gather (column blocks) is in use; */
+                             /*   2: chosen by KERNEL_AUTO from a timed trial  */
+    int     launches_per_spmv; /* kernel launches one spmv_device call issues  */
+    double  tune_ms[2];      /* AUTO's timed trial at upload: direct gather,  */
+                             /*   staged gather (0 = not tried)               */
+    int64_t exception_entries; /* entries patched after the pattern lookup    */
+    int64_t long_rows;       /* 0, or the row length from which the long-row  */
+                             /*   kernel is used (KERNEL_AUTO)                */
 } ellspmv_cuda_info;
 
 /* ---- ELL ------------------------------------------------------------- */
@@ -316,6 +337,22 @@ int csrspmv_cuda_spmv(
 int csrspmv_cuda_spmv_device(
     csrspmv_cuda_matrix *A, double *y_dev, const double *x_dev,
     int mode, void *stream);
+
+typedef struct csrspmv_cuda_info {
+    int64_t num_rows, num_columns, csrsize;
+    int64_t min_row_len, max_row_len;
+    int64_t min_col, max_col;
+    int64_t device_bytes;
+    int     kernel;            /* native kernel in use: 1 stream, 2 vector, 3 scalar, 5 adaptive */
+    int     ell_view;          /* 0: native CSR kernels; 1: sliced-ELL view with per-row        */
+                               /*   lengths; 2: view of rows of one length (no length array)    */
+    int     ell_staged;        /* the view runs the staged gather (see ellspmv_cuda_info)       */
+    int     launches_per_spmv;
+    int64_t ell_pattern_rows;  /* rows of the view on an offset pattern                         */
+    int     num_gpus;
+    int     fma;
+} csrspmv_cuda_info;
+int csrspmv_cuda_get_info(const csrspmv_cuda_matrix *A, csrspmv_cuda_info *info);
 
 int64_t csrspmv_cuda_device_bytes(const csrspmv_cuda_matrix *A);
 void csrspmv_cuda_free(csrspmv_cuda_matrix *A);

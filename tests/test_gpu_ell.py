@@ -441,6 +441,38 @@ def test_staged_gather_is_bit_exact(lib, oracle, shape, bits, monkeypatch):
             A.free()
 
 
+def test_auto_tries_the_staged_gather_on_scattered_matrices(lib, oracle, monkeypatch):
+    """KERNEL_AUTO: x larger than the threshold + no offset patterns + scattered gathers -> the staged
+    copy is built and timed against the direct gather at upload; whichever is kept, the bits are the
+    oracle's.  A banded matrix (gathers share lines) and NO_STAGED_GATHER skip the trial."""
+    monkeypatch.setenv("ELLSPMV_CUDA_AUTO_STAGED_MIN_X_BYTES", "4096")
+    monkeypatch.setenv("ELLSPMV_CUDA_BLOCK_BYTES", "65536")
+    rng = np.random.default_rng(21)
+    nr, nc, K = 6000, 70000, 32
+    ec, ea = rand_ell(rng, nr, nc, K, np.int32, pad_frac=0.0)
+    x = rng.standard_normal(nc)
+    want = np.zeros(nr)
+    oracle.ellgemv(nr, want, x, K, ec, ea)
+    A = E.EllMatrix.upload(nr, nc, K, ec, ea)
+    i = A.info()
+    assert i.tune_ms[0] > 0 and i.tune_ms[1] > 0 and i.staged in (0, 2)
+    assert i.launches_per_spmv == (1 if i.staged == 0 else 10)     # 70000 * 8 B / 64 KB -> 9 column blocks + the sum
+    y = np.zeros(nr)
+    A.spmv(y, x, 1, E.ACCUMULATE)
+    A.free()
+    assert bits_equal(y, want)
+    B = E.EllMatrix.upload(nr, nc, K, ec, ea, E.NO_STAGED_GATHER)
+    assert B.info().tune_ms[0] == 0 and B.info().staged == 0
+    B.free()
+    bc, ba = banded_ell(nr, nr, [-3, -1, 0, 1, 2], np.int32, rng)
+    Cm = E.EllMatrix.upload(nr, nr, 5, bc, ba, E.NO_PATTERN)
+    assert Cm.info().tune_ms[0] == 0 and Cm.info().staged == 0
+    Cm.free()
+    D = E.EllMatrix.upload(nr, nc, K, ec, ea, E.STAGED_GATHER)
+    assert D.info().staged == 1
+    D.free()
+
+
 def test_staged_gather_tolerance_and_special_values(lib, oracle, monkeypatch):
     """FMA on the staged path stays inside the dot-product bound; inf/NaN in x
     propagate exactly like in the reference loop (no stored zero is dropped)."""
