@@ -21,10 +21,12 @@ from typing import Optional, Sequence
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libellspmv_cuda.so")
+# ELLSPMV_B200_LIB: another build of the same ABI (A/B timing of two builds on one box); never a fallback
+LIB_PATH = os.environ.get("ELLSPMV_B200_LIB") or os.path.join(_HERE, "lib", "libellspmv_cuda.so")
 
 # ---- constants (include/ellspmv_cuda.h) -----------------------------------
 KERNEL_AUTO, KERNEL_THREAD, KERNEL_WARP = 0, 1, 2
+KERNEL_LONGROW = 4      # ELL: few, long rows (CTA per row group, bit-exact); AUTO picks it by shape
 KERNEL_CSR_SCALAR = 3   # CSR only: thread-per-row, bit-exact, for balanced rows (auto picks it)
 FMA = 1 << 4
 L2_PERSIST_X = 1 << 5
@@ -33,6 +35,8 @@ COLUMN_BLOCKED = 1 << 7
 STAGED_GATHER = 1 << 17
 NO_PATTERN = 1 << 18
 NO_STAGED_GATHER = 1 << 19
+SKIP_PADDING = 1 << 20
+KERNEL_CSR_SELL = 5     # CSR: SELL-128-sigma (AUTO takes it for unbalanced rows)
 WIDE_INDEX = 1 << 16
 ROWS_PER_THREAD_SHIFT = 8
 VARIANT_SHIFT = 12
@@ -64,7 +68,7 @@ class Info(C.Structure):
         ("device_bytes", C.c_int64), ("min_col", C.c_int64), ("max_col", C.c_int64),
         ("launches", C.c_int64), ("num_gpus", C.c_int), ("pattern_rows", C.c_int64),
         ("staged", C.c_int), ("launches_per_spmv", C.c_int), ("tune_ms", C.c_double * 2),
-        ("exception_entries", C.c_int64), ("long_rows", C.c_int64),
+        ("exception_entries", C.c_int64), ("long_rows", C.c_int64), ("sell_slots", C.c_int64),
     ]
 
 
@@ -72,7 +76,8 @@ class CsrInfo(C.Structure):
     _fields_ = [
         ("num_rows", C.c_int64), ("num_columns", C.c_int64), ("csrsize", C.c_int64),
         ("min_row_len", C.c_int64), ("max_row_len", C.c_int64), ("min_col", C.c_int64), ("max_col", C.c_int64),
-        ("device_bytes", C.c_int64), ("kernel", C.c_int), ("ell_view", C.c_int), ("ell_staged", C.c_int),
+        ("device_bytes", C.c_int64), ("kernel", C.c_int), ("sell_slots", C.c_int64), ("sell_real", C.c_int64),
+        ("sell_long_rows", C.c_int64), ("ell_view", C.c_int), ("ell_staged", C.c_int),
         ("launches_per_spmv", C.c_int), ("ell_pattern_rows", C.c_int64), ("num_gpus", C.c_int), ("fma", C.c_int),
     ]
 
@@ -383,7 +388,8 @@ class CsrMatrix:
             path = ("staged gather (column blocks), then thread-per-row" if i.ell_staged else "thread-per-row")
             return f"sliced-ELL view of the CSR rows ({how}, width {i.max_row_len}): {path}, {arith}"
         name = {1: "smem-staged stream kernel", 2: "sub-warp per row + shuffle tree (tolerance)",
-                3: "scalar thread-per-row", 5: "adaptive row blocks (short rows streamed, long rows cooperatively)"}
+                3: "scalar thread-per-row",
+                5: f"SELL-128-sigma (rows sorted by length in windows of 4096, width per slice; {i.sell_long_rows} long rows one CTA each)"}
         return f"native CSR: {name.get(i.kernel, str(i.kernel))}, {arith}"
 
     def free(self) -> None:

@@ -76,13 +76,26 @@ int configure(ellspmv_cuda_matrix *A, unsigned flags)
     if (R != 1 && R != 2 && R != 4) ELL_FAIL(EINVAL, "rows per thread must be 1, 2 or 4 (got %d)", R);
     int kernel = flags & ELLSPMV_CUDA_KERNEL_MASK;
     A->kernel_auto = kernel == ELLSPMV_CUDA_KERNEL_AUTO;
-    if (kernel == ELLSPMV_CUDA_KERNEL_AUTO) kernel = ELLSPMV_CUDA_KERNEL_THREAD;
-    if (kernel != ELLSPMV_CUDA_KERNEL_THREAD && kernel != ELLSPMV_CUDA_KERNEL_WARP)
+    if (kernel == ELLSPMV_CUDA_KERNEL_AUTO) {
+        // the nnz-per-row switch: thread-per-row keeps rows * 8 loads in flight, which feeds HBM from
+        // ~10^5 rows on at any K (the sliced layout is coalesced at any K); with fewer rows the only
+        // parallelism left is inside the rows, and from 64 entries per row on a CTA per row group
+        // (ell_longrow.cu) wins -- measured crossover in profiles/r2_k_sweep.md
+        long long max_rows = 32768, min_k = 64;
+        if (const char *env = getenv("ELLSPMV_CUDA_LONGROW_MAX_ROWS")) max_rows = atoll(env);
+        if (const char *env = getenv("ELLSPMV_CUDA_LONGROW_MIN_K")) min_k = atoll(env);
+        const bool lr = A->lay.rowsize >= min_k && A->lay.num_rows <= max_rows &&
+                        !(flags & (ELLSPMV_CUDA_STAGED_GATHER | ELLSPMV_CUDA_COLUMN_BLOCKED | ELLSPMV_CUDA_VARIANT_MASK |
+                                   ELLSPMV_CUDA_ROWS_PER_THREAD_MASK));
+        kernel = lr ? kKernelLongRow : ELLSPMV_CUDA_KERNEL_THREAD;
+    }
+    if (kernel != ELLSPMV_CUDA_KERNEL_THREAD && kernel != ELLSPMV_CUDA_KERNEL_WARP && kernel != kKernelLongRow)
         ELL_FAIL(EINVAL, "unknown kernel selector %d", kernel);
+    if (kernel == kKernelLongRow) R = 1;
     A->dev_idx_bits = A->host_idx_bits;
     if (A->host_idx_bits == 64 && !(flags & ELLSPMV_CUDA_WIDE_INDEX) && A->num_columns < (1LL << 31))
         A->dev_idx_bits = 32;     // index narrowing: a pure device-layout choice (bit-exact results)
-    A->lay.slice_rows = kBlockThreads * R;
+    A->lay.slice_rows = kernel == kKernelLongRow ? 1 : kBlockThreads * R;    // long rows: the reference's row-major layout
     A->lay.num_slices = (A->lay.num_rows + A->lay.slice_rows - 1) / A->lay.slice_rows;
     cudaDeviceProp prop;
     ELL_CK(cudaGetDeviceProperties(&prop, A->device));
@@ -134,6 +147,7 @@ void warm_kernels(ellspmv_cuda_matrix *A)
     args.rowsize = A->lay.rowsize;
     args.beta = 1;
     args.patid = A->pat.patid;
+    args.patmask = A->pat.patmask;
     args.pat = A->pat.pat;
     if (launch_ell_spmv(A->cfg, args, 1, A->stream) == cudaSuccess) cudaStreamSynchronize(A->stream);
     cudaGetLastError();
@@ -246,7 +260,16 @@ int auto_staged_gather(ellspmv_cuda_matrix *A, long long block_bytes)
 
 int build_column_blocks(ellspmv_cuda_matrix *A)
 {
-    if (A->lay.num_rows <= 0 || A->lay.rowsize <= 0) return 0;
+    if (A->lay.num_rows <= 0 || A->lay.rowsize <= 0 || A->cfg.kernel == kKernelLongRow) return 0;
+    if (A->flags & ELLSPMV_CUDA_SKIP_PADDING) {
+        // SELL-128-sigma copy without the rows' trailing padding (sell.cu); the regular layout stays
+        // (download, push, diagonal order 1 and the chunked host call use it)
+        cudaError_t ce = sell_build_ell(&A->sell, A->dev_idx_bits, A->cols, A->vals, A->lay, A->row_begin, A->num_columns,
+                                        A->stream);
+        if (ce != cudaSuccess) { set_last_error("skip padding: %s", cudaGetErrorString(ce)); return cuda_to_errno(ce); }
+        A->device_bytes += sell_bytes(A->sell);
+        return 0;
+    }
     if (!(A->flags & (ELLSPMV_CUDA_COLUMN_BLOCKED | ELLSPMV_CUDA_STAGED_GATHER))) {
         long long target = 48LL << 20;
         if (const char *env = getenv("ELLSPMV_CUDA_BLOCK_BYTES")) {
@@ -348,6 +371,7 @@ int launch(ellspmv_cuda_matrix *A, double *y_dev, const double *x_dev, int beta,
     args.ad = A->d_ad;
     args.sd_order = A->sd_order;
     args.patid = A->pat.patid;
+    args.patmask = A->pat.patmask;
     args.pat = A->pat.pat;
     args.rowlen = A->d_rowlen;
     // value-stream L2 prefetch 128 slices ahead when most rows are patterned (ell_kernels.cu)
@@ -361,6 +385,11 @@ int launch(ellspmv_cuda_matrix *A, double *y_dev, const double *x_dev, int beta,
         ELL_CK(sg_spmv(A->sg, A->cfg.fma, A->vals, x_dev, y_dev, A->d_ad, A->sd_order, A->lay.num_rows,
                        A->row_begin, beta, push, stream, A->d_rowlen));
         A->launches += sg_launches(A->sg);
+        return 0;
+    }
+    if (A->sell && !push && !sync && !(A->d_ad && A->sd_order) && slice_begin == 0 && num_slices == A->lay.num_slices) {
+        ELL_CK(sell_spmv(A->sell, A->cfg.fma, nullptr, nullptr, nullptr, 0, x_dev, y_dev, A->d_ad, A->row_begin, beta, stream));
+        A->launches += sell_launches(A->sell);
         return 0;
     }
     if (A->cb && !push && !A->d_ad && slice_begin == 0 && num_slices == A->lay.num_slices) {
@@ -467,6 +496,11 @@ namespace ellspmv {
 int csr_launch(csrspmv_cuda_matrix *A, double *y_dev, const double *x_dev, int beta, cudaStream_t stream)
 {
     if (A->ell) return launch(A->ell, y_dev, x_dev, beta, nullptr, stream, 0, -1, nullptr);
+    if (A->sell) {
+        ELL_CK(sell_spmv(A->sell, A->fma, A->rowptr, A->cols, A->vals, A->idx_bits, x_dev, y_dev, A->d_ad, A->row_begin,
+                         beta, stream));
+        return 0;
+    }
     CsrSpmvArgs args = {A->rowptr, A->cols, A->vals, x_dev, y_dev, A->num_rows, beta, A->d_ad, A->row_begin};
     ELL_CK(launch_csr_spmv(A->idx_bits, A->fma, A->kernel, args, stream));
     return 0;
@@ -556,6 +590,7 @@ void ellspmv_cuda_free(ellspmv_cuda_matrix *A)
     pattern_free(&A->pat);
     if (A->cb) cb_free(A->cb);
     if (A->sg) sg_free(A->sg);
+    if (A->sell) sell_free(A->sell);
     if (A->d_x) cudaFree(A->d_x);
     if (A->d_y) cudaFree(A->d_y);
     if (A->stream) cudaStreamDestroy(A->stream);
@@ -826,11 +861,14 @@ int ellspmv_cuda_get_info(const ellspmv_cuda_matrix *A, ellspmv_cuda_info *info)
     info->max_col = A->max_col;
     info->launches = A->launches;
     info->num_gpus = 1;
-    info->pattern_rows = A->pat.covered * A->pat.group_rows;
+    info->pattern_rows = A->pat.covered * A->pat.group_rows - A->pat.explicit_lanes * A->cfg.rows_per_thread;
+    info->exception_entries = A->pat.explicit_lanes * A->cfg.rows_per_thread * A->lay.rowsize;
     info->staged = A->sg ? A->staged_mode : 0;
-    info->launches_per_spmv = A->sg ? sg_launches(A->sg) : (A->cb ? cb_blocks(A->cb) : 1);
+    info->launches_per_spmv = A->sg ? sg_launches(A->sg) : (A->cb ? cb_blocks(A->cb) : (A->sell ? sell_launches(A->sell) : 1));
+    info->sell_slots = A->sell ? sell_entries(A->sell) : 0;
     info->tune_ms[0] = A->tune_ms[0];
     info->tune_ms[1] = A->tune_ms[1];
+    info->long_rows = A->cfg.kernel == kKernelLongRow ? A->lay.rowsize : 0;
     return 0;
 }
 
@@ -933,7 +971,8 @@ int ellspmv_cuda_spmv(
     DeviceGuard g(A->device);
     int err = ensure_vectors(A);
     if (err) return err;
-    if (repeat == 1 && mode != ELLSPMV_CUDA_ITERATE && rows >= (1 << 20) && A->lay.rowsize > 0 && ncols > 0 && !A->cb && !A->sg)
+    if (repeat == 1 && mode != ELLSPMV_CUDA_ITERATE && rows >= (1 << 20) && A->lay.rowsize > 0 && ncols > 0 && !A->cb && !A->sg && !A->sell &&
+        A->cfg.kernel != kKernelLongRow)
         return spmv_pipelined(A, y, x, mode == ELLSPMV_CUDA_ACCUMULATE ? 1 : 0, seconds);
     if ((err = ensure_events(A->events, (size_t)repeat + 1))) return err;
     cudaStream_t s = A->stream;
@@ -980,6 +1019,7 @@ void csrspmv_cuda_free(csrspmv_cuda_matrix *A)
     if (A->d_ad) cudaFree(A->d_ad);
     if (A->d_scratch) cudaFree(A->d_scratch);
     if (A->ell) ellspmv_cuda_free(A->ell);
+    if (A->sell) sell_free(A->sell);
     if (A->cols) cudaFree(A->cols);
     if (A->vals) cudaFree(A->vals);
     if (A->d_x) cudaFree(A->d_x);
@@ -1010,7 +1050,8 @@ static int csr_new(csrspmv_cuda_matrix **out, int idx_width_bits, int64_t num_ro
     // 0 = auto: bit-exact, scalar for balanced rows / stream for ragged ones (csr_pick_kernel);
     // 1 = stream, 2 = vector (tolerance), 3 = scalar
     A->auto_kernel = kernel == ELLSPMV_CUDA_KERNEL_AUTO;
-    A->kernel = kernel == ELLSPMV_CUDA_KERNEL_WARP ? ELLSPMV_CUDA_KERNEL_WARP : (kernel == 3 ? 3 : ELLSPMV_CUDA_KERNEL_THREAD);
+    A->kernel = kernel == ELLSPMV_CUDA_KERNEL_WARP ? ELLSPMV_CUDA_KERNEL_WARP
+              : (kernel == 3 ? 3 : (kernel == 5 ? 5 : ELLSPMV_CUDA_KERNEL_THREAD));      // 5: SELL-128-sigma (sell.cu)
     *out = A;
     DeviceGuard g(device);
     auto fail = [&](cudaError_t ce) {
@@ -1037,11 +1078,13 @@ static int csr_new(csrspmv_cuda_matrix **out, int idx_width_bits, int64_t num_ro
 // a slot past a row's end is never touched arithmetically, so the result is csrgemv's
 // (csrspmv.c:1588-1593) bit for bit, non-finite x included.  Rows of one length need no
 // length array at all (the random matrix of BASELINE config 4, every row K entries).
-// Skipped when the padding would exceed 25 % of the entries, a row is longer than 1024, or
+// Skipped when the padding would exceed 25 % of the entries, a row is longer than 1024 (unless
+// the matrix has at most 32768 rows: the long-row kernel then runs the view), or
 // memory is short; the CSR arrays stay on the device either way (download, fallback).
 static int csr_build_ell_view(csrspmv_cuda_matrix *A)
 {
-    if (A->num_rows <= 0 || A->csrsize <= 0 || A->max_row_len <= 0 || A->max_row_len > 1024) return 0;
+    if (A->num_rows <= 0 || A->csrsize <= 0 || A->max_row_len <= 0) return 0;
+    if (A->max_row_len > (A->num_rows <= 32768 ? (1 << 24) : 1024)) return 0;    // long rows only with few of them (long-row kernel)
     if (getenv("CSRSPMV_CUDA_NO_ELL_VIEW")) return 0;
     const int64_t K = A->max_row_len;
     const int64_t padded = A->num_rows * K;
@@ -1052,13 +1095,20 @@ static int csr_build_ell_view(csrspmv_cuda_matrix *A)
     if ((int64_t)free_b < padded * (8 + A->idx_bits / 8) + A->num_rows * 4 + (1LL << 30)) return 0;
     unsigned flags = A->flags & (ELLSPMV_CUDA_FMA | ELLSPMV_CUDA_WIDE_INDEX | ELLSPMV_CUDA_NO_PATTERN |
                                  ELLSPMV_CUDA_NO_STAGED_GATHER | ELLSPMV_CUDA_STAGED_GATHER | ELLSPMV_CUDA_L2_PERSIST_X);
-    if (!uniform) flags |= (1u << ELLSPMV_CUDA_ROWS_PER_THREAD_SHIFT) | ELLSPMV_CUDA_NO_PATTERN;   // the length-aware kernel: R = 1, explicit indices
+    // kernel of the view: the same nnz-per-row switch as an ELL upload (configure); both kernels
+    // honour the row lengths, the thread-per-row one in its R = 1 / explicit-index form
+    if (K >= 64 && A->num_rows <= 32768 && !(flags & ELLSPMV_CUDA_STAGED_GATHER)) flags |= kKernelLongRow;
+    else {
+        flags |= ELLSPMV_CUDA_KERNEL_THREAD;
+        if (!uniform) flags |= (1u << ELLSPMV_CUDA_ROWS_PER_THREAD_SHIFT) | ELLSPMV_CUDA_NO_PATTERN;
+    }
     ellspmv_cuda_matrix *V = nullptr;
     int err = new_handle(&V, A->idx_bits, A->row_begin + A->num_rows, A->num_columns, K, A->row_begin,
                          A->row_begin + A->num_rows, A->device, flags);
     if (err) return err;
     auto fail = [&](int e) { ellspmv_cuda_free(V); return e; };
     if ((err = configure(V, flags))) return fail(err);
+    V->kernel_auto = true;                         // the view may still try the staged gather (build_column_blocks)
     if ((err = alloc_matrix(V))) {
         if (err == ENOMEM) { ellspmv_cuda_free(V); cudaGetLastError(); return 0; }
         return fail(err);
@@ -1082,6 +1132,30 @@ static int csr_build_ell_view(csrspmv_cuda_matrix *A)
     return 0;
 }
 
+// KERNEL_AUTO on a CSR matrix whose rows are NOT balanced (the view above would be mostly padding):
+// SELL-128-sigma (sell.cu) -- rows sorted by length inside windows of 4096, a width per slice,
+// thread per row in entry order, rows beyond 4096 entries one CTA each.  Bit-exact like every
+// default path; the entry-balancing of the reference's csrgemvnz (csrspmv.c:1698-1740) is done
+// here by the layout instead of by atomics.  Falls back to the native kernels when memory is short.
+static int csr_build_sell(csrspmv_cuda_matrix *A)
+{
+    if (A->num_rows <= 0 || A->csrsize <= 0) { if (A->kernel == 5) A->kernel = 3; return 0; }
+    if (getenv("CSRSPMV_CUDA_NO_SELL") && A->auto_kernel) return 0;
+    size_t free_b = 0, total_b = 0;
+    ELL_CK(cudaMemGetInfo(&free_b, &total_b));
+    const int dev_bits = (A->idx_bits == 64 && !(A->flags & ELLSPMV_CUDA_WIDE_INDEX) && A->num_columns < (1LL << 31)) ? 32 : A->idx_bits;
+    const int64_t need = (A->csrsize + A->csrsize / 2) * (8 + dev_bits / 8) + A->num_rows * 16 + (1LL << 30);
+    if ((int64_t)free_b < need) { if (A->kernel == 5) A->kernel = 3; return 0; }
+    cudaError_t ce = sell_build_csr(&A->sell, A->idx_bits, dev_bits, A->num_rows, A->rowptr, A->cols, A->vals, A->stream);
+    if (ce == cudaErrorMemoryAllocation) { cudaGetLastError(); A->sell = nullptr; if (A->kernel == 5) A->kernel = 3; return 0; }
+    if (ce != cudaSuccess) { set_last_error("csr -> sell: %s", cudaGetErrorString(ce)); return cuda_to_errno(ce); }
+    if (A->sell) {
+        A->kernel = 5;
+        A->device_bytes += sell_bytes(A->sell);
+    }
+    return 0;
+}
+
 // bit-exact CSR kernels: thread-per-row (scalar) wins when the rows are balanced
 // (37 vs 48 ms on BASELINE config 4), the smem-staged stream kernel when they are ragged
 static int csr_pick_kernel(csrspmv_cuda_matrix *A)
@@ -1099,14 +1173,16 @@ static int csr_pick_kernel(csrspmv_cuda_matrix *A)
     A->min_row_len = in.min_row_len;
     A->min_col = in.min_col;
     A->max_col = in.max_col;
-    if (!A->auto_kernel) return 0;
+    if (!A->auto_kernel) return A->kernel == 5 ? csr_build_sell(A) : 0;
     const int64_t avg = A->num_rows > 0 ? (A->csrsize + A->num_rows - 1) / A->num_rows : 0;
     A->kernel = (A->max_row_len <= 4 * avg + 16) ? 3 : ELLSPMV_CUDA_KERNEL_THREAD;
     // ELLSPMV_CUDA_FMA: the stream kernel parks ROUNDED products and cannot contract; so that the
     // bits under FMA do not depend on the row-length distribution (or differ between the shards of
     // a group), AUTO then always takes a sequential-fma kernel: the ELL view or the scalar kernel
     if (A->fma) A->kernel = 3;
-    return csr_build_ell_view(A);
+    int err = csr_build_ell_view(A);
+    if (err || A->ell) return err;
+    return csr_build_sell(A);
 }
 
 int csrspmv_cuda_upload(
@@ -1297,6 +1373,12 @@ int csrspmv_cuda_get_info(const csrspmv_cuda_matrix *A, csrspmv_cuda_info *info)
     info->max_col = S->max_col;
     info->kernel = S->kernel;
     info->launches_per_spmv = 1;
+    if (S->sell) {
+        info->sell_slots = sell_entries(S->sell);
+        info->sell_real = sell_real_entries(S->sell);
+        info->sell_long_rows = sell_long_rows(S->sell);
+        info->launches_per_spmv = sell_launches(S->sell);
+    }
     if (S->ell) {
         info->ell_view = S->ell->d_rowlen ? 1 : 2;
         info->ell_staged = S->ell->sg ? S->ell->staged_mode : 0;

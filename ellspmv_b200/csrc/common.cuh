@@ -103,6 +103,7 @@ struct EllSpmvArgs {
     PushTargets   push;
     int           prefetch;     // slices ahead whose value stream is requested into L2 (0 = none)
     const unsigned char *patid; // offset patterns (pattern.cu): one id per warp (32*R rows), 0xff = explicit indices; or NULL
+    const unsigned      *patmask; // per patterned warp: lanes whose rows deviate and read the explicit indices
     const long long     *pat;   // dictionary [kMaxPatterns][K] of column offsets relative to the GLOBAL row
     StepSync      sync;
     const int    *rowlen;   // per row: how many leading slots count (CSR view: the rest is never touched
@@ -122,6 +123,9 @@ struct EllLaunchCfg {
 
 cudaError_t launch_ell_spmv(const EllLaunchCfg &cfg, const EllSpmvArgs &args,
                             int64_t num_slices, cudaStream_t stream);
+// few, long rows: CTA per row group on the row-major layout (slice height 1), ell_longrow.cu
+cudaError_t launch_ell_longrow(const EllLaunchCfg &cfg, const EllSpmvArgs &args, cudaStream_t stream);
+constexpr int kKernelLongRow = 4;   // ELLSPMV_CUDA_KERNEL_LONGROW
 // persistent bulk-async (TMA) staged variant, ell_bulk.cu; *handled = false: not applicable
 cudaError_t launch_ell_bulk(const EllLaunchCfg &cfg, const EllSpmvArgs &args, int64_t num_slices,
                             cudaStream_t stream, bool *handled);
@@ -173,6 +177,8 @@ cudaError_t mark_remote_slices(int idx_bits, const void *cols, const EllLayout &
 // ---- offset patterns: groups of 32 rows whose column indices are row + d[l] (pattern.cu) ----
 struct PatternSet {
     unsigned char *patid = nullptr;   // device: padded_rows / 32 ids
+    unsigned *patmask = nullptr;      // device: per group, the lanes that keep explicit indices (deviating rows)
+    int64_t explicit_lanes = 0;       // lanes flagged in the masks of the patterned groups
     long long *pat = nullptr;         // device: kMaxPatterns * K offsets
     int num_patterns = 0;
     int group_rows = 32;              // 32 * rows per thread
@@ -207,6 +213,22 @@ int64_t sg_bytes_estimate(int idx_bits, const EllLayout &lay);
 void sg_free(SgMatrix *sg);
 int64_t sg_bytes(const SgMatrix *sg);
 int sg_launches(const SgMatrix *sg);
+
+// ---- SELL-128-sigma: per-slice widths, rows sorted by length in windows (sell.cu) --------------
+struct SellMatrix;
+cudaError_t sell_build_csr(SellMatrix **out, int src_idx_bits, int dst_idx_bits, int64_t num_rows, const int64_t *rowptr,
+                           const void *cols, const double *vals, cudaStream_t stream);
+cudaError_t sell_build_ell(SellMatrix **out, int idx_bits, const void *cols, const double *vals, const EllLayout &lay,
+                           int64_t row_begin, int64_t num_columns, cudaStream_t stream);
+cudaError_t sell_spmv(const SellMatrix *m, bool fma, const int64_t *csr_rowptr, const void *csr_cols,
+                      const double *csr_vals, int csr_idx_bits, const double *x, double *y,
+                      const double *ad, int64_t row_begin, int beta, cudaStream_t stream);
+void sell_free(SellMatrix *m);
+int64_t sell_bytes(const SellMatrix *m);
+int64_t sell_entries(const SellMatrix *m);        // stored slots
+int64_t sell_real_entries(const SellMatrix *m);   // slots that count
+int64_t sell_long_rows(const SellMatrix *m);
+int sell_launches(const SellMatrix *m);
 
 // ---- COO -> ELL / CSR on the device (convert.cu) ------------------------------
 struct CooEllJob {

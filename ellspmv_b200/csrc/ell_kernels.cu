@@ -202,10 +202,11 @@ ell_thread_kernel(const EllSpmvArgs a)
             __syncthreads();
         }
     }
-    if (row0 >= a.num_rows) {
-        if (synced) __syncthreads();      // pairs with the barrier before the completion count below
-        return;
-    }
+    // Threads past the shard's last row leave -- except in a launch with the fused step
+    // synchronisation, whose CTAs meet at a barrier below: __syncthreads() must be reached by
+    // whole warps together, so there the surplus threads of the last slice run along on its
+    // zero-filled tail ((column 0, 0.0) slots; every store below is guarded by the row count).
+    if (row0 >= a.num_rows && !synced) return;
 
     const int64_t base = slice * S * (int64_t)K + (int64_t)threadIdx.x * R;
     const double *vp = a.vals + base;
@@ -215,13 +216,30 @@ ell_thread_kernel(const EllSpmvArgs a)
     // warp-uniform: this warp's pattern (or none); rowg = the row's global index
     const long long *__restrict__ prow = nullptr;
     const int64_t rowg = a.row_begin + row0;
+    // A patterned group may hold a few lanes whose rows deviate from its pattern (a grid
+    // boundary); they are flagged in the group's mask.  The main loop below stays the plain
+    // warp-uniform two-way branch: a flagged lane runs along on the columns of the group's first
+    // regular lane (valid addresses, its result is thrown away) and then recomputes its own rows
+    // from the explicit index stream in a short divergent tail -- K sectors of 32 bytes for that
+    // lane instead of the whole group's 128/256-byte lines.
+    bool flagged = false;
+    int64_t rowp = rowg;          // the row the pattern's offsets are applied to
     if (PAT) {
-        const unsigned pid = __ldg(a.patid + ((slice * kBlockThreads + threadIdx.x) >> 5));
-        if (pid != 0xffu) prow = a.pat + (int64_t)pid * K;
+        const int64_t grp = (slice * kBlockThreads + threadIdx.x) >> 5;
+        const unsigned pid = __ldg(a.patid + grp);
+        if (pid != 0xffu) {
+            prow = a.pat + (int64_t)pid * K;
+            const unsigned m = __ldg(a.patmask + grp);
+            if (m != 0u) {
+                const int64_t lead = __shfl_sync(0xffffffffu, rowg, __ffs(~m) - 1);
+                flagged = (m >> (threadIdx.x & 31)) & 1u;
+                if (flagged) rowp = lead;
+            }
+        }
     }
     auto load_cols = [&](int l, int64_t (&c)[R]) {
         if (PAT && prow) {
-            const int64_t c0 = rowg + __ldg(prow + l);
+            const int64_t c0 = rowp + __ldg(prow + l);
 #pragma unroll
             for (int r = 0; r < R; r++) c[r] = c0 + r;
         } else {
@@ -322,6 +340,20 @@ ell_thread_kernel(const EllSpmvArgs a)
 #pragma unroll
             for (int r = 0; r < R; r++)
                 if (!LEN || l0 < len) acc[r] = madd<FMA>(acc[r], v[r], ldx<G>(x + c[r]));
+        }
+    }
+
+    // the flagged lanes of a patterned group: their rows again, from the explicit indices
+    if (PAT && flagged) {
+#pragma unroll
+        for (int r = 0; r < R; r++) acc[r] = (ad && a.sd_order) ? dx[r] : 0.0;
+#pragma unroll 1
+        for (int l = 0; l < K; l++) {
+            double v[R]; int64_t c[R];
+            Vals<R>::ld(vp + (int64_t)l * S, v);
+            Cols<IdxT, R>::ld(cp + (int64_t)l * S, c);
+#pragma unroll
+            for (int r = 0; r < R; r++) acc[r] = madd<FMA>(acc[r], v[r], ldx<G>(x + c[r]));
         }
     }
 
@@ -505,6 +537,7 @@ cudaError_t launch_ell_spmv(const EllLaunchCfg &cfg, const EllSpmvArgs &args_in,
     static const int prefetch_env = getenv("ELLSPMV_CUDA_PREFETCH_SLICES") ? atoi(getenv("ELLSPMV_CUDA_PREFETCH_SLICES")) : -1;
     if (prefetch_env >= 0) args.prefetch = prefetch_env;
     if (num_slices > 0x7fffffffLL) return cudaErrorInvalidValue;
+    if (cfg.kernel == kKernelLongRow) return launch_ell_longrow(cfg, args, stream);
     if ((cfg.variant & 1) && args.num_rows > 0) {
         bool handled = false;
         cudaError_t e = launch_ell_bulk(cfg, args, num_slices, stream, &handled);

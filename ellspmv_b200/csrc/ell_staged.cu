@@ -279,8 +279,16 @@ sg_gather_kernel(const IdxT *__restrict__ gcols, const double *__restrict__ x, d
     double v[4] = {0.0, 0.0, 0.0, 0.0};
     if (on0) { v[0] = __ldg(x + c[0]); v[1] = __ldg(x + c[1]); }
     if (on1) { v[2] = __ldg(x + c[2]); v[3] = __ldg(x + c[3]); }
-    if (on0) __stcs(reinterpret_cast<double2 *>(xg + e), make_double2(v[0], v[1]));
-    if (on1) __stcs(reinterpret_cast<double2 *>(xg + e) + 1, make_double2(v[2], v[3]));
+    // one 256-bit store per group (SASS STG.E.EF.256): a lane writes a whole 32-byte sector.  Two
+    // 16-byte halves -- what this kernel did first -- half-fill 32 sectors per instruction and cost
+    // 0.6 gathers' worth of SM->L2 traffic per entry (176 -> 219 G gathers/s, profiles/r2_phase1_lab.md);
+    // the halves remain for the first/last group of a run
+    if (on0 && on1)
+        asm volatile("st.global.cs.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(xg + e), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]) : "memory");
+    else {
+        if (on0) __stcs(reinterpret_cast<double2 *>(xg + e), make_double2(v[0], v[1]));
+        if (on1) __stcs(reinterpret_cast<double2 *>(xg + e) + 1, make_double2(v[2], v[3]));
+    }
 }
 
 // ---- phase 2: the reference's row loop over staged x values ------------------------
@@ -353,6 +361,7 @@ sg_sum_kernel(const double *__restrict__ vals, const unsigned short *__restrict_
             asm volatile("{\n\t.reg .pred p;\n\t"
                          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
                          "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(sg_smem_u32(bar)), "r"(0) : "memory");
+        if (!ok) __trap();     // the staged values never arrived: fail the launch loudly instead of summing garbage
     }
 
     double acc = (ad && sd_order) ? dx : 0.0;

@@ -217,7 +217,11 @@ int group_info(const ellspmv_cuda_matrix *G, ellspmv_cuda_info *info)
     info->min_col = G->min_col;
     info->max_col = G->max_col;
     int64_t launches = 0;
-    for (const ellspmv_cuda_matrix *S : G->shards) { launches += S->launches; info->pattern_rows += S->pat.covered * S->pat.group_rows; }
+    for (const ellspmv_cuda_matrix *S : G->shards) {
+        launches += S->launches;
+        info->pattern_rows += S->pat.covered * S->pat.group_rows - S->pat.explicit_lanes * S->cfg.rows_per_thread;
+        info->exception_entries += S->pat.explicit_lanes * S->cfg.rows_per_thread * S->lay.rowsize;
+    }
     info->launches = launches;
     info->num_gpus = (int)G->shards.size();
     return 0;

@@ -40,6 +40,7 @@ struct ellspmv_cuda_matrix {
     double tune_ms[2] = {0.0, 0.0};          // KERNEL_AUTO's trial at upload: direct, staged
     bool kernel_auto = false;                // the caller left the kernel choice to the library
     ellspmv::CbMatrix *cb = nullptr;         // column-blocked copy (ELLSPMV_CUDA_COLUMN_BLOCKED), optional
+    ellspmv::SellMatrix *sell = nullptr;     // SELL-128-sigma copy without the trailing padding (ELLSPMV_CUDA_SKIP_PADDING), optional
     int64_t min_col = 0, max_col = -1;
     unsigned char *d_remote = nullptr;       // per slice: reads columns outside the shard's rows (fused step sync)
     unsigned *d_done = nullptr;              // CTA completion counter of the fused step sync
@@ -80,6 +81,7 @@ struct csrspmv_cuda_matrix {
     ellspmv_cuda_matrix *ell = nullptr;      // sliced-ELL view of the same entries (KERNEL_AUTO, balanced rows): the
                                              //   launches go through the ELL kernels with per-row lengths
     int64_t min_row_len = 0;
+    ellspmv::SellMatrix *sell = nullptr;     // SELL-128-sigma copy (KERNEL_AUTO, unbalanced rows; or kernel selector 5)
     int64_t min_col = 0, max_col = -1;       // range of the stored column indices
     std::vector<cudaEvent_t> events;
     int64_t device_bytes = 0;

@@ -41,11 +41,11 @@ typedef struct csrspmv_cuda_matrix csrspmv_cuda_matrix; /* opaque, CSR  */
 /* ---- flags for upload/generate (OR together) ------------------------- */
 enum {
     /* kernel selection (low 4 bits) */
-    ELLSPMV_CUDA_KERNEL_AUTO   = 0, /* ELL: thread-per-row at every nnz-per-row  */
-                                    /*   (measured fastest on the sliced layout  */
-                                    /*   from K=5 to K=32) and    */
-                                    /*   bit-exact; CSR: scalar or stream by row */
-                                    /*   balance                                 */
+    ELLSPMV_CUDA_KERNEL_AUTO   = 0, /* ELL: by nnz-per-row and row count --      */
+                                    /*   thread-per-row on the sliced layout     */
+                                    /*   (fully coalesced at any K), the long-row*/
+                                    /*   kernel for few long rows; both bit-exact*/
+                                    /*   CSR: see CSRSPMV_CUDA_KERNEL_SCALAR     */
     ELLSPMV_CUDA_KERNEL_THREAD = 1, /* thread-per-row, sequential slot order:   */
                                     /*   bit-exact with the reference loop      */
     ELLSPMV_CUDA_KERNEL_WARP   = 2, /* sub-warp-per-row + shuffle reduction:    */
@@ -59,6 +59,12 @@ enum {
                                     /*   stream kernel cannot contract (it parks rounded   */
                                     /*   products): AUTO then never picks it, so the bits  */
                                     /*   do not depend on the row lengths                  */
+    ELLSPMV_CUDA_KERNEL_LONGROW = 4,/* ELL: few, long rows -- a CTA per small group of rows  */
+                                    /*   on the reference's own row-major layout: all threads */
+                                    /*   stream and gather, the rounded products are parked   */
+                                    /*   in shared memory, one lane per row adds them in slot */
+                                    /*   order: bit-exact.  AUTO takes it for rowsize >= 64   */
+                                    /*   on matrices of at most 32768 rows  */
     ELLSPMV_CUDA_KERNEL_MASK   = 0xf,
     /* arithmetic: default is mul-then-add (__dmul_rn/__dadd_rn), the bits the
      * reference's compiled loop produces; FMA allows contraction (tolerance) */
@@ -107,6 +113,16 @@ enum {
      * one -- the results are the same bits either way.  NO_STAGED_GATHER keeps
      * the direct gather without a trial. */
     ELLSPMV_CUDA_NO_STAGED_GATHER = 1 << 19,
+    /* SELL-128-sigma for ELL matrices with ragged rows (opt-in): the reference pads every
+     * row to the longest one (ellspmv.c:944-955, 1111-1117) and streams the padding; with
+     * this flag the handle also keeps the rows sorted by their length without trailing
+     * padding (windows of 4096 rows), sliced with a width per slice, and runs
+     * y += A*x from that copy -- only the slots that count are streamed, in the
+     * reference's order.  Bit-exact for finite x; where x is inf/NaN on a row's PADDING
+     * column the reference produces 0*inf = NaN and this path does not: hence opt-in.
+     * (The CSR path uses the same layout by itself for unbalanced rows: csrgemv has no
+     * padding, so there it is exact for every x.) */
+    ELLSPMV_CUDA_SKIP_PADDING     = 1 << 20,
     /* rows handled per thread in the thread-per-row kernel (1, 2 or 4):
      * 0 = auto = 2 for rows of at most 12 entries, else 1 */
     ELLSPMV_CUDA_ROWS_PER_THREAD_SHIFT = 8,
@@ -160,6 +176,8 @@ typedef struct ellspmv_cuda_info {
     int64_t exception_entries; /* entries patched after the pattern lookup    */
     int64_t long_rows;       /* 0, or the row length from which the long-row  */
                              /*   kernel is used (KERNEL_AUTO)                */
+    int64_t sell_slots;      /* ELLSPMV_CUDA_SKIP_PADDING: slots stored in the */
+                             /*   SELL-128-sigma copy (vs num_rows * rowsize)  */
 } ellspmv_cuda_info;
 
 /* ---- ELL ------------------------------------------------------------- */
@@ -343,7 +361,10 @@ typedef struct csrspmv_cuda_info {
     int64_t min_row_len, max_row_len;
     int64_t min_col, max_col;
     int64_t device_bytes;
-    int     kernel;            /* native kernel in use: 1 stream, 2 vector, 3 scalar, 5 adaptive */
+    int     kernel;            /* kernel in use: 1 stream, 2 vector, 3 scalar, 5 SELL-128-sigma  */
+    int64_t sell_slots;        /* kernel 5: slots stored in the slices (padding included) ...    */
+    int64_t sell_real;         /*   ... of which count; */
+    int64_t sell_long_rows;    /*   rows longer than 4096 entries, run one CTA per row           */
     int     ell_view;          /* 0: native CSR kernels; 1: sliced-ELL view with per-row        */
                                /*   lengths; 2: view of rows of one length (no length array)    */
     int     ell_staged;        /* the view runs the staged gather (see ellspmv_cuda_info)       */

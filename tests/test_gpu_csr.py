@@ -256,3 +256,70 @@ def test_random_generated_csr_uses_the_uniform_view(lib, oracle):
     A.spmv(y, x, 1, E.ACCUMULATE)
     A.free()
     assert bits_equal(y, want)
+
+
+def powerlaw_csr(rng, nr, nc, dt, min_len=2, max_len=9000, alpha=1.3, empty_frac=0.05):
+    """Row lengths ~ Pareto: most rows short, a tail of very long ones."""
+    u = rng.random(nr)
+    lens = np.minimum((min_len / u ** (1.0 / alpha)).astype(np.int64), max_len)
+    lens[rng.random(nr) < empty_frac] = 0
+    rowptr = np.zeros(nr + 1, dtype=np.int64)
+    np.cumsum(lens, out=rowptr[1:])
+    nnz = int(rowptr[-1])
+    return rowptr, rng.integers(0, nc, nnz).astype(dt), rng.standard_normal(nnz)
+
+
+@pytest.mark.parametrize("shape", [(1, 50), (130, 5000), (4096, 3000), (4097, 70000), (30000, 30000)])
+@pytest.mark.parametrize("bits", [32, 64])
+def test_auto_runs_skewed_rows_through_sell(lib, oracle, shape, bits):
+    """Unbalanced rows (power law): KERNEL_AUTO builds SELL-128-sigma (rows sorted by length in
+    windows of 4096, width per slice, rows beyond 4096 entries one CTA each) -- csrgemv's bits,
+    with accumulate/overwrite, the separate diagonal, non-finite x, and several launches."""
+    nr, nc = shape
+    dt = np.int32 if bits == 32 else np.int64
+    rng = np.random.default_rng(nr + bits)
+    rowptr, ec, ea = powerlaw_csr(rng, nr, nc, dt)
+    if nr > 1000:
+        assert np.diff(rowptr).max() > 4096            # the long-row kernel has work
+    x = rng.standard_normal(nc)
+    y0 = rng.standard_normal(nr)
+    A = E.CsrMatrix.upload(nr, nc, rowptr, ec, ea)
+    i = A.info()
+    if nr >= 130:
+        assert i.kernel == E.KERNEL_CSR_SELL and i.ell_view == 0, (i.kernel, i.ell_view)
+        assert i.sell_real + sum(n for n in np.diff(rowptr) if n > 4096) == rowptr[-1]
+        assert i.sell_long_rows == int((np.diff(rowptr) > 4096).sum())
+        assert i.sell_slots < 1.6 * max(i.sell_real, 1) + 128 * 64    # sorting keeps the padding small
+    for xv in (x, np.where(rng.random(nc) < 0.01, np.inf, x)):
+        want = y0.copy()
+        for _ in range(2):
+            oracle.csrgemv(nr, want, xv, rowptr, ec, ea)
+        y = y0.copy()
+        A.spmv(y, xv, 2, E.ACCUMULATE)
+        assert np.array_equal(np.isnan(y), np.isnan(want))
+        ok = ~np.isnan(want)
+        assert bits_equal(y[ok], want[ok])
+    w0 = np.zeros(nr)
+    oracle.csrgemv(nr, w0, x, rowptr, ec, ea)
+    y = np.full(nr, 3.0)
+    A.spmv(y, x, 1, E.OVERWRITE)
+    assert bits_equal(y, w0)
+    if nr <= nc:
+        ad = rng.standard_normal(nr)
+        want = y0.copy()
+        oracle.csrgemvsd(nr, want, x, rowptr, ec, ea, ad)
+        A.set_diagonal(ad)
+        y = y0.copy()
+        A.spmv(y, x, 1, E.ACCUMULATE)
+        assert bits_equal(y, want)
+    A.free()
+    # explicit selector, and the native kernels on the same matrix
+    for kern in (E.KERNEL_CSR_SELL, E.KERNEL_THREAD, E.KERNEL_CSR_SCALAR):
+        B = E.CsrMatrix.upload(nr, nc, rowptr, ec, ea, kern)
+        assert B.info().kernel == kern or (kern == E.KERNEL_CSR_SELL and rowptr[-1] == 0)
+        y = y0.copy()
+        B.spmv(y, x, 1, E.ACCUMULATE)
+        w = y0.copy()
+        oracle.csrgemv(nr, w, x, rowptr, ec, ea)
+        assert bits_equal(y, w), kern
+        B.free()

@@ -441,6 +441,141 @@ def test_staged_gather_is_bit_exact(lib, oracle, shape, bits, monkeypatch):
             A.free()
 
 
+@pytest.mark.parametrize("shape", [(1, 5000, 5000), (3, 100, 70), (200, 3000, 257), (1000, 1000, 64), (40, 9000, 4097),
+                                   (33, 400, 1024), (5000, 5000, 96)])
+@pytest.mark.parametrize("bits", [32, 64])
+def test_long_row_kernel_is_bit_exact(lib, oracle, shape, bits):
+    """Few, long rows: KERNEL_AUTO takes the CTA-per-row-group kernel on the row-major layout
+    (ell_longrow.cu); products parked in shared memory, one lane adds them in slot order -> the
+    oracle's bits, for every rows-per-CTA choice, accumulate and overwrite, both diagonal orders."""
+    nr, nc, K = shape
+    dt = np.int32 if bits == 32 else np.int64
+    rng = np.random.default_rng(nr + K + bits)
+    ec, ea = rand_ell(rng, nr, nc, K, dt)
+    x = rng.standard_normal(nc)
+    y0 = rng.standard_normal(nr)
+    want = y0.copy()
+    oracle.ellgemv(nr, want, x, K, ec, ea)
+    want0 = np.zeros(nr)
+    oracle.ellgemv(nr, want0, x, K, ec, ea)
+    for flags in (0, E.KERNEL_LONGROW):
+        A = E.EllMatrix.upload(nr, nc, K, ec, ea, flags)
+        i = A.info()
+        assert i.kernel == E.KERNEL_LONGROW and i.slice_rows == 1 and i.long_rows == K, (flags, i.kernel)
+        c2, a2 = A.download()
+        assert np.array_equal(c2, ec) and bits_equal(a2, ea)
+        y = y0.copy()
+        A.spmv(y, x, 1, E.ACCUMULATE)
+        assert bits_equal(y, want)
+        A.spmv(y, x, 1, E.OVERWRITE)
+        assert bits_equal(y, want0)
+        if nr <= nc:
+            ad = rng.standard_normal(nr)
+            for order in (0, 1):
+                w = y0.copy()
+                oracle.ellgemvsd(nr, w, x, K, ec, ea, ad, order)
+                A.set_diagonal(ad, order)
+                y = y0.copy()
+                A.spmv(y, x, 1, E.ACCUMULATE)
+                assert bits_equal(y, w), order
+        A.free()
+    # the thread-per-row kernel on the same matrix: same bits (the switch is invisible)
+    B = E.EllMatrix.upload(nr, nc, K, ec, ea, E.KERNEL_THREAD)
+    assert B.info().kernel == E.KERNEL_THREAD
+    y = y0.copy()
+    B.spmv(y, x, 1, E.ACCUMULATE)
+    B.free()
+    assert bits_equal(y, want)
+    # special values travel the same way
+    xs = x.copy()
+    xs[rng.integers(0, nc, 3)] = np.inf
+    w = np.zeros(nr)
+    oracle.ellgemv(nr, w, xs, K, ec, ea)
+    C2 = E.EllMatrix.upload(nr, nc, K, ec, ea)
+    y = np.zeros(nr)
+    C2.spmv(y, xs, 1, E.ACCUMULATE)
+    C2.free()
+    assert np.array_equal(np.isnan(y), np.isnan(w))
+    ok = ~np.isnan(w)
+    assert bits_equal(y[ok], w[ok])
+
+
+def test_long_row_kernel_in_a_shard_and_iterate(lib, oracle):
+    import torch
+    nr = nc = 900
+    K = 130
+    rng = np.random.default_rng(3)
+    ec, ea = rand_ell(rng, nr, nc, K, np.int32)
+    ea *= 0.01
+    x = rng.standard_normal(nc)
+    want = oracle.ell_iterate(nr, x, 4, K, ec, ea)
+    A = E.EllMatrix.upload(nr, nc, K, ec, ea)
+    assert A.info().kernel == E.KERNEL_LONGROW
+    y = np.zeros(nr)
+    A.spmv(y, x, 4, E.ITERATE)
+    A.free()
+    assert bits_equal(y, want)
+    lo, hi = 123, 777
+    S = E.EllMatrix.upload(hi - lo, nc, K, ec[lo * K:hi * K], ea[lo * K:hi * K], global_rows=nr, row_begin=lo, device=0)
+    w = np.zeros(nr)
+    oracle.ellgemv(nr, w, x, K, ec, ea)
+    xd = torch.from_numpy(x).cuda()
+    own = torch.zeros(nr, dtype=torch.float64, device="cuda")
+    peer = torch.zeros(nr, dtype=torch.float64, device="cuda")
+    S.spmv_push(own[lo:hi], xd, E.OVERWRITE, [peer.data_ptr()], [200], [300], torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    S.free()
+    assert bits_equal(own[lo:hi].cpu().numpy(), w[lo:hi]) and bits_equal(peer[200:300].cpu().numpy(), w[200:300])
+    assert peer[:200].abs().sum() == 0 and peer[300:].abs().sum() == 0
+
+
+@pytest.mark.parametrize("bits", [32, 64])
+def test_skip_padding_runs_from_the_sell_copy(lib, oracle, bits):
+    """ELLSPMV_CUDA_SKIP_PADDING: rows sorted by their length without trailing padding, a width per
+    slice; only the slots that count are streamed.  Same bits as the reference for finite x; download
+    and the other entry points still see the padded ELL arrays."""
+    dt = np.int32 if bits == 32 else np.int64
+    rng = np.random.default_rng(40 + bits)
+    nr, nc, K = 9000, 9500, 40
+    ec = np.empty((nr, K), dtype=dt)
+    ea = np.zeros((nr, K))
+    lens = np.minimum((2 / rng.random(nr) ** 0.8).astype(np.int64), K)      # ragged: most rows short, a few full
+    lens[rng.random(nr) < 0.03] = 0
+    for i in range(nr):
+        n = int(lens[i])
+        ec[i, :n] = rng.integers(0, nc, n)
+        ea[i, :n] = rng.standard_normal(n)
+        ec[i, n:] = min(i, nc - 1)                                       # the reference's padding rule
+    ea[5, 1] = 0.0                                                      # a stored zero INSIDE a row is not padding
+    ec, ea = ec.reshape(-1), ea.reshape(-1)
+    x = rng.standard_normal(nc)
+    y0 = rng.standard_normal(nr)
+    want = y0.copy()
+    oracle.ellgemv(nr, want, x, K, ec, ea)
+    A = E.EllMatrix.upload(nr, nc, K, ec, ea, E.SKIP_PADDING)
+    i = A.info()
+    assert 0 < i.sell_slots < nr * K // 3, i.sell_slots
+    y = y0.copy()
+    A.spmv(y, x, 1, E.ACCUMULATE)
+    assert bits_equal(y, want)
+    y = np.full(nr, 9.0)
+    A.spmv(y, x, 1, E.OVERWRITE)
+    w0 = np.zeros(nr)
+    oracle.ellgemv(nr, w0, x, K, ec, ea)
+    assert bits_equal(y, w0)
+    c2, a2 = A.download()
+    assert np.array_equal(c2, ec) and bits_equal(a2, ea)
+    for order in (0, 1):                      # order 1 falls back to the padded layout: same bits either way
+        ad = rng.standard_normal(nr)
+        w = y0.copy()
+        oracle.ellgemvsd(nr, w, x, K, ec, ea, ad, order)
+        A.set_diagonal(ad, order)
+        y = y0.copy()
+        A.spmv(y, x, 1, E.ACCUMULATE)
+        assert bits_equal(y, w), order
+    A.free()
+
+
 def test_auto_tries_the_staged_gather_on_scattered_matrices(lib, oracle, monkeypatch):
     """KERNEL_AUTO: x larger than the threshold + no offset patterns + scattered gathers -> the staged
     copy is built and timed against the direct gather at upload; whichever is kept, the bits are the
@@ -553,8 +688,9 @@ def test_offset_patterns_are_found_and_change_nothing(lib, oracle, bits):
 
 
 def test_offset_patterns_adversarial(lib, oracle):
-    """One deviating entry keeps its group on the explicit stream; more distinct patterns than the
-    dictionary holds leaves the rest explicit; a random matrix finds nothing.  Always the oracle's bits."""
+    """A deviating entry keeps only its own ROW on the explicit stream (lane masks); more distinct
+    patterns than the dictionary holds leaves the rest explicit; a random matrix finds nothing.
+    Always the oracle's bits."""
     rng = np.random.default_rng(11)
     nr = nc = 4096
     # (a) a single entry of a single row differs from its group's pattern
@@ -573,12 +709,15 @@ def test_offset_patterns_adversarial(lib, oracle):
     ec3 = rng.integers(0, nc, nr * 4).astype(np.int32)
     ea3 = rng.standard_normal(nr * 4)
     x = rng.standard_normal(nc)
-    for K, cols, vals, lo, hi in ((3, ec, ea, 3900, 4096 - 64), (2, ec2.reshape(-1), ea2, 32, 4096 - 1024), (4, ec3, ea3, 0, 0)):
+    # (a): the two damaged rows and the boundary rows stay explicit, their groups stay patterned
+    # (the last group has 5 boundary rows, more than a mask takes: it stays explicit as a whole)
+    for K, cols, vals, lo, hi in ((3, ec, ea, 4096 - 48, 4096 - 34), (2, ec2.reshape(-1), ea2, 32, 4096 - 1024), (4, ec3, ea3, 0, 0)):
         want = np.zeros(nr)
         oracle.ellgemv(nr, want, x, K, cols, vals)
         A = E.EllMatrix.upload(nr, nc, K, cols, vals, E.rows_per_thread(1))    # groups of 32 rows
         rows = A.info().pattern_rows
         assert lo <= rows <= hi, (K, rows)
+        assert rows == expected_pattern_rows(cols, K, nr, 1), K
         y = np.zeros(nr)
         A.spmv(y, x, 1, E.OVERWRITE)
         assert bits_equal(y, want), K
@@ -602,34 +741,50 @@ def test_offset_patterns_in_a_row_shard(lib, oracle):
     A.free()
 
 
-def expected_pattern_rows(ec, K, nr, R, row_begin=0, max_patterns=16):
+def expected_pattern_rows(ec, K, nr, R, row_begin=0, max_patterns=16, max_explicit=4):
     """numpy restatement of the upload-time pattern search (pattern.cu) for matrices small
-    enough that every group is sampled: groups of 32*R rows sharing one offset vector, kept
-    if that vector is among the 16 most common (ties: first seen), dropped below 10 % coverage."""
+    enough that every group is sampled.  A group is the 32*R rows of one warp, lane j owning
+    rows j*R..j*R+R-1; a lane has an offset vector when its R rows share one; a group's
+    signature is the vector at least 32 - max_explicit of its lanes share; the 16 most common
+    signatures (ties: first seen) form the dictionary; in a group whose signature is in it the
+    lanes with another vector keep their explicit indices.  Dropped below 10 % of the groups.
+    Returns the rows that take their indices from the dictionary."""
     S = 128 * R
     G = 32 * R
     padded = -(-nr // S) * S
     groups = padded // G
     off = ec.reshape(nr, K).astype(np.int64) - (row_begin + np.arange(nr, dtype=np.int64))[:, None]
     sig = {}
-    uniform = []
+    group_sig, group_match = [], []
     for g in range(groups):
         lo, hi = g * G, (g + 1) * G
         if hi > nr:
-            uniform.append(None)
+            group_sig.append(None)
+            group_match.append(0)
             continue
-        blk = off[lo:hi]
-        if (blk == blk[0]).all():
-            key = tuple(blk[0])
-            uniform.append(key)
-            cnt, first = sig.get(key, (0, g))
-            sig[key] = (cnt + 1, first)
+        lanes = []
+        for j in range(32):
+            blk = off[lo + j * R: lo + (j + 1) * R]
+            lanes.append(tuple(blk[0]) if (blk == blk[0]).all() else None)
+        counts = {}
+        for v in lanes:
+            if v is not None:
+                counts[v] = counts.get(v, 0) + 1
+        key, cnt = max(counts.items(), key=lambda kv: kv[1]) if counts else (None, 0)
+        if cnt >= 32 - max_explicit:
+            group_sig.append(key)
+            group_match.append(cnt)
+            c, first = sig.get(key, (0, g))
+            sig[key] = (c + 1, first)
         else:
-            uniform.append(None)
+            group_sig.append(None)
+            group_match.append(0)
     best = sorted(sig.items(), key=lambda kv: (-kv[1][0], kv[1][1]))[:max_patterns]
     keep = {k for k, _ in best}
-    covered = sum(1 for u in uniform if u is not None and u in keep)
-    return covered * G if covered * 10 >= groups else 0
+    covered = [g for g in range(groups) if group_sig[g] is not None and group_sig[g] in keep]
+    if len(covered) * 10 < groups:
+        return 0
+    return sum(group_match[g] for g in covered) * R
 
 
 @pytest.mark.parametrize("seed", range(8))
