@@ -77,7 +77,7 @@ class CsrInfo(C.Structure):
         ("num_rows", C.c_int64), ("num_columns", C.c_int64), ("csrsize", C.c_int64),
         ("min_row_len", C.c_int64), ("max_row_len", C.c_int64), ("min_col", C.c_int64), ("max_col", C.c_int64),
         ("device_bytes", C.c_int64), ("kernel", C.c_int), ("sell_slots", C.c_int64), ("sell_real", C.c_int64),
-        ("sell_long_rows", C.c_int64), ("ell_view", C.c_int), ("ell_staged", C.c_int),
+        ("sell_long_rows", C.c_int64), ("sell_long_len", C.c_int64), ("ell_view", C.c_int), ("ell_staged", C.c_int),
         ("launches_per_spmv", C.c_int), ("ell_pattern_rows", C.c_int64), ("num_gpus", C.c_int), ("fma", C.c_int),
     ]
 
@@ -389,7 +389,8 @@ class CsrMatrix:
             return f"sliced-ELL view of the CSR rows ({how}, width {i.max_row_len}): {path}, {arith}"
         name = {1: "smem-staged stream kernel", 2: "sub-warp per row + shuffle tree (tolerance)",
                 3: "scalar thread-per-row",
-                5: f"SELL-128-sigma (rows sorted by length in windows of 4096, width per slice; {i.sell_long_rows} long rows one CTA each)"}
+                5: f"SELL-128-sigma (rows sorted by length in windows of 4096, width per slice; the {i.sell_long_rows} rows "
+                   f"longer than {i.sell_long_len} one CTA each on a second stream)"}
         return f"native CSR: {name.get(i.kernel, str(i.kernel))}, {arith}"
 
     def free(self) -> None:

@@ -146,8 +146,7 @@ void warm_kernels(ellspmv_cuda_matrix *A)
     args.num_rows = 0;
     args.rowsize = A->lay.rowsize;
     args.beta = 1;
-    args.patid = A->pat.patid;
-    args.patmask = A->pat.patmask;
+    args.patid = A->pat.patinfo;
     args.pat = A->pat.pat;
     if (launch_ell_spmv(A->cfg, args, 1, A->stream) == cudaSuccess) cudaStreamSynchronize(A->stream);
     cudaGetLastError();
@@ -213,7 +212,7 @@ int auto_staged_gather(ellspmv_cuda_matrix *A, long long block_bytes)
     ELL_CK(cudaMemGetInfo(&free_b, &total_b));
     const int64_t scratch = (A->num_columns + A->lay.num_rows) * 8;
     if ((int64_t)free_b < sg_bytes_estimate(A->dev_idx_bits, A->lay) + scratch + (1LL << 30)) return 0;
-    cudaError_t ce = sg_build(&A->sg, A->dev_idx_bits, A->cols, A->lay, A->num_columns, block_bytes, A->stream);
+    cudaError_t ce = sg_build(&A->sg, A->dev_idx_bits, A->cols, A->vals, A->lay, A->num_columns, block_bytes, A->stream);
     if (ce == cudaErrorMemoryAllocation) { cudaGetLastError(); A->sg = nullptr; return 0; }
     if (ce != cudaSuccess) { set_last_error("staged gather: %s", cudaGetErrorString(ce)); return cuda_to_errno(ce); }
     if (!A->sg) return 0;
@@ -288,7 +287,7 @@ int build_column_blocks(ellspmv_cuda_matrix *A)
     }
     if (A->flags & ELLSPMV_CUDA_STAGED_GATHER) {
         // the bit-exact flavour (ell_staged.cu); wins over COLUMN_BLOCKED when both are set
-        cudaError_t ce = sg_build(&A->sg, A->dev_idx_bits, A->cols, A->lay, A->num_columns, target, A->stream);
+        cudaError_t ce = sg_build(&A->sg, A->dev_idx_bits, A->cols, A->vals, A->lay, A->num_columns, target, A->stream);
         if (ce != cudaSuccess) { set_last_error("staged gather: %s", cudaGetErrorString(ce)); return cuda_to_errno(ce); }
         A->device_bytes += sg_bytes(A->sg);
         if (A->sg) A->staged_mode = 1;
@@ -370,8 +369,7 @@ int launch(ellspmv_cuda_matrix *A, double *y_dev, const double *x_dev, int beta,
     args.slice_begin = slice_begin;
     args.ad = A->d_ad;
     args.sd_order = A->sd_order;
-    args.patid = A->pat.patid;
-    args.patmask = A->pat.patmask;
+    args.patid = A->pat.patinfo;
     args.pat = A->pat.pat;
     args.rowlen = A->d_rowlen;
     // value-stream L2 prefetch 128 slices ahead when most rows are patterned (ell_kernels.cu)
@@ -382,7 +380,7 @@ int launch(ellspmv_cuda_matrix *A, double *y_dev, const double *x_dev, int beta,
     if (push) args.push = *push; else args.push.num_peers = 0;
     if (sync) args.sync = *sync;          // only passed for a full launch of a fused_sync_capable handle
     if (A->sg && slice_begin == 0 && num_slices == A->lay.num_slices) {
-        ELL_CK(sg_spmv(A->sg, A->cfg.fma, A->vals, x_dev, y_dev, A->d_ad, A->sd_order, A->lay.num_rows,
+        ELL_CK(sg_spmv(A->sg, x_dev, y_dev, A->d_ad, A->sd_order, A->lay.num_rows,
                        A->row_begin, beta, push, stream, A->d_rowlen));
         A->launches += sg_launches(A->sg);
         return 0;
@@ -427,7 +425,23 @@ int spmv_pipelined(ellspmv_cuda_matrix *A, double *y, const double *x, int beta,
     int64_t xlo, xhi;
     x_range(A, &xlo, &xhi);
     (void)ncols;
-    if (xhi > xlo) ELL_CK(cudaMemcpyAsync(A->d_x + xlo, x + xlo, (size_t)(xhi - xlo) * 8, cudaMemcpyDefault, s));
+    // x goes up in pieces too: before chunk c runs, x is on the device up to the largest column
+    // the chunk references (one-off reduction per handle).  For a banded or stencil matrix the
+    // pieces interleave with the y chunks, so the first kernel starts after 1/32 of the upload
+    // instead of after all of x; for a scattered matrix the first chunk needs everything and this
+    // degenerates to "x first".
+    if ((int)A->chunk_max.size() != nchunks) {
+        long long *d_cm = nullptr;
+        ELL_CK(cudaMalloc(&d_cm, (size_t)nchunks * 8));
+        std::vector<long long> cm((size_t)nchunks, -1);
+        cudaError_t ce = chunk_max_cols(A->dev_idx_bits, A->cols, A->lay, chunk_slices, nchunks, d_cm, s);
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(cm.data(), d_cm, (size_t)nchunks * 8, cudaMemcpyDeviceToHost, s);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
+        cudaFree(d_cm);
+        if (ce != cudaSuccess) ELL_FAIL(cuda_to_errno(ce), "chunk column ranges: %s", cudaGetErrorString(ce));
+        A->chunk_max.swap(cm);
+    }
+    int64_t up_hi = xlo;                       // x[xlo, up_hi) is on the device (or on its way, in stream order)
     int used = 0;
     for (int c = 0; c < nchunks; c++) {
         const int64_t s0 = c * chunk_slices;
@@ -435,6 +449,13 @@ int spmv_pipelined(ellspmv_cuda_matrix *A, double *y, const double *x, int beta,
         const int64_t ns = (slices - s0 < chunk_slices) ? slices - s0 : chunk_slices;
         const int64_t r0 = s0 * S;
         const int64_t r1 = (r0 + ns * S < rows) ? r0 + ns * S : rows;
+        int64_t need = A->chunk_max[(size_t)c] + 1;
+        if (A->d_ad && A->row_begin + r1 > need) need = A->row_begin + r1;      // ad[i] * x[global row i]
+        if (c == nchunks - 1 || need > xhi) need = xhi;
+        if (need > up_hi) {
+            ELL_CK(cudaMemcpyAsync(A->d_x + up_hi, x + up_hi, (size_t)(need - up_hi) * 8, cudaMemcpyDefault, s));
+            up_hi = need;
+        }
         if (beta) ELL_CK(cudaMemcpyAsync(A->d_y + r0, y + r0, (size_t)(r1 - r0) * 8, cudaMemcpyDefault, s));
         ELL_CK(cudaEventRecord(A->events[2 * c], s));
         if ((err = launch(A, A->d_y, A->d_x, beta, nullptr, s, s0, ns))) return err;
@@ -1377,6 +1398,7 @@ int csrspmv_cuda_get_info(const csrspmv_cuda_matrix *A, csrspmv_cuda_info *info)
         info->sell_slots = sell_entries(S->sell);
         info->sell_real = sell_real_entries(S->sell);
         info->sell_long_rows = sell_long_rows(S->sell);
+        info->sell_long_len = sell_long_row(S->sell);
         info->launches_per_spmv = sell_launches(S->sell);
     }
     if (S->ell) {

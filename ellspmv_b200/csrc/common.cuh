@@ -102,8 +102,8 @@ struct EllSpmvArgs {
     int           sd_order; // 0: y += ad*x + yi (ellgemvsd); 1: sum starts at ad*x (ellgemv16sd)
     PushTargets   push;
     int           prefetch;     // slices ahead whose value stream is requested into L2 (0 = none)
-    const unsigned char *patid; // offset patterns (pattern.cu): one id per warp (32*R rows), 0xff = explicit indices; or NULL
-    const unsigned      *patmask; // per patterned warp: lanes whose rows deviate and read the explicit indices
+    const unsigned long long *patid; // offset patterns (pattern.cu), one word per warp (32*R rows): low byte = pattern id
+                                //   (0xff = explicit indices), high half = lanes whose rows deviate; or NULL
     const long long     *pat;   // dictionary [kMaxPatterns][K] of column offsets relative to the GLOBAL row
     StepSync      sync;
     const int    *rowlen;   // per row: how many leading slots count (CSR view: the rest is never touched
@@ -171,13 +171,15 @@ cudaError_t init_minmax(long long *minmax, cudaStream_t stream);
 cudaError_t csr_to_sliced(int src_idx_bits, int dst_idx_bits, const int64_t *rowptr, const void *src_cols,
                           const double *src_vals, void *dst_cols, double *dst_vals, int *rowlen,
                           const EllLayout &lay, cudaStream_t stream);
+cudaError_t chunk_max_cols(int idx_bits, const void *cols, const EllLayout &lay, int64_t chunk_slices, int nchunks,
+                           long long *d_out /* device, nchunks */, cudaStream_t stream);
 cudaError_t mark_remote_slices(int idx_bits, const void *cols, const EllLayout &lay, int64_t lo, int64_t hi,
                                unsigned char *remote, cudaStream_t stream);
 
 // ---- offset patterns: groups of 32 rows whose column indices are row + d[l] (pattern.cu) ----
 struct PatternSet {
     unsigned char *patid = nullptr;   // device: padded_rows / 32 ids
-    unsigned *patmask = nullptr;      // device: per group, the lanes that keep explicit indices (deviating rows)
+    unsigned long long *patinfo = nullptr; // device: per group, id (low byte) | lanes that keep explicit indices << 32
     int64_t explicit_lanes = 0;       // lanes flagged in the masks of the patterned groups
     long long *pat = nullptr;         // device: kMaxPatterns * K offsets
     int num_patterns = 0;
@@ -202,9 +204,9 @@ int64_t cb_entries(const CbMatrix *cb);
 
 // ---- column-blocked, staged gather: bit-exact (ell_staged.cu) ---------------------
 struct SgMatrix;
-cudaError_t sg_build(SgMatrix **out, int idx_bits, const void *cols, const EllLayout &lay, int64_t num_columns,
-                     int64_t target_x_bytes, cudaStream_t stream);
-cudaError_t sg_spmv(const SgMatrix *sg, bool fma, const double *vals, const double *x, double *y, const double *ad,
+cudaError_t sg_build(SgMatrix **out, int idx_bits, const void *cols, const double *vals, const EllLayout &lay,
+                     int64_t num_columns, int64_t target_x_bytes, cudaStream_t stream);
+cudaError_t sg_spmv(const SgMatrix *sg, const double *x, double *y, const double *ad,
                     int sd_order, int64_t num_rows, int64_t row_begin, int beta, const PushTargets *push,
                     cudaStream_t stream, const int *rowlen = nullptr);
 cudaError_t sg_scatter_estimate(int idx_bits, const void *cols, const EllLayout &lay, double *lines_per_gather,
@@ -229,6 +231,7 @@ int64_t sell_entries(const SellMatrix *m);        // stored slots
 int64_t sell_real_entries(const SellMatrix *m);   // slots that count
 int64_t sell_long_rows(const SellMatrix *m);
 int sell_launches(const SellMatrix *m);
+int sell_long_row(const SellMatrix *m);       // rows longer than this run one CTA each (0: none)
 
 // ---- COO -> ELL / CSR on the device (convert.cu) ------------------------------
 struct CooEllJob {

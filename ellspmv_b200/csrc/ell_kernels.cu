@@ -219,21 +219,22 @@ ell_thread_kernel(const EllSpmvArgs a)
     // A patterned group may hold a few lanes whose rows deviate from its pattern (a grid
     // boundary); they are flagged in the group's mask.  The main loop below stays the plain
     // warp-uniform two-way branch: a flagged lane runs along on the columns of the group's first
-    // regular lane (valid addresses, its result is thrown away) and then recomputes its own rows
-    // from the explicit index stream in a short divergent tail -- K sectors of 32 bytes for that
-    // lane instead of the whole group's 128/256-byte lines.
-    bool flagged = false;
+    // regular lane (valid addresses, its result is thrown away); afterwards the WHOLE warp
+    // recomputes each flagged row from the explicit index stream -- lane l loads slot l, the rounded
+    // products are handed to everybody by shuffles and added in slot order -- one round of loads
+    // per 32 slots instead of the group's 128/256-byte index line per slot.
+    unsigned pmask = 0;           // warp-uniform: the lanes of this group that deviate
     int64_t rowp = rowg;          // the row the pattern's offsets are applied to
     if (PAT) {
         const int64_t grp = (slice * kBlockThreads + threadIdx.x) >> 5;
-        const unsigned pid = __ldg(a.patid + grp);
+        const unsigned long long info = __ldg(a.patid + grp);      // id and mask in one load
+        const unsigned pid = (unsigned)(info & 0xffull);
         if (pid != 0xffu) {
             prow = a.pat + (int64_t)pid * K;
-            const unsigned m = __ldg(a.patmask + grp);
-            if (m != 0u) {
-                const int64_t lead = __shfl_sync(0xffffffffu, rowg, __ffs(~m) - 1);
-                flagged = (m >> (threadIdx.x & 31)) & 1u;
-                if (flagged) rowp = lead;
+            pmask = (unsigned)(info >> 32);
+            if (pmask != 0u) {
+                const int64_t lead = __shfl_sync(0xffffffffu, rowg, __ffs(~pmask) - 1);
+                if ((pmask >> (threadIdx.x & 31)) & 1u) rowp = lead;
             }
         }
     }
@@ -343,17 +344,38 @@ ell_thread_kernel(const EllSpmvArgs a)
         }
     }
 
-    // the flagged lanes of a patterned group: their rows again, from the explicit indices
-    if (PAT && flagged) {
+    // the flagged lanes of a patterned group: their rows again, from the explicit indices, by the
+    // whole warp (warp-uniform control flow: pmask is the same in every lane)
+    if (PAT && pmask != 0u) {
+        const int lane = threadIdx.x & 31;
+        for (unsigned rest = pmask; rest != 0u; rest &= rest - 1) {
+            const int fl = __ffs(rest) - 1;
+            // element (row of lane fl, slot 0) of this slice: lanes are R rows apart
+            const int64_t fbase = base + (int64_t)(fl - lane) * R;
 #pragma unroll
-        for (int r = 0; r < R; r++) acc[r] = (ad && a.sd_order) ? dx[r] : 0.0;
+            for (int r = 0; r < R; r++) {
+                double accf = __shfl_sync(0xffffffffu, (ad && a.sd_order) ? dx[r] : 0.0, fl);
 #pragma unroll 1
-        for (int l = 0; l < K; l++) {
-            double v[R]; int64_t c[R];
-            Vals<R>::ld(vp + (int64_t)l * S, v);
-            Cols<IdxT, R>::ld(cp + (int64_t)l * S, c);
-#pragma unroll
-            for (int r = 0; r < R; r++) acc[r] = madd<FMA>(acc[r], v[r], ldx<G>(x + c[r]));
+                for (int l0 = 0; l0 < K; l0 += 32) {
+                    const int l = l0 + lane;
+                    double pv = 0.0, px = 0.0;
+                    if (l < K) {
+                        double v1[1]; int64_t c1[1];
+                        Vals<1>::ld(a.vals + fbase + r + (int64_t)l * S, v1);
+                        Cols<IdxT, 1>::ld(reinterpret_cast<const IdxT *>(a.cols) + fbase + r + (int64_t)l * S, c1);
+                        pv = v1[0];
+                        px = ldx<G>(x + c1[0]);
+                        if (!FMA) pv = __dmul_rn(pv, px);          // the rounded product, as in madd
+                    }
+                    const int n = K - l0 < 32 ? K - l0 : 32;
+                    for (int j = 0; j < n; j++) {
+                        const double vj = __shfl_sync(0xffffffffu, pv, j);
+                        if (FMA) accf = __fma_rn(vj, __shfl_sync(0xffffffffu, px, j), accf);
+                        else accf = __dadd_rn(accf, vj);
+                    }
+                }
+                if (lane == fl) acc[r] = accf;
+            }
         }
     }
 

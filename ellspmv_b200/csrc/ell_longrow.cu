@@ -110,12 +110,23 @@ ell_longrow_kernel(const EllSpmvArgs a, int rshift)
         issue_vc(t + 2, v2, c2);
         if (summer) {
             const int n = (len - (t << tshift) < T_row) ? len - (t << tshift) : T_row;   // may be <= 0: nothing left
+            // the next 8 operands leave shared memory while the current 8 are being added: the chain
+            // runs at the DADD latency, not DADD + LDS
             const double *q = p + tid * (T_row + 1);
             int l = 0;
-            for (; l + 8 <= n; l += 8) {
+            if (n >= 8) {
                 double w[8];
 #pragma unroll
-                for (int j = 0; j < 8; j++) w[j] = q[l + j];
+                for (int j = 0; j < 8; j++) w[j] = q[j];
+                for (l = 8; l + 8 <= n; l += 8) {
+                    double wn[8];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) wn[j] = q[l + j];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) acc = __dadd_rn(acc, w[j]);
+#pragma unroll
+                    for (int j = 0; j < 8; j++) w[j] = wn[j];
+                }
 #pragma unroll
                 for (int j = 0; j < 8; j++) acc = __dadd_rn(acc, w[j]);
             }

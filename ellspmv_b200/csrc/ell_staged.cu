@@ -10,18 +10,24 @@
 // instead, so that the arithmetic keeps the reference's exact order
 // (ellspmv.c:1146-1151):
 //
-//   phase 1 (gather): the column indices are stored a second time, sorted by
-//     (column block, slice).  One launch per column block walks its run of
-//     indices -- a flat, perfectly coalesced stream -- gathers x[col] -- the live
-//     part of x is then that block's slice (<= 48 MB), which stays in L2 -- and
-//     writes the gathered values as a flat stream xg.
-//   phase 2 (sum): one CTA per slice.  For a slice the gathered values are nb
+//   phase 1 (gather + multiply): the entries are stored a second time, sorted by
+//     (column block, slice): column index and value.  One launch per column
+//     block walks its run -- two flat, perfectly coalesced streams -- gathers
+//     x[col] -- the live part of x is then that block's slice (<= 48 MB), which
+//     stays in L2 -- and writes the ROUNDED product a*x (__dmul_rn) as a flat
+//     stream xg.
+//   phase 2 (sum): one CTA per slice.  For a slice the products are nb
 //     contiguous runs of xg (one per column block); one thread fetches them into
 //     shared memory with bulk-async copies (cp.async.bulk + mbarrier, SASS
-//     UBLKCP) while the CTA already loads its first values.  A 16-bit `pos`
-//     stream in the sliced-ELL layout says where entry (row, slot) landed, and
-//     every thread then runs the reference's loop over ITS row, slot 0..K-1,
-//     mul then add: the same roundings as ell_thread_kernel, bit for bit.
+//     UBLKCP).  A 16-bit `pos` stream in the sliced-ELL layout says where entry
+//     (row, slot) landed, and every thread then adds the products of ITS row,
+//     slot 0..K-1, with __dadd_rn: mul, then left-to-right adds -- the same
+//     roundings as ell_thread_kernel, bit for bit.
+//   (Round 1 parked x[col] and multiplied in phase 2; moving the multiplication
+//   takes the 8-byte value stream out of the HBM-bound phase 2 -- 18 -> 10 B per
+//   entry -- into phase 1, which is bound by its gathers, not by HBM:
+//   profiles/r2_staged_gather.md.  ELLSPMV_CUDA_FMA cannot contract here, the
+//   products are parked rounded: tolerance mode gets the exact mode's bits.)
 //
 // Measured on BASELINE config 4 (profiles/r1_staged_gather.md): 13.6 ms against
 // 28.2 ms for the direct gather, same bits.  Phase 2 runs at 103 % of the measured
@@ -58,9 +64,10 @@ struct SgMatrix {
     int slice_rows = 0, rowsize = 0;
     int64_t total = 0;                        // entries of gcols / xg (segments padded to even length)
     void *gcols = nullptr;                    // column indices sorted by (block, slice)
+    double *gvals = nullptr;                  // the values in the same order
     long long *seg = nullptr;                 // num_blocks * num_slices + 1 segment starts
     unsigned short *pos = nullptr;            // sliced-ELL layout: index into the slice's staging buffer
-    double *xg = nullptr;                     // gathered x, same order as gcols
+    double *xg = nullptr;                     // rounded products a*x[col], same order as gcols
     long long run_start[kSgMaxBlocks + 1];    // host copy: where column block b's run starts (seg[b * num_slices])
     int64_t bytes = 0;
     size_t smem = 0;                          // dynamic shared memory of phase 2
@@ -73,7 +80,7 @@ __host__ __device__ __forceinline__ int64_t sg_seg_index(int64_t s, int b, int64
 void sg_free(SgMatrix *sg)
 {
     if (!sg) return;
-    cudaFree(sg->gcols); cudaFree(sg->seg); cudaFree(sg->pos); cudaFree(sg->xg);
+    cudaFree(sg->gcols); cudaFree(sg->gvals); cudaFree(sg->seg); cudaFree(sg->pos); cudaFree(sg->xg);
     delete sg;
 }
 int64_t sg_bytes(const SgMatrix *sg) { return sg ? sg->bytes : 0; }
@@ -97,8 +104,9 @@ sg_count_kernel(const IdxT *__restrict__ cols, int S, int K, int nb, int64_t blo
 
 template <typename IdxT>
 __global__ void __launch_bounds__(kBlockThreads)
-sg_fill_kernel(const IdxT *__restrict__ cols, int S, int K, int nb, int64_t block_cols, int64_t ns,
-               const long long *__restrict__ seg, IdxT *__restrict__ gcols, unsigned short *__restrict__ pos)
+sg_fill_kernel(const IdxT *__restrict__ cols, const double *__restrict__ vals, int S, int K, int nb, int64_t block_cols,
+               int64_t ns, const long long *__restrict__ seg, IdxT *__restrict__ gcols, double *__restrict__ gvals,
+               unsigned short *__restrict__ pos)
 {
     __shared__ int cursor[kSgMaxBlocks];
     __shared__ int prefix[kSgMaxBlocks];
@@ -122,12 +130,13 @@ sg_fill_kernel(const IdxT *__restrict__ cols, int S, int K, int nb, int64_t bloc
         const int b = (int)((int64_t)c / block_cols);
         const int r = atomicAdd(&cursor[b], 1);
         gcols[start[b] + r] = c;
+        gvals[start[b] + r] = vals[base + i];
         pos[base + i] = (unsigned short)(prefix[b] + r);
     }
 }
 
 template <typename IdxT>
-static cudaError_t sg_build_typed(SgMatrix *sg, const IdxT *cols, cudaStream_t stream)
+static cudaError_t sg_build_typed(SgMatrix *sg, const IdxT *cols, const double *vals, cudaStream_t stream)
 {
     const int64_t ns = sg->num_slices, n = (int64_t)sg->num_blocks * ns;
     const int S = sg->slice_rows, K = sg->rowsize, nb = sg->num_blocks;
@@ -155,14 +164,16 @@ static cudaError_t sg_build_typed(SgMatrix *sg, const IdxT *cols, cudaStream_t s
     const size_t ne = (size_t)sg->total + 8;                 // slack: phase 1 loads indices in aligned groups of 4
     const size_t nk = (size_t)ns * S * K;
     if ((e = cudaMalloc(&sg->gcols, ne * sizeof(IdxT))) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&sg->gvals, ne * 8)) != cudaSuccess) return e;
     if ((e = cudaMalloc(&sg->pos, nk * 2)) != cudaSuccess) return e;
     if ((e = cudaMalloc(&sg->xg, ne * 8)) != cudaSuccess) return e;
-    sg->bytes = (int64_t)(ne * (sizeof(IdxT) + 8) + nk * 2 + (size_t)(n + 1) * 8);
-    // the padding entry of an odd segment gathers x[0]
+    sg->bytes = (int64_t)(ne * (sizeof(IdxT) + 16) + nk * 2 + (size_t)(n + 1) * 8);
+    // the padding entry of an odd segment gathers x[0] and multiplies it by 0; nobody reads the product
     if ((e = cudaMemsetAsync(sg->gcols, 0, ne * sizeof(IdxT), stream)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(sg->gvals, 0, ne * 8, stream)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(sg->xg, 0, ne * 8, stream)) != cudaSuccess) return e;
-    sg_fill_kernel<IdxT><<<(unsigned)ns, kBlockThreads, 0, stream>>>(cols, S, K, nb, sg->block_cols, ns, sg->seg,
-                                                                      (IdxT *)sg->gcols, sg->pos);
+    sg_fill_kernel<IdxT><<<(unsigned)ns, kBlockThreads, 0, stream>>>(cols, vals, S, K, nb, sg->block_cols, ns, sg->seg,
+                                                                      (IdxT *)sg->gcols, sg->gvals, sg->pos);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     return cudaStreamSynchronize(stream);
 }
@@ -219,15 +230,15 @@ cudaError_t sg_scatter_estimate(int idx_bits, const void *cols, const EllLayout 
 // device memory the staged copy of a matrix will take (to check against what is free)
 int64_t sg_bytes_estimate(int idx_bits, const EllLayout &lay)
 {
-    return lay.entries() * (int64_t)(idx_bits / 8 + 10) + (64LL << 20);
+    return lay.entries() * (int64_t)(idx_bits / 8 + 18) + (64LL << 20);
 }
 
 static cudaError_t sg_prepare_kernels();   // per device: allow the large dynamic shared memory
 
 // *out = nullptr (and success) when staging does not apply: x already fits the
 // target, or a slice's gathered values do not fit shared memory / 16-bit positions
-cudaError_t sg_build(SgMatrix **out, int idx_bits, const void *cols, const EllLayout &lay, int64_t num_columns,
-                     int64_t target_x_bytes, cudaStream_t stream)
+cudaError_t sg_build(SgMatrix **out, int idx_bits, const void *cols, const double *vals, const EllLayout &lay,
+                     int64_t num_columns, int64_t target_x_bytes, cudaStream_t stream)
 {
     *out = nullptr;
     if (lay.num_rows <= 0 || lay.rowsize <= 0 || num_columns <= 0) return cudaSuccess;
@@ -245,8 +256,8 @@ cudaError_t sg_build(SgMatrix **out, int idx_bits, const void *cols, const EllLa
     sg->slice_rows = lay.slice_rows;
     sg->rowsize = lay.rowsize;
     sg->smem = (size_t)(kSgHeader + stage * 8);
-    cudaError_t e = idx_bits == 64 ? sg_build_typed<int64_t>(sg, (const int64_t *)cols, stream)
-                                   : sg_build_typed<int32_t>(sg, (const int32_t *)cols, stream);
+    cudaError_t e = idx_bits == 64 ? sg_build_typed<int64_t>(sg, (const int64_t *)cols, vals, stream)
+                                   : sg_build_typed<int32_t>(sg, (const int32_t *)cols, vals, stream);
     if (e == cudaSuccess) e = sg_prepare_kernels();
     if (e != cudaSuccess) { sg_free(sg); return e; }
     *out = sg;
@@ -268,17 +279,22 @@ __device__ __forceinline__ void ld4(const int64_t *p, int64_t (&c)[4])
 
 template <typename IdxT>
 __global__ void __launch_bounds__(256)
-sg_gather_kernel(const IdxT *__restrict__ gcols, const double *__restrict__ x, double *__restrict__ xg,
-                 int64_t lo, int64_t hi /* run [lo, hi), both even */)
+sg_gather_kernel(const IdxT *__restrict__ gcols, const double *__restrict__ gvals, const double *__restrict__ x,
+                 double *__restrict__ xg, int64_t lo, int64_t hi /* run [lo, hi), both even */)
 {
     const int64_t e = ((lo >> 2) + blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * 4;
     if (e >= hi) return;
     int64_t c[4];
     ld4(gcols + e, c);                                   // aligned group of 4 (the arrays carry slack)
+    const double2 a01 = __ldcs(reinterpret_cast<const double2 *>(gvals + e));
+    const double2 a23 = __ldcs(reinterpret_cast<const double2 *>(gvals + e) + 1);
     const bool on0 = e >= lo, on1 = e + 2 < hi;          // which of the two pairs belong to this run
     double v[4] = {0.0, 0.0, 0.0, 0.0};
     if (on0) { v[0] = __ldg(x + c[0]); v[1] = __ldg(x + c[1]); }
     if (on1) { v[2] = __ldg(x + c[2]); v[3] = __ldg(x + c[3]); }
+    // the reference's multiplication, rounded on its own (mul, THEN add: ellspmv.c:1150 as compiled)
+    v[0] = __dmul_rn(a01.x, v[0]); v[1] = __dmul_rn(a01.y, v[1]);
+    v[2] = __dmul_rn(a23.x, v[2]); v[3] = __dmul_rn(a23.y, v[3]);
     // one 256-bit store per group (SASS STG.E.EF.256): a lane writes a whole 32-byte sector.  Two
     // 16-byte halves -- what this kernel did first -- half-fill 32 sectors per instruction and cost
     // 0.6 gathers' worth of SM->L2 traffic per entry (176 -> 219 G gathers/s, profiles/r2_phase1_lab.md);
@@ -291,12 +307,11 @@ sg_gather_kernel(const IdxT *__restrict__ gcols, const double *__restrict__ x, d
     }
 }
 
-// ---- phase 2: the reference's row loop over staged x values ------------------------
+// ---- phase 2: the reference's row sums over the staged products ------------------------
 __device__ __forceinline__ uint32_t sg_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-template <bool FMA>
 __global__ void
-sg_sum_kernel(const double *__restrict__ vals, const unsigned short *__restrict__ pos, const long long *__restrict__ seg,
+sg_sum_kernel(const unsigned short *__restrict__ pos, const long long *__restrict__ seg,
               const double *__restrict__ xg, const double *__restrict__ x, double *__restrict__ y,
               const double *__restrict__ ad, int sd_order, int64_t num_rows, int64_t row_begin, int64_t ns,
               int nb, int K, int beta, const PushTargets push, const int *__restrict__ rowlen)
@@ -339,7 +354,6 @@ sg_sum_kernel(const double *__restrict__ vals, const unsigned short *__restrict_
     const int64_t row = s * S + tid;
     const bool live = row < num_rows;
     const int64_t base = s * S * (int64_t)K + tid;
-    const double *vp = vals + base;
     const unsigned short *pp = pos + base;
     double yold = 0.0, dx = 0.0;
     // CSR view: only the first rowlen[row] slots enter the arithmetic (see ell_thread_kernel's LEN)
@@ -347,13 +361,11 @@ sg_sum_kernel(const double *__restrict__ vals, const unsigned short *__restrict_
     if (live && beta) yold = y[row];
     if (live && ad) dx = __dmul_rn(ad[row], __ldg(x + row_begin + row));
 
+    // the positions of the first batch travel while the bulk copies land
     constexpr int U = 8;
-    double v[U]; unsigned p[U];
+    unsigned p[U];
 #pragma unroll
-    for (int u = 0; u < U; u++) {
-        v[u] = 0.0; p[u] = 0;
-        if (u < K) { v[u] = __ldcs(vp + (int64_t)u * S); p[u] = __ldcs(pp + (int64_t)u * S); }
-    }
+    for (int u = 0; u < U; u++) p[u] = u < K ? (unsigned)__ldcs(pp + (int64_t)u * S) : 0u;
     __syncthreads();                       // the barrier is initialised before anyone polls it
     {
         uint32_t ok = 0;
@@ -364,40 +376,32 @@ sg_sum_kernel(const double *__restrict__ vals, const unsigned short *__restrict_
         if (!ok) __trap();     // the staged values never arrived: fail the launch loudly instead of summing garbage
     }
 
+    // the reference's additions, slot 0..K-1, over the products phase 1 rounded
     double acc = (ad && sd_order) ? dx : 0.0;
     int l0 = 0;
 #pragma unroll 1
     for (; l0 + U <= K; l0 += U) {
-        double vn[U]; unsigned pn[U];
+        unsigned pn[U];
         const bool more = l0 + 2 * U <= K;
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-            vn[u] = 0.0; pn[u] = 0;
-            if (more) { vn[u] = __ldcs(vp + (int64_t)(l0 + U + u) * S); pn[u] = __ldcs(pp + (int64_t)(l0 + U + u) * S); }
-        }
+        for (int u = 0; u < U; u++) pn[u] = more ? (unsigned)__ldcs(pp + (int64_t)(l0 + U + u) * S) : 0u;
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-            const double xv = stage[p[u]];
-            if (l0 + u < len) acc = FMA ? __fma_rn(v[u], xv, acc) : __dadd_rn(acc, __dmul_rn(v[u], xv));
-        }
+        for (int u = 0; u < U; u++)
+            if (l0 + u < len) acc = __dadd_rn(acc, stage[p[u]]);
 #pragma unroll
-        for (int u = 0; u < U; u++) { v[u] = vn[u]; p[u] = pn[u]; }
+        for (int u = 0; u < U; u++) p[u] = pn[u];
     }
     if (l0 < K) {
         // K % U leftover slots; for K < U they sit in the preloaded registers
         if (l0 == 0) {
 #pragma unroll
             for (int u = 0; u < U; u++)
-                if (u < K && u < len) {
-                    const double xv = stage[p[u]];
-                    acc = FMA ? __fma_rn(v[u], xv, acc) : __dadd_rn(acc, __dmul_rn(v[u], xv));
-                }
+                if (u < K && u < len) acc = __dadd_rn(acc, stage[p[u]]);
         } else {
 #pragma unroll 1
             for (; l0 < K; l0++) {
-                const double xv = stage[__ldcs(pp + (int64_t)l0 * S)];
-                const double vv = __ldcs(vp + (int64_t)l0 * S);
-                if (l0 < len) acc = FMA ? __fma_rn(vv, xv, acc) : __dadd_rn(acc, __dmul_rn(vv, xv));
+                const double pr = stage[__ldcs(pp + (int64_t)l0 * S)];
+                if (l0 < len) acc = __dadd_rn(acc, pr);
             }
         }
     }
@@ -414,12 +418,10 @@ sg_sum_kernel(const double *__restrict__ vals, const unsigned short *__restrict_
 
 static cudaError_t sg_prepare_kernels()
 {
-    cudaError_t e = cudaFuncSetAttribute(sg_sum_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSgMaxSmem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(sg_sum_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSgMaxSmem);
-    return e;
+    return cudaFuncSetAttribute(sg_sum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSgMaxSmem);
 }
 
-cudaError_t sg_spmv(const SgMatrix *sg, bool fma, const double *vals, const double *x, double *y, const double *ad,
+cudaError_t sg_spmv(const SgMatrix *sg, const double *x, double *y, const double *ad,
                     int sd_order, int64_t num_rows, int64_t row_begin, int beta, const PushTargets *push,
                     cudaStream_t stream, const int *rowlen)
 {
@@ -433,16 +435,15 @@ cudaError_t sg_spmv(const SgMatrix *sg, bool fma, const double *vals, const doub
         const int64_t groups = (hi + 3) / 4 - lo / 4;
         const unsigned grid = (unsigned)((groups + 255) / 256);
         if (sg->idx_bits == 64)
-            sg_gather_kernel<int64_t><<<grid, 256, 0, stream>>>((const int64_t *)sg->gcols, x, sg->xg, lo, hi);
+            sg_gather_kernel<int64_t><<<grid, 256, 0, stream>>>((const int64_t *)sg->gcols, sg->gvals, x, sg->xg, lo, hi);
         else
-            sg_gather_kernel<int32_t><<<grid, 256, 0, stream>>>((const int32_t *)sg->gcols, x, sg->xg, lo, hi);
+            sg_gather_kernel<int32_t><<<grid, 256, 0, stream>>>((const int32_t *)sg->gcols, sg->gvals, x, sg->xg, lo, hi);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }
     // phase 2
-    auto kernel = fma ? sg_sum_kernel<true> : sg_sum_kernel<false>;
-    kernel<<<(unsigned)sg->num_slices, sg->slice_rows, sg->smem, stream>>>(
-        vals, sg->pos, sg->seg, sg->xg, x, y, ad, sd_order, num_rows, row_begin, sg->num_slices, sg->num_blocks,
+    sg_sum_kernel<<<(unsigned)sg->num_slices, sg->slice_rows, sg->smem, stream>>>(
+        sg->pos, sg->seg, sg->xg, x, y, ad, sd_order, num_rows, row_begin, sg->num_slices, sg->num_blocks,
         sg->rowsize, beta, pt, rowlen);
     return cudaGetLastError();
 }

@@ -47,6 +47,7 @@ struct ellspmv_cuda_matrix {
     cudaStream_t stream = nullptr;
     cudaStream_t stream_out = nullptr;       // D2H stream of the pipelined host call
     double *d_x = nullptr, *d_y = nullptr;   // vectors of the host-facing spmv
+    std::vector<long long> chunk_max;        // pipelined host call: largest column each row chunk references
     int64_t vec_len = 0;
     std::vector<cudaEvent_t> events;
     int64_t device_bytes = 0;

@@ -380,4 +380,36 @@ cudaError_t csr_to_sliced(int src_idx_bits, int dst_idx_bits, const int64_t *row
     return cudaGetLastError();
 }
 
+// ---- largest column each row chunk of the pipelined host call references (api.cu) -------------
+template <typename IdxT>
+__global__ void __launch_bounds__(kBlockThreads)
+chunk_max_kernel(const IdxT *__restrict__ cols, EllLayout lay, int64_t chunk_slices, long long *__restrict__ out)
+{
+    const int64_t s = blockIdx.x;
+    const int n = lay.slice_rows * lay.rowsize;
+    const IdxT *c = cols + s * (int64_t)n;
+    long long best = -1;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const long long v = (long long)c[i];
+        best = v > best ? v : best;
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        const long long o = __shfl_xor_sync(0xffffffffu, best, off);
+        best = o > best ? o : best;
+    }
+    if ((threadIdx.x & 31) == 0) atomicMax(out + s / chunk_slices, best);
+}
+
+cudaError_t chunk_max_cols(int idx_bits, const void *cols, const EllLayout &lay, int64_t chunk_slices, int nchunks,
+                           long long *d_out, cudaStream_t stream)
+{
+    cudaError_t e = cudaMemsetAsync(d_out, 0xff, (size_t)nchunks * 8, stream);      // -1
+    if (e != cudaSuccess || lay.num_slices <= 0) return e;
+    if (idx_bits == 64)
+        chunk_max_kernel<int64_t><<<(unsigned)lay.num_slices, kBlockThreads, 0, stream>>>((const int64_t *)cols, lay, chunk_slices, d_out);
+    else
+        chunk_max_kernel<int32_t><<<(unsigned)lay.num_slices, kBlockThreads, 0, stream>>>((const int32_t *)cols, lay, chunk_slices, d_out);
+    return cudaGetLastError();
+}
+
 }  // namespace ellspmv

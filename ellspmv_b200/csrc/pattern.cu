@@ -16,7 +16,9 @@
 // on the pattern: up to kPatMaxExplicit of its 32 lanes may deviate; they are flagged in a
 // 32-bit mask per group and read their own indices from the explicit stream (one 32-byte
 // sector per slot instead of the group's whole 128/256-byte line), the other lanes compute
-// theirs.  27-point 384^3: 83 % -> 99.5 % of the rows stop streaming indices.
+// theirs.  27-point 384^3: 83 % -> 99.5 % of the rows stop streaming indices.  The kernel reads id and
+// mask as ONE 64-bit word per warp: a second, dependent load at the head of every warp cost more
+// than the index bytes the masks save (profiles/r2_offset_patterns.md).
 //
 // This is a device-layout choice like the 64->32-bit index narrowing: the column
 // used for every entry is the stored one (every group is verified against the
@@ -132,7 +134,7 @@ __global__ void __launch_bounds__(256)
 pat_classify_kernel(const IdxT *__restrict__ cols, EllLayout lay, int R, int64_t row_begin, int64_t num_groups,
                     const unsigned long long *__restrict__ sig, PatHashes hashes, int npat,
                     const long long *__restrict__ pat, unsigned char *__restrict__ patid,
-                    unsigned *__restrict__ patmask, unsigned long long *__restrict__ covered)
+                    unsigned long long *__restrict__ patinfo, unsigned long long *__restrict__ covered)
 {
     const int lane = threadIdx.x & 31;
     const int64_t g = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
@@ -155,7 +157,8 @@ pat_classify_kernel(const IdxT *__restrict__ cols, EllLayout lay, int R, int64_t
     }
     if (lane == 0) {
         patid[g] = ok ? (unsigned char)p : (unsigned char)0xff;
-        patmask[g] = ok ? mask : 0u;
+        // what the kernel reads, ONE load per warp: pattern id in the low byte, lane mask on top
+        patinfo[g] = ok ? (((unsigned long long)mask << 32) | (unsigned long long)p) : 0xffull;
         if (ok) { atomicAdd(covered, 1ull); atomicAdd(covered + 1, (unsigned long long)__popc(mask)); }
     }
 }
@@ -209,7 +212,7 @@ cudaError_t pattern_build_typed(PatternSet *ps, const IdxT *cols, const EllLayou
     if ((e = cudaMalloc(&covered, 16)) != cudaSuccess) { cleanup(); return e; }
     if ((e = cudaMalloc(&ps->pat, (size_t)kMaxPatterns * K * 8)) != cudaSuccess) { cleanup(); return e; }
     if ((e = cudaMalloc(&ps->patid, (size_t)groups)) != cudaSuccess) { cleanup(); return e; }
-    if ((e = cudaMalloc(&ps->patmask, (size_t)groups * sizeof(unsigned))) != cudaSuccess) { cleanup(); return e; }
+    if ((e = cudaMalloc(&ps->patinfo, (size_t)groups * sizeof(unsigned long long))) != cudaSuccess) { cleanup(); return e; }
     if ((e = cudaMemcpyAsync(reps, hreps, sizeof(hreps), cudaMemcpyHostToDevice, stream)) != cudaSuccess ||
         (e = cudaMemsetAsync(covered, 0, 16, stream)) != cudaSuccess ||
         (e = cudaMemsetAsync(ps->pat, 0, (size_t)kMaxPatterns * K * 8, stream)) != cudaSuccess) { cleanup(); return e; }
@@ -217,7 +220,7 @@ cudaError_t pattern_build_typed(PatternSet *ps, const IdxT *cols, const EllLayou
                                                        npat, ps->pat);
     if ((e = cudaGetLastError()) != cudaSuccess) { cleanup(); return e; }
     pat_classify_kernel<IdxT><<<grid, 256, 0, stream>>>(cols, lay, R, row_begin, groups, sig, hashes, npat, ps->pat,
-                                                        ps->patid, ps->patmask, covered);
+                                                        ps->patid, ps->patinfo, covered);
     unsigned long long hc[2] = {0, 0};
     if ((e = cudaGetLastError()) != cudaSuccess ||
         (e = cudaMemcpyAsync(hc, covered, 16, cudaMemcpyDeviceToHost, stream)) != cudaSuccess ||
@@ -228,7 +231,7 @@ cudaError_t pattern_build_typed(PatternSet *ps, const IdxT *cols, const EllLayou
     ps->group_rows = 32 * R;
     ps->covered = (int64_t)hc[0];
     ps->explicit_lanes = (int64_t)hc[1];
-    ps->bytes = groups * 5 + (int64_t)kMaxPatterns * K * 8;
+    ps->bytes = groups * 9 + (int64_t)kMaxPatterns * K * 8;
     return cudaSuccess;
 }
 
@@ -237,7 +240,7 @@ cudaError_t pattern_build_typed(PatternSet *ps, const IdxT *cols, const EllLayou
 void pattern_free(PatternSet *ps)
 {
     cudaFree(ps->patid);
-    cudaFree(ps->patmask);
+    cudaFree(ps->patinfo);
     cudaFree(ps->pat);
     *ps = PatternSet{};
 }

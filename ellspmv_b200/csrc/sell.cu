@@ -14,15 +14,19 @@
 //     rounding sequence; slots past a row's end are never touched arithmetically, so there is no
 //     0*inf from padding and the result equals csrgemv's bits also for non-finite x;
 //   * y is read and written through the row permutation (scattered inside one 32 KB window);
-//   * rows longer than kSellLongRow entries (a power-law tail) would still serialise a whole
-//     warp: they are left out of the slices and run afterwards one CTA per row, all threads
-//     streaming + gathering, rounded products parked in shared memory, one thread adding them in
-//     order (the scheme of ell_longrow.cu) -- reading the CSR arrays in place.
+//   * rows longer than 256 entries (a power-law tail) would still set the width of their slice
+//     (128 rows x the longest one) and serialise a warp: they are left out of the slices and run
+//     one CTA per row -- all threads streaming + gathering, rounded products parked in shared
+//     memory, one thread adding them in order (the scheme of ell_longrow.cu), reading the CSR
+//     arrays in place -- on a second stream NEXT TO the slice kernel: a row of 200 000 entries is
+//     a 1.4 ms chain of dependent additions whoever runs it, and it now hides behind the slices.
 //
 // Used by the CSR path (KERNEL_AUTO with unbalanced rows, api.cu: csr_build_sell) and, opt-in, by
 // the ELL path (ELLSPMV_CUDA_SKIP_PADDING: a row's trailing reference padding -- column
 // min(i, ncols-1), value 0.0 -- is cut off; exact for finite x, differs where x is non-finite on a
 // padding column, which is why it is opt-in there).
+#include <stdlib.h>
+
 #include <cub/cub.cuh>
 
 #include "common.cuh"
@@ -31,7 +35,7 @@ namespace ellspmv {
 
 constexpr int kSellSlice = 128;              // rows per slice = threads per CTA
 constexpr int kSellWindow = 4096;            // sigma: rows sorted by length inside windows of this size
-constexpr int kSellLongRow = 4096;           // CSR rows longer than this run one CTA per row
+constexpr int kSellLongRowDefault = 256;     // CSR rows longer than this run one CTA per row (SELL_LONG_ROW overrides)
 
 struct SellMatrix {
     int idx_bits = 32;
@@ -46,6 +50,9 @@ struct SellMatrix {
     int64_t num_long = 0;
     long long *long_rows = nullptr;          // rows run by the CTA-per-row kernel
     double *long_sum = nullptr;              // their row sums, parked between the kernels of one SpMV
+    int long_row = 0;                        // the length from which a row counts as long (0: none do)
+    cudaStream_t side = nullptr;             // the long rows run here, next to the slices on the caller's stream
+    cudaEvent_t fork = nullptr, join = nullptr;
     int64_t bytes = 0;
 };
 
@@ -54,6 +61,9 @@ void sell_free(SellMatrix *m)
     if (!m) return;
     cudaFree(m->slice_ptr); cudaFree(m->rowlen); cudaFree(m->perm); cudaFree(m->cols); cudaFree(m->vals);
     cudaFree(m->long_rows); cudaFree(m->long_sum);
+    if (m->side) cudaStreamDestroy(m->side);
+    if (m->fork) cudaEventDestroy(m->fork);
+    if (m->join) cudaEventDestroy(m->join);
     delete m;
 }
 int64_t sell_bytes(const SellMatrix *m) { return m ? m->bytes : 0; }
@@ -61,6 +71,7 @@ int64_t sell_entries(const SellMatrix *m) { return m ? m->entries : 0; }
 int64_t sell_real_entries(const SellMatrix *m) { return m ? m->real_entries : 0; }
 int64_t sell_long_rows(const SellMatrix *m) { return m ? m->num_long : 0; }
 int sell_launches(const SellMatrix *m) { return m ? 1 + (m->num_long > 0 ? 2 : 0) : 0; }
+int sell_long_row(const SellMatrix *m) { return m ? m->long_row : 0; }
 
 // ---- where a row's entries live ----------------------------------------------------------------
 struct CsrSource {                             // CSR arrays: row i at [rowptr[i], rowptr[i+1])
@@ -236,10 +247,14 @@ static cudaError_t sell_build_typed(SellMatrix *m, Src src, const SrcI *src_cols
         if ((e = cudaMemsetAsync(stats + 2, 0, 8, stream)) != cudaSuccess) { cleanup(); return e; }
         sell_long_list_kernel<Src><<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(src, n, long_row, m->long_rows, stats + 2);
         if ((e = cudaGetLastError()) != cudaSuccess) { cleanup(); return e; }
+        if ((e = cudaStreamCreateWithFlags(&m->side, cudaStreamNonBlocking)) != cudaSuccess ||
+            (e = cudaEventCreateWithFlags(&m->fork, cudaEventDisableTiming)) != cudaSuccess ||
+            (e = cudaEventCreateWithFlags(&m->join, cudaEventDisableTiming)) != cudaSuccess) { cleanup(); return e; }
     }
     e = cudaStreamSynchronize(stream);
     cleanup();
     m->idx_bits = dst_idx_bits;
+    m->long_row = long_row;
     m->bytes = (int64_t)(ne * (ib + 8)) + m->padded_rows * 8 + (m->num_slices + 1) * 8 + m->num_long * 16;
     return e;
 }
@@ -255,9 +270,11 @@ cudaError_t sell_build_csr(SellMatrix **out, int src_idx_bits, int dst_idx_bits,
     if (!m) return cudaErrorMemoryAllocation;
     m->num_rows = num_rows;
     CsrSource src{rowptr};
+    int long_row = kSellLongRowDefault;
+    if (const char *env = getenv("SELL_LONG_ROW")) { const int v = atoi(env); if (v >= 32) long_row = v; }
     cudaError_t e = src_idx_bits == 64
-        ? sell_build_typed<CsrSource, int64_t>(m, src, (const int64_t *)cols, vals, dst_idx_bits, kSellLongRow, stream)
-        : sell_build_typed<CsrSource, int32_t>(m, src, (const int32_t *)cols, vals, dst_idx_bits, kSellLongRow, stream);
+        ? sell_build_typed<CsrSource, int64_t>(m, src, (const int64_t *)cols, vals, dst_idx_bits, long_row, stream)
+        : sell_build_typed<CsrSource, int32_t>(m, src, (const int32_t *)cols, vals, dst_idx_bits, long_row, stream);
     if (e != cudaSuccess) { sell_free(m); return e; }
     *out = m;
     return cudaSuccess;
@@ -342,12 +359,37 @@ sell_spmv_kernel(const double *__restrict__ vals, const IdxT *__restrict__ cols,
 // parked in shared memory, thread 0 adds them in order (the scheme of ell_longrow.cu, reading the
 // CSR arrays in place).  The row sums are parked in long_sum; sell_long_finish_kernel applies
 // them to y after the slice kernel, which leaves the y entries of these rows alone.
+// adds n parked products to acc in order; the next 8 operands are fetched from shared memory
+// while the current 8 are being added, so the chain runs at the DADD latency, not DADD + LDS
+__device__ __forceinline__ double sum_in_order(double acc, const double *q, int n)
+{
+    int l = 0;
+    if (n >= 8) {
+        double w[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) w[j] = q[j];
+        for (l = 8; l + 8 <= n; l += 8) {
+            double wn[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) wn[j] = q[l + j];
+#pragma unroll
+            for (int j = 0; j < 8; j++) acc = __dadd_rn(acc, w[j]);
+#pragma unroll
+            for (int j = 0; j < 8; j++) w[j] = wn[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc = __dadd_rn(acc, w[j]);
+    }
+    for (; l < n; l++) acc = __dadd_rn(acc, q[l]);
+    return acc;
+}
+
 template <typename IdxT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 sell_long_kernel(const int64_t *__restrict__ rowptr, const IdxT *__restrict__ cols, const double *__restrict__ vals,
                  const long long *__restrict__ list, const double *__restrict__ x, double *__restrict__ long_sum)
 {
-    constexpr int T = 2048, PER = T / 256;
+    constexpr int NT = 128, T = 1024, PER = T / NT;
     __shared__ double prod[2][T];
     const int64_t row = list[blockIdx.x];
     const int64_t kb = rowptr[row], ke = rowptr[row + 1];
@@ -356,7 +398,7 @@ sell_long_kernel(const int64_t *__restrict__ rowptr, const IdxT *__restrict__ co
     auto issue_vc = [&](int64_t t, double (&v)[PER], int64_t (&c)[PER]) {
 #pragma unroll
         for (int u = 0; u < PER; u++) {
-            const int64_t k = kb + t * T + u * 256 + tid;
+            const int64_t k = kb + t * T + u * NT + tid;
             v[u] = 0.0; c[u] = -1;
             if (t < ntiles && k < ke) { v[u] = __ldcs(vals + k); c[u] = (int64_t)__ldcs(cols + k); }
         }
@@ -373,23 +415,14 @@ sell_long_kernel(const int64_t *__restrict__ rowptr, const IdxT *__restrict__ co
     for (int64_t t = 0; t < ntiles; t++) {
         double *p = prod[t & 1];
 #pragma unroll
-        for (int u = 0; u < PER; u++) p[u * 256 + tid] = __dmul_rn(v1[u], x1[u]);
+        for (int u = 0; u < PER; u++) p[u * NT + tid] = __dmul_rn(v1[u], x1[u]);
         __syncthreads();
 #pragma unroll
         for (int u = 0; u < PER; u++) { v1[u] = v2[u]; x1[u] = c2[u] >= 0 ? __ldg(x + c2[u]) : 0.0; }
         issue_vc(t + 2, v2, c2);
         if (tid == 0) {
             const int64_t left = ke - kb - t * T;
-            const int n = left < T ? (int)left : T;
-            int l = 0;
-            for (; l + 8 <= n; l += 8) {
-                double w[8];
-#pragma unroll
-                for (int j = 0; j < 8; j++) w[j] = p[l + j];
-#pragma unroll
-                for (int j = 0; j < 8; j++) acc = __dadd_rn(acc, w[j]);
-            }
-            for (; l < n; l++) acc = __dadd_rn(acc, p[l]);
+            acc = sum_in_order(acc, p, left < T ? (int)left : T);
         }
     }
     if (tid == 0) long_sum[blockIdx.x] = acc;
@@ -418,11 +451,16 @@ cudaError_t sell_spmv(const SellMatrix *m, bool fma, const int64_t *csr_rowptr, 
     if (!m || m->num_rows <= 0) return cudaSuccess;
     if (m->num_long > 0) {
         if (!csr_rowptr) return cudaErrorInvalidValue;
+        // fork: the long rows need x only; they run on the side stream while the slices run here
+        cudaError_t e = cudaEventRecord(m->fork, stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(m->side, m->fork, 0);
+        if (e != cudaSuccess) return e;
         if (csr_idx_bits == 64)
-            sell_long_kernel<int64_t><<<(unsigned)m->num_long, 256, 0, stream>>>(csr_rowptr, (const int64_t *)csr_cols, csr_vals, m->long_rows, x, m->long_sum);
+            sell_long_kernel<int64_t><<<(unsigned)m->num_long, 128, 0, m->side>>>(csr_rowptr, (const int64_t *)csr_cols, csr_vals, m->long_rows, x, m->long_sum);
         else
-            sell_long_kernel<int32_t><<<(unsigned)m->num_long, 256, 0, stream>>>(csr_rowptr, (const int32_t *)csr_cols, csr_vals, m->long_rows, x, m->long_sum);
-        cudaError_t e = cudaGetLastError();
+            sell_long_kernel<int32_t><<<(unsigned)m->num_long, 128, 0, m->side>>>(csr_rowptr, (const int32_t *)csr_cols, csr_vals, m->long_rows, x, m->long_sum);
+        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaEventRecord(m->join, m->side);
         if (e != cudaSuccess) return e;
     }
     const unsigned grid = (unsigned)m->num_slices;
@@ -436,6 +474,7 @@ cudaError_t sell_spmv(const SellMatrix *m, bool fma, const int64_t *csr_rowptr, 
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     if (m->num_long > 0) {
+        if ((e = cudaStreamWaitEvent(stream, m->join, 0)) != cudaSuccess) return e;      // join
         sell_long_finish_kernel<<<(unsigned)((m->num_long + 127) / 128), 128, 0, stream>>>(m->long_rows, m->long_sum, m->num_long, x, y, ad, row_begin, beta);
         e = cudaGetLastError();
     }

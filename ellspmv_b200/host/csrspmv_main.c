@@ -72,7 +72,10 @@ static void help(FILE *f)
     fprintf(f, "  -v, --verbose             be more verbose\n");
     fprintf(f, "\n");
     fprintf(f, " Options for the CUDA path are:\n");
-    fprintf(f, "  --kernel=thread|warp      row-block streaming (bit-exact, default) or sub-warp-per-row\n");
+    fprintf(f, "  --kernel=auto|stream|scalar|sell|warp\n");
+    fprintf(f, "                            auto (default): a sliced-ELL view for balanced rows, SELL-128-sigma\n");
+    fprintf(f, "                            for skewed ones; stream/scalar: the native CSR kernels (all bit-exact);\n");
+    fprintf(f, "                            warp: sub-warp-per-row (tolerance mode)\n");
     fprintf(f, "  --fma                     allow fused multiply-add (tolerance mode)\n");
     fprintf(f, "  --device-convert          convert COO to CSR on the device (general matrices)\n");
     fprintf(f, "  --gpus=N                  split the rows in N nonzero-balanced blocks over devices 0..N-1 [1]\n");
@@ -125,8 +128,10 @@ static int parse_options(int argc, char **argv, struct options *o, int *bad)
             if (!strncmp(a, "--kernel", 8) && (a[8] == '=' || a[8] == '\0')) {
                 if (!(v = optval(argc, argv, &i, "--kernel"))) return EINVAL;
                 o->flags &= ~(unsigned)ELLSPMV_CUDA_KERNEL_MASK;
-                if (!strcmp(v, "thread")) o->flags |= ELLSPMV_CUDA_KERNEL_THREAD;
+                if (!strcmp(v, "thread") || !strcmp(v, "stream")) o->flags |= ELLSPMV_CUDA_KERNEL_THREAD;
                 else if (!strcmp(v, "warp")) o->flags |= ELLSPMV_CUDA_KERNEL_WARP;
+                else if (!strcmp(v, "scalar")) o->flags |= CSRSPMV_CUDA_KERNEL_SCALAR;
+                else if (!strcmp(v, "sell")) o->flags |= CSRSPMV_CUDA_KERNEL_SELL;
                 else if (strcmp(v, "auto")) return EINVAL;
                 continue;
             }

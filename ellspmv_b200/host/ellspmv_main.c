@@ -86,7 +86,12 @@ static void help(FILE *f)
     fprintf(f, "  -v, --verbose        be more verbose\n");
     fprintf(f, "\n");
     fprintf(f, " Options for the CUDA path are:\n");
-    fprintf(f, "  --kernel=thread|warp thread-per-row (bit-exact, default) or sub-warp-per-row\n");
+    fprintf(f, "  --kernel=auto|thread|longrow|warp\n");
+    fprintf(f, "                       auto (default): thread-per-row, or the long-row kernel for few long\n");
+    fprintf(f, "                       rows -- both bit-exact; warp: sub-warp-per-row (tolerance mode)\n");
+    fprintf(f, "  --skip-padding       stream only the slots that count (rows sorted by length, width per\n");
+    fprintf(f, "                       slice); exact for finite x\n");
+    fprintf(f, "  --no-staged-gather   never take the staged gather for scattered matrices (auto tries it)\n");
     fprintf(f, "  --fma                allow fused multiply-add (tolerance mode)\n");
     fprintf(f, "  --rows-per-thread=N  1, 2 or 4 rows per thread [by row length]\n");
     fprintf(f, "  --l2-persist-x       L2 persisting access window over x\n");
@@ -162,10 +167,13 @@ static int parse_options(int argc, char **argv, struct options *o, int *bad)
                 o->flags &= ~(unsigned)ELLSPMV_CUDA_KERNEL_MASK;
                 if (!strcmp(v, "thread")) o->flags |= ELLSPMV_CUDA_KERNEL_THREAD;
                 else if (!strcmp(v, "warp")) o->flags |= ELLSPMV_CUDA_KERNEL_WARP;
+                else if (!strcmp(v, "longrow")) o->flags |= ELLSPMV_CUDA_KERNEL_LONGROW;
                 else if (strcmp(v, "auto")) return EINVAL;
                 continue;
             }
             if (!strcmp(a, "--fma")) { o->flags |= ELLSPMV_CUDA_FMA; continue; }
+            if (!strcmp(a, "--skip-padding")) { o->flags |= ELLSPMV_CUDA_SKIP_PADDING; continue; }
+            if (!strcmp(a, "--no-staged-gather")) { o->flags |= ELLSPMV_CUDA_NO_STAGED_GATHER; continue; }
             if (!strcmp(a, "--l2-persist-x")) { o->flags |= ELLSPMV_CUDA_L2_PERSIST_X; continue; }
             if (!strcmp(a, "--narrow-index")) { o->flags |= ELLSPMV_CUDA_NARROW_INDEX; continue; }
             if (!strcmp(a, "--wide-index")) { o->flags |= ELLSPMV_CUDA_WIDE_INDEX; continue; }

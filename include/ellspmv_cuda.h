@@ -65,6 +65,8 @@ enum {
                                     /*   in shared memory, one lane per row adds them in slot */
                                     /*   order: bit-exact.  AUTO takes it for rowsize >= 64   */
                                     /*   on matrices of at most 32768 rows  */
+    CSRSPMV_CUDA_KERNEL_SELL   = 5, /* CSR only: SELL-128-sigma (sell.cu); AUTO takes it for    */
+                                    /*   unbalanced rows                                        */
     ELLSPMV_CUDA_KERNEL_MASK   = 0xf,
     /* arithmetic: default is mul-then-add (__dmul_rn/__dadd_rn), the bits the
      * reference's compiled loop produces; FMA allows contraction (tolerance) */
@@ -86,15 +88,17 @@ enum {
      * zeros are dropped.  Keeps the regular layout as well (download, push
      * and separate-diagonal calls use it). */
     ELLSPMV_CUDA_COLUMN_BLOCKED = 1 << 7,
-    /* the bit-exact way to block by columns: store the column indices a
-     * second time sorted by (column block, slice); per SpMV, gather x block
-     * after block (each block's slice of x pinned in L2) into a flat stream
-     * in HBM, then run the reference's row loop -- slot 0..K-1, mul then
-     * add -- over the staged values (bulk-async copies into shared memory).
-     * Same bits as the default kernel, ~30 B instead of ~110 B of DRAM
-     * traffic per stored entry when x is much larger than L2; costs
-     * idx + 10 bytes of device memory per entry.  No-op when x fits one
-     * block or a slice's K*128 staged values do not fit shared memory. */
+    /* the bit-exact way to block by columns: store the entries a second time
+     * sorted by (column block, slice); per SpMV, walk them block after block
+     * (each block's slice of x stays in L2), gather x, multiply, and park the
+     * ROUNDED products as a flat stream in HBM; then add each row's products in
+     * slot order 0..K-1 (bulk-async copies into shared memory) -- mul, then
+     * left-to-right adds: the reference's bits, ~30 B instead of ~110 B of DRAM
+     * traffic per stored entry when x is much larger than L2; costs idx + 18
+     * bytes of device memory per entry.  KERNEL_AUTO takes this path by itself
+     * after a timed trial (see NO_STAGED_GATHER).  No-op when x fits one block or
+     * a slice's K*128 staged products do not fit shared memory.  With
+     * ELLSPMV_CUDA_FMA the products are still parked rounded (no contraction). */
     ELLSPMV_CUDA_STAGED_GATHER  = 1 << 17,
     /* offset patterns (on by default, thread-per-row kernel with one row
      * per thread): at upload, groups of 32 consecutive rows whose column
@@ -364,7 +368,8 @@ typedef struct csrspmv_cuda_info {
     int     kernel;            /* kernel in use: 1 stream, 2 vector, 3 scalar, 5 SELL-128-sigma  */
     int64_t sell_slots;        /* kernel 5: slots stored in the slices (padding included) ...    */
     int64_t sell_real;         /*   ... of which count; */
-    int64_t sell_long_rows;    /*   rows longer than 4096 entries, run one CTA per row           */
+    int64_t sell_long_rows;    /*   rows longer than sell_long_len entries, run one CTA per row  */
+    int64_t sell_long_len;     /*   that length (256; environment SELL_LONG_ROW overrides)       */
     int     ell_view;          /* 0: native CSR kernels; 1: sliced-ELL view with per-row        */
                                /*   lengths; 2: view of rows of one length (no length array)    */
     int     ell_staged;        /* the view runs the staged gather (see ellspmv_cuda_info)       */
