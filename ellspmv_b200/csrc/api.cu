@@ -146,7 +146,8 @@ void warm_kernels(ellspmv_cuda_matrix *A)
     args.num_rows = 0;
     args.rowsize = A->lay.rowsize;
     args.beta = 1;
-    args.patid = A->pat.patinfo;
+    args.patid = A->pat.max_explicit ? nullptr : A->pat.patid;
+    args.patinfo = A->pat.max_explicit ? A->pat.patinfo : nullptr;
     args.pat = A->pat.pat;
     if (launch_ell_spmv(A->cfg, args, 1, A->stream) == cudaSuccess) cudaStreamSynchronize(A->stream);
     cudaGetLastError();
@@ -179,7 +180,7 @@ int build_patterns(ellspmv_cuda_matrix *A)
         A->lay.num_rows <= 0 || A->lay.rowsize <= 0)
         return 0;
     cudaError_t ce = pattern_build(&A->pat, A->dev_idx_bits, A->cols, A->lay, A->cfg.rows_per_thread, A->row_begin,
-                                   A->stream);
+                                   (A->flags & ELLSPMV_CUDA_PATTERN_MASKS) ? 4 : 0, A->stream);
     if (ce != cudaSuccess) { set_last_error("offset patterns: %s", cudaGetErrorString(ce)); return cuda_to_errno(ce); }
     A->device_bytes += A->pat.bytes;
     if (A->pat.patid) warm_kernels(A);
@@ -369,7 +370,8 @@ int launch(ellspmv_cuda_matrix *A, double *y_dev, const double *x_dev, int beta,
     args.slice_begin = slice_begin;
     args.ad = A->d_ad;
     args.sd_order = A->sd_order;
-    args.patid = A->pat.patinfo;
+    args.patid = A->pat.max_explicit ? nullptr : A->pat.patid;
+    args.patinfo = A->pat.max_explicit ? A->pat.patinfo : nullptr;
     args.pat = A->pat.pat;
     args.rowlen = A->d_rowlen;
     // value-stream L2 prefetch 128 slices ahead when most rows are patterned (ell_kernels.cu)
@@ -1114,7 +1116,7 @@ static int csr_build_ell_view(csrspmv_cuda_matrix *A)
     size_t free_b = 0, total_b = 0;
     ELL_CK(cudaMemGetInfo(&free_b, &total_b));
     if ((int64_t)free_b < padded * (8 + A->idx_bits / 8) + A->num_rows * 4 + (1LL << 30)) return 0;
-    unsigned flags = A->flags & (ELLSPMV_CUDA_FMA | ELLSPMV_CUDA_WIDE_INDEX | ELLSPMV_CUDA_NO_PATTERN |
+    unsigned flags = A->flags & (ELLSPMV_CUDA_FMA | ELLSPMV_CUDA_WIDE_INDEX | ELLSPMV_CUDA_NO_PATTERN | ELLSPMV_CUDA_PATTERN_MASKS |
                                  ELLSPMV_CUDA_NO_STAGED_GATHER | ELLSPMV_CUDA_STAGED_GATHER | ELLSPMV_CUDA_L2_PERSIST_X);
     // kernel of the view: the same nnz-per-row switch as an ELL upload (configure); both kernels
     // honour the row lengths, the thread-per-row one in its R = 1 / explicit-index form

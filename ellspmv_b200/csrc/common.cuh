@@ -102,8 +102,8 @@ struct EllSpmvArgs {
     int           sd_order; // 0: y += ad*x + yi (ellgemvsd); 1: sum starts at ad*x (ellgemv16sd)
     PushTargets   push;
     int           prefetch;     // slices ahead whose value stream is requested into L2 (0 = none)
-    const unsigned long long *patid; // offset patterns (pattern.cu), one word per warp (32*R rows): low byte = pattern id
-                                //   (0xff = explicit indices), high half = lanes whose rows deviate; or NULL
+    const unsigned char *patid; // offset patterns (pattern.cu): one id per warp (32*R rows), 0xff = explicit indices; or NULL
+    const unsigned long long *patinfo; // with lane masks (opt-in) instead: low byte = pattern id, high half = lanes whose rows deviate
     const long long     *pat;   // dictionary [kMaxPatterns][K] of column offsets relative to the GLOBAL row
     StepSync      sync;
     const int    *rowlen;   // per row: how many leading slots count (CSR view: the rest is never touched
@@ -181,14 +181,16 @@ struct PatternSet {
     unsigned char *patid = nullptr;   // device: padded_rows / 32 ids
     unsigned long long *patinfo = nullptr; // device: per group, id (low byte) | lanes that keep explicit indices << 32
     int64_t explicit_lanes = 0;       // lanes flagged in the masks of the patterned groups
+    int max_explicit = 0;             // 0: whole groups only (patinfo unused by the kernel)
     long long *pat = nullptr;         // device: kMaxPatterns * K offsets
     int num_patterns = 0;
     int group_rows = 32;              // 32 * rows per thread
     int64_t groups = 0, covered = 0;  // groups: all / patterned
     int64_t bytes = 0;
 };
+// max_explicit: lanes of a patterned group that may deviate and keep explicit indices (0 = whole groups only)
 cudaError_t pattern_build(PatternSet *ps, int idx_bits, const void *cols, const EllLayout &lay, int rows_per_thread,
-                          int64_t row_begin, cudaStream_t stream);
+                          int64_t row_begin, int max_explicit, cudaStream_t stream);
 void pattern_free(PatternSet *ps);
 
 // ---- column-blocked ELL (ell_blocked.cu) ----------------------------------------

@@ -145,11 +145,13 @@ template <int R> struct Batch { static constexpr int U = (R == 4) ? 4 : (R == 2 
 // YVEC: y (and every push target) may be accessed with R-wide vectors.
 // PAT: the handle has offset patterns (pattern.cu).  A warp whose 32*R rows share one
 // offset vector d[] computes col = row + d[l] from the dictionary (a uniform load that
-// lives in L1) and never touches its lines of the index stream.
+// lives in L1) and never touches its lines of the index stream.  PAT = 1: whole groups only
+// (the default); PAT = 2: groups may carry a few deviating lanes (ELLSPMV_CUDA_PATTERN_MASKS,
+// opt-in: measured slower on the BASELINE shapes, profiles/r2_offset_patterns.md).
 // LEN: rows carry their own length (a.rowlen): slots past it are loaded but never enter the
 // arithmetic.  This is the CSR view (csrgemv has no padded slots, csrspmv.c:1588-1593); only
 // instantiated for R = 1, run-time K, no patterns.
-template <typename IdxT, int R, int KU, bool FMA, bool YVEC, int G, bool PAT, bool LEN = false>
+template <typename IdxT, int R, int KU, bool FMA, bool YVEC, int G, int PAT, bool LEN = false>
 __global__ void __launch_bounds__(kBlockThreads)
 ell_thread_kernel(const EllSpmvArgs a)
 {
@@ -227,15 +229,20 @@ ell_thread_kernel(const EllSpmvArgs a)
     int64_t rowp = rowg;          // the row the pattern's offsets are applied to
     if (PAT) {
         const int64_t grp = (slice * kBlockThreads + threadIdx.x) >> 5;
-        const unsigned long long info = __ldg(a.patid + grp);      // id and mask in one load
-        const unsigned pid = (unsigned)(info & 0xffull);
-        if (pid != 0xffu) {
-            prow = a.pat + (int64_t)pid * K;
-            pmask = (unsigned)(info >> 32);
-            if (pmask != 0u) {
-                const int64_t lead = __shfl_sync(0xffffffffu, rowg, __ffs(~pmask) - 1);
-                if ((pmask >> (threadIdx.x & 31)) & 1u) rowp = lead;
+        if (PAT == 2) {
+            const unsigned long long info = __ldg(a.patinfo + grp);      // id and mask in one load
+            const unsigned pid = (unsigned)(info & 0xffull);
+            if (pid != 0xffu) {
+                prow = a.pat + (int64_t)pid * K;
+                pmask = (unsigned)(info >> 32);
+                if (pmask != 0u) {
+                    const int64_t lead = __shfl_sync(0xffffffffu, rowg, __ffs(~pmask) - 1);
+                    if ((pmask >> (threadIdx.x & 31)) & 1u) rowp = lead;
+                }
             }
+        } else {
+            const unsigned pid = __ldg(a.patid + grp);
+            if (pid != 0xffu) prow = a.pat + (int64_t)pid * K;
         }
     }
     auto load_cols = [&](int l, int64_t (&c)[R]) {
@@ -346,7 +353,7 @@ ell_thread_kernel(const EllSpmvArgs a)
 
     // the flagged lanes of a patterned group: their rows again, from the explicit indices, by the
     // whole warp (warp-uniform control flow: pmask is the same in every lane)
-    if (PAT && pmask != 0u) {
+    if (PAT == 2 && pmask != 0u) {
         const int lane = threadIdx.x & 31;
         for (unsigned rest = pmask; rest != 0u; rest &= rest - 1) {
             const int fl = __ffs(rest) - 1;
@@ -487,16 +494,20 @@ static cudaError_t launch_thread_g(const EllSpmvArgs &args, bool yvec, cudaLaunc
 {
     if (args.rowlen) {
         // per-row lengths (CSR view): one row per thread, run-time K, explicit indices
-        if (R != 1 || KU != 0 || args.patid) return cudaErrorInvalidValue;
-        if (yvec) return cudaLaunchKernelEx(&lc, ell_thread_kernel<IdxT, 1, 0, FMA, true, G, false, true>, args);
-        return cudaLaunchKernelEx(&lc, ell_thread_kernel<IdxT, 1, 0, FMA, false, G, false, true>, args);
+        if (R != 1 || KU != 0 || args.patid || args.patinfo) return cudaErrorInvalidValue;
+        if (yvec) return cudaLaunchKernelEx(&lc, ell_thread_kernel<IdxT, 1, 0, FMA, true, G, 0, true>, args);
+        return cudaLaunchKernelEx(&lc, ell_thread_kernel<IdxT, 1, 0, FMA, false, G, 0, true>, args);
+    }
+    if (args.patinfo) {
+        if (yvec) return cudaLaunchKernelEx(&lc, ell_thread_kernel<IdxT, R, KU, FMA, true, G, 2>, args);
+        return cudaLaunchKernelEx(&lc, ell_thread_kernel<IdxT, R, KU, FMA, false, G, 2>, args);
     }
     if (args.patid) {
-        if (yvec) return cudaLaunchKernelEx(&lc, ell_thread_kernel<IdxT, R, KU, FMA, true, G, true>, args);
-        return cudaLaunchKernelEx(&lc, ell_thread_kernel<IdxT, R, KU, FMA, false, G, true>, args);
+        if (yvec) return cudaLaunchKernelEx(&lc, ell_thread_kernel<IdxT, R, KU, FMA, true, G, 1>, args);
+        return cudaLaunchKernelEx(&lc, ell_thread_kernel<IdxT, R, KU, FMA, false, G, 1>, args);
     }
-    if (yvec) return cudaLaunchKernelEx(&lc, ell_thread_kernel<IdxT, R, KU, FMA, true, G, false>, args);
-    return cudaLaunchKernelEx(&lc, ell_thread_kernel<IdxT, R, KU, FMA, false, G, false>, args);
+    if (yvec) return cudaLaunchKernelEx(&lc, ell_thread_kernel<IdxT, R, KU, FMA, true, G, 0>, args);
+    return cudaLaunchKernelEx(&lc, ell_thread_kernel<IdxT, R, KU, FMA, false, G, 0>, args);
 }
 
 template <typename IdxT, int R, int KU, bool FMA>

@@ -11,14 +11,16 @@
 // kernel computes col = row + d[l] from the dictionary (a warp-uniform, L1-resident
 // load) instead of loading the 128/256-byte line of indices from HBM.
 //
-// Lane masks: a grid boundary puts ONE deviating row into an otherwise regular group (its
-// entries shift left when a neighbour is missing, ellspmv.c:1102-1117).  Such a group stays
-// on the pattern: up to kPatMaxExplicit of its 32 lanes may deviate; they are flagged in a
-// 32-bit mask per group and read their own indices from the explicit stream (one 32-byte
-// sector per slot instead of the group's whole 128/256-byte line), the other lanes compute
-// theirs.  27-point 384^3: 83 % -> 99.5 % of the rows stop streaming indices.  The kernel reads id and
-// mask as ONE 64-bit word per warp: a second, dependent load at the head of every warp cost more
-// than the index bytes the masks save (profiles/r2_offset_patterns.md).
+// Lane masks (ELLSPMV_CUDA_PATTERN_MASKS, opt-in): a grid boundary puts ONE deviating row into
+// an otherwise regular group (its entries shift left when a neighbour is missing,
+// ellspmv.c:1102-1117), and by default that voids the group.  With the flag a group stays on
+// the pattern when at most 4 of its 32 lanes deviate: they are flagged in a 32-bit mask (read
+// together with the id as one 64-bit word per warp) and their rows are recomputed from the
+// explicit indices by the whole warp after the main loop.  27-point 384^3: 83 % -> 99.5 % of
+// the rows stop streaming indices -- and the kernel gets SLOWER (2.11 -> 2.25 ms): without
+// the index stream it is latency-bound, and the extra round of loads per masked group costs
+// more than the 6 % of bytes it saves.  Three variants measured, all slower than whole groups
+// (profiles/r2_offset_patterns.md); hence opt-in.
 //
 // This is a device-layout choice like the 64->32-bit index narrowing: the column
 // used for every entry is the stored one (every group is verified against the
@@ -44,7 +46,6 @@ __device__ __forceinline__ unsigned long long pat_mix(unsigned long long h, long
     return h ^ (h >> 29);
 }
 
-constexpr int kPatMaxExplicit = 4;   // lanes of a patterned group that may keep explicit indices
 
 // offsets of the lane's R rows at slot l, relative to each row: equal for all R rows, or not
 template <typename IdxT>
@@ -63,7 +64,7 @@ __device__ __forceinline__ bool lane_offset(const IdxT *__restrict__ cols, const
 template <typename IdxT>
 __global__ void __launch_bounds__(256)
 pat_signature_kernel(const IdxT *__restrict__ cols, EllLayout lay, int R, int64_t row_begin, int64_t num_groups,
-                     unsigned long long *__restrict__ sig)
+                     int max_explicit, unsigned long long *__restrict__ sig)
 {
     const int lane = threadIdx.x & 31;
     const int64_t g = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
@@ -83,7 +84,7 @@ pat_signature_kernel(const IdxT *__restrict__ cols, EllLayout lay, int R, int64_
     const unsigned key = ((unsigned)__popc(peers) << 8) | (unsigned)(31 - lane);
     const unsigned best = __reduce_max_sync(0xffffffffu, key);
     const unsigned long long hmaj = __shfl_sync(0xffffffffu, h, 31 - (int)(best & 0xffu));
-    if (lane == 0) sig[g] = (whole && (hmaj & 1ull) && (int)(best >> 8) >= 32 - kPatMaxExplicit) ? hmaj : 0ull;
+    if (lane == 0) sig[g] = (whole && (hmaj & 1ull) && (int)(best >> 8) >= 32 - max_explicit) ? hmaj : 0ull;
 }
 
 __global__ void pat_sample_kernel(const unsigned long long *__restrict__ sig, int64_t stride, int64_t n,
@@ -132,7 +133,7 @@ __global__ void pat_extract_kernel(const IdxT *__restrict__ cols, EllLayout lay,
 template <typename IdxT>
 __global__ void __launch_bounds__(256)
 pat_classify_kernel(const IdxT *__restrict__ cols, EllLayout lay, int R, int64_t row_begin, int64_t num_groups,
-                    const unsigned long long *__restrict__ sig, PatHashes hashes, int npat,
+                    int max_explicit, const unsigned long long *__restrict__ sig, PatHashes hashes, int npat,
                     const long long *__restrict__ pat, unsigned char *__restrict__ patid,
                     unsigned long long *__restrict__ patinfo, unsigned long long *__restrict__ covered)
 {
@@ -153,7 +154,7 @@ pat_classify_kernel(const IdxT *__restrict__ cols, EllLayout lay, int R, int64_t
         for (int l = 0; l < lay.rowsize && mine; l++)
             for (int r = 0; r < R; r++) mine = mine && (long long)cols[lay.offset(row + r, l)] - (row_begin + row + r) == d[l];
         mask = ~__ballot_sync(0xffffffffu, mine);
-        ok = __popc(mask) <= kPatMaxExplicit;
+        ok = __popc(mask) <= max_explicit;
     }
     if (lane == 0) {
         patid[g] = ok ? (unsigned char)p : (unsigned char)0xff;
@@ -165,7 +166,7 @@ pat_classify_kernel(const IdxT *__restrict__ cols, EllLayout lay, int R, int64_t
 
 template <typename IdxT>
 cudaError_t pattern_build_typed(PatternSet *ps, const IdxT *cols, const EllLayout &lay, int R, int64_t row_begin,
-                                cudaStream_t stream)
+                                int max_explicit, cudaStream_t stream)
 {
     const int64_t groups = lay.padded_rows() / (32 * R);
     const int K = lay.rowsize;
@@ -175,7 +176,7 @@ cudaError_t pattern_build_typed(PatternSet *ps, const IdxT *cols, const EllLayou
     auto cleanup = [&]() { cudaFree(sig); cudaFree(sample); cudaFree(covered); cudaFree(reps); };
     if ((e = cudaMalloc(&sig, (size_t)groups * 8)) != cudaSuccess) return e;
     const unsigned grid = (unsigned)((groups * 32 + 255) / 256);
-    pat_signature_kernel<IdxT><<<grid, 256, 0, stream>>>(cols, lay, R, row_begin, groups, sig);
+    pat_signature_kernel<IdxT><<<grid, 256, 0, stream>>>(cols, lay, R, row_begin, groups, max_explicit, sig);
     if ((e = cudaGetLastError()) != cudaSuccess) { cleanup(); return e; }
 
     // dictionary candidates: the most common signatures of a strided sample (the
@@ -219,7 +220,7 @@ cudaError_t pattern_build_typed(PatternSet *ps, const IdxT *cols, const EllLayou
     pat_extract_kernel<IdxT><<<npat, 128, 0, stream>>>(cols, lay, R, row_begin, reps, (const unsigned long long *)nullptr,
                                                        npat, ps->pat);
     if ((e = cudaGetLastError()) != cudaSuccess) { cleanup(); return e; }
-    pat_classify_kernel<IdxT><<<grid, 256, 0, stream>>>(cols, lay, R, row_begin, groups, sig, hashes, npat, ps->pat,
+    pat_classify_kernel<IdxT><<<grid, 256, 0, stream>>>(cols, lay, R, row_begin, groups, max_explicit, sig, hashes, npat, ps->pat,
                                                         ps->patid, ps->patinfo, covered);
     unsigned long long hc[2] = {0, 0};
     if ((e = cudaGetLastError()) != cudaSuccess ||
@@ -231,6 +232,7 @@ cudaError_t pattern_build_typed(PatternSet *ps, const IdxT *cols, const EllLayou
     ps->group_rows = 32 * R;
     ps->covered = (int64_t)hc[0];
     ps->explicit_lanes = (int64_t)hc[1];
+    ps->max_explicit = max_explicit;
     ps->bytes = groups * 9 + (int64_t)kMaxPatterns * K * 8;
     return cudaSuccess;
 }
@@ -248,14 +250,16 @@ void pattern_free(PatternSet *ps)
 // Leaves *ps empty (and returns success) when fewer than 1 group in 10 is patterned:
 // the table would cost a byte per group and buy nothing.
 cudaError_t pattern_build(PatternSet *ps, int idx_bits, const void *cols, const EllLayout &lay, int rows_per_thread,
-                          int64_t row_begin, cudaStream_t stream)
+                          int64_t row_begin, int max_explicit, cudaStream_t stream)
 {
     *ps = PatternSet{};
     const int R = rows_per_thread;
     if (lay.num_rows < 32 * R || lay.rowsize <= 0 || lay.rowsize > 4096 || lay.slice_rows != kBlockThreads * R)
         return cudaSuccess;
-    cudaError_t e = idx_bits == 64 ? pattern_build_typed<int64_t>(ps, (const int64_t *)cols, lay, R, row_begin, stream)
-                                   : pattern_build_typed<int32_t>(ps, (const int32_t *)cols, lay, R, row_begin, stream);
+    if (max_explicit < 0) max_explicit = 0;
+    if (max_explicit > 8) max_explicit = 8;
+    cudaError_t e = idx_bits == 64 ? pattern_build_typed<int64_t>(ps, (const int64_t *)cols, lay, R, row_begin, max_explicit, stream)
+                                   : pattern_build_typed<int32_t>(ps, (const int32_t *)cols, lay, R, row_begin, max_explicit, stream);
     if (e != cudaSuccess || ps->covered * 10 < ps->groups) pattern_free(ps);
     return e;
 }

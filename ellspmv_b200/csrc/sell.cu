@@ -186,11 +186,16 @@ sell_fill_kernel(Src src, const SrcI *__restrict__ src_cols, const double *__res
 
 template <typename Src>
 __global__ void sell_long_list_kernel(Src src, int64_t num_rows, int long_row, long long *__restrict__ list,
-                                      unsigned long long *__restrict__ cursor)
+                                      long long *__restrict__ lens, unsigned long long *__restrict__ cursor)
 {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= num_rows) return;
-    if (src.length(i) > long_row) list[atomicAdd(cursor, 1ull)] = i;    // order does not matter: one CTA per row
+    const int64_t n = src.length(i);
+    if (n > long_row) {
+        const unsigned long long at = atomicAdd(cursor, 1ull);
+        list[at] = i;
+        lens[at] = n;
+    }
 }
 
 template <typename Src, typename SrcI>
@@ -245,8 +250,27 @@ static cudaError_t sell_build_typed(SellMatrix *m, Src src, const SrcI *src_cols
         if ((e = cudaMalloc(&m->long_rows, (size_t)m->num_long * 8)) != cudaSuccess) { cleanup(); return e; }
         if ((e = cudaMalloc(&m->long_sum, (size_t)m->num_long * 8)) != cudaSuccess) { cleanup(); return e; }
         if ((e = cudaMemsetAsync(stats + 2, 0, 8, stream)) != cudaSuccess) { cleanup(); return e; }
-        sell_long_list_kernel<Src><<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(src, n, long_row, m->long_rows, stats + 2);
-        if ((e = cudaGetLastError()) != cudaSuccess) { cleanup(); return e; }
+        // the list, longest row first: a row is one chain of dependent additions, so the longest one
+        // sets the finish time and must start first (stable sort of (length, row) by length, descending)
+        long long *rows_unsorted = nullptr, *lens = nullptr, *lens_sorted = nullptr;
+        void *stemp = nullptr;
+        size_t sb = 0;
+        auto cleanup2 = [&]() { cudaFree(rows_unsorted); cudaFree(lens); cudaFree(lens_sorted); cudaFree(stemp); };
+        if ((e = cudaMalloc(&rows_unsorted, (size_t)m->num_long * 8)) != cudaSuccess ||
+            (e = cudaMalloc(&lens, (size_t)m->num_long * 8)) != cudaSuccess ||
+            (e = cudaMalloc(&lens_sorted, (size_t)m->num_long * 8)) != cudaSuccess) { cleanup2(); cleanup(); return e; }
+        sell_long_list_kernel<Src><<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(src, n, long_row, rows_unsorted, lens, stats + 2);
+        e = cudaGetLastError();
+        if (e == cudaSuccess)
+            e = cub::DeviceRadixSort::SortPairsDescending(nullptr, sb, lens, lens_sorted, rows_unsorted, m->long_rows,
+                                                          m->num_long, 0, 64, stream);
+        if (e == cudaSuccess) e = cudaMalloc(&stemp, sb + 16);
+        if (e == cudaSuccess)
+            e = cub::DeviceRadixSort::SortPairsDescending(stemp, sb, lens, lens_sorted, rows_unsorted, m->long_rows,
+                                                          m->num_long, 0, 64, stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+        cleanup2();
+        if (e != cudaSuccess) { cleanup(); return e; }
         if ((e = cudaStreamCreateWithFlags(&m->side, cudaStreamNonBlocking)) != cudaSuccess ||
             (e = cudaEventCreateWithFlags(&m->fork, cudaEventDisableTiming)) != cudaSuccess ||
             (e = cudaEventCreateWithFlags(&m->join, cudaEventDisableTiming)) != cudaSuccess) { cleanup(); return e; }

@@ -127,6 +127,12 @@ enum {
      * (The CSR path uses the same layout by itself for unbalanced rows: csrgemv has no
      * padding, so there it is exact for every x.) */
     ELLSPMV_CUDA_SKIP_PADDING     = 1 << 20,
+    /* offset patterns with lane masks: a group of 32*R rows stays on its pattern when at
+     * most 4 of its lanes hold deviating rows (a grid boundary); those rows are recomputed
+     * from the explicit indices by the whole warp.  Raises the coverage (27-point 384^3:
+     * 83 % -> 99.5 % of the rows) but measured slower than whole groups on the BASELINE
+     * shapes (profiles/r2_offset_patterns.md): opt-in.  Same bits either way. */
+    ELLSPMV_CUDA_PATTERN_MASKS    = 1 << 21,
     /* rows handled per thread in the thread-per-row kernel (1, 2 or 4):
      * 0 = auto = 2 for rows of at most 12 entries, else 1 */
     ELLSPMV_CUDA_ROWS_PER_THREAD_SHIFT = 8,

@@ -688,9 +688,9 @@ def test_offset_patterns_are_found_and_change_nothing(lib, oracle, bits):
 
 
 def test_offset_patterns_adversarial(lib, oracle):
-    """A deviating entry keeps only its own ROW on the explicit stream (lane masks); more distinct
-    patterns than the dictionary holds leaves the rest explicit; a random matrix finds nothing.
-    Always the oracle's bits."""
+    """One deviating entry keeps its group on the explicit stream -- or, with ELLSPMV_CUDA_PATTERN_MASKS,
+    only its own row; more distinct patterns than the dictionary holds leaves the rest explicit; a
+    random matrix finds nothing.  Always the oracle's bits."""
     rng = np.random.default_rng(11)
     nr = nc = 4096
     # (a) a single entry of a single row differs from its group's pattern
@@ -709,19 +709,22 @@ def test_offset_patterns_adversarial(lib, oracle):
     ec3 = rng.integers(0, nc, nr * 4).astype(np.int32)
     ea3 = rng.standard_normal(nr * 4)
     x = rng.standard_normal(nc)
-    # (a): the two damaged rows and the boundary rows stay explicit, their groups stay patterned
-    # (the last group has 5 boundary rows, more than a mask takes: it stays explicit as a whole)
-    for K, cols, vals, lo, hi in ((3, ec, ea, 4096 - 48, 4096 - 34), (2, ec2.reshape(-1), ea2, 32, 4096 - 1024), (4, ec3, ea3, 0, 0)):
+    # (a) with lane masks: the two damaged rows and the boundary rows stay explicit, their groups stay
+    # patterned (the last group has 5 boundary rows, more than a mask takes: explicit as a whole)
+    for K, cols, vals, lo, hi, mlo, mhi in ((3, ec, ea, 3900, 4096 - 64, 4096 - 48, 4096 - 34),
+                                            (2, ec2.reshape(-1), ea2, 32, 4096 - 1024, 32, 4096 - 1024),
+                                            (4, ec3, ea3, 0, 0, 0, 0)):
         want = np.zeros(nr)
         oracle.ellgemv(nr, want, x, K, cols, vals)
-        A = E.EllMatrix.upload(nr, nc, K, cols, vals, E.rows_per_thread(1))    # groups of 32 rows
-        rows = A.info().pattern_rows
-        assert lo <= rows <= hi, (K, rows)
-        assert rows == expected_pattern_rows(cols, K, nr, 1), K
-        y = np.zeros(nr)
-        A.spmv(y, x, 1, E.OVERWRITE)
-        assert bits_equal(y, want), K
-        A.free()
+        for flags, a, b, me in ((0, lo, hi, 0), (E.PATTERN_MASKS, mlo, mhi, 4)):
+            A = E.EllMatrix.upload(nr, nc, K, cols, vals, E.rows_per_thread(1) | flags)    # groups of 32 rows
+            rows = A.info().pattern_rows
+            assert a <= rows <= b, (K, rows, flags)
+            assert rows == expected_pattern_rows(cols, K, nr, 1, max_explicit=me), (K, flags)
+            y = np.zeros(nr)
+            A.spmv(y, x, 1, E.OVERWRITE)
+            assert bits_equal(y, want), (K, flags)
+            A.free()
 
 
 def test_offset_patterns_in_a_row_shard(lib, oracle):
@@ -741,13 +744,14 @@ def test_offset_patterns_in_a_row_shard(lib, oracle):
     A.free()
 
 
-def expected_pattern_rows(ec, K, nr, R, row_begin=0, max_patterns=16, max_explicit=4):
+def expected_pattern_rows(ec, K, nr, R, row_begin=0, max_patterns=16, max_explicit=0):
     """numpy restatement of the upload-time pattern search (pattern.cu) for matrices small
     enough that every group is sampled.  A group is the 32*R rows of one warp, lane j owning
     rows j*R..j*R+R-1; a lane has an offset vector when its R rows share one; a group's
-    signature is the vector at least 32 - max_explicit of its lanes share; the 16 most common
-    signatures (ties: first seen) form the dictionary; in a group whose signature is in it the
-    lanes with another vector keep their explicit indices.  Dropped below 10 % of the groups.
+    signature is the vector at least 32 - max_explicit of its lanes share (max_explicit = 0, the
+    default: all of them; 4 with ELLSPMV_CUDA_PATTERN_MASKS); the 16 most common signatures (ties:
+    first seen) form the dictionary; in a group whose signature is in it the lanes with another
+    vector keep their explicit indices.  Dropped below 10 % of the groups.
     Returns the rows that take their indices from the dictionary."""
     S = 128 * R
     G = 32 * R
@@ -811,20 +815,22 @@ def test_offset_patterns_randomized(lib, oracle, seed):
     oracle.ellgemv(nr, want, x, K, ec, ea)
     auto_R = 2 if K <= 12 else 1
     for R in (0, 1, 2, 4):
-        A = E.EllMatrix.upload(nr, nc, K, ec, ea, E.rows_per_thread(R) if R else 0)
-        info = A.info()
-        assert info.rows_per_thread == (R or auto_R)
-        assert info.pattern_rows == expected_pattern_rows(ec, K, nr, R or auto_R), (seed, K, nr, R)
-        y = rng.standard_normal(nr)
-        A.spmv(y, x, 1, E.OVERWRITE)
-        assert bits_equal(y, want), (seed, K, nr, R)
-        A.free()
+        for flags, me in ((0, 0), (E.PATTERN_MASKS, 4)):
+            A = E.EllMatrix.upload(nr, nc, K, ec, ea, (E.rows_per_thread(R) if R else 0) | flags)
+            info = A.info()
+            assert info.rows_per_thread == (R or auto_R)
+            assert info.pattern_rows == expected_pattern_rows(ec, K, nr, R or auto_R, max_explicit=me), (seed, K, nr, R, me)
+            y = rng.standard_normal(nr)
+            A.spmv(y, x, 1, E.OVERWRITE)
+            assert bits_equal(y, want), (seed, K, nr, R, me)
+            A.free()
     # a row shard: local rows, global columns
     lo, hi = nr // 5, nr - nr // 7
-    A = E.EllMatrix.upload(hi - lo, nc, K, ec[lo * K:hi * K], ea[lo * K:hi * K], E.rows_per_thread(1),
-                           global_rows=nr, row_begin=lo)
-    assert A.info().pattern_rows == expected_pattern_rows(ec[lo * K:hi * K], K, hi - lo, 1, row_begin=lo)
-    y = np.zeros(hi - lo)
-    A.spmv(y, x, 1, E.OVERWRITE)
-    assert bits_equal(y, want[lo:hi])
-    A.free()
+    for flags, me in ((0, 0), (E.PATTERN_MASKS, 4)):
+        A = E.EllMatrix.upload(hi - lo, nc, K, ec[lo * K:hi * K], ea[lo * K:hi * K], E.rows_per_thread(1) | flags,
+                               global_rows=nr, row_begin=lo)
+        assert A.info().pattern_rows == expected_pattern_rows(ec[lo * K:hi * K], K, hi - lo, 1, row_begin=lo, max_explicit=me)
+        y = np.zeros(hi - lo)
+        A.spmv(y, x, 1, E.OVERWRITE)
+        assert bits_equal(y, want[lo:hi])
+        A.free()
