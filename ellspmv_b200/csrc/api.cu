@@ -558,6 +558,9 @@ int launch_shard_exchange(ellspmv_cuda_matrix *A, double *y_dev, const double *x
     }
     sync.done = A->d_done;
     sync.remote = A->d_remote;
+    // warps that own at least one row: a warp covers 32 * R consecutive rows
+    const int64_t per_warp = 32 * (int64_t)A->cfg.rows_per_thread;
+    sync.total_warps = (unsigned)((A->lay.num_rows + per_warp - 1) / per_warp);
     return launch(A, y_dev, x_dev, beta, push, stream, 0, -1, &sync);
 }
 void shard_x_range(const ellspmv_cuda_matrix *A, int64_t *lo, int64_t *hi) { x_range(A, lo, hi); }

@@ -72,10 +72,11 @@ struct PushTargets {
 
 // ---- fused step synchronisation of the row-sharded y -> x loop (ell_kernels.cu) ----------
 // Instead of a barrier kernel between two steps, the SpMV kernel itself signals and waits:
-// its last CTA to finish stores the step number into slot [rank] of every listed rank's flag
-// array (peer-mapped HBM, system-scope release), and only the CTAs that read halo columns or
-// push to a peer wait -- at their start -- until the listed ranks have signalled the previous
-// step.  Interior CTAs never wait, so the flag round trip over NVLink hides behind them.
+// its last warp to finish stores the step number into slot [rank] of every listed rank's flag
+// array (peer-mapped HBM, system-scope release), and only the warps of CTAs that read halo
+// columns or push to a peer wait -- at their start -- until the listed ranks have signalled the
+// previous step.  Interior CTAs never wait, so the flag round trip over NVLink hides behind
+// them.  Everything is per warp (no CTA barrier): threads past the last row can simply exit.
 struct StepSync {
     long long *local_flags;            // this rank's flag array, slot [q] = last step rank q finished; NULL = off
     long long *peer_flags[kMaxPeers];  // flag arrays of the ranks below (peer-mapped)
@@ -83,7 +84,8 @@ struct StepSync {
     int        num_peers;
     int        rank;
     long long  epoch;                  // this step's number (>= 1): wait for epoch-1, signal epoch
-    unsigned  *done;                   // CTAs finished so far (device memory, zero between launches)
+    unsigned  *done;                   // warps finished so far (device memory, zero between launches)
+    unsigned   total_warps;            // warps of the launch that own at least one row
     const unsigned char *remote;       // per slice: reads columns outside the 16-aligned local row range
     int       *error;                  // set when a peer never showed up
 };

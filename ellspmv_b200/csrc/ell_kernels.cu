@@ -175,40 +175,44 @@ ell_thread_kernel(const EllSpmvArgs a)
             asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;"
                          :: "l"(a.vals + ps * S * (int64_t)K), "r"((unsigned)(S * K * 8)) : "memory");
     }
-    // fused step synchronisation (row-sharded y -> x loop): a CTA that reads halo columns or
-    // pushes into a peer's vector first waits until those peers have finished the previous step
-    // (their pushes have landed here, and they no longer read the vector this step overwrites)
+    // Threads past the shard's last row leave first (no CTA-wide barrier follows anywhere below:
+    // the step synchronisation works warp by warp).
+    if (row0 >= a.num_rows) return;
+
+    // fused step synchronisation (row-sharded y -> x loop): a warp of a CTA that reads halo columns
+    // or pushes into a peer's vector first waits until those peers have finished the previous step
+    // (their pushes have landed here, and they no longer read the vector this step overwrites).
+    // Warps of interior CTAs never wait, so the flag round trip over NVLink hides behind them.
     const bool synced = a.sync.local_flags != nullptr;
-    bool cta_pushes = false;
+    unsigned live = 0xffffffffu;                    // the lanes of this warp that own rows (taken while converged)
     if (synced) {
+        live = __activemask();
         const int64_t g_lo = a.row_begin + slice * S;
         const int64_t g_hi = g_lo + S;
+        bool cta_pushes = false;
         for (int p = 0; p < a.push.num_peers; p++)
             cta_pushes = cta_pushes || (g_lo < a.push.row_hi[p] && g_hi > a.push.row_lo[p]);
         if (cta_pushes || a.sync.remote[slice]) {
-            if (threadIdx.x < a.sync.num_peers) {
-                const long long *src = a.sync.local_flags + a.sync.peer_rank[threadIdx.x];
+            if ((threadIdx.x & 31) == 0) {
                 const long long want = a.sync.epoch - 1;
                 const long long t0 = clock64();
-                long long seen;
-                for (;;) {
-                    asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(seen) : "l"(src) : "memory");
-                    if (seen >= want) break;
-                    if (clock64() - t0 > 40000000000LL) {   // ~20 s: a peer died; do not hang the GPU
-                        if (a.sync.error) *a.sync.error = 1 + a.sync.peer_rank[threadIdx.x];
-                        break;
+                for (int p = 0; p < a.sync.num_peers; p++) {
+                    const long long *src = a.sync.local_flags + a.sync.peer_rank[p];
+                    long long seen;
+                    for (;;) {
+                        asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(seen) : "l"(src) : "memory");
+                        if (seen >= want) break;
+                        if (clock64() - t0 > 40000000000LL) {   // ~20 s: a peer died; do not hang the GPU
+                            if (a.sync.error) *a.sync.error = 1 + a.sync.peer_rank[p];
+                            break;
+                        }
+                        __nanosleep(32);
                     }
-                    __nanosleep(32);
                 }
             }
-            __syncthreads();
+            __syncwarp(live);                 // nobody gathers before lane 0 has seen the flags
         }
     }
-    // Threads past the shard's last row leave -- except in a launch with the fused step
-    // synchronisation, whose CTAs meet at a barrier below: __syncthreads() must be reached by
-    // whole warps together, so there the surplus threads of the last slice run along on its
-    // zero-filled tail ((column 0, 0.0) slots; every store below is guarded by the row count).
-    if (row0 >= a.num_rows && !synced) return;
 
     const int64_t base = slice * S * (int64_t)K + (int64_t)threadIdx.x * R;
     const double *vp = a.vals + base;
@@ -228,8 +232,8 @@ ell_thread_kernel(const EllSpmvArgs a)
     unsigned pmask = 0;           // warp-uniform: the lanes of this group that deviate
     int64_t rowp = rowg;          // the row the pattern's offsets are applied to
     if (PAT) {
-        const int64_t grp = (slice * kBlockThreads + threadIdx.x) >> 5;
         if (PAT == 2) {
+            const int64_t grp = (slice * kBlockThreads + threadIdx.x) >> 5;
             const unsigned long long info = __ldg(a.patinfo + grp);      // id and mask in one load
             const unsigned pid = (unsigned)(info & 0xffull);
             if (pid != 0xffu) {
@@ -241,13 +245,13 @@ ell_thread_kernel(const EllSpmvArgs a)
                 }
             }
         } else {
-            const unsigned pid = __ldg(a.patid + grp);
+            const unsigned pid = __ldg(a.patid + ((slice * kBlockThreads + threadIdx.x) >> 5));
             if (pid != 0xffu) prow = a.pat + (int64_t)pid * K;
         }
     }
     auto load_cols = [&](int l, int64_t (&c)[R]) {
         if (PAT && prow) {
-            const int64_t c0 = rowp + __ldg(prow + l);
+            const int64_t c0 = (PAT == 2 ? rowp : rowg) + __ldg(prow + l);
 #pragma unroll
             for (int r = 0; r < R; r++) c[r] = c0 + r;
         } else {
@@ -424,14 +428,15 @@ ell_thread_kernel(const EllSpmvArgs a)
         }
     }
 
-    // completion count: the last CTA of the launch tells the peers that this rank's step is done
+    // completion count, per warp: the last warp of the launch to get here tells the peers that this
+    // rank's step is done (all its pushes are visible system-wide, and it no longer reads x)
     if (synced) {
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            if (cta_pushes) __threadfence_system(); else __threadfence();
+        __syncwarp(live);                           // every lane's stores (y and the pushes) are issued
+        if ((threadIdx.x & 31) == 0) {
+            __threadfence_system();
             const unsigned prev = atomicAdd(a.sync.done, 1u);
-            if (prev == gridDim.x - 1) {
-                *a.sync.done = 0;                       // every CTA has counted: ready for the next launch
+            if (prev == a.sync.total_warps - 1) {
+                *a.sync.done = 0;                       // every warp has counted: ready for the next launch
                 __threadfence_system();
                 for (int p = 0; p < a.sync.num_peers; p++)
                     asm volatile("st.release.sys.global.s64 [%0], %1;"
