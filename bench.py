@@ -184,16 +184,27 @@ class ClockSampler:
 
     def nvlink_tx_bytes(self):
         """NVLink payload bytes this GPU has sent so far (NVML throughput counter, KiB), or None."""
-        try:
-            nv = self.nv
-            fid = getattr(nv, "NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX", 138)
-            vals = nv.nvmlDeviceGetFieldValues(self.h, [(fid, 0xFFFFFFFF)])
-            v = vals[0]
-            if v.nvmlReturn != 0:
-                return None
-            return int(v.value.ullVal) * 1024
-        except Exception:
+        nv = self.nv
+        if nv is None:
             return None
+        fid = getattr(nv, "NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX", 138)
+        for arg in ([(fid, 0xFFFFFFFF)], [fid]):            # all links at once, where the driver takes it
+            try:
+                v = nv.nvmlDeviceGetFieldValues(self.h, arg)[0]
+                if v.nvmlReturn == 0:
+                    return int(v.value.ullVal) * 1024
+            except Exception:
+                pass
+        total, ok = 0, False
+        for link in range(18):                              # else link by link (NV18 on this box)
+            try:
+                v = nv.nvmlDeviceGetFieldValues(self.h, [(fid, link)])[0]
+                if v.nvmlReturn == 0:
+                    total += int(v.value.ullVal) * 1024
+                    ok = True
+            except Exception:
+                break
+        return total if ok else None
 
 
 # ---------------------------------------------------------------------------

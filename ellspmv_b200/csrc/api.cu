@@ -350,8 +350,8 @@ int launch(ellspmv_cuda_matrix *A, double *y_dev, const double *x_dev, int beta,
 // can this handle's SpMV launch carry the fused step synchronisation (ell_thread_kernel only)?
 bool fused_sync_capable(const ellspmv_cuda_matrix *A)
 {
-    return A->cfg.kernel == ELLSPMV_CUDA_KERNEL_THREAD && !(A->cfg.variant & 1) && !A->sg && !A->cb &&
-           A->lay.rowsize > 0 && A->lay.num_rows > 0;
+    return A->cfg.kernel == ELLSPMV_CUDA_KERNEL_THREAD && !(A->cfg.variant & 1) && !A->sg && !A->cb && !A->sell &&
+           !A->d_rowlen && !A->pat.max_explicit && A->lay.rowsize > 0 && A->lay.num_rows > 0;
 }
 
 int launch(ellspmv_cuda_matrix *A, double *y_dev, const double *x_dev, int beta,
@@ -553,14 +553,56 @@ int launch_shard_exchange(ellspmv_cuda_matrix *A, double *y_dev, const double *x
         ELL_CK(cudaMalloc(&A->d_done, sizeof(unsigned)));
         ELL_CK(cudaMemsetAsync(A->d_done, 0, sizeof(unsigned), A->stream));
         ELL_CK(mark_remote_slices(A->dev_idx_bits, A->cols, A->lay, lo, hi, A->d_remote, A->stream));
+        A->h_remote.resize((size_t)A->lay.num_slices);
+        ELL_CK(cudaMemcpyAsync(A->h_remote.data(), A->d_remote, (size_t)A->lay.num_slices, cudaMemcpyDeviceToHost, A->stream));
         ELL_CK(cudaStreamSynchronize(A->stream));
         A->device_bytes += A->lay.num_slices + 4;
+        A->sync_plan_valid = false;
     }
     sync.done = A->d_done;
-    sync.remote = A->d_remote;
-    // warps that own at least one row: a warp covers 32 * R consecutive rows
-    const int64_t per_warp = 32 * (int64_t)A->cfg.rows_per_thread;
-    sync.total_warps = (unsigned)((A->lay.num_rows + per_warp - 1) / per_warp);
+    // the boundary slices under this push plan -- the ones that push to a peer or read halo columns;
+    // only their warps wait at the start and take part in the completion count.  Described once per
+    // plan: as up to 4 ranges of slice indices (kernel parameters), else as a per-slice table.
+    bool same = A->sync_plan_valid && push && A->sync_plan.num_peers == push->num_peers;
+    for (int p = 0; same && p < push->num_peers; p++)
+        same = A->sync_plan.row_lo[p] == push->row_lo[p] && A->sync_plan.row_hi[p] == push->row_hi[p];
+    if (!same) {
+        const int64_t S = A->lay.slice_rows, per_warp = 32 * (int64_t)A->cfg.rows_per_thread;
+        std::vector<unsigned char> flag((size_t)A->lay.num_slices);
+        unsigned total = 0;
+        int runs = 0;
+        long long lo[4] = {0, 0, 0, 0}, hi[4] = {0, 0, 0, 0};
+        bool prev = false;
+        for (int64_t sl = 0; sl < A->lay.num_slices; sl++) {
+            bool b = A->h_remote[(size_t)sl] != 0;
+            const int64_t g_lo = A->row_begin + sl * S, g_hi = g_lo + S;
+            for (int p = 0; push && !b && p < push->num_peers; p++) b = g_lo < push->row_hi[p] && g_hi > push->row_lo[p];
+            flag[(size_t)sl] = b ? 1 : 0;
+            if (b) {
+                const int64_t rows_here = (A->lay.num_rows - sl * S < S) ? A->lay.num_rows - sl * S : S;
+                total += (unsigned)((rows_here + per_warp - 1) / per_warp);
+                if (!prev) { if (runs < 4) lo[runs] = sl; runs++; }
+                if (runs <= 4) hi[runs - 1] = sl + 1;
+            }
+            prev = b;
+        }
+        A->sync_total = total;
+        if (runs <= 4) {
+            A->sync_num_ranges = runs;
+            for (int i = 0; i < 4; i++) { A->sync_range_lo[i] = lo[i]; A->sync_range_hi[i] = hi[i]; }
+        } else {
+            A->sync_num_ranges = -1;
+            if (!A->d_boundary) ELL_CK(cudaMalloc(&A->d_boundary, (size_t)A->lay.num_slices));
+            ELL_CK(cudaMemcpyAsync(A->d_boundary, flag.data(), (size_t)A->lay.num_slices, cudaMemcpyHostToDevice, stream));
+            ELL_CK(cudaStreamSynchronize(stream));          // `flag` goes out of scope
+        }
+        if (push) A->sync_plan = *push; else A->sync_plan.num_peers = 0;
+        A->sync_plan_valid = push != nullptr;
+    }
+    sync.num_ranges = A->sync_num_ranges;
+    for (int i = 0; i < 4; i++) { sync.range_lo[i] = A->sync_range_lo[i]; sync.range_hi[i] = A->sync_range_hi[i]; }
+    sync.table = A->d_boundary;
+    sync.total_warps = A->sync_total;
     return launch(A, y_dev, x_dev, beta, push, stream, 0, -1, &sync);
 }
 void shard_x_range(const ellspmv_cuda_matrix *A, int64_t *lo, int64_t *hi) { x_range(A, lo, hi); }
@@ -612,6 +654,7 @@ void ellspmv_cuda_free(ellspmv_cuda_matrix *A)
     if (A->d_ad) cudaFree(A->d_ad);
     if (A->d_rowlen) cudaFree(A->d_rowlen);
     if (A->d_remote) cudaFree(A->d_remote);
+    if (A->d_boundary) cudaFree(A->d_boundary);
     if (A->d_done) cudaFree(A->d_done);
     pattern_free(&A->pat);
     if (A->cb) cb_free(A->cb);

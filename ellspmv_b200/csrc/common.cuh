@@ -84,9 +84,16 @@ struct StepSync {
     int        num_peers;
     int        rank;
     long long  epoch;                  // this step's number (>= 1): wait for epoch-1, signal epoch
-    unsigned  *done;                   // warps finished so far (device memory, zero between launches)
-    unsigned   total_warps;            // warps of the launch that own at least one row
-    const unsigned char *remote;       // per slice: reads columns outside the 16-aligned local row range
+    unsigned  *done;                   // boundary warps finished so far (device memory, zero between launches)
+    unsigned   total_warps;            // warps (with at least one row) of the boundary slices
+    // boundary slices = those that push to a peer or read columns outside the (16-aligned) local row
+    // range.  Given as up to 4 ranges of slice indices (a stencil shard: its first and last few
+    // slices), so that an interior CTA decides with a few compares on kernel parameters -- a
+    // per-slice table lookup put a dependent global load at the head of every warp and cost 10 %
+    // of a step.  num_ranges < 0: more than 4 runs, look slice s up in `table`.
+    int        num_ranges;
+    long long  range_lo[4], range_hi[4];
+    const unsigned char *table;
     int       *error;                  // set when a peer never showed up
 };
 

@@ -151,7 +151,7 @@ template <int R> struct Batch { static constexpr int U = (R == 4) ? 4 : (R == 2 
 // LEN: rows carry their own length (a.rowlen): slots past it are loaded but never enter the
 // arithmetic.  This is the CSR view (csrgemv has no padded slots, csrspmv.c:1588-1593); only
 // instantiated for R = 1, run-time K, no patterns.
-template <typename IdxT, int R, int KU, bool FMA, bool YVEC, int G, int PAT, bool LEN = false>
+template <typename IdxT, int R, int KU, bool FMA, bool YVEC, int G, int PAT, bool LEN = false, bool SYNC = false>
 __global__ void __launch_bounds__(kBlockThreads)
 ell_thread_kernel(const EllSpmvArgs a)
 {
@@ -183,16 +183,19 @@ ell_thread_kernel(const EllSpmvArgs a)
     // or pushes into a peer's vector first waits until those peers have finished the previous step
     // (their pushes have landed here, and they no longer read the vector this step overwrites).
     // Warps of interior CTAs never wait, so the flag round trip over NVLink hides behind them.
-    const bool synced = a.sync.local_flags != nullptr;
+    // (SYNC is a template parameter: launches without the hand-shake run the kernel without any of it)
+    constexpr bool synced = SYNC;
     unsigned live = 0xffffffffu;                    // the lanes of this warp that own rows (taken while converged)
+    bool boundary = false;                          // CTA-uniform: this slice pushes to a peer or reads halo columns
     if (synced) {
         live = __activemask();
-        const int64_t g_lo = a.row_begin + slice * S;
-        const int64_t g_hi = g_lo + S;
-        bool cta_pushes = false;
-        for (int p = 0; p < a.push.num_peers; p++)
-            cta_pushes = cta_pushes || (g_lo < a.push.row_hi[p] && g_hi > a.push.row_lo[p]);
-        if (cta_pushes || a.sync.remote[slice]) {
+        if (a.sync.num_ranges >= 0) {
+            for (int i = 0; i < a.sync.num_ranges; i++)
+                boundary = boundary || (slice >= a.sync.range_lo[i] && slice < a.sync.range_hi[i]);
+        } else {
+            boundary = a.sync.table[slice] != 0;
+        }
+        if (boundary) {
             if ((threadIdx.x & 31) == 0) {
                 const long long want = a.sync.epoch - 1;
                 const long long t0 = clock64();
@@ -428,9 +431,12 @@ ell_thread_kernel(const EllSpmvArgs a)
         }
     }
 
-    // completion count, per warp: the last warp of the launch to get here tells the peers that this
-    // rank's step is done (all its pushes are visible system-wide, and it no longer reads x)
-    if (synced) {
+    // completion count, per warp, of the BOUNDARY slices only -- the ones that push to a peer or
+    // read halo columns: when the last of their warps gets here, every push of this rank is visible
+    // system-wide and nothing of this rank reads the halo any more, which is all a peer needs to
+    // know (interior slices touch neither).  A counter bumped by every warp of the launch cost
+    // 1.3 ms per step on the 8192^2 shard (a million same-address atomics); this one sees ~10^2.
+    if (synced && boundary) {
         __syncwarp(live);                           // every lane's stores (y and the pushes) are issued
         if ((threadIdx.x & 31) == 0) {
             __threadfence_system();
@@ -502,6 +508,18 @@ static cudaError_t launch_thread_g(const EllSpmvArgs &args, bool yvec, cudaLaunc
         if (R != 1 || KU != 0 || args.patid || args.patinfo) return cudaErrorInvalidValue;
         if (yvec) return cudaLaunchKernelEx(&lc, ell_thread_kernel<IdxT, 1, 0, FMA, true, G, 0, true>, args);
         return cudaLaunchKernelEx(&lc, ell_thread_kernel<IdxT, 1, 0, FMA, false, G, 0, true>, args);
+    }
+    if (args.sync.local_flags) {
+        // the fused step hand-shake: separate instantiations, so that every other launch runs a
+        // kernel without a trace of it (the whole-group PAT = 1 form serves masked handles too:
+        // patinfo's low byte is the id)
+        if (args.patinfo) return cudaErrorNotSupported;          // api.cu does not fuse for masked handles
+        if (args.patid) {
+            if (yvec) return cudaLaunchKernelEx(&lc, ell_thread_kernel<IdxT, R, KU, FMA, true, G, 1, false, true>, args);
+            return cudaLaunchKernelEx(&lc, ell_thread_kernel<IdxT, R, KU, FMA, false, G, 1, false, true>, args);
+        }
+        if (yvec) return cudaLaunchKernelEx(&lc, ell_thread_kernel<IdxT, R, KU, FMA, true, G, 0, false, true>, args);
+        return cudaLaunchKernelEx(&lc, ell_thread_kernel<IdxT, R, KU, FMA, false, G, 0, false, true>, args);
     }
     if (args.patinfo) {
         if (yvec) return cudaLaunchKernelEx(&lc, ell_thread_kernel<IdxT, R, KU, FMA, true, G, 2>, args);

@@ -43,7 +43,14 @@ struct ellspmv_cuda_matrix {
     ellspmv::SellMatrix *sell = nullptr;     // SELL-128-sigma copy without the trailing padding (ELLSPMV_CUDA_SKIP_PADDING), optional
     int64_t min_col = 0, max_col = -1;
     unsigned char *d_remote = nullptr;       // per slice: reads columns outside the shard's rows (fused step sync)
-    unsigned *d_done = nullptr;              // CTA completion counter of the fused step sync
+    unsigned *d_done = nullptr;              // completion counter of the fused step sync
+    std::vector<unsigned char> h_remote;     // host copy of d_remote
+    ellspmv::PushTargets sync_plan = {};     // the push ranges the boundary description below was made for
+    unsigned sync_total = 0;                 // warps of the boundary slices (push or halo) under that plan
+    int sync_num_ranges = 0;                 // boundary slices as <= 4 index ranges, or -1: per-slice table d_boundary
+    long long sync_range_lo[4] = {0, 0, 0, 0}, sync_range_hi[4] = {0, 0, 0, 0};
+    unsigned char *d_boundary = nullptr;
+    bool sync_plan_valid = false;
     cudaStream_t stream = nullptr;
     cudaStream_t stream_out = nullptr;       // D2H stream of the pipelined host call
     double *d_x = nullptr, *d_y = nullptr;   // vectors of the host-facing spmv
