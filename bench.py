@@ -601,11 +601,11 @@ def main_ours(args, rank: int, local_rank: int, world: int):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = float(t.item())
     ms_per_step = total_ms / args.steps
-    # our kernels launched inside the timed region: the SpMV launches counted by the library
-    # (the fused exchange needs no other kernel), plus one barrier kernel per step in the
-    # "device" hand-shake mode
+    # our kernels launched inside the timed region: the SpMV launches counted by the library, plus one
+    # one-warp hand-shake kernel per step (none with --flags FUSED_SYNC, where the SpMV kernel does it)
     timed_launches = int(A.info().launches - launches_before)
-    if sharded is not None and sharded.exchange == "push" and sharded.barrier == "device":
+    if sharded is not None and sharded.exchange == "push" and sharded.barrier in ("device", "neighbours") \
+            and not (flags & E.FUSED_SYNC):
         timed_launches += args.steps
 
     flops_step = 2.0 * global_rows * K
@@ -731,7 +731,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--exchange", choices=["auto", "push", "allgather"], default="auto")
-    ap.add_argument("--barrier", choices=["fused", "device", "nccl"], default="fused")
+    ap.add_argument("--barrier", choices=["neighbours", "device", "nccl"], default="neighbours")
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="laplace2d")
     ap.add_argument("--flags", type=lambda s: int(s, 0), default=0, help="ELLSPMV_CUDA_* upload flags")
     ap.add_argument("--e2e-steps", type=int, default=5)

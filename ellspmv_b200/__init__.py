@@ -37,6 +37,7 @@ NO_PATTERN = 1 << 18
 NO_STAGED_GATHER = 1 << 19
 SKIP_PADDING = 1 << 20
 PATTERN_MASKS = 1 << 21
+FUSED_SYNC = 1 << 22
 KERNEL_CSR_SELL = 5     # CSR: SELL-128-sigma (AUTO takes it for unbalanced rows)
 WIDE_INDEX = 1 << 16
 ROWS_PER_THREAD_SHIFT = 8

@@ -350,7 +350,7 @@ int launch(ellspmv_cuda_matrix *A, double *y_dev, const double *x_dev, int beta,
 // can this handle's SpMV launch carry the fused step synchronisation (ell_thread_kernel only)?
 bool fused_sync_capable(const ellspmv_cuda_matrix *A)
 {
-    return A->cfg.kernel == ELLSPMV_CUDA_KERNEL_THREAD && !(A->cfg.variant & 1) && !A->sg && !A->cb && !A->sell &&
+    return (A->flags & ELLSPMV_CUDA_FUSED_SYNC) && A->cfg.kernel == ELLSPMV_CUDA_KERNEL_THREAD && !(A->cfg.variant & 1) && !A->sg && !A->cb && !A->sell &&
            !A->d_rowlen && !A->pat.max_explicit && A->lay.rowsize > 0 && A->lay.num_rows > 0;
 }
 
@@ -539,7 +539,7 @@ int launch_shard_exchange(ellspmv_cuda_matrix *A, double *y_dev, const double *x
                           const PushTargets *push, StepSync sync, cudaStream_t stream)
 {
     if (!fused_sync_capable(A)) {
-        // kernels without the fused form: push, then signal + wait in a one-warp kernel
+        // the default, and the kernels without the fused form: push, then signal + wait in a one-warp kernel
         int err = launch(A, y_dev, x_dev, beta, push, stream, 0, -1);
         if (err) return err;
         ELL_CK(launch_peer_sync(sync, stream));
@@ -599,6 +599,10 @@ int launch_shard_exchange(ellspmv_cuda_matrix *A, double *y_dev, const double *x
         if (push) A->sync_plan = *push; else A->sync_plan.num_peers = 0;
         A->sync_plan_valid = push != nullptr;
     }
+    static const int poll_env = getenv("ELLSPMV_CUDA_SYNC_POLL_NS") ? atoi(getenv("ELLSPMV_CUDA_SYNC_POLL_NS")) : 100;
+    static const int nowait_env = getenv("ELLSPMV_CUDA_SYNC_NOWAIT") ? atoi(getenv("ELLSPMV_CUDA_SYNC_NOWAIT")) : 0;
+    sync.poll_ns = (unsigned)(poll_env > 0 ? poll_env : 100);
+    sync.debug_nowait = nowait_env;
     sync.num_ranges = A->sync_num_ranges;
     for (int i = 0; i < 4; i++) { sync.range_lo[i] = A->sync_range_lo[i]; sync.range_hi[i] = A->sync_range_hi[i]; }
     sync.table = A->d_boundary;

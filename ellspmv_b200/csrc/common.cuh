@@ -95,6 +95,8 @@ struct StepSync {
     long long  range_lo[4], range_hi[4];
     const unsigned char *table;
     int       *error;                  // set when a peer never showed up
+    unsigned   poll_ns;                // back-off between two looks at a flag
+    int        debug_nowait;           // experiments only (ELLSPMV_CUDA_SYNC_NOWAIT): do not wait -- results undefined
 };
 
 struct EllSpmvArgs {

@@ -195,7 +195,7 @@ ell_thread_kernel(const EllSpmvArgs a)
         } else {
             boundary = a.sync.table[slice] != 0;
         }
-        if (boundary) {
+        if (boundary && !a.sync.debug_nowait) {
             if ((threadIdx.x & 31) == 0) {
                 const long long want = a.sync.epoch - 1;
                 const long long t0 = clock64();
@@ -209,7 +209,7 @@ ell_thread_kernel(const EllSpmvArgs a)
                             if (a.sync.error) *a.sync.error = 1 + a.sync.peer_rank[p];
                             break;
                         }
-                        __nanosleep(32);
+                        __nanosleep(a.sync.poll_ns);
                     }
                 }
             }

@@ -125,11 +125,14 @@ class ShardedIterate:
     EllMatrix (or any object with .info(), .spmv_device(), .spmv_push())."""
 
     def __init__(self, A, rank: int, world: int, exchange: str = "auto", group=None,
-                 device: Optional[torch.device] = None, barrier: str = "fused"):
+                 device: Optional[torch.device] = None, barrier: str = "neighbours"):
         self.A, self.rank, self.world, self.group = A, rank, world, group
-        # "fused": the SpMV kernel signals and waits itself (ellspmv_cuda_spmv_exchange), neighbours only;
-        # "device": flag barrier kernel over peer memory after the kernel; "nccl": 1-element all-reduce
-        if barrier not in ("fused", "device", "nccl"):
+        # "neighbours": ellspmv_cuda_spmv_exchange -- the step hand-shake only with the ranks rows are exchanged
+        #   with (a one-warp kernel after the SpMV kernel; inside it for handles uploaded with FUSED_SYNC);
+        # "device": all-ranks flag barrier kernel after the kernel; "nccl": 1-element all-reduce
+        if barrier == "fused":
+            barrier = "neighbours"
+        if barrier not in ("neighbours", "device", "nccl"):
             raise ValueError(f"unknown barrier {barrier!r}")
         self.barrier = barrier
         info = A.info()
@@ -222,8 +225,8 @@ class ShardedIterate:
     def step(self, stream: int = 0) -> None:
         cur, nxt = self.x[self.cur], self.x[1 - self.cur]
         y = nxt[self.lo:self.hi]
-        if self.exchange == "push" and self.world > 1 and self.barrier == "fused":
-            # one kernel: SpMV, push, and the step hand-shake with the neighbouring ranks
+        if self.exchange == "push" and self.world > 1 and self.barrier == "neighbours":
+            # SpMV + push, and the step hand-shake with the neighbouring ranks only
             self.A.spmv_exchange(y, cur, OVERWRITE, self._peer_ptrs[1 - self.cur],
                                  [lo for _, lo, _ in self.plan], [hi for _, _, hi in self.plan],
                                  self.rank, self._sync_ranks, [self._flag_ptrs[p] for p in self._sync_ranks],

@@ -133,6 +133,12 @@ enum {
      * 83 % -> 99.5 % of the rows) but measured slower than whole groups on the BASELINE
      * shapes (profiles/r2_offset_patterns.md): opt-in.  Same bits either way. */
     ELLSPMV_CUDA_PATTERN_MASKS    = 1 << 21,
+    /* ellspmv_cuda_spmv_exchange: do the step hand-shake INSIDE the SpMV kernel (boundary
+     * warps wait at their start and signal at their end) instead of in a one-warp kernel
+     * after it.  Saves a launch per step, but the SpMV instantiation that carries it
+     * measured 10 % slower than kernel + hand-shake kernel on the 8192^2 shard
+     * (profiles/r2_scaling.md): opt-in.  Same protocol, same bits. */
+    ELLSPMV_CUDA_FUSED_SYNC       = 1 << 22,
     /* rows handled per thread in the thread-per-row kernel (1, 2 or 4):
      * 0 = auto = 2 for rows of at most 12 entries, else 1 */
     ELLSPMV_CUDA_ROWS_PER_THREAD_SHIFT = 8,
@@ -285,19 +291,20 @@ int ellspmv_cuda_spmv_push(
     const int64_t *peer_row_lo, const int64_t *peer_row_hi, void *stream);
 
 /*
- * The fused step of the row-sharded y -> x loop (BASELINE config 5): spmv_push plus the
- * synchronisation between this rank and the ranks it exchanges rows with, inside the SpMV
- * kernel.  CTAs that read halo columns or push wait -- at their start -- until every rank in
- * sync_ranks has finished step epoch-1; interior CTAs never wait; the last CTA to finish
- * stores `epoch` into slot [rank] of each of those ranks' flag arrays (system-scope release
- * over NVLink).  No barrier kernel, no NCCL call between two steps.
+ * One step of the row-sharded y -> x loop (BASELINE config 5): spmv_push plus the hand-shake
+ * between this rank and the ranks it exchanges rows with -- no all-ranks barrier, no NCCL call
+ * between two steps.  After its SpMV + push kernel a one-warp kernel stores `epoch` into slot
+ * [rank] of each listed rank's flag array (system-scope release over NVLink) and waits until
+ * those ranks have stored `epoch` here: their pushes of this step have landed, and they are
+ * done reading the vector the next step overwrites.  With ELLSPMV_CUDA_FUSED_SYNC (upload
+ * flag) the hand-shake runs inside the SpMV kernel instead: warps of the slices that read halo
+ * columns or push wait -- at their start -- for epoch-1, interior warps never wait, the last
+ * boundary warp to finish signals `epoch`.
  *   sync_ranks/sync_flags  the ranks this one pushes to or is pushed by, and their flag arrays
  *                          (peer-mapped; see ellspmv_cuda_peer_barrier for the array's shape)
  *   local_flags            this rank's own flag array; slot [16] turns non-zero if a peer never
  *                          arrived (~20 s), slot [rank] is unused
  *   epoch                  1, 2, 3, ... one per step, the same on every rank
- * Handles whose kernel has no fused form (sub-warp kernel, staged gather) run spmv_push
- * followed by a one-warp signal-and-wait kernel with the same protocol.
  */
 int ellspmv_cuda_spmv_exchange(
     ellspmv_cuda_matrix *A, double *y_dev, const double *x_dev, int mode,

@@ -234,11 +234,12 @@ def test_push_to_peer_vectors(lib, oracle):
     assert p1[:2000].abs().sum() == 0 and p1[2500:].abs().sum() == 0
 
 
-def test_exchange_on_one_gpu(lib, oracle):
+@pytest.mark.parametrize("fused", [0, 1])
+def test_exchange_on_one_gpu(lib, oracle, fused):
     """ellspmv_cuda_spmv_exchange with two shards of one matrix on ONE device, each playing a
-    rank: SpMV + push + the fused step hand-shake, several steps of x <- A*x, bits of the
-    oracle's iteration.  (Both 'ranks' run on the same GPU on two streams, so a CTA that waits
-    is really waiting for the other shard's kernel.)"""
+    rank: SpMV + push + the step hand-shake (one-warp kernel after the SpMV kernel, or inside it
+    with FUSED_SYNC), several steps of x <- A*x, bits of the oracle's iteration.  (Both 'ranks' run
+    on the same GPU on two streams, so whoever waits is really waiting for the other shard.)"""
     import torch
     for name, dims, vals, bits in [("laplace2d", (700, 97), (0.25, -0.125), 32),
                                    ("stencil27", (30, 9, 11), (0.5, -1.0 / 52), 64)]:
@@ -249,8 +250,8 @@ def test_exchange_on_one_gpu(lib, oracle):
         want = oracle.ell_iterate(rows, x0, steps, K, ec, ea)
         cut = rows // 2 + 3                                   # not a multiple of 16
         parts = [(0, cut), (cut, rows)]
-        S = [E.EllMatrix.upload(b - a, ncols, K, ec[a * K:b * K], ea[a * K:b * K], 0, global_rows=rows,
-                                row_begin=a, device=0) for a, b in parts]
+        S = [E.EllMatrix.upload(b - a, ncols, K, ec[a * K:b * K], ea[a * K:b * K], E.FUSED_SYNC if fused else 0,
+                                global_rows=rows, row_begin=a, device=0) for a, b in parts]
         needs = [(S[r].info().min_col, S[r].info().max_col + 1) for r in range(2)]
         # each rank owns two full-length vectors and a flag array
         xb = [[torch.zeros(rows, dtype=torch.float64, device="cuda") for _ in range(2)] for _ in range(2)]

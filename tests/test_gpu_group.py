@@ -24,7 +24,7 @@ def ngpus():
     (E.GEN_LAPLACE2D, "laplace2d", (61, 100), (0.5, 0.125), 32),
     (E.GEN_STENCIL27, "stencil27", (23, 9, 11), (0.5, 1.0 / 52), 64),
     (E.GEN_RANDOM, "random", (5003, 5003, 9), (0.0, 0.0), 32)])
-@pytest.mark.parametrize("flags", [0, E.STAGED_GATHER])
+@pytest.mark.parametrize("flags", [0, E.STAGED_GATHER, E.FUSED_SYNC])
 def test_group_equals_oracle(lib, oracle, kind, name, dims, vals, bits, flags, monkeypatch):
     # STAGED_GATHER: every shard gathers x column block by column block (several blocks at this
     # size with 4 KB per block) and the fused push runs out of the staged sum kernel

@@ -20,7 +20,7 @@ CASES = [(E.GEN_LAPLACE2D, "laplace2d", (64, 100), (0.25, -0.125), 32),
          (E.GEN_LAPLACE2D, "laplace2d", (1201, 97), (0.25, -0.125), 32),
          (E.GEN_STENCIL27, "stencil27", (24, 9, 11), (0.5, -1.0 / 52), 64),
          (E.GEN_RANDOM, "random", (5003, 5003, 9), (0.0, 0.0), 32)]
-MODES = ("allgather", "push-fused", "push-device", "push-nccl")
+MODES = ("allgather", "push-neighbours", "push-fusedsync", "push-device", "push-nccl")
 STEPS = 12
 
 
@@ -38,9 +38,11 @@ def _worker(rank, world, port, q):
             x0 = np.random.default_rng(0).uniform(-1, 1, rows)
             for mode in MODES:
                 lo, hi = partition_rows(rows, world)[rank]
-                A = E.EllMatrix.generate(kind, dims, vals, 42, bits, row_begin=lo, row_end=hi, device=rank)
+                fused = mode.endswith("fusedsync")        # the hand-shake inside the SpMV kernel (opt-in upload flag)
+                A = E.EllMatrix.generate(kind, dims, vals, 42, bits, row_begin=lo, row_end=hi, device=rank,
+                                         flags=E.FUSED_SYNC if fused else 0)
                 it = ShardedIterate(A, rank, world, exchange=mode.split("-")[0],
-                                    barrier=mode.split("-")[1] if "-" in mode else "fused")
+                                    barrier="neighbours" if fused or "-" not in mode else mode.split("-")[1])
                 it.set_x(lambda a, b: torch.from_numpy(x0[a:b].copy()).to(dev))
                 for _ in range(STEPS):
                     it.step(torch.cuda.current_stream().cuda_stream)
