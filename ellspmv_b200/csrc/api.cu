@@ -140,7 +140,8 @@ int alloc_matrix(ellspmv_cuda_matrix *A)
 // first timed launch is a steady-state one (an empty launch: zero rows).
 void warm_kernels(ellspmv_cuda_matrix *A)
 {
-    if (A->lay.rowsize <= 0) return;
+    preload_sync_kernels();
+    if (A->lay.rowsize <= 0) { cudaGetLastError(); return; }
     EllSpmvArgs args = {};
     args.vals = A->vals; args.cols = A->cols; args.x = A->vals; args.y = A->vals;
     args.num_rows = 0;
@@ -149,7 +150,20 @@ void warm_kernels(ellspmv_cuda_matrix *A)
     args.patid = A->pat.max_explicit ? nullptr : A->pat.patid;
     args.patinfo = A->pat.max_explicit ? A->pat.patinfo : nullptr;
     args.pat = A->pat.pat;
-    if (launch_ell_spmv(A->cfg, args, 1, A->stream) == cudaSuccess) cudaStreamSynchronize(A->stream);
+    args.rowlen = A->d_rowlen;
+    // every instantiation a later launch of this handle may pick: y aligned for vector access or
+    // not (a shard that starts at an odd row), with and without the in-kernel hand-shake.  A first
+    // launch loads code, and a load can wait for a kernel that is spinning for this one's signal.
+    long long dummy_flags[1] = {0};
+    for (int misaligned = 0; misaligned < 2; misaligned++)
+        for (int synced = 0; synced < 2; synced++) {
+            if (synced && !(A->flags & ELLSPMV_CUDA_FUSED_SYNC)) continue;
+            args.y = reinterpret_cast<double *>(reinterpret_cast<char *>(A->vals) + (misaligned ? 8 : 0));
+            args.sync = StepSync{};
+            if (synced) { args.sync.local_flags = dummy_flags; args.sync.num_ranges = 0; }   // never dereferenced: no rows
+            if (launch_ell_spmv(A->cfg, args, 1, A->stream) != cudaSuccess) cudaGetLastError();
+        }
+    cudaStreamSynchronize(A->stream);
     cudaGetLastError();
 }
 

@@ -85,4 +85,17 @@ cudaError_t launch_peer_sync(const StepSync &sync, cudaStream_t stream)
     return cudaGetLastError();
 }
 
+// CUDA loads a kernel's code on its first launch, and that load can wait for kernels already
+// running in the context.  A hand-shake kernel that is first launched while a peer on the SAME
+// device is already spinning for its signal would never get there (two shards of one process on
+// one GPU: tests/test_gpu_ell.py::test_exchange_on_one_gpu).  Called at upload time, before
+// anything can spin.
+cudaError_t preload_sync_kernels()
+{
+    cudaFuncAttributes attr;
+    cudaError_t e = cudaFuncGetAttributes(&attr, peer_barrier_kernel);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&attr, peer_sync_kernel);
+    return e;
+}
+
 }  // namespace ellspmv

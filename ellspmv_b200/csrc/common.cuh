@@ -273,5 +273,6 @@ cudaError_t launch_peer_barrier(int rank, int nranks, long long epoch, long long
 // the same between a rank and the ranks it exchanges with only (the protocol of StepSync, for the
 // kernels that do not carry the fused form): signal `epoch` to them, wait for `epoch` from them
 cudaError_t launch_peer_sync(const StepSync &sync, cudaStream_t stream);
+cudaError_t preload_sync_kernels();      // load the hand-shake kernels' code now (see barrier.cu)
 
 }  // namespace ellspmv
