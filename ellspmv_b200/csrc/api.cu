@@ -549,18 +549,13 @@ int launch_shard(ellspmv_cuda_matrix *A, double *y_dev, const double *x_dev, int
 }
 int ensure_event_count(std::vector<cudaEvent_t> &ev, size_t n) { return ensure_events(ev, n); }
 
-int launch_shard_exchange(ellspmv_cuda_matrix *A, double *y_dev, const double *x_dev, int beta,
-                          const PushTargets *push, StepSync sync, cudaStream_t stream)
+// The boundary slices of a shard under a push plan -- the ones that push to a peer or read a column
+// outside the shard's own (16-entry-aligned) row range -- as runs of slice indices; recomputed only
+// when the plan changes.  Everything else is interior: it neither needs a peer's data nor produces
+// any, which is what both forms of the step hand-shake build on.
+static int exchange_plan(ellspmv_cuda_matrix *A, const PushTargets *push, cudaStream_t stream)
 {
-    if (!fused_sync_capable(A)) {
-        // the default, and the kernels without the fused form: push, then signal + wait in a one-warp kernel
-        int err = launch(A, y_dev, x_dev, beta, push, stream, 0, -1);
-        if (err) return err;
-        ELL_CK(launch_peer_sync(sync, stream));
-        return 0;
-    }
     if (!A->d_remote) {
-        // one-off: which slices read columns outside this shard's own (16-aligned) row range
         const int64_t lo = (A->row_begin + 15) & ~(int64_t)15;
         const int64_t hi = (A->row_begin + A->lay.num_rows) & ~(int64_t)15;
         ELL_CK(cudaMalloc(&A->d_remote, (size_t)A->lay.num_slices));
@@ -573,55 +568,108 @@ int launch_shard_exchange(ellspmv_cuda_matrix *A, double *y_dev, const double *x
         A->device_bytes += A->lay.num_slices + 4;
         A->sync_plan_valid = false;
     }
-    sync.done = A->d_done;
-    // the boundary slices under this push plan -- the ones that push to a peer or read halo columns;
-    // only their warps wait at the start and take part in the completion count.  Described once per
-    // plan: as up to 4 ranges of slice indices (kernel parameters), else as a per-slice table.
     bool same = A->sync_plan_valid && push && A->sync_plan.num_peers == push->num_peers;
     for (int p = 0; same && p < push->num_peers; p++)
         same = A->sync_plan.row_lo[p] == push->row_lo[p] && A->sync_plan.row_hi[p] == push->row_hi[p];
-    if (!same) {
-        const int64_t S = A->lay.slice_rows, per_warp = 32 * (int64_t)A->cfg.rows_per_thread;
-        std::vector<unsigned char> flag((size_t)A->lay.num_slices);
-        unsigned total = 0;
-        int runs = 0;
-        long long lo[4] = {0, 0, 0, 0}, hi[4] = {0, 0, 0, 0};
-        bool prev = false;
-        for (int64_t sl = 0; sl < A->lay.num_slices; sl++) {
-            bool b = A->h_remote[(size_t)sl] != 0;
-            const int64_t g_lo = A->row_begin + sl * S, g_hi = g_lo + S;
-            for (int p = 0; push && !b && p < push->num_peers; p++) b = g_lo < push->row_hi[p] && g_hi > push->row_lo[p];
-            flag[(size_t)sl] = b ? 1 : 0;
-            if (b) {
-                const int64_t rows_here = (A->lay.num_rows - sl * S < S) ? A->lay.num_rows - sl * S : S;
-                total += (unsigned)((rows_here + per_warp - 1) / per_warp);
-                if (!prev) { if (runs < 4) lo[runs] = sl; runs++; }
-                if (runs <= 4) hi[runs - 1] = sl + 1;
-            }
-            prev = b;
+    if (same) return 0;
+    const int64_t S = A->lay.slice_rows, per_warp = 32 * (int64_t)A->cfg.rows_per_thread;
+    std::vector<unsigned char> flag((size_t)A->lay.num_slices);
+    unsigned total = 0;
+    int runs = 0;
+    int64_t count = 0;
+    long long lo[4] = {0, 0, 0, 0}, hi[4] = {0, 0, 0, 0};
+    bool prev = false;
+    for (int64_t sl = 0; sl < A->lay.num_slices; sl++) {
+        bool b = A->h_remote[(size_t)sl] != 0;
+        const int64_t g_lo = A->row_begin + sl * S, g_hi = g_lo + S;
+        for (int p = 0; push && !b && p < push->num_peers; p++) b = g_lo < push->row_hi[p] && g_hi > push->row_lo[p];
+        flag[(size_t)sl] = b ? 1 : 0;
+        if (b) {
+            const int64_t rows_here = (A->lay.num_rows - sl * S < S) ? A->lay.num_rows - sl * S : S;
+            total += (unsigned)((rows_here + per_warp - 1) / per_warp);
+            count++;
+            if (!prev) { if (runs < 4) lo[runs] = sl; runs++; }
+            if (runs <= 4) hi[runs - 1] = sl + 1;
         }
-        A->sync_total = total;
-        if (runs <= 4) {
-            A->sync_num_ranges = runs;
-            for (int i = 0; i < 4; i++) { A->sync_range_lo[i] = lo[i]; A->sync_range_hi[i] = hi[i]; }
-        } else {
-            A->sync_num_ranges = -1;
-            if (!A->d_boundary) ELL_CK(cudaMalloc(&A->d_boundary, (size_t)A->lay.num_slices));
-            ELL_CK(cudaMemcpyAsync(A->d_boundary, flag.data(), (size_t)A->lay.num_slices, cudaMemcpyHostToDevice, stream));
-            ELL_CK(cudaStreamSynchronize(stream));          // `flag` goes out of scope
-        }
-        if (push) A->sync_plan = *push; else A->sync_plan.num_peers = 0;
-        A->sync_plan_valid = push != nullptr;
+        prev = b;
     }
-    static const int poll_env = getenv("ELLSPMV_CUDA_SYNC_POLL_NS") ? atoi(getenv("ELLSPMV_CUDA_SYNC_POLL_NS")) : 100;
-    static const int nowait_env = getenv("ELLSPMV_CUDA_SYNC_NOWAIT") ? atoi(getenv("ELLSPMV_CUDA_SYNC_NOWAIT")) : 0;
-    sync.poll_ns = (unsigned)(poll_env > 0 ? poll_env : 100);
-    sync.debug_nowait = nowait_env;
-    sync.num_ranges = A->sync_num_ranges;
-    for (int i = 0; i < 4; i++) { sync.range_lo[i] = A->sync_range_lo[i]; sync.range_hi[i] = A->sync_range_hi[i]; }
-    sync.table = A->d_boundary;
-    sync.total_warps = A->sync_total;
-    return launch(A, y_dev, x_dev, beta, push, stream, 0, -1, &sync);
+    A->sync_total = total;
+    A->sync_boundary_slices = count;
+    if (runs <= 4) {
+        A->sync_num_ranges = runs;
+        for (int i = 0; i < 4; i++) { A->sync_range_lo[i] = lo[i]; A->sync_range_hi[i] = hi[i]; }
+    } else {
+        A->sync_num_ranges = -1;
+        if (!A->d_boundary) ELL_CK(cudaMalloc(&A->d_boundary, (size_t)A->lay.num_slices));
+        ELL_CK(cudaMemcpyAsync(A->d_boundary, flag.data(), (size_t)A->lay.num_slices, cudaMemcpyHostToDevice, stream));
+        ELL_CK(cudaStreamSynchronize(stream));          // `flag` goes out of scope
+    }
+    if (push) A->sync_plan = *push; else A->sync_plan.num_peers = 0;
+    A->sync_plan_valid = push != nullptr;
+    return 0;
+}
+
+int launch_shard_exchange(ellspmv_cuda_matrix *A, double *y_dev, const double *x_dev, int beta,
+                          const PushTargets *push, StepSync sync, cudaStream_t stream)
+{
+    const bool sliceable = A->cfg.kernel == ELLSPMV_CUDA_KERNEL_THREAD && !(A->cfg.variant & 1) && !A->sg && !A->cb &&
+                           !A->sell && A->lay.rowsize > 0 && A->lay.num_rows > 0;
+    int err;
+    if (!sliceable) {
+        // kernels that only run whole (long-row, staged gather, SELL ...): push, then the one-warp hand-shake
+        if ((err = launch(A, y_dev, x_dev, beta, push, stream, 0, -1))) return err;
+        ELL_CK(launch_peer_sync(sync, stream));
+        return 0;
+    }
+    if ((err = exchange_plan(A, push, stream))) return err;
+    if (fused_sync_capable(A)) {
+        // opt-in: the hand-shake inside the SpMV kernel
+        static const int poll_env = getenv("ELLSPMV_CUDA_SYNC_POLL_NS") ? atoi(getenv("ELLSPMV_CUDA_SYNC_POLL_NS")) : 100;
+        static const int nowait_env = getenv("ELLSPMV_CUDA_SYNC_NOWAIT") ? atoi(getenv("ELLSPMV_CUDA_SYNC_NOWAIT")) : 0;
+        sync.done = A->d_done;
+        sync.poll_ns = (unsigned)(poll_env > 0 ? poll_env : 100);
+        sync.debug_nowait = nowait_env;
+        sync.num_ranges = A->sync_num_ranges;
+        for (int i = 0; i < 4; i++) { sync.range_lo[i] = A->sync_range_lo[i]; sync.range_hi[i] = A->sync_range_hi[i]; }
+        sync.table = A->d_boundary;
+        sync.total_warps = A->sync_total;
+        return launch(A, y_dev, x_dev, beta, push, stream, 0, -1, &sync);
+    }
+    static const int nosplit_env = getenv("ELLSPMV_CUDA_NO_SPLIT_EXCHANGE") ? atoi(getenv("ELLSPMV_CUDA_NO_SPLIT_EXCHANGE")) : 0;
+    const int runs = A->sync_num_ranges;
+    if (nosplit_env || runs < 1 || runs > 4 || A->sync_boundary_slices * 4 > A->lay.num_slices) {
+        // no interior worth the name (a scattered matrix: every slice reads remote columns)
+        if ((err = launch(A, y_dev, x_dev, beta, push, stream, 0, -1))) return err;
+        ELL_CK(launch_peer_sync(sync, stream));
+        return 0;
+    }
+    // Default: the step in two parts.  The boundary slices -- the only ones that need the peers'
+    // pushes of the previous step and the only ones that push -- run first; their hand-shake with
+    // the neighbouring ranks then runs on a second stream WHILE the interior slices (nearly all of
+    // the work, no dependence on any peer) run here.  The next step's boundary launch waits for
+    // that hand-shake; by then it has long finished, so neither the flag round trip over NVLink nor
+    // the skew between ranks is on the critical path.
+    if (!A->side) {
+        ELL_CK(cudaStreamCreateWithFlags(&A->side, cudaStreamNonBlocking));
+        ELL_CK(cudaEventCreateWithFlags(&A->ev_boundary, cudaEventDisableTiming));
+        ELL_CK(cudaEventCreateWithFlags(&A->ev_handshake, cudaEventDisableTiming));
+    }
+    if (A->handshake_pending) ELL_CK(cudaStreamWaitEvent(stream, A->ev_handshake, 0));
+    for (int i = 0; i < runs; i++)
+        if ((err = launch(A, y_dev, x_dev, beta, push, stream, A->sync_range_lo[i], A->sync_range_hi[i] - A->sync_range_lo[i])))
+            return err;
+    ELL_CK(cudaEventRecord(A->ev_boundary, stream));
+    ELL_CK(cudaStreamWaitEvent(A->side, A->ev_boundary, 0));
+    ELL_CK(launch_peer_sync(sync, A->side));
+    ELL_CK(cudaEventRecord(A->ev_handshake, A->side));
+    A->handshake_pending = true;
+    int64_t at = 0;
+    for (int i = 0; i <= runs; i++) {
+        const int64_t end = i < runs ? A->sync_range_lo[i] : A->lay.num_slices;
+        if (end > at && (err = launch(A, y_dev, x_dev, beta, nullptr, stream, at, end - at))) return err;
+        if (i < runs) at = A->sync_range_hi[i];
+    }
+    return 0;
 }
 void shard_x_range(const ellspmv_cuda_matrix *A, int64_t *lo, int64_t *hi) { x_range(A, lo, hi); }
 // same for a CSR handle: the stored column range, plus its own global rows with csrgemvsd's diagonal
@@ -673,6 +721,9 @@ void ellspmv_cuda_free(ellspmv_cuda_matrix *A)
     if (A->d_rowlen) cudaFree(A->d_rowlen);
     if (A->d_remote) cudaFree(A->d_remote);
     if (A->d_boundary) cudaFree(A->d_boundary);
+    if (A->side) { cudaStreamSynchronize(A->side); cudaStreamDestroy(A->side); }
+    if (A->ev_boundary) cudaEventDestroy(A->ev_boundary);
+    if (A->ev_handshake) cudaEventDestroy(A->ev_handshake);
     if (A->d_done) cudaFree(A->d_done);
     pattern_free(&A->pat);
     if (A->cb) cb_free(A->cb);

@@ -334,7 +334,11 @@ int group_spmv(ellspmv_cuda_matrix *G, double *y, const double *x, int repeat, i
         if (S->lay.num_rows > 0)
             ELL_CK(cudaMemcpyAsync(y + S->row_begin, src, (size_t)S->lay.num_rows * 8, cudaMemcpyDefault, S->stream));
     }
-    for (int p = 0; p < n; p++) { ELL_CK(cudaSetDevice(p)); ELL_CK(cudaStreamSynchronize(G->shards[p]->stream)); }
+    for (int p = 0; p < n; p++) {
+        ELL_CK(cudaSetDevice(p));
+        ELL_CK(cudaStreamSynchronize(G->shards[p]->stream));
+        if (G->shards[p]->side) ELL_CK(cudaStreamSynchronize(G->shards[p]->side));   // the last step's hand-shake
+    }
     if (seconds) {
         for (int r = 0; r < repeat; r++) {
             double worst = 0.0;

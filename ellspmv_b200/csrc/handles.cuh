@@ -50,7 +50,11 @@ struct ellspmv_cuda_matrix {
     int sync_num_ranges = 0;                 // boundary slices as <= 4 index ranges, or -1: per-slice table d_boundary
     long long sync_range_lo[4] = {0, 0, 0, 0}, sync_range_hi[4] = {0, 0, 0, 0};
     unsigned char *d_boundary = nullptr;
+    int64_t sync_boundary_slices = 0;
     bool sync_plan_valid = false;
+    cudaStream_t side = nullptr;             // the step hand-shake runs here, next to the interior slices
+    cudaEvent_t ev_boundary = nullptr, ev_handshake = nullptr;
+    bool handshake_pending = false;
     cudaStream_t stream = nullptr;
     cudaStream_t stream_out = nullptr;       // D2H stream of the pipelined host call
     double *d_x = nullptr, *d_y = nullptr;   // vectors of the host-facing spmv

@@ -14,14 +14,16 @@ TIME = {"ns": 1e-3, "nsecond": 1e-3, "us": 1.0, "usecond": 1.0, "ms": 1e3, "msec
 BYTES = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
 
 
-def load(path):
-    """-> ordered {kernel name: {"n": launches, "us": total time, "rd": bytes, "wr": bytes}}"""
+def load(path, by_grid=False):
+    """-> ordered {kernel name: {"n": launches, "us": total time, "rd": bytes, "wr": bytes}};
+    by_grid keeps launches of one kernel with different grid sizes apart (a full-matrix launch
+    and the row pieces of the pipelined host-vector path are the same kernel)"""
     per_launch = collections.OrderedDict()
     with open(path, newline="") as f:
         for r in csv.reader(f):
             if len(r) < 15 or not r[0].isdigit():
                 continue
-            key = (int(r[0]), r[4])
+            key = (int(r[0]), r[4] + (f"  grid {r[8]}" if by_grid else ""))
             per_launch.setdefault(key, {})[r[12]] = (float(r[14].replace(",", "")), r[13])
     agg = collections.OrderedDict()
     for (_, name), m in per_launch.items():
@@ -41,8 +43,9 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("csv")
     ap.add_argument("--markdown", action="store_true")
+    ap.add_argument("--by-grid", action="store_true", help="keep different grid sizes of one kernel apart")
     args = ap.parse_args()
-    agg = load(args.csv)
+    agg = load(args.csv, args.by_grid)
     total = sum(a["us"] for a in agg.values()) or 1.0
     with_bytes = any(a["rd"] or a["wr"] for a in agg.values())
     if args.markdown:
@@ -53,7 +56,7 @@ def main():
         if with_bytes:
             cols += [f"{a['rd'] / a['n'] / 1e9:.3f}", f"{a['wr'] / a['n'] / 1e9:.3f}"]
         if args.markdown:
-            print("| " + " | ".join(cols) + f" | `{name[:110]}` |")
+            print("| " + " | ".join(cols) + f" | `{name[:110] if not args.by_grid else name[:70] + name[name.rfind('  grid'):]}` |")
         else:
             print("  ".join(c.rjust(10) for c in cols) + "  " + name[:110])
 
