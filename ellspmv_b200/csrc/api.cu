@@ -635,31 +635,44 @@ int launch_shard_exchange(ellspmv_cuda_matrix *A, double *y_dev, const double *x
         sync.total_warps = A->sync_total;
         return launch(A, y_dev, x_dev, beta, push, stream, 0, -1, &sync);
     }
-    static const int nosplit_env = getenv("ELLSPMV_CUDA_NO_SPLIT_EXCHANGE") ? atoi(getenv("ELLSPMV_CUDA_NO_SPLIT_EXCHANGE")) : 0;
+    // ELLSPMV_CUDA_SPLIT_EXCHANGE: 0 = one launch + hand-shake behind it, 1 = boundary, then interior
+    // on one stream, 2 (default) = boundary and interior side by side on two streams
+    static const int split_env = getenv("ELLSPMV_CUDA_NO_SPLIT_EXCHANGE") && atoi(getenv("ELLSPMV_CUDA_NO_SPLIT_EXCHANGE")) ? 0
+                                 : getenv("ELLSPMV_CUDA_SPLIT_EXCHANGE") ? atoi(getenv("ELLSPMV_CUDA_SPLIT_EXCHANGE")) : 2;
     const int runs = A->sync_num_ranges;
-    if (nosplit_env || runs < 1 || runs > 4 || A->sync_boundary_slices * 4 > A->lay.num_slices) {
+    if (split_env <= 0 || runs < 1 || runs > 4 || A->sync_boundary_slices * 4 > A->lay.num_slices) {
         // no interior worth the name (a scattered matrix: every slice reads remote columns)
         if ((err = launch(A, y_dev, x_dev, beta, push, stream, 0, -1))) return err;
         ELL_CK(launch_peer_sync(sync, stream));
         return 0;
     }
     // Default: the step in two parts.  The boundary slices -- the only ones that need the peers'
-    // pushes of the previous step and the only ones that push -- run first; their hand-shake with
-    // the neighbouring ranks then runs on a second stream WHILE the interior slices (nearly all of
-    // the work, no dependence on any peer) run here.  The next step's boundary launch waits for
-    // that hand-shake; by then it has long finished, so neither the flag round trip over NVLink nor
-    // the skew between ranks is on the critical path.
+    // pushes of the previous step and the only ones that push -- and their hand-shake with the
+    // neighbouring ranks run on a second stream; the interior slices (nearly all of the work, no
+    // dependence on any peer) run on the caller's stream at the same time.  The second stream keeps
+    // its own order from step to step (boundary e, hand-shake e, boundary e+1 ...), so neither the
+    // flag round trip over NVLink nor the skew between ranks is on the interior's critical path.
+    // On return `stream` is ordered after ALL rows of y (not after the hand-shake: the halo of y
+    // is for the next exchange call, which is).
     if (!A->side) {
         ELL_CK(cudaStreamCreateWithFlags(&A->side, cudaStreamNonBlocking));
+        ELL_CK(cudaEventCreateWithFlags(&A->ev_start, cudaEventDisableTiming));
         ELL_CK(cudaEventCreateWithFlags(&A->ev_boundary, cudaEventDisableTiming));
         ELL_CK(cudaEventCreateWithFlags(&A->ev_handshake, cudaEventDisableTiming));
     }
-    if (A->handshake_pending) ELL_CK(cudaStreamWaitEvent(stream, A->ev_handshake, 0));
+    const bool side_by_side = split_env >= 2;
+    cudaStream_t bs = side_by_side ? A->side : stream;
+    if (side_by_side) {
+        ELL_CK(cudaEventRecord(A->ev_start, stream));           // x complete, previous step's y rows consumed
+        ELL_CK(cudaStreamWaitEvent(A->side, A->ev_start, 0));
+    } else if (A->handshake_pending) {
+        ELL_CK(cudaStreamWaitEvent(stream, A->ev_handshake, 0));
+    }
     for (int i = 0; i < runs; i++)
-        if ((err = launch(A, y_dev, x_dev, beta, push, stream, A->sync_range_lo[i], A->sync_range_hi[i] - A->sync_range_lo[i])))
+        if ((err = launch(A, y_dev, x_dev, beta, push, bs, A->sync_range_lo[i], A->sync_range_hi[i] - A->sync_range_lo[i])))
             return err;
-    ELL_CK(cudaEventRecord(A->ev_boundary, stream));
-    ELL_CK(cudaStreamWaitEvent(A->side, A->ev_boundary, 0));
+    ELL_CK(cudaEventRecord(A->ev_boundary, bs));
+    if (!side_by_side) ELL_CK(cudaStreamWaitEvent(A->side, A->ev_boundary, 0));
     ELL_CK(launch_peer_sync(sync, A->side));
     ELL_CK(cudaEventRecord(A->ev_handshake, A->side));
     A->handshake_pending = true;
@@ -669,6 +682,7 @@ int launch_shard_exchange(ellspmv_cuda_matrix *A, double *y_dev, const double *x
         if (end > at && (err = launch(A, y_dev, x_dev, beta, nullptr, stream, at, end - at))) return err;
         if (i < runs) at = A->sync_range_hi[i];
     }
+    if (side_by_side) ELL_CK(cudaStreamWaitEvent(stream, A->ev_boundary, 0));
     return 0;
 }
 void shard_x_range(const ellspmv_cuda_matrix *A, int64_t *lo, int64_t *hi) { x_range(A, lo, hi); }
@@ -722,6 +736,7 @@ void ellspmv_cuda_free(ellspmv_cuda_matrix *A)
     if (A->d_remote) cudaFree(A->d_remote);
     if (A->d_boundary) cudaFree(A->d_boundary);
     if (A->side) { cudaStreamSynchronize(A->side); cudaStreamDestroy(A->side); }
+    if (A->ev_start) cudaEventDestroy(A->ev_start);
     if (A->ev_boundary) cudaEventDestroy(A->ev_boundary);
     if (A->ev_handshake) cudaEventDestroy(A->ev_handshake);
     if (A->d_done) cudaFree(A->d_done);

@@ -53,7 +53,7 @@ struct ellspmv_cuda_matrix {
     int64_t sync_boundary_slices = 0;
     bool sync_plan_valid = false;
     cudaStream_t side = nullptr;             // the step hand-shake runs here, next to the interior slices
-    cudaEvent_t ev_boundary = nullptr, ev_handshake = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_boundary = nullptr, ev_handshake = nullptr;
     bool handshake_pending = false;
     cudaStream_t stream = nullptr;
     cudaStream_t stream_out = nullptr;       // D2H stream of the pipelined host call
