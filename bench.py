@@ -382,7 +382,8 @@ def kernel_record(E, info, rows: int, K: int, idx_bits: int, ms: float, y_rmw: b
     dev_ib = int(info.dev_idx_bits) // 8 if info is not None else idx_bits // 8
     pattern_rows = int(info.pattern_rows) if info is not None else 0
     alg = n_entries * (8 + idx_bits // 8) + 8 * x_touched + 8 * rows * (2 if y_rmw else 1)
-    stored = n_entries * (8 + dev_ib) - pattern_rows * K * dev_ib + 8 * x_touched + 8 * rows * (2 if y_rmw else 1)
+    id_bytes = int(getattr(info, "pattern_id_bytes", 0)) if info is not None else 0
+    stored = n_entries * (8 + dev_ib) - pattern_rows * K * dev_ib + id_bytes + 8 * x_touched + 8 * rows * (2 if y_rmw else 1)
     return {"ms_per_step": round(ms, 5), "gflops": round(2.0 * n_entries / ms * 1e-6, 2),
             "as_stored_gbs": round(stored / ms * 1e-6, 1), "frac_as_stored": round(stored / ms * 1e-6 / peak, 4),
             "algorithmic_gbs": round(alg / ms * 1e-6, 1), "frac_algorithmic": round(alg / ms * 1e-6 / peak, 4),
@@ -631,7 +632,7 @@ def main_ours(args, rank: int, local_rank: int, world: int):
                      "traffic": recorded_traffic(workload_name(args.workload, 1) + "_iterate") if world == 1 else None,
                      "peak_source": peak_src, "bytes_per_launch": head["bytes_as_stored"],
                      "bytes_model": "as stored on the device: 8*K*rows (values) + index bytes actually read "
-                                    "(device index width; rows on an offset pattern read none) + 8*x_touched + 8*rows (y written once)",
+                                    "(device index width; rows on an offset pattern read none) + the pattern ids (one byte per group or per thread) + 8*x_touched + 8*rows (y written once)",
                      "algorithmic": {"achieved": head["algorithmic_gbs"], "frac": head["frac_algorithmic"],
                                      "bytes_per_launch": head["bytes_algorithmic"],
                                      "bytes_model": f"SURVEY 8(d): K*(8+{idx_bits // 8})*rows + 8*x_touched + 8*rows"},

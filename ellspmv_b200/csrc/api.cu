@@ -149,6 +149,7 @@ void warm_kernels(ellspmv_cuda_matrix *A)
     args.beta = 1;
     args.patid = A->pat.max_explicit ? nullptr : A->pat.patid;
     args.patinfo = A->pat.max_explicit ? A->pat.patinfo : nullptr;
+    args.patlane = A->pat.patlane;
     args.pat = A->pat.pat;
     args.rowlen = A->d_rowlen;
     // every instantiation a later launch of this handle may pick: y aligned for vector access or
@@ -194,10 +195,11 @@ int build_patterns(ellspmv_cuda_matrix *A)
         A->lay.num_rows <= 0 || A->lay.rowsize <= 0)
         return 0;
     cudaError_t ce = pattern_build(&A->pat, A->dev_idx_bits, A->cols, A->lay, A->cfg.rows_per_thread, A->row_begin,
-                                   (A->flags & ELLSPMV_CUDA_PATTERN_MASKS) ? 4 : 0, A->stream);
+                                   (A->flags & ELLSPMV_CUDA_PATTERN_MASKS) ? 4 : 0,
+                                   !(A->flags & ELLSPMV_CUDA_NO_PATTERN_LANES), A->stream);
     if (ce != cudaSuccess) { set_last_error("offset patterns: %s", cudaGetErrorString(ce)); return cuda_to_errno(ce); }
     A->device_bytes += A->pat.bytes;
-    if (A->pat.patid) warm_kernels(A);
+    if (A->pat.any()) warm_kernels(A);
     return 0;
 }
 
@@ -219,7 +221,7 @@ int auto_staged_gather(ellspmv_cuda_matrix *A, long long block_bytes)
         return 0;
     long long min_x = 96LL << 20;                    // L2 is 126 MB: below this x mostly stays resident by itself
     if (const char *env = getenv("ELLSPMV_CUDA_AUTO_STAGED_MIN_X_BYTES")) min_x = atoll(env);
-    if (x_bytes <= min_x || A->pat.patid) return 0;
+    if (x_bytes <= min_x || A->pat.any()) return 0;
     double lines = 0.0;
     ELL_CK(sg_scatter_estimate(A->dev_idx_bits, A->cols, A->lay, &lines, A->stream));
     if (lines < 16.0) return 0;                      // gathers mostly share lines: L1/L2 serve them
@@ -365,7 +367,7 @@ int launch(ellspmv_cuda_matrix *A, double *y_dev, const double *x_dev, int beta,
 bool fused_sync_capable(const ellspmv_cuda_matrix *A)
 {
     return (A->flags & ELLSPMV_CUDA_FUSED_SYNC) && A->cfg.kernel == ELLSPMV_CUDA_KERNEL_THREAD && !(A->cfg.variant & 1) && !A->sg && !A->cb && !A->sell &&
-           !A->d_rowlen && !A->pat.max_explicit && A->lay.rowsize > 0 && A->lay.num_rows > 0;
+           !A->d_rowlen && !A->pat.max_explicit && !A->pat.patlane && A->lay.rowsize > 0 && A->lay.num_rows > 0;
 }
 
 int launch(ellspmv_cuda_matrix *A, double *y_dev, const double *x_dev, int beta,
@@ -386,11 +388,12 @@ int launch(ellspmv_cuda_matrix *A, double *y_dev, const double *x_dev, int beta,
     args.sd_order = A->sd_order;
     args.patid = A->pat.max_explicit ? nullptr : A->pat.patid;
     args.patinfo = A->pat.max_explicit ? A->pat.patinfo : nullptr;
+    args.patlane = A->pat.patlane;
     args.pat = A->pat.pat;
     args.rowlen = A->d_rowlen;
     // value-stream L2 prefetch 128 slices ahead when most rows are patterned (ell_kernels.cu)
     // (long rows have the loads in flight anyway; keep one request at or below 256 KB)
-    args.prefetch = (A->pat.patid && A->pat.covered * 2 >= A->pat.groups &&
+    args.prefetch = (A->pat.any() && A->pat.covered * 2 >= A->pat.groups &&
                      (int64_t)A->lay.slice_rows * A->lay.rowsize * 8 <= (1 << 18)) ? 128 : 0;
     if (num_slices < 0) num_slices = A->lay.num_slices - slice_begin;
     if (push) args.push = *push; else args.push.num_peers = 0;
@@ -1019,6 +1022,7 @@ int ellspmv_cuda_get_info(const ellspmv_cuda_matrix *A, ellspmv_cuda_info *info)
     info->staged = A->sg ? A->staged_mode : 0;
     info->launches_per_spmv = A->sg ? sg_launches(A->sg) : (A->cb ? cb_blocks(A->cb) : (A->sell ? sell_launches(A->sell) : 1));
     info->sell_slots = A->sell ? sell_entries(A->sell) : 0;
+    info->pattern_id_bytes = A->pat.patlane ? A->pat.groups * 32 : (A->pat.max_explicit ? A->pat.groups * 8 : (A->pat.patid ? A->pat.groups : 0));
     info->tune_ms[0] = A->tune_ms[0];
     info->tune_ms[1] = A->tune_ms[1];
     info->long_rows = A->cfg.kernel == kKernelLongRow ? A->lay.rowsize : 0;

@@ -38,7 +38,8 @@ int  cuda_to_errno(cudaError_t e);
 
 constexpr int kBlockThreads = 128;  // threads per CTA of the thread-per-row kernels
 constexpr int kMaxPeers = 8;
-constexpr int kMaxPatterns = 16;    // offset-pattern dictionary size (pattern.cu)
+constexpr int kMaxPatterns = 16;    // offset-pattern dictionary size, one id per group (pattern.cu)
+constexpr int kMaxLanePatterns = 32; // ... one id per thread (the dictionary holds boundary rows' vectors too)
 
 // ---- sliced-ELL device layout -------------------------------------------
 // Rows are grouped into slices of S = kBlockThreads * R rows (R = rows per
@@ -115,6 +116,7 @@ struct EllSpmvArgs {
     int           prefetch;     // slices ahead whose value stream is requested into L2 (0 = none)
     const unsigned char *patid; // offset patterns (pattern.cu): one id per warp (32*R rows), 0xff = explicit indices; or NULL
     const unsigned long long *patinfo; // with lane masks (opt-in) instead: low byte = pattern id, high half = lanes whose rows deviate
+    const unsigned char *patlane; // or one id per THREAD (R rows): all 0xff or none in a warp (pattern.cu, lane patterns)
     const long long     *pat;   // dictionary [kMaxPatterns][K] of column offsets relative to the GLOBAL row
     StepSync      sync;
     const int    *rowlen;   // per row: how many leading slots count (CSR view: the rest is never touched
@@ -193,15 +195,18 @@ struct PatternSet {
     unsigned long long *patinfo = nullptr; // device: per group, id (low byte) | lanes that keep explicit indices << 32
     int64_t explicit_lanes = 0;       // lanes flagged in the masks of the patterned groups
     int max_explicit = 0;             // 0: whole groups only (patinfo unused by the kernel)
-    long long *pat = nullptr;         // device: kMaxPatterns * K offsets
+    unsigned char *patlane = nullptr; // device: padded_rows / R ids, one per thread of the thread-per-row kernel (lane patterns)
+    long long *pat = nullptr;         // device: kMaxLanePatterns * K offsets
     int num_patterns = 0;
     int group_rows = 32;              // 32 * rows per thread
     int64_t groups = 0, covered = 0;  // groups: all / patterned
     int64_t bytes = 0;
+    bool any() const { return patid || patlane; }
 };
 // max_explicit: lanes of a patterned group that may deviate and keep explicit indices (0 = whole groups only)
+// lanes: also try one pattern id per thread and keep it when it saves more index bytes than the ids cost
 cudaError_t pattern_build(PatternSet *ps, int idx_bits, const void *cols, const EllLayout &lay, int rows_per_thread,
-                          int64_t row_begin, int max_explicit, cudaStream_t stream);
+                          int64_t row_begin, int max_explicit, bool lanes, cudaStream_t stream);
 void pattern_free(PatternSet *ps);
 
 // ---- column-blocked ELL (ell_blocked.cu) ----------------------------------------

@@ -147,7 +147,10 @@ template <int R> struct Batch { static constexpr int U = (R == 4) ? 4 : (R == 2 
 // offset vector d[] computes col = row + d[l] from the dictionary (a uniform load that
 // lives in L1) and never touches its lines of the index stream.  PAT = 1: whole groups only
 // (the default); PAT = 2: groups may carry a few deviating lanes (ELLSPMV_CUDA_PATTERN_MASKS,
-// opt-in: measured slower on the BASELINE shapes, profiles/r2_offset_patterns.md).
+// opt-in: measured slower on the BASELINE shapes, profiles/r2_offset_patterns.md); PAT = 3: one
+// pattern id per THREAD, so a grid-boundary row sits in the same warp as its interior
+// neighbours with its own offset vector -- same instruction stream as PAT = 1, the dictionary
+// load just stops being warp-uniform (2-3 distinct L1 lines in a mixed warp).
 // LEN: rows carry their own length (a.rowlen): slots past it are loaded but never enter the
 // arithmetic.  This is the CSR view (csrgemv has no padded slots, csrspmv.c:1588-1593); only
 // instantiated for R = 1, run-time K, no patterns.
@@ -247,6 +250,11 @@ ell_thread_kernel(const EllSpmvArgs a)
                     if ((pmask >> (threadIdx.x & 31)) & 1u) rowp = lead;
                 }
             }
+        } else if (PAT == 3) {
+            // pattern.cu writes 0xff into all 32 ids of a group or into none: the branch in
+            // load_cols stays warp-uniform without a vote
+            const unsigned pid = __ldg(a.patlane + slice * kBlockThreads + threadIdx.x);
+            if (pid != 0xffu) prow = a.pat + (int64_t)pid * K;
         } else {
             const unsigned pid = __ldg(a.patid + ((slice * kBlockThreads + threadIdx.x) >> 5));
             if (pid != 0xffu) prow = a.pat + (int64_t)pid * K;
@@ -505,7 +513,7 @@ static cudaError_t launch_thread_g(const EllSpmvArgs &args, bool yvec, cudaLaunc
 {
     if (args.rowlen) {
         // per-row lengths (CSR view): one row per thread, run-time K, explicit indices
-        if (R != 1 || KU != 0 || args.patid || args.patinfo) return cudaErrorInvalidValue;
+        if (R != 1 || KU != 0 || args.patid || args.patinfo || args.patlane) return cudaErrorInvalidValue;
         if (yvec) return cudaLaunchKernelEx(&lc, ell_thread_kernel<IdxT, 1, 0, FMA, true, G, 0, true>, args);
         return cudaLaunchKernelEx(&lc, ell_thread_kernel<IdxT, 1, 0, FMA, false, G, 0, true>, args);
     }
@@ -513,7 +521,7 @@ static cudaError_t launch_thread_g(const EllSpmvArgs &args, bool yvec, cudaLaunc
         // the fused step hand-shake: separate instantiations, so that every other launch runs a
         // kernel without a trace of it (the whole-group PAT = 1 form serves masked handles too:
         // patinfo's low byte is the id)
-        if (args.patinfo) return cudaErrorNotSupported;          // api.cu does not fuse for masked handles
+        if (args.patinfo || args.patlane) return cudaErrorNotSupported;   // api.cu does not fuse for these handles
         if (args.patid) {
             if (yvec) return cudaLaunchKernelEx(&lc, ell_thread_kernel<IdxT, R, KU, FMA, true, G, 1, false, true>, args);
             return cudaLaunchKernelEx(&lc, ell_thread_kernel<IdxT, R, KU, FMA, false, G, 1, false, true>, args);
@@ -524,6 +532,10 @@ static cudaError_t launch_thread_g(const EllSpmvArgs &args, bool yvec, cudaLaunc
     if (args.patinfo) {
         if (yvec) return cudaLaunchKernelEx(&lc, ell_thread_kernel<IdxT, R, KU, FMA, true, G, 2>, args);
         return cudaLaunchKernelEx(&lc, ell_thread_kernel<IdxT, R, KU, FMA, false, G, 2>, args);
+    }
+    if (args.patlane) {
+        if (yvec) return cudaLaunchKernelEx(&lc, ell_thread_kernel<IdxT, R, KU, FMA, true, G, 3>, args);
+        return cudaLaunchKernelEx(&lc, ell_thread_kernel<IdxT, R, KU, FMA, false, G, 3>, args);
     }
     if (args.patid) {
         if (yvec) return cudaLaunchKernelEx(&lc, ell_thread_kernel<IdxT, R, KU, FMA, true, G, 1>, args);

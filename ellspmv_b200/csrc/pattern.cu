@@ -22,6 +22,14 @@
 // more than the 6 % of bytes it saves.  Three variants measured, all slower than whole groups
 // (profiles/r2_offset_patterns.md); hence opt-in.
 //
+// Lane patterns (default where they pay, ELLSPMV_CUDA_NO_PATTERN_LANES turns them off): the same
+// boundary row costs nothing when every THREAD has its own pattern id.  The dictionary then
+// holds the up to 32 most common per-thread offset vectors (interior rows and the few kinds of
+// boundary rows alike), a group is patterned when each of its 32 threads matches some entry,
+// and the kernel is the whole-group one with a per-thread id (no tail, no extra round trip:
+// id -> offsets from L1 -> gather).  One byte per thread instead of one per group, so it is
+// kept only when the index bytes it saves exceed twice that (27-point 384^3: 18 B/row saved).
+//
 // This is a device-layout choice like the 64->32-bit index narrowing: the column
 // used for every entry is the stored one (every group is verified against the
 // dictionary entry by entry, not by hash), so results stay bit-exact; the explicit
@@ -38,7 +46,7 @@ namespace ellspmv {
 
 namespace {
 
-struct PatHashes { unsigned long long h[kMaxPatterns]; };
+struct PatHashes { unsigned long long h[kMaxLanePatterns]; };
 
 __device__ __forceinline__ unsigned long long pat_mix(unsigned long long h, long long d)
 {
@@ -211,12 +219,12 @@ cudaError_t pattern_build_typed(PatternSet *ps, const IdxT *cols, const EllLayou
     for (int p = 0; p < npat; p++) { hashes.h[p] = cands[(size_t)p].h; hreps[p] = cands[(size_t)p].first; }
     if ((e = cudaMalloc(&reps, sizeof(hreps))) != cudaSuccess) { cleanup(); return e; }
     if ((e = cudaMalloc(&covered, 16)) != cudaSuccess) { cleanup(); return e; }
-    if ((e = cudaMalloc(&ps->pat, (size_t)kMaxPatterns * K * 8)) != cudaSuccess) { cleanup(); return e; }
+    if ((e = cudaMalloc(&ps->pat, (size_t)kMaxLanePatterns * K * 8)) != cudaSuccess) { cleanup(); return e; }
     if ((e = cudaMalloc(&ps->patid, (size_t)groups)) != cudaSuccess) { cleanup(); return e; }
     if ((e = cudaMalloc(&ps->patinfo, (size_t)groups * sizeof(unsigned long long))) != cudaSuccess) { cleanup(); return e; }
     if ((e = cudaMemcpyAsync(reps, hreps, sizeof(hreps), cudaMemcpyHostToDevice, stream)) != cudaSuccess ||
         (e = cudaMemsetAsync(covered, 0, 16, stream)) != cudaSuccess ||
-        (e = cudaMemsetAsync(ps->pat, 0, (size_t)kMaxPatterns * K * 8, stream)) != cudaSuccess) { cleanup(); return e; }
+        (e = cudaMemsetAsync(ps->pat, 0, (size_t)kMaxLanePatterns * K * 8, stream)) != cudaSuccess) { cleanup(); return e; }
     pat_extract_kernel<IdxT><<<npat, 128, 0, stream>>>(cols, lay, R, row_begin, reps, (const unsigned long long *)nullptr,
                                                        npat, ps->pat);
     if ((e = cudaGetLastError()) != cudaSuccess) { cleanup(); return e; }
@@ -233,7 +241,150 @@ cudaError_t pattern_build_typed(PatternSet *ps, const IdxT *cols, const EllLayou
     ps->covered = (int64_t)hc[0];
     ps->explicit_lanes = (int64_t)hc[1];
     ps->max_explicit = max_explicit;
-    ps->bytes = groups * 9 + (int64_t)kMaxPatterns * K * 8;
+    ps->bytes = groups * 9 + (int64_t)kMaxLanePatterns * K * 8;
+    return cudaSuccess;
+}
+
+// ---- lane patterns: one id per thread ---------------------------------------------------------
+// where sample i of n looks among `threads` threads: every one when they all fit, else a
+// pseudo-random one (a stride would alias with the grid: every 54th row of a 384-row line never
+// meets the line's last row)
+__host__ __device__ inline int64_t lane_sample_pos(int64_t i, int64_t n, int64_t threads)
+{
+    if (threads <= n) return i;
+    unsigned long long z = (unsigned long long)i + 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return (int64_t)(z % (unsigned long long)threads);
+}
+
+// hash of thread t's offset vector (odd), or 0 when its R rows differ or pass the last row
+template <typename IdxT>
+__device__ __forceinline__ unsigned long long lane_hash(const IdxT *__restrict__ cols, const EllLayout &lay, int R,
+                                                        int64_t row_begin, int64_t t)
+{
+    const int64_t row = t * R;
+    if (row + R > lay.num_rows) return 0ull;
+    unsigned long long h = 0x243F6A8885A308D3ull;
+    for (int l = 0; l < lay.rowsize; l++) {
+        long long d;
+        if (!lane_offset(cols, lay, R, row_begin, row, l, &d)) return 0ull;
+        h = pat_mix(h, d);
+    }
+    return h | 1ull;
+}
+
+template <typename IdxT>
+__global__ void pat_lane_sample_kernel(const IdxT *__restrict__ cols, EllLayout lay, int R, int64_t row_begin,
+                                       int64_t n, int64_t threads, unsigned long long *__restrict__ out)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = lane_hash(cols, lay, R, row_begin, lane_sample_pos(i, n, threads));
+}
+
+// dictionary entry p = the offset vector of its representative thread
+template <typename IdxT>
+__global__ void pat_lane_extract_kernel(const IdxT *__restrict__ cols, EllLayout lay, int R, int64_t row_begin,
+                                        const long long *__restrict__ reps, int npat, long long *__restrict__ pat)
+{
+    const int p = blockIdx.x;
+    if (p >= npat) return;
+    const int64_t row = reps[p] * R;
+    for (int l = threadIdx.x; l < lay.rowsize; l += blockDim.x)
+        pat[(int64_t)p * lay.rowsize + l] = (long long)cols[lay.offset(row, l)] - (row_begin + row);
+}
+
+// one warp per group: every thread looks its vector up by hash, verifies it entry by entry, and
+// the group is patterned when all 32 succeed -- else all 32 ids are 0xff (the kernel's branch on
+// the id is warp-uniform by construction)
+template <typename IdxT>
+__global__ void __launch_bounds__(256)
+pat_lane_classify_kernel(const IdxT *__restrict__ cols, EllLayout lay, int R, int64_t row_begin, int64_t num_groups,
+                         PatHashes hashes, int npat, const long long *__restrict__ pat,
+                         unsigned char *__restrict__ patlane, unsigned long long *__restrict__ covered)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t g = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (g >= num_groups) return;
+    const int64_t t = g * 32 + lane;
+    const unsigned long long h = lane_hash(cols, lay, R, row_begin, t);
+    int p = -1;
+    if (h != 0ull)
+        for (int q = 0; q < npat; q++)
+            if (hashes.h[q] == h) { p = q; break; }
+    bool mine = p >= 0;
+    if (mine) {
+        const int64_t row = t * R;
+        const long long *d = pat + (int64_t)p * lay.rowsize;
+        for (int l = 0; l < lay.rowsize && mine; l++)
+            for (int r = 0; r < R; r++) mine = mine && (long long)cols[lay.offset(row + r, l)] - (row_begin + row + r) == d[l];
+    }
+    const bool ok = __all_sync(0xffffffffu, mine);
+    patlane[t] = ok ? (unsigned char)p : (unsigned char)0xff;
+    if (ok && lane == 0) atomicAdd(covered, 1ull);
+}
+
+template <typename IdxT>
+cudaError_t pattern_build_lanes_typed(PatternSet *ps, const IdxT *cols, const EllLayout &lay, int R, int64_t row_begin,
+                                      cudaStream_t stream)
+{
+    const int64_t groups = lay.padded_rows() / (32 * R);
+    const int64_t threads = groups * 32;
+    const int K = lay.rowsize;
+    cudaError_t e;
+    unsigned long long *sample = nullptr, *covered = nullptr;
+    long long *reps = nullptr;
+    auto cleanup = [&]() { cudaFree(sample); cudaFree(covered); cudaFree(reps); };
+    const int64_t n = std::min<int64_t>(threads, 1 << 20);
+    if ((e = cudaMalloc(&sample, (size_t)n * 8)) != cudaSuccess) return e;
+    pat_lane_sample_kernel<IdxT><<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(cols, lay, R, row_begin, n, threads, sample);
+    std::vector<unsigned long long> hs((size_t)n);
+    if ((e = cudaGetLastError()) != cudaSuccess ||
+        (e = cudaMemcpyAsync(hs.data(), sample, (size_t)n * 8, cudaMemcpyDeviceToHost, stream)) != cudaSuccess ||
+        (e = cudaStreamSynchronize(stream)) != cudaSuccess) { cleanup(); return e; }
+    // the most common vectors of the sample, ties by the lowest thread that shows them
+    struct Cand { unsigned long long h; int64_t count, first; };
+    std::unordered_map<unsigned long long, Cand> seen;
+    for (int64_t i = 0; i < n; i++) {
+        if (hs[(size_t)i] == 0) continue;
+        const int64_t t = lane_sample_pos(i, n, threads);
+        auto it = seen.find(hs[(size_t)i]);
+        if (it == seen.end()) seen.emplace(hs[(size_t)i], Cand{hs[(size_t)i], 1, t});
+        else { it->second.count++; if (t < it->second.first) it->second.first = t; }
+    }
+    std::vector<Cand> cands;
+    cands.reserve(seen.size());
+    for (auto &kv : seen) cands.push_back(kv.second);
+    std::sort(cands.begin(), cands.end(), [](const Cand &a, const Cand &b) {
+        return a.count != b.count ? a.count > b.count : a.first < b.first;
+    });
+    const int npat = (int)std::min<size_t>(cands.size(), (size_t)kMaxLanePatterns);
+    if (npat == 0) { cleanup(); return cudaSuccess; }
+    PatHashes hashes = {};
+    long long hreps[kMaxLanePatterns] = {};
+    for (int p = 0; p < npat; p++) { hashes.h[p] = cands[(size_t)p].h; hreps[p] = cands[(size_t)p].first; }
+    if ((e = cudaMalloc(&reps, sizeof(hreps))) != cudaSuccess) { cleanup(); return e; }
+    if ((e = cudaMalloc(&covered, 8)) != cudaSuccess) { cleanup(); return e; }
+    if ((e = cudaMalloc(&ps->pat, (size_t)kMaxLanePatterns * K * 8)) != cudaSuccess) { cleanup(); return e; }
+    if ((e = cudaMalloc(&ps->patlane, (size_t)threads)) != cudaSuccess) { cleanup(); return e; }
+    if ((e = cudaMemcpyAsync(reps, hreps, sizeof(hreps), cudaMemcpyHostToDevice, stream)) != cudaSuccess ||
+        (e = cudaMemsetAsync(covered, 0, 8, stream)) != cudaSuccess ||
+        (e = cudaMemsetAsync(ps->pat, 0, (size_t)kMaxLanePatterns * K * 8, stream)) != cudaSuccess) { cleanup(); return e; }
+    pat_lane_extract_kernel<IdxT><<<npat, 128, 0, stream>>>(cols, lay, R, row_begin, reps, npat, ps->pat);
+    if ((e = cudaGetLastError()) != cudaSuccess) { cleanup(); return e; }
+    pat_lane_classify_kernel<IdxT><<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(cols, lay, R, row_begin, groups, hashes, npat,
+                                                                                          ps->pat, ps->patlane, covered);
+    unsigned long long hc = 0;
+    if ((e = cudaGetLastError()) != cudaSuccess ||
+        (e = cudaMemcpyAsync(&hc, covered, 8, cudaMemcpyDeviceToHost, stream)) != cudaSuccess ||
+        (e = cudaStreamSynchronize(stream)) != cudaSuccess) { cleanup(); return e; }
+    cleanup();
+    ps->num_patterns = npat;
+    ps->groups = groups;
+    ps->group_rows = 32 * R;
+    ps->covered = (int64_t)hc;
+    ps->bytes = threads + (int64_t)kMaxLanePatterns * K * 8;
     return cudaSuccess;
 }
 
@@ -243,6 +394,7 @@ void pattern_free(PatternSet *ps)
 {
     cudaFree(ps->patid);
     cudaFree(ps->patinfo);
+    cudaFree(ps->patlane);
     cudaFree(ps->pat);
     *ps = PatternSet{};
 }
@@ -250,7 +402,7 @@ void pattern_free(PatternSet *ps)
 // Leaves *ps empty (and returns success) when fewer than 1 group in 10 is patterned:
 // the table would cost a byte per group and buy nothing.
 cudaError_t pattern_build(PatternSet *ps, int idx_bits, const void *cols, const EllLayout &lay, int rows_per_thread,
-                          int64_t row_begin, int max_explicit, cudaStream_t stream)
+                          int64_t row_begin, int max_explicit, bool lanes, cudaStream_t stream)
 {
     *ps = PatternSet{};
     const int R = rows_per_thread;
@@ -260,8 +412,21 @@ cudaError_t pattern_build(PatternSet *ps, int idx_bits, const void *cols, const 
     if (max_explicit > 8) max_explicit = 8;
     cudaError_t e = idx_bits == 64 ? pattern_build_typed<int64_t>(ps, (const int64_t *)cols, lay, R, row_begin, max_explicit, stream)
                                    : pattern_build_typed<int32_t>(ps, (const int32_t *)cols, lay, R, row_begin, max_explicit, stream);
-    if (e != cudaSuccess || ps->covered * 10 < ps->groups) pattern_free(ps);
-    return e;
+    if (e != cudaSuccess) { pattern_free(ps); return e; }
+    const int64_t groups = lay.padded_rows() / (32 * R);
+    if (lanes && max_explicit == 0 && ps->covered < groups) {
+        // one id per thread instead: worth it when the index bytes of the groups it wins back
+        // exceed twice the byte per thread it costs (the ids are read by every warp)
+        PatternSet pl = PatternSet{};
+        e = idx_bits == 64 ? pattern_build_lanes_typed<int64_t>(&pl, (const int64_t *)cols, lay, R, row_begin, stream)
+                           : pattern_build_lanes_typed<int32_t>(&pl, (const int32_t *)cols, lay, R, row_begin, stream);
+        if (e != cudaSuccess) { pattern_free(&pl); pattern_free(ps); return e; }
+        const int64_t won = (pl.covered - ps->covered) * 32 * R * lay.rowsize * (idx_bits / 8);
+        if (pl.patlane && won > 2 * groups * 32) { pattern_free(ps); *ps = pl; }
+        else pattern_free(&pl);
+    }
+    if (ps->covered * 10 < ps->groups) pattern_free(ps);
+    return cudaSuccess;
 }
 
 }  // namespace ellspmv

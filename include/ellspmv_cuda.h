@@ -139,6 +139,15 @@ enum {
      * measured 10 % slower than kernel + hand-shake kernel on the 8192^2 shard
      * (profiles/r2_scaling.md): opt-in.  Same protocol, same bits. */
     ELLSPMV_CUDA_FUSED_SYNC       = 1 << 22,
+    /* lane patterns: where whole groups leave index bytes on the table (a grid boundary
+     * puts one deviating row into every 12th group of the 27-point 384^3 stencil and voids
+     * it), the upload also tries ONE PATTERN ID PER THREAD instead of one per group: the
+     * boundary row's own offset vector goes into the (32-entry) dictionary like any other
+     * and the row stays in the warp of its interior neighbours.  Kept when the index bytes
+     * saved exceed twice the byte per thread the ids cost (27-point 384^3: 83 % -> 99.9 %
+     * of the rows; 2D 5-point 8192^2: not worth it, stays on group ids).  Same kernel
+     * otherwise, same bits.  NO_PATTERN_LANES keeps group ids. */
+    ELLSPMV_CUDA_NO_PATTERN_LANES = 1 << 23,
     /* rows handled per thread in the thread-per-row kernel (1, 2 or 4):
      * 0 = auto = 2 for rows of at most 12 entries, else 1 */
     ELLSPMV_CUDA_ROWS_PER_THREAD_SHIFT = 8,
@@ -194,6 +203,9 @@ typedef struct ellspmv_cuda_info {
                              /*   kernel is used (KERNEL_AUTO)                */
     int64_t sell_slots;      /* ELLSPMV_CUDA_SKIP_PADDING: slots stored in the */
                              /*   SELL-128-sigma copy (vs num_rows * rowsize)  */
+    int64_t pattern_id_bytes;/* bytes of pattern ids one SpMV reads: one per  */
+                             /*   group of 32*R rows, or one per thread (lane */
+                             /*   patterns); 0 without offset patterns        */
 } ellspmv_cuda_info;
 
 /* ---- ELL ------------------------------------------------------------- */

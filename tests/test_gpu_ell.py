@@ -728,6 +728,49 @@ def test_offset_patterns_adversarial(lib, oracle):
             A.free()
 
 
+@pytest.mark.parametrize("bits", [32, 64])
+def test_lane_patterns_on_small_grids(lib, oracle, bits):
+    """Grids whose lines are shorter than a group: every group of 32 rows holds a boundary row, so
+    whole-group ids find (almost) nothing and one id per thread covers the matrix.  The rows on
+    the dictionary are the numpy restatement's, y is the oracle's bit for bit -- whole matrix, row
+    shard, with NO_PATTERN_LANES and NO_PATTERN beside it."""
+    rng = np.random.default_rng(77)
+    for kind, dims, K in ((E.GEN_STENCIL27, (24, 20, 16), 27), (E.GEN_STENCIL27, (48, 9, 40), 27),
+                          (E.GEN_LAPLACE2D, (96, 50), 5)):
+        G = E.EllMatrix.generate(kind, dims, (26.0, -1.0), 42, bits, flags=E.NO_PATTERN)
+        nr = int(np.prod(dims))
+        ec, ea = G.download()
+        G.free()
+        ea = rng.standard_normal(ea.shape) * (ea != 0.0)       # variable coefficients, padding stays zero
+        x = rng.standard_normal(nr)
+        want = rng.standard_normal(nr)
+        y0 = want.copy()
+        oracle.ellgemv(nr, want, x, K, ec, ea)
+        seen = {}
+        for R in (1, 2):
+            for flags, lanes in ((0, True), (E.NO_PATTERN_LANES, False)):
+                A = E.EllMatrix.upload(nr, nr, K, ec, ea, E.rows_per_thread(R) | flags)
+                rows = A.info().pattern_rows
+                assert rows == expected_pattern_rows(ec, K, nr, R, lanes=lanes), (kind, dims, R, lanes, rows)
+                seen[(R, lanes)] = rows
+                y = y0.copy()
+                A.spmv(y, x, 1, E.ACCUMULATE)
+                assert bits_equal(y, want), (kind, dims, R, lanes)
+                c2, a2 = A.download()
+                assert np.array_equal(c2, ec) and bits_equal(a2, ea)
+                A.free()
+        assert seen[(1, True)] > seen[(1, False)] and seen[(1, True)] >= 0.85 * nr, (kind, dims, seen)
+        # a row shard: local rows, global columns, an odd first row (y not vector-aligned)
+        lo, hi = nr // 3 + 1, nr - nr // 5
+        A = E.EllMatrix.upload(hi - lo, nr, K, ec[lo * K:hi * K], ea[lo * K:hi * K], E.rows_per_thread(1),
+                               global_rows=nr, row_begin=lo)
+        assert A.info().pattern_rows == expected_pattern_rows(ec[lo * K:hi * K], K, hi - lo, 1, row_begin=lo)
+        y = y0[lo:hi].copy()
+        A.spmv(y, x, 1, E.ACCUMULATE)
+        assert bits_equal(y, want[lo:hi])
+        A.free()
+
+
 def test_offset_patterns_in_a_row_shard(lib, oracle):
     """A shard's rows are local, its columns global: the pattern offsets are relative to the GLOBAL row."""
     rng = np.random.default_rng(5)
@@ -745,34 +788,50 @@ def test_offset_patterns_in_a_row_shard(lib, oracle):
     A.free()
 
 
-def expected_pattern_rows(ec, K, nr, R, row_begin=0, max_patterns=16, max_explicit=0):
+def expected_pattern_rows(ec, K, nr, R, row_begin=0, max_patterns=16, max_explicit=0, lanes=None, idx_bytes=4):
     """numpy restatement of the upload-time pattern search (pattern.cu) for matrices small
     enough that every group is sampled.  A group is the 32*R rows of one warp, lane j owning
     rows j*R..j*R+R-1; a lane has an offset vector when its R rows share one; a group's
     signature is the vector at least 32 - max_explicit of its lanes share (max_explicit = 0, the
     default: all of them; 4 with ELLSPMV_CUDA_PATTERN_MASKS); the 16 most common signatures (ties:
     first seen) form the dictionary; in a group whose signature is in it the lanes with another
-    vector keep their explicit indices.  Dropped below 10 % of the groups.
+    vector keep their explicit indices.
+    Lane patterns (default when max_explicit = 0, off with NO_PATTERN_LANES): the dictionary is the
+    32 most common LANE vectors (ties: lowest thread), a group is patterned when each of its 32
+    lanes has its vector in it; taken instead of the group ids when the index bytes of the
+    groups it wins exceed twice the byte per thread the ids cost.
+    Dropped below 10 % of the groups.
     Returns the rows that take their indices from the dictionary."""
+    if lanes is None:
+        lanes = max_explicit == 0
     S = 128 * R
     G = 32 * R
     padded = -(-nr // S) * S
     groups = padded // G
     off = ec.reshape(nr, K).astype(np.int64) - (row_begin + np.arange(nr, dtype=np.int64))[:, None]
     sig = {}
-    group_sig, group_match = [], []
+    group_sig, group_match, group_lanes = [], [], []
     for g in range(groups):
         lo, hi = g * G, (g + 1) * G
         if hi > nr:
             group_sig.append(None)
             group_match.append(0)
+            lv = []
+            for j in range(32):
+                if lo + (j + 1) * R <= nr:
+                    blk = off[lo + j * R: lo + (j + 1) * R]
+                    lv.append(tuple(blk[0]) if (blk == blk[0]).all() else None)
+                else:
+                    lv.append(None)
+            group_lanes.append(lv)
             continue
-        lanes = []
+        lv = []
         for j in range(32):
             blk = off[lo + j * R: lo + (j + 1) * R]
-            lanes.append(tuple(blk[0]) if (blk == blk[0]).all() else None)
+            lv.append(tuple(blk[0]) if (blk == blk[0]).all() else None)
+        group_lanes.append(lv)
         counts = {}
-        for v in lanes:
+        for v in lv:
             if v is not None:
                 counts[v] = counts.get(v, 0) + 1
         key, cnt = max(counts.items(), key=lambda kv: kv[1]) if counts else (None, 0)
@@ -787,9 +846,22 @@ def expected_pattern_rows(ec, K, nr, R, row_begin=0, max_patterns=16, max_explic
     best = sorted(sig.items(), key=lambda kv: (-kv[1][0], kv[1][1]))[:max_patterns]
     keep = {k for k, _ in best}
     covered = [g for g in range(groups) if group_sig[g] is not None and group_sig[g] in keep]
-    if len(covered) * 10 < groups:
+    rows = sum(group_match[g] for g in covered) * R
+    ncov = len(covered)
+    if lanes and max_explicit == 0 and ncov < groups:
+        lsig = {}
+        for g in range(groups):
+            for j, v in enumerate(group_lanes[g]):
+                if v is not None:
+                    c, first = lsig.get(v, (0, g * 32 + j))
+                    lsig[v] = (c + 1, first)
+        lkeep = {k for k, _ in sorted(lsig.items(), key=lambda kv: (-kv[1][0], kv[1][1]))[:32]}
+        lcov = sum(1 for g in range(groups) if all(v is not None and v in lkeep for v in group_lanes[g]))
+        if lkeep and (lcov - ncov) * 32 * R * K * idx_bytes > 2 * groups * 32:
+            ncov, rows = lcov, lcov * G
+    if ncov * 10 < groups:
         return 0
-    return sum(group_match[g] for g in covered) * R
+    return rows
 
 
 @pytest.mark.parametrize("seed", range(8))
@@ -815,22 +887,24 @@ def test_offset_patterns_randomized(lib, oracle, seed):
     want = np.zeros(nr)
     oracle.ellgemv(nr, want, x, K, ec, ea)
     auto_R = 2 if K <= 12 else 1
+    modes = ((0, 0, True), (E.NO_PATTERN_LANES, 0, False), (E.PATTERN_MASKS, 4, False))
     for R in (0, 1, 2, 4):
-        for flags, me in ((0, 0), (E.PATTERN_MASKS, 4)):
+        for flags, me, lanes in modes:
             A = E.EllMatrix.upload(nr, nc, K, ec, ea, (E.rows_per_thread(R) if R else 0) | flags)
             info = A.info()
             assert info.rows_per_thread == (R or auto_R)
-            assert info.pattern_rows == expected_pattern_rows(ec, K, nr, R or auto_R, max_explicit=me), (seed, K, nr, R, me)
+            assert info.pattern_rows == expected_pattern_rows(ec, K, nr, R or auto_R, max_explicit=me, lanes=lanes), (seed, K, nr, R, me, lanes)
             y = rng.standard_normal(nr)
             A.spmv(y, x, 1, E.OVERWRITE)
             assert bits_equal(y, want), (seed, K, nr, R, me)
             A.free()
     # a row shard: local rows, global columns
     lo, hi = nr // 5, nr - nr // 7
-    for flags, me in ((0, 0), (E.PATTERN_MASKS, 4)):
+    for flags, me, lanes in modes:
         A = E.EllMatrix.upload(hi - lo, nc, K, ec[lo * K:hi * K], ea[lo * K:hi * K], E.rows_per_thread(1) | flags,
                                global_rows=nr, row_begin=lo)
-        assert A.info().pattern_rows == expected_pattern_rows(ec[lo * K:hi * K], K, hi - lo, 1, row_begin=lo, max_explicit=me)
+        assert A.info().pattern_rows == expected_pattern_rows(ec[lo * K:hi * K], K, hi - lo, 1, row_begin=lo, max_explicit=me,
+                                                              lanes=lanes)
         y = np.zeros(hi - lo)
         A.spmv(y, x, 1, E.OVERWRITE)
         assert bits_equal(y, want[lo:hi])

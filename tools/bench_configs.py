@@ -55,7 +55,7 @@ def main():
     sptr = torch.cuda.current_stream().cuda_stream
     for name in args.configs.split(","):
         kind_name, kind, dims, vals, bits = configs[name]
-        variants = [("auto", 0)]
+        variants = [("auto", 0), ("auto group-ids (no lane patterns)", E.NO_PATTERN_LANES)]
         for R in (4, 2, 1):
             variants.append((f"thread R={R}", E.KERNEL_THREAD | E.rows_per_thread(R)))
         for R in (1, 2, 4):
