@@ -383,12 +383,15 @@ def kernel_record(E, info, rows: int, K: int, idx_bits: int, ms: float, y_rmw: b
     pattern_rows = int(info.pattern_rows) if info is not None else 0
     alg = n_entries * (8 + idx_bits // 8) + 8 * x_touched + 8 * rows * (2 if y_rmw else 1)
     id_bytes = int(getattr(info, "pattern_id_bytes", 0)) if info is not None else 0
-    stored = n_entries * (8 + dev_ib) - pattern_rows * K * dev_ib + id_bytes + 8 * x_touched + 8 * rows * (2 if y_rmw else 1)
+    value_rows = int(getattr(info, "value_pattern_rows", 0)) if info is not None else 0
+    stored = (n_entries * (8 + dev_ib) - pattern_rows * K * dev_ib - value_rows * K * 8 + id_bytes
+              + 8 * x_touched + 8 * rows * (2 if y_rmw else 1))
     return {"ms_per_step": round(ms, 5), "gflops": round(2.0 * n_entries / ms * 1e-6, 2),
             "as_stored_gbs": round(stored / ms * 1e-6, 1), "frac_as_stored": round(stored / ms * 1e-6 / peak, 4),
             "algorithmic_gbs": round(alg / ms * 1e-6, 1), "frac_algorithmic": round(alg / ms * 1e-6 / peak, 4),
             "bytes_as_stored": stored, "bytes_algorithmic": alg,
-            "pattern_rows_frac": round(pattern_rows / max(rows, 1), 4)}
+            "pattern_rows_frac": round(pattern_rows / max(rows, 1), 4),
+            "value_pattern_rows_frac": round(value_rows / max(rows, 1), 4)}
 
 
 def other_configs(E, torch, dev, sptr, stream, reps: int, peak: float, with_cpu: bool):

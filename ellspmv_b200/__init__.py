@@ -38,6 +38,7 @@ NO_STAGED_GATHER = 1 << 19
 SKIP_PADDING = 1 << 20
 PATTERN_MASKS = 1 << 21
 NO_PATTERN_LANES = 1 << 23
+NO_VALUE_PATTERN = 1 << 24
 FUSED_SYNC = 1 << 22
 KERNEL_CSR_SELL = 5     # CSR: SELL-128-sigma (AUTO takes it for unbalanced rows)
 WIDE_INDEX = 1 << 16
@@ -72,7 +73,7 @@ class Info(C.Structure):
         ("launches", C.c_int64), ("num_gpus", C.c_int), ("pattern_rows", C.c_int64),
         ("staged", C.c_int), ("launches_per_spmv", C.c_int), ("tune_ms", C.c_double * 2),
         ("exception_entries", C.c_int64), ("long_rows", C.c_int64), ("sell_slots", C.c_int64),
-        ("pattern_id_bytes", C.c_int64),
+        ("value_pattern_rows", C.c_int64), ("pattern_id_bytes", C.c_int64),
     ]
 
 

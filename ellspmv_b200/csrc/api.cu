@@ -151,6 +151,7 @@ void warm_kernels(ellspmv_cuda_matrix *A)
     args.patinfo = A->pat.max_explicit ? A->pat.patinfo : nullptr;
     args.patlane = A->pat.patlane;
     args.pat = A->pat.pat;
+    args.vpat = A->pat.vpat;
     args.rowlen = A->d_rowlen;
     // every instantiation a later launch of this handle may pick: y aligned for vector access or
     // not (a shard that starts at an odd row), with and without the in-kernel hand-shake.  A first
@@ -194,7 +195,9 @@ int build_patterns(ellspmv_cuda_matrix *A)
     if ((A->flags & ELLSPMV_CUDA_NO_PATTERN) || A->cfg.kernel != ELLSPMV_CUDA_KERNEL_THREAD ||
         A->lay.num_rows <= 0 || A->lay.rowsize <= 0)
         return 0;
-    cudaError_t ce = pattern_build(&A->pat, A->dev_idx_bits, A->cols, A->lay, A->cfg.rows_per_thread, A->row_begin,
+    // value patterns too (a constant-coefficient stencil streams neither indices nor values): bit-exact mode only
+    const double *pv = ((A->flags & ELLSPMV_CUDA_NO_VALUE_PATTERN) || A->cfg.fma) ? nullptr : A->vals;
+    cudaError_t ce = pattern_build(&A->pat, A->dev_idx_bits, A->cols, pv, A->lay, A->cfg.rows_per_thread, A->row_begin,
                                    (A->flags & ELLSPMV_CUDA_PATTERN_MASKS) ? 4 : 0,
                                    !(A->flags & ELLSPMV_CUDA_NO_PATTERN_LANES), A->stream);
     if (ce != cudaSuccess) { set_last_error("offset patterns: %s", cudaGetErrorString(ce)); return cuda_to_errno(ce); }
@@ -367,7 +370,7 @@ int launch(ellspmv_cuda_matrix *A, double *y_dev, const double *x_dev, int beta,
 bool fused_sync_capable(const ellspmv_cuda_matrix *A)
 {
     return (A->flags & ELLSPMV_CUDA_FUSED_SYNC) && A->cfg.kernel == ELLSPMV_CUDA_KERNEL_THREAD && !(A->cfg.variant & 1) && !A->sg && !A->cb && !A->sell &&
-           !A->d_rowlen && !A->pat.max_explicit && !A->pat.patlane && A->lay.rowsize > 0 && A->lay.num_rows > 0;
+           !A->d_rowlen && !A->pat.max_explicit && !A->pat.patlane && !A->pat.vpat && A->lay.rowsize > 0 && A->lay.num_rows > 0;
 }
 
 int launch(ellspmv_cuda_matrix *A, double *y_dev, const double *x_dev, int beta,
@@ -390,10 +393,11 @@ int launch(ellspmv_cuda_matrix *A, double *y_dev, const double *x_dev, int beta,
     args.patinfo = A->pat.max_explicit ? A->pat.patinfo : nullptr;
     args.patlane = A->pat.patlane;
     args.pat = A->pat.pat;
+    args.vpat = A->pat.vpat;
     args.rowlen = A->d_rowlen;
     // value-stream L2 prefetch 128 slices ahead when most rows are patterned (ell_kernels.cu)
     // (long rows have the loads in flight anyway; keep one request at or below 256 KB)
-    args.prefetch = (A->pat.any() && A->pat.covered * 2 >= A->pat.groups &&
+    args.prefetch = (A->pat.any() && !A->pat.vpat && A->pat.covered * 2 >= A->pat.groups &&
                      (int64_t)A->lay.slice_rows * A->lay.rowsize * 8 <= (1 << 18)) ? 128 : 0;
     if (num_slices < 0) num_slices = A->lay.num_slices - slice_begin;
     if (push) args.push = *push; else args.push.num_peers = 0;
@@ -1022,6 +1026,7 @@ int ellspmv_cuda_get_info(const ellspmv_cuda_matrix *A, ellspmv_cuda_info *info)
     info->staged = A->sg ? A->staged_mode : 0;
     info->launches_per_spmv = A->sg ? sg_launches(A->sg) : (A->cb ? cb_blocks(A->cb) : (A->sell ? sell_launches(A->sell) : 1));
     info->sell_slots = A->sell ? sell_entries(A->sell) : 0;
+    info->value_pattern_rows = A->pat.vpat ? info->pattern_rows : 0;
     info->pattern_id_bytes = A->pat.patlane ? A->pat.groups * 32 : (A->pat.max_explicit ? A->pat.groups * 8 : (A->pat.patid ? A->pat.groups : 0));
     info->tune_ms[0] = A->tune_ms[0];
     info->tune_ms[1] = A->tune_ms[1];

@@ -118,6 +118,7 @@ struct EllSpmvArgs {
     const unsigned long long *patinfo; // with lane masks (opt-in) instead: low byte = pattern id, high half = lanes whose rows deviate
     const unsigned char *patlane; // or one id per THREAD (R rows): all 0xff or none in a warp (pattern.cu, lane patterns)
     const long long     *pat;   // dictionary [kMaxPatterns][K] of column offsets relative to the GLOBAL row
+    const double        *vpat;  // value patterns: the dictionary entry's K coefficients too (then the value stream of a patterned thread is not read), or NULL
     StepSync      sync;
     const int    *rowlen;   // per row: how many leading slots count (CSR view: the rest is never touched
                             //   arithmetically, so no 0*inf from a padded slot); NULL = all K
@@ -197,6 +198,7 @@ struct PatternSet {
     int max_explicit = 0;             // 0: whole groups only (patinfo unused by the kernel)
     unsigned char *patlane = nullptr; // device: padded_rows / R ids, one per thread of the thread-per-row kernel (lane patterns)
     long long *pat = nullptr;         // device: kMaxLanePatterns * K offsets
+    double *vpat = nullptr;           // device: kMaxLanePatterns * K coefficients (value patterns), or NULL
     int num_patterns = 0;
     int group_rows = 32;              // 32 * rows per thread
     int64_t groups = 0, covered = 0;  // groups: all / patterned
@@ -205,8 +207,9 @@ struct PatternSet {
 };
 // max_explicit: lanes of a patterned group that may deviate and keep explicit indices (0 = whole groups only)
 // lanes: also try one pattern id per thread and keep it when it saves more index bytes than the ids cost
-cudaError_t pattern_build(PatternSet *ps, int idx_bits, const void *cols, const EllLayout &lay, int rows_per_thread,
-                          int64_t row_begin, int max_explicit, bool lanes, cudaStream_t stream);
+// vals: also look for value patterns (rows that share offsets AND coefficients), or NULL
+cudaError_t pattern_build(PatternSet *ps, int idx_bits, const void *cols, const double *vals, const EllLayout &lay,
+                          int rows_per_thread, int64_t row_begin, int max_explicit, bool lanes, cudaStream_t stream);
 void pattern_free(PatternSet *ps);
 
 // ---- column-blocked ELL (ell_blocked.cu) ----------------------------------------

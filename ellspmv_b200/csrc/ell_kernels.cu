@@ -151,10 +151,13 @@ template <int R> struct Batch { static constexpr int U = (R == 4) ? 4 : (R == 2 
 // pattern id per THREAD, so a grid-boundary row sits in the same warp as its interior
 // neighbours with its own offset vector -- same instruction stream as PAT = 1, the dictionary
 // load just stops being warp-uniform (2-3 distinct L1 lines in a mixed warp).
+// VPAT (with PAT = 1 or 3): value patterns -- the dictionary entry carries the K coefficients
+// too (a constant-coefficient stencil), so a patterned thread reads neither stream from HBM:
+// what is left is the x gather and the y store.
 // LEN: rows carry their own length (a.rowlen): slots past it are loaded but never enter the
 // arithmetic.  This is the CSR view (csrgemv has no padded slots, csrspmv.c:1588-1593); only
 // instantiated for R = 1, run-time K, no patterns.
-template <typename IdxT, int R, int KU, bool FMA, bool YVEC, int G, int PAT, bool LEN = false, bool SYNC = false>
+template <typename IdxT, int R, int KU, bool FMA, bool YVEC, int G, int PAT, bool LEN = false, bool SYNC = false, bool VPAT = false>
 __global__ void __launch_bounds__(kBlockThreads)
 ell_thread_kernel(const EllSpmvArgs a)
 {
@@ -227,6 +230,7 @@ ell_thread_kernel(const EllSpmvArgs a)
 
     // warp-uniform: this warp's pattern (or none); rowg = the row's global index
     const long long *__restrict__ prow = nullptr;
+    const double *__restrict__ vrow = nullptr;      // VPAT: the pattern's coefficients
     const int64_t rowg = a.row_begin + row0;
     // A patterned group may hold a few lanes whose rows deviate from its pattern (a grid
     // boundary); they are flagged in the group's mask.  The main loop below stays the plain
@@ -254,12 +258,21 @@ ell_thread_kernel(const EllSpmvArgs a)
             // pattern.cu writes 0xff into all 32 ids of a group or into none: the branch in
             // load_cols stays warp-uniform without a vote
             const unsigned pid = __ldg(a.patlane + slice * kBlockThreads + threadIdx.x);
-            if (pid != 0xffu) prow = a.pat + (int64_t)pid * K;
+            if (pid != 0xffu) { prow = a.pat + (int64_t)pid * K; if (VPAT) vrow = a.vpat + (int64_t)pid * K; }
         } else {
             const unsigned pid = __ldg(a.patid + ((slice * kBlockThreads + threadIdx.x) >> 5));
-            if (pid != 0xffu) prow = a.pat + (int64_t)pid * K;
+            if (pid != 0xffu) { prow = a.pat + (int64_t)pid * K; if (VPAT) vrow = a.vpat + (int64_t)pid * K; }
         }
     }
+    auto load_vals = [&](int l, double (&v)[R]) {
+        if (VPAT && prow) {
+            const double av = __ldg(vrow + l);
+#pragma unroll
+            for (int r = 0; r < R; r++) v[r] = av;
+        } else {
+            Vals<R>::ld(vp + (int64_t)l * S, v);
+        }
+    };
     auto load_cols = [&](int l, int64_t (&c)[R]) {
         if (PAT && prow) {
             const int64_t c0 = (PAT == 2 ? rowp : rowg) + __ldg(prow + l);
@@ -318,7 +331,7 @@ ell_thread_kernel(const EllSpmvArgs a)
             double v[U][R]; int64_t c[U][R]; double xv[U][R];
 #pragma unroll
             for (int u = 0; u < U; u++) if (l0 + u < KU) {
-                Vals<R>::ld(vp + (int64_t)(l0 + u) * S, v[u]);
+                load_vals(l0 + u, v[u]);
                 load_cols(l0 + u, c[u]);
             }
 #pragma unroll
@@ -340,7 +353,7 @@ ell_thread_kernel(const EllSpmvArgs a)
             double v[U][R]; int64_t c[U][R]; double xv[U][R];
 #pragma unroll
             for (int u = 0; u < U; u++) {
-                Vals<R>::ld(vp + (int64_t)(l0 + u) * S, v[u]);
+                load_vals(l0 + u, v[u]);
                 load_cols(l0 + u, c[u]);
             }
 #pragma unroll
@@ -358,7 +371,7 @@ ell_thread_kernel(const EllSpmvArgs a)
 #pragma unroll 1
         for (; l0 < Kl; l0++) {
             double v[R]; int64_t c[R];
-            Vals<R>::ld(vp + (int64_t)l0 * S, v);
+            load_vals(l0, v);
             load_cols(l0, c);
 #pragma unroll
             for (int r = 0; r < R; r++)
@@ -513,7 +526,7 @@ static cudaError_t launch_thread_g(const EllSpmvArgs &args, bool yvec, cudaLaunc
 {
     if (args.rowlen) {
         // per-row lengths (CSR view): one row per thread, run-time K, explicit indices
-        if (R != 1 || KU != 0 || args.patid || args.patinfo || args.patlane) return cudaErrorInvalidValue;
+        if (R != 1 || KU != 0 || args.patid || args.patinfo || args.patlane || args.vpat) return cudaErrorInvalidValue;
         if (yvec) return cudaLaunchKernelEx(&lc, ell_thread_kernel<IdxT, 1, 0, FMA, true, G, 0, true>, args);
         return cudaLaunchKernelEx(&lc, ell_thread_kernel<IdxT, 1, 0, FMA, false, G, 0, true>, args);
     }
@@ -521,7 +534,7 @@ static cudaError_t launch_thread_g(const EllSpmvArgs &args, bool yvec, cudaLaunc
         // the fused step hand-shake: separate instantiations, so that every other launch runs a
         // kernel without a trace of it (the whole-group PAT = 1 form serves masked handles too:
         // patinfo's low byte is the id)
-        if (args.patinfo || args.patlane) return cudaErrorNotSupported;   // api.cu does not fuse for these handles
+        if (args.patinfo || args.patlane || args.vpat) return cudaErrorNotSupported;   // api.cu does not fuse for these handles
         if (args.patid) {
             if (yvec) return cudaLaunchKernelEx(&lc, ell_thread_kernel<IdxT, R, KU, FMA, true, G, 1, false, true>, args);
             return cudaLaunchKernelEx(&lc, ell_thread_kernel<IdxT, R, KU, FMA, false, G, 1, false, true>, args);
@@ -532,6 +545,20 @@ static cudaError_t launch_thread_g(const EllSpmvArgs &args, bool yvec, cudaLaunc
     if (args.patinfo) {
         if (yvec) return cudaLaunchKernelEx(&lc, ell_thread_kernel<IdxT, R, KU, FMA, true, G, 2>, args);
         return cudaLaunchKernelEx(&lc, ell_thread_kernel<IdxT, R, KU, FMA, false, G, 2>, args);
+    }
+    if (args.vpat) {
+        // value patterns: bit-exact arithmetic only (api.cu does not look for them with FMA)
+        if constexpr (!FMA) {
+            if (args.patlane) {
+                if (yvec) return cudaLaunchKernelEx(&lc, ell_thread_kernel<IdxT, R, KU, false, true, G, 3, false, false, true>, args);
+                return cudaLaunchKernelEx(&lc, ell_thread_kernel<IdxT, R, KU, false, false, G, 3, false, false, true>, args);
+            }
+            if (args.patid) {
+                if (yvec) return cudaLaunchKernelEx(&lc, ell_thread_kernel<IdxT, R, KU, false, true, G, 1, false, false, true>, args);
+                return cudaLaunchKernelEx(&lc, ell_thread_kernel<IdxT, R, KU, false, false, G, 1, false, false, true>, args);
+            }
+        }
+        return cudaErrorNotSupported;
     }
     if (args.patlane) {
         if (yvec) return cudaLaunchKernelEx(&lc, ell_thread_kernel<IdxT, R, KU, FMA, true, G, 3>, args);

@@ -221,6 +221,7 @@ int group_info(const ellspmv_cuda_matrix *G, ellspmv_cuda_info *info)
         launches += S->launches;
         info->pattern_rows += S->pat.covered * S->pat.group_rows - S->pat.explicit_lanes * S->cfg.rows_per_thread;
         info->exception_entries += S->pat.explicit_lanes * S->cfg.rows_per_thread * S->lay.rowsize;
+        if (S->pat.vpat) info->value_pattern_rows += S->pat.covered * S->pat.group_rows;
         info->pattern_id_bytes += S->pat.patlane ? S->pat.groups * 32 : (S->pat.max_explicit ? S->pat.groups * 8 : (S->pat.patid ? S->pat.groups : 0));
     }
     info->launches = launches;

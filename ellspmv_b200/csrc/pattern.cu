@@ -66,13 +66,24 @@ __device__ __forceinline__ bool lane_offset(const IdxT *__restrict__ cols, const
     return same;
 }
 
+// same for the values (only when the handle looks for value patterns): the bit pattern of the
+// lane's R rows at slot l, equal for all R rows, or not
+__device__ __forceinline__ bool lane_value(const double *__restrict__ vals, const EllLayout &lay, int R,
+                                           int64_t row, int l, long long *bits)
+{
+    *bits = __double_as_longlong(vals[lay.offset(row, l)]);
+    bool same = true;
+    for (int r = 1; r < R; r++) same = same && __double_as_longlong(vals[lay.offset(row + r, l)]) == *bits;
+    return same;
+}
+
 // one warp per group of 32*R rows (the rows one warp of the thread-per-row kernel owns; lane j
 // holds rows j*R .. j*R+R-1 of it).  Every lane hashes its own offset vector; the group's
 // signature is the hash that at least 32 - kPatMaxExplicit lanes share, 0 if there is none.
 template <typename IdxT>
 __global__ void __launch_bounds__(256)
-pat_signature_kernel(const IdxT *__restrict__ cols, EllLayout lay, int R, int64_t row_begin, int64_t num_groups,
-                     int max_explicit, unsigned long long *__restrict__ sig)
+pat_signature_kernel(const IdxT *__restrict__ cols, const double *__restrict__ vals, EllLayout lay, int R, int64_t row_begin,
+                     int64_t num_groups, int max_explicit, unsigned long long *__restrict__ sig)
 {
     const int lane = threadIdx.x & 31;
     const int64_t g = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
@@ -85,6 +96,7 @@ pat_signature_kernel(const IdxT *__restrict__ cols, EllLayout lay, int R, int64_
         long long d;
         lane_ok = lane_offset(cols, lay, R, row_begin, row, l, &d);
         h = pat_mix(h, d);
+        if (vals && lane_ok) { lane_ok = lane_value(vals, lay, R, row, l, &d); h = pat_mix(h, d); }
     }
     h |= 1ull;
     if (!lane_ok) h = 2ull * (unsigned long long)(lane + 1);               // even: never equal to a real hash or each other
@@ -105,9 +117,9 @@ __global__ void pat_sample_kernel(const unsigned long long *__restrict__ sig, in
 // dictionary entry p = the offset vector most lanes of its representative group share (the lane
 // is found again here: the first lane whose own hash is the group's signature)
 template <typename IdxT>
-__global__ void pat_extract_kernel(const IdxT *__restrict__ cols, EllLayout lay, int R, int64_t row_begin,
-                                   const long long *__restrict__ reps, const unsigned long long *, int npat,
-                                   long long *__restrict__ pat)
+__global__ void pat_extract_kernel(const IdxT *__restrict__ cols, const double *__restrict__ vals, EllLayout lay, int R, int64_t row_begin,
+                                   const long long *__restrict__ reps, int npat,
+                                   long long *__restrict__ pat, double *__restrict__ vpat)
 {
     const int p = blockIdx.x;
     if (p >= npat) return;
@@ -121,6 +133,7 @@ __global__ void pat_extract_kernel(const IdxT *__restrict__ cols, EllLayout lay,
             long long d;
             lane_ok = lane_offset(cols, lay, R, row_begin, row, l, &d);
             h = pat_mix(h, d);
+            if (vals && lane_ok) { lane_ok = lane_value(vals, lay, R, row, l, &d); h = pat_mix(h, d); }
         }
         h |= 1ull;
         if (!lane_ok) h = 2ull * (unsigned long long)(lane + 1);
@@ -131,8 +144,10 @@ __global__ void pat_extract_kernel(const IdxT *__restrict__ cols, EllLayout lay,
     }
     __syncthreads();
     const int64_t row = (reps[p] * 32 + s_lane) * R;
-    for (int l = threadIdx.x; l < lay.rowsize; l += blockDim.x)
+    for (int l = threadIdx.x; l < lay.rowsize; l += blockDim.x) {
         pat[(int64_t)p * lay.rowsize + l] = (long long)cols[lay.offset(row, l)] - (row_begin + row);
+        if (vals) vpat[(int64_t)p * lay.rowsize + l] = vals[lay.offset(row, l)];
+    }
 }
 
 // final word: every lane is checked entry by entry against dictionary pattern p; the lanes that
@@ -140,9 +155,9 @@ __global__ void pat_extract_kernel(const IdxT *__restrict__ cols, EllLayout lay,
 // pattern if at most kPatMaxExplicit lanes do
 template <typename IdxT>
 __global__ void __launch_bounds__(256)
-pat_classify_kernel(const IdxT *__restrict__ cols, EllLayout lay, int R, int64_t row_begin, int64_t num_groups,
-                    int max_explicit, const unsigned long long *__restrict__ sig, PatHashes hashes, int npat,
-                    const long long *__restrict__ pat, unsigned char *__restrict__ patid,
+pat_classify_kernel(const IdxT *__restrict__ cols, const double *__restrict__ vals, EllLayout lay, int R, int64_t row_begin,
+                    int64_t num_groups, int max_explicit, const unsigned long long *__restrict__ sig, PatHashes hashes, int npat,
+                    const long long *__restrict__ pat, const double *__restrict__ vpat, unsigned char *__restrict__ patid,
                     unsigned long long *__restrict__ patinfo, unsigned long long *__restrict__ covered)
 {
     const int lane = threadIdx.x & 31;
@@ -160,7 +175,11 @@ pat_classify_kernel(const IdxT *__restrict__ cols, EllLayout lay, int R, int64_t
         const long long *d = pat + (int64_t)p * lay.rowsize;
         bool mine = true;
         for (int l = 0; l < lay.rowsize && mine; l++)
-            for (int r = 0; r < R; r++) mine = mine && (long long)cols[lay.offset(row + r, l)] - (row_begin + row + r) == d[l];
+            for (int r = 0; r < R; r++) {
+                mine = mine && (long long)cols[lay.offset(row + r, l)] - (row_begin + row + r) == d[l];
+                if (vals) mine = mine && __double_as_longlong(vals[lay.offset(row + r, l)]) ==
+                                             __double_as_longlong(vpat[(int64_t)p * lay.rowsize + l]);
+            }
         mask = ~__ballot_sync(0xffffffffu, mine);
         ok = __popc(mask) <= max_explicit;
     }
@@ -173,8 +192,8 @@ pat_classify_kernel(const IdxT *__restrict__ cols, EllLayout lay, int R, int64_t
 }
 
 template <typename IdxT>
-cudaError_t pattern_build_typed(PatternSet *ps, const IdxT *cols, const EllLayout &lay, int R, int64_t row_begin,
-                                int max_explicit, cudaStream_t stream)
+cudaError_t pattern_build_typed(PatternSet *ps, const IdxT *cols, const double *vals, const EllLayout &lay, int R,
+                                int64_t row_begin, int max_explicit, cudaStream_t stream)
 {
     const int64_t groups = lay.padded_rows() / (32 * R);
     const int K = lay.rowsize;
@@ -184,7 +203,7 @@ cudaError_t pattern_build_typed(PatternSet *ps, const IdxT *cols, const EllLayou
     auto cleanup = [&]() { cudaFree(sig); cudaFree(sample); cudaFree(covered); cudaFree(reps); };
     if ((e = cudaMalloc(&sig, (size_t)groups * 8)) != cudaSuccess) return e;
     const unsigned grid = (unsigned)((groups * 32 + 255) / 256);
-    pat_signature_kernel<IdxT><<<grid, 256, 0, stream>>>(cols, lay, R, row_begin, groups, max_explicit, sig);
+    pat_signature_kernel<IdxT><<<grid, 256, 0, stream>>>(cols, vals, lay, R, row_begin, groups, max_explicit, sig);
     if ((e = cudaGetLastError()) != cudaSuccess) { cleanup(); return e; }
 
     // dictionary candidates: the most common signatures of a strided sample (the
@@ -220,16 +239,16 @@ cudaError_t pattern_build_typed(PatternSet *ps, const IdxT *cols, const EllLayou
     if ((e = cudaMalloc(&reps, sizeof(hreps))) != cudaSuccess) { cleanup(); return e; }
     if ((e = cudaMalloc(&covered, 16)) != cudaSuccess) { cleanup(); return e; }
     if ((e = cudaMalloc(&ps->pat, (size_t)kMaxLanePatterns * K * 8)) != cudaSuccess) { cleanup(); return e; }
+    if (vals && (e = cudaMalloc(&ps->vpat, (size_t)kMaxLanePatterns * K * 8)) != cudaSuccess) { cleanup(); return e; }
     if ((e = cudaMalloc(&ps->patid, (size_t)groups)) != cudaSuccess) { cleanup(); return e; }
     if ((e = cudaMalloc(&ps->patinfo, (size_t)groups * sizeof(unsigned long long))) != cudaSuccess) { cleanup(); return e; }
     if ((e = cudaMemcpyAsync(reps, hreps, sizeof(hreps), cudaMemcpyHostToDevice, stream)) != cudaSuccess ||
         (e = cudaMemsetAsync(covered, 0, 16, stream)) != cudaSuccess ||
         (e = cudaMemsetAsync(ps->pat, 0, (size_t)kMaxLanePatterns * K * 8, stream)) != cudaSuccess) { cleanup(); return e; }
-    pat_extract_kernel<IdxT><<<npat, 128, 0, stream>>>(cols, lay, R, row_begin, reps, (const unsigned long long *)nullptr,
-                                                       npat, ps->pat);
+    pat_extract_kernel<IdxT><<<npat, 128, 0, stream>>>(cols, vals, lay, R, row_begin, reps, npat, ps->pat, ps->vpat);
     if ((e = cudaGetLastError()) != cudaSuccess) { cleanup(); return e; }
-    pat_classify_kernel<IdxT><<<grid, 256, 0, stream>>>(cols, lay, R, row_begin, groups, max_explicit, sig, hashes, npat, ps->pat,
-                                                        ps->patid, ps->patinfo, covered);
+    pat_classify_kernel<IdxT><<<grid, 256, 0, stream>>>(cols, vals, lay, R, row_begin, groups, max_explicit, sig, hashes, npat, ps->pat,
+                                                        ps->vpat, ps->patid, ps->patinfo, covered);
     unsigned long long hc[2] = {0, 0};
     if ((e = cudaGetLastError()) != cudaSuccess ||
         (e = cudaMemcpyAsync(hc, covered, 16, cudaMemcpyDeviceToHost, stream)) != cudaSuccess ||
@@ -261,8 +280,8 @@ __host__ __device__ inline int64_t lane_sample_pos(int64_t i, int64_t n, int64_t
 
 // hash of thread t's offset vector (odd), or 0 when its R rows differ or pass the last row
 template <typename IdxT>
-__device__ __forceinline__ unsigned long long lane_hash(const IdxT *__restrict__ cols, const EllLayout &lay, int R,
-                                                        int64_t row_begin, int64_t t)
+__device__ __forceinline__ unsigned long long lane_hash(const IdxT *__restrict__ cols, const double *__restrict__ vals,
+                                                        const EllLayout &lay, int R, int64_t row_begin, int64_t t)
 {
     const int64_t row = t * R;
     if (row + R > lay.num_rows) return 0ull;
@@ -271,28 +290,35 @@ __device__ __forceinline__ unsigned long long lane_hash(const IdxT *__restrict__
         long long d;
         if (!lane_offset(cols, lay, R, row_begin, row, l, &d)) return 0ull;
         h = pat_mix(h, d);
+        if (vals) {
+            if (!lane_value(vals, lay, R, row, l, &d)) return 0ull;
+            h = pat_mix(h, d);
+        }
     }
     return h | 1ull;
 }
 
 template <typename IdxT>
-__global__ void pat_lane_sample_kernel(const IdxT *__restrict__ cols, EllLayout lay, int R, int64_t row_begin,
-                                       int64_t n, int64_t threads, unsigned long long *__restrict__ out)
+__global__ void pat_lane_sample_kernel(const IdxT *__restrict__ cols, const double *__restrict__ vals, EllLayout lay, int R,
+                                       int64_t row_begin, int64_t n, int64_t threads, unsigned long long *__restrict__ out)
 {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i < n) out[i] = lane_hash(cols, lay, R, row_begin, lane_sample_pos(i, n, threads));
+    if (i < n) out[i] = lane_hash(cols, vals, lay, R, row_begin, lane_sample_pos(i, n, threads));
 }
 
 // dictionary entry p = the offset vector of its representative thread
 template <typename IdxT>
-__global__ void pat_lane_extract_kernel(const IdxT *__restrict__ cols, EllLayout lay, int R, int64_t row_begin,
-                                        const long long *__restrict__ reps, int npat, long long *__restrict__ pat)
+__global__ void pat_lane_extract_kernel(const IdxT *__restrict__ cols, const double *__restrict__ vals, EllLayout lay, int R,
+                                        int64_t row_begin, const long long *__restrict__ reps, int npat,
+                                        long long *__restrict__ pat, double *__restrict__ vpat)
 {
     const int p = blockIdx.x;
     if (p >= npat) return;
     const int64_t row = reps[p] * R;
-    for (int l = threadIdx.x; l < lay.rowsize; l += blockDim.x)
+    for (int l = threadIdx.x; l < lay.rowsize; l += blockDim.x) {
         pat[(int64_t)p * lay.rowsize + l] = (long long)cols[lay.offset(row, l)] - (row_begin + row);
+        if (vals) vpat[(int64_t)p * lay.rowsize + l] = vals[lay.offset(row, l)];
+    }
 }
 
 // one warp per group: every thread looks its vector up by hash, verifies it entry by entry, and
@@ -300,15 +326,16 @@ __global__ void pat_lane_extract_kernel(const IdxT *__restrict__ cols, EllLayout
 // the id is warp-uniform by construction)
 template <typename IdxT>
 __global__ void __launch_bounds__(256)
-pat_lane_classify_kernel(const IdxT *__restrict__ cols, EllLayout lay, int R, int64_t row_begin, int64_t num_groups,
-                         PatHashes hashes, int npat, const long long *__restrict__ pat,
-                         unsigned char *__restrict__ patlane, unsigned long long *__restrict__ covered)
+pat_lane_classify_kernel(const IdxT *__restrict__ cols, const double *__restrict__ vals, EllLayout lay, int R, int64_t row_begin,
+                         int64_t num_groups, PatHashes hashes, int npat, const long long *__restrict__ pat,
+                         const double *__restrict__ vpat, unsigned char *__restrict__ patlane,
+                         unsigned long long *__restrict__ covered)
 {
     const int lane = threadIdx.x & 31;
     const int64_t g = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     if (g >= num_groups) return;
     const int64_t t = g * 32 + lane;
-    const unsigned long long h = lane_hash(cols, lay, R, row_begin, t);
+    const unsigned long long h = lane_hash(cols, vals, lay, R, row_begin, t);
     int p = -1;
     if (h != 0ull)
         for (int q = 0; q < npat; q++)
@@ -318,7 +345,11 @@ pat_lane_classify_kernel(const IdxT *__restrict__ cols, EllLayout lay, int R, in
         const int64_t row = t * R;
         const long long *d = pat + (int64_t)p * lay.rowsize;
         for (int l = 0; l < lay.rowsize && mine; l++)
-            for (int r = 0; r < R; r++) mine = mine && (long long)cols[lay.offset(row + r, l)] - (row_begin + row + r) == d[l];
+            for (int r = 0; r < R; r++) {
+                mine = mine && (long long)cols[lay.offset(row + r, l)] - (row_begin + row + r) == d[l];
+                if (vals) mine = mine && __double_as_longlong(vals[lay.offset(row + r, l)]) ==
+                                             __double_as_longlong(vpat[(int64_t)p * lay.rowsize + l]);
+            }
     }
     const bool ok = __all_sync(0xffffffffu, mine);
     patlane[t] = ok ? (unsigned char)p : (unsigned char)0xff;
@@ -326,8 +357,8 @@ pat_lane_classify_kernel(const IdxT *__restrict__ cols, EllLayout lay, int R, in
 }
 
 template <typename IdxT>
-cudaError_t pattern_build_lanes_typed(PatternSet *ps, const IdxT *cols, const EllLayout &lay, int R, int64_t row_begin,
-                                      cudaStream_t stream)
+cudaError_t pattern_build_lanes_typed(PatternSet *ps, const IdxT *cols, const double *vals, const EllLayout &lay, int R,
+                                      int64_t row_begin, cudaStream_t stream)
 {
     const int64_t groups = lay.padded_rows() / (32 * R);
     const int64_t threads = groups * 32;
@@ -338,7 +369,7 @@ cudaError_t pattern_build_lanes_typed(PatternSet *ps, const IdxT *cols, const El
     auto cleanup = [&]() { cudaFree(sample); cudaFree(covered); cudaFree(reps); };
     const int64_t n = std::min<int64_t>(threads, 1 << 20);
     if ((e = cudaMalloc(&sample, (size_t)n * 8)) != cudaSuccess) return e;
-    pat_lane_sample_kernel<IdxT><<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(cols, lay, R, row_begin, n, threads, sample);
+    pat_lane_sample_kernel<IdxT><<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(cols, vals, lay, R, row_begin, n, threads, sample);
     std::vector<unsigned long long> hs((size_t)n);
     if ((e = cudaGetLastError()) != cudaSuccess ||
         (e = cudaMemcpyAsync(hs.data(), sample, (size_t)n * 8, cudaMemcpyDeviceToHost, stream)) != cudaSuccess ||
@@ -367,14 +398,15 @@ cudaError_t pattern_build_lanes_typed(PatternSet *ps, const IdxT *cols, const El
     if ((e = cudaMalloc(&reps, sizeof(hreps))) != cudaSuccess) { cleanup(); return e; }
     if ((e = cudaMalloc(&covered, 8)) != cudaSuccess) { cleanup(); return e; }
     if ((e = cudaMalloc(&ps->pat, (size_t)kMaxLanePatterns * K * 8)) != cudaSuccess) { cleanup(); return e; }
+    if (vals && (e = cudaMalloc(&ps->vpat, (size_t)kMaxLanePatterns * K * 8)) != cudaSuccess) { cleanup(); return e; }
     if ((e = cudaMalloc(&ps->patlane, (size_t)threads)) != cudaSuccess) { cleanup(); return e; }
     if ((e = cudaMemcpyAsync(reps, hreps, sizeof(hreps), cudaMemcpyHostToDevice, stream)) != cudaSuccess ||
         (e = cudaMemsetAsync(covered, 0, 8, stream)) != cudaSuccess ||
         (e = cudaMemsetAsync(ps->pat, 0, (size_t)kMaxLanePatterns * K * 8, stream)) != cudaSuccess) { cleanup(); return e; }
-    pat_lane_extract_kernel<IdxT><<<npat, 128, 0, stream>>>(cols, lay, R, row_begin, reps, npat, ps->pat);
+    pat_lane_extract_kernel<IdxT><<<npat, 128, 0, stream>>>(cols, vals, lay, R, row_begin, reps, npat, ps->pat, ps->vpat);
     if ((e = cudaGetLastError()) != cudaSuccess) { cleanup(); return e; }
-    pat_lane_classify_kernel<IdxT><<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(cols, lay, R, row_begin, groups, hashes, npat,
-                                                                                          ps->pat, ps->patlane, covered);
+    pat_lane_classify_kernel<IdxT><<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(cols, vals, lay, R, row_begin, groups, hashes,
+                                                                                          npat, ps->pat, ps->vpat, ps->patlane, covered);
     unsigned long long hc = 0;
     if ((e = cudaGetLastError()) != cudaSuccess ||
         (e = cudaMemcpyAsync(&hc, covered, 8, cudaMemcpyDeviceToHost, stream)) != cudaSuccess ||
@@ -395,14 +427,42 @@ void pattern_free(PatternSet *ps)
     cudaFree(ps->patid);
     cudaFree(ps->patinfo);
     cudaFree(ps->patlane);
+    cudaFree(ps->vpat);
     cudaFree(ps->pat);
     *ps = PatternSet{};
 }
 
+// one search, with the values in the signatures or without: group ids first, then (lanes) one id
+// per thread when that wins back more bytes than twice the byte per thread the ids cost
+static cudaError_t pattern_search(PatternSet *ps, int idx_bits, const void *cols, const double *vals, const EllLayout &lay,
+                                  int R, int64_t row_begin, int max_explicit, bool lanes, cudaStream_t stream)
+{
+    *ps = PatternSet{};
+    cudaError_t e = idx_bits == 64 ? pattern_build_typed<int64_t>(ps, (const int64_t *)cols, vals, lay, R, row_begin, max_explicit, stream)
+                                   : pattern_build_typed<int32_t>(ps, (const int32_t *)cols, vals, lay, R, row_begin, max_explicit, stream);
+    if (e != cudaSuccess) { pattern_free(ps); return e; }
+    const int64_t groups = lay.padded_rows() / (32 * R);
+    if (lanes && max_explicit == 0 && ps->covered < groups) {
+        PatternSet pl = PatternSet{};
+        e = idx_bits == 64 ? pattern_build_lanes_typed<int64_t>(&pl, (const int64_t *)cols, vals, lay, R, row_begin, stream)
+                           : pattern_build_lanes_typed<int32_t>(&pl, (const int32_t *)cols, vals, lay, R, row_begin, stream);
+        if (e != cudaSuccess) { pattern_free(&pl); pattern_free(ps); return e; }
+        const int64_t per_entry = idx_bits / 8 + (vals ? 8 : 0);
+        const int64_t won = (pl.covered - ps->covered) * 32 * R * lay.rowsize * per_entry;
+        if (pl.patlane && won > 2 * groups * 32) { pattern_free(ps); *ps = pl; }
+        else pattern_free(&pl);
+    }
+    return cudaSuccess;
+}
+
 // Leaves *ps empty (and returns success) when fewer than 1 group in 10 is patterned:
 // the table would cost a byte per group and buy nothing.
-cudaError_t pattern_build(PatternSet *ps, int idx_bits, const void *cols, const EllLayout &lay, int rows_per_thread,
-                          int64_t row_begin, int max_explicit, bool lanes, cudaStream_t stream)
+// vals != NULL: also look for VALUE patterns -- rows that share offsets AND coefficients (a
+// constant-coefficient stencil); the dictionary entry then carries both and a patterned thread
+// streams neither indices nor values.  Taken when it covers at least 9/10 of the rows the
+// index-only search covers (a matrix with variable coefficients has none and keeps index patterns).
+cudaError_t pattern_build(PatternSet *ps, int idx_bits, const void *cols, const double *vals, const EllLayout &lay,
+                          int rows_per_thread, int64_t row_begin, int max_explicit, bool lanes, cudaStream_t stream)
 {
     *ps = PatternSet{};
     const int R = rows_per_thread;
@@ -410,22 +470,16 @@ cudaError_t pattern_build(PatternSet *ps, int idx_bits, const void *cols, const 
         return cudaSuccess;
     if (max_explicit < 0) max_explicit = 0;
     if (max_explicit > 8) max_explicit = 8;
-    cudaError_t e = idx_bits == 64 ? pattern_build_typed<int64_t>(ps, (const int64_t *)cols, lay, R, row_begin, max_explicit, stream)
-                                   : pattern_build_typed<int32_t>(ps, (const int32_t *)cols, lay, R, row_begin, max_explicit, stream);
-    if (e != cudaSuccess) { pattern_free(ps); return e; }
-    const int64_t groups = lay.padded_rows() / (32 * R);
-    if (lanes && max_explicit == 0 && ps->covered < groups) {
-        // one id per thread instead: worth it when the index bytes of the groups it wins back
-        // exceed twice the byte per thread it costs (the ids are read by every warp)
-        PatternSet pl = PatternSet{};
-        e = idx_bits == 64 ? pattern_build_lanes_typed<int64_t>(&pl, (const int64_t *)cols, lay, R, row_begin, stream)
-                           : pattern_build_lanes_typed<int32_t>(&pl, (const int32_t *)cols, lay, R, row_begin, stream);
-        if (e != cudaSuccess) { pattern_free(&pl); pattern_free(ps); return e; }
-        const int64_t won = (pl.covered - ps->covered) * 32 * R * lay.rowsize * (idx_bits / 8);
-        if (pl.patlane && won > 2 * groups * 32) { pattern_free(ps); *ps = pl; }
-        else pattern_free(&pl);
+    cudaError_t e = pattern_search(ps, idx_bits, cols, nullptr, lay, R, row_begin, max_explicit, lanes, stream);
+    if (e != cudaSuccess) return e;
+    if (ps->covered * 10 < ps->groups) { pattern_free(ps); return cudaSuccess; }
+    if (vals && max_explicit == 0) {
+        PatternSet pv = PatternSet{};
+        e = pattern_search(&pv, idx_bits, cols, vals, lay, R, row_begin, 0, lanes, stream);
+        if (e != cudaSuccess) { pattern_free(ps); return e; }
+        if (pv.vpat && pv.covered * 10 >= ps->covered * 9) { pattern_free(ps); *ps = pv; }
+        else pattern_free(&pv);
     }
-    if (ps->covered * 10 < ps->groups) pattern_free(ps);
     return cudaSuccess;
 }
 

@@ -148,6 +148,17 @@ enum {
      * of the rows; 2D 5-point 8192^2: not worth it, stays on group ids).  Same kernel
      * otherwise, same bits.  NO_PATTERN_LANES keeps group ids. */
     ELLSPMV_CUDA_NO_PATTERN_LANES = 1 << 23,
+    /* value patterns: in a constant-coefficient stencil the rows share not only their column
+     * offsets but their COEFFICIENTS (2D 5-point Laplacian: 4, -1, -1, -1, -1 in every interior
+     * row).  The upload looks for that too -- the pattern signature then includes the bit
+     * patterns of the values, every row is verified entry by entry, bit for bit -- and a
+     * dictionary entry carries offsets and coefficients: a patterned thread streams neither
+     * indices nor values from HBM; what is left is the x gather and the y store.  Taken when it
+     * covers at least 9/10 of the rows the index-only search covers; a matrix with variable
+     * coefficients keeps index patterns and its value stream.  Same arithmetic on the same
+     * numbers in the same order: same bits.  Not searched with ELLSPMV_CUDA_FMA.
+     * NO_VALUE_PATTERN streams the values always. */
+    ELLSPMV_CUDA_NO_VALUE_PATTERN = 1 << 24,
     /* rows handled per thread in the thread-per-row kernel (1, 2 or 4):
      * 0 = auto = 2 for rows of at most 12 entries, else 1 */
     ELLSPMV_CUDA_ROWS_PER_THREAD_SHIFT = 8,
@@ -203,6 +214,9 @@ typedef struct ellspmv_cuda_info {
                              /*   kernel is used (KERNEL_AUTO)                */
     int64_t sell_slots;      /* ELLSPMV_CUDA_SKIP_PADDING: slots stored in the */
                              /*   SELL-128-sigma copy (vs num_rows * rowsize)  */
+    int64_t value_pattern_rows; /* rows whose coefficients come from the       */
+                             /*   dictionary too (value patterns): = pattern_rows */
+                             /*   or 0                                         */
     int64_t pattern_id_bytes;/* bytes of pattern ids one SpMV reads: one per  */
                              /*   group of 32*R rows, or one per thread (lane */
                              /*   patterns); 0 without offset patterns        */

@@ -35,7 +35,7 @@ def test_version_and_strerror(lib):
 
 def test_info_struct_layout_matches_header():
     # 5 int64, 7 int, pad, 4 int64, 1 int, pad, 1 int64, 2 int, 2 double, 3 int64
-    assert C.sizeof(E.Info) == 5 * 8 + 7 * 4 + 4 + 4 * 8 + 8 + 8 + 2 * 4 + 2 * 8 + 4 * 8
+    assert C.sizeof(E.Info) == 5 * 8 + 7 * 4 + 4 + 4 * 8 + 8 + 8 + 2 * 4 + 2 * 8 + 5 * 8
 
 
 def test_product_never_imports_the_oracle():

@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Key metrics of a .ncu-rep (run here, no GPU needed): one line per captured launch."""
+"""Key metrics of a .ncu-rep, or of its `ncu -i X.ncu-rep --page raw --csv` export (*_raw.csv):
+one block per captured launch.  Runs here, no GPU needed."""
 import csv
 import subprocess
 import sys
@@ -19,7 +20,10 @@ def to_bytes(v, unit):
 
 
 for path in sys.argv[1:]:
-    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if path.endswith(".csv"):
+        out = "".join(l for l in open(path) if l.startswith('"'))
+    else:
+        out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr, units = rows[0], rows[1]
     for r in rows[2:]:
