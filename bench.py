@@ -261,14 +261,29 @@ def cpu_reference_run(workload: str, world: int, steps: int, warmup: int, budget
         del c, a
         x[:] = 1.0
         y[:] = 0.0
+        if compact:
+            # a stencil in CSR form (csr_from_coo keeps the entries of a row in the same order and
+            # has no padding): drop the padded slots -- the generated coefficients are non-zero
+            keep = ea != 0.0
+            state["rowptr"] = np.concatenate(([0], np.cumsum(keep.reshape(rows, K).sum(axis=1, dtype=np.int64))))
+            ec, ea = np.ascontiguousarray(ec[keep]), np.ascontiguousarray(ea[keep])
         return ec, ea, x, y
+
+    compact = fmt == "csr" and kind_name != "random"
+    state = {"rowptr": None}
 
     def run(ec, ea, x, y, rows, n):
         if fmt == "csr":
-            # every generated row has exactly K stored entries: the CSR arrays are the row-major ELL arrays
-            rowptr = np.arange(rows + 1, dtype=np.int64) * K
+            if compact:
+                rowptr = state["rowptr"][: rows + 1]
+                lens = np.diff(rowptr)
+                kmin, kmax = int(lens.min()), int(lens.max())
+            else:
+                # every generated row has exactly K stored entries: the CSR arrays are the row-major ELL arrays
+                rowptr = np.arange(rows + 1, dtype=np.int64) * K
+                kmin = kmax = K
             if ref is not None:
-                return ref.csrgemv(rows, y, ncols, x, rowptr, ec, ea, repeat=n, rowsizemin=K, rowsizemax=K)
+                return ref.csrgemv(rows, y, ncols, x, rowptr, ec, ea, repeat=n, rowsizemin=kmin, rowsizemax=kmax)
             out = []
             for _ in range(n):
                 t0 = time.perf_counter()
@@ -297,11 +312,13 @@ def cpu_reference_run(workload: str, world: int, steps: int, warmup: int, budget
             ec, ea, x, y = build(rows)
     elif t_probe * (steps + warmup) > budget_s and rows > 1 << 18:
         rows = max(1 << 18, int(rows * budget_s / (t_probe * (steps + warmup))))
-        ec, ea, y = ec[: rows * K], ea[: rows * K], y[:rows]
+        nkeep = int(state["rowptr"][rows]) if compact else rows * K
+        ec, ea, y = ec[:nkeep], ea[:nkeep], y[:rows]
     run(ec, ea, x, y, rows, max(warmup, 1))
     secs = run(ec, ea, x, y, rows, steps)
     total = float(np.sum(secs))
-    flops = 2.0 * rows * K
+    stored = int(state["rowptr"][rows]) if compact else rows * K
+    flops = 2.0 * stored
     cores = host_cores()
     sample = (f"{steps} timed passes of the reference {'csrgemv' if fmt == 'csr' else 'ellgemv'} over "
               f"{'all' if rows == rows_full else 'the first'} {rows} of {rows_full} rows of {workload_name(workload, world)} "
@@ -313,7 +330,8 @@ def cpu_reference_run(workload: str, world: int, steps: int, warmup: int, budget
         "gflops": flops * steps / total * 1e-9,
         "best_gflops": flops / float(np.min(secs)) * 1e-9,
         "ms_per_step": total / steps * 1e3,
-        "gbs": (rows * K * (8 + idx_bits // 8) + 16 * rows + (8 * ncols if rows == rows_full else 0)) * steps / total * 1e-9,
+        "gbs": (stored * (8 + idx_bits // 8) + 16 * rows + (8 * (rows + 1) if fmt == "csr" else 0)
+                + (8 * ncols if rows == rows_full else 0)) * steps / total * 1e-9,
     }
 
 
@@ -395,7 +413,8 @@ def kernel_record(E, info, rows: int, K: int, idx_bits: int, ms: float, y_rmw: b
 
 
 def other_configs(E, torch, dev, sptr, stream, reps: int, peak: float, with_cpu: bool):
-    """BASELINE configs 3 and 4 (ELL and the CSR comparison path), kernel only, N = 1."""
+    """BASELINE configs 3 and 4 (ELL and the CSR comparison path) and config 2's matrix through the
+    CSR path (csrspmv on a structured grid), kernel only, N = 1."""
     import numpy as np
     out = []
 
@@ -407,7 +426,7 @@ def other_configs(E, torch, dev, sptr, stream, reps: int, peak: float, with_cpu:
             fn()
         return time_steps(torch, stream, fn, reps, sync) / reps
 
-    for name, fmt in (("stencil27_384", "ell"), ("random50m", "ell"), ("random50m", "csr")):
+    for name, fmt in (("stencil27_384", "ell"), ("random50m", "ell"), ("random50m", "csr"), ("laplace2d", "csr")):
         kind_name, K, idx_bits, vals_acc, _, dims_of, _ = WORKLOADS[name]
         kind = {"laplace2d": E.GEN_LAPLACE2D, "stencil27": E.GEN_STENCIL27, "random": E.GEN_RANDOM}[kind_name]
         dims = dims_of(1)
@@ -427,13 +446,26 @@ def other_configs(E, torch, dev, sptr, stream, reps: int, peak: float, with_cpu:
                 rec["launches_per_step"] = int(getattr(info, "launches_per_spmv", 1)) or 1
                 rec["device_bytes"] = int(info.device_bytes)
             else:
-                A = E.CsrMatrix.generate(kind, dims, seed=42, idx_bits=idx_bits)
+                A = E.CsrMatrix.generate(kind, dims, seed=42, idx_bits=idx_bits, vals=vals_acc)
+                ci = A.info()
+                nnz = int(ci.csrsize)
                 ms = timed(lambda: A.spmv_device(y, x, E.ACCUMULATE, sptr))
-                rec.update(kernel_record(E, None, rows, K, idx_bits, ms, True, ncols, peak))
+                rec.update(kernel_record(E, None, rows, K, idx_bits, ms, True, ncols, peak, entries=nnz))
                 # csrspmv.c:2882-2887: the CSR byte model adds the row pointers
-                extra = 8 * (rows + 1)
-                for k in ("bytes_as_stored", "bytes_algorithmic"):
-                    rec[k] += extra
+                rec["bytes_algorithmic"] += 8 * (rows + 1)
+                if ci.ell_view:
+                    # what the sliced-ELL view streams: every slot's value (width = the longest row),
+                    # the indices of the rows that are not on an offset pattern, the pattern ids, and
+                    # one 4-byte length per row when the rows differ (instead of 8-byte row pointers)
+                    Kv, dib = int(ci.max_row_len), int(ci.ell_dev_idx_bits) // 8
+                    prow = int(ci.ell_pattern_rows)
+                    rec["bytes_as_stored"] = (rows * Kv * 8 + (rows - prow) * Kv * dib + int(ci.ell_pattern_id_bytes)
+                                              + (4 * rows if ci.ell_view == 1 else 0) + 8 * ncols + 16 * rows)
+                    rec["pattern_rows_frac"] = round(prow / max(rows, 1), 4)
+                    rec["view"] = {"width": Kv, "slots": rows * Kv, "stored_entries": nnz, "dev_idx_bits": dib * 8,
+                                   "row_lengths": ci.ell_view == 1}
+                else:
+                    rec["bytes_as_stored"] += 8 * (rows + 1)
                 rec["as_stored_gbs"] = round(rec["bytes_as_stored"] / ms * 1e-6, 1)
                 rec["algorithmic_gbs"] = round(rec["bytes_algorithmic"] / ms * 1e-6, 1)
                 rec["frac_as_stored"] = round(rec["as_stored_gbs"] / peak, 4)

@@ -38,7 +38,7 @@ NO_STAGED_GATHER = 1 << 19
 SKIP_PADDING = 1 << 20
 PATTERN_MASKS = 1 << 21
 NO_PATTERN_LANES = 1 << 23
-NO_VALUE_PATTERN = 1 << 24
+VALUE_PATTERN = 1 << 24     # opt-in: coefficients from the pattern dictionary too
 FUSED_SYNC = 1 << 22
 KERNEL_CSR_SELL = 5     # CSR: SELL-128-sigma (AUTO takes it for unbalanced rows)
 WIDE_INDEX = 1 << 16
@@ -84,6 +84,7 @@ class CsrInfo(C.Structure):
         ("device_bytes", C.c_int64), ("kernel", C.c_int), ("sell_slots", C.c_int64), ("sell_real", C.c_int64),
         ("sell_long_rows", C.c_int64), ("sell_long_len", C.c_int64), ("ell_view", C.c_int), ("ell_staged", C.c_int),
         ("launches_per_spmv", C.c_int), ("ell_pattern_rows", C.c_int64), ("num_gpus", C.c_int), ("fma", C.c_int),
+        ("ell_pattern_id_bytes", C.c_int64), ("ell_dev_idx_bits", C.c_int), ("ell_rows_per_thread", C.c_int),
     ]
 
 
@@ -354,10 +355,12 @@ class CsrMatrix:
 
     @classmethod
     def generate(cls, kind: int, dims: Sequence[int], seed: int = 42, idx_bits: int = 32, device: int = -1,
-                 flags: int = 0) -> "CsrMatrix":
+                 flags: int = 0, vals: Sequence[float] = (0.0, 0.0)) -> "CsrMatrix":
+        """GEN_RANDOM (rows of exactly K entries), or GEN_LAPLACE2D / GEN_STENCIL27 as csr_from_coo
+        stores them (no padding; vals = (centre, off-diagonal))."""
         h = C.c_void_p()
         d = (C.c_int64 * 3)(*(list(dims) + [0, 0, 0])[:3])
-        v = (C.c_double * 2)(0.0, 0.0)
+        v = (C.c_double * 2)(float(vals[0]), float(vals[1]))
         err = load_library().csrspmv_cuda_generate(C.byref(h), kind, d, v, seed, idx_bits, device, flags)
         _check(err, "csrspmv_cuda_generate")
         return cls(h.value)
@@ -391,7 +394,9 @@ class CsrMatrix:
         if i.ell_view:
             how = "rows of one length" if i.ell_view == 2 else "per-row lengths"
             path = ("staged gather (column blocks), then thread-per-row" if i.ell_staged else "thread-per-row")
-            return f"sliced-ELL view of the CSR rows ({how}, width {i.max_row_len}): {path}, {arith}"
+            pat = (f", offset patterns on {100.0 * i.ell_pattern_rows / max(i.num_rows, 1):.1f} % of the rows"
+                   if i.ell_pattern_rows else "")
+            return f"sliced-ELL view of the CSR rows ({how}, width {i.max_row_len}): {path}, {arith}{pat}"
         name = {1: "smem-staged stream kernel", 2: "sub-warp per row + shuffle tree (tolerance)",
                 3: "scalar thread-per-row",
                 5: f"SELL-128-sigma (rows sorted by length in windows of 4096, width per slice; the {i.sell_long_rows} rows "

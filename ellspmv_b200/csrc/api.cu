@@ -195,8 +195,8 @@ int build_patterns(ellspmv_cuda_matrix *A)
     if ((A->flags & ELLSPMV_CUDA_NO_PATTERN) || A->cfg.kernel != ELLSPMV_CUDA_KERNEL_THREAD ||
         A->lay.num_rows <= 0 || A->lay.rowsize <= 0)
         return 0;
-    // value patterns too (a constant-coefficient stencil streams neither indices nor values): bit-exact mode only
-    const double *pv = ((A->flags & ELLSPMV_CUDA_NO_VALUE_PATTERN) || A->cfg.fma) ? nullptr : A->vals;
+    // value patterns (opt-in; a constant-coefficient stencil then streams neither indices nor values): bit-exact mode only
+    const double *pv = (!(A->flags & ELLSPMV_CUDA_VALUE_PATTERN) || A->cfg.fma) ? nullptr : A->vals;
     cudaError_t ce = pattern_build(&A->pat, A->dev_idx_bits, A->cols, pv, A->lay, A->cfg.rows_per_thread, A->row_begin,
                                    (A->flags & ELLSPMV_CUDA_PATTERN_MASKS) ? 4 : 0,
                                    !(A->flags & ELLSPMV_CUDA_NO_PATTERN_LANES), A->stream);
@@ -1255,14 +1255,17 @@ static int csr_build_ell_view(csrspmv_cuda_matrix *A)
     size_t free_b = 0, total_b = 0;
     ELL_CK(cudaMemGetInfo(&free_b, &total_b));
     if ((int64_t)free_b < padded * (8 + A->idx_bits / 8) + A->num_rows * 4 + (1LL << 30)) return 0;
-    unsigned flags = A->flags & (ELLSPMV_CUDA_FMA | ELLSPMV_CUDA_WIDE_INDEX | ELLSPMV_CUDA_NO_PATTERN | ELLSPMV_CUDA_PATTERN_MASKS |
+    unsigned flags = A->flags & (ELLSPMV_CUDA_FMA | ELLSPMV_CUDA_WIDE_INDEX | ELLSPMV_CUDA_NO_PATTERN | ELLSPMV_CUDA_PATTERN_MASKS | ELLSPMV_CUDA_NO_PATTERN_LANES |
                                  ELLSPMV_CUDA_NO_STAGED_GATHER | ELLSPMV_CUDA_STAGED_GATHER | ELLSPMV_CUDA_L2_PERSIST_X);
     // kernel of the view: the same nnz-per-row switch as an ELL upload (configure); both kernels
     // honour the row lengths, the thread-per-row one in its R = 1 / explicit-index form
     if (K >= 64 && A->num_rows <= 32768 && !(flags & ELLSPMV_CUDA_STAGED_GATHER)) flags |= kKernelLongRow;
     else {
         flags |= ELLSPMV_CUDA_KERNEL_THREAD;
-        if (!uniform) flags |= (1u << ELLSPMV_CUDA_ROWS_PER_THREAD_SHIFT) | ELLSPMV_CUDA_NO_PATTERN;
+        // rows with their own lengths: one row per thread; offset patterns apply all the same (a
+        // boundary row of a stencil is one more kind of row: the unused slots repeat its last
+        // column, csr_to_sliced), only the lane-mask form is not instantiated for them
+        if (!uniform) flags = (flags & ~(unsigned)ELLSPMV_CUDA_PATTERN_MASKS) | (1u << ELLSPMV_CUDA_ROWS_PER_THREAD_SHIFT);
     }
     ellspmv_cuda_matrix *V = nullptr;
     int err = new_handle(&V, A->idx_bits, A->row_begin + A->num_rows, A->num_columns, K, A->row_begin,
@@ -1401,15 +1404,34 @@ int csrspmv_cuda_generate(
     const double vals[2], uint64_t seed, int idx_width_bits,
     int device, unsigned flags)
 {
-    (void)vals;
     if (!dims) ELL_FAIL(EINVAL, "dims is NULL");
-    if (kind != ELLSPMV_CUDA_GEN_RANDOM) ELL_FAIL(ENOTSUP, "csrspmv_cuda_generate: only the random kind");
-    if (dims[0] < 0 || dims[1] < 1 || dims[2] < 0) ELL_FAIL(EINVAL, "random needs rows >= 0, cols >= 1, K >= 0");
-    int err = csr_new(out, idx_width_bits, dims[0], dims[1], dims[0] * dims[2], device, flags);
+    int64_t rows = 0, cols = 0, nnz = 0;
+    if (kind == ELLSPMV_CUDA_GEN_RANDOM) {
+        if (dims[0] < 0 || dims[1] < 1 || dims[2] < 0) ELL_FAIL(EINVAL, "random needs rows >= 0, cols >= 1, K >= 0");
+        rows = dims[0]; cols = dims[1]; nnz = dims[0] * dims[2];
+    } else if (kind == ELLSPMV_CUDA_GEN_LAPLACE2D || kind == ELLSPMV_CUDA_GEN_STENCIL27) {
+        // the stencils as csr_from_coo stores them: no padding, boundary rows are shorter
+        if (!vals) ELL_FAIL(EINVAL, "vals is NULL");
+        const int nd = kind == ELLSPMV_CUDA_GEN_LAPLACE2D ? 2 : 3;
+        rows = 1;
+        for (int d = 0; d < nd; d++) {
+            if (dims[d] < 1) ELL_FAIL(EINVAL, "grid dimensions must be >= 1");
+            if (rows > (1LL << 40) / dims[d]) ELL_FAIL(EINVAL, "grid too large");
+            rows *= dims[d];
+        }
+        cols = rows;
+        nnz = csr_stencil_nnz(kind, dims);
+    } else {
+        ELL_FAIL(EINVAL, "unknown generator kind %d", kind);
+    }
+    if (idx_width_bits == 32 && cols > 0x7fffffffLL) ELL_FAIL(EINVAL, "32-bit indices cannot address %lld columns", (long long)cols);
+    int err = csr_new(out, idx_width_bits, rows, cols, nnz, device, flags);
     if (err) return err;
     csrspmv_cuda_matrix *A = *out;
     DeviceGuard g(A->device);
-    cudaError_t ce = generate_csr_random(dims, seed, idx_width_bits, A->rowptr, A->cols, A->vals, A->stream);
+    cudaError_t ce = kind == ELLSPMV_CUDA_GEN_RANDOM
+        ? generate_csr_random(dims, seed, idx_width_bits, A->rowptr, A->cols, A->vals, A->stream)
+        : generate_csr_stencil(kind, dims, vals, idx_width_bits, A->rowptr, A->cols, A->vals, A->stream);
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(A->stream);
     if (ce != cudaSuccess) {
         set_last_error("csr generate: %s", cudaGetErrorString(ce));
@@ -1547,6 +1569,10 @@ int csrspmv_cuda_get_info(const csrspmv_cuda_matrix *A, csrspmv_cuda_info *info)
         info->ell_staged = S->ell->sg ? S->ell->staged_mode : 0;
         info->launches_per_spmv = S->ell->sg ? sg_launches(S->ell->sg) : 1;
         info->ell_pattern_rows = S->ell->pat.covered * S->ell->pat.group_rows;
+        info->ell_pattern_id_bytes = S->ell->pat.patlane ? S->ell->pat.groups * 32
+                                   : (S->ell->pat.max_explicit ? S->ell->pat.groups * 8 : (S->ell->pat.patid ? S->ell->pat.groups : 0));
+        info->ell_dev_idx_bits = S->ell->dev_idx_bits;
+        info->ell_rows_per_thread = S->ell->cfg.rows_per_thread;
     }
     if (!A->shards.empty()) {
         info->max_row_len = 0;

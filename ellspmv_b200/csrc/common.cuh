@@ -179,6 +179,10 @@ cudaError_t generate_sliced(int kind, const int64_t dims[3], const double vals[2
                             long long *minmax, cudaStream_t stream);
 cudaError_t generate_csr_random(const int64_t dims[3], uint64_t seed, int idx_bits,
                                 int64_t *rowptr, void *cols, double *vals, cudaStream_t stream);
+// CSR form of the laplace2d / stencil27 generators (no padding, entries in the ELL order)
+int64_t csr_stencil_nnz(int kind, const int64_t dims[3]);
+cudaError_t generate_csr_stencil(int kind, const int64_t dims[3], const double vals[2], int idx_bits,
+                                 int64_t *rowptr, void *cols, double *out_vals, cudaStream_t stream);
 cudaError_t init_minmax(long long *minmax, cudaStream_t stream);
 // CSR rows -> sliced-ELL layout of width lay.rowsize (>= the longest row): entries keep their order,
 // the unused slots of a row get (its last column or 0, 0.0), rowlen[r] = the row's length

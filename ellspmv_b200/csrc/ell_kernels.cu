@@ -156,7 +156,7 @@ template <int R> struct Batch { static constexpr int U = (R == 4) ? 4 : (R == 2 
 // what is left is the x gather and the y store.
 // LEN: rows carry their own length (a.rowlen): slots past it are loaded but never enter the
 // arithmetic.  This is the CSR view (csrgemv has no padded slots, csrspmv.c:1588-1593); only
-// instantiated for R = 1, run-time K, no patterns.
+// instantiated for R = 1, run-time K, PAT = 0 / 1 / 3.
 template <typename IdxT, int R, int KU, bool FMA, bool YVEC, int G, int PAT, bool LEN = false, bool SYNC = false, bool VPAT = false>
 __global__ void __launch_bounds__(kBlockThreads)
 ell_thread_kernel(const EllSpmvArgs a)
@@ -525,8 +525,17 @@ template <typename IdxT, int R, int KU, bool FMA, int G>
 static cudaError_t launch_thread_g(const EllSpmvArgs &args, bool yvec, cudaLaunchConfig_t &lc)
 {
     if (args.rowlen) {
-        // per-row lengths (CSR view): one row per thread, run-time K, explicit indices
-        if (R != 1 || KU != 0 || args.patid || args.patinfo || args.patlane || args.vpat) return cudaErrorInvalidValue;
+        // per-row lengths (CSR view): one row per thread, run-time K; explicit indices, group ids
+        // or one id per thread (a CSR stencil: its boundary rows are shorter, not padded)
+        if (R != 1 || KU != 0 || args.patinfo || args.vpat) return cudaErrorInvalidValue;
+        if (args.patlane) {
+            if (yvec) return cudaLaunchKernelEx(&lc, ell_thread_kernel<IdxT, 1, 0, FMA, true, G, 3, true>, args);
+            return cudaLaunchKernelEx(&lc, ell_thread_kernel<IdxT, 1, 0, FMA, false, G, 3, true>, args);
+        }
+        if (args.patid) {
+            if (yvec) return cudaLaunchKernelEx(&lc, ell_thread_kernel<IdxT, 1, 0, FMA, true, G, 1, true>, args);
+            return cudaLaunchKernelEx(&lc, ell_thread_kernel<IdxT, 1, 0, FMA, false, G, 1, true>, args);
+        }
         if (yvec) return cudaLaunchKernelEx(&lc, ell_thread_kernel<IdxT, 1, 0, FMA, true, G, 0, true>, args);
         return cudaLaunchKernelEx(&lc, ell_thread_kernel<IdxT, 1, 0, FMA, false, G, 0, true>, args);
     }

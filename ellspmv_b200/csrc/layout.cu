@@ -286,6 +286,93 @@ cudaError_t generate_csr_random(const int64_t dims[3], uint64_t seed, int idx_bi
     return cudaGetLastError();
 }
 
+// CSR form of the two stencils: what csr_from_coo (csrspmv.c:1390-1475) makes of the same
+// canonical COO stream -- the entries of a row in the ELL order above, no padding.  Row lengths
+// are products (27-point) or sums (5-point) of per-axis neighbour counts, so rowptr has a closed
+// form and one thread per row writes its pointer and its entries without a scan.
+//   axis_prefix(t, n) = sum over t' < t of (1 + [t' > 0] + [t' < n-1])
+__host__ __device__ __forceinline__ int64_t axis_prefix(int64_t t, int64_t n)
+{
+    return t + (t > 0 ? t - 1 : 0) + (t < n - 1 ? t : n - 1);
+}
+__host__ __device__ __forceinline__ int64_t laplace2d_rowptr(int64_t i, int64_t j, int64_t nx, int64_t ny)
+{
+    const int64_t ci = (i > 0) + (i + 1 < nx);
+    const int64_t cj_before = (j > 0 ? j - 1 : 0) + (j < ny - 1 ? j : ny - 1);
+    return ny * axis_prefix(i, nx) + i * (2 * ny - 2) + j * (1 + ci) + cj_before;
+}
+__host__ __device__ __forceinline__ int64_t stencil27_rowptr(int64_t i, int64_t j, int64_t k, int64_t nx, int64_t ny, int64_t nz)
+{
+    const int64_t a = 1 + (i > 0) + (i + 1 < nx), b = 1 + (j > 0) + (j + 1 < ny);
+    return axis_prefix(i, nx) * (3 * ny - 2) * (3 * nz - 2) + a * axis_prefix(j, ny) * (3 * nz - 2) + a * b * axis_prefix(k, nz);
+}
+
+int64_t csr_stencil_nnz(int kind, const int64_t dims[3])
+{
+    if (kind == ELLSPMV_CUDA_GEN_LAPLACE2D)
+        return dims[0] > 0 && dims[1] > 0 ? laplace2d_rowptr(dims[0], 0, dims[0], dims[1]) : 0;
+    if (kind == ELLSPMV_CUDA_GEN_STENCIL27)
+        return dims[0] > 0 && dims[1] > 0 && dims[2] > 0 ? (3 * dims[0] - 2) * (3 * dims[1] - 2) * (3 * dims[2] - 2) : 0;
+    return -1;
+}
+
+template <typename DstI>
+__global__ void gen_csr_laplace2d_kernel(int64_t nx, int64_t ny, double cval, double oval, int64_t *__restrict__ rowptr,
+                                         DstI *__restrict__ cols, double *__restrict__ vals)
+{
+    const int64_t rows = nx * ny;
+    for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r <= rows; r += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = r / ny, j = r - i * ny;
+        int64_t e = laplace2d_rowptr(i, j, nx, ny);
+        rowptr[r] = e;
+        if (r == rows) break;
+        if (i > 0)      { cols[e] = (DstI)(r - ny); vals[e] = oval; e++; }
+        if (j > 0)      { cols[e] = (DstI)(r - 1);  vals[e] = oval; e++; }
+        cols[e] = (DstI)r; vals[e] = cval; e++;
+        if (j + 1 < ny) { cols[e] = (DstI)(r + 1);  vals[e] = oval; e++; }
+        if (i + 1 < nx) { cols[e] = (DstI)(r + ny); vals[e] = oval; e++; }
+    }
+}
+
+template <typename DstI>
+__global__ void gen_csr_stencil27_kernel(int64_t nx, int64_t ny, int64_t nz, double cval, double oval,
+                                         int64_t *__restrict__ rowptr, DstI *__restrict__ cols, double *__restrict__ vals)
+{
+    const int64_t rows = nx * ny * nz;
+    for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r <= rows; r += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t k = r % nz, j = (r / nz) % ny, i = r / (nz * ny);
+        int64_t e = stencil27_rowptr(i, j, k, nx, ny, nz);
+        rowptr[r] = e;
+        if (r == rows) break;
+        for (int di = -1; di <= 1; di++)
+            for (int dj = -1; dj <= 1; dj++)
+                for (int dk = -1; dk <= 1; dk++) {
+                    const int64_t ii = i + di, jj = j + dj, kk = k + dk;
+                    if (ii < 0 || ii >= nx || jj < 0 || jj >= ny || kk < 0 || kk >= nz) continue;
+                    cols[e] = (DstI)((ii * ny + jj) * nz + kk);
+                    vals[e] = (di == 0 && dj == 0 && dk == 0) ? cval : oval;
+                    e++;
+                }
+    }
+}
+
+cudaError_t generate_csr_stencil(int kind, const int64_t dims[3], const double v[2], int idx_bits,
+                                 int64_t *rowptr, void *cols, double *vals, cudaStream_t stream)
+{
+    const int64_t rows = kind == ELLSPMV_CUDA_GEN_LAPLACE2D ? dims[0] * dims[1] : dims[0] * dims[1] * dims[2];
+    const int g = grid_for(rows + 1, 128);
+    if (kind == ELLSPMV_CUDA_GEN_LAPLACE2D) {
+        if (idx_bits == 32) gen_csr_laplace2d_kernel<int32_t><<<g, 128, 0, stream>>>(dims[0], dims[1], v[0], v[1], rowptr, (int32_t *)cols, vals);
+        else gen_csr_laplace2d_kernel<int64_t><<<g, 128, 0, stream>>>(dims[0], dims[1], v[0], v[1], rowptr, (int64_t *)cols, vals);
+    } else if (kind == ELLSPMV_CUDA_GEN_STENCIL27) {
+        if (idx_bits == 32) gen_csr_stencil27_kernel<int32_t><<<g, 128, 0, stream>>>(dims[0], dims[1], dims[2], v[0], v[1], rowptr, (int32_t *)cols, vals);
+        else gen_csr_stencil27_kernel<int64_t><<<g, 128, 0, stream>>>(dims[0], dims[1], dims[2], v[0], v[1], rowptr, (int64_t *)cols, vals);
+    } else {
+        return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
 // ---- which slices read columns outside the shard's own rows (fused step sync, ell_kernels.cu) ----
 // remote[s] = 1 when slice s references a column outside [lo, hi): such a CTA must wait for the
 // peers' pushes of the previous step before it gathers.  lo/hi are the shard's row range shrunk

@@ -40,6 +40,7 @@ struct options {
     bool separate_diagonal, sort_rows, ignored_partition, device_convert;
     int repeat, warmup, verbose, quiet, gpus;
     unsigned flags;
+    const char *synthetic;
 };
 
 static void usage(FILE *f) { fprintf(f, "Usage: %s [OPTION..] A [x] [y]\n", prog); }
@@ -78,6 +79,8 @@ static void help(FILE *f)
     fprintf(f, "                            warp: sub-warp-per-row (tolerance mode)\n");
     fprintf(f, "  --fma                     allow fused multiply-add (tolerance mode)\n");
     fprintf(f, "  --device-convert          convert COO to CSR on the device (general matrices)\n");
+    fprintf(f, "  --synthetic=SPEC          build A on the device instead of reading a file:\n");
+    fprintf(f, "                            laplace2d:NX,NY | stencil27:NX,NY,NZ | random:ROWS,COLS,K[,SEED]\n");
     fprintf(f, "  --gpus=N                  split the rows in N nonzero-balanced blocks over devices 0..N-1 [1]\n");
     fprintf(f, "\n");
     fprintf(f, "  -h, --help                display this help and exit\n");
@@ -137,6 +140,10 @@ static int parse_options(int argc, char **argv, struct options *o, int *bad)
             }
             if (!strcmp(a, "--fma")) { o->flags |= ELLSPMV_CUDA_FMA; continue; }
             if (!strcmp(a, "--device-convert")) { o->device_convert = true; continue; }
+            if (!strncmp(a, "--synthetic", 11) && (a[11] == '=' || a[11] == '\0')) {
+                if (!(o->synthetic = optval(argc, argv, &i, "--synthetic"))) return EINVAL;
+                continue;
+            }
             if (!strncmp(a, "--gpus", 6) && (a[6] == '=' || a[6] == '\0')) {
                 if (!(v = optval(argc, argv, &i, "--gpus")) || to_int(v, &o->gpus) || o->gpus < 1) return EINVAL;
                 continue;
@@ -154,7 +161,32 @@ static int parse_options(int argc, char **argv, struct options *o, int *bad)
         else return EINVAL;
         npos++;
     }
-    if (npos < 1) { usage(stdout); exit(EXIT_FAILURE); }
+    if (o->synthetic && npos > 0) {
+        /* with --synthetic the positionals are [x] [y] */
+        o->ypath = o->xpath; o->xpath = o->Apath; o->Apath = NULL;
+        if (npos > 2) return EINVAL;
+    } else if (npos < 1 && !o->synthetic) {
+        usage(stdout);
+        exit(EXIT_FAILURE);
+    }
+    return 0;
+}
+
+static int parse_synthetic(const char *spec, int *kind, int64_t dims[3], double vals[2], uint64_t *seed)
+{
+    char name[32];
+    long long d[4] = {0, 0, 0, 42};
+    const char *colon = strchr(spec, ':');
+    if (!colon || (size_t)(colon - spec) >= sizeof(name)) return EINVAL;
+    memcpy(name, spec, (size_t)(colon - spec));
+    name[colon - spec] = '\0';
+    int n = sscanf(colon + 1, "%lld,%lld,%lld,%lld", &d[0], &d[1], &d[2], &d[3]);
+    *seed = 42;
+    if (!strcmp(name, "laplace2d") && n == 2) { *kind = ELLSPMV_CUDA_GEN_LAPLACE2D; vals[0] = 4.0; vals[1] = -1.0; }
+    else if (!strcmp(name, "stencil27") && n == 3) { *kind = ELLSPMV_CUDA_GEN_STENCIL27; vals[0] = 26.0; vals[1] = -1.0; }
+    else if (!strcmp(name, "random") && n >= 3) { *kind = ELLSPMV_CUDA_GEN_RANDOM; if (n == 4) *seed = (uint64_t)d[3]; }
+    else return EINVAL;
+    dims[0] = d[0]; dims[1] = d[1]; dims[2] = d[2];
     return 0;
 }
 
@@ -175,6 +207,44 @@ int main(int argc, char *argv[])
     if (o.ignored_partition && o.verbose > 0)
         fprintf(stderr, "%s: note: CPU thread-partitioning options are ignored on the CUDA path\n", prog);
 
+    idx_t num_rows = 0, num_columns = 0;
+    int64_t num_nonzeros = 0;
+    csrspmv_cuda_matrix *A = NULL;
+    int64_t csrsize = 0, diagsize = 0;
+
+    if (o.synthetic) {
+        /* build the matrix on the device, in the form csr_from_coo gives it (shapes too large for a text file) */
+        int kind = 0;
+        int64_t dims[3];
+        double vals[2] = {0, 0};
+        uint64_t seed;
+        if (o.separate_diagonal || o.sort_rows || o.gpus > 1) {
+            fprintf(stderr, "%s: --synthetic takes neither --separate-diagonal, --sort-rows nor --gpus\n", prog);
+            return EXIT_FAILURE;
+        }
+        if (parse_synthetic(o.synthetic, &kind, dims, vals, &seed)) {
+            fprintf(stderr, "%s: %s --synthetic=%s\n", prog, strerror(EINVAL), o.synthetic);
+            return EXIT_FAILURE;
+        }
+        if (o.verbose > 0) { fprintf(stderr, "cuda_generate: "); clock_gettime(CLOCK_MONOTONIC, &t0); }
+        err = csrspmv_cuda_generate(&A, kind, dims, vals, seed, IDX_BITS, -1, o.flags);
+        if (err) {
+            if (o.verbose > 0) fprintf(stderr, "\n");
+            fprintf(stderr, "%s: %s (%s)\n", prog, strerror(err), ellspmv_cuda_last_error());
+            return EXIT_FAILURE;
+        }
+        csrspmv_cuda_info info;
+        csrspmv_cuda_get_info(A, &info);
+        num_rows = (idx_t)info.num_rows;
+        num_columns = (idx_t)info.num_columns;
+        num_nonzeros = csrsize = info.csrsize;
+        if (o.verbose > 0) {
+            clock_gettime(CLOCK_MONOTONIC, &t1);
+            fprintf(stderr, "%'.6f seconds, %'" PRIdx " rows, %'" PRIdx " columns, %'" PRId64 " nonzeros"
+                            ", %'" PRId64 " to %'" PRId64 " nonzeros per row\n",
+                    seconds_between(t0, t1), num_rows, num_columns, csrsize, info.min_row_len, info.max_row_len);
+        }
+    } else {
     /* 2. read the matrix (csrspmv.c:1843-1909) */
     if (o.verbose > 0) { fprintf(stderr, "mtxfile_read: "); clock_gettime(CLOCK_MONOTONIC, &t0); }
     struct mtx_stream *s = mtx_open(o.Apath, o.gzip);
@@ -189,8 +259,8 @@ int main(int argc, char *argv[])
         mtx_close(s);
         return EXIT_FAILURE;
     }
-    const idx_t num_rows = h.num_rows, num_columns = h.num_columns;
-    const int64_t num_nonzeros = h.num_nonzeros;
+    num_rows = h.num_rows; num_columns = h.num_columns;
+    num_nonzeros = h.num_nonzeros;
     size_t nz = num_nonzeros > 0 ? (size_t)num_nonzeros : 1;
     idx_t *rowidx = malloc(nz * sizeof(idx_t));
     idx_t *colidx = malloc(nz * sizeof(idx_t));
@@ -217,8 +287,6 @@ int main(int argc, char *argv[])
         fprintf(stderr, "%s: --separate-diagonal needs a square matrix\n", prog);
         return EXIT_FAILURE;
     }
-    csrspmv_cuda_matrix *A = NULL;
-    int64_t csrsize, diagsize = 0;
     if (o.device_convert && !o.separate_diagonal && !o.sort_rows && h.symmetry == MTX_GENERAL && o.gpus == 1) {
         /* stable sort by row on the device; rowsizemin/max are only printed, count them here */
         int64_t *cnt = calloc((size_t)num_rows + 1, sizeof(*cnt));
@@ -275,6 +343,8 @@ int main(int argc, char *argv[])
                     csrspmv_cuda_device_bytes(A));
         }
     }
+
+    }   /* !synthetic */
 
     /* 4. vectors (csrspmv.c:2340-2631) */
     double *x = NULL, *y = NULL;

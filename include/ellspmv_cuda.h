@@ -148,17 +148,19 @@ enum {
      * of the rows; 2D 5-point 8192^2: not worth it, stays on group ids).  Same kernel
      * otherwise, same bits.  NO_PATTERN_LANES keeps group ids. */
     ELLSPMV_CUDA_NO_PATTERN_LANES = 1 << 23,
-    /* value patterns: in a constant-coefficient stencil the rows share not only their column
-     * offsets but their COEFFICIENTS (2D 5-point Laplacian: 4, -1, -1, -1, -1 in every interior
-     * row).  The upload looks for that too -- the pattern signature then includes the bit
-     * patterns of the values, every row is verified entry by entry, bit for bit -- and a
-     * dictionary entry carries offsets and coefficients: a patterned thread streams neither
-     * indices nor values from HBM; what is left is the x gather and the y store.  Taken when it
-     * covers at least 9/10 of the rows the index-only search covers; a matrix with variable
-     * coefficients keeps index patterns and its value stream.  Same arithmetic on the same
-     * numbers in the same order: same bits.  Not searched with ELLSPMV_CUDA_FMA.
-     * NO_VALUE_PATTERN streams the values always. */
-    ELLSPMV_CUDA_NO_VALUE_PATTERN = 1 << 24,
+    /* value patterns (OPT-IN): in a constant-coefficient stencil the rows share not only their
+     * column offsets but their COEFFICIENTS (2D 5-point Laplacian: 4, -1, -1, -1, -1 in every
+     * interior row).  With this flag the upload looks for that too -- the pattern signature then
+     * includes the bit patterns of the values, every row is verified entry by entry, bit for bit
+     * -- and a dictionary entry carries offsets and coefficients: a patterned thread streams
+     * neither indices nor values from HBM; what is left is the x gather and the y store (the
+     * matrix-free limit of the same arithmetic).  Taken when it covers at least 9/10 of the rows
+     * the index-only search covers; a matrix with variable coefficients keeps index patterns and
+     * its value stream.  Same arithmetic on the same numbers in the same order: same bits.  Not
+     * searched with ELLSPMV_CUDA_FMA.  Off by default, and never set by bench.py's headline:
+     * constant coefficients are a property of synthetic matrices, and a benchmark that does not
+     * read A no longer measures an SpMV. */
+    ELLSPMV_CUDA_VALUE_PATTERN    = 1 << 24,
     /* rows handled per thread in the thread-per-row kernel (1, 2 or 4):
      * 0 = auto = 2 for rows of at most 12 entries, else 1 */
     ELLSPMV_CUDA_ROWS_PER_THREAD_SHIFT = 8,
@@ -380,7 +382,10 @@ int csrspmv_cuda_upload_coo(
 /* copy the CSR arrays back to the host (rowptr: num_rows+1 int64) */
 int csrspmv_cuda_download(const csrspmv_cuda_matrix *A, int64_t *rowptr, void *colidx, double *a);
 
-/* CSR view of ELLSPMV_CUDA_GEN_RANDOM (every row has exactly K entries) */
+/* the generators of ellspmv_cuda_generate in CSR form, as csr_from_coo (csrspmv.c:1390-1475)
+ * stores the same canonical COO stream: ELLSPMV_CUDA_GEN_RANDOM (every row has exactly K
+ * entries: rowptr[i] = i*K), ELLSPMV_CUDA_GEN_LAPLACE2D / _STENCIL27 (no padding: rows at the
+ * grid boundary are shorter; vals = {centre, off}) */
 int csrspmv_cuda_generate(
     csrspmv_cuda_matrix **out, int kind, const int64_t dims[3],
     const double vals[2], uint64_t seed, int idx_width_bits,
@@ -416,6 +421,9 @@ typedef struct csrspmv_cuda_info {
     int64_t ell_pattern_rows;  /* rows of the view on an offset pattern                         */
     int     num_gpus;
     int     fma;
+    int64_t ell_pattern_id_bytes; /* pattern-id bytes one SpMV of the view reads             */
+    int     ell_dev_idx_bits;  /* index width of the view on the device (0 without a view)  */
+    int     ell_rows_per_thread;
 } csrspmv_cuda_info;
 int csrspmv_cuda_get_info(const csrspmv_cuda_matrix *A, csrspmv_cuda_info *info);
 

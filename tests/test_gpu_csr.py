@@ -258,6 +258,60 @@ def test_random_generated_csr_uses_the_uniform_view(lib, oracle):
     assert bits_equal(y, want)
 
 
+STENCIL_GRIDS = [("laplace2d", (1, 1)), ("laplace2d", (1, 7)), ("laplace2d", (96, 50)), ("laplace2d", (300, 257)),
+                 ("stencil27", (1, 1, 1)), ("stencil27", (2, 1, 3)), ("stencil27", (24, 20, 16)), ("stencil27", (40, 36, 33))]
+
+
+@pytest.mark.parametrize("kind,dims", STENCIL_GRIDS)
+@pytest.mark.parametrize("bits", [32, 64])
+def test_generated_stencils_in_csr_form(lib, oracle, kind, dims, bits):
+    """csrspmv_cuda_generate for the two stencils: the arrays are what csr_from_coo (csrspmv.c:1390-1475)
+    makes of the canonical COO stream (no padding, shorter rows at the grid boundary); the SpMV runs
+    through the sliced-ELL view with per-row lengths AND offset patterns, and gives csrgemv's bits --
+    also with variable coefficients uploaded on the same structure, and with non-finite x."""
+    rng = np.random.default_rng(len(dims) * 1000 + int(np.prod(dims)) + bits)
+    rows, ncols, ri, ci, a = oracle.gen_coo(kind, dims, (26.0, -1.0), bits=bits)
+    rowptr, cc, ca, lo, hi = oracle.csr_from_coo(rows, ncols, ri, ci, a)
+    gk = E.GEN_LAPLACE2D if kind == "laplace2d" else E.GEN_STENCIL27
+    A = E.CsrMatrix.generate(gk, dims, idx_bits=bits, vals=(26.0, -1.0))
+    i = A.info()
+    assert (i.num_rows, i.num_columns, i.csrsize) == (rows, ncols, len(ca))
+    assert (i.min_row_len, i.max_row_len) == (lo, hi)
+    r2, c2, a2 = A.download(rows, len(ca), bits)
+    assert np.array_equal(r2, rowptr) and np.array_equal(c2, cc) and bits_equal(a2, ca)
+    assert i.ell_view == (2 if lo == hi else 1)
+    if rows >= 4000:
+        # interior rows (and, with one id per thread, the boundary rows too) are on the dictionary
+        assert i.ell_pattern_rows >= 0.6 * rows, (i.ell_pattern_rows, rows)
+    x = rng.standard_normal(ncols)
+    y0 = rng.standard_normal(rows)
+    for xv in (x, np.where(rng.random(ncols) < 0.03, np.inf, x)):
+        want = y0.copy()
+        oracle.csrgemv(rows, want, xv, rowptr, cc, ca)
+        y = y0.copy()
+        A.spmv(y, xv, 1, E.ACCUMULATE)
+        assert np.array_equal(np.isnan(y), np.isnan(want))
+        ok = ~np.isnan(want)
+        assert bits_equal(y[ok], want[ok])
+    A.free()
+    # the same structure with variable coefficients, uploaded: patterns with and without, lanes or group ids
+    va = rng.standard_normal(len(ca))
+    want = np.zeros(rows)
+    oracle.csrgemv(rows, want, x, rowptr, cc, va)
+    seen = {}
+    for flags in (0, E.NO_PATTERN_LANES, E.NO_PATTERN, E.FMA):
+        B = E.CsrMatrix.upload(rows, ncols, rowptr, cc, va, flags)
+        seen[flags] = B.info().ell_pattern_rows
+        y = np.zeros(rows)
+        B.spmv(y, x, 1, E.OVERWRITE)
+        if flags & E.FMA:
+            assert np.allclose(y, want, rtol=1e-13, atol=1e-13)
+        else:
+            assert bits_equal(y, want), flags
+        B.free()
+    assert seen[E.NO_PATTERN] == 0 and seen[0] >= seen[E.NO_PATTERN_LANES]
+
+
 def powerlaw_csr(rng, nr, nc, dt, min_len=2, max_len=9000, alpha=1.3, empty_frac=0.05):
     """Row lengths ~ Pareto: most rows short, a tail of very long ones."""
     u = rng.random(nr)

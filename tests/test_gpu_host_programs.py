@@ -96,6 +96,25 @@ def test_synthetic_and_iterate_options(oracle):
     assert r.returncode == 1 and "not supported" in r.stderr
 
 
+def test_csrspmv_synthetic_prints_what_ellspmv_prints():
+    """csrspmv --synthetic builds the stencil in CSR form on the device; with x = ones both programs
+    print the same row sums (the padded ELL slots add exact zeros), and -v reports the row lengths."""
+    for spec, prog_e, prog_c, lens in (("laplace2d:50,40", "ellspmv", "csrspmv", "3 to 5"),
+                                       ("stencil27:9,8,7", "ellspmv64", "csrspmv64", "8 to 27"),
+                                       ("random:300,200,7", "ellspmv", "csrspmv", "7 to 7")):
+        re_ = run(prog_e, [f"--synthetic={spec}"])
+        rc = run(prog_c, [f"--synthetic={spec}", "-v", "--repeat=2", "--warmup=1"])
+        assert re_.returncode == 0 and rc.returncode == 0, rc.stderr
+        if not spec.startswith("random"):
+            # two accumulating passes + one warm-up: three times the row sums, exact in fp64
+            ye = np.array([float(t) for t in re_.stdout.splitlines()[2:]])
+            yc = np.array([float(t) for t in rc.stdout.splitlines()[2:]])
+            assert np.array_equal(3.0 * ye, yc)
+        assert f"{lens} nonzeros per row" in rc.stderr and rc.stderr.count("gemv") == 3
+    r = run("csrspmv", ["--synthetic=laplace2d:4,4", "--sort-rows"])
+    assert r.returncode == 1
+
+
 @pytest.mark.parametrize("name", ["rand_square", "long_rows", "rand_wide"])
 def test_ell_sort_rows_prints_what_the_reference_csr_program_prints(tmp_path, name):
     """ellspmv --sort-rows (intended semantics) adds the same products in the same
