@@ -660,11 +660,13 @@ def main_ours(args, rank: int, local_rank: int, world: int):
         "kernel": {"name": kernel_description(info, flags), "rows_per_thread": info.rows_per_thread,
                    "slice_rows": info.slice_rows, "dev_idx_bits": int(info.dev_idx_bits),
                    "pattern_rows_frac": head["pattern_rows_frac"],
+                   "value_pattern_rows_frac": head.get("value_pattern_rows_frac", 0.0),   # > 0 only with --flags 0x1000000 (opt-in)
                    "l2": f"inputs larger than L2 ({rows * K * (8 + idx_bits // 8) / 1e9:.1f} GB matrix per GPU vs 126 MB L2), no flush needed"},
         "gbs": round(head["as_stored_gbs"] * world, 1),
         "roofline": {"bound": "hbm", "achieved": head["as_stored_gbs"], "peak": peak, "unit": "GB/s",
                      "frac": head["frac_as_stored"],
-                     "traffic": recorded_traffic(workload_name(args.workload, 1) + "_iterate") if world == 1 else None,
+                     "traffic": (recorded_traffic(workload_name(args.workload, 1) + "_iterate")
+                                 if world == 1 and args.flags == 0 else None),   # the capture is of the default kernel
                      "peak_source": peak_src, "bytes_per_launch": head["bytes_as_stored"],
                      "bytes_model": "as stored on the device: 8*K*rows (values) + index bytes actually read "
                                     "(device index width; rows on an offset pattern read none) + the pattern ids (one byte per group or per thread) + 8*x_touched + 8*rows (y written once)",
@@ -684,7 +686,7 @@ def main_ours(args, rank: int, local_rank: int, world: int):
         n2 = min(args.steps, 50)
         ms2 = time_steps(torch, stream, lambda: A.spmv_device(y, xa, E.ACCUMULATE, sptr), n2, barrier) / n2
         acc = kernel_record(E, info, rows, K, idx_bits, ms2, True, x_touched, peak)
-        acc["traffic"] = recorded_traffic(workload_name(args.workload, 1) + "_accumulate")
+        acc["traffic"] = recorded_traffic(workload_name(args.workload, 1) + "_accumulate") if args.flags == 0 else None
         line["accumulate"] = acc
         del y
     else:

@@ -368,14 +368,26 @@ ell_thread_kernel(const EllSpmvArgs a)
                     if (!LEN || l0 + u < len) acc[r] = madd<FMA>(acc[r], v[u][r], xv[u][r]);
             }
         }
-#pragma unroll 1
-        for (; l0 < Kl; l0++) {
-            double v[R]; int64_t c[R];
-            load_vals(l0, v);
-            load_cols(l0, c);
+        // the last K mod U slots as ONE guarded batch: their loads are in flight together (a
+        // slot-by-slot tail is K mod U dependent round trips -- all of a 5-entry row's time)
+        if (l0 < Kl) {
+            double v[U][R]; int64_t c[U][R]; double xv[U][R];
 #pragma unroll
-            for (int r = 0; r < R; r++)
-                if (!LEN || l0 < len) acc[r] = madd<FMA>(acc[r], v[r], ldx<G>(x + c[r]));
+            for (int u = 0; u < U; u++) if (l0 + u < Kl) {
+                load_vals(l0 + u, v[u]);
+                load_cols(l0 + u, c[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) if (l0 + u < Kl) {
+#pragma unroll
+                for (int r = 0; r < R; r++) xv[u][r] = ldx<G>(x + c[u][r]);
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) if (l0 + u < Kl) {
+#pragma unroll
+                for (int r = 0; r < R; r++)
+                    if (!LEN || l0 + u < len) acc[r] = madd<FMA>(acc[r], v[u][r], xv[u][r]);
+            }
         }
     }
 

@@ -776,8 +776,9 @@ def test_value_patterns_are_opt_in_and_bit_exact(lib, oracle, bits):
     """ELLSPMV_CUDA_VALUE_PATTERN: rows that share offsets AND coefficients take both from the
     dictionary.  Off by default (value_pattern_rows == 0 with flags = 0); with the flag a
     constant-coefficient stencil is covered, a matrix with variable coefficients keeps its value
-    stream, a single coefficient that differs in its last bit (or in the sign of a zero) keeps its
-    row off the dictionary -- and y is the oracle's bit for bit every time."""
+    stream, a coefficient that differs in its last bit (or in its sign) either keeps its group off
+    the dictionary (group ids) or becomes one more dictionary entry (one id per thread) -- and y
+    is the oracle's bit for bit every time."""
     rng = np.random.default_rng(123 + bits)
     for kind, dims, K in ((E.GEN_LAPLACE2D, (128, 96), 5), (E.GEN_STENCIL27, (24, 20, 16), 27),
                           (E.GEN_STENCIL27, (40, 36, 33), 27)):
@@ -788,47 +789,59 @@ def test_value_patterns_are_opt_in_and_bit_exact(lib, oracle, bits):
         x = rng.standard_normal(nr)
         y0 = rng.standard_normal(nr)
         variable = rng.standard_normal(ea.shape) * (ea != 0.0)
+        # two dents in interior rows (no padded slot): one ulp in one coefficient, the sign of another
+        interior = np.flatnonzero((ea.reshape(nr, K) != 0.0).all(axis=1))
+        ra, rb = int(interior[len(interior) // 2]), int(interior[len(interior) // 3])
         dented = ea.copy()
-        dented[(nr // 2) * K + 1] = np.nextafter(dented[(nr // 2) * K + 1], 0.0)     # one ulp
-        dented[(nr // 3) * K + K - 1] = -0.0 if dented[(nr // 3) * K + K - 1] == 0.0 else -dented[(nr // 3) * K + K - 1]
+        dented[ra * K + 1] = np.nextafter(dented[ra * K + 1], 0.0)
+        dented[rb * K + K - 1] = -dented[rb * K + K - 1]
+        full = {}
         for name, vals in (("constant", ea), ("variable", variable), ("dented", dented)):
             want = y0.copy()
             oracle.ellgemv(nr, want, x, K, ec, vals)
+            w2 = np.zeros(nr)
+            oracle.ellgemv(nr, w2, x, K, ec, vals)
             for R in (1, 2):
-                base = E.EllMatrix.upload(nr, nr, K, ec, vals, E.rows_per_thread(R))
-                assert base.info().value_pattern_rows == 0
-                index_rows = base.info().pattern_rows
-                base.free()
-                A = E.EllMatrix.upload(nr, nr, K, ec, vals, E.rows_per_thread(R) | E.VALUE_PATTERN)
-                info = A.info()
-                if name == "variable":
-                    assert info.value_pattern_rows == 0 and info.pattern_rows == index_rows, (kind, dims, R)
-                elif index_rows > 0:
-                    assert info.value_pattern_rows == info.pattern_rows, (kind, dims, R, name)
-                    assert info.value_pattern_rows >= 0.9 * index_rows * 0.9, (kind, dims, R, name)
-                    if name == "dented":
-                        full = expected_value_rows[(kind, dims, R)]
-                        assert 0 < info.value_pattern_rows < full or full == 0, (kind, dims, R)
+                for lanes in (0, E.NO_PATTERN_LANES):
+                    base = E.EllMatrix.upload(nr, nr, K, ec, vals, E.rows_per_thread(R) | lanes)
+                    assert base.info().value_pattern_rows == 0
+                    index_rows = base.info().pattern_rows
+                    base.free()
+                    A = E.EllMatrix.upload(nr, nr, K, ec, vals, E.rows_per_thread(R) | lanes | E.VALUE_PATTERN)
+                    info = A.info()
+                    key = (R, lanes)
+                    if name == "variable":
+                        assert info.value_pattern_rows == 0 and info.pattern_rows == index_rows, (kind, dims, key)
                     else:
-                        expected_value_rows[(kind, dims, R)] = info.value_pattern_rows
-                y = y0.copy()
-                A.spmv(y, x, 1, E.ACCUMULATE)
-                assert bits_equal(y, want), (kind, dims, R, name)
-                y = np.zeros(nr)
-                A.spmv(y, x, 1, E.OVERWRITE)
-                w2 = np.zeros(nr)
-                oracle.ellgemv(nr, w2, x, K, ec, vals)
-                assert bits_equal(y, w2), (kind, dims, R, name, "overwrite")
-                c2, a2 = A.download()
-                assert np.array_equal(c2, ec) and bits_equal(a2, vals)
-                A.free()
+                        assert info.value_pattern_rows in (0, info.pattern_rows), (kind, dims, key, name)
+                        if name == "constant":
+                            full[key] = info.value_pattern_rows
+                            if index_rows > 0:
+                                assert info.value_pattern_rows == index_rows, (kind, dims, key)
+                        else:
+                            # at most the two groups of the dents leave the dictionary
+                            assert full[key] - 2 * 32 * R <= info.value_pattern_rows <= full[key], (kind, dims, key)
+                            if lanes and full[key] > 0:
+                                # group ids: a group holding a dent stays off the dictionary, if it was on it
+                                group = 32 * R
+                                on = lambda r: (ea.reshape(nr, K)[r // group * group:(r // group + 1) * group] != 0.0).all()
+                                lost = sum(group for g in {ra // group, rb // group} if on(g * group))
+                                assert info.value_pattern_rows == full[key] - lost, (kind, dims, key, lost)
+                    y = y0.copy()
+                    A.spmv(y, x, 1, E.ACCUMULATE)
+                    assert bits_equal(y, want), (kind, dims, key, name)
+                    y = np.zeros(nr)
+                    A.spmv(y, x, 1, E.OVERWRITE)
+                    assert bits_equal(y, w2), (kind, dims, key, name, "overwrite")
+                    c2, a2 = A.download()
+                    assert np.array_equal(c2, ec) and bits_equal(a2, vals)
+                    A.free()
         # FMA never searches for value patterns
         A = E.EllMatrix.upload(nr, nr, K, ec, ea, E.VALUE_PATTERN | E.FMA)
         assert A.info().value_pattern_rows == 0
         A.free()
 
 
-expected_value_rows = {}
 
 
 def test_offset_patterns_in_a_row_shard(lib, oracle):

@@ -39,8 +39,11 @@ def main():
         i = A.info()
         rows, ncols = i.num_rows, i.num_columns
     else:
-        A = E.CsrMatrix.generate(kind, dims, 42, bits, flags=E.KERNEL_WARP if args.path == "csrvec" else 0)
-        rows, ncols = dims[0], dims[1]
+        A = E.CsrMatrix.generate(kind, dims, 42, bits, flags=(E.KERNEL_WARP if args.path == "csrvec" else 0) | args.flags,
+                                 vals=vals)
+        i = A.info()
+        rows, ncols = i.num_rows, i.num_columns
+        print(A.describe())
     x = torch.randn(ncols, dtype=torch.float64, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1))
     y = torch.zeros(rows, dtype=torch.float64, device="cuda")
     for _ in range(args.launches):
