@@ -207,6 +207,25 @@ class ClockSampler:
         return total if ok else None
 
 
+def bind_near_gpu(torch, index: int) -> dict:
+    """Move this rank's host thread onto the CPUs next to its GPU (NVML's ideal affinity) before the
+    pinned e2e vectors are allocated and first touched, so that each rank's host buffers live on its
+    GPU's NUMA node instead of all ranks sharing one node's memory system."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            p = torch.cuda.get_device_properties(index)
+            h = pynvml.nvmlDeviceGetHandleByPciBusId(f"{p.pci_domain_id:08x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0")
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        before = len(os.sched_getaffinity(0))
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return {"cpus_before": before, "cpus_near_gpu": len(os.sched_getaffinity(0))}
+    except Exception as exc:
+        return {"error": repr(exc)[:120]}
+
+
 # ---------------------------------------------------------------------------
 # CPU reference arm / cpu_baseline
 # ---------------------------------------------------------------------------
@@ -702,6 +721,7 @@ def main_ours(args, rank: int, local_rank: int, world: int):
     if world == 1:
         del xs
     torch.cuda.empty_cache()
+    numa = bind_near_gpu(torch, local_rank) if world > 1 else None
     xh = torch.empty(int(info.num_columns), dtype=torch.float64).pin_memory()
     yh = torch.zeros(rows, dtype=torch.float64).pin_memory()
     xh.fill_(1.0)
@@ -732,6 +752,8 @@ def main_ours(args, rank: int, local_rank: int, world: int):
                    "steps": n_e2e, "ms_per_step": round(t_e2e / n_e2e * 1e3, 3),
                    "api": "ellspmv_cuda_spmv(A, y_host, x_host, 1, ACCUMULATE) on every rank's shard, pinned host "
                           "vectors; x is uploaded on the column range the shard references only"}
+    if numa is not None:
+        line["e2e"]["host_thread_affinity"] = numa
     del xh, yh, xn, yn
     A.free()
     torch.cuda.empty_cache()

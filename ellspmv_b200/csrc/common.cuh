@@ -139,6 +139,8 @@ cudaError_t launch_ell_spmv(const EllLaunchCfg &cfg, const EllSpmvArgs &args,
                             int64_t num_slices, cudaStream_t stream);
 // few, long rows: CTA per row group on the row-major layout (slice height 1), ell_longrow.cu
 cudaError_t launch_ell_longrow(const EllLaunchCfg &cfg, const EllSpmvArgs &args, cudaStream_t stream);
+// the thread-per-row kernel with per-row lengths (the CSR view), ell_kernels_len.cu
+cudaError_t launch_ell_thread_len(const EllLaunchCfg &cfg, const EllSpmvArgs &args, bool yvec, cudaLaunchConfig_t &lc);
 constexpr int kKernelLongRow = 4;   // ELLSPMV_CUDA_KERNEL_LONGROW
 // persistent bulk-async (TMA) staged variant, ell_bulk.cu; *handled = false: not applicable
 cudaError_t launch_ell_bulk(const EllLaunchCfg &cfg, const EllSpmvArgs &args, int64_t num_slices,
