@@ -25,8 +25,9 @@ scaling efficiency compares like with like.
              references and of y, launch, D2H of y inside the timing)
   cpu_baseline   the unmodified reference's ellgemv (oracle/_ref) on the box's
              host cores, same matrix -- a reported baseline, not the target
-  other_configs  (N = 1) BASELINE configs 3 and 4 (ELL and CSR), kernel only,
-             each with its CPU baseline on a bounded sample
+  other_configs  (N = 1) BASELINE configs 3 and 4 (ELL and CSR) and the matrices of
+             configs 2 and 3 through the CSR comparison path, kernel only, each
+             with its CPU baseline on a bounded sample
   config5    (N > 1) BASELINE config 5 itself: 27-point 768^3, strong-scaled,
              100 iterations, fused push exchange and NCCL all-gather
   parity_check   (N > 1) after k steps every rank recomputes its rows from the
@@ -445,7 +446,8 @@ def other_configs(E, torch, dev, sptr, stream, reps: int, peak: float, with_cpu:
             fn()
         return time_steps(torch, stream, fn, reps, sync) / reps
 
-    for name, fmt in (("stencil27_384", "ell"), ("random50m", "ell"), ("random50m", "csr"), ("laplace2d", "csr")):
+    for name, fmt in (("stencil27_384", "ell"), ("random50m", "ell"), ("random50m", "csr"), ("laplace2d", "csr"),
+                      ("stencil27_384", "csr")):
         kind_name, K, idx_bits, vals_acc, _, dims_of, _ = WORKLOADS[name]
         kind = {"laplace2d": E.GEN_LAPLACE2D, "stencil27": E.GEN_STENCIL27, "random": E.GEN_RANDOM}[kind_name]
         dims = dims_of(1)
