@@ -430,21 +430,24 @@ int launch(ellspmv_cuda_matrix *A, double *y_dev, const double *x_dev, int beta,
 }
 
 // One y <- beta*y + A*x with host vectors, software-pipelined over row chunks:
-// x goes up first; then for each chunk the y rows go up (beta = 1), the chunk's
-// slices run, and the finished y rows come back on a second stream, so the
-// upload of chunk c+1 (host->device) overlaps the download of chunk c
-// (device->host) on the full-duplex PCIe link.  seconds = sum of the chunk
-// kernels' device-event times.
+// three streams, one per engine.  Upload stream: for each chunk the x piece it
+// needs and its y rows (beta = 1) go up, back to back -- the host->device link is
+// what bounds the call and never waits for a kernel.  Compute stream: the chunk's
+// slices run as soon as its upload has landed.  Download stream: the finished y
+// rows come back, so the upload of chunk c+1 overlaps the download of chunk c on
+// the full-duplex PCIe link.  seconds = sum of the chunk kernels' device-event
+// times.
 int spmv_pipelined(ellspmv_cuda_matrix *A, double *y, const double *x, int beta, double *seconds)
 {
     const int64_t rows = A->lay.num_rows, ncols = A->num_columns, S = A->lay.slice_rows;
     const int64_t slices = A->lay.num_slices;
     const int nchunks = (int)(slices < 32 ? slices : 32);
     const int64_t chunk_slices = (slices + nchunks - 1) / nchunks;
-    int err = ensure_events(A->events, 2 * (size_t)nchunks);
+    int err = ensure_events(A->events, 3 * (size_t)nchunks + 1);
     if (err) return err;
     if (!A->stream_out) ELL_CK(cudaStreamCreateWithFlags(&A->stream_out, cudaStreamNonBlocking));
-    cudaStream_t s = A->stream, so = A->stream_out;
+    if (!A->stream_in) ELL_CK(cudaStreamCreateWithFlags(&A->stream_in, cudaStreamNonBlocking));
+    cudaStream_t s = A->stream, so = A->stream_out, si = A->stream_in;
     int64_t xlo, xhi;
     x_range(A, &xlo, &xhi);
     (void)ncols;
@@ -466,6 +469,9 @@ int spmv_pipelined(ellspmv_cuda_matrix *A, double *y, const double *x, int beta,
     }
     int64_t up_hi = xlo;                       // x[xlo, up_hi) is on the device (or on its way, in stream order)
     int used = 0;
+    // the uploads overwrite the handle's vectors: order them after whatever the compute stream still holds
+    ELL_CK(cudaEventRecord(A->events[3 * (size_t)nchunks], s));
+    ELL_CK(cudaStreamWaitEvent(si, A->events[3 * (size_t)nchunks], 0));
     for (int c = 0; c < nchunks; c++) {
         const int64_t s0 = c * chunk_slices;
         if (s0 >= slices) break;
@@ -476,10 +482,12 @@ int spmv_pipelined(ellspmv_cuda_matrix *A, double *y, const double *x, int beta,
         if (A->d_ad && A->row_begin + r1 > need) need = A->row_begin + r1;      // ad[i] * x[global row i]
         if (c == nchunks - 1 || need > xhi) need = xhi;
         if (need > up_hi) {
-            ELL_CK(cudaMemcpyAsync(A->d_x + up_hi, x + up_hi, (size_t)(need - up_hi) * 8, cudaMemcpyDefault, s));
+            ELL_CK(cudaMemcpyAsync(A->d_x + up_hi, x + up_hi, (size_t)(need - up_hi) * 8, cudaMemcpyDefault, si));
             up_hi = need;
         }
-        if (beta) ELL_CK(cudaMemcpyAsync(A->d_y + r0, y + r0, (size_t)(r1 - r0) * 8, cudaMemcpyDefault, s));
+        if (beta) ELL_CK(cudaMemcpyAsync(A->d_y + r0, y + r0, (size_t)(r1 - r0) * 8, cudaMemcpyDefault, si));
+        ELL_CK(cudaEventRecord(A->events[2 * (size_t)nchunks + c], si));
+        ELL_CK(cudaStreamWaitEvent(s, A->events[2 * (size_t)nchunks + c], 0));
         ELL_CK(cudaEventRecord(A->events[2 * c], s));
         if ((err = launch(A, A->d_y, A->d_x, beta, nullptr, s, s0, ns))) return err;
         ELL_CK(cudaEventRecord(A->events[2 * c + 1], s));
@@ -487,6 +495,7 @@ int spmv_pipelined(ellspmv_cuda_matrix *A, double *y, const double *x, int beta,
         ELL_CK(cudaMemcpyAsync(y + r0, A->d_y + r0, (size_t)(r1 - r0) * 8, cudaMemcpyDefault, so));
         used = c + 1;
     }
+    ELL_CK(cudaStreamSynchronize(si));
     ELL_CK(cudaStreamSynchronize(s));
     ELL_CK(cudaStreamSynchronize(so));
     if (seconds) {
@@ -755,6 +764,7 @@ void ellspmv_cuda_free(ellspmv_cuda_matrix *A)
     if (A->d_y) cudaFree(A->d_y);
     if (A->stream) cudaStreamDestroy(A->stream);
     if (A->stream_out) cudaStreamDestroy(A->stream_out);
+    if (A->stream_in) cudaStreamDestroy(A->stream_in);
     delete A;
 }
 

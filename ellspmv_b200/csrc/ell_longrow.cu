@@ -143,6 +143,214 @@ ell_longrow_kernel(const EllSpmvArgs a, int rshift)
         if (g >= a.push.row_lo[q] && g < a.push.row_hi[q]) a.push.x[q][g] = out;
 }
 
+// ---- the ring form (default): loader warps and a summing warp decoupled by mbarriers ----------
+//
+// The kernel above runs in lock-step: one CTA barrier per tile, every warp waits for the indices it
+// asked for one tile ago and then for warp 0's 128-step chain (ncu, 32 768 x 4096: long scoreboard
+// and barrier stalls in equal parts, 3 CTAs of 160 registers per SM, 1.7 TB/s).  Here the two jobs
+// never wait for each other except through a ring of parked products:
+//
+//   8 loader warps   stream the CTA's rows stage by stage (1024 entries, 4 per lane).  Values and
+//                    indices go straight into shared memory with cp.async (LDGSTS: no registers),
+//                    4 stages ahead, every lane reading back only what it asked for itself (no
+//                    barrier, just cp.async.wait_group); the gathers x[c] are issued 2 stages ahead
+//                    into registers; the ROUNDED product a*x of stage s is parked in a ring of 3
+//                    product stages, one mbarrier arrive per warp and stage.
+//   1 summing warp   lane r owns row r of the CTA (up to 32 rows): waits for a product stage, adds
+//                    its row's products in slot order with __dadd_rn (the reference's rounding
+//                    sequence, bit for bit -- same chain as above), hands the stage back.
+//
+// Same layout (row-major), same arithmetic, same y/push/diagonal/row-length handling as above.
+constexpr int kLr2Loaders = 8;                           // loader warps
+constexpr int kLr2Threads = (kLr2Loaders + 1) * 32;      // + the summing warp
+constexpr int kLr2E = 4;                                 // entries per loader lane and stage
+constexpr int kLr2Stage = kLr2Loaders * 32 * kLr2E;      // 1024 entries per stage
+constexpr int kLr2Ahead = 4;                             // cp.async distance (stages) of the default instantiation
+constexpr int kLr2Products = 3;                          // product stages of the default instantiation
+constexpr int kLr2ProdStride = kLr2Stage + 32;           // a row of a stage starts at r * (T_row + 1)
+
+__device__ __forceinline__ unsigned lr_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+// a wait that never ends (a lost arrive) traps the launch after ~10 s instead of hanging the device
+__device__ __forceinline__ void lr_mbar_wait(unsigned bar, unsigned parity)
+{
+    long long t0 = 0;
+    for (int spin = 0;; spin++) {
+        unsigned ok;
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok) return;
+        if (spin == 1024) t0 = clock64();
+        if (spin > 1024 && (spin & 1023) == 0 && clock64() - t0 > 20000000000LL) __trap();
+    }
+}
+__device__ __forceinline__ void lr_mbar_arrive(unsigned bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+template <typename IdxT, int kLr2Ahead, int kLr2NSP>
+__global__ void __launch_bounds__(kLr2Threads)
+ell_longrow_ring_kernel(const EllSpmvArgs a, int rshift)
+{
+    constexpr int kLr2NSV = kLr2Ahead + 1;                                    // value/index staging slots
+    extern __shared__ __align__(16) unsigned char lr_smem[];
+    double *sv = reinterpret_cast<double *>(lr_smem);                         // [NSV][1024] values
+    double *sp = sv + kLr2NSV * kLr2Stage;                                    // [NSP][1024 + 32] products
+    IdxT *sc = reinterpret_cast<IdxT *>(sp + kLr2NSP * kLr2ProdStride);       // [NSV][1024] indices
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(sc + kLr2NSV * kLr2Stage);   // full[NSP], empty[NSP]
+
+    const int K = a.rowsize;
+    const int rpc = 1 << rshift;
+    const int tshift = 10 - rshift;                                           // log2(T_row)
+    const int T_row = 1 << tshift;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t row0 = (int64_t)blockIdx.x * rpc;
+    const int nrows = (int)((a.num_rows - row0 < rpc) ? a.num_rows - row0 : rpc);
+    const int ntiles = (K + T_row - 1) >> tshift;
+    const unsigned bar0 = lr_smem_u32(bars);
+
+    if (tid == 0) {
+        for (int i = 0; i < kLr2NSP; i++) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8 * i), "r"(kLr2Loaders));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8 * (kLr2NSP + i)), "r"(1));
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp < kLr2Loaders) {
+        // ---- loader: entry j of this lane is flat f = j*256 + tid of a stage -> row f >> tshift,
+        // slot (stage << tshift) + (f & (T_row-1)); T_row is a multiple of 32, so the 32 lanes of an
+        // instruction read 32 consecutive slots of one row
+        const double *__restrict__ x = a.x;
+        const IdxT *cols = reinterpret_cast<const IdxT *>(a.cols);
+        int64_t ebase[kLr2E];
+        int lo[kLr2E], poff[kLr2E];
+#pragma unroll
+        for (int j = 0; j < kLr2E; j++) {
+            const int f = j * (kLr2Loaders * 32) + tid;
+            const int r = f >> tshift;
+            lo[j] = (r < nrows) ? (f & (T_row - 1)) : K;                      // K: never valid
+            ebase[j] = (row0 + r) * (int64_t)K + (f & (T_row - 1));
+            poff[j] = r * (T_row + 1) + (f & (T_row - 1));
+        }
+        auto stage_in = [&](int t) {                                          // cp.async of stage t (one group, maybe empty)
+            if (t < ntiles) {
+                const int q = t % kLr2NSV;
+#pragma unroll
+                for (int j = 0; j < kLr2E; j++) {
+                    if ((int64_t)lo[j] + ((int64_t)t << tshift) < K) {
+                        const int64_t e = ebase[j] + ((int64_t)t << tshift);
+                        const int si = q * kLr2Stage + j * (kLr2Loaders * 32) + tid;
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(lr_smem_u32(sv + si)), "l"(a.vals + e) : "memory");
+                        if (sizeof(IdxT) == 4)
+                            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(lr_smem_u32(sc + si)), "l"(cols + e) : "memory");
+                        else
+                            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(lr_smem_u32(sc + si)), "l"(cols + e) : "memory");
+                    }
+                }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        auto gather = [&](int t, double (&xv)[kLr2E]) {                       // x[c] of stage t (its indices have landed)
+            const int q = t % kLr2NSV;
+#pragma unroll
+            for (int j = 0; j < kLr2E; j++) {
+                xv[j] = 0.0;
+                if (t < ntiles && (int64_t)lo[j] + ((int64_t)t << tshift) < K)
+                    xv[j] = __ldg(x + (int64_t)sc[q * kLr2Stage + j * (kLr2Loaders * 32) + tid]);
+            }
+        };
+        auto park = [&](int t, const double (&xv)[kLr2E]) {                   // products of stage t -> ring, one arrive per warp
+            const int q = t % kLr2NSV, pq = t % kLr2NSP, use = t / kLr2NSP;
+            if (use > 0) lr_mbar_wait(bar0 + 8 * (kLr2NSP + pq), (unsigned)((use - 1) & 1));
+            double *p = sp + pq * kLr2ProdStride;
+#pragma unroll
+            for (int j = 0; j < kLr2E; j++)
+                if ((int64_t)lo[j] + ((int64_t)t << tshift) < K)
+                    p[poff[j]] = __dmul_rn(sv[q * kLr2Stage + j * (kLr2Loaders * 32) + tid], xv[j]);
+            __syncwarp();
+            if (lane == 0) lr_mbar_arrive(bar0 + 8 * pq);
+        };
+
+        double xa[kLr2E], xb[kLr2E];
+#pragma unroll
+        for (int t = 0; t < kLr2Ahead; t++) stage_in(t);
+        asm volatile("cp.async.wait_group %0;" ::"n"(kLr2Ahead - 2) : "memory");    // stages 0 and 1 have landed
+        gather(0, xa);
+        gather(1, xb);
+        // iteration t: ask for stage t+4, wait until stage t+2 has landed, park stage t (its gathers
+        // were issued two iterations ago), issue the gathers of stage t+2 into the registers just freed
+        for (int t = 0; t < ntiles; t += 2) {
+            stage_in(t + kLr2Ahead);
+            asm volatile("cp.async.wait_group %0;" ::"n"(kLr2Ahead - 2) : "memory");
+            park(t, xa);
+            gather(t + 2, xa);
+            if (t + 1 < ntiles) {
+                stage_in(t + 1 + kLr2Ahead);
+                asm volatile("cp.async.wait_group %0;" ::"n"(kLr2Ahead - 2) : "memory");
+                park(t + 1, xb);
+                gather(t + 3, xb);
+            }
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        return;
+    }
+
+    // ---- the summing warp: lane r adds row r's products in slot order
+    const bool summer = lane < nrows;
+    const int64_t row = row0 + lane;
+    const int len = (summer && a.rowlen) ? a.rowlen[row] : K;                 // CSR view: only the first rowlen[row] slots count
+    double acc = 0.0, dx = 0.0;
+    if (summer && a.ad) {
+        dx = __dmul_rn(a.ad[row], __ldg(a.x + a.row_begin + row));
+        if (a.sd_order) acc = dx;
+    }
+    for (int t = 0; t < ntiles; t++) {
+        const int pq = t % kLr2NSP, use = t / kLr2NSP;
+        lr_mbar_wait(bar0 + 8 * pq, (unsigned)(use & 1));
+        if (summer) {
+            const int n = (len - (t << tshift) < T_row) ? len - (t << tshift) : T_row;   // may be <= 0: nothing left
+            const double *q = sp + pq * kLr2ProdStride + lane * (T_row + 1);
+            int l = 0;
+            if (n >= 8) {
+                double w[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) w[j] = q[j];
+                for (l = 8; l + 8 <= n; l += 8) {
+                    double wn[8];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) wn[j] = q[l + j];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) acc = __dadd_rn(acc, w[j]);
+#pragma unroll
+                    for (int j = 0; j < 8; j++) w[j] = wn[j];
+                }
+#pragma unroll
+                for (int j = 0; j < 8; j++) acc = __dadd_rn(acc, w[j]);
+            }
+            for (; l < n; l++) acc = __dadd_rn(acc, q[l]);
+        }
+        __syncwarp();
+        if (lane == 0) lr_mbar_arrive(bar0 + 8 * (kLr2NSP + pq));
+    }
+    if (!summer) return;
+    if (a.ad && !a.sd_order) acc = __dadd_rn(dx, acc);
+    const double yold = a.beta ? a.y[row] : 0.0;
+    const double out = __dadd_rn(yold, acc);
+    a.y[row] = out;
+    const int64_t g = a.row_begin + row;
+    for (int q = 0; q < a.push.num_peers; q++)
+        if (g >= a.push.row_lo[q] && g < a.push.row_hi[q]) a.push.x[q][g] = out;
+}
+
+template <typename IdxT, int AHEAD, int NSP>
+constexpr size_t lr2_smem_bytes()
+{
+    return (size_t)(AHEAD + 1) * kLr2Stage * (8 + sizeof(IdxT)) + (size_t)NSP * kLr2ProdStride * 8 + 2 * NSP * 8;
+}
+
 // Rows per CTA (1 << rshift).  A tile is 1024 entries; with r rows per CTA each row contributes
 // T_row = 1024 / r consecutive slots per tile.  Two opposite costs (profiles/r2_k_sweep.md):
 //   * the summing lane of a row runs T_row dependent additions per tile while the loads of the
@@ -152,6 +360,7 @@ ell_longrow_kernel(const EllSpmvArgs a, int rshift)
 // T_row = 128 (8 rows per CTA: 1 KB value pieces, 128-step chains) balances the two; short rows
 // (K < 128) take more rows per CTA so that a tile is not mostly empty, and matrices with few
 // rows take fewer so that there are ~4 CTAs per SM.
+// the lock-step form: rows per CTA for ~4 CTAs per SM
 int longrow_rshift(int64_t num_rows, int rowsize, int num_sms)
 {
     int rshift = 3;
@@ -160,14 +369,57 @@ int longrow_rshift(int64_t num_rows, int rowsize, int num_sms)
     return rshift;
 }
 
+// the ring form: the summing warp has 32 lanes, so up to 32 rows per CTA (32-slot pieces per row and
+// stage).  What bounds a CTA is either its loaders (a stage per ~0.5 us whatever the rows per CTA) or
+// the chain of its rows (1024 / rows-per-CTA dependent additions per stage): as many rows per CTA as
+// still leave ~1.5 CTAs per SM (two are resident) keeps the most chains running at once
+// (profiles/r2_longrow_ring.md).
+int longrow_ring_rshift(int64_t num_rows, int rowsize, int num_sms)
+{
+    int rshift = 5;
+    while (rshift > 0 && (num_rows >> rshift) < ((int64_t)num_sms * 3) / 2) rshift--;
+    return rshift;
+}
+
+template <typename IdxT, int AHEAD, int NSP>
+static cudaError_t launch_ring(const EllSpmvArgs &args, int rshift, unsigned grid, cudaStream_t stream)
+{
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaError_t ce = cudaGetDevice(&dev);
+    if (ce != cudaSuccess) return ce;
+    constexpr size_t smem = lr2_smem_bytes<IdxT, AHEAD, NSP>();
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+        ce = cudaFuncSetAttribute(ell_longrow_ring_kernel<IdxT, AHEAD, NSP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (ce != cudaSuccess) return ce;
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
+    ell_longrow_ring_kernel<IdxT, AHEAD, NSP><<<grid, kLr2Threads, smem, stream>>>(args, rshift);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_ell_longrow(const EllLaunchCfg &cfg, const EllSpmvArgs &args, cudaStream_t stream)
 {
     if (args.num_rows <= 0) return cudaSuccess;
-    int rshift = longrow_rshift(args.num_rows, args.rowsize, cfg.num_sms > 0 ? cfg.num_sms : 148);
-    static const int rshift_env = getenv("ELLSPMV_CUDA_LONGROW_RSHIFT") ? atoi(getenv("ELLSPMV_CUDA_LONGROW_RSHIFT")) : -1;
+    const int sms = cfg.num_sms > 0 ? cfg.num_sms : 148;
+    // read per launch (a launch here moves megabytes): the parity tests walk every form and rows-per-CTA choice
+    const char *ve = getenv("ELLSPMV_CUDA_LONGROW_VARIANT"), *re = getenv("ELLSPMV_CUDA_LONGROW_RSHIFT");
+    const int variant_env = ve ? atoi(ve) : 1, rshift_env = re ? atoi(re) : -1;
+    const bool ring = variant_env != 0;                              // 0: the lock-step form (experiments, A/B)
+    int rshift = ring ? longrow_ring_rshift(args.num_rows, args.rowsize, sms) : longrow_rshift(args.num_rows, args.rowsize, sms);
     if (rshift_env >= 0 && rshift_env <= 5) rshift = rshift_env;     // experiments
     const int64_t grid = (args.num_rows + (1 << rshift) - 1) >> rshift;
     if (grid > 0x7fffffffLL) return cudaErrorInvalidValue;
+    if (ring) {
+        if (variant_env == 2)                                        // experiments: 3 CTAs per SM, shorter rings
+            return cfg.idx_bits == 64 ? launch_ring<int64_t, 3, 2>(args, rshift, (unsigned)grid, stream)
+                                      : launch_ring<int32_t, 3, 2>(args, rshift, (unsigned)grid, stream);
+        if (variant_env == 3)
+            return cfg.idx_bits == 64 ? launch_ring<int64_t, 3, 3>(args, rshift, (unsigned)grid, stream)
+                                      : launch_ring<int32_t, 3, 3>(args, rshift, (unsigned)grid, stream);
+        return cfg.idx_bits == 64 ? launch_ring<int64_t, kLr2Ahead, kLr2Products>(args, rshift, (unsigned)grid, stream)
+                                  : launch_ring<int32_t, kLr2Ahead, kLr2Products>(args, rshift, (unsigned)grid, stream);
+    }
     if (cfg.idx_bits == 64)
         ell_longrow_kernel<int64_t><<<(unsigned)grid, kLrThreads, 0, stream>>>(args, rshift);
     else

@@ -57,6 +57,7 @@ struct ellspmv_cuda_matrix {
     bool handshake_pending = false;
     cudaStream_t stream = nullptr;
     cudaStream_t stream_out = nullptr;       // D2H stream of the pipelined host call
+    cudaStream_t stream_in = nullptr;        // H2D stream of the pipelined host call
     double *d_x = nullptr, *d_y = nullptr;   // vectors of the host-facing spmv
     std::vector<long long> chunk_max;        // pipelined host call: largest column each row chunk references
     int64_t vec_len = 0;

@@ -501,6 +501,50 @@ def test_long_row_kernel_is_bit_exact(lib, oracle, shape, bits):
     assert bits_equal(y[ok], w[ok])
 
 
+@pytest.mark.parametrize("variant", [1, 0])
+@pytest.mark.parametrize("rshift", [0, 1, 2, 3, 4, 5])
+def test_long_row_kernel_every_rows_per_cta(lib, oracle, monkeypatch, variant, rshift):
+    """Both forms of the long-row kernel (1: loader warps + a summing warp over an mbarrier ring, the
+    default; 0: the lock-step form) at every rows-per-CTA choice: ragged last CTA, K not a multiple of
+    the stage, one tile, many tiles, 64-bit indices, per-row lengths through the CSR view."""
+    monkeypatch.setenv("ELLSPMV_CUDA_LONGROW_VARIANT", str(variant))
+    monkeypatch.setenv("ELLSPMV_CUDA_LONGROW_RSHIFT", str(rshift))
+    for (nr, nc, K), dt in (((37, 5000, 3001), np.int32), ((70, 300, 64), np.int64), ((5, 20000, 10241), np.int32),
+                            ((1, 7, 1), np.int32), ((129, 4000, 1024), np.int64)):
+        rng = np.random.default_rng(nr * 7 + K + rshift)
+        ec, ea = rand_ell(rng, nr, nc, K, dt)
+        x = rng.standard_normal(nc)
+        y0 = rng.standard_normal(nr)
+        want = y0.copy()
+        oracle.ellgemv(nr, want, x, K, ec, ea)
+        A = E.EllMatrix.upload(nr, nc, K, ec, ea, E.KERNEL_LONGROW)
+        assert A.info().kernel == E.KERNEL_LONGROW
+        y = y0.copy()
+        A.spmv(y, x, 1, E.ACCUMULATE)
+        A.free()
+        assert bits_equal(y, want), (nr, nc, K, variant, rshift)
+    # CSR rows of different lengths (few, long): the view hands the kernel per-row lengths
+    rng = np.random.default_rng(rshift)
+    nr, nc = 50, 6000
+    lens = rng.integers(1500, 1900, nr)
+    rowptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    cols = rng.integers(0, nc, rowptr[-1]).astype(np.int32)
+    vals = rng.standard_normal(rowptr[-1])
+    x = rng.standard_normal(nc)
+    x[rng.integers(0, nc, 2)] = np.inf
+    want = np.zeros(nr)
+    oracle.csrgemv(nr, want, x, rowptr, cols, vals)
+    C = E.CsrMatrix.upload(nr, nc, rowptr, cols, vals)
+    y = np.zeros(nr)
+    C.spmv(y, x, 1, E.ACCUMULATE)
+    view = C.info().ell_view
+    C.free()
+    assert view == 1                      # the sliced-ELL view with per-row lengths; 50 rows -> the long-row kernel
+    assert np.array_equal(np.isnan(y), np.isnan(want))
+    ok = ~np.isnan(want)
+    assert bits_equal(y[ok], want[ok]), (variant, rshift)
+
+
 def test_long_row_kernel_in_a_shard_and_iterate(lib, oracle):
     import torch
     nr = nc = 900

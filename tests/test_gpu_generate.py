@@ -131,6 +131,51 @@ def test_full_size_stencil27_properties(lib):
     assert torch.equal(ys[0], ys[1])
 
 
+@pytest.mark.parametrize("rank", [0, 3])
+def test_full_size_config5_shard_properties(lib, rank):
+    """BASELINE config 5 (27-point 768^3, IDXTYPEWIDTH=64) as one of its 8 row shards at full size
+    (56.6M rows of 453M, global column indices, x of full length -- what rank `rank` of
+    `bench.py --gpus 8` holds): A*ones = 27 - (#stencil points) exactly, the indices are narrowed
+    (453M columns < 2^31) and mostly taken from offset patterns, and scaling x by 2 scales y by 2 bit
+    for bit.  The exchange itself is covered by test_gpu_sharded / bench.py's parity_check."""
+    import torch
+    n, world = 768, 8
+    rows = n ** 3
+    lo, hi = rank * (rows // world), (rank + 1) * (rows // world)
+    s = torch.cuda.current_stream().cuda_stream
+    A = E.EllMatrix.generate(E.GEN_STENCIL27, (n, n, n), (26.0, -1.0), 42, 64, row_begin=lo, row_end=hi)
+    i = A.info()
+    assert (i.num_rows, i.num_columns, i.rowsize, i.idx_width_bits, i.dev_idx_bits) == (hi - lo, rows, 27, 64, 32)
+    assert i.pattern_rows >= 0.9 * (hi - lo)
+    c = torch.full((n,), 3.0, dtype=torch.float64, device="cuda")
+    c[0] = c[-1] = 2.0
+    planes = n // world
+    want = 27.0 - (c[rank * planes:(rank + 1) * planes, None, None] * c[None, :, None] * c[None, None, :]).reshape(-1)
+    x = torch.ones(rows, dtype=torch.float64, device="cuda")
+    y = torch.zeros(hi - lo, dtype=torch.float64, device="cuda")
+    A.spmv_device(y, x, E.ACCUMULATE, s)
+    assert torch.equal(y, want)
+    del want
+    gen = torch.Generator(device="cuda").manual_seed(11 + rank)
+    x.normal_(generator=gen)
+    A.spmv_device(y, x, E.OVERWRITE, s)
+    y2 = torch.empty_like(y)
+    x *= 2
+    A.spmv_device(y2, x, E.OVERWRITE, s)
+    assert torch.equal(y2, 2 * y)
+    # the same rows without patterns and with the caller's 64-bit indices: same bits
+    torch.cuda.synchronize()
+    A.free()
+    B = E.EllMatrix.generate(E.GEN_STENCIL27, (n, n, n), (26.0, -1.0), 42, 64, row_begin=lo, row_end=hi,
+                             flags=E.WIDE_INDEX | E.NO_PATTERN)
+    assert B.info().dev_idx_bits == 64 and B.info().pattern_rows == 0
+    y3 = torch.empty_like(y)
+    B.spmv_device(y3, x, E.OVERWRITE, s)
+    assert torch.equal(y3, y2)
+    torch.cuda.synchronize()
+    B.free()
+
+
 def test_full_size_random_ell_equals_csr(lib):
     """BASELINE config 4 at full size (50M x 32, 19 GB per format): the ELL
     path and the CSR comparison path hold the same entries in the same order,
