@@ -4,7 +4,10 @@
 // for HBM; a matrix with a few thousand rows of a few thousand entries each leaves most of the
 // GPU idle there (profiles/r2_k_sweep.md).  The reference's loop (ellspmv.c:1146-1151) fixes the
 // ORDER of the additions inside a row but says nothing about who loads the operands, so here a
-// whole CTA works on a small group of rows:
+// whole CTA works on a small group of rows.  Two forms share layout and arithmetic: the lock-step
+// form directly below (round 2's first; kept for A/B and the parity tests,
+// ELLSPMV_CUDA_LONGROW_VARIANT=0) and the ring form further down (the default: loader warps and a
+// summing warp decoupled by mbarriers, 1.5-2.3x faster).  The lock-step form:
 //
 //   layout   row-major, exactly the reference's arrays (slice height 1): entries of a row are
 //            contiguous, so 32 lanes reading 32 consecutive slots of one row is a fully
@@ -154,8 +157,8 @@ ell_longrow_kernel(const EllSpmvArgs a, int rshift)
 //                    indices go straight into shared memory with cp.async (LDGSTS: no registers),
 //                    4 stages ahead, every lane reading back only what it asked for itself (no
 //                    barrier, just cp.async.wait_group); the gathers x[c] are issued 2 stages ahead
-//                    into registers; the ROUNDED product a*x of stage s is parked in a ring of 3
-//                    product stages, one mbarrier arrive per warp and stage.
+//                    into registers (L2-only loads); the ROUNDED product a*x of stage s is parked in a
+//                    ring of 2 product stages, one mbarrier arrive per warp and stage.
 //   1 summing warp   lane r owns row r of the CTA (up to 32 rows): waits for a product stage, adds
 //                    its row's products in slot order with __dadd_rn (the reference's rounding
 //                    sequence, bit for bit -- same chain as above), hands the stage back.
@@ -165,8 +168,13 @@ constexpr int kLr2Loaders = 8;                           // loader warps
 constexpr int kLr2Threads = (kLr2Loaders + 1) * 32;      // + the summing warp
 constexpr int kLr2E = 4;                                 // entries per loader lane and stage
 constexpr int kLr2Stage = kLr2Loaders * 32 * kLr2E;      // 1024 entries per stage
-constexpr int kLr2Ahead = 4;                             // cp.async distance (stages) of the default instantiation
-constexpr int kLr2Products = 3;                          // product stages of the default instantiation
+// Depths, measured (profiles/r2_longrow_ring.md): cp.async 4 stages ahead (3: twice as slow -- a stage then
+// has one iteration to land), 2 product stages and L2-only gathers (ld.global.cg).  Shared memory and
+// L1 share 256 KB per SM and every gather in flight holds an L1 line: a smaller ring and gathers that
+// bypass L1 beat a deeper ring (6 stages ahead: twice as slow again; L1::no_allocate gathers: 30 % slower).
+constexpr int kLr2Ahead = 4;                             // cp.async distance (stages)
+constexpr int kLr2Products = 2;                          // product stages
+constexpr int kLr2Gather = 2;                            // 0: ld.global.nc (__ldg), 1: nc.L1::no_allocate, 2: ld.global.cg
 constexpr int kLr2ProdStride = kLr2Stage + 32;           // a row of a stage starts at r * (T_row + 1)
 
 __device__ __forceinline__ unsigned lr_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -189,7 +197,17 @@ __device__ __forceinline__ void lr_mbar_arrive(unsigned bar)
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-template <typename IdxT, int kLr2Ahead, int kLr2NSP>
+template <int GM>
+__device__ __forceinline__ double lr_gather(const double *p)
+{
+    double v;
+    if (GM == 1) asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    else if (GM == 2) asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    else v = __ldg(p);
+    return v;
+}
+
+template <typename IdxT, int kLr2Ahead, int kLr2NSP, int GM = 0>
 __global__ void __launch_bounds__(kLr2Threads)
 ell_longrow_ring_kernel(const EllSpmvArgs a, int rshift)
 {
@@ -222,76 +240,104 @@ ell_longrow_ring_kernel(const EllSpmvArgs a, int rshift)
     if (warp < kLr2Loaders) {
         // ---- loader: entry j of this lane is flat f = j*256 + tid of a stage -> row f >> tshift,
         // slot (stage << tshift) + (f & (T_row-1)); T_row is a multiple of 32, so the 32 lanes of an
-        // instruction read 32 consecutive slots of one row
+        // instruction read 32 consecutive slots of one row.  Stages below nfull hold a real entry for
+        // every lane (all rows of the CTA exist, the stage ends inside the rows): no per-entry checks
+        // there; stage numbers and ring slots are running counters (no division in the loop).
         const double *__restrict__ x = a.x;
         const IdxT *cols = reinterpret_cast<const IdxT *>(a.cols);
-        int64_t ebase[kLr2E];
+        constexpr int kLanes = kLr2Loaders * 32;
+        const int nfull = (nrows == rpc) ? (K >> tshift) : 0;
+        const double *vptr[kLr2E];
+        const IdxT *cptr[kLr2E];
         int lo[kLr2E], poff[kLr2E];
 #pragma unroll
         for (int j = 0; j < kLr2E; j++) {
-            const int f = j * (kLr2Loaders * 32) + tid;
-            const int r = f >> tshift;
-            lo[j] = (r < nrows) ? (f & (T_row - 1)) : K;                      // K: never valid
-            ebase[j] = (row0 + r) * (int64_t)K + (f & (T_row - 1));
-            poff[j] = r * (T_row + 1) + (f & (T_row - 1));
+            const int f = j * kLanes + tid;
+            const int r = f >> tshift, s0 = f & (T_row - 1);
+            lo[j] = (r < nrows) ? s0 : K;                                     // K: never a real entry
+            const int64_t e0 = (row0 + r) * (int64_t)K + s0;
+            vptr[j] = a.vals + e0;
+            cptr[j] = cols + e0;
+            poff[j] = r * (T_row + 1) + s0;
         }
-        auto stage_in = [&](int t) {                                          // cp.async of stage t (one group, maybe empty)
-            if (t < ntiles) {
-                const int q = t % kLr2NSV;
+        int ti = 0, qi = 0;                                                   // next stage to ask for, its staging slot
+        auto stage_in = [&]() {                                               // cp.async of stage ti (one group, maybe empty)
+            if (ti < ntiles) {
+                const int64_t off = (int64_t)ti << tshift;
+                double *dv = sv + qi * kLr2Stage + tid;
+                IdxT *dc = sc + qi * kLr2Stage + tid;
+                const bool full = ti < nfull;
 #pragma unroll
                 for (int j = 0; j < kLr2E; j++) {
-                    if ((int64_t)lo[j] + ((int64_t)t << tshift) < K) {
-                        const int64_t e = ebase[j] + ((int64_t)t << tshift);
-                        const int si = q * kLr2Stage + j * (kLr2Loaders * 32) + tid;
-                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(lr_smem_u32(sv + si)), "l"(a.vals + e) : "memory");
+                    if (full || (int64_t)lo[j] + off < K) {
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(lr_smem_u32(dv + j * kLanes)), "l"(vptr[j] + off) : "memory");
                         if (sizeof(IdxT) == 4)
-                            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(lr_smem_u32(sc + si)), "l"(cols + e) : "memory");
+                            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(lr_smem_u32(dc + j * kLanes)), "l"(cptr[j] + off) : "memory");
                         else
-                            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(lr_smem_u32(sc + si)), "l"(cols + e) : "memory");
+                            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(lr_smem_u32(dc + j * kLanes)), "l"(cptr[j] + off) : "memory");
                     }
                 }
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
+            ti++;
+            qi = (qi + 1 == kLr2NSV) ? 0 : qi + 1;
         };
-        auto gather = [&](int t, double (&xv)[kLr2E]) {                       // x[c] of stage t (its indices have landed)
-            const int q = t % kLr2NSV;
+        int tg = 0, qg = 0;                                                   // next stage to gather for, its staging slot
+        auto gather = [&](double (&xv)[kLr2E]) {                              // x[c] of stage tg (its indices have landed)
+            const IdxT *c = sc + qg * kLr2Stage + tid;
+            if (tg < nfull) {
 #pragma unroll
-            for (int j = 0; j < kLr2E; j++) {
-                xv[j] = 0.0;
-                if (t < ntiles && (int64_t)lo[j] + ((int64_t)t << tshift) < K)
-                    xv[j] = __ldg(x + (int64_t)sc[q * kLr2Stage + j * (kLr2Loaders * 32) + tid]);
+                for (int j = 0; j < kLr2E; j++) xv[j] = lr_gather<GM>(x + (int64_t)c[j * kLanes]);
+            } else {
+                const int64_t off = (int64_t)tg << tshift;
+#pragma unroll
+                for (int j = 0; j < kLr2E; j++) {
+                    xv[j] = 0.0;
+                    if (tg < ntiles && (int64_t)lo[j] + off < K) xv[j] = lr_gather<GM>(x + (int64_t)c[j * kLanes]);
+                }
             }
+            tg++;
+            qg = (qg + 1 == kLr2NSV) ? 0 : qg + 1;
         };
-        auto park = [&](int t, const double (&xv)[kLr2E]) {                   // products of stage t -> ring, one arrive per warp
-            const int q = t % kLr2NSV, pq = t % kLr2NSP, use = t / kLr2NSP;
-            if (use > 0) lr_mbar_wait(bar0 + 8 * (kLr2NSP + pq), (unsigned)((use - 1) & 1));
+        int tp = 0, qp = 0, pq = 0, pround = 0;                               // next stage to park, its staging / product slots
+        auto park = [&](const double (&xv)[kLr2E]) {                          // products of stage tp -> ring, one arrive per warp
+            if (pround > 0) lr_mbar_wait(bar0 + 8 * (kLr2NSP + pq), (unsigned)((pround - 1) & 1));
             double *p = sp + pq * kLr2ProdStride;
+            const double *v = sv + qp * kLr2Stage + tid;
+            if (tp < nfull) {
 #pragma unroll
-            for (int j = 0; j < kLr2E; j++)
-                if ((int64_t)lo[j] + ((int64_t)t << tshift) < K)
-                    p[poff[j]] = __dmul_rn(sv[q * kLr2Stage + j * (kLr2Loaders * 32) + tid], xv[j]);
+                for (int j = 0; j < kLr2E; j++) p[poff[j]] = __dmul_rn(v[j * kLanes], xv[j]);
+            } else {
+                const int64_t off = (int64_t)tp << tshift;
+#pragma unroll
+                for (int j = 0; j < kLr2E; j++)
+                    if ((int64_t)lo[j] + off < K) p[poff[j]] = __dmul_rn(v[j * kLanes], xv[j]);
+            }
             __syncwarp();
             if (lane == 0) lr_mbar_arrive(bar0 + 8 * pq);
+            tp++;
+            qp = (qp + 1 == kLr2NSV) ? 0 : qp + 1;
+            if (++pq == kLr2NSP) { pq = 0; pround++; }
         };
 
         double xa[kLr2E], xb[kLr2E];
 #pragma unroll
-        for (int t = 0; t < kLr2Ahead; t++) stage_in(t);
+        for (int t = 0; t < kLr2Ahead; t++) stage_in();
         asm volatile("cp.async.wait_group %0;" ::"n"(kLr2Ahead - 2) : "memory");    // stages 0 and 1 have landed
-        gather(0, xa);
-        gather(1, xb);
+        gather(xa);
+        gather(xb);
         // iteration t: ask for stage t+4, wait until stage t+2 has landed, park stage t (its gathers
         // were issued two iterations ago), issue the gathers of stage t+2 into the registers just freed
         for (int t = 0; t < ntiles; t += 2) {
-            stage_in(t + kLr2Ahead);
+            stage_in();
             asm volatile("cp.async.wait_group %0;" ::"n"(kLr2Ahead - 2) : "memory");
-            park(t, xa);
-            gather(t + 2, xa);
+            park(xa);
+            gather(xa);
             if (t + 1 < ntiles) {
-                stage_in(t + 1 + kLr2Ahead);
+                stage_in();
                 asm volatile("cp.async.wait_group %0;" ::"n"(kLr2Ahead - 2) : "memory");
-                park(t + 1, xb);
-                gather(t + 3, xb);
+                park(xb);
+                gather(xb);
             }
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -307,11 +353,11 @@ ell_longrow_ring_kernel(const EllSpmvArgs a, int rshift)
         dx = __dmul_rn(a.ad[row], __ldg(a.x + a.row_begin + row));
         if (a.sd_order) acc = dx;
     }
+    int pq = 0, pround = 0, left = len;                                       // left: slots of this row not yet added
     for (int t = 0; t < ntiles; t++) {
-        const int pq = t % kLr2NSP, use = t / kLr2NSP;
-        lr_mbar_wait(bar0 + 8 * pq, (unsigned)(use & 1));
+        lr_mbar_wait(bar0 + 8 * pq, (unsigned)(pround & 1));
         if (summer) {
-            const int n = (len - (t << tshift) < T_row) ? len - (t << tshift) : T_row;   // may be <= 0: nothing left
+            const int n = left < T_row ? left : T_row;                        // may be <= 0: nothing left
             const double *q = sp + pq * kLr2ProdStride + lane * (T_row + 1);
             int l = 0;
             if (n >= 8) {
@@ -331,9 +377,11 @@ ell_longrow_ring_kernel(const EllSpmvArgs a, int rshift)
                 for (int j = 0; j < 8; j++) acc = __dadd_rn(acc, w[j]);
             }
             for (; l < n; l++) acc = __dadd_rn(acc, q[l]);
+            left -= T_row;
         }
         __syncwarp();
         if (lane == 0) lr_mbar_arrive(bar0 + 8 * (kLr2NSP + pq));
+        if (++pq == kLr2NSP) { pq = 0; pround++; }
     }
     if (!summer) return;
     if (a.ad && !a.sd_order) acc = __dadd_rn(dx, acc);
@@ -381,7 +429,7 @@ int longrow_ring_rshift(int64_t num_rows, int rowsize, int num_sms)
     return rshift;
 }
 
-template <typename IdxT, int AHEAD, int NSP>
+template <typename IdxT, int AHEAD, int NSP, int GM = 0>
 static cudaError_t launch_ring(const EllSpmvArgs &args, int rshift, unsigned grid, cudaStream_t stream)
 {
     static bool attr_set[64] = {};
@@ -390,11 +438,11 @@ static cudaError_t launch_ring(const EllSpmvArgs &args, int rshift, unsigned gri
     if (ce != cudaSuccess) return ce;
     constexpr size_t smem = lr2_smem_bytes<IdxT, AHEAD, NSP>();
     if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-        ce = cudaFuncSetAttribute(ell_longrow_ring_kernel<IdxT, AHEAD, NSP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        ce = cudaFuncSetAttribute(ell_longrow_ring_kernel<IdxT, AHEAD, NSP, GM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (ce != cudaSuccess) return ce;
         if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
-    ell_longrow_ring_kernel<IdxT, AHEAD, NSP><<<grid, kLr2Threads, smem, stream>>>(args, rshift);
+    ell_longrow_ring_kernel<IdxT, AHEAD, NSP, GM><<<grid, kLr2Threads, smem, stream>>>(args, rshift);
     return cudaGetLastError();
 }
 
@@ -405,20 +453,17 @@ cudaError_t launch_ell_longrow(const EllLaunchCfg &cfg, const EllSpmvArgs &args,
     // read per launch (a launch here moves megabytes): the parity tests walk every form and rows-per-CTA choice
     const char *ve = getenv("ELLSPMV_CUDA_LONGROW_VARIANT"), *re = getenv("ELLSPMV_CUDA_LONGROW_RSHIFT");
     const int variant_env = ve ? atoi(ve) : 1, rshift_env = re ? atoi(re) : -1;
-    const bool ring = variant_env != 0;                              // 0: the lock-step form (experiments, A/B)
+    const bool ring = variant_env != 0;                              // 0: the lock-step form (A/B, parity tests)
     int rshift = ring ? longrow_ring_rshift(args.num_rows, args.rowsize, sms) : longrow_rshift(args.num_rows, args.rowsize, sms);
     if (rshift_env >= 0 && rshift_env <= 5) rshift = rshift_env;     // experiments
     const int64_t grid = (args.num_rows + (1 << rshift) - 1) >> rshift;
     if (grid > 0x7fffffffLL) return cudaErrorInvalidValue;
     if (ring) {
-        if (variant_env == 2)                                        // experiments: 3 CTAs per SM, shorter rings
-            return cfg.idx_bits == 64 ? launch_ring<int64_t, 3, 2>(args, rshift, (unsigned)grid, stream)
-                                      : launch_ring<int32_t, 3, 2>(args, rshift, (unsigned)grid, stream);
-        if (variant_env == 3)
-            return cfg.idx_bits == 64 ? launch_ring<int64_t, 3, 3>(args, rshift, (unsigned)grid, stream)
-                                      : launch_ring<int32_t, 3, 3>(args, rshift, (unsigned)grid, stream);
-        return cfg.idx_bits == 64 ? launch_ring<int64_t, kLr2Ahead, kLr2Products>(args, rshift, (unsigned)grid, stream)
-                                  : launch_ring<int32_t, kLr2Ahead, kLr2Products>(args, rshift, (unsigned)grid, stream);
+        if (variant_env == 2)                                        // the first ring form: __ldg gathers, 3 product stages (A/B)
+            return cfg.idx_bits == 64 ? launch_ring<int64_t, kLr2Ahead, 3, 0>(args, rshift, (unsigned)grid, stream)
+                                      : launch_ring<int32_t, kLr2Ahead, 3, 0>(args, rshift, (unsigned)grid, stream);
+        return cfg.idx_bits == 64 ? launch_ring<int64_t, kLr2Ahead, kLr2Products, kLr2Gather>(args, rshift, (unsigned)grid, stream)
+                                  : launch_ring<int32_t, kLr2Ahead, kLr2Products, kLr2Gather>(args, rshift, (unsigned)grid, stream);
     }
     if (cfg.idx_bits == 64)
         ell_longrow_kernel<int64_t><<<(unsigned)grid, kLrThreads, 0, stream>>>(args, rshift);

@@ -501,7 +501,7 @@ def test_long_row_kernel_is_bit_exact(lib, oracle, shape, bits):
     assert bits_equal(y[ok], w[ok])
 
 
-@pytest.mark.parametrize("variant", [1, 0])
+@pytest.mark.parametrize("variant", [1, 2, 0])
 @pytest.mark.parametrize("rshift", [0, 1, 2, 3, 4, 5])
 def test_long_row_kernel_every_rows_per_cta(lib, oracle, monkeypatch, variant, rshift):
     """Both forms of the long-row kernel (1: loader warps + a summing warp over an mbarrier ring, the

@@ -25,10 +25,20 @@ def main():
     ap.add_argument("--kernel", default="longrow", choices=["longrow", "thread", "auto"])
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--idx", type=int, default=32)
+    ap.add_argument("--banded", action="store_true", help="consecutive columns per row (coalesced gathers): the HBM-bound case")
     args = ap.parse_args()
     flags = {"longrow": E.KERNEL_LONGROW, "thread": E.KERNEL_THREAD | E.rows_per_thread(1), "auto": 0}[args.kernel]
     s = torch.cuda.current_stream()
-    A = E.EllMatrix.generate(E.GEN_RANDOM, (args.rows, args.cols, args.K), (0.0, 0.0), 42, args.idx, flags=flags)
+    if args.banded:
+        import numpy as np
+        rng = np.random.default_rng(1)
+        base = (np.arange(args.rows, dtype=np.int64) * 37) % args.cols
+        cols = ((base[:, None] + np.arange(args.K, dtype=np.int64)[None, :]) % args.cols).astype(np.int32 if args.idx == 32 else np.int64)
+        vals = rng.standard_normal(args.rows * args.K)
+        A = E.EllMatrix.upload(args.rows, args.cols, args.K, cols.reshape(-1), vals, flags | E.NO_PATTERN)
+        del cols, vals
+    else:
+        A = E.EllMatrix.generate(E.GEN_RANDOM, (args.rows, args.cols, args.K), (0.0, 0.0), 42, args.idx, flags=flags)
     x = torch.randn(args.cols, dtype=torch.float64, device="cuda")
     y = torch.zeros(args.rows, dtype=torch.float64, device="cuda")
     for _ in range(2):
@@ -44,7 +54,7 @@ def main():
     ms = ts[len(ts) // 2]
     idx_bytes = A.info().dev_idx_bits // 8
     nbytes = args.rows * args.K * (8 + idx_bytes) + 8 * args.rows + 8 * min(args.cols, args.rows * args.K)
-    print(json.dumps({"rows": args.rows, "K": args.K, "kernel": args.kernel, "ms": round(ms, 4),
+    print(json.dumps({"rows": args.rows, "K": args.K, "kernel": args.kernel, "banded": args.banded, "ms": round(ms, 4),
                       "gbs": round(nbytes / ms / 1e6, 1), "variant": os.environ.get("ELLSPMV_CUDA_LONGROW_VARIANT", ""),
                       "rshift": os.environ.get("ELLSPMV_CUDA_LONGROW_RSHIFT", "")}), flush=True)
     A.free()
