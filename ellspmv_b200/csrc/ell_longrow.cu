@@ -446,9 +446,18 @@ static cudaError_t launch_ring(const EllSpmvArgs &args, int rshift, unsigned gri
     return cudaGetLastError();
 }
 
+template <typename IdxT>
+static cudaError_t preload_ring()
+{
+    // an upload-time "launch" of zero rows (api.cu::warm_kernels): load the kernel's code and set its
+    // shared-memory limit now, so that the first real launch is a steady-state one
+    cudaFuncAttributes fa;
+    return cudaFuncGetAttributes(&fa, ell_longrow_ring_kernel<IdxT, kLr2Ahead, kLr2Products, kLr2Gather>);
+}
+
 cudaError_t launch_ell_longrow(const EllLaunchCfg &cfg, const EllSpmvArgs &args, cudaStream_t stream)
 {
-    if (args.num_rows <= 0) return cudaSuccess;
+    if (args.num_rows <= 0) return cfg.idx_bits == 64 ? preload_ring<int64_t>() : preload_ring<int32_t>();
     const int sms = cfg.num_sms > 0 ? cfg.num_sms : 148;
     // read per launch (a launch here moves megabytes): the parity tests walk every form and rows-per-CTA choice
     const char *ve = getenv("ELLSPMV_CUDA_LONGROW_VARIANT"), *re = getenv("ELLSPMV_CUDA_LONGROW_RSHIFT");
