@@ -25,6 +25,8 @@ scaling efficiency compares like with like.
              references and of y, launch, D2H of y inside the timing)
   cpu_baseline   the unmodified reference's ellgemv (oracle/_ref) on the box's
              host cores, same matrix -- a reported baseline, not the target
+  kernel_switch  (N = 1) the nnz-per-row switch: thread-per-row vs the long-row kernel vs KERNEL_AUTO on
+                 2^27-entry random matrices from 4M x 32 to 8192 x 16384, with an on-box bit-parity check
   other_configs  (N = 1) BASELINE configs 3 and 4 (ELL and CSR) and the matrices of
              configs 2 and 3 through the CSR comparison path, kernel only, each
              with its CPU baseline on a bounded sample
@@ -510,6 +512,48 @@ def other_configs(E, torch, dev, sptr, stream, reps: int, peak: float, with_cpu:
     return out
 
 
+def kernel_switch(E, torch, dev, sptr, stream, reps: int, peak: float):
+    """The north-star's nnz-per-row switch on the driver's box (N = 1): random ELL matrices of 2^27
+    entries from many short rows to few long ones (x small and L2-resident, as in tools/k_sweep.py),
+    through KERNEL_AUTO and through each kernel forced; the three results must agree bit for bit."""
+    out = []
+
+    def sync():
+        torch.cuda.synchronize()
+
+    for rows, K in ((4_194_304, 32), (131_072, 1024), (32_768, 4096), (8_192, 16_384)):
+        rec = {"rows": rows, "rowsize": K, "entries": rows * K}
+        try:
+            ncols = 1 << 20
+            gen = torch.Generator(device=dev).manual_seed(99)
+            x = torch.randn(ncols, dtype=torch.float64, device=dev, generator=gen)
+            ys = {}
+            for name, flags in (("auto", 0), ("thread_per_row", E.KERNEL_THREAD | E.rows_per_thread(1)),
+                                ("long_row", E.KERNEL_LONGROW)):
+                A = E.EllMatrix.generate(E.GEN_RANDOM, (rows, ncols, K), (0.0, 0.0), 42, 32, flags=flags)
+                info = A.info()
+                y = torch.zeros(rows, dtype=torch.float64, device=dev)
+
+                def fn():
+                    A.spmv_device(y, x, E.OVERWRITE, sptr)
+                for _ in range(3):
+                    fn()
+                ms = time_steps(torch, stream, fn, reps, sync) / reps
+                nbytes = rows * K * (8 + info.dev_idx_bits // 8) + 8 * rows + 8 * ncols
+                rec[name] = {"ms": round(ms, 4), "gbs": round(nbytes / ms * 1e-6, 1), "frac": round(nbytes / ms * 1e-6 / peak, 4)}
+                if name == "auto":
+                    rec["auto_picks"] = "long_row" if info.kernel == E.KERNEL_LONGROW else "thread_per_row"
+                ys[name] = y
+                A.free()
+            rec["bit_equal"] = bool(torch.equal(ys["auto"], ys["thread_per_row"]) and torch.equal(ys["auto"], ys["long_row"]))
+            del ys, x, y
+            torch.cuda.empty_cache()
+        except Exception as exc:
+            rec["error"] = repr(exc)
+        out.append(rec)
+    return out
+
+
 def parity_check(E, torch, dist, it, A, sptr, dev) -> dict:
     """x_k gathered on every rank -> plain single-GPU launch over this rank's rows -> compare with
     the slice the sharded step produces from its own (pushed / gathered) copy of x_k."""
@@ -764,6 +808,7 @@ def main_ours(args, rank: int, local_rank: int, world: int):
     if world == 1 and args.workload == "laplace2d" and not args.no_other_configs:
         line["other_configs"] = other_configs(E, torch, dev, sptr, stream, min(args.steps, 20), peak,
                                               with_cpu=not args.no_cpu_baseline)
+        line["kernel_switch"] = kernel_switch(E, torch, dev, sptr, stream, min(args.steps, 10), peak)
     if world > 1 and args.workload == "laplace2d" and not args.no_config5:
         try:
             line["config5"] = run_config5(E, torch, dist, rank, world, local_rank, dev, sptr, stream, peak, sampler,

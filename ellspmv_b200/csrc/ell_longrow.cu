@@ -24,6 +24,7 @@
 // of different rows overlap and the kernel is HBM-bound like the others.  ELLSPMV_CUDA_FMA cannot
 // contract here (the products are parked rounded): tolerance mode gets the same bits as the
 // exact mode.
+#include <stdint.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -197,6 +198,14 @@ __device__ __forceinline__ void lr_mbar_arrive(unsigned bar)
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
+// A per-thread constant the compiler must keep in its register: without this it re-derives staging
+// and product offsets from %tid at every use (a dozen integer instructions per entry in the loop).
+__device__ __forceinline__ int lr_keep(int v)
+{
+    asm volatile("mov.b32 %0, %0;" : "+r"(v));
+    return v;
+}
+
 template <int GM>
 __device__ __forceinline__ double lr_gather(const double *p)
 {
@@ -207,7 +216,7 @@ __device__ __forceinline__ double lr_gather(const double *p)
     return v;
 }
 
-template <typename IdxT, int kLr2Ahead, int kLr2NSP, int GM = 0>
+template <typename IdxT, int kLr2Ahead, int kLr2NSP, int GM = 0, bool VEC = false>
 __global__ void __launch_bounds__(kLr2Threads)
 ell_longrow_ring_kernel(const EllSpmvArgs a, int rshift)
 {
@@ -258,11 +267,52 @@ ell_longrow_ring_kernel(const EllSpmvArgs a, int rshift)
             const int64_t e0 = (row0 + r) * (int64_t)K + s0;
             vptr[j] = a.vals + e0;
             cptr[j] = cols + e0;
-            poff[j] = r * (T_row + 1) + s0;
+            poff[j] = lr_keep(r * (T_row + 1) + s0);
+        }
+        // VEC (every 32-slot piece of every row starts 16-byte aligned: K a multiple of 4, or of 2 with
+        // 64-bit indices): a full stage goes up in 16-byte copies that bypass L1 (cp.async.cg) -- the
+        // warp's four 32-slot pieces are 64 value chunks (two per lane) and 32 / 64 index chunks (one /
+        // two per lane): 3-4 LDGSTS per lane and stage instead of 8.  Lanes then read what OTHER lanes
+        // of their warp asked for, hence the __syncwarp after the wait below.
+        constexpr int kVC = 2, kCC = sizeof(IdxT) == 4 ? 1 : 2;               // 16-byte chunks per lane: values, indices
+        const double *vsrc[kVC] = {};
+        const IdxT *csrc[kCC] = {};
+        int vdst[kVC] = {}, cdst[kCC] = {};
+        if (VEC) {
+            auto piece = [&](int seg, int64_t &e0, int &d0) {                 // piece `seg` of this warp: first entry, staging offset
+                const int f = seg * kLanes + warp * 32;
+                e0 = (row0 + (f >> tshift)) * (int64_t)K + (f & (T_row - 1));
+                d0 = f;
+            };
+#pragma unroll
+            for (int h = 0; h < kVC; h++) {
+                const int c = lane + 32 * h;                                  // chunk c: piece c >> 4, two values at 2 * (c & 15)
+                int64_t e0; int d0;
+                piece(c >> 4, e0, d0);
+                vsrc[h] = a.vals + e0 + 2 * (c & 15);
+                vdst[h] = lr_keep(d0 + 2 * (c & 15));
+            }
+#pragma unroll
+            for (int h = 0; h < kCC; h++) {
+                const int c = lane + 32 * h;
+                constexpr int per = sizeof(IdxT) == 4 ? 8 : 16, n = 16 / (int)sizeof(IdxT);   // chunks per piece, indices per chunk
+                int64_t e0; int d0;
+                piece(c / per, e0, d0);
+                csrc[h] = cols + e0 + n * (c % per);
+                cdst[h] = lr_keep(d0 + n * (c % per));
+            }
         }
         int ti = 0, qi = 0;                                                   // next stage to ask for, its staging slot
         auto stage_in = [&]() {                                               // cp.async of stage ti (one group, maybe empty)
-            if (ti < ntiles) {
+            if (VEC && ti < nfull) {
+                const int64_t off = (int64_t)ti << tshift;
+#pragma unroll
+                for (int h = 0; h < kVC; h++)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(lr_smem_u32(sv + qi * kLr2Stage + vdst[h])), "l"(vsrc[h] + off) : "memory");
+#pragma unroll
+                for (int h = 0; h < kCC; h++)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(lr_smem_u32(sc + qi * kLr2Stage + cdst[h])), "l"(csrc[h] + off) : "memory");
+            } else if (ti < ntiles) {
                 const int64_t off = (int64_t)ti << tshift;
                 double *dv = sv + qi * kLr2Stage + tid;
                 IdxT *dc = sc + qi * kLr2Stage + tid;
@@ -324,6 +374,7 @@ ell_longrow_ring_kernel(const EllSpmvArgs a, int rshift)
 #pragma unroll
         for (int t = 0; t < kLr2Ahead; t++) stage_in();
         asm volatile("cp.async.wait_group %0;" ::"n"(kLr2Ahead - 2) : "memory");    // stages 0 and 1 have landed
+        if (VEC) __syncwarp();
         gather(xa);
         gather(xb);
         // iteration t: ask for stage t+4, wait until stage t+2 has landed, park stage t (its gathers
@@ -331,11 +382,13 @@ ell_longrow_ring_kernel(const EllSpmvArgs a, int rshift)
         for (int t = 0; t < ntiles; t += 2) {
             stage_in();
             asm volatile("cp.async.wait_group %0;" ::"n"(kLr2Ahead - 2) : "memory");
+            if (VEC) __syncwarp();
             park(xa);
             gather(xa);
             if (t + 1 < ntiles) {
                 stage_in();
                 asm volatile("cp.async.wait_group %0;" ::"n"(kLr2Ahead - 2) : "memory");
+                if (VEC) __syncwarp();
                 park(xb);
                 gather(xb);
             }
@@ -429,7 +482,7 @@ int longrow_ring_rshift(int64_t num_rows, int rowsize, int num_sms)
     return rshift;
 }
 
-template <typename IdxT, int AHEAD, int NSP, int GM = 0>
+template <typename IdxT, int AHEAD, int NSP, int GM = 0, bool VEC = false>
 static cudaError_t launch_ring(const EllSpmvArgs &args, int rshift, unsigned grid, cudaStream_t stream)
 {
     static bool attr_set[64] = {};
@@ -438,11 +491,11 @@ static cudaError_t launch_ring(const EllSpmvArgs &args, int rshift, unsigned gri
     if (ce != cudaSuccess) return ce;
     constexpr size_t smem = lr2_smem_bytes<IdxT, AHEAD, NSP>();
     if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-        ce = cudaFuncSetAttribute(ell_longrow_ring_kernel<IdxT, AHEAD, NSP, GM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        ce = cudaFuncSetAttribute(ell_longrow_ring_kernel<IdxT, AHEAD, NSP, GM, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (ce != cudaSuccess) return ce;
         if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
-    ell_longrow_ring_kernel<IdxT, AHEAD, NSP, GM><<<grid, kLr2Threads, smem, stream>>>(args, rshift);
+    ell_longrow_ring_kernel<IdxT, AHEAD, NSP, GM, VEC><<<grid, kLr2Threads, smem, stream>>>(args, rshift);
     return cudaGetLastError();
 }
 
@@ -452,7 +505,8 @@ static cudaError_t preload_ring()
     // an upload-time "launch" of zero rows (api.cu::warm_kernels): load the kernel's code and set its
     // shared-memory limit now, so that the first real launch is a steady-state one
     cudaFuncAttributes fa;
-    return cudaFuncGetAttributes(&fa, ell_longrow_ring_kernel<IdxT, kLr2Ahead, kLr2Products, kLr2Gather>);
+    cudaError_t ce = cudaFuncGetAttributes(&fa, ell_longrow_ring_kernel<IdxT, kLr2Ahead, kLr2Products, kLr2Gather, true>);
+    return ce != cudaSuccess ? ce : cudaFuncGetAttributes(&fa, ell_longrow_ring_kernel<IdxT, kLr2Ahead, kLr2Products, kLr2Gather, false>);
 }
 
 cudaError_t launch_ell_longrow(const EllLaunchCfg &cfg, const EllSpmvArgs &args, cudaStream_t stream)
@@ -471,6 +525,13 @@ cudaError_t launch_ell_longrow(const EllLaunchCfg &cfg, const EllSpmvArgs &args,
         if (variant_env == 2)                                        // the first ring form: __ldg gathers, 3 product stages (A/B)
             return cfg.idx_bits == 64 ? launch_ring<int64_t, kLr2Ahead, 3, 0>(args, rshift, (unsigned)grid, stream)
                                       : launch_ring<int32_t, kLr2Ahead, 3, 0>(args, rshift, (unsigned)grid, stream);
+        // 16-byte copies where every 32-slot piece of every row starts 16-byte aligned (variant 3: never)
+        const int idx_per16 = cfg.idx_bits == 64 ? 2 : 4;
+        const bool vec = variant_env != 3 && args.rowsize % idx_per16 == 0 &&
+                         ((reinterpret_cast<uintptr_t>(args.vals) | reinterpret_cast<uintptr_t>(args.cols)) & 15) == 0;
+        if (vec)
+            return cfg.idx_bits == 64 ? launch_ring<int64_t, kLr2Ahead, kLr2Products, kLr2Gather, true>(args, rshift, (unsigned)grid, stream)
+                                      : launch_ring<int32_t, kLr2Ahead, kLr2Products, kLr2Gather, true>(args, rshift, (unsigned)grid, stream);
         return cfg.idx_bits == 64 ? launch_ring<int64_t, kLr2Ahead, kLr2Products, kLr2Gather>(args, rshift, (unsigned)grid, stream)
                                   : launch_ring<int32_t, kLr2Ahead, kLr2Products, kLr2Gather>(args, rshift, (unsigned)grid, stream);
     }

@@ -501,24 +501,28 @@ def test_long_row_kernel_is_bit_exact(lib, oracle, shape, bits):
     assert bits_equal(y[ok], w[ok])
 
 
-@pytest.mark.parametrize("variant", [1, 2, 0])
+@pytest.mark.parametrize("variant", [1, 2, 3, 0])
 @pytest.mark.parametrize("rshift", [0, 1, 2, 3, 4, 5])
 def test_long_row_kernel_every_rows_per_cta(lib, oracle, monkeypatch, variant, rshift):
-    """Both forms of the long-row kernel (1: loader warps + a summing warp over an mbarrier ring, the
-    default; 0: the lock-step form) at every rows-per-CTA choice: ragged last CTA, K not a multiple of
+    """The forms of the long-row kernel (1: loader warps + a summing warp over an mbarrier ring, the
+    default; 3: the same without 16-byte copies; 2: the first ring build; 0: the lock-step form) at
+    every rows-per-CTA choice: ragged last CTA, K not a multiple of
     the stage, one tile, many tiles, 64-bit indices, per-row lengths through the CSR view."""
     monkeypatch.setenv("ELLSPMV_CUDA_LONGROW_VARIANT", str(variant))
     monkeypatch.setenv("ELLSPMV_CUDA_LONGROW_RSHIFT", str(rshift))
+    # K a multiple of 4 (of 2 with 64-bit indices kept wide): full stages go up in 16-byte copies
     for (nr, nc, K), dt in (((37, 5000, 3001), np.int32), ((70, 300, 64), np.int64), ((5, 20000, 10241), np.int32),
-                            ((1, 7, 1), np.int32), ((129, 4000, 1024), np.int64)):
+                            ((1, 7, 1), np.int32), ((129, 4000, 1024), np.int64), ((64, 3000, 2052), np.int32),
+                            ((96, 900, 1030), np.int32)):
         rng = np.random.default_rng(nr * 7 + K + rshift)
         ec, ea = rand_ell(rng, nr, nc, K, dt)
         x = rng.standard_normal(nc)
         y0 = rng.standard_normal(nr)
         want = y0.copy()
         oracle.ellgemv(nr, want, x, K, ec, ea)
-        A = E.EllMatrix.upload(nr, nc, K, ec, ea, E.KERNEL_LONGROW)
-        assert A.info().kernel == E.KERNEL_LONGROW
+        # 64-bit indices stay 64-bit on the device here (the kernel's int64 instantiation)
+        A = E.EllMatrix.upload(nr, nc, K, ec, ea, E.KERNEL_LONGROW | (E.WIDE_INDEX if dt == np.int64 else 0))
+        assert A.info().kernel == E.KERNEL_LONGROW and A.info().dev_idx_bits == ec.dtype.itemsize * 8
         y = y0.copy()
         A.spmv(y, x, 1, E.ACCUMULATE)
         A.free()
