@@ -72,7 +72,8 @@ int configure(ellspmv_cuda_matrix *A, unsigned flags)
     // that owns one row has 48 bytes in flight and the kernel is latency-bound once the offset
     // patterns (pattern.cu) take the index stream away: 0.649 / 0.603 / 0.608 ms on config 2
     // (profiles/r1_offset_patterns.md).  The boundary at K = 12 is interpolated.
-    if (R == 0) R = A->lay.rowsize <= 12 ? 2 : 1;
+    A->rpt_auto = R == 0;
+    if (R == 0) R = A->lay.rowsize <= 12 ? 2 : 1;          // K <= 12: revisited in build_patterns once the coverage is known
     if (R != 1 && R != 2 && R != 4) ELL_FAIL(EINVAL, "rows per thread must be 1, 2 or 4 (got %d)", R);
     int kernel = flags & ELLSPMV_CUDA_KERNEL_MASK;
     A->kernel_auto = kernel == ELLSPMV_CUDA_KERNEL_AUTO;
@@ -187,6 +188,51 @@ int finish_minmax(ellspmv_cuda_matrix *A)
     return 0;
 }
 
+// Re-lay a handle's matrix for another number of rows per thread (slice height 128 * R): a pure
+// permutation on the device, through two row-major staging buffers.  ENOMEM (the second copy does
+// not fit next to the first) leaves the handle untouched.
+int change_rows_per_thread(ellspmv_cuda_matrix *A, int R)
+{
+    EllLayout nl = A->lay;
+    nl.slice_rows = kBlockThreads * R;
+    nl.num_slices = (nl.num_rows + nl.slice_rows - 1) / nl.slice_rows;
+    const int64_t rows = A->lay.num_rows, K = A->lay.rowsize, n = nl.entries();
+    const int ib = A->dev_idx_bits / 8;
+    double *nv = nullptr, *sv = nullptr;
+    void *nc = nullptr, *sc = nullptr;
+    int64_t chunk_rows = (64LL << 20) / (K * (8 + ib));
+    if (chunk_rows < 1) chunk_rows = 1;
+    if (chunk_rows > rows) chunk_rows = rows;
+    auto cleanup = [&]() { cudaFree(nv); cudaFree(nc); cudaFree(sv); cudaFree(sc); };
+    cudaError_t ce = cudaMalloc(&nv, (size_t)n * 8);
+    if (ce == cudaSuccess) ce = cudaMalloc(&nc, (size_t)n * ib);
+    if (ce == cudaSuccess) ce = cudaMalloc(&sv, (size_t)chunk_rows * K * 8);
+    if (ce == cudaSuccess) ce = cudaMalloc(&sc, (size_t)chunk_rows * K * ib);
+    if (ce == cudaErrorMemoryAllocation) { cudaGetLastError(); cleanup(); return ENOMEM; }
+    // the tail of the last slice must hold harmless entries (col 0, 0.0)
+    if (ce == cudaSuccess) ce = cudaMemsetAsync(nv, 0, (size_t)n * 8, A->stream);
+    if (ce == cudaSuccess) ce = cudaMemsetAsync(nc, 0, (size_t)n * ib, A->stream);
+    for (int64_t r0 = 0; r0 < rows && ce == cudaSuccess; r0 += chunk_rows) {
+        const int64_t m = (rows - r0 < chunk_rows) ? rows - r0 : chunk_rows;
+        ce = unlayout_chunk(A->dev_idx_bits, A->dev_idx_bits, A->cols, A->vals, sc, sv, A->lay, r0, m, A->stream);
+        if (ce == cudaSuccess)
+            ce = relayout_chunk(A->dev_idx_bits, A->dev_idx_bits, sc, sv, nc, nv, nl, r0, m, A->d_minmax, A->stream);
+    }
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(A->stream);
+    if (ce != cudaSuccess) {
+        cleanup();
+        set_last_error("re-layout: %s", cudaGetErrorString(ce));
+        return cuda_to_errno(ce);
+    }
+    cudaFree(sv); cudaFree(sc);
+    A->device_bytes += (n - A->lay.entries()) * (8 + ib);
+    cudaFree(A->vals); cudaFree(A->cols);
+    A->vals = nv; A->cols = nc;
+    A->lay = nl;
+    A->cfg.rows_per_thread = R;
+    return 0;
+}
+
 // Offset patterns (pattern.cu): groups of 32 rows whose column indices are row + d[l] stop
 // reading the index stream.  On by default for the thread-per-row kernel;
 // ELLSPMV_CUDA_NO_PATTERN turns it off.
@@ -201,6 +247,23 @@ int build_patterns(ellspmv_cuda_matrix *A)
                                    (A->flags & ELLSPMV_CUDA_PATTERN_MASKS) ? 4 : 0,
                                    !(A->flags & ELLSPMV_CUDA_NO_PATTERN_LANES), A->stream);
     if (ce != cudaSuccess) { set_last_error("offset patterns: %s", cudaGetErrorString(ce)); return cuda_to_errno(ce); }
+    // AUTO rows per thread, second look.  Two rows per thread (K <= 12) pay only while the 64-row groups
+    // keep their patterns: a 3D grid puts a boundary row into most groups of 64 (7-point 224^3: 57 % of
+    // the rows patterned at two rows per thread, 100 % at one -- 0.195 vs 0.168 ms,
+    // profiles/r2_stencil_sweep.md).  Such a matrix is re-laid with one row per thread and searched again;
+    // a matrix without any pattern stays as it is (both layouts then run at the same speed).
+    if (A->rpt_auto && A->cfg.rows_per_thread == 2 && A->pat.any() && A->pat.covered * 10 < A->pat.groups * 9) {
+        const int e2 = change_rows_per_thread(A, 1);
+        if (e2 == 0) {
+            pattern_free(&A->pat);
+            ce = pattern_build(&A->pat, A->dev_idx_bits, A->cols, pv, A->lay, A->cfg.rows_per_thread, A->row_begin,
+                               (A->flags & ELLSPMV_CUDA_PATTERN_MASKS) ? 4 : 0,
+                               !(A->flags & ELLSPMV_CUDA_NO_PATTERN_LANES), A->stream);
+            if (ce != cudaSuccess) { set_last_error("offset patterns: %s", cudaGetErrorString(ce)); return cuda_to_errno(ce); }
+        } else if (e2 != ENOMEM) {
+            return e2;
+        }
+    }
     A->device_bytes += A->pat.bytes;
     if (A->pat.any()) warm_kernels(A);
     return 0;

@@ -39,6 +39,7 @@ struct ellspmv_cuda_matrix {
     int staged_mode = 0;                     // 0 direct gather, 1 staged on request, 2 staged chosen by the timed trial
     double tune_ms[2] = {0.0, 0.0};          // KERNEL_AUTO's trial at upload: direct, staged
     bool kernel_auto = false;                // the caller left the kernel choice to the library
+    bool rpt_auto = false;                   // ... and the rows per thread
     ellspmv::CbMatrix *cb = nullptr;         // column-blocked copy (ELLSPMV_CUDA_COLUMN_BLOCKED), optional
     ellspmv::SellMatrix *sell = nullptr;     // SELL-128-sigma copy without the trailing padding (ELLSPMV_CUDA_SKIP_PADDING), optional
     int64_t min_col = 0, max_col = -1;

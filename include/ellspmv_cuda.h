@@ -60,11 +60,12 @@ enum {
                                     /*   products): AUTO then never picks it, so the bits  */
                                     /*   do not depend on the row lengths                  */
     ELLSPMV_CUDA_KERNEL_LONGROW = 4,/* ELL: few, long rows -- a CTA per small group of rows  */
-                                    /*   on the reference's own row-major layout: all threads */
-                                    /*   stream and gather, the rounded products are parked   */
-                                    /*   in shared memory, one lane per row adds them in slot */
-                                    /*   order: bit-exact.  AUTO takes it for rowsize >= 64   */
-                                    /*   on matrices of at most 32768 rows  */
+                                    /*   on the reference's own row-major layout: eight loader */
+                                    /*   warps stream and gather (cp.async ring), the rounded  */
+                                    /*   products are parked in shared memory, one lane per    */
+                                    /*   row of a summing warp adds them in slot order:        */
+                                    /*   bit-exact.  AUTO takes it for rowsize >= 64 on        */
+                                    /*   matrices of at most 32768 rows       */
     CSRSPMV_CUDA_KERNEL_SELL   = 5, /* CSR only: SELL-128-sigma (sell.cu); AUTO takes it for    */
                                     /*   unbalanced rows                                        */
     ELLSPMV_CUDA_KERNEL_MASK   = 0xf,
