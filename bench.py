@@ -512,6 +512,43 @@ def other_configs(E, torch, dev, sptr, stream, reps: int, peak: float, with_cpu:
     return out
 
 
+def pcie_floor(torch, dev, xh, yh, x_touched: int, rows: int, e2e_ms: float) -> dict:
+    """The e2e call's own roofline: its H2D bytes (the x range + y) and D2H bytes (y) as plain
+    cudaMemcpyAsync between the same pinned host vectors and device buffers, alone and -- like the
+    pipelined call -- both directions at once on two streams.  Median of 3, CUDA events."""
+    dx = torch.empty(x_touched, dtype=torch.float64, device=dev)
+    dy = torch.empty(rows, dtype=torch.float64, device=dev)
+    up, down = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+
+    def run(do_up: bool, do_down: bool) -> float:
+        ts = []
+        for _ in range(4):
+            torch.cuda.synchronize()
+            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            e0.record(up)
+            down.wait_event(e0)
+            if do_up:
+                with torch.cuda.stream(up):
+                    dx.copy_(xh[:x_touched], non_blocking=True)
+                    dy.copy_(yh, non_blocking=True)
+            e1.record(up)
+            if do_down:
+                with torch.cuda.stream(down):
+                    yh.copy_(dy, non_blocking=True)
+            e2.record(down)
+            torch.cuda.synchronize()
+            ts.append(max(e0.elapsed_time(e1), e0.elapsed_time(e2)))
+        return sorted(ts[1:])[1]
+
+    h2d_bytes, d2h_bytes = (x_touched + rows) * 8, rows * 8
+    t_up, t_down, t_both = run(True, False), run(False, True), run(True, True)
+    return {"h2d_alone_gbs": round(h2d_bytes / t_up * 1e-6, 1), "d2h_alone_gbs": round(d2h_bytes / t_down * 1e-6, 1),
+            "both_directions_ms": round(t_both, 3), "h2d_gbs_while_both": round(h2d_bytes / t_both * 1e-6, 1),
+            "floor_ms_per_step": round(t_both, 3), "e2e_over_floor": round(e2e_ms / t_both, 3),
+            "how": "plain copies of the step's H2D (x range + y) and D2H (y) bytes between the same pinned vectors and "
+                   "device buffers, both directions at once on two streams, no kernel; median of 3"}
+
+
 def kernel_switch(E, torch, dev, sptr, stream, reps: int, peak: float):
     """The north-star's nnz-per-row switch on the driver's box (N = 1): random ELL matrices of 2^27
     entries from many short rows to few long ones (x small and L2-resident, as in tools/k_sweep.py),
@@ -800,6 +837,12 @@ def main_ours(args, rank: int, local_rank: int, world: int):
                           "vectors; x is uploaded on the column range the shard references only"}
     if numa is not None:
         line["e2e"]["host_thread_affinity"] = numa
+    # what bounds the call: the same bytes as plain copies between the same pinned vectors and the
+    # device (no kernel), upload and download at the same time on two streams -- the PCIe floor of a step
+    try:
+        line["e2e"]["pcie"] = pcie_floor(torch, dev, xh, yh, x_touched, rows, t_e2e / n_e2e * 1e3)
+    except Exception as exc:
+        line["e2e"]["pcie"] = {"error": repr(exc)}
     del xh, yh, xn, yn
     A.free()
     torch.cuda.empty_cache()
