@@ -13,9 +13,9 @@ LIB = os.path.join(ROOT, "ellspmv_b200", "lib", "libellspmv_cuda.so")
 WANT = [r"ell_thread_kernel<int, 2, 5, false, true, 0, 1, false, false>", r"ell_thread_kernel<int, 1, 27, false, true, 0, 1, false, false>",
         r"ell_thread_kernel<int, 4, 5, false, true, 0, 1, false, false>", r"ell_thread_kernel<int, 2, 5, false, true, 0, 1, false, true>",
         r"ell_thread_kernel<int, 2, 5, false, true, 0, 2, false, false>", r"ell_thread_kernel<int, 1, 0, false, true, 0, 0, true, false>",
-        r"ell_longrow_kernel<int>", r"sg_gather_kernel<int>", r"sg_sum_kernel", r"sell_spmv_kernel<int, false>", r"sell_long_kernel<int>",
+        r"ell_longrow_kernel<int>", r"ell_longrow_ring_kernel<int, 4, 2, 2, true>", r"ell_longrow_ring_kernel<int, 4, 2, 2, false>", r"sg_gather_kernel<int>", r"sg_sum_kernel", r"sell_spmv_kernel<int, false>", r"sell_long_kernel<int>",
         r"csr_stream_kernel<int, false>", r"ell_bulk_kernel<int, 1, false>", r"peer_sync_kernel", r"peer_barrier_kernel"]
-KEYS = re.compile(r"\b(LDG\.E[\w.]*|STG\.E[\w.]*|UBLKPF[\w.]*|UBLKCP[\w.]*|SYNCS[\w.]*|ATOMG[\w.]*|RED[\w.]*|MEMBAR[\w.]*|CCTL[\w.]*|"
+KEYS = re.compile(r"\b(LDGSTS[\w.]*|LDGDEPBAR|DEPBAR[\w.]*|LDG\.E[\w.]*|STG\.E[\w.]*|UBLKPF[\w.]*|UBLKCP[\w.]*|SYNCS[\w.]*|ATOMG[\w.]*|RED[\w.]*|MEMBAR[\w.]*|CCTL[\w.]*|"
                   r"WARPSYNC[\w.]*|BAR\.SYNC[\w.]*|SHFL[\w.]*|DMUL|DADD|DFMA|LDS[\w.]*|STS[\w.]*|NANOSLEEP|REDUX[\w.]*|MATCH[\w.]*)")
 
 out = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True).stdout
