@@ -500,12 +500,39 @@ int launch(ellspmv_cuda_matrix *A, double *y_dev, const double *x_dev, int beta,
 // rows come back, so the upload of chunk c+1 overlaps the download of chunk c on
 // the full-duplex PCIe link.  seconds = sum of the chunk kernels' device-event
 // times.
+//
+// Chunk sizes (profiles/r2_e2e_chunks.md): the call is the upload (x range + y) plus a fill (the
+// first chunk's upload, before anything runs) and a drain (the last chunk's download); every copy
+// costs ~13 us of set-up on top of its bytes (8 / 16 / 32 / 64 / 128 equal chunks: 21.98 / 21.91 /
+// 22.55 / 24.27 / 25.94 ms on BASELINE config 2).  So the rows are cut into 64 units and the chunks
+// ramp up and down: 1, 1, 2, 4, then 8 units each, then 4, 2, 1, 1 -- small at both ends (fill and
+// drain are 1/64 of the transfer), few copies in between.
 int spmv_pipelined(ellspmv_cuda_matrix *A, double *y, const double *x, int beta, double *seconds)
 {
-    const int64_t rows = A->lay.num_rows, ncols = A->num_columns, S = A->lay.slice_rows;
+    const int64_t rows = A->lay.num_rows, S = A->lay.slice_rows;
     const int64_t slices = A->lay.num_slices;
-    const int nchunks = (int)(slices < 32 ? slices : 32);
-    const int64_t chunk_slices = (slices + nchunks - 1) / nchunks;
+    std::vector<int> plan = {1, 1, 2, 4, 8, 8, 8, 8, 8, 8, 4, 2, 1, 1};      // chunk sizes in units
+    int64_t nunits = 64;
+    if (const char *env = getenv("ELLSPMV_CUDA_HOST_CHUNKS")) {              // experiments: that many equal chunks
+        const long long v = atoll(env);
+        if (v >= 1 && v <= 4096) { nunits = v; plan.assign((size_t)v, 1); }
+    }
+    if (const char *env = getenv("ELLSPMV_CUDA_HOST_PLAN")) {                // experiments: "1,1,2,4,..." chunk sizes in units
+        std::vector<int> p;
+        int64_t sum = 0;
+        for (const char *q = env; *q;) {
+            char *end = nullptr;
+            const long v = strtol(q, &end, 10);
+            if (end == q || v < 1 || v > 4096) { p.clear(); break; }
+            p.push_back((int)v); sum += v;
+            q = (*end == ',') ? end + 1 : end;
+            if (*end && *end != ',') { p.clear(); break; }
+        }
+        if (!p.empty() && sum <= 65536) { plan.swap(p); nunits = sum; }
+    }
+    if (slices < nunits) { nunits = slices; plan.assign((size_t)nunits, 1); }
+    const int nchunks = (int)plan.size();
+    const int64_t unit_slices = (slices + nunits - 1) / nunits;
     int err = ensure_events(A->events, 3 * (size_t)nchunks + 1);
     if (err) return err;
     if (!A->stream_out) ELL_CK(cudaStreamCreateWithFlags(&A->stream_out, cudaStreamNonBlocking));
@@ -513,18 +540,17 @@ int spmv_pipelined(ellspmv_cuda_matrix *A, double *y, const double *x, int beta,
     cudaStream_t s = A->stream, so = A->stream_out, si = A->stream_in;
     int64_t xlo, xhi;
     x_range(A, &xlo, &xhi);
-    (void)ncols;
-    // x goes up in pieces too: before chunk c runs, x is on the device up to the largest column
-    // the chunk references (one-off reduction per handle).  For a banded or stencil matrix the
-    // pieces interleave with the y chunks, so the first kernel starts after 1/32 of the upload
-    // instead of after all of x; for a scattered matrix the first chunk needs everything and this
-    // degenerates to "x first".
-    if ((int)A->chunk_max.size() != nchunks) {
+    // x goes up in pieces too: before a chunk runs, x is on the device up to the largest column
+    // the chunk references (one-off reduction per handle and unit size).  For a banded or stencil
+    // matrix the pieces interleave with the y chunks, so the first kernel starts after 1/64 of the
+    // upload instead of after all of x; for a scattered matrix the first chunk needs everything and
+    // this degenerates to "x first".
+    if ((int64_t)A->chunk_max.size() != nunits) {
         long long *d_cm = nullptr;
-        ELL_CK(cudaMalloc(&d_cm, (size_t)nchunks * 8));
-        std::vector<long long> cm((size_t)nchunks, -1);
-        cudaError_t ce = chunk_max_cols(A->dev_idx_bits, A->cols, A->lay, chunk_slices, nchunks, d_cm, s);
-        if (ce == cudaSuccess) ce = cudaMemcpyAsync(cm.data(), d_cm, (size_t)nchunks * 8, cudaMemcpyDeviceToHost, s);
+        ELL_CK(cudaMalloc(&d_cm, (size_t)nunits * 8));
+        std::vector<long long> cm((size_t)nunits, -1);
+        cudaError_t ce = chunk_max_cols(A->dev_idx_bits, A->cols, A->lay, unit_slices, (int)nunits, d_cm, s);
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(cm.data(), d_cm, (size_t)nunits * 8, cudaMemcpyDeviceToHost, s);
         if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
         cudaFree(d_cm);
         if (ce != cudaSuccess) ELL_FAIL(cuda_to_errno(ce), "chunk column ranges: %s", cudaGetErrorString(ce));
@@ -535,15 +561,19 @@ int spmv_pipelined(ellspmv_cuda_matrix *A, double *y, const double *x, int beta,
     // the uploads overwrite the handle's vectors: order them after whatever the compute stream still holds
     ELL_CK(cudaEventRecord(A->events[3 * (size_t)nchunks], s));
     ELL_CK(cudaStreamWaitEvent(si, A->events[3 * (size_t)nchunks], 0));
+    int64_t u0 = 0;
     for (int c = 0; c < nchunks; c++) {
-        const int64_t s0 = c * chunk_slices;
+        const int64_t nu = plan[(size_t)c];
+        const int64_t s0 = u0 * unit_slices;
         if (s0 >= slices) break;
-        const int64_t ns = (slices - s0 < chunk_slices) ? slices - s0 : chunk_slices;
+        const int64_t ns = (slices - s0 < nu * unit_slices) ? slices - s0 : nu * unit_slices;
         const int64_t r0 = s0 * S;
         const int64_t r1 = (r0 + ns * S < rows) ? r0 + ns * S : rows;
-        int64_t need = A->chunk_max[(size_t)c] + 1;
+        int64_t need = 0;
+        for (int64_t u = u0; u < u0 + nu && u < nunits; u++)
+            if (A->chunk_max[(size_t)u] + 1 > need) need = A->chunk_max[(size_t)u] + 1;
         if (A->d_ad && A->row_begin + r1 > need) need = A->row_begin + r1;      // ad[i] * x[global row i]
-        if (c == nchunks - 1 || need > xhi) need = xhi;
+        if (s0 + ns >= slices || need > xhi) need = xhi;
         if (need > up_hi) {
             ELL_CK(cudaMemcpyAsync(A->d_x + up_hi, x + up_hi, (size_t)(need - up_hi) * 8, cudaMemcpyDefault, si));
             up_hi = need;
@@ -557,6 +587,7 @@ int spmv_pipelined(ellspmv_cuda_matrix *A, double *y, const double *x, int beta,
         ELL_CK(cudaStreamWaitEvent(so, A->events[2 * c + 1], 0));
         ELL_CK(cudaMemcpyAsync(y + r0, A->d_y + r0, (size_t)(r1 - r0) * 8, cudaMemcpyDefault, so));
         used = c + 1;
+        u0 += nu;
     }
     ELL_CK(cudaStreamSynchronize(si));
     ELL_CK(cudaStreamSynchronize(s));
