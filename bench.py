@@ -495,6 +495,21 @@ def other_configs(E, torch, dev, sptr, stream, reps: int, peak: float, with_cpu:
                 rec["frac_algorithmic"] = round(rec["algorithmic_gbs"] / peak, 4)
                 rec["kernel"] = A.describe() if hasattr(A, "describe") else "csr"
                 rec["device_bytes"] = int(A.device_bytes())
+                if name == "laplace2d":
+                    # the CSR host-vector call (csrspmv_cuda_spmv, what INTEGRATION.md's csrspmv.c patch calls)
+                    xh = torch.ones(ncols, dtype=torch.float64).pin_memory()
+                    yh = torch.zeros(rows, dtype=torch.float64).pin_memory()
+                    A.spmv(yh.numpy(), xh.numpy(), 1, E.ACCUMULATE)
+                    ts = []
+                    for _ in range(3):
+                        t0 = time.perf_counter()
+                        A.spmv(yh.numpy(), xh.numpy(), 1, E.ACCUMULATE)
+                        ts.append(time.perf_counter() - t0)
+                    t = sorted(ts)[1]
+                    rec["e2e"] = {"ms_per_step": round(t * 1e3, 3), "value": round(2.0 * rows * K / t * 1e-9, 2), "unit": "GFLOP/s",
+                                  "h2d_bytes_per_step": (ncols + rows) * 8, "d2h_bytes_per_step": rows * 8,
+                                  "api": "csrspmv_cuda_spmv(A, y_host, x_host, 1, ACCUMULATE), pinned host vectors"}
+                    del xh, yh
             rec["mode"] = "accumulate (y <- y + A*x)"
             rec["traffic"] = recorded_traffic(f"{rec['config']}_{fmt}")
             A.free()

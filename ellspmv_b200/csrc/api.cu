@@ -604,6 +604,13 @@ int spmv_pipelined(ellspmv_cuda_matrix *A, double *y, const double *x, int beta,
     return 0;
 }
 
+// one launch on many rows through kernels that can run a range of slices: worth pipelining
+bool pipelined_host_call_applies(const ellspmv_cuda_matrix *A)
+{
+    return A->lay.num_rows >= (1 << 20) && A->lay.rowsize > 0 && A->num_columns > 0 && !A->cb && !A->sg && !A->sell &&
+           A->cfg.kernel != kKernelLongRow;
+}
+
 int new_handle(ellspmv_cuda_matrix **out, int idx_width_bits, int64_t global_rows,
                int64_t num_columns, int64_t rowsize, int64_t row_begin, int64_t row_end,
                int device, unsigned flags)
@@ -1237,8 +1244,7 @@ int ellspmv_cuda_spmv(
     DeviceGuard g(A->device);
     int err = ensure_vectors(A);
     if (err) return err;
-    if (repeat == 1 && mode != ELLSPMV_CUDA_ITERATE && rows >= (1 << 20) && A->lay.rowsize > 0 && ncols > 0 && !A->cb && !A->sg && !A->sell &&
-        A->cfg.kernel != kKernelLongRow)
+    if (repeat == 1 && mode != ELLSPMV_CUDA_ITERATE && pipelined_host_call_applies(A))
         return spmv_pipelined(A, y, x, mode == ELLSPMV_CUDA_ACCUMULATE ? 1 : 0, seconds);
     if ((err = ensure_events(A->events, (size_t)repeat + 1))) return err;
     cudaStream_t s = A->stream;
@@ -1602,6 +1608,17 @@ int csrspmv_cuda_spmv(
     if (repeat == 0) return 0;
     if (!A->shards.empty()) return csr_group_spmv(A, y, x, repeat, mode, seconds);
     DeviceGuard g(A->device);
+    if (repeat == 1 && A->ell && pipelined_host_call_applies(A->ell)) {
+        // one launch through the sliced-ELL view: the ELL host call's pipeline (upload, kernel and download
+        // of row chunks on three streams) on this handle's vectors, lent to the view for the call
+        ellspmv_cuda_matrix *V = A->ell;
+        V->d_x = A->d_x; V->d_y = A->d_y;
+        V->vec_len = A->num_rows > A->num_columns ? A->num_rows : A->num_columns;
+        const int e = spmv_pipelined(V, y, x, mode == ELLSPMV_CUDA_ACCUMULATE ? 1 : 0, seconds);
+        V->d_x = V->d_y = nullptr;
+        V->vec_len = 0;
+        return e;
+    }
     int err = ensure_events(A->events, (size_t)repeat + 1);
     if (err) return err;
     cudaStream_t s = A->stream;

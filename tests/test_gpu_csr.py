@@ -208,6 +208,45 @@ def test_auto_runs_balanced_rows_through_the_ell_view(lib, oracle, shape, bits, 
         B.free()
 
 
+@pytest.mark.parametrize("mode", [E.ACCUMULATE, E.OVERWRITE])
+def test_pipelined_host_call_through_the_ell_view(lib, oracle, mode):
+    """One launch on >= 2^20 balanced CSR rows with host vectors takes the ELL host call's pipeline
+    (row chunks uploaded, run and downloaded on three streams) on the view: same bits as csrgemv,
+    pageable and pinned vectors, with and without the separately stored diagonal, and the plain
+    path (repeat = 2) agrees."""
+    import torch
+    rng = np.random.default_rng(17)
+    nr = nc = (1 << 20) + 12345
+    rowptr, ec, ea = balanced_csr(rng, nr, nc, 6, np.int32, uniform=False)
+    x = rng.standard_normal(nc)
+    y0 = rng.standard_normal(nr)
+    want = y0.copy() if mode == E.ACCUMULATE else np.zeros(nr)
+    oracle.csrgemv(nr, want, x, rowptr, ec, ea)
+    A = E.CsrMatrix.upload(nr, nc, rowptr, ec, ea)
+    assert A.info().ell_view == 1
+    y = y0.copy()
+    secs = A.spmv(y, x, 1, mode)
+    assert bits_equal(y, want) and secs[0] > 0
+    xp = torch.from_numpy(x).pin_memory()
+    yp = torch.from_numpy(y0.copy()).pin_memory()
+    A.spmv(yp.numpy(), xp.numpy(), 1, mode)
+    assert bits_equal(yp.numpy(), want)
+    if mode == E.ACCUMULATE:
+        want2 = want.copy()
+        oracle.csrgemv(nr, want2, x, rowptr, ec, ea)
+        y = y0.copy()
+        A.spmv(y, x, 2, mode)                      # repeat = 2: the plain path, vectors resident
+        assert bits_equal(y, want2)
+    ad = rng.standard_normal(nr)
+    w = y0.copy() if mode == E.ACCUMULATE else np.zeros(nr)
+    oracle.csrgemvsd(nr, w, x, rowptr, ec, ea, ad)
+    A.set_diagonal(ad)
+    y = y0.copy()
+    A.spmv(y, x, 1, mode)
+    assert bits_equal(y, w)
+    A.free()
+
+
 def test_ell_view_padding_never_meets_x(lib, oracle):
     """Every row but one is short; x is +inf on every column that only the view's padded slots touch."""
     rng = np.random.default_rng(5)
